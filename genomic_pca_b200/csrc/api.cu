@@ -1,0 +1,432 @@
+// api.cu -- the C ABI (include/gpca.h): context, ingest, statistics, sketch entry points.
+// The PCA drivers (rfit, EigenSNP) live in drivers.cu.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <new>
+
+#include "host_qc.h"
+#include "kernels.cuh"
+
+#define CHECK_CTX(c) \
+  if (!(c)) return GPCA_ERR_INVALID;
+
+static int fail(gpca_ctx* c, int code, const std::string& msg) {
+  c->set_error(msg);
+  return code;
+}
+
+extern "C" const char* gpca_version(void) { return "genomic_pca_b200 0.1 (sm_100a)"; }
+
+extern "C" int gpca_init(gpca_ctx** out, int device) {
+  if (!out) return GPCA_ERR_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) return GPCA_ERR_NO_DEVICE;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return GPCA_ERR_NO_DEVICE;
+  if (prop.major != 10) return GPCA_ERR_NO_DEVICE;  // sm_100a binary only: no fallback of any kind
+  if (cudaSetDevice(device) != cudaSuccess) return GPCA_ERR_CUDA;
+  gpca_ctx* c = new (std::nothrow) gpca_ctx();
+  if (!c) return GPCA_ERR_OOM;
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete c;
+    return GPCA_ERR_CUDA;
+  }
+  const char* eng = getenv("GPCA_SKETCH_ENGINE");
+  if (eng) c->engine = atoi(eng);
+  *out = c;
+  return GPCA_OK;
+}
+
+extern "C" void gpca_destroy(gpca_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (auto& pr : c->pending_events) {
+    cudaEventDestroy(pr.first);
+    cudaEventDestroy(pr.second);
+  }
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+extern "C" const char* gpca_last_error(const gpca_ctx* c) { return c ? c->err.c_str() : "null context"; }
+extern "C" uint64_t gpca_launch_count(const gpca_ctx* c) { return c ? c->launches : 0; }
+extern "C" void gpca_reset_launch_count(gpca_ctx* c) {
+  if (c) c->launches = 0;
+}
+extern "C" int gpca_set_sketch_engine(gpca_ctx* c, int engine) {
+  CHECK_CTX(c);
+  if (engine != 0 && engine != 1) return fail(c, GPCA_ERR_INVALID, "engine must be 0 or 1");
+  c->engine = engine;
+  return GPCA_OK;
+}
+extern "C" int gpca_set_allreduce(gpca_ctx* c, gpca_allreduce_fn fn, void* user) {
+  CHECK_CTX(c);
+  c->allreduce = fn;
+  c->allreduce_user = user;
+  return GPCA_OK;
+}
+extern "C" int gpca_set_shard(gpca_ctx* c, uint64_t off, uint64_t total) {
+  CHECK_CTX(c);
+  c->shard_offset = off;
+  c->shard_total = total;
+  return GPCA_OK;
+}
+extern "C" uint64_t gpca_num_samples(const gpca_ctx* c) { return c ? c->N : 0; }
+extern "C" uint64_t gpca_num_snps(const gpca_ctx* c) { return c ? c->M : 0; }
+extern "C" uint64_t gpca_num_pca_snps(const gpca_ctx* c) { return c ? c->D : 0; }
+extern "C" int gpca_synchronize(gpca_ctx* c) {
+  CHECK_CTX(c);
+  GPCA_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return GPCA_OK;
+}
+
+static void reset_loaded(gpca_ctx* c) {
+  c->have_counts = false;
+  c->h_counts.clear();
+  c->D = 0;
+  c->pca_idx.clear();
+  c->Gs = PackedMat();
+  c->Gt = PackedMat();
+  c->gs_store.release();
+  c->gt_store.release();
+  c->any_missing = false;
+}
+
+// ---- ingest ------------------------------------------------------------------------------
+static int alloc_raw(gpca_ctx* c, uint64_t N, uint64_t M) {
+  reset_loaded(c);
+  c->N = N;
+  c->M = M;
+  c->raw_pitch = round_up((N + 3) / 4, 16);
+  c->raw.release();
+  GPCA_CUDA_TRY(c, c->raw.alloc(std::max<size_t>(c->raw_pitch * M, 16)));
+  return GPCA_OK;
+}
+
+extern "C" int gpca_load_bed(gpca_ctx* c, const uint8_t* host_payload, uint64_t n_in, uint64_t n_snps,
+                             const int64_t* keep, uint64_t n_keep) {
+  CHECK_CTX(c);
+  GPCA_CUDA_TRY(c, cudaSetDevice(c->device));
+  if (!host_payload && n_snps) return fail(c, GPCA_ERR_INVALID, "null payload");
+  if (n_in == 0) return fail(c, GPCA_ERR_INVALID, "no samples");
+  const uint64_t N = keep ? n_keep : n_in;
+  if (N == 0) return fail(c, GPCA_ERR_INVALID, "No samples passed QC.");  // prepare.rs:1010
+  if (keep)
+    for (uint64_t i = 0; i < n_keep; ++i)
+      if (keep[i] < 0 || (uint64_t)keep[i] >= n_in || (i && keep[i] <= keep[i - 1]))
+        return fail(c, GPCA_ERR_INVALID, "keep_samples must be increasing indices into the FAM order");
+  c->vcf_mode = false;
+  GPCA_TRY(alloc_raw(c, N, n_snps));
+  DevBuf<int64_t> d_keep;
+  if (keep) {
+    GPCA_CUDA_TRY(c, d_keep.alloc(n_keep));
+    GPCA_CUDA_TRY(c, cudaMemcpyAsync(d_keep.p, keep, n_keep * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+  }
+  const size_t in_pitch = (n_in + 3) / 4;
+  // stream the payload through two staging buffers (rows per chunk sized to ~256 MiB)
+  uint64_t rows_per_chunk = std::max<uint64_t>(1, (256ull << 20) / std::max<size_t>(in_pitch, 1));
+  rows_per_chunk = std::min<uint64_t>(rows_per_chunk, std::max<uint64_t>(n_snps, 1));
+  DevBuf<uint8_t> stage[2];
+  cudaEvent_t done[2] = {nullptr, nullptr};
+  for (int i = 0; i < 2; ++i) {
+    GPCA_CUDA_TRY(c, stage[i].alloc(rows_per_chunk * in_pitch + 16));
+    GPCA_CUDA_TRY(c, cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+  }
+  int rc = GPCA_OK;
+  int buf = 0;
+  for (uint64_t r0 = 0; r0 < n_snps && rc == GPCA_OK; r0 += rows_per_chunk, buf ^= 1) {
+    const uint64_t nr = std::min<uint64_t>(rows_per_chunk, n_snps - r0);
+    cudaError_t e = cudaEventSynchronize(done[buf]);  // previous use of this staging buffer finished
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(stage[buf].p, host_payload + r0 * in_pitch, nr * in_pitch, cudaMemcpyHostToDevice, c->stream);
+    if (e != cudaSuccess) {
+      rc = fail(c, GPCA_ERR_CUDA, std::string("load_bed H2D: ") + cudaGetErrorString(e));
+      break;
+    }
+    rc = launch_repitch_gather(c, stage[buf].p, in_pitch, n_in, keep ? d_keep.p : nullptr, N, nr,
+                               c->raw.p + r0 * c->raw_pitch, c->raw_pitch);
+    cudaEventRecord(done[buf], c->stream);
+  }
+  cudaStreamSynchronize(c->stream);
+  for (int i = 0; i < 2; ++i) cudaEventDestroy(done[i]);
+  return rc;
+}
+
+extern "C" int gpca_load_bed_device(gpca_ctx* c, const uint8_t* dev_payload, uint64_t n_samples, uint64_t n_snps) {
+  CHECK_CTX(c);
+  GPCA_CUDA_TRY(c, cudaSetDevice(c->device));
+  if (n_samples == 0) return fail(c, GPCA_ERR_INVALID, "no samples");
+  c->vcf_mode = false;
+  GPCA_TRY(alloc_raw(c, n_samples, n_snps));
+  GPCA_TRY(launch_repitch_gather(c, dev_payload, (n_samples + 3) / 4, n_samples, nullptr, n_samples, n_snps, c->raw.p,
+                                 c->raw_pitch));
+  return GPCA_OK;
+}
+
+extern "C" int gpca_load_u8_variant_major(gpca_ctx* c, const uint8_t* host_dosage, uint64_t n_samples,
+                                          uint64_t n_variants) {
+  CHECK_CTX(c);
+  GPCA_CUDA_TRY(c, cudaSetDevice(c->device));
+  if (n_samples == 0) return fail(c, GPCA_ERR_INVALID, "No samples available to build matrix.");  // vcf.rs:325
+  if (n_variants == 0) return fail(c, GPCA_ERR_INVALID, "No variants available to build matrix.");  // vcf.rs:322
+  GPCA_TRY(alloc_raw(c, n_samples, n_variants));
+  c->vcf_mode = true;
+  uint64_t rows_per_chunk = std::max<uint64_t>(1, (256ull << 20) / n_samples);
+  rows_per_chunk = std::min<uint64_t>(rows_per_chunk, n_variants);
+  DevBuf<uint8_t> stage;
+  GPCA_CUDA_TRY(c, stage.alloc(rows_per_chunk * n_samples));
+  for (uint64_t r0 = 0; r0 < n_variants; r0 += rows_per_chunk) {
+    const uint64_t nr = std::min<uint64_t>(rows_per_chunk, n_variants - r0);
+    GPCA_CUDA_TRY(c, cudaMemcpyAsync(stage.p, host_dosage + r0 * n_samples, nr * n_samples, cudaMemcpyHostToDevice,
+                                     c->stream));
+    GPCA_TRY(launch_u8_to_plink(c, stage.p, n_samples, nr, c->raw.p + r0 * c->raw_pitch, c->raw_pitch));
+    GPCA_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  }
+  return GPCA_OK;
+}
+
+// ---- statistics ----------------------------------------------------------------------------
+static int ensure_counts(gpca_ctx* c) {
+  if (c->have_counts) return GPCA_OK;
+  if (!c->raw.p) return fail(c, GPCA_ERR_INVALID, "no genotype payload loaded (or it was released)");
+  const uint64_t M = c->M;
+  DevBuf<uint4> d_cnt;
+  GPCA_CUDA_TRY(c, d_cnt.alloc(std::max<uint64_t>(M, 1)));
+  GPCA_TRY(launch_bed_counts(c, c->raw.p, c->raw_pitch, M, d_cnt.p));
+  std::vector<uint4> h(M);
+  GPCA_CUDA_TRY(c, cudaMemcpyAsync(h.data(), d_cnt.p, M * sizeof(uint4), cudaMemcpyDeviceToHost, c->stream));
+  GPCA_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  const uint32_t pad = (uint32_t)(c->raw_pitch * 4 - c->N);  // pad fields were written as 01
+  c->h_counts.resize(M * 4);
+  for (uint64_t j = 0; j < M; ++j) {
+    const uint32_t miss = h[j].x - pad, het = h[j].y, d0 = h[j].z;
+    const uint32_t nv = (uint32_t)c->N - miss;
+    c->h_counts[4 * j + 0] = nv;
+    c->h_counts[4 * j + 1] = d0;             // code 11 -> dosage 0
+    c->h_counts[4 * j + 2] = het;            // code 10 -> dosage 1
+    c->h_counts[4 * j + 3] = nv - d0 - het;  // code 00 -> dosage 2
+  }
+  c->have_counts = true;
+  return GPCA_OK;
+}
+
+extern "C" int gpca_snp_counts(gpca_ctx* c, uint32_t* n_valid, uint32_t* n0, uint32_t* n1, uint32_t* n2) {
+  CHECK_CTX(c);
+  GPCA_TRY(ensure_counts(c));
+  for (uint64_t j = 0; j < c->M; ++j) {
+    if (n_valid) n_valid[j] = c->h_counts[4 * j + 0];
+    if (n0) n0[j] = c->h_counts[4 * j + 1];
+    if (n1) n1[j] = c->h_counts[4 * j + 2];
+    if (n2) n2[j] = c->h_counts[4 * j + 3];
+  }
+  return GPCA_OK;
+}
+
+extern "C" int gpca_snp_qc(gpca_ctx* c, const gpca_qc_cfg* cfg, uint8_t* keep, float* mean, float* sd,
+                           uint8_t* fail_code) {
+  CHECK_CTX(c);
+  if (!cfg || !keep) return fail(c, GPCA_ERR_INVALID, "cfg/keep null");
+  GPCA_TRY(ensure_counts(c));
+  host_snp_qc(c->N, c->M, c->h_counts.data(), *cfg, keep, mean, sd, fail_code);
+  return GPCA_OK;
+}
+
+extern "C" int gpca_vcf_maf_filter(gpca_ctx* c, double maf_threshold, uint8_t* keep, float* mean, float* sd) {
+  CHECK_CTX(c);
+  if (!keep) return fail(c, GPCA_ERR_INVALID, "keep null");
+  GPCA_TRY(ensure_counts(c));
+  host_vcf_maf(c->N, c->M, c->h_counts.data(), maf_threshold, keep, mean, sd);
+  return GPCA_OK;
+}
+
+// ---- PCA SNP set -----------------------------------------------------------------------------
+extern "C" int gpca_set_pca_snps(gpca_ctx* c, const uint64_t* snp_idx, uint64_t D, const float* mean,
+                                 const float* sd) {
+  CHECK_CTX(c);
+  GPCA_CUDA_TRY(c, cudaSetDevice(c->device));
+  if (!c->raw.p) return fail(c, GPCA_ERR_INVALID, "no genotype payload loaded (or it was released)");
+  if (D == 0) return fail(c, GPCA_ERR_INVALID, "No SNPs passed all QC filters.");  // prepare.rs:1020
+  if (!snp_idx || !mean || !sd) return fail(c, GPCA_ERR_INVALID, "null argument");
+  for (uint64_t i = 0; i < D; ++i)
+    if (snp_idx[i] >= c->M || (i && snp_idx[i] <= snp_idx[i - 1]))
+      return fail(c, GPCA_ERR_INVALID, "snp_idx must be strictly increasing and < num_snps");
+  GPCA_TRY(ensure_counts(c));
+  c->D = D;
+  c->pca_idx.assign(snp_idx, snp_idx + D);
+  c->h_mean.assign(mean, mean + D);
+  c->h_sd.assign(sd, sd + D);
+  std::vector<float> inv(D), muinv(D);
+  uint64_t nmiss = 0;
+  for (uint64_t i = 0; i < D; ++i) {
+    // same f32 expressions as prepare.rs:1948-1949 (recip, -mean*recip); sd < 1e-9 -> the row standardises to 0
+    if (std::fabs(sd[i]) < 1e-9f) {
+      inv[i] = 0.f;
+      muinv[i] = 0.f;
+    } else {
+      const float r = 1.0f / sd[i];
+      inv[i] = r;
+      muinv[i] = mean[i] * r;
+    }
+    nmiss += c->N - c->h_counts[4 * snp_idx[i]];
+  }
+  c->any_missing = nmiss > 0;
+  GPCA_CUDA_TRY(c, c->d_mean.alloc(D));
+  GPCA_CUDA_TRY(c, c->d_sd.alloc(D));
+  GPCA_CUDA_TRY(c, c->d_inv_sd.alloc(D));
+  GPCA_CUDA_TRY(c, c->d_mu_inv_sd.alloc(D));
+  GPCA_CUDA_TRY(c, cudaMemcpyAsync(c->d_mean.p, mean, D * 4, cudaMemcpyHostToDevice, c->stream));
+  GPCA_CUDA_TRY(c, cudaMemcpyAsync(c->d_sd.p, sd, D * 4, cudaMemcpyHostToDevice, c->stream));
+  GPCA_CUDA_TRY(c, cudaMemcpyAsync(c->d_inv_sd.p, inv.data(), D * 4, cudaMemcpyHostToDevice, c->stream));
+  GPCA_CUDA_TRY(c, cudaMemcpyAsync(c->d_mu_inv_sd.p, muinv.data(), D * 4, cudaMemcpyHostToDevice, c->stream));
+  DevBuf<uint64_t> d_idx;
+  GPCA_CUDA_TRY(c, d_idx.alloc(D));
+  GPCA_CUDA_TRY(c, cudaMemcpyAsync(d_idx.p, snp_idx, D * 8, cudaMemcpyHostToDevice, c->stream));
+
+  c->gs_store.release();
+  c->gt_store.release();
+  c->Gs.rows = D;
+  c->Gs.cols = c->N;
+  c->Gs.pitch = round_up((c->N + 3) / 4, 128);
+  c->Gt.rows = c->N;
+  c->Gt.cols = D;
+  c->Gt.pitch = round_up((D + 3) / 4, 128);
+  GPCA_CUDA_TRY(c, c->gs_store.alloc(c->Gs.pitch * D));
+  c->Gs.p = c->gs_store.p;
+  GPCA_TRY(launch_build_gs(c, c->raw.p, c->raw_pitch, d_idx.p, c->Gs));
+  GPCA_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  // the PLINK-coded staging copy is only needed again for a different SNP selection; release it when large
+  if (c->raw_pitch * c->M > (4ull << 30)) c->raw.release();
+  GPCA_CUDA_TRY(c, c->gt_store.alloc(c->Gt.pitch * c->N));
+  c->Gt.p = c->gt_store.p;
+  GPCA_TRY(launch_transpose(c, c->Gs, c->Gt));
+  GPCA_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return GPCA_OK;
+}
+
+// ---- accessor parity ---------------------------------------------------------------------------
+extern "C" int gpca_get_standardized_block(gpca_ctx* c, const uint64_t* ids, uint64_t n_ids, const uint64_t* samp,
+                                           uint64_t n_samp, float* host_out) {
+  CHECK_CTX(c);
+  GPCA_CUDA_TRY(c, cudaSetDevice(c->device));
+  if (c->D == 0) return fail(c, GPCA_ERR_INVALID, "gpca_set_pca_snps has not been called");
+  if (n_ids == 0 || n_samp == 0) return GPCA_OK;  // prepare.rs:1848 -> empty array
+  if (!ids || !host_out) return fail(c, GPCA_ERR_INVALID, "null argument");
+  for (uint64_t i = 0; i < n_ids; ++i)
+    if (ids[i] >= c->D) return fail(c, GPCA_ERR_INVALID, "PcaSnpId out of range");
+  if (samp)
+    for (uint64_t j = 0; j < n_samp; ++j)
+      if (samp[j] >= c->N) return fail(c, GPCA_ERR_INVALID, "QcSampleId out of range");
+  if (!samp && n_samp != c->N) return fail(c, GPCA_ERR_INVALID, "sample list null but n_samp != num_samples");
+  DevBuf<uint64_t> d_ids, d_samp;
+  DevBuf<float> d_out;
+  DevBuf<int> d_flag;
+  GPCA_CUDA_TRY(c, d_ids.alloc(n_ids));
+  GPCA_CUDA_TRY(c, d_out.alloc(n_ids * n_samp));
+  GPCA_CUDA_TRY(c, d_flag.alloc(1));
+  GPCA_CUDA_TRY(c, cudaMemcpyAsync(d_ids.p, ids, n_ids * 8, cudaMemcpyHostToDevice, c->stream));
+  if (samp) {
+    GPCA_CUDA_TRY(c, d_samp.alloc(n_samp));
+    GPCA_CUDA_TRY(c, cudaMemcpyAsync(d_samp.p, samp, n_samp * 8, cudaMemcpyHostToDevice, c->stream));
+  }
+  GPCA_CUDA_TRY(c, cudaMemsetAsync(d_flag.p, 0, sizeof(int), c->stream));
+  GPCA_TRY(launch_std_block(c, c->Gs, c->d_mean.p, c->d_sd.p, d_ids.p, n_ids, samp ? d_samp.p : nullptr, n_samp,
+                            d_out.p, d_flag.p));
+  int flag = 0;
+  GPCA_CUDA_TRY(c, cudaMemcpyAsync(&flag, d_flag.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  GPCA_CUDA_TRY(c, cudaMemcpyAsync(host_out, d_out.p, n_ids * n_samp * 4, cudaMemcpyDeviceToHost, c->stream));
+  GPCA_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  if (flag) return fail(c, GPCA_ERR_MISSING, "Unexpected missing genotype in SnpBlockData (prepare.rs:1910)");
+  return GPCA_OK;
+}
+
+// ---- sketch passes ---------------------------------------------------------------------------------
+static int timed_sketch(gpca_ctx* c, const SketchProblem& p) {
+  cudaEvent_t e0, e1;
+  GPCA_CUDA_TRY(c, cudaEventCreate(&e0));
+  GPCA_CUDA_TRY(c, cudaEventCreate(&e1));
+  GPCA_CUDA_TRY(c, cudaEventRecord(e0, c->stream));
+  const int rc = launch_sketch(c, p);
+  GPCA_CUDA_TRY(c, cudaEventRecord(e1, c->stream));
+  c->pending_events.push_back({e0, e1});
+  c->sk_bytes += (double)p.G.rows * (double)((p.G.cols + 3) / 4);
+  c->sk_passes += 1;
+  return rc;
+}
+
+int sketch_snp_side(gpca_ctx* c, const float* dev_in, float* dev_out, uint32_t l, uint32_t ld_in, uint32_t ld_out) {
+  SketchProblem p;
+  p.G = c->Gs;
+  p.Bin = dev_in;
+  p.l = l;
+  p.ld = ld_in;
+  p.f = nullptr;
+  p.e = nullptr;
+  p.a = c->d_inv_sd.p;
+  p.b = c->d_mu_inv_sd.p;
+  p.out = dev_out;
+  p.ldo = ld_out;
+  return timed_sketch(c, p);
+}
+
+int sketch_sample_side(gpca_ctx* c, const float* dev_in, float* dev_out, uint32_t l, uint32_t ld_in, uint32_t ld_out) {
+  SketchProblem p;
+  p.G = c->Gt;
+  p.Bin = dev_in;
+  p.l = l;
+  p.ld = ld_in;
+  p.f = c->d_inv_sd.p;
+  p.e = c->d_mu_inv_sd.p;
+  p.a = nullptr;
+  p.b = nullptr;
+  p.out = dev_out;
+  p.ldo = ld_out;
+  GPCA_TRY(timed_sketch(c, p));
+  if (c->allreduce) {
+    if (ld_out != l) return fail(c, GPCA_ERR_INVALID, "sharded sample-side sketch needs ld == l");
+    if (c->allreduce(dev_out, c->N * (uint64_t)l, 0, (void*)c->stream, c->allreduce_user) != 0)
+      return fail(c, GPCA_ERR_CUDA, "allreduce hook failed");
+  }
+  return GPCA_OK;
+}
+
+extern "C" int gpca_sketch_snp_side(gpca_ctx* c, const float* dev_in, float* dev_out, uint32_t l, uint32_t ld) {
+  CHECK_CTX(c);
+  GPCA_CUDA_TRY(c, cudaSetDevice(c->device));
+  if (c->D == 0) return fail(c, GPCA_ERR_INVALID, "gpca_set_pca_snps has not been called");
+  if (l == 0 || l > 64 || ld < l) return fail(c, GPCA_ERR_INVALID, "need 1 <= l <= 64 and ld >= l");
+  return sketch_snp_side(c, dev_in, dev_out, l, ld, ld);
+}
+
+extern "C" int gpca_sketch_sample_side(gpca_ctx* c, const float* dev_in, float* dev_out, uint32_t l, uint32_t ld) {
+  CHECK_CTX(c);
+  GPCA_CUDA_TRY(c, cudaSetDevice(c->device));
+  if (c->D == 0) return fail(c, GPCA_ERR_INVALID, "gpca_set_pca_snps has not been called");
+  if (l == 0 || l > 64 || ld < l) return fail(c, GPCA_ERR_INVALID, "need 1 <= l <= 64 and ld >= l");
+  return sketch_sample_side(c, dev_in, dev_out, l, ld, ld);
+}
+
+extern "C" int gpca_sketch_stats(gpca_ctx* c, double* ms_total, double* bytes_total, uint64_t* n_passes, int reset) {
+  CHECK_CTX(c);
+  GPCA_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  for (auto& pr : c->pending_events) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) c->sk_ms += ms;
+    cudaEventDestroy(pr.first);
+    cudaEventDestroy(pr.second);
+  }
+  c->pending_events.clear();
+  if (ms_total) *ms_total = c->sk_ms;
+  if (bytes_total) *bytes_total = c->sk_bytes;
+  if (n_passes) *n_passes = c->sk_passes;
+  if (reset) {
+    c->sk_ms = 0;
+    c->sk_bytes = 0;
+    c->sk_passes = 0;
+  }
+  return GPCA_OK;
+}

@@ -1,0 +1,135 @@
+// common.cuh -- context, error plumbing and small device helpers shared by all translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/gpca.h"
+
+#define GPCA_CUDA_TRY(ctx, expr)                                                         \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      (ctx)->set_error(std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" +       \
+                       __FILE__ + ":" + std::to_string(__LINE__) + ")");                 \
+      return (_e == cudaErrorMemoryAllocation) ? GPCA_ERR_OOM : GPCA_ERR_CUDA;           \
+    }                                                                                    \
+  } while (0)
+
+#define GPCA_TRY(expr)          \
+  do {                          \
+    int _rc = (expr);           \
+    if (_rc != GPCA_OK) return _rc; \
+  } while (0)
+
+// Owning device buffer (raw cudaMalloc; freed in dtor).
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  cudaError_t alloc(size_t count) {
+    if (count <= n && p) return cudaSuccess;
+    release();
+    if (count == 0) return cudaSuccess;
+    cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+    if (e == cudaSuccess) n = count;
+    return e;
+  }
+};
+
+static inline size_t round_up(size_t x, size_t m) { return (x + m - 1) / m * m; }
+
+// Resident packed genotype matrix, dosage-coded 2-bit fields (0,1,2 = A1 dosage, 3 = missing),
+// field k of a row in bits 2*(k%4) of byte k/4, pad fields = 0.  pitch is a multiple of 128 B.
+struct PackedMat {
+  uint8_t* p = nullptr;
+  size_t pitch = 0;      // bytes per row
+  uint64_t rows = 0;     // logical rows
+  uint64_t cols = 0;     // logical 2-bit fields per row
+};
+
+struct gpca_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  uint64_t launches = 0;
+  int engine = 1;
+
+  // collective hook / shard
+  gpca_allreduce_fn allreduce = nullptr;
+  void* allreduce_user = nullptr;
+  uint64_t shard_offset = 0, shard_total = 0;
+
+  // loaded (pre-QC) data, PLINK-coded, kept samples only, pad fields = 01
+  uint64_t N = 0, M = 0;
+  DevBuf<uint8_t> raw;
+  size_t raw_pitch = 0;
+  bool have_counts = false;
+  std::vector<uint32_t> h_counts;  // [M][4] = n_valid, n0, n1, n2
+  bool vcf_mode = false;
+
+  // PCA SNP set + resident copies
+  uint64_t D = 0;
+  std::vector<uint64_t> pca_idx;
+  std::vector<float> h_mean, h_sd;
+  DevBuf<float> d_mean, d_sd;           // [D]
+  DevBuf<float> d_inv_sd, d_mu_inv_sd;  // [D]  1/sd (0 if sd<1e-9) and mean/sd
+  DevBuf<uint8_t> gs_store, gt_store;
+  PackedMat Gs, Gt;                     // [D x N] and [N x D]
+  bool any_missing = false;
+
+  // sketch statistics
+  double sk_ms = 0, sk_bytes = 0;
+  uint64_t sk_passes = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_events;
+
+  // scratch
+  DevBuf<float> ws_bprep;      // prepared B' operand
+  DevBuf<float> ws_partial;    // split-K partials
+  DevBuf<float> ws_cvec;       // epilogue vector(s)
+  DevBuf<double> ws_f64;       // gram partials
+  DevBuf<double> ws_cpart;     // column-sum partials
+  DevBuf<double> ws_small;     // l x l matrices: G, evals, evecs, T
+  DevBuf<uint8_t> ws_bytes;
+
+  void set_error(const std::string& s) { err = s; }
+};
+
+// ---- device helpers -------------------------------------------------------------------
+__device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ unsigned warp_sum_u32(unsigned v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}

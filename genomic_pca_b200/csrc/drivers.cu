@@ -1,0 +1,172 @@
+// drivers.cu -- PCA drivers built from the sketch passes:
+//   gpca_rfit     replaces pca_runner::run_genomic_pca = PCA::rfit + PCA::transform (src/main.rs:598-679)
+//   gpca_eigensnp replaces EigenSNPCoreAlgorithm::compute_pca (src/main.rs:359-366)
+// The arithmetic of both lives in the external efficient_pca crate (parity unpinned); the stage
+// order implemented here is the one restated in oracle/pca.py, which the tests check it against.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <random>
+
+#include "kernels.cuh"
+
+int sketch_snp_side(gpca_ctx* c, const float* dev_in, float* dev_out, uint32_t l, uint32_t ld_in, uint32_t ld_out);
+int sketch_sample_side(gpca_ctx* c, const float* dev_in, float* dev_out, uint32_t l, uint32_t ld_in, uint32_t ld_out);
+
+static int fail(gpca_ctx* c, int code, const std::string& msg) {
+  c->set_error(msg);
+  return code;
+}
+
+namespace {
+constexpr uint32_t STREAM_RFIT_OMEGA = 1;
+
+struct Small {  // f64 scratch for l x l work, all on device
+  double *G, *evals, *evecs, *T;
+};
+
+int get_small(gpca_ctx* c, Small& s) {
+  GPCA_CUDA_TRY(c, c->ws_small.alloc(4 * 64 * 64));
+  s.G = c->ws_small.p;
+  s.evals = s.G + 64 * 64;
+  s.evecs = s.evals + 64 * 64;
+  s.T = s.evecs + 64 * 64;
+  return GPCA_OK;
+}
+
+// Orthonormalise the columns of Y [n x l] in place: two rounds of  G = Y^T Y = V L V^T ; Y <- Y V L^-1/2
+// (eigen-based CholeskyQR2 variant; rank-deficient directions are zeroed instead of breaking a Cholesky).
+// `sharded`: rows of Y are split across shards -> the l x l Gram is summed through the allreduce hook.
+int orthonormalize(gpca_ctx* c, float* y, uint64_t n, uint32_t l, uint32_t ld, bool sharded, const Small& s) {
+  for (int rep = 0; rep < 2; ++rep) {
+    GPCA_TRY(launch_gram(c, y, n, l, ld, s.G));
+    if (sharded && c->allreduce)
+      if (c->allreduce(s.G, (uint64_t)l * l, 1, (void*)c->stream, c->allreduce_user) != 0)
+        return fail(c, GPCA_ERR_CUDA, "allreduce hook failed");
+    GPCA_TRY(launch_jacobi_eigh(c, s.G, l, s.evals, s.evecs));
+    GPCA_TRY(launch_make_orth_transform(c, s.evals, s.evecs, l, s.T, rep == 0 ? 1e-11 : 1e-13));
+    GPCA_TRY(launch_apply_right(c, y, n, l, ld, s.T, l, y, ld));
+  }
+  return GPCA_OK;
+}
+
+__global__ void make_rotation_transform_kernel(const double* evals, const double* evecs, uint32_t l, uint32_t k,
+                                               double* t) {
+  // t [l x k] = evecs[:, :k] / sqrt(evals[:k])
+  for (int i = threadIdx.x; i < (int)(l * k); i += blockDim.x) {
+    const int r = i / k, j = i % k;
+    const double lam = evals[j];
+    t[i] = lam > 0.0 ? evecs[r * l + j] / sqrt(lam) : 0.0;
+  }
+}
+
+void fix_signs_host(std::vector<float>& scores, uint64_t n, uint32_t k, std::vector<int>& flip) {
+  flip.assign(k, 0);
+  for (uint32_t j = 0; j < k; ++j) {
+    float best = -1.f;
+    uint64_t bi = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+      const float a = std::fabs(scores[i * k + j]);
+      if (a > best) {
+        best = a;
+        bi = i;
+      }
+    }
+    if (n && scores[bi * k + j] < 0) {
+      flip[j] = 1;
+      for (uint64_t i = 0; i < n; ++i) scores[i * k + j] = -scores[i * k + j];
+    }
+  }
+}
+}  // namespace
+
+extern "C" int gpca_rfit(gpca_ctx* c, uint32_t k, uint32_t oversample, uint32_t power_iters, uint64_t seed,
+                         int has_seed, double* scores, double* eigenvalues, float* loadings, uint32_t* k_out) {
+  if (!c) return GPCA_ERR_INVALID;
+  GPCA_CUDA_TRY(c, cudaSetDevice(c->device));
+  if (c->D == 0) return fail(c, GPCA_ERR_INVALID, "gpca_set_pca_snps has not been called");
+  if (k == 0) return fail(c, GPCA_ERR_INVALID, "Number of components (-k) must be > 0.");  // main.rs:607
+  const uint64_t N = c->N, D = c->D;
+  const uint64_t Dtot = c->shard_total ? c->shard_total : D;
+  if (N < 2) return fail(c, GPCA_ERR_INVALID, "PCA requires at least 2 samples");            // main.rs:614
+  const uint64_t maxk = std::min<uint64_t>(N, Dtot);                                        // main.rs:621
+  if (k > maxk) k = (uint32_t)maxk;                                                         // main.rs:622-628
+  uint64_t l64 = std::min<uint64_t>((uint64_t)k + oversample, maxk);
+  if (l64 > 64) return fail(c, GPCA_ERR_INVALID, "k + oversample must be <= 64 in this build");
+  const uint32_t l = (uint32_t)l64;
+  if (!has_seed) {
+    std::random_device rd;
+    seed = ((uint64_t)rd() << 32) ^ rd() ^ (uint64_t)std::chrono::steady_clock::now().time_since_epoch().count();
+  }
+  Small s;
+  GPCA_TRY(get_small(c, s));
+  DevBuf<float> Y, Z;
+  GPCA_CUDA_TRY(c, Y.alloc(N * l));
+  GPCA_CUDA_TRY(c, Z.alloc(D * l));
+  const bool sharded = c->allreduce != nullptr;
+
+  // Y = S^T Omega
+  GPCA_TRY(launch_gaussian(c, Z.p, D, l, l, seed, STREAM_RFIT_OMEGA, c->shard_offset));
+  GPCA_TRY(sketch_sample_side(c, Z.p, Y.p, l, l, l));
+  for (uint32_t it = 0; it < power_iters; ++it) {
+    GPCA_TRY(orthonormalize(c, Y.p, N, l, l, false, s));
+    GPCA_TRY(sketch_snp_side(c, Y.p, Z.p, l, l, l));      // Z = S Q
+    // (range(S^T Z) does not depend on a column transform of Z; the snp-side basis is left unnormalised
+    //  between the two half-steps, the sample side is re-orthonormalised every iteration)
+    GPCA_TRY(sketch_sample_side(c, Z.p, Y.p, l, l, l));   // Y = S^T Z
+  }
+  GPCA_TRY(orthonormalize(c, Y.p, N, l, l, false, s));
+  GPCA_TRY(sketch_snp_side(c, Y.p, Z.p, l, l, l));        // B = S Q   [D x l]
+  GPCA_TRY(launch_gram(c, Z.p, D, l, l, s.G));
+  if (sharded)
+    if (c->allreduce(s.G, (uint64_t)l * l, 1, (void*)c->stream, c->allreduce_user) != 0)
+      return fail(c, GPCA_ERR_CUDA, "allreduce hook failed");
+  GPCA_TRY(launch_jacobi_eigh(c, s.G, l, s.evals, s.evecs));
+  make_rotation_transform_kernel<<<1, 256, 0, c->stream>>>(s.evals, s.evecs, l, k, s.T);
+  c->launches++;
+  GPCA_CUDA_TRY(c, cudaGetLastError());
+  DevBuf<float> R, Sc;
+  GPCA_CUDA_TRY(c, R.alloc(D * k));
+  GPCA_CUDA_TRY(c, Sc.alloc(N * k));
+  GPCA_TRY(launch_apply_right(c, Z.p, D, l, l, s.T, k, R.p, k));  // rotation = B V_b / s  [D x k]
+  GPCA_TRY(sketch_sample_side(c, R.p, Sc.p, k, k, k));            // transform(): scores = S^T rotation
+
+  std::vector<double> h_ev(l);
+  std::vector<float> h_sc(N * k);
+  GPCA_CUDA_TRY(c, cudaMemcpyAsync(h_ev.data(), s.evals, l * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  GPCA_CUDA_TRY(c, cudaMemcpyAsync(h_sc.data(), Sc.p, N * k * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  GPCA_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  std::vector<int> flip;
+  fix_signs_host(h_sc, N, k, flip);
+  if (scores)
+    for (uint64_t i = 0; i < N * k; ++i) scores[i] = (double)h_sc[i];
+  if (eigenvalues)
+    for (uint32_t j = 0; j < k; ++j) eigenvalues[j] = h_ev[j] / (double)(N - 1);
+  if (loadings) {
+    GPCA_CUDA_TRY(c, cudaMemcpyAsync(loadings, R.p, D * k * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    GPCA_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    for (uint32_t j = 0; j < k; ++j)
+      if (flip[j])
+        for (uint64_t i = 0; i < D; ++i) loadings[i * k + j] = -loadings[i * k + j];
+  }
+  if (k_out) *k_out = k;
+  return GPCA_OK;
+}
+
+extern "C" void gpca_eigensnp_default_cfg(gpca_eigensnp_cfg* cfg) {
+  if (!cfg) return;
+  cfg->target_num_global_pcs = 10;      // main.rs:554
+  cfg->components_per_ld_block = 7;     // main.rs:557
+  cfg->subset_factor = 0.075;           // main.rs:560
+  cfg->min_subset_size = 10000;         // main.rs:563
+  cfg->max_subset_size = 40000;         // main.rs:566
+  cfg->global_oversampling = 10;        // main.rs:569
+  cfg->global_power_iters = 2;          // main.rs:572
+  cfg->local_oversampling = 10;         // main.rs:575
+  cfg->local_power_iters = 2;           // main.rs:578
+  cfg->random_seed = 2025;              // main.rs:581
+  cfg->snp_processing_strip_size = 2000;  // main.rs:584
+  cfg->refine_pass_count = 1;           // main.rs:587
+  cfg->collect_diagnostics = 0;
+}

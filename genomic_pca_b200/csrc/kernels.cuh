@@ -1,0 +1,52 @@
+// kernels.cuh -- host-callable launch wrappers (one per kernel family).
+#pragma once
+#include "common.cuh"
+
+// ---- ingest (kernels_ingest.cu) ---------------------------------------------------------
+// PLINK rows with arbitrary byte pitch -> 16B-aligned pitch, optional sample gather; pad fields = 01.
+int launch_repitch_gather(gpca_ctx* c, const uint8_t* d_in, size_t in_pitch, uint64_t n_in_samples,
+                          const int64_t* d_keep, uint64_t N, uint64_t M, uint8_t* d_out, size_t out_pitch);
+// variant-major u8 dosages -> PLINK-coded rows (pad fields = 01)
+int launch_u8_to_plink(gpca_ctx* c, const uint8_t* d_in, uint64_t N, uint64_t M, uint8_t* d_out, size_t out_pitch);
+// K-a: per-row code counts over ALL fields of the pitch: out[row] = {n(01), n(10), n(11), 0}
+int launch_bed_counts(gpca_ctx* c, const uint8_t* d_raw, size_t pitch, uint64_t M, uint4* d_out);
+// gather rows + recode PLINK -> dosage-coded, zero pads: Gs
+int launch_build_gs(gpca_ctx* c, const uint8_t* d_raw, size_t raw_pitch, const uint64_t* d_idx, PackedMat gs);
+// 2-bit transpose: Gt[n][d] = Gs[d][n]
+int launch_transpose(gpca_ctx* c, PackedMat gs, PackedMat gt);
+// standardized block (accessor parity): out[i][j] = fma(x, 1/sd, -mean/sd); flag set if any missing
+int launch_std_block(gpca_ctx* c, PackedMat gs, const float* d_mean, const float* d_sd, const uint64_t* d_ids,
+                     uint64_t n_ids, const uint64_t* d_samp, uint64_t n_samp, float* d_out, int* d_missing_flag);
+
+// ---- dense helpers (kernels_dense.cu) ---------------------------------------------------
+// Gaussian test matrix: out[r][c] = N(0,1) keyed by (seed, stream, row0 + r, c); ld in floats
+int launch_gaussian(gpca_ctx* c, float* d_out, uint64_t rows, uint32_t cols, uint32_t ld, uint64_t seed,
+                    uint32_t stream, uint64_t row0);
+// G[l x l] (f64, row-major) = Y^T Y, Y [n x l] fp32 with row stride ld.  Deterministic two-stage.
+int launch_gram(gpca_ctx* c, const float* d_y, uint64_t n, uint32_t l, uint32_t ld, double* d_g);
+// Y <- Y * T (T [l x l2] f64 row-major on device), in place allowed when d_out == d_y. out ld = ldo
+int launch_apply_right(gpca_ctx* c, const float* d_y, uint64_t n, uint32_t l, uint32_t ld, const double* d_t,
+                       uint32_t l2, float* d_out, uint32_t ldo);
+// single-CTA Jacobi eigensolver on a symmetric l x l f64 matrix (l <= 64):
+// evals descending, evecs as columns (row-major [l x l]).
+int launch_jacobi_eigh(gpca_ctx* c, const double* d_a, uint32_t l, double* d_evals, double* d_evecs);
+// T = V * diag(lambda^-1/2) with rank truncation (lambda <= eps*lambda_max -> column zeroed)
+int launch_make_orth_transform(gpca_ctx* c, const double* d_evals, const double* d_evecs, uint32_t l, double* d_t,
+                               double rel_eps);
+int launch_f32_to_f64(gpca_ctx* c, const float* in, double* out, uint64_t n);
+int launch_scale_cols_to_f64(gpca_ctx* c, const float* in, uint64_t n, uint32_t k, uint32_t ld, double* out);
+
+// ---- sketch (kernels_sketch.cu) -----------------------------------------------------------
+struct SketchProblem {
+  PackedMat G;            // [rows x K]
+  const float* Bin;       // [K x ld] dense operand
+  uint32_t l, ld;         // logical columns (<=64), row stride
+  const float* f;         // [K] per-k operand scale (nullptr = 1)
+  const float* e;         // [K] per-k weight for the rank-one term (nullptr = 1)
+  const float* a;         // [rows] per-row output scale (nullptr = 1)
+  const float* b;         // [rows] per-row weight of the rank-one term (nullptr = 1)
+  float* out;             // [rows x ldo]
+  uint32_t ldo;
+};
+// out[r,:] = a_r * sum_k code(r,k) f_k Bin[k,:]  -  b_r * sum_k e_k Bin[k,:]  (+ missing correction)
+int launch_sketch(gpca_ctx* c, const SketchProblem& p);

@@ -1,0 +1,312 @@
+// kernels_dense.cu -- the small dense linear algebra around the sketch passes:
+// Gaussian test matrices, l x l Gram (f64 accumulation), right-multiplication by an l x l2
+// transform, single-CTA Jacobi eigensolver.  These replace the QR / small-SVD calls that
+// efficient_pca makes through faer/LAPACK (external crate; call sites src/main.rs:648-659, :365).
+#include "kernels.cuh"
+#include "philox.cuh"
+
+#define KLAUNCH_CHECK(c)                    \
+  do {                                      \
+    (c)->launches++;                        \
+    GPCA_CUDA_TRY((c), cudaGetLastError()); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------
+__global__ void gaussian_kernel(float* __restrict__ out, uint64_t rows, uint32_t cols, uint32_t ld, uint64_t seed,
+                                uint32_t stream, uint64_t row0) {
+  const uint64_t total = rows * ld;
+  for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < total;
+       t += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t r = t / ld;
+    const uint32_t cidx = (uint32_t)(t - r * ld);
+    out[t] = (cidx < cols) ? philox_normal(seed, stream, row0 + r, cidx) : 0.0f;
+  }
+}
+
+int launch_gaussian(gpca_ctx* c, float* d_out, uint64_t rows, uint32_t cols, uint32_t ld, uint64_t seed,
+                    uint32_t stream, uint64_t row0) {
+  const uint64_t total = rows * ld;
+  if (total == 0) return GPCA_OK;
+  const int threads = 256;
+  const uint64_t blocks = (total + threads - 1) / threads;
+  const int grid = (int)(blocks < (uint64_t)c->sm_count * 16 ? blocks : (uint64_t)c->sm_count * 16);
+  gaussian_kernel<<<grid, threads, 0, c->stream>>>(d_out, rows, cols, ld, seed, stream, row0);
+  KLAUNCH_CHECK(c);
+  return GPCA_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Gram: each CTA owns a contiguous range of rows, stages 64 rows at a time in shared memory and
+// accumulates a 64 x 64 (padded) f64 partial with a 4 x 4 register tile per thread; partials are
+// then summed in a fixed order by gram_reduce_kernel (deterministic).
+constexpr int GRAM_LP = 64;
+constexpr int GRAM_ROWS = 64;
+
+__global__ void __launch_bounds__(256) gram_partial_kernel(const float* __restrict__ y, uint64_t n, uint32_t l,
+                                                           uint32_t ld, uint64_t rows_per_cta,
+                                                           double* __restrict__ partial) {
+  __shared__ __align__(16) float tile[GRAM_ROWS][GRAM_LP + 4];
+  const int ti = threadIdx.x / 16, tj = threadIdx.x % 16;
+  double acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+  const uint64_t r_begin = blockIdx.x * rows_per_cta;
+  uint64_t r_end = r_begin + rows_per_cta;
+  if (r_end > n) r_end = n;
+  const bool need_i = (uint32_t)(ti * 4) < l, need_j = (uint32_t)(tj * 4) < l;
+  for (uint64_t r0 = r_begin; r0 < r_end; r0 += GRAM_ROWS) {
+    for (int t = threadIdx.x; t < GRAM_ROWS * GRAM_LP; t += 256) {
+      const int rr = t / GRAM_LP, cc = t % GRAM_LP;
+      const uint64_t r = r0 + rr;
+      tile[rr][cc] = (r < r_end && (uint32_t)cc < l) ? y[r * ld + cc] : 0.0f;
+    }
+    __syncthreads();
+    if (need_i && need_j) {
+#pragma unroll 4
+      for (int rr = 0; rr < GRAM_ROWS; ++rr) {
+        const float4 a = *reinterpret_cast<const float4*>(&tile[rr][ti * 4]);
+        const float4 b = *reinterpret_cast<const float4*>(&tile[rr][tj * 4]);
+        const double av[4] = {a.x, a.y, a.z, a.w};
+        const double bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+      }
+    }
+    __syncthreads();
+  }
+  double* p = partial + (uint64_t)blockIdx.x * GRAM_LP * GRAM_LP;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) p[(ti * 4 + i) * GRAM_LP + tj * 4 + j] = acc[i][j];
+}
+
+__global__ void gram_reduce_kernel(const double* __restrict__ partial, int nparts, uint32_t l, double* __restrict__ g) {
+  for (int t = threadIdx.x; t < (int)(l * l); t += blockDim.x) {
+    const int i = t / l, j = t % l;
+    double s = 0.0;
+    for (int p = 0; p < nparts; ++p) s += partial[(uint64_t)p * GRAM_LP * GRAM_LP + i * GRAM_LP + j];
+    g[t] = s;
+  }
+}
+
+int launch_gram(gpca_ctx* c, const float* d_y, uint64_t n, uint32_t l, uint32_t ld, double* d_g) {
+  if (l == 0 || l > 64) {
+    c->set_error("launch_gram: l must be in 1..64");
+    return GPCA_ERR_INVALID;
+  }
+  int nparts = (int)((n + 1023) / 1024);
+  if (nparts > c->sm_count * 4) nparts = c->sm_count * 4;
+  if (nparts < 1) nparts = 1;
+  uint64_t rows_per_cta = (n + nparts - 1) / nparts;
+  rows_per_cta = round_up(rows_per_cta ? rows_per_cta : 1, GRAM_ROWS);
+  nparts = (int)((n + rows_per_cta - 1) / rows_per_cta);
+  if (nparts < 1) nparts = 1;
+  GPCA_CUDA_TRY(c, c->ws_f64.alloc((size_t)nparts * GRAM_LP * GRAM_LP + 4096));
+  gram_partial_kernel<<<nparts, 256, 0, c->stream>>>(d_y, n, l, ld, rows_per_cta, c->ws_f64.p);
+  KLAUNCH_CHECK(c);
+  gram_reduce_kernel<<<1, 256, 0, c->stream>>>(c->ws_f64.p, nparts, l, d_g);
+  KLAUNCH_CHECK(c);
+  return GPCA_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// out[r, :l2] = y[r, :l] * T   (T f64 in shared memory, f64 accumulation, fp32 store)
+__global__ void __launch_bounds__(256) apply_right_kernel(const float* __restrict__ y, uint64_t n, uint32_t l,
+                                                          uint32_t ld, const double* __restrict__ t, uint32_t l2,
+                                                          float* __restrict__ out, uint32_t ldo) {
+  extern __shared__ double sm[];
+  double* ts = sm;                                            // [l][l2]
+  float* tile = reinterpret_cast<float*>(sm + l * l2);        // [64][l+1]
+  for (int i = threadIdx.x; i < (int)(l * l2); i += 256) ts[i] = t[i];
+  const int lp = l + 1;
+  const uint64_t ntiles = (n + 63) / 64;
+  for (uint64_t tix = blockIdx.x; tix < ntiles; tix += gridDim.x) {
+    const uint64_t r0 = tix * 64;
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * (int)l; i += 256) {
+      const int rr = i / l, cc = i % l;
+      const uint64_t r = r0 + rr;
+      tile[rr * lp + cc] = (r < n) ? y[r * ld + cc] : 0.0f;
+    }
+    __syncthreads();
+    const int rr = threadIdx.x >> 2, cg = threadIdx.x & 3;
+    const uint64_t r = r0 + rr;
+    if (r < n) {
+      for (uint32_t c2 = cg; c2 < l2; c2 += 4) {
+        double s = 0.0;
+        for (uint32_t cc = 0; cc < l; ++cc) s = fma((double)tile[rr * lp + cc], ts[cc * l2 + c2], s);
+        out[r * ldo + c2] = (float)s;
+      }
+    }
+  }
+}
+
+int launch_apply_right(gpca_ctx* c, const float* d_y, uint64_t n, uint32_t l, uint32_t ld, const double* d_t,
+                       uint32_t l2, float* d_out, uint32_t ldo) {
+  if (n == 0 || l == 0 || l2 == 0) return GPCA_OK;
+  const size_t smem = (size_t)l * l2 * sizeof(double) + (size_t)64 * (l + 1) * sizeof(float);
+  if (smem > 48 * 1024) GPCA_CUDA_TRY(c, cudaFuncSetAttribute(apply_right_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const uint64_t ntiles = (n + 63) / 64;
+  const int grid = (int)(ntiles < (uint64_t)c->sm_count * 4 ? ntiles : (uint64_t)c->sm_count * 4);
+  apply_right_kernel<<<grid, 256, smem, c->stream>>>(d_y, n, l, ld, d_t, l2, d_out, ldo);
+  KLAUNCH_CHECK(c);
+  return GPCA_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Single-CTA two-sided cyclic Jacobi (round-robin pairing), f64, l <= 64.
+__global__ void __launch_bounds__(256) jacobi_eigh_kernel(const double* __restrict__ a_in, uint32_t l,
+                                                          double* __restrict__ evals, double* __restrict__ evecs) {
+  constexpr int LP = 64;
+  extern __shared__ double jsm[];
+  double (*A)[LP + 1] = reinterpret_cast<double (*)[LP + 1]>(jsm);
+  double (*V)[LP + 1] = reinterpret_cast<double (*)[LP + 1]>(jsm + LP * (LP + 1));
+  __shared__ double cs[LP / 2][2];
+  __shared__ int pairs[LP / 2][2];
+  __shared__ int order[LP];
+  __shared__ double red[8];
+  __shared__ int done;
+  const int n = (int)l;
+  const int ne = n + (n & 1);  // even size, dummy index n if odd
+  for (int t = threadIdx.x; t < LP * LP; t += blockDim.x) {
+    const int i = t / LP, j = t % LP;
+    A[i][j] = (i < n && j < n) ? 0.5 * (a_in[i * n + j] + a_in[j * n + i]) : 0.0;
+    V[i][j] = (i == j) ? 1.0 : 0.0;
+  }
+  if (threadIdx.x == 0) done = 0;
+  __syncthreads();
+  const int npairs = ne / 2;
+  for (int sweep = 0; sweep < 40; ++sweep) {
+    // convergence: off-diagonal Frobenius^2 vs diagonal
+    double off = 0.0, dg = 0.0;
+    for (int t = threadIdx.x; t < n * n; t += blockDim.x) {
+      const int i = t / n, j = t % n;
+      const double v = A[i][j];
+      if (i == j) dg += v * v;
+      else off += v * v;
+    }
+    off = warp_sum_f64(off);
+    dg = warp_sum_f64(dg);
+    if ((threadIdx.x & 31) == 0) {
+      red[(threadIdx.x >> 5)] = off;
+    }
+    __syncthreads();
+    double off_t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) off_t += red[w];
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[(threadIdx.x >> 5)] = dg;
+    __syncthreads();
+    double dg_t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) dg_t += red[w];
+    __syncthreads();
+    if (off_t <= 1e-30 * dg_t || off_t == 0.0) break;
+    for (int round = 0; round < ne - 1; ++round) {
+      // round-robin tournament: position 0 fixed, others rotate
+      if ((int)threadIdx.x < npairs) {
+        const int k = threadIdx.x;
+        int p = (k == 0) ? 0 : 1 + (round + k - 1) % (ne - 1);
+        int q = 1 + (round + ne - 1 - k - 1) % (ne - 1);
+        if (p > q) {
+          const int tmp = p;
+          p = q;
+          q = tmp;
+        }
+        pairs[k][0] = p;
+        pairs[k][1] = q;
+        double cth = 1.0, sth = 0.0;
+        if (q < n) {
+          const double apq = A[p][q];
+          if (apq != 0.0) {
+            const double app = A[p][p], aqq = A[q][q];
+            const double tau = (aqq - app) / (2.0 * apq);
+            const double tt = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+            cth = 1.0 / sqrt(1.0 + tt * tt);
+            sth = tt * cth;
+          }
+        }
+        cs[k][0] = cth;
+        cs[k][1] = sth;
+      }
+      __syncthreads();
+      // columns: A <- A J, V <- V J
+      for (int t = threadIdx.x; t < npairs * n; t += blockDim.x) {
+        const int k = t / n, i = t % n;
+        const int p = pairs[k][0], q = pairs[k][1];
+        const double cth = cs[k][0], sth = cs[k][1];
+        if (q < n && sth != 0.0) {
+          const double aip = A[i][p], aiq = A[i][q];
+          A[i][p] = cth * aip - sth * aiq;
+          A[i][q] = sth * aip + cth * aiq;
+          const double vip = V[i][p], viq = V[i][q];
+          V[i][p] = cth * vip - sth * viq;
+          V[i][q] = sth * vip + cth * viq;
+        }
+      }
+      __syncthreads();
+      // rows: A <- J^T A
+      for (int t = threadIdx.x; t < npairs * n; t += blockDim.x) {
+        const int k = t / n, j = t % n;
+        const int p = pairs[k][0], q = pairs[k][1];
+        const double cth = cs[k][0], sth = cs[k][1];
+        if (q < n && sth != 0.0) {
+          const double apj = A[p][j], aqj = A[q][j];
+          A[p][j] = cth * apj - sth * aqj;
+          A[q][j] = sth * apj + cth * aqj;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  // sort descending (rank by counting), write out
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double di = A[i][i];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) {
+      const double dj = A[j][j];
+      if (dj > di || (dj == di && j < i)) ++rank;
+    }
+    order[rank] = i;
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < n; t += blockDim.x) evals[t] = A[order[t]][order[t]];
+  for (int t = threadIdx.x; t < n * n; t += blockDim.x) {
+    const int i = t / n, j = t % n;
+    evecs[i * n + j] = V[i][order[j]];
+  }
+}
+
+int launch_jacobi_eigh(gpca_ctx* c, const double* d_a, uint32_t l, double* d_evals, double* d_evecs) {
+  if (l == 0 || l > 64) {
+    c->set_error("jacobi_eigh: l must be in 1..64");
+    return GPCA_ERR_INVALID;
+  }
+  const size_t smem = 2 * 64 * 65 * sizeof(double);
+  GPCA_CUDA_TRY(c, cudaFuncSetAttribute(jacobi_eigh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  jacobi_eigh_kernel<<<1, 256, smem, c->stream>>>(d_a, l, d_evals, d_evecs);
+  KLAUNCH_CHECK(c);
+  return GPCA_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void make_orth_transform_kernel(const double* __restrict__ evals, const double* __restrict__ evecs,
+                                           uint32_t l, double* __restrict__ t, double rel_eps) {
+  const double lmax = evals[0];
+  for (int i = threadIdx.x; i < (int)(l * l); i += blockDim.x) {
+    const int j = i % l;
+    const double lam = evals[j];
+    t[i] = (lam > rel_eps * lmax && lam > 0.0) ? evecs[i] / sqrt(lam) : 0.0;
+  }
+}
+
+int launch_make_orth_transform(gpca_ctx* c, const double* d_evals, const double* d_evecs, uint32_t l, double* d_t,
+                               double rel_eps) {
+  make_orth_transform_kernel<<<1, 256, 0, c->stream>>>(d_evals, d_evecs, l, d_t, rel_eps);
+  KLAUNCH_CHECK(c);
+  return GPCA_OK;
+}

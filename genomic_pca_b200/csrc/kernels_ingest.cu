@@ -1,0 +1,359 @@
+// kernels_ingest.cu -- PLINK 2-bit ingest: re-pitch/gather, allele-count kernel (K-a),
+// recode to the resident dosage coding, 2-bit transpose, standardized-block accessor.
+//
+// Reference semantics replaced here:
+//   * bed-reader reads with count_a1 (src/prepare.rs:622-629, 682-687): 00->2, 01->missing, 10->1, 11->0
+//   * pass 1 of perform_snp_qc_and_calc_std_params (src/prepare.rs:1232-1279): integer counts
+//   * get_standardized_snp_sample_block (src/prepare.rs:1884-2016)
+#include "kernels.cuh"
+
+#define KLAUNCH_CHECK(c)                                   \
+  do {                                                     \
+    (c)->launches++;                                       \
+    GPCA_CUDA_TRY((c), cudaGetLastError());                \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------
+// Re-pitch (and optionally gather samples).  One thread per output 32-bit word (16 fields).
+// Source rows may start at any byte offset (pitch ceil(N/4) is rarely 4-aligned), so the source
+// is read with byte loads; they hit the same L1 sectors across the warp.
+__global__ void repitch_gather_kernel(const uint8_t* __restrict__ in, size_t in_pitch, uint64_t n_in,
+                                      const int64_t* __restrict__ keep, uint64_t N, uint64_t M,
+                                      uint8_t* __restrict__ out, size_t out_pitch) {
+  const uint64_t words_per_row = out_pitch / 4;
+  const uint64_t total = M * words_per_row;
+  for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < total;
+       t += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t row = t / words_per_row;
+    const uint64_t wi = t - row * words_per_row;
+    const uint8_t* src = in + row * in_pitch;
+    const uint64_t k0 = wi * 16;
+    uint32_t w = 0x55555555u;  // all fields = 01 (missing) -> pads
+    if (k0 < N) {
+      if (keep == nullptr) {
+        uint32_t v = 0;
+        const uint64_t b0 = wi * 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t byte = 0x55u;
+          if ((b0 + j) * 4 < n_in) byte = src[b0 + j];
+          v |= byte << (8 * j);
+        }
+        w = v;
+        if (k0 + 16 > N) {  // mask the tail fields to 01
+          const int valid = (int)(N - k0);
+          const uint32_t m = (valid >= 16) ? 0xffffffffu : ((1u << (2 * valid)) - 1u);
+          w = (v & m) | (0x55555555u & ~m);
+        }
+      } else {
+        uint32_t v = 0;
+#pragma unroll 4
+        for (int j = 0; j < 16; ++j) {
+          uint32_t code = 1u;
+          if (k0 + j < N) {
+            const uint64_t s = (uint64_t)keep[k0 + j];
+            code = (src[s >> 2] >> (2 * (s & 3))) & 3u;
+          }
+          v |= code << (2 * j);
+        }
+        w = v;
+      }
+    }
+    *reinterpret_cast<uint32_t*>(out + row * out_pitch + wi * 4) = w;
+  }
+}
+
+int launch_repitch_gather(gpca_ctx* c, const uint8_t* d_in, size_t in_pitch, uint64_t n_in_samples,
+                          const int64_t* d_keep, uint64_t N, uint64_t M, uint8_t* d_out, size_t out_pitch) {
+  if (M == 0) return GPCA_OK;
+  const uint64_t total = M * (out_pitch / 4);
+  const int threads = 256;
+  const uint64_t blocks = (total + threads - 1) / threads;
+  const int grid = (int)(blocks < (uint64_t)c->sm_count * 32 ? blocks : (uint64_t)c->sm_count * 32);
+  repitch_gather_kernel<<<grid, threads, 0, c->stream>>>(d_in, in_pitch, n_in_samples, d_keep, N, M, d_out, out_pitch);
+  KLAUNCH_CHECK(c);
+  return GPCA_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// VCF path: variant-major u8 dosages (vcf.rs:293-315 Vec<Vec<u8>>) -> PLINK codes.
+__global__ void u8_to_plink_kernel(const uint8_t* __restrict__ in, uint64_t N, uint64_t M,
+                                   uint8_t* __restrict__ out, size_t out_pitch) {
+  const uint64_t words_per_row = out_pitch / 4;
+  const uint64_t total = M * words_per_row;
+  for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < total;
+       t += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t row = t / words_per_row;
+    const uint64_t wi = t - row * words_per_row;
+    const uint8_t* src = in + row * N;
+    const uint64_t k0 = wi * 16;
+    uint32_t w = 0;
+#pragma unroll 4
+    for (int j = 0; j < 16; ++j) {
+      uint32_t code = 1u;
+      if (k0 + j < N) {
+        const uint32_t d = src[k0 + j];
+        code = (d == 0) ? 3u : (d == 1) ? 2u : (d == 2) ? 0u : 1u;
+      }
+      w |= code << (2 * j);
+    }
+    *reinterpret_cast<uint32_t*>(out + row * out_pitch + wi * 4) = w;
+  }
+}
+
+int launch_u8_to_plink(gpca_ctx* c, const uint8_t* d_in, uint64_t N, uint64_t M, uint8_t* d_out, size_t out_pitch) {
+  if (M == 0) return GPCA_OK;
+  const uint64_t total = M * (out_pitch / 4);
+  const int threads = 256;
+  const uint64_t blocks = (total + threads - 1) / threads;
+  const int grid = (int)(blocks < (uint64_t)c->sm_count * 32 ? blocks : (uint64_t)c->sm_count * 32);
+  u8_to_plink_kernel<<<grid, threads, 0, c->stream>>>(d_in, N, M, d_out, out_pitch);
+  KLAUNCH_CHECK(c);
+  return GPCA_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// K-a  bed_counts: HBM-bound.  128-bit loads, 2-bit field popcounts, shuffle reduction.
+//   lo = w & 0x5555.., hi = (w>>1) & 0x5555..;  n(11)=popc(hi&lo)  n(10)=popc(hi&~lo)  n(01)=popc(~hi&lo)
+// GROUP lanes cooperate on one row (GROUP = 8, 32) or a whole CTA does (GROUP = 0).
+__device__ __forceinline__ void count_word(uint32_t w, uint32_t& c01, uint32_t& c10, uint32_t& c11) {
+  const uint32_t lo = w & 0x55555555u;
+  const uint32_t hi = (w >> 1) & 0x55555555u;
+  c11 += __popc(hi & lo);
+  c10 += __popc(hi & ~lo);
+  c01 += __popc(lo & ~hi);
+}
+
+template <int GROUP>
+__global__ void __launch_bounds__(256) bed_counts_kernel(const uint8_t* __restrict__ raw, size_t pitch, uint64_t M,
+                                                         uint4* __restrict__ out) {
+  const int chunks = (int)(pitch / 16);
+  if constexpr (GROUP > 0) {
+    // warp-uniform outer loop (all 32 lanes reach every shuffle); a warp covers 32/GROUP rows per step
+    constexpr int GPW = 32 / GROUP;
+    const uint64_t warp_id = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x % GROUP;
+    const int sub = (threadIdx.x & 31) / GROUP;
+    for (uint64_t base = warp_id * GPW; base < M; base += nwarps * GPW) {
+      const uint64_t row = base + sub;
+      const bool live = row < M;
+      const uint4* p = reinterpret_cast<const uint4*>(raw + (live ? row : 0) * pitch);
+      uint32_t c01 = 0, c10 = 0, c11 = 0;
+      for (int i = lane; live && i < chunks; i += GROUP) {
+        const uint4 v = ldg_nc_v4(p + i);
+        count_word(v.x, c01, c10, c11);
+        count_word(v.y, c01, c10, c11);
+        count_word(v.z, c01, c10, c11);
+        count_word(v.w, c01, c10, c11);
+      }
+#pragma unroll
+      for (int o = GROUP / 2; o > 0; o >>= 1) {
+        c01 += __shfl_xor_sync(0xffffffffu, c01, o);
+        c10 += __shfl_xor_sync(0xffffffffu, c10, o);
+        c11 += __shfl_xor_sync(0xffffffffu, c11, o);
+      }
+      if (lane == 0 && live) out[row] = make_uint4(c01, c10, c11, 0u);
+    }
+  } else {
+    __shared__ uint32_t s[3][8];
+    for (uint64_t row = blockIdx.x; row < M; row += gridDim.x) {
+      const uint4* p = reinterpret_cast<const uint4*>(raw + row * pitch);
+      uint32_t c01 = 0, c10 = 0, c11 = 0;
+      for (int i = threadIdx.x; i < chunks; i += blockDim.x) {
+        const uint4 v = ldg_nc_v4(p + i);
+        count_word(v.x, c01, c10, c11);
+        count_word(v.y, c01, c10, c11);
+        count_word(v.z, c01, c10, c11);
+        count_word(v.w, c01, c10, c11);
+      }
+      c01 = warp_sum_u32(c01);
+      c10 = warp_sum_u32(c10);
+      c11 = warp_sum_u32(c11);
+      const int wid = threadIdx.x >> 5;
+      if ((threadIdx.x & 31) == 0) {
+        s[0][wid] = c01;
+        s[1][wid] = c10;
+        s[2][wid] = c11;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        uint32_t t0 = 0, t1 = 0, t2 = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+          t0 += s[0][w];
+          t1 += s[1][w];
+          t2 += s[2][w];
+        }
+        out[row] = make_uint4(t0, t1, t2, 0u);
+      }
+      __syncthreads();
+    }
+  }
+}
+
+int launch_bed_counts(gpca_ctx* c, const uint8_t* d_raw, size_t pitch, uint64_t M, uint4* d_out) {
+  if (M == 0) return GPCA_OK;
+  const int threads = 256;
+  const int chunks = (int)(pitch / 16);
+  // grid: a multiple of the SM count, 8 resident CTAs of 256 threads per SM
+  const int grid_full = c->sm_count * 8;
+  if (chunks <= 16) {
+    uint64_t need = (M * 8 + threads - 1) / threads;
+    int grid = (int)(need < (uint64_t)grid_full ? need : (uint64_t)grid_full);
+    bed_counts_kernel<8><<<grid, threads, 0, c->stream>>>(d_raw, pitch, M, d_out);
+  } else if (chunks <= 1024) {
+    uint64_t need = (M * 32 + threads - 1) / threads;
+    int grid = (int)(need < (uint64_t)grid_full ? need : (uint64_t)grid_full);
+    bed_counts_kernel<32><<<grid, threads, 0, c->stream>>>(d_raw, pitch, M, d_out);
+  } else {
+    int grid = (int)(M < (uint64_t)grid_full ? M : (uint64_t)grid_full);
+    bed_counts_kernel<0><<<grid, threads, 0, c->stream>>>(d_raw, pitch, M, d_out);
+  }
+  KLAUNCH_CHECK(c);
+  return GPCA_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Gather PCA rows + recode PLINK -> dosage code:  d_hi = ~hi, d_lo = lo ^ hi
+//   00->10 (2)  01->11 (3 = missing)  10->01 (1)  11->00 (0);   pad fields (k >= N) -> 00.
+__device__ __forceinline__ uint32_t recode_word(uint32_t w) {
+  return ((~w) & 0xAAAAAAAAu) | ((w ^ (w >> 1)) & 0x55555555u);
+}
+
+__global__ void build_gs_kernel(const uint8_t* __restrict__ raw, size_t raw_pitch, const uint64_t* __restrict__ idx,
+                                uint8_t* __restrict__ gs, size_t gs_pitch, uint64_t D, uint64_t N) {
+  const uint64_t chunks_per_row = gs_pitch / 16;
+  const uint64_t raw_chunks = raw_pitch / 16;
+  const uint64_t total = D * chunks_per_row;
+  for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < total;
+       t += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t row = t / chunks_per_row;
+    const uint64_t ci = t - row * chunks_per_row;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (ci < raw_chunks && ci * 64 < N) {
+      const uint64_t src_row = idx ? idx[row] : row;
+      v = ldg_nc_v4(raw + src_row * raw_pitch + ci * 16);
+      uint32_t w[4] = {recode_word(v.x), recode_word(v.y), recode_word(v.z), recode_word(v.w)};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint64_t k0 = ci * 64 + (uint64_t)j * 16;
+        if (k0 >= N) w[j] = 0;
+        else if (k0 + 16 > N) w[j] &= (1u << (2 * (int)(N - k0))) - 1u;
+      }
+      v = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    *reinterpret_cast<uint4*>(gs + row * gs_pitch + ci * 16) = v;
+  }
+}
+
+int launch_build_gs(gpca_ctx* c, const uint8_t* d_raw, size_t raw_pitch, const uint64_t* d_idx, PackedMat gs) {
+  if (gs.rows == 0) return GPCA_OK;
+  const uint64_t total = gs.rows * (gs.pitch / 16);
+  const int threads = 256;
+  const uint64_t blocks = (total + threads - 1) / threads;
+  const int grid = (int)(blocks < (uint64_t)c->sm_count * 16 ? blocks : (uint64_t)c->sm_count * 16);
+  build_gs_kernel<<<grid, threads, 0, c->stream>>>(d_raw, raw_pitch, d_idx, gs.p, gs.pitch, gs.rows, gs.cols);
+  KLAUNCH_CHECK(c);
+  return GPCA_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// 2-bit transpose.  A CTA moves a tile of 128 source rows x 64 source fields through shared
+// memory (one byte per field) and writes, for each of the 64 destination rows, 128 fields = 32 B.
+__global__ void __launch_bounds__(256) transpose2bit_kernel(const uint8_t* __restrict__ src, size_t src_pitch,
+                                                            uint64_t src_rows, uint64_t src_cols,
+                                                            uint8_t* __restrict__ dst, size_t dst_pitch) {
+  __shared__ uint32_t tile[128][17];  // 64 bytes per row (+1 word pad)
+  const uint64_t tiles_c = (src_cols + 63) / 64;
+  const uint64_t tiles_r = (src_rows + 127) / 128;
+  const uint64_t ntiles = tiles_c * tiles_r;
+  for (uint64_t tix = blockIdx.x; tix < ntiles; tix += gridDim.x) {
+    const uint64_t tr = tix / tiles_c, tc = tix - tr * tiles_c;
+    const uint64_t r0 = tr * 128, c0 = tc * 64;
+    // phase 1: 128 threads each load 16 B (64 fields) of one source row and spread to bytes
+    if (threadIdx.x < 128) {
+      const uint64_t r = r0 + threadIdx.x;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (r < src_rows) v = ldg_nc_v4(src + r * src_pitch + c0 / 4);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t b = (w[j] >> (8 * q)) & 0xffu;  // 4 fields
+          tile[threadIdx.x][j * 4 + q] = (b & 3u) | ((b & 0xcu) << 6) | ((b & 0x30u) << 12) | ((b & 0xc0u) << 18);
+        }
+      }
+    }
+    __syncthreads();
+    // phase 2: thread -> (dest row n = tid%64, quarter q = tid/64 of 32 source rows) -> 8 bytes
+    {
+      const int n = threadIdx.x & 63;
+      const int q = threadIdx.x >> 6;
+      const uint8_t* tb = reinterpret_cast<const uint8_t*>(&tile[0][0]);
+      uint32_t lo = 0, hi = 0;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        lo |= (uint32_t)tb[(32 * q + i) * 68 + n] << (2 * i);
+        hi |= (uint32_t)tb[(32 * q + 16 + i) * 68 + n] << (2 * i);
+      }
+      const uint64_t dn = c0 + n;
+      if (dn < src_cols) {
+        uint2* o = reinterpret_cast<uint2*>(dst + dn * dst_pitch + r0 / 4 + 8 * q);
+        *o = make_uint2(lo, hi);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+int launch_transpose(gpca_ctx* c, PackedMat gs, PackedMat gt) {
+  if (gs.rows == 0 || gs.cols == 0) return GPCA_OK;
+  // dst pitch must cover round_up(src_rows,128)/4 bytes (true: pitch is a multiple of 128 B = 512 fields)
+  const uint64_t ntiles = ((gs.cols + 63) / 64) * ((gs.rows + 127) / 128);
+  const int grid = (int)(ntiles < (uint64_t)c->sm_count * 8 ? ntiles : (uint64_t)c->sm_count * 8);
+  // zero the destination first so that pad fields beyond src_rows are 0
+  GPCA_CUDA_TRY(c, cudaMemsetAsync(gt.p, 0, gt.pitch * gt.rows, c->stream));
+  transpose2bit_kernel<<<grid, 256, 0, c->stream>>>(gs.p, gs.pitch, gs.rows, gs.cols, gt.p, gt.pitch);
+  KLAUNCH_CHECK(c);
+  return GPCA_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Accessor parity kernel (prepare.rs:1884-2016): f32 fma standardisation of a gathered block.
+__global__ void std_block_kernel(const uint8_t* __restrict__ gs, size_t pitch, const float* __restrict__ mean,
+                                 const float* __restrict__ sd, const uint64_t* __restrict__ ids, uint64_t n_ids,
+                                 const uint64_t* __restrict__ samp, uint64_t n_samp, float* __restrict__ out,
+                                 int* __restrict__ missing_flag) {
+  const uint64_t total = n_ids * n_samp;
+  for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < total;
+       t += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t i = t / n_samp, j = t - i * n_samp;
+    const uint64_t id = ids[i];
+    const uint64_t s = samp ? samp[j] : j;
+    const uint32_t code = (gs[id * pitch + (s >> 2)] >> (2 * (s & 3))) & 3u;
+    const float m = mean[id], sdev = sd[id];
+    float z = 0.0f;
+    if (code == 3u) {
+      atomicExch(missing_flag, 1);
+    } else if (!(fabsf(sdev) < 1e-9f)) {
+      const float recip = __fdiv_rn(1.0f, sdev);
+      const float bterm = __fmul_rn(-m, recip);
+      z = __fmaf_rn((float)code, recip, bterm);
+    }
+    out[t] = z;
+  }
+}
+
+int launch_std_block(gpca_ctx* c, PackedMat gs, const float* d_mean, const float* d_sd, const uint64_t* d_ids,
+                     uint64_t n_ids, const uint64_t* d_samp, uint64_t n_samp, float* d_out, int* d_missing_flag) {
+  const uint64_t total = n_ids * n_samp;
+  if (total == 0) return GPCA_OK;
+  const int threads = 256;
+  const uint64_t blocks = (total + threads - 1) / threads;
+  const int grid = (int)(blocks < (uint64_t)c->sm_count * 16 ? blocks : (uint64_t)c->sm_count * 16);
+  std_block_kernel<<<grid, threads, 0, c->stream>>>(gs.p, gs.pitch, d_mean, d_sd, d_ids, n_ids, d_samp, n_samp, d_out,
+                                                    d_missing_flag);
+  KLAUNCH_CHECK(c);
+  return GPCA_OK;
+}

@@ -1,0 +1,7 @@
+// sketch_tc.cuh -- tcgen05 / TMEM / TMA engine for the sketch pass (engine 1).
+#pragma once
+#include "kernels.cuh"
+
+// true when the tcgen05 engine can take this problem (shape/alignment); otherwise the SIMT engine runs.
+bool sketch_tc_supported(gpca_ctx* c, const SketchProblem& p);
+int launch_sketch_tc(gpca_ctx* c, const SketchProblem& p);

@@ -1,0 +1,175 @@
+/*
+ * gpca.h -- C ABI of the B200-native hot path of genomic_pca.
+ *
+ * This is the drop-in boundary: exactly the calls the reference's Rust host would bind
+ * through an FFI crate in place of (a) efficient_pca::PCA::{rfit,transform} and
+ * (b) the PcaReadyGenotypeAccessor / EigenSNPCoreAlgorithm::compute_pca pair.
+ * Plain pointers and sizes only; no C++/torch types.  INTEGRATION.md shows the Rust
+ * `extern "C"` block and the two call-site patches.
+ *
+ * Conventions:
+ *   - every function returns 0 on success, <0 on error; gpca_last_error(ctx) gives text;
+ *   - the caller allocates and frees every output buffer; the library owns device memory,
+ *     streams and events inside the opaque context;
+ *   - one context per GPU per process; calls on one context are serialized by the caller;
+ *   - there is NO CPU fallback: every entry point that computes needs an sm_100 device.
+ *   - "host" pointers are ordinary host memory (pinned or pageable); "dev" pointers are
+ *     CUDA device pointers on the context's device.
+ *
+ * Layouts:
+ *   - PLINK payload: SNP-major, row = ceil(N/4) bytes, sample i in bits 2*(i%4) of byte i/4,
+ *     codes 00 -> dosage 2 (hom A1), 01 -> missing, 10 -> 1, 11 -> 0  (bed-reader count_a1,
+ *     reference src/prepare.rs:622-629).
+ *   - all dense matrices are row-major.
+ */
+#ifndef GPCA_H_
+#define GPCA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gpca_ctx gpca_ctx;
+
+enum {
+  GPCA_OK = 0,
+  GPCA_ERR_INVALID = -1,   /* bad argument / wrong call order */
+  GPCA_ERR_CUDA = -2,      /* CUDA runtime error (text in gpca_last_error) */
+  GPCA_ERR_NO_DEVICE = -3, /* no sm_100 device: there is no CPU fallback */
+  GPCA_ERR_MISSING = -4,   /* missing genotype where the reference would error (prepare.rs:1906-1912) */
+  GPCA_ERR_OOM = -5
+};
+
+/* ---- lifetime ------------------------------------------------------------------------ */
+int gpca_init(gpca_ctx** ctx, int device);
+void gpca_destroy(gpca_ctx* ctx);
+const char* gpca_last_error(const gpca_ctx* ctx);
+const char* gpca_version(void);
+/* kernels launched by this context since creation / last reset (bench.py "gpu_launches") */
+uint64_t gpca_launch_count(const gpca_ctx* ctx);
+void gpca_reset_launch_count(gpca_ctx* ctx);
+/* 0 = SIMT fp32 path, 1 = tcgen05 path where the shape allows (default 1) */
+int gpca_set_sketch_engine(gpca_ctx* ctx, int engine);
+/* device time (ms) and algorithmic packed bytes of the sketch passes since the last reset */
+int gpca_sketch_stats(gpca_ctx* ctx, double* ms_total, double* packed_bytes_total, uint64_t* n_passes, int reset);
+
+/* Cross-shard sum hook (multi-GPU, SNP-sharded): called on the context's stream order with a
+ * DEVICE buffer that must be replaced by its sum over all shards (fp32 or fp64).
+ * dtype: 0 = f32, 1 = f64.  Replaces nothing in the reference (single process); it is where
+ * the host binds ncclAllReduce.  NULL (default) = single shard. */
+typedef int (*gpca_allreduce_fn)(void* dev_buf, uint64_t count, int dtype, void* cuda_stream, void* user);
+int gpca_set_allreduce(gpca_ctx* ctx, gpca_allreduce_fn fn, void* user);
+/* global row offset / total of this shard's variants (for shard-independent random streams) */
+int gpca_set_shard(gpca_ctx* ctx, uint64_t variant_offset, uint64_t variants_total);
+
+/* ---- ingest -------------------------------------------------------------------------- */
+/* Replaces IoService + bed-reader reads (src/prepare.rs:169-920, 606-629): the packed payload
+ * (after the 3-byte magic) is copied to the device once.  keep_samples (original FAM indices,
+ * increasing; src/prepare.rs:1058-1096) may be NULL = all samples. */
+int gpca_load_bed(gpca_ctx* ctx, const uint8_t* host_payload, uint64_t n_samples_in_file, uint64_t n_snps,
+                  const int64_t* keep_samples, uint64_t n_keep);
+/* Same, payload already on the device (row pitch = ceil(n_samples/4)); no sample subsetting. */
+int gpca_load_bed_device(gpca_ctx* ctx, const uint8_t* dev_payload, uint64_t n_samples, uint64_t n_snps);
+/* Replaces vcf::matrix_ops::build_matrix (src/vcf.rs:317-345): variant-major u8 dosages
+ * (0,1,2; any other value = missing), D rows of N bytes, as aggregated at src/vcf.rs:293-315. */
+int gpca_load_u8_variant_major(gpca_ctx* ctx, const uint8_t* host_dosage, uint64_t n_samples, uint64_t n_variants);
+
+uint64_t gpca_num_samples(const gpca_ctx* ctx);
+uint64_t gpca_num_snps(const gpca_ctx* ctx);      /* loaded rows (before QC) */
+uint64_t gpca_num_pca_snps(const gpca_ctx* ctx);  /* after gpca_set_pca_snps */
+
+/* ---- statistics / QC ----------------------------------------------------------------- */
+/* Pass 1 of perform_snp_qc_and_calc_std_params (src/prepare.rs:1232-1279): per loaded SNP
+ * n_valid, n(dosage 0), n(dosage 1), n(dosage 2) over the kept samples.  Bit-exact integers. */
+int gpca_snp_counts(gpca_ctx* ctx, uint32_t* n_valid, uint32_t* n0, uint32_t* n1, uint32_t* n2);
+
+typedef struct {
+  double min_call_rate; /* src/main.rs:545  default 0.98 */
+  double min_maf;       /* src/main.rs:548  default 0.01 */
+  double max_hwe_p;     /* src/main.rs:551  default 1e-6 ; >= 1.0 disables */
+} gpca_qc_cfg;
+/* The QC ladder + mean/sigma (src/prepare.rs:1281-1375) in f64 on the host from the integer
+ * counts.  keep[M] (0/1), mean[M], sd[M] (f32, 0 where dropped), fail_code[M] may be NULL.
+ * fail codes: 0 kept, 1 call-rate, 2 no valid, 3 maf, 4 monomorphic, 5 hwe, 6 variance. */
+int gpca_snp_qc(gpca_ctx* ctx, const gpca_qc_cfg* cfg, uint8_t* keep, float* mean, float* sd, uint8_t* fail_code);
+/* VCF-mode filter (src/vcf.rs:244-266): keep iff min(p,1-p) >= maf, p = sum/(2N); variants with
+ * any missing call are dropped (src/vcf.rs:227-242).  mean/sd: column mean, ddof=1 sd
+ * (sd <= 1e-9 -> 1) as rfit standardises. */
+int gpca_vcf_maf_filter(gpca_ctx* ctx, double maf_threshold, uint8_t* keep, float* mean, float* sd);
+/* HWE chi-square p-value alone (src/prepare.rs:1641-1745); pure host arithmetic, exported so
+ * the parity tests can pin it. */
+double gpca_hwe_chi_squared_p_value(uint64_t hom1, uint64_t het, uint64_t hom2);
+
+/* Select the PCA SNP set (PcaSnpId i <-> loaded row snp_idx[i], strictly increasing) with its
+ * standardisation parameters; builds the resident device copies used by every sketch pass.
+ * Mirrors MicroarrayGenotypeAccessor::new (src/prepare.rs:1783-1822). */
+int gpca_set_pca_snps(gpca_ctx* ctx, const uint64_t* snp_idx, uint64_t n_pca_snps, const float* mean, const float* sd);
+
+/* ---- the accessor the GPU path makes unnecessary, kept for parity ---------------------- */
+/* get_standardized_snp_sample_block (src/prepare.rs:1839-2022): out[n_ids x n_samp] row-major
+ * f32, z = fma(x, 1/sd, -mean/sd); sd < 1e-9 -> 0; any missing call -> GPCA_ERR_MISSING. */
+int gpca_get_standardized_block(gpca_ctx* ctx, const uint64_t* pca_snp_ids, uint64_t n_ids,
+                                const uint64_t* qc_sample_ids, uint64_t n_samp, float* host_out);
+
+/* ---- sketch passes (the hot path), device-pointer level -------------------------------- */
+/* S = standardized [D x N] (never materialised).  Missing calls contribute 0.
+ *   snp side   : dev_out[D x l]  = S   * dev_in[N x l]      (reduction over samples)
+ *   sample side: dev_out[N x l]  = S^T * dev_in[D x l]      (reduction over SNPs; summed over
+ *                                                            shards through the allreduce hook)
+ * l <= 64.  ld = row stride in floats of both dense operands. */
+int gpca_sketch_snp_side(gpca_ctx* ctx, const float* dev_in, float* dev_out, uint32_t l, uint32_t ld);
+int gpca_sketch_sample_side(gpca_ctx* ctx, const float* dev_in, float* dev_out, uint32_t l, uint32_t ld);
+int gpca_synchronize(gpca_ctx* ctx);
+
+/* ---- drivers --------------------------------------------------------------------------- */
+/* Replaces pca_runner::run_genomic_pca = PCA::rfit + PCA::transform (src/main.rs:598-679).
+ * scores[N x k_out] f64 row-major (the reference's Array2<f64>), explained variance
+ * eigenvalues[k_out] = s^2/(N-1), loadings[D x k_out] f32 (rotation; may be NULL).
+ * oversample: src/main.rs:636 (10).  has_seed=0 mirrors `--rfit-seed` absent (entropy seed). */
+int gpca_rfit(gpca_ctx* ctx, uint32_t k, uint32_t oversample, uint32_t power_iters, uint64_t seed, int has_seed,
+              double* scores, double* eigenvalues, float* loadings, uint32_t* k_out);
+
+typedef struct {                         /* EigenSNPCoreAlgorithmConfig, src/main.rs:311-327 */
+  uint32_t target_num_global_pcs;        /* --eigensnp-k-global            10    */
+  uint32_t components_per_ld_block;      /* --eigensnp-components-per-block 7    */
+  double subset_factor;                  /* --eigensnp-subset-factor       0.075 */
+  uint64_t min_subset_size;              /* --eigensnp-min-subset-size     10000 */
+  uint64_t max_subset_size;              /* --eigensnp-max-subset-size     40000 */
+  uint32_t global_oversampling;          /* --eigensnp-global-oversampling 10    */
+  uint32_t global_power_iters;           /* --eigensnp-global-power-iter   2     */
+  uint32_t local_oversampling;           /* --eigensnp-local-oversampling  10    */
+  uint32_t local_power_iters;            /* --eigensnp-local-power-iter    2     */
+  uint64_t random_seed;                  /* --eigensnp-seed                2025  */
+  uint32_t snp_processing_strip_size;    /* --eigensnp-snp-strip-size      2000 (accepted, unused: no strips on GPU) */
+  uint32_t refine_pass_count;            /* --eigensnp-refine-passes       1     */
+  uint32_t collect_diagnostics;          /* accepted, ignored */
+} gpca_eigensnp_cfg;
+void gpca_eigensnp_default_cfg(gpca_eigensnp_cfg* cfg);
+
+/* Replaces EigenSNPCoreAlgorithm::compute_pca(&accessor, &ld_block_specifications)
+ * (src/main.rs:365).  Blocks in tag-sorted order; block b owns PcaSnpIds
+ * block_snp_ids[block_offsets[b] .. block_offsets[b+1]) (sorted within a block),
+ * i.e. Vec<LdBlockSpecification> flattened (src/prepare.rs:1526-1549).
+ * scores[N x k_out] f32, eigenvalues[k_out] f64, loadings[D x k_out] f32
+ * (final_sample_principal_component_scores / _eigenvalues / final_snp_principal_component_loadings). */
+int gpca_eigensnp(gpca_ctx* ctx, const gpca_eigensnp_cfg* cfg, const uint64_t* block_offsets, uint64_t n_blocks,
+                  const uint64_t* block_snp_ids, float* scores, double* eigenvalues, float* loadings, uint32_t* k_out);
+
+/* ---- host-side helpers of the path (no GPU needed) -------------------------------------- */
+/* map_snps_to_ld_blocks (src/prepare.rs:1424-1563) over parsed blocks.  Inputs per QC'd SNP
+ * in increasing original index; chromosomes as normalised strings.  Outputs: pca_pos[n_qc]
+ * = PcaSnpId or -1; block_of[n_qc] = index into the tag-sorted block list or -1;
+ * returns number of PCA SNPs through n_pca and number of non-empty blocks through n_blocks_out;
+ * sorted_block_order[n_blocks] maps sorted position -> input block index. */
+int gpca_map_snps_to_ld_blocks(const char* const* snp_chrom, const int32_t* snp_bp, uint64_t n_qc,
+                               const char* const* blk_chrom, const int32_t* blk_start, const int32_t* blk_end,
+                               uint64_t n_blocks, int64_t* pca_pos, int64_t* block_of, uint64_t* n_pca,
+                               uint64_t* n_blocks_out, uint64_t* sorted_block_order);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPCA_H_ */

@@ -1,0 +1,29 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (sm_100a) GPU; run with `pytest -m gpu` on the GPU box")
+
+
+@pytest.fixture(scope="session")
+def golden_rows():
+    z = np.load(os.path.join(GOLDEN, "chr22_subset50_rows.npz"))
+    return {k: z[k] for k in z.files}
+
+
+@pytest.fixture(scope="session")
+def gpu_ctx():
+    import genomic_pca_b200 as gp
+    ctx = gp.Context(0)
+    yield ctx
+    ctx.close()

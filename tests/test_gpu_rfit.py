@@ -1,0 +1,60 @@
+"""GPU parity of the rfit driver: against the oracle's restatement with the same Philox test matrix,
+and against the exact f64 eigen-decomposition.  Tolerances are the north star's:
+eigenvalues 1e-4 relative, principal subspace angles < 1e-3 rad."""
+import numpy as np
+import pytest
+
+from oracle import pca
+
+from helpers import make_dataset, standardized
+
+pytestmark = pytest.mark.gpu
+
+EV_RTOL = 1e-4
+ANGLE_TOL = 1e-3
+
+
+def _prep(ctx, n, m, n_pops, seed, vcf=False):
+    import genomic_pca_b200 as gp
+    g, payload = make_dataset(n, m, n_pops=n_pops, seed=seed)
+    if vcf:
+        ctx.load_u8_variant_major(g.astype(np.uint8))
+        keep, mean, sd = ctx.vcf_maf_filter(0.01)
+    else:
+        ctx.load_bed(payload, n, m)
+        keep, mean, sd, _ = ctx.snp_qc(gp.QcConfig(0.98, 0.01, 1.0))
+    idx = np.nonzero(keep)[0]
+    ctx.set_pca_snps(idx, mean[idx], sd[idx])
+    return standardized(g[idx], mean[idx], sd[idx])
+
+
+@pytest.mark.parametrize("engine", [0, 1])
+@pytest.mark.parametrize("n,m,pops,k", [(600, 4000, 5, 4), (2504, 6000, 6, 5)])
+def test_rfit_matches_oracle_and_exact(gpu_ctx, engine, n, m, pops, k):
+    S = _prep(gpu_ctx, n, m, pops, seed=n, vcf=True)
+    gpu_ctx.set_sketch_engine(engine)
+    sc, ev, ld = gpu_ctx.rfit(k, 10, power_iters=3, seed=42)
+    sc_o, ev_o, ld_o = pca.rfit(S, k, 10, seed=42, power_iters=3)
+    sc_x, ev_x, ld_x = pca.exact_pca(S, k)
+    assert np.abs(ev / ev_o - 1).max() < EV_RTOL
+    assert np.abs(ev / ev_x - 1).max() < EV_RTOL
+    assert pca.subspace_angle(sc, sc_o) < ANGLE_TOL
+    assert pca.subspace_angle(ld, ld_o) < ANGLE_TOL
+    assert pca.subspace_angle(sc, sc_x) < 3e-3     # limited by the randomized method itself (oracle shows the same)
+    # sign convention + column-wise agreement with the oracle
+    assert np.abs(sc - sc_o).max() / np.abs(sc_o).max() < 5e-3
+
+
+def test_rfit_reference_argument_rules(gpu_ctx):
+    import genomic_pca_b200 as gp
+    S = _prep(gpu_ctx, 40, 300, 3, seed=1)
+    with pytest.raises(gp.GpcaError):
+        gpu_ctx.rfit(0)                                   # main.rs:607
+    sc, ev, ld = gpu_ctx.rfit(60, 10, seed=1)             # k capped at min(N, D) = 40 (main.rs:621-628)
+    assert sc.shape[1] == 40 and ev.shape[0] == 40
+    # seeded runs are reproducible, unseeded runs still valid
+    a = gpu_ctx.rfit(3, 10, seed=7)[1]
+    b = gpu_ctx.rfit(3, 10, seed=7)[1]
+    assert np.array_equal(a, b)
+    c = gpu_ctx.rfit(3, 10, seed=None)[1]
+    assert np.all(np.isfinite(c)) and np.abs(c / a - 1).max() < 0.05

@@ -1,0 +1,87 @@
+"""GPU parity of the sketch passes against a dense f64 product with the standardized matrix."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import make_dataset, standardized
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(ctx, n, m, seed, missing_rate=0.0, call_rate=0.9):
+    import genomic_pca_b200 as gp
+    g, payload = make_dataset(n, m, seed=seed, missing_rate=missing_rate)
+    ctx.load_bed(payload, n, m)
+    keep, mean, sd, _ = ctx.snp_qc(gp.QcConfig(call_rate, 0.01, 1.0))
+    idx = np.nonzero(keep)[0]
+    ctx.set_pca_snps(idx, mean[idx], sd[idx])
+    return standardized(g[idx], mean[idx], sd[idx])
+
+
+def _run(ctx, S, l, engine, seed=0):
+    d, n = S.shape
+    r = np.random.default_rng(seed)
+    ctx.set_sketch_engine(engine)
+    y = r.standard_normal((n, l)).astype(np.float32)
+    w = r.standard_normal((d, l)).astype(np.float32)
+    ty = torch.from_numpy(y).cuda()
+    tw = torch.from_numpy(w).cuda()
+    out_d = torch.full((d, l), float("nan"), device="cuda", dtype=torch.float32)
+    out_n = torch.full((n, l), float("nan"), device="cuda", dtype=torch.float32)
+    torch.cuda.synchronize()
+    ctx.sketch_snp_side(ty.data_ptr(), out_d.data_ptr(), l, l)
+    ctx.sketch_sample_side(tw.data_ptr(), out_n.data_ptr(), l, l)
+    ctx.synchronize()
+    ref_d = S @ y.astype(np.float64)
+    ref_n = S.T @ w.astype(np.float64)
+    return out_d.cpu().numpy(), ref_d, out_n.cpu().numpy(), ref_n
+
+
+def _relerr(a, b):
+    return np.abs(a - b).max() / np.abs(b).max()
+
+
+@pytest.mark.parametrize("n,m,l", [(64, 200, 5), (130, 700, 30), (2504, 3000, 30), (1000, 257, 64), (33, 40, 1),
+                                   (5000, 600, 17)])
+def test_sketch_simt_matches_dense(gpu_ctx, n, m, l):
+    S = _setup(gpu_ctx, n, m, seed=n + m)
+    od, rd, on, rn = _run(gpu_ctx, S, l, engine=0)
+    assert _relerr(od, rd) < 2e-5          # fp32 accumulation vs f64
+    assert _relerr(on, rn) < 2e-5
+
+
+def test_sketch_with_missing_calls_mean_imputed(gpu_ctx):
+    S = _setup(gpu_ctx, 300, 500, seed=3, missing_rate=0.02)
+    od, rd, on, rn = _run(gpu_ctx, S, 12, engine=0)
+    assert _relerr(od, rd) < 2e-5
+    assert _relerr(on, rn) < 2e-5
+
+
+def test_sketch_linearity_full_width(gpu_ctx):
+    """Size-independent property: S(aY1 + Y2) = a S Y1 + S Y2 (checked at a larger shape than the oracle needs)."""
+    S = _setup(gpu_ctx, 20000, 4000, seed=8)
+    d, n = S.shape
+    l = 30
+    gpu_ctx.set_sketch_engine(0)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    y1 = torch.randn(n, l, device="cuda", generator=g)
+    y2 = torch.randn(n, l, device="cuda", generator=g)
+    o1 = torch.empty(d, l, device="cuda")
+    o2 = torch.empty(d, l, device="cuda")
+    o3 = torch.empty(d, l, device="cuda")
+    y3 = (0.5 * y1 + y2).contiguous()
+    torch.cuda.synchronize()
+    for a, b in ((y1, o1), (y2, o2), (y3, o3)):
+        gpu_ctx.sketch_snp_side(a.data_ptr(), b.data_ptr(), l, l)
+    gpu_ctx.synchronize()
+    err = (o3 - (0.5 * o1 + o2)).abs().max() / o3.abs().max()
+    assert err < 1e-4
+    # adjointness: <S y, w> == <y, S^T w>
+    w = torch.randn(d, l, device="cuda", generator=g)
+    ow = torch.empty(n, l, device="cuda")
+    torch.cuda.synchronize()
+    gpu_ctx.sketch_sample_side(w.data_ptr(), ow.data_ptr(), l, l)
+    gpu_ctx.synchronize()
+    lhs = (o1.double() * w.double()).sum()
+    rhs = (y1.double() * ow.double()).sum()
+    assert abs(lhs - rhs) / abs(lhs) < 1e-4
