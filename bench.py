@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path (randomized-SVD sketch passes of the rfit PCA) on synthetic data.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--snps M] [--samples N]
+
+One "step" = one complete rfit PCA (1 + 2q + 2 sketch passes over the resident 2-bit matrix, the
+re-orthonormalisations and the small eigensolves) on the workload named in config.workload.
+metric = genotype GB/s per sketch pass = packed genotype bytes streamed by the sketch passes / time.
+  value : inputs resident in HBM when the timed region starts (device-timed, CUDA events, max over ranks)
+  e2e   : the same PCA through the C ABI from HOST buffers (pinned .bed payload -> H2D -> counts ->
+          QC -> resident build -> rfit -> scores back on the host), H2D/D2H inside the timed region.
+N > 1 (torchrun): SNP-sharded, one rank per GPU, weak scaling (per-GPU shard fixed); the N x l sketch
+is summed over ranks with NCCL after every sample-side pass (the path's one exchange step).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DATA_SEED = 20260101
+K_COMPONENTS = 20
+OVERSAMPLE = 10
+POWER_ITERS = 2
+RFIT_SEED = 42
+N_POPS = K_COMPONENTS + 2
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=5)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--samples", type=int, default=2504)
+    p.add_argument("--snps", type=int, default=10_000_000, help="SNPs per GPU (weak scaling)")
+    p.add_argument("--engine", type=int, default=None)
+    p.add_argument("--cpu-snps", type=int, default=150_000, help="SNP rows of the CPU baseline sample")
+    p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-cpu", action="store_true")
+    return p.parse_args()
+
+
+# ------------------------------------------------------------------------------------------
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+def synth_bed_device(torch, n_samples, n_snps, snp_offset, device):
+    """Balding-Nichols genotypes generated on the device straight into PLINK .bed layout
+    (P = k+2 populations, ancestral AF ~ U(0.05,0.5), F_ST = 0.1, no missing calls).
+    Counter-free but shard-reproducible: the generator is re-seeded per 65,536-SNP chunk from
+    (DATA_SEED, global chunk index)."""
+    bps = (n_samples + 3) // 4
+    out = torch.empty((n_snps, bps), dtype=torch.uint8, device=device)
+    pops = (torch.arange(n_samples, device=device) * N_POPS // n_samples)
+    chunk = 65536
+    assert snp_offset % chunk == 0
+    fst = 0.1
+    pad = bps * 4 - n_samples
+    for c0 in range(0, n_snps, chunk):
+        c1 = min(c0 + chunk, n_snps)
+        g = torch.Generator(device=device)
+        g.manual_seed(DATA_SEED * 1000003 + (snp_offset + c0) // chunk)
+        m = c1 - c0
+        p_anc = 0.05 + 0.45 * torch.rand(m, 1, device=device, generator=g)
+        # population frequencies: normal approximation of the Balding-Nichols beta, clipped
+        z = torch.randn(m, N_POPS, device=device, generator=g)
+        p_pop = (p_anc + torch.sqrt(fst * p_anc * (1 - p_anc)) * z).clamp_(0.01, 0.99)
+        p = p_pop[:, pops]                                                   # [m, N]
+        a = (torch.rand(m, n_samples, device=device, generator=g) < p).to(torch.uint8)
+        a += (torch.rand(m, n_samples, device=device, generator=g) < p).to(torch.uint8)   # A1 dosage 0..2
+        code = torch.tensor([3, 2, 0], dtype=torch.uint8, device=device)[a.long()]        # count_a1: 0->11 1->10 2->00
+        if pad:
+            code = torch.cat([code, torch.zeros(m, pad, dtype=torch.uint8, device=device)], 1)
+        code = code.view(m, bps, 4)
+        out[c0:c1] = code[:, :, 0] | (code[:, :, 1] << 2) | (code[:, :, 2] << 4) | (code[:, :, 3] << 6)
+        del p, a, code, z, p_pop
+    return out
+
+
+def cpu_rfit_sample(n_samples, n_snps, steps=1):
+    """The reference's CPU algorithm (oracle restatement: f64 matrix, OpenBLAS GEMMs, numpy QR/eigh)
+    timed on a bounded sample of the same workload.  Returns (seconds per step, passes, bytes per pass)."""
+    from oracle import pca, synth
+    g = np.concatenate([synth.balding_nichols(n_samples, min(20000, n_snps - c0), n_pops=N_POPS, seed=7 + c0)[0]
+                        for c0 in range(0, n_snps, 20000)])
+    mean = g.mean(1)
+    sd = g.std(1, ddof=1)
+    ok = sd > 1e-9
+    g = g[ok]
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        # build_matrix (vcf.rs:317-345: u8 -> f64) + standardise + rfit + transform, as the reference does per run
+        S = pca.standardize_dense(g, mean[ok], sd[ok])
+        pca.rfit(S, K_COMPONENTS, OVERSAMPLE, seed=RFIT_SEED, power_iters=POWER_ITERS)
+    dt = (time.perf_counter() - t0) / steps
+    passes = 2 * POWER_ITERS + 3
+    return dt, passes, g.shape[0] * ((n_samples + 3) // 4)
+
+
+# ------------------------------------------------------------------------------------------
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    per_step = []
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        cpu_rfit_sample(args.samples, args.cpu_snps)
+    for _ in range(args.steps):
+        dt, passes, bpp = cpu_rfit_sample(args.samples, args.cpu_snps)
+        per_step.append(dt)
+    dt = float(np.mean(per_step))
+    val = passes * bpp / dt / 1e9
+    line = {
+        "impl": "reference", "metric": "genotype_GBps_per_sketch_pass", "value": val, "unit": "GB/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"rfit k={K_COMPONENTS} oversample={OVERSAMPLE} q={POWER_ITERS}, "
+                               f"{args.samples} samples x {args.cpu_snps} SNPs (bounded CPU sample of the "
+                               f"1000G-shape config: {args.samples} x {args.snps})",
+                   "passes_per_step": passes},
+        "cpu_baseline": {"value": val, "unit": "GB/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.samples} samples x {args.cpu_snps} SNPs, numpy/OpenBLAS f64 restatement "
+                                   "(reference binary cannot be built here: no cargo/rustc)"},
+        "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, world):
+    import torch
+    import torch.distributed as dist
+    import genomic_pca_b200 as gp
+
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n, m = args.samples, args.snps
+    bps = (n + 3) // 4
+    payload = synth_bed_device(torch, n, m, rank * m, dev)
+    torch.cuda.synchronize()
+
+    ctx = gp.Context(local_rank)
+    if args.engine is not None:
+        ctx.set_sketch_engine(args.engine)
+    if world > 1:
+        def hook(ptr, count, dtype, stream):
+            es = torch.cuda.ExternalStream(stream, device=dev)
+            td = torch.float32 if dtype == 0 else torch.float64
+            iface = {"shape": (count,), "typestr": "<f4" if dtype == 0 else "<f8", "data": (ptr, False), "version": 2}
+            holder = type("P", (), {"__cuda_array_interface__": iface})()
+            t = torch.as_tensor(holder, device=dev)
+            assert t.dtype == td
+            with torch.cuda.stream(es):
+                dist.all_reduce(t)
+        ctx.set_allreduce(hook)
+        ctx.set_shard(rank * m, world * m)
+
+    def prepare_from_device():
+        ctx.load_bed_device(payload.data_ptr(), n, m)
+        keep, mean, sd = ctx.vcf_maf_filter(0.01)
+        idx = np.nonzero(keep)[0]
+        ctx.set_pca_snps(idx, mean[idx], sd[idx])
+        return idx.size
+
+    d_kept = prepare_from_device()
+    passes = 2 * POWER_ITERS + 3
+    bytes_per_pass = d_kept * bps                          # algorithmic: M_loc * ceil(N/4)
+    flops_per_pass = 2.0 * n * d_kept * (K_COMPONENTS + OVERSAMPLE)
+
+    def step():
+        return ctx.rfit(K_COMPONENTS, OVERSAMPLE, power_iters=POWER_ITERS, seed=RFIT_SEED, want_loadings=False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    ctx.sketch_stats(reset=True)
+    ctx.reset_launch_count()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    lib_stream = torch.cuda.ExternalStream(ctx.stream, device=dev)      # the stream the kernels are launched on
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(lib_stream)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        sc, ev, _ = step()
+    ev1.record(lib_stream)
+    barrier()
+    wall = time.perf_counter() - t0
+    dev_s = ev0.elapsed_time(ev1) * 1e-3
+    clocks = sampler.stop()
+    launches = ctx.launch_count
+    sk_ms, sk_bytes, sk_n = ctx.sketch_stats(reset=True)
+    # device time between CUDA events on the library's stream (the wall clock is kept as a cross-check)
+    t_step = torch.tensor([dev_s / args.steps], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_step, op=dist.ReduceOp.MAX)
+    t_step = float(t_step.item())
+    value = world * passes * bytes_per_pass / t_step / 1e9
+
+    # ---- e2e through the C ABI from pinned host memory --------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        host = torch.empty((m, bps), dtype=torch.uint8, pin_memory=True)
+        host.copy_(payload)
+        torch.cuda.synchronize()
+        del payload
+        e2e_steps = max(1, min(args.steps, 3))
+
+        def e2e_step():
+            ctx.load_bed_host_ptr(host.data_ptr(), n, m)
+            keep, mean, sd = ctx.vcf_maf_filter(0.01)
+            idx = np.nonzero(keep)[0]
+            ctx.set_pca_snps(idx, mean[idx], sd[idx])
+            return ctx.rfit(K_COMPONENTS, OVERSAMPLE, power_iters=POWER_ITERS, seed=RFIT_SEED, want_loadings=False)
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            sc2, ev2, _ = e2e_step()
+        barrier()
+        te = (time.perf_counter() - t0) / e2e_steps
+        te_t = torch.tensor([te], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te_t, op=dist.ReduceOp.MAX)
+        te = float(te_t.item())
+        e2e = {"value": world * passes * bytes_per_pass / te / 1e9, "unit": "GB/s",
+               "h2d_bytes_per_step": int(m * bps), "d2h_bytes_per_step": int(n * K_COMPONENTS * 4 + m * 16),
+               "ms_per_step": te * 1e3, "steps": e2e_steps}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk, pk_src = peaks()
+    t_pass = (sk_ms / max(sk_n, 1)) * 1e-3                      # device time of one sketch pass (CUDA events, lib stream)
+    ach_gbs = bytes_per_pass / t_pass / 1e9 if t_pass > 0 else 0.0
+    ach_tf = flops_per_pass / t_pass / 1e12 if t_pass > 0 else 0.0
+    roofline = {"bound": "hbm", "achieved": ach_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": ach_gbs / pk["hbm_gbs"], "traffic": None, "peak_source": pk_src,
+                "kernel": "sketch pass (prep + sketch kernel + split-K reduce)", "ms_per_pass": t_pass * 1e3,
+                "tensor_achieved_tflops": ach_tf, "tensor_frac_of_sustained_bf16": ach_tf / pk["bf16_tflops_sustained"],
+                "sketch_share_of_step": (sk_ms * 1e-3 / args.steps) / t_step}
+    line = {
+        "metric": "genotype_GBps_per_sketch_pass", "value": value, "unit": "GB/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f16xf32acc" if ctx_engine(ctx, args) else "f32",
+        "data": "synthetic",
+        "config": {"workload": f"1000G-shape rfit k={K_COMPONENTS} oversample={OVERSAMPLE} q={POWER_ITERS}: "
+                               f"{n} samples x {m} SNPs per GPU ({d_kept} after MAF 0.01), 2-bit packed, SNP-sharded",
+                   "passes_per_step": passes, "bytes_per_pass": bytes_per_pass,
+                   "l2": "inputs larger than L2 (packed shard >> 126 MB)" if bytes_per_pass > 2e8 else "input fits L2",
+                   "pca_wall_s": t_step, "host_wall_s_per_step": wall / args.steps},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+        "eigenvalues_head": [float(x) for x in ev[:3]],
+    }
+    if not args.no_cpu:
+        dt, cp, cb = cpu_rfit_sample(n, args.cpu_snps)
+        line["cpu_baseline"] = {"value": cp * cb / dt / 1e9, "unit": "GB/s", "cores": os.cpu_count() or 1,
+                                "kind": "port", "sample": f"{n} samples x {args.cpu_snps} SNPs, one rfit "
+                                f"(numpy/OpenBLAS f64 restatement of the reference's CPU path), {dt:.1f} s"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def ctx_engine(ctx, args):
+    return (args.engine if args.engine is not None else int(os.environ.get("GPCA_SKETCH_ENGINE", "1"))) == 1
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        print(json.dumps({"error": "launch with torchrun for --gpus > 1"}))
+        sys.exit(2)
+    run_ours(args, rank, world)
+
+
+if __name__ == "__main__":
+    main()

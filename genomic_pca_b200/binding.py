@@ -102,6 +102,7 @@ _sig("gpca_get_standardized_block", C.c_int, C.c_void_p, _u64p, C.c_uint64, _u64
 _sig("gpca_sketch_snp_side", C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32)
 _sig("gpca_sketch_sample_side", C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32)
 _sig("gpca_synchronize", C.c_int, C.c_void_p)
+_sig("gpca_get_stream", C.c_void_p, C.c_void_p)
 _sig("gpca_rfit", C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_int, _f64p, _f64p, _f32p,
      _u32p)
 _sig("gpca_eigensnp_default_cfg", None, C.POINTER(EigenSnpConfig))
@@ -283,6 +284,10 @@ class Context:
 
     def sketch_sample_side(self, in_ptr: int, out_ptr: int, l: int, ld: int):
         self._chk(lib.gpca_sketch_sample_side(self._h, in_ptr, out_ptr, l, ld))
+
+    @property
+    def stream(self) -> int:
+        return int(lib.gpca_get_stream(self._h) or 0)
 
     def synchronize(self):
         self._chk(lib.gpca_synchronize(self._h))

@@ -79,6 +79,7 @@ extern "C" int gpca_set_shard(gpca_ctx* c, uint64_t off, uint64_t total) {
 extern "C" uint64_t gpca_num_samples(const gpca_ctx* c) { return c ? c->N : 0; }
 extern "C" uint64_t gpca_num_snps(const gpca_ctx* c) { return c ? c->M : 0; }
 extern "C" uint64_t gpca_num_pca_snps(const gpca_ctx* c) { return c ? c->D : 0; }
+extern "C" void* gpca_get_stream(gpca_ctx* c) { return c ? (void*)c->stream : nullptr; }
 extern "C" int gpca_synchronize(gpca_ctx* c) {
   CHECK_CTX(c);
   GPCA_CUDA_TRY(c, cudaStreamSynchronize(c->stream));

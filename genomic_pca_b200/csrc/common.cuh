@@ -104,7 +104,8 @@ struct gpca_ctx {
   DevBuf<double> ws_f64;       // gram partials
   DevBuf<double> ws_cpart;     // column-sum partials
   DevBuf<double> ws_small;     // l x l matrices: G, evals, evecs, T
-  DevBuf<uint8_t> ws_bytes;
+  DevBuf<uint8_t> ws_bytes;    // tcgen05 engine: fp16 B' image
+  bool tc_amax_zeroed = false;
 
   void set_error(const std::string& s) { err = s; }
 };

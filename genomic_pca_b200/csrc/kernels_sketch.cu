@@ -161,18 +161,23 @@ __global__ void sketch_reduce_kernel(const float* __restrict__ partial, int nspl
 }
 
 // ------------------------------------------------------------------------------------------
-// Missing-call correction: out[r,:] += b_r * sum_{k : code(r,k)==3} e_k Bin[k,:]   (warp per row)
+// Missing-call correction (warp per row):
+//   out[r,:] += sum_{k : code(r,k)==3} (b_r e_k - a_r miss_val f_k) Bin[k,:]
+// miss_val = what the engine's product used for a missing field (0: SIMT engine, 3: tcgen05 engine).
 __global__ void __launch_bounds__(256) missing_fix_kernel(const uint8_t* __restrict__ g, size_t pitch, uint64_t rows,
                                                           uint64_t K, const float* __restrict__ bin, uint32_t l,
                                                           uint32_t ld, const float* __restrict__ e,
-                                                          const float* __restrict__ b, float* __restrict__ out,
-                                                          uint32_t ldo) {
+                                                          const float* __restrict__ f, const float* __restrict__ a,
+                                                          const float* __restrict__ b, float miss_val,
+                                                          float* __restrict__ out, uint32_t ldo) {
   const uint64_t warp_id = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
   const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
   const int lane = threadIdx.x & 31;
   const uint64_t words = (K + 15) / 16;
   for (uint64_t r = warp_id; r < rows; r += nwarps) {
     const uint32_t* p = reinterpret_cast<const uint32_t*>(g + r * pitch);
+    const float br = b ? b[r] : 1.0f;
+    const float am = (a ? a[r] : 1.0f) * miss_val;
     float c0 = 0.0f, c1 = 0.0f;
     bool any = false;
     for (uint64_t w0 = 0; w0 < words; w0 += 32) {
@@ -189,16 +194,15 @@ __global__ void __launch_bounds__(256) missing_fix_kernel(const uint8_t* __restr
           const int bit = __ffs(m) - 1;
           m &= m - 1;
           const uint64_t k = (w0 + src) * 16 + (bit >> 1);
-          const float ek = e ? e[k] : 1.0f;
-          if ((uint32_t)lane < l) c0 = fmaf(ek, bin[k * ld + lane], c0);
-          if ((uint32_t)(lane + 32) < l) c1 = fmaf(ek, bin[k * ld + lane + 32], c1);
+          const float wk = br * (e ? e[k] : 1.0f) - am * (f ? f[k] : 1.0f);
+          if ((uint32_t)lane < l) c0 = fmaf(wk, bin[k * ld + lane], c0);
+          if ((uint32_t)(lane + 32) < l) c1 = fmaf(wk, bin[k * ld + lane + 32], c1);
         }
       }
     }
     if (any) {
-      const float br = b ? b[r] : 1.0f;
-      if ((uint32_t)lane < l) out[r * ldo + lane] += br * c0;
-      if ((uint32_t)(lane + 32) < l) out[r * ldo + lane + 32] += br * c1;
+      if ((uint32_t)lane < l) out[r * ldo + lane] += c0;
+      if ((uint32_t)(lane + 32) < l) out[r * ldo + lane + 32] += c1;
     }
   }
 }
@@ -281,8 +285,8 @@ int launch_sketch(gpca_ctx* c, const SketchProblem& p) {
   if (c->any_missing) {
     const uint64_t need = (p.G.rows * 32 + 255) / 256;
     const int grid = (int)(need < (uint64_t)c->sm_count * 8 ? need : (uint64_t)c->sm_count * 8);
-    missing_fix_kernel<<<grid, 256, 0, c->stream>>>(p.G.p, p.G.pitch, p.G.rows, p.G.cols, p.Bin, p.l, p.ld, p.e, p.b,
-                                                    p.out, p.ldo);
+    missing_fix_kernel<<<grid, 256, 0, c->stream>>>(p.G.p, p.G.pitch, p.G.rows, p.G.cols, p.Bin, p.l, p.ld, p.e, p.f,
+                                                    p.a, p.b, done ? 3.0f : 0.0f, p.out, p.ldo);
     KLAUNCH_CHECK(c);
   }
   return GPCA_OK;

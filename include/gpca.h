@@ -123,6 +123,8 @@ int gpca_get_standardized_block(gpca_ctx* ctx, const uint64_t* pca_snp_ids, uint
 int gpca_sketch_snp_side(gpca_ctx* ctx, const float* dev_in, float* dev_out, uint32_t l, uint32_t ld);
 int gpca_sketch_sample_side(gpca_ctx* ctx, const float* dev_in, float* dev_out, uint32_t l, uint32_t ld);
 int gpca_synchronize(gpca_ctx* ctx);
+/* the CUDA stream (cudaStream_t) every kernel of this context is launched on -- for CUDA-event timing */
+void* gpca_get_stream(gpca_ctx* ctx);
 
 /* ---- drivers --------------------------------------------------------------------------- */
 /* Replaces pca_runner::run_genomic_pca = PCA::rfit + PCA::transform (src/main.rs:598-679).

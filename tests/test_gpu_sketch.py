@@ -85,3 +85,23 @@ def test_sketch_linearity_full_width(gpu_ctx):
     lhs = (o1.double() * w.double()).sum()
     rhs = (y1.double() * ow.double()).sum()
     assert abs(lhs - rhs) / abs(lhs) < 1e-4
+
+
+@pytest.mark.parametrize("n,m,l", [(2504, 3000, 30), (700, 1500, 5), (4100, 900, 64), (256, 128 * 3 + 5, 17),
+                                   (20000, 2000, 30)])
+def test_sketch_tcgen05_matches_dense(gpu_ctx, n, m, l):
+    """tcgen05 engine (fp16 operands, fp32 TMEM accumulators): the only rounding is B' -> fp16 (2^-11)."""
+    S = _setup(gpu_ctx, n, m, seed=n + m + 1)
+    od, rd, on, rn = _run(gpu_ctx, S, l, engine=1)
+    assert _relerr(od, rd) < 1.5e-3
+    assert _relerr(on, rn) < 1.5e-3
+    # and it agrees with the SIMT engine to the same level
+    od0, _, on0, _ = _run(gpu_ctx, S, l, engine=0)
+    assert _relerr(od, od0) < 1.5e-3 and _relerr(on, on0) < 1.5e-3
+
+
+def test_sketch_tcgen05_with_missing(gpu_ctx):
+    S = _setup(gpu_ctx, 1500, 1200, seed=5, missing_rate=0.02)
+    od, rd, on, rn = _run(gpu_ctx, S, 20, engine=1)
+    assert _relerr(od, rd) < 1.5e-3
+    assert _relerr(on, rn) < 1.5e-3
