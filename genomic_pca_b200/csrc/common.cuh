@@ -106,6 +106,7 @@ struct gpca_ctx {
   DevBuf<double> ws_small;     // l x l matrices: G, evals, evecs, T
   DevBuf<uint8_t> ws_bytes;    // tcgen05 engine: fp16 B' image
   bool tc_amax_zeroed = false;
+  DevBuf<float> drv_a, drv_b, drv_c, drv_d;   // driver-level dense operands (kept across calls: no per-call cudaMalloc)
 
   void set_error(const std::string& s) { err = s; }
 };

@@ -101,7 +101,7 @@ extern "C" int gpca_rfit(gpca_ctx* c, uint32_t k, uint32_t oversample, uint32_t 
   }
   Small s;
   GPCA_TRY(get_small(c, s));
-  DevBuf<float> Y, Z;
+  DevBuf<float>&Y = c->drv_a, &Z = c->drv_b, &R = c->drv_c, &Sc = c->drv_d;
   GPCA_CUDA_TRY(c, Y.alloc(N * l));
   GPCA_CUDA_TRY(c, Z.alloc(D * l));
   const bool sharded = c->allreduce != nullptr;
@@ -126,7 +126,6 @@ extern "C" int gpca_rfit(gpca_ctx* c, uint32_t k, uint32_t oversample, uint32_t 
   make_rotation_transform_kernel<<<1, 256, 0, c->stream>>>(s.evals, s.evecs, l, k, s.T);
   c->launches++;
   GPCA_CUDA_TRY(c, cudaGetLastError());
-  DevBuf<float> R, Sc;
   GPCA_CUDA_TRY(c, R.alloc(D * k));
   GPCA_CUDA_TRY(c, Sc.alloc(N * k));
   GPCA_TRY(launch_apply_right(c, Z.p, D, l, l, s.T, k, R.p, k));  // rotation = B V_b / s  [D x k]

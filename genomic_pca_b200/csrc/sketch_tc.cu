@@ -29,19 +29,20 @@ constexpr int RT = 2;             // row tiles (of 128 rows) per CTA
 constexpr int STAGE_FIELDS = 256; // K fields per pipeline stage (64 B per row)
 constexpr int CHUNKS = 4;         // 64-field chunks per stage
 constexpr int A_TILE_BYTES = 128 * 64;
-constexpr int NUM_THREADS = 320;  // 10 warps
+constexpr int NUM_THREADS = 352;  // 11 warps
 
 template <int NC>
 struct Cfg {
-  static constexpr int STAGES = (NC == 32) ? 3 : 2;
-  static constexpr int SLOTS = (NC == 32) ? 3 : 2;          // TMEM A slots per row tile
+  static constexpr int SA = (NC == 32) ? 4 : 3;             // packed-A ring depth (the HBM stream)
+  static constexpr int SB = (NC == 32) ? 3 : 2;             // B' ring depth (L2-resident operand)
+  static constexpr int SLOTS = (NC == 32) ? 3 : 2;          // TMEM A slots (each holds both row tiles)
+  static constexpr int A_STAGE_BYTES = RT * A_TILE_BYTES;
   static constexpr int B_STAGE_BYTES = STAGE_FIELDS * NC * 2;
-  static constexpr int STAGE_BYTES = RT * A_TILE_BYTES + B_STAGE_BYTES;
   static constexpr int TMEM_COLS = 256;
   static constexpr int D_COL0 = 0;                          // accumulators: RT * NC columns
   static constexpr int A_COL0 = RT * NC;                    // A slots: RT * SLOTS * 32 columns
   static_assert(RT * NC + RT * SLOTS * 32 <= TMEM_COLS, "TMEM budget");
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = SA * A_STAGE_BYTES + SB * B_STAGE_BYTES + 256 /*barriers*/;
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------
@@ -69,17 +70,30 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.b32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
+constexpr uint64_t L2_EVICT_FIRST = 0x12F0000000000000ull;   // createpolicy encodings (as used by CUTLASS TMA::CacheHintSm90)
+constexpr uint64_t L2_EVICT_LAST = 0x14F0000000000000ull;
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-      "l"(map), "r"(bar), "r"(x), "r"(y)
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(x), "r"(y), "l"(L2_EVICT_FIRST)
       : "memory");
 }
 __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar), "l"(L2_EVICT_LAST)
                : "memory");
 }
 
@@ -154,6 +168,7 @@ struct TcParams {
   uint32_t total_stages;
   uint32_t stages_per_split;
   uint32_t ksplit;
+  uint32_t row_groups;
   uint32_t n_items;
   const float* a;
   const float* b;
@@ -169,16 +184,19 @@ template <int NC>
 __global__ void __launch_bounds__(NUM_THREADS, 2)
 sketch_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
   using C = Cfg<NC>;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  // stage s: [A tile 0][A tile 1][B]
-  const uint32_t bars = smem_base + C::STAGES * C::STAGE_BYTES;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
+  // [A ring: SA x (RT tiles of 128 rows x 64 B)][B ring: SB x B' stage image][barriers]
+  const uint32_t a_ring = smem_base;
+  const uint32_t b_ring = smem_base + C::SA * C::A_STAGE_BYTES;
+  const uint32_t bars = b_ring + C::SB * C::B_STAGE_BYTES;
   // barrier map (8 B each)
-  auto bar_full = [&](int s) { return bars + 8u * s; };
+  auto bar_afull = [&](int s) { return bars + 8u * s; };
   auto bar_aempty = [&](int s) { return bars + 8u * (4 + s); };
-  auto bar_bempty = [&](int s) { return bars + 8u * (8 + s); };
-  auto bar_tfull = [&](int t, int j) { return bars + 8u * (12 + t * 4 + j); };
-  auto bar_tempty = [&](int t, int j) { return bars + 8u * (20 + t * 4 + j); };
+  auto bar_bfull = [&](int s) { return bars + 8u * (8 + s); };
+  auto bar_bempty = [&](int s) { return bars + 8u * (24 + s); };
+  auto bar_tfull = [&](int j) { return bars + 8u * (12 + j); };
+  auto bar_tempty = [&](int j) { return bars + 8u * (20 + j); };
   const uint32_t bar_accfull = bars + 8u * 28;
   const uint32_t bar_accempty = bars + 8u * 29;
   const uint32_t tmem_slot = bars + 8u * 30;   // 4 bytes: TMEM base address
@@ -187,16 +205,18 @@ sketch_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < C::STAGES; ++s) {
-      mbar_init(bar_full(s), 1);
-      mbar_init(bar_aempty(s), 8);
+    for (int s = 0; s < C::SA; ++s) {
+      mbar_init(bar_afull(s), 1);
+      mbar_init(bar_aempty(s), 4 * RT);
+    }
+    for (int s = 0; s < C::SB; ++s) {
+      mbar_init(bar_bfull(s), 1);
       mbar_init(bar_bempty(s), 1);
     }
-    for (int t = 0; t < RT; ++t)
-      for (int j = 0; j < C::SLOTS; ++j) {
-        mbar_init(bar_tfull(t, j), 4);
-        mbar_init(bar_tempty(t, j), 1);
-      }
+    for (int j = 0; j < C::SLOTS; ++j) {
+      mbar_init(bar_tfull(j), 4 * RT);   // every expander warp of both row tiles
+      mbar_init(bar_tempty(j), 1);       // tcgen05.commit
+    }
     mbar_init(bar_accfull, 1);
     mbar_init(bar_accempty, 8);
     fence_barrier_init();
@@ -211,77 +231,94 @@ sketch_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (uint32_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const uint32_t rg = item / p.ksplit, ks = item - rg * p.ksplit;
-        const uint32_t st0 = ks * p.stages_per_split;
-        uint32_t st1 = st0 + p.stages_per_split;
-        if (st1 > p.total_stages) st1 = p.total_stages;
-        const int row0 = (int)(rg * (RT * 128));
-        for (uint32_t st = st0; st < st1; ++st, ++it) {
-          const int s = it % C::STAGES;
-          const uint32_t ph = (it / C::STAGES) & 1u;
+  if (warp == 0 || warp == 10) {
+    // ===================== producers (warp-uniform control flow, one elected lane issues) ==========
+    // warp 0 streams the packed genotype tiles (TMA 2-D, evict-first: read once from HBM);
+    // warp 10 streams the B' image (1-D bulk copies, evict-last: shared by all CTAs through L2).
+    const bool is_a = (warp == 0);
+    uint32_t it = 0;
+    for (uint32_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      const uint32_t ks = item / p.row_groups, rg = item - ks * p.row_groups;
+      const uint32_t st0 = ks * p.stages_per_split;
+      uint32_t st1 = st0 + p.stages_per_split;
+      if (st1 > p.total_stages) st1 = p.total_stages;
+      const int row0 = (int)(rg * (RT * 128));
+      for (uint32_t st = st0; st < st1; ++st, ++it) {
+        if (is_a) {
+          const int s = it % C::SA;
+          const uint32_t ph = (it / C::SA) & 1u;
           mbar_wait(bar_aempty(s), ph ^ 1u);
-          mbar_wait(bar_bempty(s), ph ^ 1u);
-          const uint32_t sbase = smem_base + s * C::STAGE_BYTES;
-          mbar_arrive_expect_tx(bar_full(s), C::STAGE_BYTES);
+          if (elect_one()) {
+            const uint32_t sbase = a_ring + s * C::A_STAGE_BYTES;
+            mbar_arrive_expect_tx(bar_afull(s), C::A_STAGE_BYTES);
 #pragma unroll
-          for (int t = 0; t < RT; ++t)
-            tma_load_2d(sbase + t * A_TILE_BYTES, &tmap, bar_full(s), (int)(st * 64), row0 + t * 128);
-          bulk_load_1d(sbase + RT * A_TILE_BYTES, p.bimg + (size_t)st * STAGE_FIELDS * NC, C::B_STAGE_BYTES, bar_full(s));
+            for (int t = 0; t < RT; ++t)
+              tma_load_2d(sbase + t * A_TILE_BYTES, &tmap, bar_afull(s), (int)(st * 64), row0 + t * 128);
+          }
+        } else {
+          const int s = it % C::SB;
+          const uint32_t ph = (it / C::SB) & 1u;
+          mbar_wait(bar_bempty(s), ph ^ 1u);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(bar_bfull(s), C::B_STAGE_BYTES);
+            bulk_load_1d(b_ring + s * C::B_STAGE_BYTES, p.bimg + (size_t)st * STAGE_FIELDS * NC, C::B_STAGE_BYTES,
+                         bar_bfull(s));
+          }
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
-      // instruction descriptor: D=f32, A=B=f16, K-major both, N=NC, M=128
-      const uint32_t idesc = (1u << 4) | ((uint32_t)(NC >> 3) << 17) | (8u << 24);
-      // B smem descriptor template: K-major, no swizzle; LBO = NC*16 B (next 8-wide K chunk), SBO = 128 B (next 8 n)
-      const uint64_t desc_hi = ((uint64_t)((NC * 16) >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
-      uint32_t it = 0, cit = 0, item_idx = 0;
-      for (uint32_t item = blockIdx.x; item < p.n_items; item += gridDim.x, ++item_idx) {
-        const uint32_t rg = item / p.ksplit, ks = item - rg * p.ksplit;
-        const uint32_t st0 = ks * p.stages_per_split;
-        uint32_t st1 = st0 + p.stages_per_split;
-        if (st1 > p.total_stages) st1 = p.total_stages;
-        mbar_wait(bar_accempty, (item_idx & 1u) ^ 1u);   // previous item's epilogue drained the accumulators
-        tc_fence_after();
-        uint32_t acc_flag = 0;
-        for (uint32_t st = st0; st < st1; ++st, ++it) {
-          const int s = it % C::STAGES;
-          const uint32_t ph = (it / C::STAGES) & 1u;
-          mbar_wait(bar_full(s), ph);
-          const uint32_t bsm = smem_base + s * C::STAGE_BYTES + RT * A_TILE_BYTES;
+    // ===================== MMA issuer (warp-uniform control flow, one elected lane issues) ============
+    // instruction descriptor: D=f32, A=B=f16, K-major both, N=NC, M=128
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(NC >> 3) << 17) | (8u << 24);
+    // B smem descriptor: K-major, no swizzle; LBO = NC*16 B (next 8-wide K chunk), SBO = 128 B (next 8 n), version 1
+    const uint32_t desc_lo_const = (uint32_t)((NC * 16) >> 4) << 16;
+    const uint32_t desc_hi = (uint32_t)(128 >> 4) | (1u << 14);
+    uint32_t it = 0, cit = 0, item_idx = 0;
+    for (uint32_t item = blockIdx.x; item < p.n_items; item += gridDim.x, ++item_idx) {
+      const uint32_t ks = item / p.row_groups;
+      const uint32_t st0 = ks * p.stages_per_split;
+      uint32_t st1 = st0 + p.stages_per_split;
+      if (st1 > p.total_stages) st1 = p.total_stages;
+      mbar_wait(bar_accempty, (item_idx & 1u) ^ 1u);   // previous item's epilogue drained the accumulators
+      tc_fence_after();
+      uint32_t acc_flag = 0;
+      for (uint32_t st = st0; st < st1; ++st, ++it) {
+        const int s = it % C::SB;
+        const uint32_t ph = (it / C::SB) & 1u;
+        mbar_wait(bar_bfull(s), ph);
+        const uint32_t bsm = b_ring + s * C::B_STAGE_BYTES;
 #pragma unroll
-          for (int q = 0; q < CHUNKS; ++q, ++cit) {
-            const int slot = cit % C::SLOTS;
-            const uint32_t sph = (cit / C::SLOTS) & 1u;
+        for (int q = 0; q < CHUNKS; ++q, ++cit) {
+          const int slot = cit % C::SLOTS;
+          const uint32_t sph = (cit / C::SLOTS) & 1u;
+          mbar_wait(bar_tfull(slot), sph);
+          tc_fence_after();
+          if (elect_one()) {
 #pragma unroll
             for (int t = 0; t < RT; ++t) {
-              mbar_wait(bar_tfull(t, slot), sph);
-              tc_fence_after();
               const uint32_t d_t = tmem_base + C::D_COL0 + t * NC;
-              const uint32_t a_t = tmem_base + C::A_COL0 + (t * C::SLOTS + slot) * 32;
+              const uint32_t a_t = tmem_base + C::A_COL0 + (slot * RT + t) * 32;
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const uint32_t baddr = bsm + (uint32_t)((q * 4 + i) * (32 * NC));
-                const uint64_t bdesc = desc_hi | (uint64_t)((baddr >> 4) & 0x3FFFu);
+                const uint64_t bdesc = ((uint64_t)desc_hi << 32) | (uint64_t)(desc_lo_const | ((baddr >> 4) & 0x3FFFu));
                 tc_mma_ts(d_t, a_t + 8 * i, bdesc, idesc, acc_flag | (uint32_t)i);
               }
-              tc_commit(bar_tempty(t, slot));
             }
-            acc_flag = 1;
+            tc_commit(bar_tempty(slot));
           }
-          tc_commit(bar_bempty(s));
+          __syncwarp();
+          acc_flag = 1;
         }
-        tc_commit(bar_accfull);
+        if (elect_one()) tc_commit(bar_bempty(s));
+        __syncwarp();
       }
+      if (elect_one()) tc_commit(bar_accfull);
+      __syncwarp();
     }
-  } else {
+  } else if (warp >= 2 && warp < 10) {
     // ===================== expanders + epilogue =====================
     const int tile = (warp - 2) >> 2;
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may touch
@@ -290,15 +327,15 @@ sketch_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
     const uint32_t sw = (uint32_t)((row_in_tile >> 1) & 3);
     uint32_t it = 0, cit = 0, item_idx = 0;
     for (uint32_t item = blockIdx.x; item < p.n_items; item += gridDim.x, ++item_idx) {
-      const uint32_t rg = item / p.ksplit, ks = item - rg * p.ksplit;
+      const uint32_t ks = item / p.row_groups, rg = item - ks * p.row_groups;
       const uint32_t st0 = ks * p.stages_per_split;
       uint32_t st1 = st0 + p.stages_per_split;
       if (st1 > p.total_stages) st1 = p.total_stages;
       for (uint32_t st = st0; st < st1; ++st, ++it) {
-        const int s = it % C::STAGES;
-        const uint32_t ph = (it / C::STAGES) & 1u;
-        mbar_wait(bar_full(s), ph);
-        const uint32_t arow = smem_base + s * C::STAGE_BYTES + tile * A_TILE_BYTES + row_in_tile * 64;
+        const int s = it % C::SA;
+        const uint32_t ph = (it / C::SA) & 1u;
+        mbar_wait(bar_afull(s), ph);
+        const uint32_t arow = a_ring + s * C::A_STAGE_BYTES + tile * A_TILE_BYTES + row_in_tile * 64;
         uint4 v[CHUNKS];
 #pragma unroll
         for (int q = 0; q < CHUNKS; ++q) {
@@ -318,13 +355,13 @@ sketch_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
           expand_word(v[q].y, r + 8);
           expand_word(v[q].z, r + 16);
           expand_word(v[q].w, r + 24);
-          mbar_wait(bar_tempty(tile, slot), sph ^ 1u);   // MMAs that read this TMEM slot have completed
+          mbar_wait(bar_tempty(slot), sph ^ 1u);   // MMAs that read this TMEM slot have completed
           tc_fence_after();
-          tmem_st32(tmem_base + lane_addr + C::A_COL0 + (tile * C::SLOTS + slot) * 32, r);
+          tmem_st32(tmem_base + lane_addr + C::A_COL0 + (slot * RT + tile) * 32, r);
           tc_wait_st();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_tfull(tile, slot));
+          if (lane == 0) mbar_arrive(bar_tfull(slot));
         }
       }
       // ---- epilogue of this work item ----
@@ -575,6 +612,7 @@ int run_tc(gpca_ctx* c, const SketchProblem& p) {
   tp.total_stages = total_stages;
   tp.stages_per_split = spp;
   tp.ksplit = ksplit;
+  tp.row_groups = row_groups;
   tp.n_items = (uint32_t)n_items64;
   tp.a = p.a;
   tp.b = p.b;
