@@ -42,7 +42,7 @@ struct Cfg {
   static constexpr int D_COL0 = 0;                          // accumulators: RT * NC columns
   static constexpr int A_COL0 = RT * NC;                    // A slots: RT * SLOTS * 32 columns
   static_assert(RT * NC + RT * SLOTS * 32 <= TMEM_COLS, "TMEM budget");
-  static constexpr int SMEM_BYTES = SA * A_STAGE_BYTES + SB * B_STAGE_BYTES + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = SA * A_STAGE_BYTES + SB * B_STAGE_BYTES + 256 /*barriers*/ + 320 /*cvec, scale*/;
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------
@@ -225,9 +225,18 @@ sketch_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
     tmem_alloc(tmem_slot, C::TMEM_COLS);
     tmem_relinquish();
   }
+  // epilogue constants staged once per CTA: cvec[64] and the accumulator scale
+  const uint32_t cvec_smem = bars + 256;
+  if (threadIdx.x >= 64 && threadIdx.x < 128) {
+    const int i = threadIdx.x - 64;
+    reinterpret_cast<float*>(smem_raw + (cvec_smem - smem_base))[i] = (i < NC) ? p.cvec[i] : 0.0f;
+  } else if (threadIdx.x == 128) {
+    reinterpret_cast<float*>(smem_raw + (cvec_smem - smem_base))[64] = p.scales[1];
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  const float s_scale = reinterpret_cast<const float*>(smem_raw + (cvec_smem - smem_base))[64];
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
@@ -365,6 +374,13 @@ sketch_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
         }
       }
       // ---- epilogue of this work item ----
+      const uint64_t r = (uint64_t)rg * (RT * 128) + tile * 128 + row_in_tile;
+      // per-row epilogue factors are fetched before waiting for the accumulators (latency overlaps the MMA drain)
+      float ar = 1.0f, br = 1.0f;
+      if (!p.partial && r < p.rows) {
+        if (p.a) ar = __ldg(p.a + r);
+        if (p.b) br = __ldg(p.b + r);
+      }
       mbar_wait(bar_accfull, item_idx & 1u);
       tc_fence_after();
       uint32_t acc[NC];
@@ -383,9 +399,8 @@ sketch_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_accempty);
-      const uint64_t r = (uint64_t)rg * (RT * 128) + tile * 128 + row_in_tile;
       if (r < p.rows) {
-        const float scale = p.scales[1];
+        const float scale = s_scale;
         if (p.partial) {
           float* dst = p.partial + ((uint64_t)ks * p.rows + r) * NC;
 #pragma unroll
@@ -398,12 +413,26 @@ sketch_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
             *reinterpret_cast<float4*>(dst + cidx) = o;
           }
         } else {
-          const float ar = (p.a ? p.a[r] : 1.0f) * scale;
-          const float br = p.b ? p.b[r] : 1.0f;
+          const float as = ar * scale;
           float* dst = p.out + r * p.ldo;
+          const float* cv = reinterpret_cast<const float*>(smem_raw + (cvec_smem - smem_base));
+          if ((p.ldo & 1u) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 7) == 0) {
 #pragma unroll
-          for (int cidx = 0; cidx < NC; ++cidx)
-            if ((uint32_t)cidx < p.l) dst[cidx] = ar * __uint_as_float(acc[cidx]) - br * p.cvec[cidx];
+            for (int cidx = 0; cidx < NC; cidx += 2) {
+              if ((uint32_t)cidx + 1 < p.l) {
+                float2 o;
+                o.x = as * __uint_as_float(acc[cidx]) - br * cv[cidx];
+                o.y = as * __uint_as_float(acc[cidx + 1]) - br * cv[cidx + 1];
+                *reinterpret_cast<float2*>(dst + cidx) = o;
+              } else if ((uint32_t)cidx < p.l) {
+                dst[cidx] = as * __uint_as_float(acc[cidx]) - br * cv[cidx];
+              }
+            }
+          } else {
+#pragma unroll
+            for (int cidx = 0; cidx < NC; ++cidx)
+              if ((uint32_t)cidx < p.l) dst[cidx] = as * __uint_as_float(acc[cidx]) - br * cv[cidx];
+          }
         }
       }
     }
