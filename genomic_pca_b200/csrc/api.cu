@@ -346,7 +346,7 @@ extern "C" int gpca_get_standardized_block(gpca_ctx* c, const uint64_t* ids, uin
 }
 
 // ---- sketch passes ---------------------------------------------------------------------------------
-static int timed_sketch(gpca_ctx* c, const SketchProblem& p) {
+int timed_sketch(gpca_ctx* c, const SketchProblem& p) {
   cudaEvent_t e0, e1;
   GPCA_CUDA_TRY(c, cudaEventCreate(&e0));
   GPCA_CUDA_TRY(c, cudaEventCreate(&e1));

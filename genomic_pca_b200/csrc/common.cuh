@@ -58,6 +58,7 @@ struct PackedMat {
   size_t pitch = 0;      // bytes per row
   uint64_t rows = 0;     // logical rows
   uint64_t cols = 0;     // logical 2-bit fields per row
+  size_t avail = 0;      // bytes readable from p to the end of the physical row (0 = pitch); views set it
 };
 
 struct gpca_ctx {

@@ -1,0 +1,28 @@
+// driver_util.cuh -- helpers shared by the PCA drivers (drivers.cu, eigensnp.cu).
+#pragma once
+#include <vector>
+
+#include "kernels.cuh"
+
+struct Small {  // f64 scratch for l x l work, all on device
+  double *G, *evals, *evecs, *T;
+};
+int get_small(gpca_ctx* c, Small& s);
+
+// Orthonormalise the columns of Y [n x l] in place: two rounds of  G = Y^T Y = V L V^T ; Y <- Y V L^-1/2
+// (eigen-based CholeskyQR2 variant; rank-deficient directions are zeroed instead of breaking a Cholesky).
+// `sharded`: rows of Y are split across shards -> the l x l Gram is summed through the allreduce hook.
+int orthonormalize(gpca_ctx* c, float* y, uint64_t n, uint32_t l, uint32_t ld, bool sharded, const Small& s);
+
+// t [l x k] = evecs[:, :k] * diag(evals[:k]^-1/2)  (inv_sqrt) or evecs[:, :k] (plain)
+int launch_rotation_transform(gpca_ctx* c, const double* evals, const double* evecs, uint32_t l, uint32_t k, double* t,
+                              bool inv_sqrt);
+
+void fix_signs_host(std::vector<float>& scores, uint64_t n, uint32_t k, std::vector<int>& flip);
+
+int driver_allreduce(gpca_ctx* c, void* buf, uint64_t count, int dtype);
+
+int sketch_snp_side(gpca_ctx* c, const float* dev_in, float* dev_out, uint32_t l, uint32_t ld_in, uint32_t ld_out);
+int sketch_sample_side(gpca_ctx* c, const float* dev_in, float* dev_out, uint32_t l, uint32_t ld_in, uint32_t ld_out);
+// generic timed sketch on an arbitrary view (used by the EigenSNP driver)
+int timed_sketch(gpca_ctx* c, const SketchProblem& p);

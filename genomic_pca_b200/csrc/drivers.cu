@@ -1,30 +1,21 @@
-// drivers.cu -- PCA drivers built from the sketch passes:
-//   gpca_rfit     replaces pca_runner::run_genomic_pca = PCA::rfit + PCA::transform (src/main.rs:598-679)
-//   gpca_eigensnp replaces EigenSNPCoreAlgorithm::compute_pca (src/main.rs:359-366)
-// The arithmetic of both lives in the external efficient_pca crate (parity unpinned); the stage
-// order implemented here is the one restated in oracle/pca.py, which the tests check it against.
+// drivers.cu -- the rfit PCA driver built from the sketch passes, plus helpers shared with eigensnp.cu.
+//   gpca_rfit replaces pca_runner::run_genomic_pca = PCA::rfit + PCA::transform (src/main.rs:598-679)
+// The arithmetic lives in the external efficient_pca crate (parity unpinned); the stage order implemented
+// here is the one restated in oracle/pca.py::rfit, which the tests check it against.
 #include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstring>
 #include <random>
 
-#include "kernels.cuh"
-
-int sketch_snp_side(gpca_ctx* c, const float* dev_in, float* dev_out, uint32_t l, uint32_t ld_in, uint32_t ld_out);
-int sketch_sample_side(gpca_ctx* c, const float* dev_in, float* dev_out, uint32_t l, uint32_t ld_in, uint32_t ld_out);
+#include "driver_util.cuh"
 
 static int fail(gpca_ctx* c, int code, const std::string& msg) {
   c->set_error(msg);
   return code;
 }
 
-namespace {
 constexpr uint32_t STREAM_RFIT_OMEGA = 1;
-
-struct Small {  // f64 scratch for l x l work, all on device
-  double *G, *evals, *evecs, *T;
-};
 
 int get_small(gpca_ctx* c, Small& s) {
   GPCA_CUDA_TRY(c, c->ws_small.alloc(4 * 64 * 64));
@@ -35,15 +26,17 @@ int get_small(gpca_ctx* c, Small& s) {
   return GPCA_OK;
 }
 
-// Orthonormalise the columns of Y [n x l] in place: two rounds of  G = Y^T Y = V L V^T ; Y <- Y V L^-1/2
-// (eigen-based CholeskyQR2 variant; rank-deficient directions are zeroed instead of breaking a Cholesky).
-// `sharded`: rows of Y are split across shards -> the l x l Gram is summed through the allreduce hook.
+int driver_allreduce(gpca_ctx* c, void* buf, uint64_t count, int dtype) {
+  if (!c->allreduce) return GPCA_OK;
+  if (c->allreduce(buf, count, dtype, (void*)c->stream, c->allreduce_user) != 0)
+    return fail(c, GPCA_ERR_CUDA, "allreduce hook failed");
+  return GPCA_OK;
+}
+
 int orthonormalize(gpca_ctx* c, float* y, uint64_t n, uint32_t l, uint32_t ld, bool sharded, const Small& s) {
   for (int rep = 0; rep < 2; ++rep) {
     GPCA_TRY(launch_gram(c, y, n, l, ld, s.G));
-    if (sharded && c->allreduce)
-      if (c->allreduce(s.G, (uint64_t)l * l, 1, (void*)c->stream, c->allreduce_user) != 0)
-        return fail(c, GPCA_ERR_CUDA, "allreduce hook failed");
+    if (sharded) GPCA_TRY(driver_allreduce(c, s.G, (uint64_t)l * l, 1));
     GPCA_TRY(launch_jacobi_eigh(c, s.G, l, s.evals, s.evecs));
     GPCA_TRY(launch_make_orth_transform(c, s.evals, s.evecs, l, s.T, rep == 0 ? 1e-11 : 1e-13));
     GPCA_TRY(launch_apply_right(c, y, n, l, ld, s.T, l, y, ld));
@@ -51,14 +44,22 @@ int orthonormalize(gpca_ctx* c, float* y, uint64_t n, uint32_t l, uint32_t ld, b
   return GPCA_OK;
 }
 
-__global__ void make_rotation_transform_kernel(const double* evals, const double* evecs, uint32_t l, uint32_t k,
-                                               double* t) {
-  // t [l x k] = evecs[:, :k] / sqrt(evals[:k])
+__global__ void rotation_transform_kernel(const double* evals, const double* evecs, uint32_t l, uint32_t k, double* t,
+                                          int inv_sqrt) {
   for (int i = threadIdx.x; i < (int)(l * k); i += blockDim.x) {
     const int r = i / k, j = i % k;
     const double lam = evals[j];
-    t[i] = lam > 0.0 ? evecs[r * l + j] / sqrt(lam) : 0.0;
+    const double v = evecs[r * l + j];
+    t[i] = inv_sqrt ? (lam > 0.0 ? v / sqrt(lam) : 0.0) : v;
   }
+}
+
+int launch_rotation_transform(gpca_ctx* c, const double* evals, const double* evecs, uint32_t l, uint32_t k, double* t,
+                              bool inv_sqrt) {
+  rotation_transform_kernel<<<1, 256, 0, c->stream>>>(evals, evecs, l, k, t, inv_sqrt ? 1 : 0);
+  c->launches++;
+  GPCA_CUDA_TRY(c, cudaGetLastError());
+  return GPCA_OK;
 }
 
 void fix_signs_host(std::vector<float>& scores, uint64_t n, uint32_t k, std::vector<int>& flip) {
@@ -79,7 +80,6 @@ void fix_signs_host(std::vector<float>& scores, uint64_t n, uint32_t k, std::vec
     }
   }
 }
-}  // namespace
 
 extern "C" int gpca_rfit(gpca_ctx* c, uint32_t k, uint32_t oversample, uint32_t power_iters, uint64_t seed,
                          int has_seed, double* scores, double* eigenvalues, float* loadings, uint32_t* k_out) {
@@ -104,7 +104,6 @@ extern "C" int gpca_rfit(gpca_ctx* c, uint32_t k, uint32_t oversample, uint32_t 
   DevBuf<float>&Y = c->drv_a, &Z = c->drv_b, &R = c->drv_c, &Sc = c->drv_d;
   GPCA_CUDA_TRY(c, Y.alloc(N * l));
   GPCA_CUDA_TRY(c, Z.alloc(D * l));
-  const bool sharded = c->allreduce != nullptr;
 
   // Y = S^T Omega
   GPCA_TRY(launch_gaussian(c, Z.p, D, l, l, seed, STREAM_RFIT_OMEGA, c->shard_offset));
@@ -119,13 +118,9 @@ extern "C" int gpca_rfit(gpca_ctx* c, uint32_t k, uint32_t oversample, uint32_t 
   GPCA_TRY(orthonormalize(c, Y.p, N, l, l, false, s));
   GPCA_TRY(sketch_snp_side(c, Y.p, Z.p, l, l, l));        // B = S Q   [D x l]
   GPCA_TRY(launch_gram(c, Z.p, D, l, l, s.G));
-  if (sharded)
-    if (c->allreduce(s.G, (uint64_t)l * l, 1, (void*)c->stream, c->allreduce_user) != 0)
-      return fail(c, GPCA_ERR_CUDA, "allreduce hook failed");
+  GPCA_TRY(driver_allreduce(c, s.G, (uint64_t)l * l, 1));
   GPCA_TRY(launch_jacobi_eigh(c, s.G, l, s.evals, s.evecs));
-  make_rotation_transform_kernel<<<1, 256, 0, c->stream>>>(s.evals, s.evecs, l, k, s.T);
-  c->launches++;
-  GPCA_CUDA_TRY(c, cudaGetLastError());
+  GPCA_TRY(launch_rotation_transform(c, s.evals, s.evecs, l, k, s.T, true));
   GPCA_CUDA_TRY(c, R.alloc(D * k));
   GPCA_CUDA_TRY(c, Sc.alloc(N * k));
   GPCA_TRY(launch_apply_right(c, Z.p, D, l, l, s.T, k, R.p, k));  // rotation = B V_b / s  [D x k]

@@ -183,6 +183,7 @@ __global__ void __launch_bounds__(256) missing_fix_kernel(const uint8_t* __restr
     for (uint64_t w0 = 0; w0 < words; w0 += 32) {
       const uint64_t wi = w0 + lane;
       uint32_t w = (wi < words) ? p[wi] : 0u;
+      if (wi + 1 == words && (K & 15)) w &= (1u << (2 * (int)(K & 15))) - 1u;   // a view's last word may hold a neighbour's fields
       uint32_t miss = w & (w >> 1) & 0x55555555u;
       unsigned ballot = __ballot_sync(0xffffffffu, miss != 0u);
       while (ballot) {

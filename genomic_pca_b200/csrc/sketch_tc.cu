@@ -574,7 +574,8 @@ EncodeTiledFn get_encode_fn() {
 bool make_tmap(const PackedMat& g, CUtensorMap* map) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return false;
-  const cuuint64_t dims[2] = {(cuuint64_t)g.pitch, (cuuint64_t)g.rows};
+  // a K-range view starts inside a physical row: only `avail` bytes belong to it (the rest is zero-filled by TMA)
+  const cuuint64_t dims[2] = {(cuuint64_t)(g.avail ? g.avail : g.pitch), (cuuint64_t)g.rows};
   const cuuint64_t strides[1] = {(cuuint64_t)g.pitch};
   const cuuint32_t box[2] = {64, 128};
   const cuuint32_t estr[2] = {1, 1};
@@ -682,7 +683,7 @@ bool sketch_tc_supported(gpca_ctx* c, const SketchProblem& p) {
   (void)c;
   if (p.l == 0 || p.l > 64) return false;
   if (p.G.rows < 128 || p.G.cols < 256) return false;      // tiny problems: SIMT engine
-  if (p.G.pitch % 16 != 0 || (reinterpret_cast<uintptr_t>(p.G.p) & 127) != 0) return false;
+  if (p.G.pitch % 16 != 0 || (reinterpret_cast<uintptr_t>(p.G.p) & 15) != 0) return false;   // TMA: 16 B
   if (p.G.pitch >= (1ull << 31) || p.G.rows >= (1ull << 31)) return false;
   return get_encode_fn() != nullptr;
 }

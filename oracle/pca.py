@@ -156,7 +156,7 @@ def _rsvd_left_basis(x, c, oversample, q, seed, stream):
 def eigensnp(S, block_snp_ids, *, k=10, components_per_block=7, subset_factor=0.075,
              min_subset=10_000, max_subset=40_000, global_oversampling=10, global_power_iters=2,
              local_oversampling=10, local_power_iters=2, seed=2025, refine_passes=1,
-             return_intermediates=False):
+             return_intermediates=False, snp_id_offset=0):
     """EigenSNP restatement (effective defaults: src/main.rs:545-588, tests/sweep_run.py:24-47).
     S: [D, N] standardized in PcaSnpId order; block_snp_ids: list of id arrays (tag-sorted)."""
     S = np.asarray(S, dtype=np.float64)
@@ -165,12 +165,15 @@ def eigensnp(S, block_snp_ids, *, k=10, components_per_block=7, subset_factor=0.
     ssub = S[:, sub]
     feats = []
     bases = []
+    keys = []
     for p, ids in enumerate(block_snp_ids):
         ids = np.asarray(ids, dtype=np.int64)
-        up = _rsvd_left_basis(ssub[ids], components_per_block, local_oversampling,
-                              local_power_iters, seed, STREAM_EIGENSNP_LOCAL0 + p)
+        first = int(ids[0]) + snp_id_offset      # streams are keyed by the block's first (global) PcaSnpId,
+        up = _rsvd_left_basis(ssub[ids], components_per_block, local_oversampling,   # so any sharding of blocks
+                              local_power_iters, seed, (STREAM_EIGENSNP_LOCAL0 + first) & 0xFFFFFFFF)  # agrees
         bases.append(up)
         feats.append(up.T @ S[ids])             # [c_p, N]
+        keys.extend(first * 64 + j for j in range(up.shape[1]))
     c = np.concatenate(feats, axis=0)           # [R, N]
     cm = c.mean(axis=1, keepdims=True)
     cs = c.std(axis=1, ddof=1, keepdims=True)
@@ -178,7 +181,7 @@ def eigensnp(S, block_snp_ids, *, k=10, components_per_block=7, subset_factor=0.
     r = cz.shape[0]
     lg = min(k + global_oversampling, r, n)
     kk = min(k, lg)
-    omega = rng.gaussian_matrix(seed, STREAM_EIGENSNP_GLOBAL, 0, r, lg)
+    omega = rng.gaussian_rows(seed, STREAM_EIGENSNP_GLOBAL, np.array(keys, dtype=np.uint64), lg)
     y = cz.T @ omega
     for _ in range(global_power_iters):
         q = orth(y)

@@ -55,6 +55,17 @@ def gaussian_matrix(seed: int, stream: int, row0: int, n_rows: int, n_cols: int)
     return np.sqrt(-2.0 * np.log(u1)) * np.cos(2.0 * np.pi * u2)
 
 
+def gaussian_rows(seed: int, stream: int, row_keys: np.ndarray, n_cols: int) -> np.ndarray:
+    """Same generator with an explicit 64-bit key per row (EigenSNP condensed-feature test matrix)."""
+    rows = np.asarray(row_keys, dtype=np.uint64)[:, None]
+    cols = np.arange(n_cols, dtype=np.uint64)[None, :]
+    x0, x1, _, _ = philox4x32_10(rows & _MASK, rows >> np.uint64(32), cols, np.uint64(stream),
+                                 seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    u1 = ((x0 >> np.uint32(8)).astype(np.float64) + 0.5) * (1.0 / 16777216.0)
+    u2 = (x1 >> np.uint32(8)).astype(np.float64) * (1.0 / 16777216.0)
+    return np.sqrt(-2.0 * np.log(u1)) * np.cos(2.0 * np.pi * u2)
+
+
 def subset_keys(seed: int, stream: int, n: int) -> np.ndarray:
     """uint32 key per sample used to pick the EigenSNP local-basis subset."""
     idx = np.arange(n, dtype=np.uint64)
