@@ -110,19 +110,17 @@ class ClockSampler:
 def synth_bed_device(torch, n_samples, n_snps, snp_offset, device):
     """Balding-Nichols genotypes generated on the device straight into PLINK .bed layout
     (P = k+2 populations, ancestral AF ~ U(0.05,0.5), F_ST = 0.1, no missing calls).
-    Counter-free but shard-reproducible: the generator is re-seeded per 65,536-SNP chunk from
-    (DATA_SEED, global chunk index)."""
+    The generator is re-seeded per 65,536-SNP chunk from (DATA_SEED, shard offset, chunk index)."""
     bps = (n_samples + 3) // 4
     out = torch.empty((n_snps, bps), dtype=torch.uint8, device=device)
     pops = (torch.arange(n_samples, device=device) * N_POPS // n_samples)
     chunk = 65536
-    assert snp_offset % chunk == 0
     fst = 0.1
     pad = bps * 4 - n_samples
     for c0 in range(0, n_snps, chunk):
         c1 = min(c0 + chunk, n_snps)
         g = torch.Generator(device=device)
-        g.manual_seed(DATA_SEED * 1000003 + (snp_offset + c0) // chunk)
+        g.manual_seed(DATA_SEED * 1000003 + (snp_offset // chunk) * 7919 + c0 // chunk)
         m = c1 - c0
         p_anc = 0.05 + 0.45 * torch.rand(m, 1, device=device, generator=g)
         # population frequencies: normal approximation of the Balding-Nichols beta, clipped
