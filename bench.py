@@ -114,7 +114,7 @@ def synth_bed_device(torch, n_samples, n_snps, snp_offset, device):
     bps = (n_samples + 3) // 4
     out = torch.empty((n_snps, bps), dtype=torch.uint8, device=device)
     pops = (torch.arange(n_samples, device=device) * N_POPS // n_samples)
-    chunk = 65536
+    chunk = int(min(65536, max(64, (1 << 27) // max(n_samples, 1))))   # ~128M genotypes of temporaries per chunk
     fst = 0.1
     pad = bps * 4 - n_samples
     for c0 in range(0, n_snps, chunk):

@@ -85,10 +85,11 @@ __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarr
 
 constexpr uint64_t L2_EVICT_FIRST = 0x12F0000000000000ull;   // createpolicy encodings (as used by CUTLASS TMA::CacheHintSm90)
 constexpr uint64_t L2_EVICT_LAST = 0x14F0000000000000ull;
+constexpr uint64_t L2_EVICT_NORMAL = 0x1000000000000000ull;
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
-      "l"(map), "r"(bar), "r"(x), "r"(y), "l"(L2_EVICT_FIRST)
+      "l"(map), "r"(bar), "r"(x), "r"(y), "l"(L2_EVICT_NORMAL)
       : "memory");
 }
 __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -151,7 +152,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 // 16 fields of a 32-bit word -> 8 registers of fp16x2 subnormals (column c holds fields (c, c+8);
 // scale class of column c = {0,1,2,3,4,2,3,4}[c], value = code * 2^-24 * 4^class)
 __device__ __forceinline__ void expand_word(uint32_t w, uint32_t* r) {
-  const uint32_t u = w >> 6;
+  const uint32_t u = __umulhi(w, 1u << 26);   // = w >> 6, but on the FMA pipe (IMAD.HI): the ALU pipe is the co-limiter
   r[0] = w & 0x00030003u;
   r[1] = w & 0x000C000Cu;
   r[2] = w & 0x00300030u;
@@ -355,22 +356,39 @@ sketch_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_aempty(s));   // packed bytes are in registers: the stage may be refilled
+        // two chunks per completion wait: the second chunk's expansion overlaps the first TMEM store in flight,
+        // and one tcgen05.wait::st covers both stores before the two slots are published to the MMA issuer
 #pragma unroll
-        for (int q = 0; q < CHUNKS; ++q, ++cit) {
-          const int slot = cit % C::SLOTS;
-          const uint32_t sph = (cit / C::SLOTS) & 1u;
-          uint32_t r[32];
-          expand_word(v[q].x, r + 0);
-          expand_word(v[q].y, r + 8);
-          expand_word(v[q].z, r + 16);
-          expand_word(v[q].w, r + 24);
-          mbar_wait(bar_tempty(slot), sph ^ 1u);   // MMAs that read this TMEM slot have completed
-          tc_fence_after();
-          tmem_st32(tmem_base + lane_addr + C::A_COL0 + (slot * RT + tile) * 32, r);
+        for (int q = 0; q < CHUNKS; q += 2, cit += 2) {
+          const int slot0 = cit % C::SLOTS, slot1 = (cit + 1) % C::SLOTS;
+          const uint32_t sph0 = (cit / C::SLOTS) & 1u, sph1 = ((cit + 1) / C::SLOTS) & 1u;
+          {
+            uint32_t r[32];
+            expand_word(v[q].x, r + 0);
+            expand_word(v[q].y, r + 8);
+            expand_word(v[q].z, r + 16);
+            expand_word(v[q].w, r + 24);
+            mbar_wait(bar_tempty(slot0), sph0 ^ 1u);   // MMAs that read this TMEM slot have completed
+            tc_fence_after();
+            tmem_st32(tmem_base + lane_addr + C::A_COL0 + (slot0 * RT + tile) * 32, r);
+          }
+          {
+            uint32_t r[32];
+            expand_word(v[q + 1].x, r + 0);
+            expand_word(v[q + 1].y, r + 8);
+            expand_word(v[q + 1].z, r + 16);
+            expand_word(v[q + 1].w, r + 24);
+            mbar_wait(bar_tempty(slot1), sph1 ^ 1u);
+            tc_fence_after();
+            tmem_st32(tmem_base + lane_addr + C::A_COL0 + (slot1 * RT + tile) * 32, r);
+          }
           tc_wait_st();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_tfull(slot));
+          if (lane == 0) {
+            mbar_arrive(bar_tfull(slot0));
+            mbar_arrive(bar_tfull(slot1));
+          }
         }
       }
       // ---- epilogue of this work item ----
@@ -580,7 +598,7 @@ bool make_tmap(const PackedMat& g, CUtensorMap* map) {
   const cuuint32_t box[2] = {64, 128};
   const cuuint32_t estr[2] = {1, 1};
   return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)g.p, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-             CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
