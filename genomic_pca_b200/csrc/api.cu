@@ -7,6 +7,7 @@
 
 #include "host_qc.h"
 #include "kernels.cuh"
+#include "parallel_for.h"
 
 #define CHECK_CTX(c) \
   if (!(c)) return GPCA_ERR_INVALID;
@@ -204,14 +205,19 @@ static int ensure_counts(gpca_ctx* c) {
   GPCA_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   const uint32_t pad = (uint32_t)(c->raw_pitch * 4 - c->N);  // pad fields were written as 01
   c->h_counts.resize(M * 4);
-  for (uint64_t j = 0; j < M; ++j) {
-    const uint32_t miss = h[j].x - pad, het = h[j].y, d0 = h[j].z;
-    const uint32_t nv = (uint32_t)c->N - miss;
-    c->h_counts[4 * j + 0] = nv;
-    c->h_counts[4 * j + 1] = d0;             // code 11 -> dosage 0
-    c->h_counts[4 * j + 2] = het;            // code 10 -> dosage 1
-    c->h_counts[4 * j + 3] = nv - d0 - het;  // code 00 -> dosage 2
-  }
+  uint32_t* hc = c->h_counts.data();
+  const uint32_t n32 = (uint32_t)c->N;
+  const uint4* hp = h.data();
+  parallel_for(M, [=](uint64_t lo, uint64_t hi) {
+    for (uint64_t j = lo; j < hi; ++j) {
+      const uint32_t miss = hp[j].x - pad, het = hp[j].y, d0 = hp[j].z;
+      const uint32_t nv = n32 - miss;
+      hc[4 * j + 0] = nv;
+      hc[4 * j + 1] = d0;             // code 11 -> dosage 0
+      hc[4 * j + 2] = het;            // code 10 -> dosage 1
+      hc[4 * j + 3] = nv - d0 - het;  // code 00 -> dosage 2
+    }
+  });
   c->have_counts = true;
   return GPCA_OK;
 }

@@ -126,24 +126,25 @@ extern "C" int gpca_rfit(gpca_ctx* c, uint32_t k, uint32_t oversample, uint32_t 
   GPCA_TRY(launch_apply_right(c, Z.p, D, l, l, s.T, k, R.p, k));  // rotation = B V_b / s  [D x k]
   GPCA_TRY(sketch_sample_side(c, R.p, Sc.p, k, k, k));            // transform(): scores = S^T rotation
 
+  // sign convention, f32 -> f64 conversion and the flips of the loadings all happen on the device;
+  // the host only receives the final buffers
   std::vector<double> h_ev(l);
-  std::vector<float> h_sc(N * k);
+  DevBuf<int> d_flags;
+  GPCA_CUDA_TRY(c, d_flags.alloc(64));
+  GPCA_TRY(launch_sign_flags(c, Sc.p, N, k, k, d_flags.p));
   GPCA_CUDA_TRY(c, cudaMemcpyAsync(h_ev.data(), s.evals, l * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  GPCA_CUDA_TRY(c, cudaMemcpyAsync(h_sc.data(), Sc.p, N * k * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  if (scores) {
+    GPCA_CUDA_TRY(c, c->ws_f64.alloc(N * k));
+    GPCA_TRY(launch_apply_flags(c, Sc.p, N, k, k, d_flags.p, nullptr, c->ws_f64.p));
+    GPCA_CUDA_TRY(c, cudaMemcpyAsync(scores, c->ws_f64.p, N * k * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  }
+  if (loadings) {
+    GPCA_TRY(launch_apply_flags(c, R.p, D, k, k, d_flags.p, R.p, nullptr));
+    GPCA_CUDA_TRY(c, cudaMemcpyAsync(loadings, R.p, D * k * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  }
   GPCA_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-  std::vector<int> flip;
-  fix_signs_host(h_sc, N, k, flip);
-  if (scores)
-    for (uint64_t i = 0; i < N * k; ++i) scores[i] = (double)h_sc[i];
   if (eigenvalues)
     for (uint32_t j = 0; j < k; ++j) eigenvalues[j] = h_ev[j] / (double)(N - 1);
-  if (loadings) {
-    GPCA_CUDA_TRY(c, cudaMemcpyAsync(loadings, R.p, D * k * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-    GPCA_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    for (uint32_t j = 0; j < k; ++j)
-      if (flip[j])
-        for (uint64_t i = 0; i < D; ++i) loadings[i * k + j] = -loadings[i * k + j];
-  }
   if (k_out) *k_out = k;
   return GPCA_OK;
 }

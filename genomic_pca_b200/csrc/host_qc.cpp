@@ -14,6 +14,7 @@
 
 #include "../../include/gpca.h"
 #include "host_qc.h"
+#include "parallel_for.h"
 
 extern "C" double gpca_hwe_chi_squared_p_value(uint64_t hom1, uint64_t het, uint64_t hom2) {
   const uint64_t total = hom1 + het + hom2;
@@ -63,7 +64,8 @@ extern "C" double gpca_hwe_chi_squared_p_value(uint64_t hom1, uint64_t het, uint
 
 void host_snp_qc(uint64_t n_samples, uint64_t M, const uint32_t* counts /*[M][4] nvalid,n0,n1,n2*/,
                  const gpca_qc_cfg& cfg, uint8_t* keep, float* mean, float* sd, uint8_t* fail_code) {
-  for (uint64_t j = 0; j < M; ++j) {
+  parallel_for(M, [&](uint64_t j_lo, uint64_t j_hi) {
+  for (uint64_t j = j_lo; j < j_hi; ++j) {
     const uint32_t nv = counts[4 * j + 0], n0 = counts[4 * j + 1], n1 = counts[4 * j + 2], n2 = counts[4 * j + 3];
     uint8_t code = 0;
     float m32 = 0.f, s32 = 0.f;
@@ -94,11 +96,13 @@ void host_snp_qc(uint64_t n_samples, uint64_t M, const uint32_t* counts /*[M][4]
     if (sd) sd[j] = s32;
     if (fail_code) fail_code[j] = code;
   }
+  });
 }
 
 void host_vcf_maf(uint64_t n_samples, uint64_t M, const uint32_t* counts, double maf_threshold, uint8_t* keep,
                   float* mean, float* sd) {
-  for (uint64_t j = 0; j < M; ++j) {
+  parallel_for(M, [&](uint64_t j_lo, uint64_t j_hi) {
+  for (uint64_t j = j_lo; j < j_hi; ++j) {
     const uint32_t nv = counts[4 * j + 0], n0 = counts[4 * j + 1], n1 = counts[4 * j + 2], n2 = counts[4 * j + 3];
     bool k = false;
     float m32 = 0.f, s32 = 0.f;
@@ -122,6 +126,7 @@ void host_vcf_maf(uint64_t n_samples, uint64_t M, const uint32_t* counts, double
     if (mean) mean[j] = m32;
     if (sd) sd[j] = s32;
   }
+  });
 }
 
 extern "C" int gpca_map_snps_to_ld_blocks(const char* const* snp_chrom, const int32_t* snp_bp, uint64_t n_qc,

@@ -50,3 +50,9 @@ struct SketchProblem {
 };
 // out[r,:] = a_r * sum_k code(r,k) f_k Bin[k,:]  -  b_r * sum_k e_k Bin[k,:]  (+ missing correction)
 int launch_sketch(gpca_ctx* c, const SketchProblem& p);
+
+// sign convention helpers (kernels_dense.cu): largest-|.| entry of every column positive
+int launch_sign_flags(gpca_ctx* c, const float* d_x, uint64_t n, uint32_t k, uint32_t ld, int* d_flags);
+// out[i][j] = flags[j] ? -x[i][j] : x[i][j], compact [n x k], as f32 and/or f64 (either may be null)
+int launch_apply_flags(gpca_ctx* c, const float* d_x, uint64_t n, uint32_t k, uint32_t ld, const int* d_flags,
+                       float* d_out_f32, double* d_out_f64);

@@ -310,3 +310,69 @@ int launch_make_orth_transform(gpca_ctx* c, const double* d_evals, const double*
   KLAUNCH_CHECK(c);
   return GPCA_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// Sign convention on the device: flags[j] = 1 when the largest-|.| entry of column j (first one on ties) is negative.
+__global__ void __launch_bounds__(256) sign_flags_kernel(const float* __restrict__ x, uint64_t n, uint32_t k, uint32_t ld,
+                                                         int* __restrict__ flags) {
+  __shared__ float sv[256];
+  __shared__ unsigned long long si[256];
+  const uint32_t j = blockIdx.x;
+  float best = -1.0f;
+  unsigned long long bi = 0;
+  for (uint64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const float a = fabsf(x[i * ld + j]);
+    if (a > best) {
+      best = a;
+      bi = i;
+    }
+  }
+  sv[threadIdx.x] = best;
+  si[threadIdx.x] = bi;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      const float b2 = sv[threadIdx.x + o];
+      const unsigned long long i2 = si[threadIdx.x + o];
+      if (b2 > sv[threadIdx.x] || (b2 == sv[threadIdx.x] && i2 < si[threadIdx.x])) {
+        sv[threadIdx.x] = b2;
+        si[threadIdx.x] = i2;
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) flags[j] = (n && x[si[0] * ld + j] < 0.0f) ? 1 : 0;
+}
+
+__global__ void apply_flags_kernel(const float* __restrict__ x, uint64_t n, uint32_t k, uint32_t ld,
+                                   const int* __restrict__ flags, float* __restrict__ out_f32,
+                                   double* __restrict__ out_f64) {
+  const uint64_t total = n * k;
+  for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < total;
+       t += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t i = t / k;
+    const uint32_t j = (uint32_t)(t - i * k);
+    float v = x[i * ld + j];
+    if (flags[j]) v = -v;
+    if (out_f32) out_f32[t] = v;
+    if (out_f64) out_f64[t] = (double)v;
+  }
+}
+
+int launch_sign_flags(gpca_ctx* c, const float* d_x, uint64_t n, uint32_t k, uint32_t ld, int* d_flags) {
+  if (k == 0) return GPCA_OK;
+  sign_flags_kernel<<<k, 256, 0, c->stream>>>(d_x, n, k, ld, d_flags);
+  KLAUNCH_CHECK(c);
+  return GPCA_OK;
+}
+
+int launch_apply_flags(gpca_ctx* c, const float* d_x, uint64_t n, uint32_t k, uint32_t ld, const int* d_flags,
+                       float* d_out_f32, double* d_out_f64) {
+  const uint64_t total = n * k;
+  if (total == 0) return GPCA_OK;
+  const uint64_t blocks = (total + 255) / 256;
+  const int grid = (int)(blocks < (uint64_t)c->sm_count * 16 ? blocks : (uint64_t)c->sm_count * 16);
+  apply_flags_kernel<<<grid, 256, 0, c->stream>>>(d_x, n, k, ld, d_flags, d_out_f32, d_out_f64);
+  KLAUNCH_CHECK(c);
+  return GPCA_OK;
+}

@@ -469,29 +469,51 @@ __global__ void __launch_bounds__(256) tc_colstats_kernel(const float* __restric
                                                           uint32_t ld, const float* __restrict__ f,
                                                           const float* __restrict__ e, double* __restrict__ cpart,
                                                           unsigned int* __restrict__ amax_bits) {
-  __shared__ double red[256];
+  // lane = column (and column + 32 when l > 32), 8 row lanes per CTA, 4 independent rows in flight per thread
+  __shared__ double red[2][256];
   __shared__ float redm[256];
-  const int cidx = threadIdx.x % 64;
-  const int rr = threadIdx.x / 64;   // 4 rows per iteration
-  double acc = 0.0;
+  const int cidx = threadIdx.x & 31;
+  const int rr = threadIdx.x >> 5;
+  const bool c0 = (uint32_t)cidx < l, c1 = (uint32_t)(cidx + 32) < l;
+  double acc0 = 0.0, acc1 = 0.0;
   float mx = 0.0f;
-  if ((uint32_t)cidx < l) {
-    for (uint64_t k = (uint64_t)blockIdx.x * 4 + rr; k < K; k += (uint64_t)gridDim.x * 4) {
-      const float x = bin[k * ld + cidx];
-      acc += (double)(e ? x * e[k] : x);
-      mx = fmaxf(mx, fabsf(f ? x * f[k] : x));
+  const uint64_t stride = (uint64_t)gridDim.x * 8;
+  for (uint64_t k = (uint64_t)blockIdx.x * 8 + rr; k < K; k += 4 * stride) {
+    float x0[4], x1[4], ek[4], fk[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint64_t kk = k + u * stride;
+      const bool live = kk < K;
+      x0[u] = (live && c0) ? bin[kk * ld + cidx] : 0.0f;
+      x1[u] = (live && c1) ? bin[kk * ld + cidx + 32] : 0.0f;
+      ek[u] = (live && e) ? e[kk] : 1.0f;
+      fk[u] = (live && f) ? f[kk] : 1.0f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      acc0 += (double)(x0[u] * ek[u]);
+      acc1 += (double)(x1[u] * ek[u]);
+      mx = fmaxf(mx, fmaxf(fabsf(x0[u] * fk[u]), fabsf(x1[u] * fk[u])));
     }
   }
-  red[threadIdx.x] = acc;
+  red[0][threadIdx.x] = acc0;
+  red[1][threadIdx.x] = acc1;
   redm[threadIdx.x] = mx;
   __syncthreads();
   if (rr == 0) {
-    double s = red[cidx] + red[64 + cidx] + red[128 + cidx] + red[192 + cidx];
-    cpart[(uint64_t)blockIdx.x * 64 + cidx] = s;
-    float m = fmaxf(fmaxf(redm[cidx], redm[64 + cidx]), fmaxf(redm[128 + cidx], redm[192 + cidx]));
+    double s0 = 0.0, s1 = 0.0;
+    float m = 0.0f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      s0 += red[0][q * 32 + cidx];
+      s1 += red[1][q * 32 + cidx];
+      m = fmaxf(m, redm[q * 32 + cidx]);
+    }
+    cpart[(uint64_t)blockIdx.x * 64 + cidx] = s0;
+    cpart[(uint64_t)blockIdx.x * 64 + 32 + cidx] = s1;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((cidx & 31) == 0 && m > 0.0f && isfinite(m)) atomicMax(amax_bits, __float_as_uint(m));
+    if (cidx == 0 && m > 0.0f && isfinite(m)) atomicMax(amax_bits, __float_as_uint(m));
   }
 }
 
@@ -611,7 +633,7 @@ int run_tc(gpca_ctx* c, const SketchProblem& p) {
   // ---- operand prep
   GPCA_CUDA_TRY(c, c->ws_bytes.alloc(Kpad * NC * sizeof(__half)));
   __half* img = reinterpret_cast<__half*>(c->ws_bytes.p);
-  int nb = (int)((K + 3) / 4);
+  int nb = (int)((K + 31) / 32);
   if (nb > c->sm_count * 8) nb = c->sm_count * 8;
   if (nb < 1) nb = 1;
   GPCA_CUDA_TRY(c, c->ws_cpart.alloc((size_t)nb * 64));
