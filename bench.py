@@ -223,9 +223,7 @@ def run_ours(args, rank, world):
     def prepare_from_device():
         ctx.load_bed_device(payload.data_ptr(), n, m)
         keep, mean, sd = ctx.vcf_maf_filter(0.01)
-        idx = np.nonzero(keep)[0]
-        ctx.set_pca_snps(idx, mean[idx], sd[idx])
-        return idx.size
+        return ctx.set_pca_snps_mask(keep, mean, sd)
 
     d_kept = prepare_from_device()
     passes = 2 * POWER_ITERS + 3
@@ -279,8 +277,7 @@ def run_ours(args, rank, world):
         def e2e_step():
             ctx.load_bed_host_ptr(host.data_ptr(), n, m)
             keep, mean, sd = ctx.vcf_maf_filter(0.01)
-            idx = np.nonzero(keep)[0]
-            ctx.set_pca_snps(idx, mean[idx], sd[idx])
+            ctx.set_pca_snps_mask(keep, mean, sd)
             return ctx.rfit(K_COMPONENTS, OVERSAMPLE, power_iters=POWER_ITERS, seed=RFIT_SEED, want_loadings=False)
 
         e2e_step()

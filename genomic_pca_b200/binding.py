@@ -98,6 +98,7 @@ _sig("gpca_snp_qc", C.c_int, C.c_void_p, C.POINTER(QcConfig), _u8p, _f32p, _f32p
 _sig("gpca_vcf_maf_filter", C.c_int, C.c_void_p, C.c_double, _u8p, _f32p, _f32p)
 _sig("gpca_hwe_chi_squared_p_value", C.c_double, C.c_uint64, C.c_uint64, C.c_uint64)
 _sig("gpca_set_pca_snps", C.c_int, C.c_void_p, _u64p, C.c_uint64, _f32p, _f32p)
+_sig("gpca_set_pca_snps_mask", C.c_int, C.c_void_p, _u8p, _f32p, _f32p, _u64p)
 _sig("gpca_get_standardized_block", C.c_int, C.c_void_p, _u64p, C.c_uint64, _u64p, C.c_uint64, _f32p)
 _sig("gpca_sketch_snp_side", C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32)
 _sig("gpca_sketch_sample_side", C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32)
@@ -268,6 +269,16 @@ class Context:
         sd = np.ascontiguousarray(sd, dtype=np.float32)
         assert idx.size == mean.size == sd.size
         self._chk(lib.gpca_set_pca_snps(self._h, _ptr(idx, _u64p), idx.size, _ptr(mean, _f32p), _ptr(sd, _f32p)))
+
+    def set_pca_snps_mask(self, keep, mean_all, sd_all) -> int:
+        keep = np.ascontiguousarray(keep, dtype=np.uint8)
+        mean_all = np.ascontiguousarray(mean_all, dtype=np.float32)
+        sd_all = np.ascontiguousarray(sd_all, dtype=np.float32)
+        assert keep.size == mean_all.size == sd_all.size == self.num_snps
+        n = C.c_uint64(0)
+        self._chk(lib.gpca_set_pca_snps_mask(self._h, _ptr(keep, _u8p), _ptr(mean_all, _f32p), _ptr(sd_all, _f32p),
+                                             C.byref(n)))
+        return int(n.value)
 
     def get_standardized_snp_sample_block(self, pca_snp_ids, qc_sample_ids=None):
         ids = np.ascontiguousarray(pca_snp_ids, dtype=np.uint64)

@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <atomic>
 #include <new>
 
 #include "host_qc.h"
@@ -51,6 +52,7 @@ extern "C" void gpca_destroy(gpca_ctx* c) {
     cudaEventDestroy(pr.second);
   }
   if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->h_cnt) cudaFreeHost(c->h_cnt);
   delete c;
 }
 
@@ -93,9 +95,7 @@ static void reset_loaded(gpca_ctx* c) {
   c->D = 0;
   c->pca_idx.clear();
   c->Gs = PackedMat();
-  c->Gt = PackedMat();
-  c->gs_store.release();
-  c->gt_store.release();
+  c->Gt = PackedMat();   // (the stores are kept: DevBuf::alloc reuses them when the next data set fits)
   c->any_missing = false;
 }
 
@@ -105,7 +105,6 @@ static int alloc_raw(gpca_ctx* c, uint64_t N, uint64_t M) {
   c->N = N;
   c->M = M;
   c->raw_pitch = round_up((N + 3) / 4, 16);
-  c->raw.release();
   GPCA_CUDA_TRY(c, c->raw.alloc(std::max<size_t>(c->raw_pitch * M, 16)));
   return GPCA_OK;
 }
@@ -197,17 +196,22 @@ static int ensure_counts(gpca_ctx* c) {
   if (c->have_counts) return GPCA_OK;
   if (!c->raw.p) return fail(c, GPCA_ERR_INVALID, "no genotype payload loaded (or it was released)");
   const uint64_t M = c->M;
-  DevBuf<uint4> d_cnt;
-  GPCA_CUDA_TRY(c, d_cnt.alloc(std::max<uint64_t>(M, 1)));
-  GPCA_TRY(launch_bed_counts(c, c->raw.p, c->raw_pitch, M, d_cnt.p));
-  std::vector<uint4> h(M);
-  GPCA_CUDA_TRY(c, cudaMemcpyAsync(h.data(), d_cnt.p, M * sizeof(uint4), cudaMemcpyDeviceToHost, c->stream));
+  GPCA_CUDA_TRY(c, c->d_cnt.alloc(std::max<uint64_t>(M, 1)));
+  GPCA_TRY(launch_bed_counts(c, c->raw.p, c->raw_pitch, M, c->d_cnt.p));
+  if (c->h_cnt_cap < M) {   // pinned landing buffer for the 16 B/SNP count records, kept across calls
+    if (c->h_cnt) cudaFreeHost(c->h_cnt);
+    c->h_cnt = nullptr;
+    c->h_cnt_cap = 0;
+    GPCA_CUDA_TRY(c, cudaMallocHost((void**)&c->h_cnt, std::max<uint64_t>(M, 1) * sizeof(uint4)));
+    c->h_cnt_cap = M;
+  }
+  GPCA_CUDA_TRY(c, cudaMemcpyAsync(c->h_cnt, c->d_cnt.p, M * sizeof(uint4), cudaMemcpyDeviceToHost, c->stream));
   GPCA_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   const uint32_t pad = (uint32_t)(c->raw_pitch * 4 - c->N);  // pad fields were written as 01
   c->h_counts.resize(M * 4);
   uint32_t* hc = c->h_counts.data();
   const uint32_t n32 = (uint32_t)c->N;
-  const uint4* hp = h.data();
+  const uint4* hp = c->h_cnt;
   parallel_for(M, [=](uint64_t lo, uint64_t hi) {
     for (uint64_t j = lo; j < hi; ++j) {
       const uint32_t miss = hp[j].x - pad, het = hp[j].y, d0 = hp[j].z;
@@ -252,50 +256,46 @@ extern "C" int gpca_vcf_maf_filter(gpca_ctx* c, double maf_threshold, uint8_t* k
 }
 
 // ---- PCA SNP set -----------------------------------------------------------------------------
-extern "C" int gpca_set_pca_snps(gpca_ctx* c, const uint64_t* snp_idx, uint64_t D, const float* mean,
-                                 const float* sd) {
-  CHECK_CTX(c);
-  GPCA_CUDA_TRY(c, cudaSetDevice(c->device));
-  if (!c->raw.p) return fail(c, GPCA_ERR_INVALID, "no genotype payload loaded (or it was released)");
-  if (D == 0) return fail(c, GPCA_ERR_INVALID, "No SNPs passed all QC filters.");  // prepare.rs:1020
-  if (!snp_idx || !mean || !sd) return fail(c, GPCA_ERR_INVALID, "null argument");
-  for (uint64_t i = 0; i < D; ++i)
-    if (snp_idx[i] >= c->M || (i && snp_idx[i] <= snp_idx[i - 1]))
-      return fail(c, GPCA_ERR_INVALID, "snp_idx must be strictly increasing and < num_snps");
-  GPCA_TRY(ensure_counts(c));
-  c->D = D;
-  c->pca_idx.assign(snp_idx, snp_idx + D);
-  c->h_mean.assign(mean, mean + D);
-  c->h_sd.assign(sd, sd + D);
-  std::vector<float> inv(D), muinv(D);
-  uint64_t nmiss = 0;
-  for (uint64_t i = 0; i < D; ++i) {
-    // same f32 expressions as prepare.rs:1948-1949 (recip, -mean*recip); sd < 1e-9 -> the row standardises to 0
-    if (std::fabs(sd[i]) < 1e-9f) {
-      inv[i] = 0.f;
-      muinv[i] = 0.f;
-    } else {
-      const float r = 1.0f / sd[i];
-      inv[i] = r;
-      muinv[i] = mean[i] * r;
+static int build_pca_set(gpca_ctx* c, uint64_t D) {
+  // c->pca_idx, c->h_mean, c->h_sd are filled; derive the device-side vectors and the resident copies
+  const uint64_t* idx = c->pca_idx.data();
+  const float* mean = c->h_mean.data();
+  const float* sd = c->h_sd.data();
+  c->h_inv.resize(D);
+  c->h_muinv.resize(D);
+  float* inv = c->h_inv.data();
+  float* muinv = c->h_muinv.data();
+  const uint32_t* hc = c->h_counts.data();
+  const uint64_t N = c->N;
+  std::atomic<uint64_t> nmiss_total{0};
+  parallel_for(D, [&, idx, mean, sd, inv, muinv, hc, N](uint64_t lo, uint64_t hi) {
+    uint64_t nm = 0;
+    for (uint64_t i = lo; i < hi; ++i) {
+      // same f32 expressions as prepare.rs:1948-1949 (recip, mean*recip); sd < 1e-9 -> the row standardises to 0
+      if (std::fabs(sd[i]) < 1e-9f) {
+        inv[i] = 0.f;
+        muinv[i] = 0.f;
+      } else {
+        const float r = 1.0f / sd[i];
+        inv[i] = r;
+        muinv[i] = mean[i] * r;
+      }
+      nm += N - hc[4 * idx[i]];
     }
-    nmiss += c->N - c->h_counts[4 * snp_idx[i]];
-  }
-  c->any_missing = nmiss > 0;
+    nmiss_total.fetch_add(nm);
+  });
+  c->any_missing = nmiss_total.load() > 0;
+  c->D = D;
   GPCA_CUDA_TRY(c, c->d_mean.alloc(D));
   GPCA_CUDA_TRY(c, c->d_sd.alloc(D));
   GPCA_CUDA_TRY(c, c->d_inv_sd.alloc(D));
   GPCA_CUDA_TRY(c, c->d_mu_inv_sd.alloc(D));
+  GPCA_CUDA_TRY(c, c->d_idx.alloc(D));
+  GPCA_CUDA_TRY(c, cudaMemcpyAsync(c->d_idx.p, idx, D * 8, cudaMemcpyHostToDevice, c->stream));
   GPCA_CUDA_TRY(c, cudaMemcpyAsync(c->d_mean.p, mean, D * 4, cudaMemcpyHostToDevice, c->stream));
   GPCA_CUDA_TRY(c, cudaMemcpyAsync(c->d_sd.p, sd, D * 4, cudaMemcpyHostToDevice, c->stream));
-  GPCA_CUDA_TRY(c, cudaMemcpyAsync(c->d_inv_sd.p, inv.data(), D * 4, cudaMemcpyHostToDevice, c->stream));
-  GPCA_CUDA_TRY(c, cudaMemcpyAsync(c->d_mu_inv_sd.p, muinv.data(), D * 4, cudaMemcpyHostToDevice, c->stream));
-  DevBuf<uint64_t> d_idx;
-  GPCA_CUDA_TRY(c, d_idx.alloc(D));
-  GPCA_CUDA_TRY(c, cudaMemcpyAsync(d_idx.p, snp_idx, D * 8, cudaMemcpyHostToDevice, c->stream));
-
-  c->gs_store.release();
-  c->gt_store.release();
+  GPCA_CUDA_TRY(c, cudaMemcpyAsync(c->d_inv_sd.p, inv, D * 4, cudaMemcpyHostToDevice, c->stream));
+  GPCA_CUDA_TRY(c, cudaMemcpyAsync(c->d_mu_inv_sd.p, muinv, D * 4, cudaMemcpyHostToDevice, c->stream));
   c->Gs.rows = D;
   c->Gs.cols = c->N;
   c->Gs.pitch = round_up((c->N + 3) / 4, 128);
@@ -304,15 +304,87 @@ extern "C" int gpca_set_pca_snps(gpca_ctx* c, const uint64_t* snp_idx, uint64_t 
   c->Gt.pitch = round_up((D + 3) / 4, 128);
   GPCA_CUDA_TRY(c, c->gs_store.alloc(c->Gs.pitch * D));
   c->Gs.p = c->gs_store.p;
-  GPCA_TRY(launch_build_gs(c, c->raw.p, c->raw_pitch, d_idx.p, c->Gs));
-  GPCA_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-  // the PLINK-coded staging copy is only needed again for a different SNP selection; release it when large
-  if (c->raw_pitch * c->M > (4ull << 30)) c->raw.release();
+  GPCA_TRY(launch_build_gs(c, c->raw.p, c->raw_pitch, c->d_idx.p, c->Gs));
+  // the PLINK-coded staging copy is only needed again for a different SNP selection; under memory pressure
+  // (three copies would not fit comfortably) it is released before the transposed copy is allocated
+  size_t free_b = 0, total_b = 0;
+  cudaMemGetInfo(&free_b, &total_b);
+  if (c->gt_store.n < c->Gt.pitch * c->N && free_b < c->Gt.pitch * c->N + (8ull << 30)) {
+    GPCA_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    c->raw.release();
+  }
   GPCA_CUDA_TRY(c, c->gt_store.alloc(c->Gt.pitch * c->N));
   c->Gt.p = c->gt_store.p;
   GPCA_TRY(launch_transpose(c, c->Gs, c->Gt));
   GPCA_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   return GPCA_OK;
+}
+
+extern "C" int gpca_set_pca_snps(gpca_ctx* c, const uint64_t* snp_idx, uint64_t D, const float* mean,
+                                 const float* sd) {
+  CHECK_CTX(c);
+  GPCA_CUDA_TRY(c, cudaSetDevice(c->device));
+  if (!c->raw.p) return fail(c, GPCA_ERR_INVALID, "no genotype payload loaded (or it was released)");
+  if (D == 0) return fail(c, GPCA_ERR_INVALID, "No SNPs passed all QC filters.");  // prepare.rs:1020
+  if (!snp_idx || !mean || !sd) return fail(c, GPCA_ERR_INVALID, "null argument");
+  std::atomic<int> bad{0};
+  const uint64_t M = c->M;
+  parallel_for(D, [&, snp_idx, M](uint64_t lo, uint64_t hi) {
+    for (uint64_t i = lo; i < hi; ++i)
+      if (snp_idx[i] >= M || (i && snp_idx[i] <= snp_idx[i - 1])) bad.store(1);
+  });
+  if (bad.load()) return fail(c, GPCA_ERR_INVALID, "snp_idx must be strictly increasing and < num_snps");
+  GPCA_TRY(ensure_counts(c));
+  c->pca_idx.assign(snp_idx, snp_idx + D);
+  c->h_mean.assign(mean, mean + D);
+  c->h_sd.assign(sd, sd + D);
+  return build_pca_set(c, D);
+}
+
+extern "C" int gpca_set_pca_snps_mask(gpca_ctx* c, const uint8_t* keep, const float* mean_all, const float* sd_all,
+                                      uint64_t* n_pca_out) {
+  CHECK_CTX(c);
+  GPCA_CUDA_TRY(c, cudaSetDevice(c->device));
+  if (!c->raw.p) return fail(c, GPCA_ERR_INVALID, "no genotype payload loaded (or it was released)");
+  if (!keep || !mean_all || !sd_all) return fail(c, GPCA_ERR_INVALID, "null argument");
+  GPCA_TRY(ensure_counts(c));
+  const uint64_t M = c->M;
+  // two-pass compaction over host threads: count per chunk, then fill
+  const uint64_t CH = 1u << 18;
+  const uint64_t nch = (M + CH - 1) / CH;
+  std::vector<uint64_t> cnt(nch + 1, 0);
+  parallel_for(nch, [&, keep, M](uint64_t lo, uint64_t hi) {
+    for (uint64_t q = lo; q < hi; ++q) {
+      uint64_t n = 0;
+      const uint64_t e = std::min(M, (q + 1) * CH);
+      for (uint64_t j = q * CH; j < e; ++j) n += keep[j] != 0;
+      cnt[q + 1] = n;
+    }
+  }, 1);
+  for (uint64_t q = 0; q < nch; ++q) cnt[q + 1] += cnt[q];
+  const uint64_t D = cnt[nch];
+  if (n_pca_out) *n_pca_out = D;
+  if (D == 0) return fail(c, GPCA_ERR_INVALID, "No SNPs passed all QC filters.");  // prepare.rs:1020
+  c->pca_idx.resize(D);
+  c->h_mean.resize(D);
+  c->h_sd.resize(D);
+  uint64_t* pi = c->pca_idx.data();
+  float* pm = c->h_mean.data();
+  float* ps = c->h_sd.data();
+  parallel_for(nch, [&, keep, M, mean_all, sd_all, pi, pm, ps](uint64_t lo, uint64_t hi) {
+    for (uint64_t q = lo; q < hi; ++q) {
+      uint64_t o = cnt[q];
+      const uint64_t e = std::min(M, (q + 1) * CH);
+      for (uint64_t j = q * CH; j < e; ++j)
+        if (keep[j]) {
+          pi[o] = j;
+          pm[o] = mean_all[j];
+          ps[o] = sd_all[j];
+          ++o;
+        }
+    }
+  }, 1);
+  return build_pca_set(c, D);
 }
 
 // ---- accessor parity ---------------------------------------------------------------------------

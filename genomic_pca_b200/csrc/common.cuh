@@ -85,7 +85,11 @@ struct gpca_ctx {
   // PCA SNP set + resident copies
   uint64_t D = 0;
   std::vector<uint64_t> pca_idx;
-  std::vector<float> h_mean, h_sd;
+  std::vector<float> h_mean, h_sd, h_inv, h_muinv;
+  DevBuf<uint64_t> d_idx;
+  DevBuf<uint4> d_cnt;
+  uint4* h_cnt = nullptr;      // pinned landing buffer for the count records
+  uint64_t h_cnt_cap = 0;
   DevBuf<float> d_mean, d_sd;           // [D]
   DevBuf<float> d_inv_sd, d_mu_inv_sd;  // [D]  1/sd (0 if sd<1e-9) and mean/sd
   DevBuf<uint8_t> gs_store, gt_store;

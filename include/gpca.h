@@ -107,6 +107,10 @@ double gpca_hwe_chi_squared_p_value(uint64_t hom1, uint64_t het, uint64_t hom2);
  * standardisation parameters; builds the resident device copies used by every sketch pass.
  * Mirrors MicroarrayGenotypeAccessor::new (src/prepare.rs:1783-1822). */
 int gpca_set_pca_snps(gpca_ctx* ctx, const uint64_t* snp_idx, uint64_t n_pca_snps, const float* mean, const float* sd);
+/* Same, selecting every loaded SNP with keep[j] != 0 and taking mean/sd from the full-length arrays that
+ * gpca_snp_qc / gpca_vcf_maf_filter filled (saves the host a gather over millions of SNPs). */
+int gpca_set_pca_snps_mask(gpca_ctx* ctx, const uint8_t* keep, const float* mean_all, const float* sd_all,
+                           uint64_t* n_pca_out);
 
 /* ---- the accessor the GPU path makes unnecessary, kept for parity ---------------------- */
 /* get_standardized_snp_sample_block (src/prepare.rs:1839-2022): out[n_ids x n_samp] row-major

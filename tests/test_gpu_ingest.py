@@ -97,3 +97,19 @@ def test_standardized_block_errors_on_missing(gpu_ctx):
     with pytest.raises(gp.GpcaError) as e:
         gpu_ctx.get_standardized_snp_sample_block(has_missing[:1])
     assert e.value.code == -4
+
+
+def test_set_pca_snps_mask_equals_index_form(gpu_ctx):
+    g, payload = make_dataset(300, 2000, seed=21, missing_rate=0.01)
+    gpu_ctx.load_bed(payload, 300, 2000)
+    keep, mean, sd, _ = gpu_ctx.snp_qc()
+    idx = np.nonzero(keep)[0]
+    gpu_ctx.set_pca_snps(idx, mean[idx], sd[idx])
+    ids = np.arange(0, idx.size, 7)
+    has_missing = (g[idx][ids] == bed.MISSING_I8).any(1)
+    ids = ids[~has_missing]
+    z1 = gpu_ctx.get_standardized_snp_sample_block(ids)
+    n = gpu_ctx.set_pca_snps_mask(keep, mean, sd)
+    assert n == idx.size == gpu_ctx.num_pca_snps
+    z2 = gpu_ctx.get_standardized_snp_sample_block(ids)
+    assert np.array_equal(z1, z2)
