@@ -1,0 +1,573 @@
+// genomic_pca_cli.cpp -- command-line front end with the reference's flag surface and output files,
+// driving the hot path through the C ABI (include/gpca.h).  No CPU fallback: gpca_init fails without a B200.
+//
+// Mirrors (names, defaults, messages, output formats):
+//   CliArgs                         src/main.rs:505-592   (effective defaults via default_value_if: main.rs:545-588)
+//   run_vcf_workflow                src/main.rs:133-247   (file discovery :139-152, sample set from the first file :157-160)
+//   process_single_vcf              src/vcf.rs:65-287     (biallelic single-base filter, GT -> 0/1/2, drop on missing, MAF)
+//   run_eigensnp_rust_workflow      src/main.rs:250-447
+//   MicroarrayDataPreparer          src/prepare.rs:922-1096 (BIM/FAM metadata, sample keep list), :1565-1616 (LD file)
+//   output_writer                   src/main.rs:682-839   (file names, headers, {:.6})
+// Deliberate differences: plain or gzip/BGZF VCF text is parsed with zlib (the reference uses noodles-vcf);
+// --threads / --log-level are accepted; the rfit eigenvalues file is header-only exactly like the reference
+// (src/main.rs:676) unless --write-eigenvalues is given.
+#include <dirent.h>
+#include <sys/stat.h>
+#include <zlib.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <set>
+#include <sstream>
+#include <string>
+#include <unordered_set>
+#include <vector>
+
+#include "../../../include/gpca.h"
+
+namespace {
+
+struct Args {
+  std::string out;
+  std::string vcf_dir, bed_file, ld_block_file, keep_file, log_level = "Info";
+  long threads = -1;
+  long components = -1;
+  double maf = -1.0;
+  bool has_seed = false;
+  uint64_t rfit_seed = 0;
+  bool eigensnp = false;
+  bool write_eigenvalues = false;
+  uint32_t rfit_power_iters = 2;
+  gpca_qc_cfg qc{0.98, 0.01, 1e-6};
+  gpca_eigensnp_cfg es;
+};
+
+[[noreturn]] void die(const std::string& msg) {
+  fprintf(stderr, "Error: %s\n", msg.c_str());
+  exit(1);
+}
+void info(const std::string& msg) { fprintf(stderr, "[INFO] %s\n", msg.c_str()); }
+void warn(const std::string& msg) { fprintf(stderr, "[WARN] %s\n", msg.c_str()); }
+
+void usage() {
+  fprintf(stderr,
+          "Genomic PCA Tool from VCF or BED/LD-block files (B200-native hot path).\n\n"
+          "Usage: genomic_pca --out <OUTPUT_PREFIX> [OPTIONS]\n\n"
+          "  -o, --out <PREFIX>            Output file prefix (required)\n"
+          "  -t, --threads <N>             accepted for compatibility (host-side loops use all cores)\n"
+          "      --log-level <LEVEL>       accepted for compatibility\n"
+          "  -d, --vcf-dir <DIR>           Directory containing VCF files (required unless --eigensnp)\n"
+          "  -k, --components <K>          Number of principal components (VCF workflow)\n"
+          "      --maf <MAF>               Minimum MAF for VCF variant filtering (default 0.01)\n"
+          "      --rfit-seed <SEED>        Seed for the randomized SVD (VCF workflow)\n"
+          "      --eigensnp                EigenSNP workflow (requires --bed-file and --ld-block-file)\n"
+          "      --bed-file <PATH>         PLINK .bed (with .bim/.fam beside it)\n"
+          "      --ld-block-file <PATH>    LD block definitions: chr start end\n"
+          "      --eigensnp-sample-keep-file <PATH>\n"
+          "      --eigensnp-min-call-rate <F> (0.98)  --eigensnp-min-maf <F> (0.01)  --eigensnp-max-hwe-p <F> (1e-6)\n"
+          "      --eigensnp-k-global <N> (10)  --eigensnp-components-per-block <N> (7)\n"
+          "      --eigensnp-subset-factor <F> (0.075)  --eigensnp-min-subset-size <N> (10000)\n"
+          "      --eigensnp-max-subset-size <N> (40000)  --eigensnp-global-oversampling <N> (10)\n"
+          "      --eigensnp-global-power-iter <N> (2)  --eigensnp-local-oversampling <N> (10)\n"
+          "      --eigensnp-local-power-iter <N> (2)  --eigensnp-seed <N> (2025)\n"
+          "      --eigensnp-snp-strip-size <N> (2000)  --eigensnp-refine-passes <N> (1)\n"
+          "      --eigensnp-collect-diagnostics\n"
+          "      --write-eigenvalues       (extension) also write the rfit eigenvalues\n");
+}
+
+Args parse(int argc, char** argv) {
+  Args a;
+  gpca_eigensnp_default_cfg(&a.es);
+  auto need = [&](int& i) -> std::string {
+    if (i + 1 >= argc) die(std::string("missing value for ") + argv[i]);
+    return argv[++i];
+  };
+  for (int i = 1; i < argc; ++i) {
+    std::string f = argv[i];
+    std::string inline_val;
+    const size_t eq = f.find('=');
+    bool has_inline = false;
+    if (f.rfind("--", 0) == 0 && eq != std::string::npos) {
+      inline_val = f.substr(eq + 1);
+      f = f.substr(0, eq);
+      has_inline = true;
+    }
+    auto val = [&]() -> std::string { return has_inline ? inline_val : need(i); };
+    if (f == "-h" || f == "--help") { usage(); exit(0); }
+    else if (f == "-V" || f == "--version") { printf("genomic_pca %s\n", gpca_version()); exit(0); }
+    else if (f == "-o" || f == "--out") a.out = val();
+    else if (f == "-t" || f == "--threads") a.threads = atol(val().c_str());
+    else if (f == "--log-level") a.log_level = val();
+    else if (f == "-d" || f == "--vcf-dir") a.vcf_dir = val();
+    else if (f == "-k" || f == "--components") a.components = atol(val().c_str());
+    else if (f == "--maf") a.maf = atof(val().c_str());
+    else if (f == "--rfit-seed") { a.rfit_seed = strtoull(val().c_str(), nullptr, 10); a.has_seed = true; }
+    else if (f == "--rfit-power-iter") a.rfit_power_iters = (uint32_t)atol(val().c_str());
+    else if (f == "--eigensnp") a.eigensnp = true;
+    else if (f == "--bed-file") a.bed_file = val();
+    else if (f == "--ld-block-file") a.ld_block_file = val();
+    else if (f == "--eigensnp-sample-keep-file") a.keep_file = val();
+    else if (f == "--eigensnp-min-call-rate") a.qc.min_call_rate = atof(val().c_str());
+    else if (f == "--eigensnp-min-maf") a.qc.min_maf = atof(val().c_str());
+    else if (f == "--eigensnp-max-hwe-p") a.qc.max_hwe_p = atof(val().c_str());
+    else if (f == "--eigensnp-k-global") a.es.target_num_global_pcs = (uint32_t)atol(val().c_str());
+    else if (f == "--eigensnp-components-per-block") a.es.components_per_ld_block = (uint32_t)atol(val().c_str());
+    else if (f == "--eigensnp-subset-factor") a.es.subset_factor = atof(val().c_str());
+    else if (f == "--eigensnp-min-subset-size") a.es.min_subset_size = strtoull(val().c_str(), nullptr, 10);
+    else if (f == "--eigensnp-max-subset-size") a.es.max_subset_size = strtoull(val().c_str(), nullptr, 10);
+    else if (f == "--eigensnp-global-oversampling") a.es.global_oversampling = (uint32_t)atol(val().c_str());
+    else if (f == "--eigensnp-global-power-iter") a.es.global_power_iters = (uint32_t)atol(val().c_str());
+    else if (f == "--eigensnp-local-oversampling") a.es.local_oversampling = (uint32_t)atol(val().c_str());
+    else if (f == "--eigensnp-local-power-iter") a.es.local_power_iters = (uint32_t)atol(val().c_str());
+    else if (f == "--eigensnp-seed") a.es.random_seed = strtoull(val().c_str(), nullptr, 10);
+    else if (f == "--eigensnp-snp-strip-size") a.es.snp_processing_strip_size = (uint32_t)atol(val().c_str());
+    else if (f == "--eigensnp-refine-passes") a.es.refine_pass_count = (uint32_t)atol(val().c_str());
+    else if (f == "--eigensnp-collect-diagnostics") a.es.collect_diagnostics = 1;
+    else if (f == "--write-eigenvalues") a.write_eigenvalues = true;
+    else die("unexpected argument '" + f + "' (see --help)");
+  }
+  if (a.out.empty()) die("the following required arguments were not provided: --out <OUTPUT_PREFIX>");
+  if (!a.eigensnp) {
+    if (a.vcf_dir.empty()) die("--vcf-dir is required for the default VCF workflow.");          // main.rs:116
+    if (a.components < 0) die("-k/--components is required for the default VCF workflow.");    // main.rs:119
+  } else {
+    if (a.bed_file.empty()) die("--bed-file is required when --eigensnp is used");              // main.rs:296
+    if (a.ld_block_file.empty()) die("--ld-block-file is required when --eigensnp is used");    // main.rs:299
+  }
+  return a;
+}
+
+void make_parent_dirs(const std::string& prefix) {      // main.rs:219-225
+  const size_t p = prefix.find_last_of('/');
+  if (p == std::string::npos || p == 0) return;
+  std::string dir = prefix.substr(0, p), cur;
+  std::stringstream ss(dir);
+  std::string part;
+  if (dir[0] == '/') cur = "/";
+  while (std::getline(ss, part, '/')) {
+    if (part.empty()) continue;
+    cur += part + "/";
+    mkdir(cur.c_str(), 0777);
+  }
+}
+
+FILE* create_output(const std::string& prefix, const std::string& suffix) {
+  const std::string fn = prefix + "." + suffix;
+  FILE* f = fopen(fn.c_str(), "w");
+  if (!f) die("Failed to create output file '" + fn + "'");
+  return f;
+}
+
+template <class T>
+void write_pcs(const std::string& prefix, const std::string& suffix, const std::vector<std::string>& names,
+               const T* scores, uint64_t n, uint32_t k) {
+  if (k == 0) return;
+  FILE* f = create_output(prefix, suffix);
+  fputs("SampleID", f);
+  for (uint32_t j = 1; j <= k; ++j) fprintf(f, "\tPC%u", j);
+  fputc('\n', f);
+  for (uint64_t i = 0; i < names.size(); ++i) {
+    fputs(names[i].c_str(), f);
+    for (uint32_t j = 0; j < k; ++j) {
+      if (i < n) fprintf(f, "\t%.6f", (double)scores[i * k + j]);
+      else fputs("\tNA", f);
+    }
+    fputc('\n', f);
+  }
+  fclose(f);
+}
+
+void write_eigenvalues(const std::string& prefix, const std::vector<double>& ev) {
+  FILE* f = create_output(prefix, "eigenvalues.tsv");
+  fputs("PC\tEigenvalue\n", f);
+  for (size_t i = 0; i < ev.size(); ++i) fprintf(f, "%zu\t%.6f\n", i + 1, ev[i]);
+  fclose(f);
+}
+
+void check(gpca_ctx* ctx, int rc, const char* what) {
+  if (rc != GPCA_OK) die(std::string(what) + " failed: " + gpca_last_error(ctx));
+}
+
+// ---------------------------------------------------------------------------------------------- VCF workflow
+struct GzLines {
+  gzFile f;
+  std::vector<char> buf;
+  size_t pos = 0, len = 0;
+  explicit GzLines(const std::string& path) : buf(1 << 20) {
+    f = gzopen(path.c_str(), "rb");
+    if (!f) die("cannot open " + path);
+    gzbuffer(f, 1 << 20);
+  }
+  ~GzLines() { gzclose(f); }
+  bool next(std::string& line) {
+    line.clear();
+    for (;;) {
+      if (pos == len) {
+        const int n = gzread(f, buf.data(), (unsigned)buf.size());
+        if (n <= 0) return !line.empty();
+        len = (size_t)n;
+        pos = 0;
+      }
+      const char* s = buf.data() + pos;
+      const char* nl = (const char*)memchr(s, '\n', len - pos);
+      if (nl) {
+        line.append(s, nl - s);
+        pos += (nl - s) + 1;
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        return true;
+      }
+      line.append(s, len - pos);
+      pos = len;
+    }
+  }
+};
+
+bool ends_with(const std::string& s, const std::string& suf) {
+  return s.size() >= suf.size() && s.compare(s.size() - suf.size(), suf.size(), suf) == 0;
+}
+
+int run_vcf(const Args& a) {
+  // discovery: regular files with extension vcf or gz whose name contains ".vcf", sorted (main.rs:139-152)
+  std::vector<std::string> files;
+  DIR* d = opendir(a.vcf_dir.c_str());
+  if (!d) die("cannot read directory " + a.vcf_dir);
+  while (dirent* e = readdir(d)) {
+    const std::string name = e->d_name;
+    const std::string path = a.vcf_dir + "/" + name;
+    struct stat st;
+    if (stat(path.c_str(), &st) != 0 || !S_ISREG(st.st_mode)) continue;
+    if ((ends_with(name, ".vcf") || ends_with(name, ".gz")) && name.find(".vcf") != std::string::npos) files.push_back(path);
+  }
+  closedir(d);
+  if (files.empty()) die("No VCF files (ending in .vcf or .vcf.gz) found in directory: " + a.vcf_dir);
+  std::sort(files.begin(), files.end());
+  const double maf_thr = a.maf >= 0 ? a.maf : 0.01;                                 // vcf.rs:257
+  std::vector<std::string> samples, ids;
+  std::vector<uint8_t> dosage;                                                      // variant-major, D rows of N bytes
+  std::vector<uint8_t> tmp;
+  for (size_t fi = 0; fi < files.size(); ++fi) {
+    GzLines in(files[fi]);
+    std::string line;
+    std::vector<std::string> hdr_samples;
+    bool have_gt_format = false;
+    while (in.next(line)) {
+      if (line.empty()) continue;
+      if (line[0] == '#') {
+        if (line.rfind("##FORMAT=<ID=GT", 0) == 0) have_gt_format = true;
+        if (line.rfind("#CHROM", 0) == 0) {
+          std::stringstream ss(line);
+          std::string t;
+          int col = 0;
+          while (std::getline(ss, t, '\t')) if (col++ >= 9) hdr_samples.push_back(t);
+          if (fi == 0) {
+            samples = hdr_samples;
+            if (samples.empty()) die("VCF header from " + files[fi] + " contains no samples.");   // vcf.rs:32
+          } else if (hdr_samples != samples) {
+            die("Sample mismatch in VCF " + files[fi] + ": all VCFs must match the sample set of the first VCF (" + files[0] + ").");
+          }
+          if (!have_gt_format) die("GT key (FORMAT=GT) not found in FORMAT header for VCF " + files[fi]);   // vcf.rs:93
+        }
+        continue;
+      }
+      // CHROM POS ID REF ALT QUAL FILTER INFO FORMAT samples...
+      const size_t n = samples.size();
+      const char* p = line.c_str();
+      const char* fld[9];
+      size_t flen[9];
+      int nf = 0;
+      const char* s = p;
+      while (nf < 9) {
+        const char* t = strchr(s, '\t');
+        if (!t) break;
+        fld[nf] = s;
+        flen[nf] = (size_t)(t - s);
+        ++nf;
+        s = t + 1;
+      }
+      if (nf < 9) continue;
+      const std::string ref(fld[3], flen[3]), alt(fld[4], flen[4]);
+      if (ref.size() != 1 || alt == "." || alt.find(',') != std::string::npos) continue;     // vcf.rs:109-121
+      // GT position inside FORMAT
+      int gt_pos = -1;
+      {
+        int idx = 0;
+        const char* q = fld[8];
+        const char* end = fld[8] + flen[8];
+        while (q <= end) {
+          const char* c = (const char*)memchr(q, ':', (size_t)(end - q));
+          const size_t l = c ? (size_t)(c - q) : (size_t)(end - q);
+          if (l == 2 && q[0] == 'G' && q[1] == 'T') { gt_pos = idx; break; }
+          if (!c) break;
+          q = c + 1;
+          ++idx;
+        }
+      }
+      if (gt_pos < 0) continue;                                                              // vcf.rs:218-224
+      tmp.assign(n, 0);
+      size_t si = 0;
+      bool bad = false;
+      uint32_t allele_sum = 0;
+      while (si < n && *s) {
+        const char* t = strchr(s, '\t');
+        const char* end = t ? t : s + strlen(s);
+        // select sub-field gt_pos
+        const char* q = s;
+        for (int g = 0; g < gt_pos && q < end; ++g) {
+          const char* c = (const char*)memchr(q, ':', (size_t)(end - q));
+          if (!c) { q = end; break; }
+          q = c + 1;
+        }
+        const char* qe = (const char*)memchr(q, ':', (size_t)(end - q));
+        if (!qe) qe = end;
+        // first two alleles, '/' or '|' separated, each exactly "0" or "1" (vcf.rs:52-63, 153-193)
+        int dos = 0, na = 0;
+        const char* r = q;
+        while (r < qe && na < 2) {
+          const char* sep = r;
+          while (sep < qe && *sep != '/' && *sep != '|') ++sep;
+          if (sep - r != 1 || (*r != '0' && *r != '1')) { bad = true; break; }
+          dos += *r - '0';
+          ++na;
+          r = sep + 1;
+        }
+        if (bad || na != 2) { bad = true; break; }
+        tmp[si++] = (uint8_t)dos;
+        allele_sum += (uint32_t)dos;
+        if (!t) break;
+        s = t + 1;
+      }
+      if (bad || si != n) continue;                                                          // vcf.rs:227-242
+      const uint32_t total = (uint32_t)(n * 2);
+      if (total == 0) continue;
+      const double freq = (double)allele_sum / (double)total;                                // vcf.rs:254
+      const double maf = std::min(freq, 1.0 - freq);
+      if (maf < maf_thr) continue;                                                           // vcf.rs:259
+      ids.push_back(std::string(fld[0], flen[0]) + ":" + std::string(fld[1], flen[1]) + ":" + ref + ":" + alt);
+      dosage.insert(dosage.end(), tmp.begin(), tmp.end());
+    }
+  }
+  const uint64_t n = samples.size(), dvar = ids.size();
+  if (dvar == 0) die("No variants passed filters across all VCF files. Cannot proceed with PCA.");   // main.rs:198
+  info("Aggregated " + std::to_string(dvar) + " variants in total across all VCFs.");
+  if (a.components == 0) die("Number of components (-k) must be > 0.");                              // main.rs:607
+  if (n < 2) die("PCA requires at least 2 samples, found " + std::to_string(n) + ".");               // main.rs:614
+  gpca_ctx* ctx = nullptr;
+  if (gpca_init(&ctx, 0) != GPCA_OK) die("no sm_100 (B200) GPU available: this build has no CPU fallback");
+  check(ctx, gpca_load_u8_variant_major(ctx, dosage.data(), n, dvar), "load");
+  std::vector<uint8_t> keep(dvar);
+  std::vector<float> mean(dvar), sd(dvar);
+  check(ctx, gpca_vcf_maf_filter(ctx, maf_thr, keep.data(), mean.data(), sd.data()), "maf filter");
+  uint64_t d_kept = 0;
+  check(ctx, gpca_set_pca_snps_mask(ctx, keep.data(), mean.data(), sd.data(), &d_kept), "set_pca_snps");
+  uint32_t k = (uint32_t)a.components;
+  const uint64_t maxk = std::min<uint64_t>(n, d_kept);
+  if (k > maxk) {
+    warn("Requested k=" + std::to_string(k) + " components exceeds max possible for data; adjusting to " + std::to_string(maxk) + ".");
+    k = (uint32_t)maxk;
+  }
+  std::vector<double> scores(n * k), ev(k);
+  uint32_t k_out = 0;
+  const auto t0 = std::chrono::steady_clock::now();
+  check(ctx, gpca_rfit(ctx, k, 10 /* main.rs:636 */, a.rfit_power_iters, a.rfit_seed, a.has_seed ? 1 : 0, scores.data(),
+                       ev.data(), nullptr, &k_out), "rfit");
+  const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  info("VCF PCA computation (rfit on GPU) completed in " + std::to_string(ms) + " ms.");
+  make_parent_dirs(a.out);
+  write_pcs<double>(a.out, "vcf.pca.tsv", samples, scores.data(), n, k_out);
+  ev.resize(k_out);
+  write_eigenvalues(a.out, a.write_eigenvalues ? ev : std::vector<double>());   // reference writes a header-only file (main.rs:676)
+  warn("Loadings output for VCF-based PCA is currently skipped (as in the reference, main.rs:233).");
+  gpca_destroy(ctx);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ EigenSNP workflow
+std::string normalize_chromosome_name(std::string s) {      // prepare.rs:1610-1616
+  for (auto& ch : s) ch = (char)tolower((unsigned char)ch);
+  while (s.rfind("chr", 0) == 0) s = s.substr(3);
+  return s;
+}
+
+std::vector<std::string> split_ws(const std::string& s) {
+  std::vector<std::string> out;
+  std::stringstream ss(s);
+  std::string t;
+  while (ss >> t) out.push_back(t);
+  return out;
+}
+
+std::string trim(const std::string& s) {
+  size_t a = 0, b = s.size();
+  while (a < b && isspace((unsigned char)s[a])) ++a;
+  while (b > a && isspace((unsigned char)s[b - 1])) --b;
+  return s.substr(a, b - a);
+}
+
+int run_eigensnp(const Args& a) {
+  std::string prefix = a.bed_file;
+  if (ends_with(prefix, ".bed")) prefix = prefix.substr(0, prefix.size() - 4);
+  // FAM: IID = 2nd column; BIM: chrom, sid, cm, bp
+  std::vector<std::string> iids, chrom, sid;
+  std::vector<int32_t> bp;
+  {
+    std::ifstream f(prefix + ".fam");
+    if (!f) die("Failed to open FAM file '" + prefix + ".fam'");
+    std::string line;
+    while (std::getline(f, line)) {
+      auto p = split_ws(line);
+      if (p.size() >= 2) iids.push_back(p[1]);
+    }
+  }
+  {
+    std::ifstream f(prefix + ".bim");
+    if (!f) die("Failed to open BIM file '" + prefix + ".bim'");
+    std::string line;
+    while (std::getline(f, line)) {
+      auto p = split_ws(line);
+      if (p.size() >= 4) {
+        chrom.push_back(p[0]);
+        sid.push_back(p[1]);
+        bp.push_back((int32_t)atol(p[3].c_str()));
+      }
+    }
+  }
+  const uint64_t n_fam = iids.size(), m = sid.size();
+  info("Initial metadata loaded: " + std::to_string(n_fam) + " samples, " + std::to_string(m) + " SNPs.");
+  // payload
+  std::vector<uint8_t> bed;
+  {
+    std::ifstream f(a.bed_file, std::ios::binary | std::ios::ate);
+    if (!f) die("Failed to open BED file '" + a.bed_file + "'");
+    const std::streamsize sz = f.tellg();
+    f.seekg(0);
+    bed.resize((size_t)sz);
+    f.read((char*)bed.data(), sz);
+  }
+  const uint64_t bps = (n_fam + 3) / 4;
+  if (bed.size() < 3 || bed[0] != 0x6c || bed[1] != 0x1b || bed[2] != 0x01) die("not a SNP-major PLINK .bed");
+  if (bed.size() != 3 + bps * m) die("BED size does not match BIM/FAM");
+  // sample QC (prepare.rs:1058-1096)
+  std::vector<int64_t> keep_idx;
+  bool use_keep = false;
+  if (!a.keep_file.empty()) {
+    std::ifstream f(a.keep_file);
+    if (!f) die("Failed to read sample ID file '" + a.keep_file + "'");
+    std::unordered_set<std::string> ks;
+    std::string line;
+    while (std::getline(f, line)) ks.insert(line);
+    for (uint64_t i = 0; i < n_fam; ++i)
+      if (ks.count(iids[i])) keep_idx.push_back((int64_t)i);
+    use_keep = true;
+    if (keep_idx.empty()) die("No samples passed QC.");                                   // prepare.rs:1010
+  } else {
+    warn("No external sample ID list provided; using all " + std::to_string(n_fam) + " initial samples.");
+  }
+  gpca_ctx* ctx = nullptr;
+  if (gpca_init(&ctx, 0) != GPCA_OK) die("no sm_100 (B200) GPU available: this build has no CPU fallback");
+  check(ctx, gpca_load_bed(ctx, bed.data() + 3, n_fam, m, use_keep ? keep_idx.data() : nullptr, keep_idx.size()), "load_bed");
+  const uint64_t n = gpca_num_samples(ctx);
+  std::vector<uint8_t> keep(m);
+  std::vector<float> mean(m), sd(m);
+  check(ctx, gpca_snp_qc(ctx, &a.qc, keep.data(), mean.data(), sd.data(), nullptr), "snp_qc");
+  std::vector<uint64_t> qidx;
+  for (uint64_t j = 0; j < m; ++j)
+    if (keep[j]) qidx.push_back(j);
+  info("SNP QC & Stats calculation complete. " + std::to_string(qidx.size()) + " / " + std::to_string(m) + " initial SNPs passed all filters.");
+  if (qidx.empty()) die("No SNPs passed all QC filters.");                                // prepare.rs:1020
+  // LD block file (prepare.rs:1565-1607)
+  std::vector<std::string> bchr;
+  std::vector<int32_t> bstart, bend;
+  {
+    std::ifstream f(a.ld_block_file);
+    if (!f) die("Failed to open LD block file '" + a.ld_block_file + "'");
+    std::string line;
+    while (std::getline(f, line)) {
+      const std::string t = trim(line);
+      if (t.empty() || t[0] == '#' || t.rfind("chr\t", 0) == 0 || t.rfind("chromosome\t", 0) == 0) continue;
+      auto p = split_ws(t);
+      if (p.size() < 3) { warn("Skipping malformed LD block line: '" + line + "'"); continue; }
+      bchr.push_back(normalize_chromosome_name(p[0]));
+      bstart.push_back((int32_t)atol(p[1].c_str()));
+      bend.push_back((int32_t)atol(p[2].c_str()));
+    }
+  }
+  std::vector<std::string> qchr_s(qidx.size());
+  std::vector<const char*> qchr(qidx.size()), bchr_c(bchr.size());
+  std::vector<int32_t> qbp(qidx.size());
+  for (size_t i = 0; i < qidx.size(); ++i) {
+    qchr_s[i] = normalize_chromosome_name(chrom[qidx[i]]);
+    qchr[i] = qchr_s[i].c_str();
+    qbp[i] = bp[qidx[i]];
+  }
+  for (size_t b = 0; b < bchr.size(); ++b) bchr_c[b] = bchr[b].c_str();
+  std::vector<int64_t> pca_pos(qidx.size()), block_of(qidx.size());
+  std::vector<uint64_t> order(std::max<size_t>(bchr.size(), 1));
+  uint64_t n_pca = 0, n_blk = 0;
+  if (gpca_map_snps_to_ld_blocks(qchr.data(), qbp.data(), qidx.size(), bchr_c.data(), bstart.data(), bend.data(), bchr.size(),
+                                 pca_pos.data(), block_of.data(), &n_pca, &n_blk, order.data()) != GPCA_OK)
+    die("LD block mapping failed");
+  if (n_pca == 0) die("No SNPs mapped to LD blocks or all resulting blocks were empty.");  // prepare.rs:1031
+  info("LD Mapping: " + std::to_string(n_pca) + " unique SNPs (D_blocked) mapped to " + std::to_string(n_blk) + " LD blocks.");
+  std::vector<uint64_t> pca_orig;
+  std::vector<float> pmean, psd;
+  std::vector<std::vector<uint64_t>> blocks(n_blk);
+  for (size_t i = 0; i < qidx.size(); ++i)
+    if (pca_pos[i] >= 0) {
+      pca_orig.push_back(qidx[i]);
+      pmean.push_back(mean[qidx[i]]);
+      psd.push_back(sd[qidx[i]]);
+      blocks[block_of[i]].push_back((uint64_t)pca_pos[i]);
+    }
+  check(ctx, gpca_set_pca_snps(ctx, pca_orig.data(), n_pca, pmean.data(), psd.data()), "set_pca_snps");
+  std::vector<uint64_t> offs(n_blk + 1, 0), flat;
+  for (uint64_t b = 0; b < n_blk; ++b) {
+    offs[b + 1] = offs[b] + blocks[b].size();
+    flat.insert(flat.end(), blocks[b].begin(), blocks[b].end());
+  }
+  const uint32_t k = a.es.target_num_global_pcs;
+  std::vector<float> scores(n * k), loadings(n_pca * k);
+  std::vector<double> ev(k);
+  uint32_t k_out = 0;
+  const auto t0 = std::chrono::steady_clock::now();
+  check(ctx, gpca_eigensnp(ctx, &a.es, offs.data(), n_blk, flat.data(), scores.data(), ev.data(), loadings.data(), &k_out), "eigensnp");
+  const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  info("EigenSNP PCA algorithm completed in " + std::to_string(ms) + " ms.");
+  // outputs (main.rs:382-408)
+  make_parent_dirs(a.out);
+  std::vector<std::string> names;
+  if (use_keep) for (int64_t i : keep_idx) names.push_back(iids[i]);
+  else names = iids;
+  write_pcs<float>(a.out, "eigensnp.pca.tsv", names, scores.data(), n, k_out);
+  ev.resize(k_out);
+  write_eigenvalues(a.out, ev);
+  if (k_out > 0) {
+    FILE* f = create_output(a.out, "eigensnp.loadings.tsv");
+    fputs("VariantID\tChrom\tPos", f);
+    for (uint32_t j = 1; j <= k_out; ++j) fprintf(f, "\tPC%u_loading", j);
+    fputc('\n', f);
+    for (uint64_t i = 0; i < n_pca; ++i) {
+      const uint64_t o = pca_orig[i];
+      fprintf(f, "%s\t%s\t%llu", sid[o].c_str(), chrom[o].c_str(), (unsigned long long)(uint64_t)bp[o]);
+      for (uint32_t j = 0; j < k_out; ++j) fprintf(f, "\t%.6f", (double)loadings[i * k_out + j]);
+      fputc('\n', f);
+    }
+    fclose(f);
+  }
+  gpca_destroy(ctx);
+  return 0;
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+  const Args a = parse(argc, argv);
+  const auto t0 = std::chrono::steady_clock::now();
+  const int rc = a.eigensnp ? run_eigensnp(a) : run_vcf(a);
+  const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  info(std::string("genomic_pca (mode: ") + (a.eigensnp ? "EigenSNP" : "VCF") + ") finished successfully in " + std::to_string(s) + " s.");
+  return rc;
+}

@@ -1,0 +1,123 @@
+"""Drop-in CLI (genomic_pca_b200/genomic_pca): flag surface / messages on the CPU, full workflows on the GPU."""
+import gzip
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import bed, vcf
+
+from conftest import ROOT
+from helpers import make_dataset
+
+CLI = os.path.join(ROOT, "genomic_pca_b200", "genomic_pca")
+
+
+def _run(*args):
+    return subprocess.run([CLI, *args], capture_output=True, text=True)
+
+
+def test_cli_argument_surface():
+    assert os.path.exists(CLI), "build the CLI with __graft_entry__.build()"
+    h = _run("--help")
+    for flag in ["--vcf-dir", "--components", "--maf", "--rfit-seed", "--eigensnp", "--bed-file", "--ld-block-file",
+                 "--eigensnp-sample-keep-file", "--eigensnp-min-call-rate", "--eigensnp-min-maf", "--eigensnp-max-hwe-p",
+                 "--eigensnp-k-global", "--eigensnp-components-per-block", "--eigensnp-subset-factor",
+                 "--eigensnp-min-subset-size", "--eigensnp-max-subset-size", "--eigensnp-global-oversampling",
+                 "--eigensnp-global-power-iter", "--eigensnp-local-oversampling", "--eigensnp-local-power-iter",
+                 "--eigensnp-seed", "--eigensnp-snp-strip-size", "--eigensnp-refine-passes",
+                 "--eigensnp-collect-diagnostics", "--out", "--threads", "--log-level"]:
+        assert flag in h.stderr, flag                                      # src/main.rs:505-592
+    r = _run("-o", "/tmp/x")
+    assert r.returncode != 0 and "--vcf-dir is required" in r.stderr      # main.rs:116
+    r = _run("-o", "/tmp/x", "-d", "/tmp")
+    assert r.returncode != 0 and "--components is required" in r.stderr   # main.rs:119
+    r = _run("-o", "/tmp/x", "--eigensnp")
+    assert r.returncode != 0 and "--bed-file is required" in r.stderr     # main.rs:296
+    r = _run("-d", "/tmp", "-k", "3")
+    assert r.returncode != 0 and "--out" in r.stderr
+
+
+def _write_plink(tmp, g, payload, chrom="1"):
+    m, n = g.shape
+    (tmp / "d.bed").write_bytes(bytes([0x6C, 0x1B, 0x01]) + payload.tobytes())
+    (tmp / "d.fam").write_text("".join(f"F{i} S{i} 0 0 0 -9\n" for i in range(n)))
+    (tmp / "d.bim").write_text("".join(f"{chrom}\trs{j}\t0\t{1000 + 10 * j}\tA\tG\n" for j in range(m)))
+
+
+@pytest.mark.gpu
+def test_cli_eigensnp_workflow(tmp_path, gpu_ctx):
+    import genomic_pca_b200 as gp
+    from genomic_pca_b200 import plink
+    g, payload = make_dataset(400, 1500, n_pops=4, seed=31)
+    _write_plink(tmp_path, g, payload)
+    (tmp_path / "ld.txt").write_text("# blocks\nchr1 1000 5990\n1 6000 10990\nchr1 11000 99999999\n")
+    out = tmp_path / "res" / "run"
+    r = _run("--eigensnp", "--bed-file", str(tmp_path / "d.bed"), "--ld-block-file", str(tmp_path / "ld.txt"),
+             "-o", str(out), "--eigensnp-k-global", "3", "--eigensnp-min-subset-size", "100",
+             "--eigensnp-max-subset-size", "300", "--eigensnp-subset-factor", "0.5", "--eigensnp-seed", "9")
+    assert r.returncode == 0, r.stderr
+    pcs = (tmp_path / "res" / "run.eigensnp.pca.tsv").read_text().splitlines()
+    assert pcs[0] == "SampleID\tPC1\tPC2\tPC3" and len(pcs) == 401 and pcs[1].split("\t")[0] == "S0"
+    evs = (tmp_path / "res" / "run.eigenvalues.tsv").read_text().splitlines()
+    assert evs[0] == "PC\tEigenvalue" and len(evs) == 4
+    lds = (tmp_path / "res" / "run.eigensnp.loadings.tsv").read_text().splitlines()
+    assert lds[0] == "VariantID\tChrom\tPos\tPC1_loading\tPC2_loading\tPC3_loading"
+    # same numbers as the library driven from Python with the same configuration
+    chrom, sid, bp = plink.read_bim(str(tmp_path / "d.bim"))
+    prep = plink.prepare_data_for_eigen_snp(gpu_ctx, payload, plink.read_fam(str(tmp_path / "d.fam")), chrom, bp,
+                                            plink.parse_ld_block_file(str(tmp_path / "ld.txt")))
+    cfg = gp.EigenSnpConfig(target_num_global_pcs=3, min_subset_size=100, max_subset_size=300, subset_factor=0.5,
+                            random_seed=9)
+    sc, ev, load = gpu_ctx.eigensnp(prep["block_snp_ids"], cfg)
+    got = np.array([[float(x) for x in ln.split("\t")[1:]] for ln in pcs[1:]])
+    assert np.abs(got - sc).max() <= 1e-6 + 1e-6 * np.abs(sc).max()
+    got_ev = np.array([float(ln.split("\t")[1]) for ln in evs[1:]])
+    assert np.abs(got_ev - ev).max() <= 1e-6 + 1e-6 * np.abs(ev).max()
+    assert len(lds) - 1 == prep["pca_original_idx"].size
+    assert lds[1].split("\t")[0] == f"rs{prep['pca_original_idx'][0]}"
+
+
+@pytest.mark.gpu
+def test_cli_vcf_workflow(tmp_path, gpu_ctx):
+    g, _ = make_dataset(120, 900, n_pops=3, seed=33)
+    g = g.astype(np.uint8)
+
+    def vcf_text(rows, chrom, with_bad):
+        lines = ["##fileformat=VCFv4.2", '##FORMAT=<ID=GT,Number=1,Type=String,Description="Genotype">',
+                 "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + "\t".join(f"s{i}" for i in range(120))]
+        gt = {0: "0|0", 1: "0|1", 2: "1/1"}
+        for j, row in enumerate(rows):
+            lines.append(f"{chrom}\t{100 + j}\t.\tA\tC\t.\t.\t.\tGT:DP\t" + "\t".join(gt[int(v)] + ":7" for v in row))
+        if with_bad:
+            lines.append(f"{chrom}\t5000\t.\tAT\tC\t.\t.\t.\tGT\t" + "\t".join(["0|1"] * 120))          # REF len 2
+            lines.append(f"{chrom}\t5001\t.\tA\tC,G\t.\t.\t.\tGT\t" + "\t".join(["0|1"] * 120))         # multi-allelic
+            lines.append(f"{chrom}\t5002\t.\tA\tC\t.\t.\t.\tGT\t" + "\t".join(["./."] + ["0|1"] * 119))  # missing
+        return "\n".join(lines) + "\n"
+
+    d = tmp_path / "vcfs"
+    d.mkdir()
+    t2 = vcf_text(g[500:], "2", True)
+    with gzip.open(d / "b.chr2.vcf.gz", "wt") as f:
+        f.write(t2)
+    t1 = vcf_text(g[:500], "1", False)
+    (d / "a.chr1.vcf").write_text(t1)
+    (d / "notes.txt").write_text("ignored")
+    out = tmp_path / "o" / "v"
+    r = _run("-d", str(d), "-o", str(out), "-k", "3", "--maf", "0.05", "--rfit-seed", "11")
+    assert r.returncode == 0, r.stderr
+    pcs = (tmp_path / "o" / "v.vcf.pca.tsv").read_text().splitlines()
+    assert pcs[0] == "SampleID\tPC1\tPC2\tPC3" and len(pcs) == 121 and pcs[1].startswith("s0\t")
+    assert (tmp_path / "o" / "v.eigenvalues.tsv").read_text() == "PC\tEigenvalue\n"        # main.rs:676 quirk kept
+    # same numbers as: oracle VCF filter semantics -> library rfit with the same seed
+    s1, ids1, d1 = vcf.parse_vcf_text(t1, 0.05)
+    s2, ids2, d2 = vcf.parse_vcf_text(t2, 0.05)
+    dos = np.concatenate([d1, d2])                     # files in sorted-path order (main.rs:152)
+    gpu_ctx.load_u8_variant_major(dos)
+    keep, mean, sd = gpu_ctx.vcf_maf_filter(0.05)
+    assert keep.all()
+    gpu_ctx.set_pca_snps_mask(keep, mean, sd)
+    sc, ev, _ = gpu_ctx.rfit(3, 10, power_iters=2, seed=11, want_loadings=False)
+    got = np.array([[float(x) for x in ln.split("\t")[1:]] for ln in pcs[1:]])
+    assert np.abs(got - sc).max() <= 1e-6 + 1e-6 * np.abs(sc).max()
