@@ -63,7 +63,7 @@ extern "C" void gpca_reset_launch_count(gpca_ctx* c) {
 }
 extern "C" int gpca_set_sketch_engine(gpca_ctx* c, int engine) {
   CHECK_CTX(c);
-  if (engine != 0 && engine != 1) return fail(c, GPCA_ERR_INVALID, "engine must be 0 or 1");
+  if (engine < 0 || engine > 2) return fail(c, GPCA_ERR_INVALID, "engine must be 0 (SIMT), 1 (tcgen05 f16) or 2 (tcgen05 i8)");
   c->engine = engine;
   return GPCA_OK;
 }

@@ -268,7 +268,10 @@ int launch_sketch(gpca_ctx* c, const SketchProblem& p) {
   if (p.G.rows == 0 || p.G.cols == 0) return GPCA_OK;
   int rc = GPCA_ERR_INVALID;
   bool done = false;
-  if (c->engine == 1 && sketch_tc_supported(c, p)) {
+  if (c->engine == 2 && sketch_i8_supported(c, p)) {
+    rc = launch_sketch_i8(c, p);
+    done = true;
+  } else if (c->engine >= 1 && sketch_tc_supported(c, p)) {
     rc = launch_sketch_tc(c, p);
     done = true;
   }

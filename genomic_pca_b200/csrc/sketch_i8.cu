@@ -1,0 +1,561 @@
+// sketch_i8.cu -- integer tensor-core engine for the sketch pass (engine 2, l <= 32).
+//
+//   acc[r, :] = sum_k code(r,k) * B[k, :]    computed EXACTLY in int32 from
+//     A = the 2-bit dosage codes widened to u8 in registers (4 genotypes per register:
+//         r_j = (w >> 2j) & 0x03030303, shifts on the FMA pipe, one LOP3 per 4 genotypes) and stored to TMEM,
+//     B = the dense operand quantised to 16-bit fixed point (relative to max|f o B|) and split into two
+//         signed 8-bit limbs q = 256*hi + lo, hi/lo in [-128,127]  ->  N = 64 columns (hi | lo) per MMA,
+//   with tcgen05.mma.kind::i8 (u8 x s8 -> s32, A from TMEM, B from smem).  The epilogue recombines
+//   (256*D_hi + D_lo) in f64, rescales, and applies the rank-one standardisation correction.
+//
+// Why a second tensor engine: in the fp16 engine the ALU pipe (LOP3, 64 lanes/clk/SM) is the
+// co-limiter with HBM -- 9 ALU ops per 16 genotypes; here it is 4, TMEM store traffic is halved, a TMEM slot holds
+// twice the genotypes, the accumulation is exact (bit-reproducible for any K split), and the only rounding left is the
+// 16-bit quantisation of the dense operand (about 2^-15 of the column maximum, tighter than fp16's 2^-11).
+// Same warp roles / rings / persistent scheduling as sketch_tc.cu.
+#include <cuda.h>
+
+#include "sketch_tc.cuh"
+#include "tc_ptx.cuh"
+
+namespace {
+using namespace tcptx;
+
+constexpr int RT = 2;              // row tiles of 128 rows per CTA
+constexpr int STAGE_FIELDS = 256;  // 64 B per row per stage
+constexpr int CHUNKS = 4;          // 64-field chunks per stage
+constexpr int A_TILE_BYTES = 128 * 64;
+constexpr int NUM_THREADS = 352;
+constexpr int NL = 32;             // logical columns
+constexpr int NM = 64;             // MMA N = hi | lo limbs
+constexpr int SA = 4, SB = 3, SLOTS = 4;
+constexpr int A_STAGE_BYTES = RT * A_TILE_BYTES;
+constexpr int B_STAGE_BYTES = STAGE_FIELDS * NM;       // 1 byte per element
+constexpr int TMEM_COLS = 256;
+constexpr int D_COL0 = 0;                              // RT * 64 accumulator columns
+constexpr int A_COL0 = RT * NM;                        // SLOTS * RT * 16 columns
+static_assert(RT * NM + SLOTS * RT * 16 <= TMEM_COLS, "TMEM budget");
+constexpr int SMEM_BYTES = SA * A_STAGE_BYTES + SB * B_STAGE_BYTES + 256 + 320;
+constexpr uint32_t MAX_STAGES_PER_ITEM = 20000;        // 3 * 128 * 256 * 20000 < 2^31: no int32 overflow
+
+// 16 fields of a word -> 4 registers of 4 x u8 (register j holds fields j, j+4, j+8, j+12)
+__device__ __forceinline__ void expand_word_u8(uint32_t w, uint32_t* r) {
+  r[0] = w & 0x03030303u;
+  r[1] = __umulhi(w, 1u << 30) & 0x03030303u;   // w >> 2 on the FMA pipe
+  r[2] = __umulhi(w, 1u << 28) & 0x03030303u;   // w >> 4
+  r[3] = __umulhi(w, 1u << 26) & 0x03030303u;   // w >> 6
+}
+
+struct I8Params {
+  const int8_t* bimg;   // [total_stages][STAGE_FIELDS * 64] bytes (UMMA K-major core-matrix image, hi|lo limbs)
+  uint64_t rows;
+  uint32_t total_stages, stages_per_split, ksplit, row_groups, n_items;
+  const float* a;
+  const float* b;
+  const float* cvec;
+  const float* scales;  // [0] = quantisation scale, [1] = dequantisation scale
+  float* out;
+  uint32_t ldo, l;
+  float* partial;       // [ksplit][rows][32]
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 2) sketch_i8_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                                    const I8Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
+  const uint32_t a_ring = smem_base;
+  const uint32_t b_ring = smem_base + SA * A_STAGE_BYTES;
+  const uint32_t bars = b_ring + SB * B_STAGE_BYTES;
+  auto bar_afull = [&](int s) { return bars + 8u * s; };
+  auto bar_aempty = [&](int s) { return bars + 8u * (4 + s); };
+  auto bar_bfull = [&](int s) { return bars + 8u * (8 + s); };
+  auto bar_tfull = [&](int j) { return bars + 8u * (12 + j); };
+  auto bar_tempty = [&](int j) { return bars + 8u * (20 + j); };
+  auto bar_bempty = [&](int s) { return bars + 8u * (24 + s); };
+  const uint32_t bar_accfull = bars + 8u * 28;
+  const uint32_t bar_accempty = bars + 8u * 29;
+  const uint32_t tmem_slot = bars + 8u * 30;
+  const uint32_t cvec_smem = bars + 256;
+  float* cv_s = reinterpret_cast<float*>(smem_raw + (cvec_smem - smem_base));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < SA; ++s) {
+      mbar_init(bar_afull(s), 1);
+      mbar_init(bar_aempty(s), 4 * RT);
+    }
+    for (int s = 0; s < SB; ++s) {
+      mbar_init(bar_bfull(s), 1);
+      mbar_init(bar_bempty(s), 1);
+    }
+    for (int j = 0; j < SLOTS; ++j) {
+      mbar_init(bar_tfull(j), 4 * RT);
+      mbar_init(bar_tempty(j), 1);
+    }
+    mbar_init(bar_accfull, 1);
+    mbar_init(bar_accempty, 4 * RT);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  if (threadIdx.x >= 64 && threadIdx.x < 128) {
+    const int i = threadIdx.x - 64;
+    cv_s[i] = (i < NL) ? p.cvec[i] : 0.0f;
+  } else if (threadIdx.x == 128) {
+    cv_s[64] = p.scales[1];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const float s_scale = cv_s[64];
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0 || warp == 10) {
+    // ---- producers: warp 0 = packed genotype tiles (TMA 2-D), warp 10 = B image (1-D bulk copies)
+    const bool is_a = (warp == 0);
+    uint32_t it = 0;
+    for (uint32_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      const uint32_t ks = item / p.row_groups, rg = item - ks * p.row_groups;
+      const uint32_t st0 = ks * p.stages_per_split;
+      uint32_t st1 = st0 + p.stages_per_split;
+      if (st1 > p.total_stages) st1 = p.total_stages;
+      const int row0 = (int)(rg * (RT * 128));
+      for (uint32_t st = st0; st < st1; ++st, ++it) {
+        if (is_a) {
+          const int s = it % SA;
+          const uint32_t ph = (it / SA) & 1u;
+          mbar_wait(bar_aempty(s), ph ^ 1u);
+          if (elect_one()) {
+            const uint32_t sbase = a_ring + s * A_STAGE_BYTES;
+            mbar_arrive_expect_tx(bar_afull(s), A_STAGE_BYTES);
+#pragma unroll
+            for (int t = 0; t < RT; ++t)
+              tma_load_2d(sbase + t * A_TILE_BYTES, &tmap, bar_afull(s), (int)(st * 64), row0 + t * 128);
+          }
+        } else {
+          const int s = it % SB;
+          const uint32_t ph = (it / SB) & 1u;
+          mbar_wait(bar_bempty(s), ph ^ 1u);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(bar_bfull(s), B_STAGE_BYTES);
+            bulk_load_1d(b_ring + s * B_STAGE_BYTES, p.bimg + (size_t)st * B_STAGE_BYTES, B_STAGE_BYTES, bar_bfull(s));
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer: D = s32, A = u8 (TMEM), B = s8 (smem, K-major, no swizzle), M = 128, N = 64, K = 32
+    const uint32_t idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(NM >> 3) << 17) | (8u << 24);
+    // B descriptor: LBO = 64 rows * 16 B = 1024 B (next 16-wide K chunk), SBO = 128 B (next 8 columns), version 1
+    const uint32_t desc_lo_const = (uint32_t)(1024 >> 4) << 16;
+    const uint32_t desc_hi = (uint32_t)(128 >> 4) | (1u << 14);
+    uint32_t it = 0, cit = 0, item_idx = 0;
+    for (uint32_t item = blockIdx.x; item < p.n_items; item += gridDim.x, ++item_idx) {
+      const uint32_t ks = item / p.row_groups;
+      const uint32_t st0 = ks * p.stages_per_split;
+      uint32_t st1 = st0 + p.stages_per_split;
+      if (st1 > p.total_stages) st1 = p.total_stages;
+      mbar_wait(bar_accempty, (item_idx & 1u) ^ 1u);
+      tc_fence_after();
+      uint32_t acc_flag = 0;
+      for (uint32_t st = st0; st < st1; ++st, ++it) {
+        const int s = it % SB;
+        const uint32_t ph = (it / SB) & 1u;
+        mbar_wait(bar_bfull(s), ph);
+        const uint32_t bsm = b_ring + s * B_STAGE_BYTES;
+#pragma unroll
+        for (int q = 0; q < CHUNKS; ++q, ++cit) {
+          const int slot = cit % SLOTS;
+          const uint32_t sph = (cit / SLOTS) & 1u;
+          mbar_wait(bar_tfull(slot), sph);
+          tc_fence_after();
+          if (elect_one()) {
+#pragma unroll
+            for (int t = 0; t < RT; ++t) {
+              const uint32_t d_t = tmem_base + D_COL0 + t * NM;
+              const uint32_t a_t = tmem_base + A_COL0 + (slot * RT + t) * 16;
+#pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                const uint32_t baddr = bsm + (uint32_t)((q * 2 + i) * (32 * NM));
+                const uint64_t bdesc = ((uint64_t)desc_hi << 32) | (uint64_t)(desc_lo_const | ((baddr >> 4) & 0x3FFFu));
+                tc_mma_ts_i8(d_t, a_t + 8 * i, bdesc, idesc, acc_flag | (uint32_t)i);
+              }
+            }
+            tc_commit(bar_tempty(slot));
+          }
+          __syncwarp();
+          acc_flag = 1;
+        }
+        if (elect_one()) tc_commit(bar_bempty(s));
+        __syncwarp();
+      }
+      if (elect_one()) tc_commit(bar_accfull);
+      __syncwarp();
+    }
+  } else if (warp >= 2 && warp < 10) {
+    // ---- expanders + epilogue
+    const int tile = (warp - 2) >> 2;
+    const int quarter = warp & 3;
+    const int row_in_tile = quarter * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const uint32_t sw = (uint32_t)((row_in_tile >> 1) & 3);
+    uint32_t it = 0, cit = 0, item_idx = 0;
+    for (uint32_t item = blockIdx.x; item < p.n_items; item += gridDim.x, ++item_idx) {
+      const uint32_t ks = item / p.row_groups, rg = item - ks * p.row_groups;
+      const uint32_t st0 = ks * p.stages_per_split;
+      uint32_t st1 = st0 + p.stages_per_split;
+      if (st1 > p.total_stages) st1 = p.total_stages;
+      for (uint32_t st = st0; st < st1; ++st, ++it) {
+        const int s = it % SA;
+        const uint32_t ph = (it / SA) & 1u;
+        mbar_wait(bar_afull(s), ph);
+        const uint32_t arow = a_ring + s * A_STAGE_BYTES + tile * A_TILE_BYTES + row_in_tile * 64;
+        uint4 v[CHUNKS];
+#pragma unroll
+        for (int q = 0; q < CHUNKS; ++q) {
+          const uint32_t addr = arow + (((uint32_t)q ^ sw) << 4);
+          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(v[q].x), "=r"(v[q].y), "=r"(v[q].z), "=r"(v[q].w)
+                       : "r"(addr));
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_aempty(s));
+#pragma unroll
+        for (int q = 0; q < CHUNKS; q += 2, cit += 2) {
+          const int slot0 = cit % SLOTS, slot1 = (cit + 1) % SLOTS;
+          const uint32_t sph0 = (cit / SLOTS) & 1u, sph1 = ((cit + 1) / SLOTS) & 1u;
+          {
+            uint32_t r[16];
+            expand_word_u8(v[q].x, r + 0);
+            expand_word_u8(v[q].y, r + 4);
+            expand_word_u8(v[q].z, r + 8);
+            expand_word_u8(v[q].w, r + 12);
+            mbar_wait(bar_tempty(slot0), sph0 ^ 1u);
+            tc_fence_after();
+            tmem_st16(tmem_base + lane_addr + A_COL0 + (slot0 * RT + tile) * 16, r);
+          }
+          {
+            uint32_t r[16];
+            expand_word_u8(v[q + 1].x, r + 0);
+            expand_word_u8(v[q + 1].y, r + 4);
+            expand_word_u8(v[q + 1].z, r + 8);
+            expand_word_u8(v[q + 1].w, r + 12);
+            mbar_wait(bar_tempty(slot1), sph1 ^ 1u);
+            tc_fence_after();
+            tmem_st16(tmem_base + lane_addr + A_COL0 + (slot1 * RT + tile) * 16, r);
+          }
+          tc_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(bar_tfull(slot0));
+            mbar_arrive(bar_tfull(slot1));
+          }
+        }
+      }
+      // ---- epilogue
+      const uint64_t r = (uint64_t)rg * (RT * 128) + tile * 128 + row_in_tile;
+      float ar = 1.0f, br = 1.0f;
+      if (!p.partial && r < p.rows) {
+        if (p.a) ar = __ldg(p.a + r);
+        if (p.b) br = __ldg(p.b + r);
+      }
+      mbar_wait(bar_accfull, item_idx & 1u);
+      tc_fence_after();
+      uint32_t hi[32], lo[32];
+      tmem_ld32(tmem_base + lane_addr + D_COL0 + tile * NM, hi);
+      tmem_ld32(tmem_base + lane_addr + D_COL0 + tile * NM + 32, lo);
+      tc_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_accempty);
+      if (r < p.rows) {
+        const double scale = (double)s_scale;
+        if (p.partial) {
+          float* dst = p.partial + ((uint64_t)ks * p.rows + r) * NL;
+#pragma unroll
+          for (int c = 0; c < NL; c += 4) {
+            float4 o;
+            o.x = (float)((double)((long long)(int)hi[c + 0] * 256 + (int)lo[c + 0]) * scale);
+            o.y = (float)((double)((long long)(int)hi[c + 1] * 256 + (int)lo[c + 1]) * scale);
+            o.z = (float)((double)((long long)(int)hi[c + 2] * 256 + (int)lo[c + 2]) * scale);
+            o.w = (float)((double)((long long)(int)hi[c + 3] * 256 + (int)lo[c + 3]) * scale);
+            *reinterpret_cast<float4*>(dst + c) = o;
+          }
+        } else {
+          float* dst = p.out + r * p.ldo;
+          const bool vec2 = (p.ldo & 1u) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 7) == 0;
+#pragma unroll
+          for (int c = 0; c < NL; c += 2) {
+            const float v0 = ar * (float)((double)((long long)(int)hi[c] * 256 + (int)lo[c]) * scale) - br * cv_s[c];
+            const float v1 =
+                ar * (float)((double)((long long)(int)hi[c + 1] * 256 + (int)lo[c + 1]) * scale) - br * cv_s[c + 1];
+            if (vec2 && (uint32_t)c + 1 < p.l) {
+              *reinterpret_cast<float2*>(dst + c) = make_float2(v0, v1);
+            } else {
+              if ((uint32_t)c < p.l) dst[c] = v0;
+              if ((uint32_t)c + 1 < p.l) dst[c + 1] = v1;
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---- operand preparation ----------------------------------------------------------------------------------------
+// (column statistics reuse tc_colstats_kernel's twin below: cvec = e^T Bin in f64, amax = max |f o Bin|)
+__global__ void __launch_bounds__(256) i8_colstats_kernel(const float* __restrict__ bin, uint64_t K, uint32_t l,
+                                                          uint32_t ld, const float* __restrict__ f,
+                                                          const float* __restrict__ e, double* __restrict__ cpart,
+                                                          unsigned int* __restrict__ amax_bits) {
+  __shared__ double red[256];
+  __shared__ float redm[256];
+  const int cidx = threadIdx.x & 31;
+  const int rr = threadIdx.x >> 5;
+  const bool c0 = (uint32_t)cidx < l;
+  double acc0 = 0.0;
+  float mx = 0.0f;
+  const uint64_t stride = (uint64_t)gridDim.x * 8;
+  for (uint64_t k = (uint64_t)blockIdx.x * 8 + rr; k < K; k += 4 * stride) {
+    float x0[4], ek[4], fk[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint64_t kk = k + u * stride;
+      const bool live = kk < K;
+      x0[u] = (live && c0) ? bin[kk * ld + cidx] : 0.0f;
+      ek[u] = (live && e) ? e[kk] : 1.0f;
+      fk[u] = (live && f) ? f[kk] : 1.0f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      acc0 += (double)(x0[u] * ek[u]);
+      mx = fmaxf(mx, fabsf(x0[u] * fk[u]));
+    }
+  }
+  red[threadIdx.x] = acc0;
+  redm[threadIdx.x] = mx;
+  __syncthreads();
+  if (rr == 0) {
+    double s0 = 0.0;
+    float m = 0.0f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      s0 += red[q * 32 + cidx];
+      m = fmaxf(m, redm[q * 32 + cidx]);
+    }
+    cpart[(uint64_t)blockIdx.x * 32 + cidx] = s0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (cidx == 0 && m > 0.0f && isfinite(m)) atomicMax(amax_bits, __float_as_uint(m));
+  }
+}
+
+__global__ void i8_finalize_stats_kernel(const double* __restrict__ cpart, int nparts, float* __restrict__ cvec,
+                                         unsigned int* __restrict__ amax_bits, float* __restrict__ scales) {
+  const int cidx = threadIdx.x;
+  if (cidx < 32) {
+    double s = 0.0;
+    for (int q = 0; q < nparts; ++q) s += cpart[(uint64_t)q * 32 + cidx];
+    cvec[cidx] = (float)s;
+  }
+  if (cidx == 0) {
+    const float m = __uint_as_float(*amax_bits);
+    scales[0] = (m > 0.0f) ? 32512.0f / m : 0.0f;     // |q| <= 32512 = 127*256: both limbs fit s8
+    scales[1] = (m > 0.0f) ? m / 32512.0f : 0.0f;
+    *amax_bits = 0u;
+  }
+}
+
+// B image: MMA group g covers fields 32g .. 32g+31; K-slot s (0..31) holds field 32g + 16*(c/4) + (c%4) + 4*b with
+// c = s/4, b = s%4 (the order in which expand_word_u8 lays the fields into TMEM columns/bytes).
+// Element (slot s, column n in 0..63; n < 32: hi limb of logical column n, n >= 32: lo limb of column n-32) lives at
+//   g*32*64 + (s/16)*(64*16) + (n/8)*128 + (n%8)*16 + (s%16)       (UMMA K-major core matrices, no swizzle)
+__global__ void __launch_bounds__(256) prep_b_i8_kernel(const float* __restrict__ bin, uint64_t K, uint64_t Kpad,
+                                                        uint32_t l, uint32_t ld, const float* __restrict__ f,
+                                                        const float* __restrict__ scales, int8_t* __restrict__ img) {
+  const uint64_t total = (Kpad / 16) * NL;   // one thread per (16-slot K chunk, logical column): writes 16 B hi + 16 B lo
+  const float qs = scales[0];
+  for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < total;
+       t += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t n = (uint32_t)(t % NL);
+    const uint64_t kc = t / NL;               // global 16-slot chunk
+    const uint64_t g = kc >> 1;
+    const uint32_t half_idx = (uint32_t)(kc & 1);
+    __align__(16) int8_t vhi[16], vlo[16];
+#pragma unroll
+    for (int ss = 0; ss < 16; ++ss) {
+      const int s = half_idx * 16 + ss;
+      const int cc = s >> 2, bb = s & 3;
+      const uint64_t k = g * 32 + 16 * (cc >> 2) + (cc & 3) + 4 * bb;
+      int q = 0;
+      if (k < K && n < l) {
+        float v = bin[k * ld + n];
+        if (f) v *= f[k];
+        q = __float2int_rn(v * qs);
+        q = max(-32512, min(32512, q));
+      }
+      const int h = (q + 128) >> 8;           // floor((q+128)/256): lo = q - 256 h in [-128, 127]
+      vhi[ss] = (int8_t)h;
+      vlo[ss] = (int8_t)(q - 256 * h);
+    }
+    const uint64_t base = g * 32 * NM + (uint64_t)half_idx * (NM * 16);
+    *reinterpret_cast<uint4*>(img + base + (n >> 3) * 128 + (n & 7) * 16) = *reinterpret_cast<const uint4*>(vhi);
+    *reinterpret_cast<uint4*>(img + base + ((n + 32) >> 3) * 128 + (n & 7) * 16) = *reinterpret_cast<const uint4*>(vlo);
+  }
+}
+
+__global__ void sketch_reduce_i8_kernel(const float* __restrict__ partial, int nsplit, uint64_t rows,
+                                        const float* __restrict__ a, const float* __restrict__ b,
+                                        const float* __restrict__ cvec, float* __restrict__ out, uint32_t ldo, uint32_t l) {
+  const uint64_t total = rows * NL;
+  for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < total;
+       t += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t r = t / NL;
+    const uint32_t cc = (uint32_t)(t % NL);
+    if (cc >= l) continue;
+    float s = 0.0f;
+    for (int q = 0; q < nsplit; ++q) s += partial[((uint64_t)q * rows + r) * NL + cc];
+    const float ar = a ? a[r] : 1.0f, br = b ? b[r] : 1.0f;
+    out[r * ldo + cc] = ar * s - br * cvec[cc];
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_fn_i8() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+}  // namespace
+
+bool sketch_i8_supported(gpca_ctx* c, const SketchProblem& p) {
+  (void)c;
+  if (p.l == 0 || p.l > 32) return false;
+  if (p.G.rows < 128 || p.G.cols < 256) return false;
+  if (p.G.pitch % 16 != 0 || (reinterpret_cast<uintptr_t>(p.G.p) & 15) != 0) return false;
+  if (p.G.pitch >= (1ull << 31) || p.G.rows >= (1ull << 31)) return false;
+  return get_encode_fn_i8() != nullptr;
+}
+
+int launch_sketch_i8(gpca_ctx* c, const SketchProblem& p) {
+  const uint64_t K = p.G.cols, rows = p.G.rows;
+  const uint64_t Kpad = round_up(K, STAGE_FIELDS);
+  const uint32_t total_stages = (uint32_t)(Kpad / STAGE_FIELDS);
+  GPCA_CUDA_TRY(c, c->ws_bytes.alloc(Kpad * NM));
+  int8_t* img = reinterpret_cast<int8_t*>(c->ws_bytes.p);
+  int nb = (int)((K + 31) / 32);
+  if (nb > c->sm_count * 8) nb = c->sm_count * 8;
+  if (nb < 1) nb = 1;
+  GPCA_CUDA_TRY(c, c->ws_cpart.alloc((size_t)nb * 64));
+  GPCA_CUDA_TRY(c, c->ws_cvec.alloc(64 + 8));
+  float* cvec = c->ws_cvec.p;
+  float* scales = c->ws_cvec.p + 64;
+  unsigned int* amax = reinterpret_cast<unsigned int*>(c->ws_cvec.p + 66);
+  if (!c->tc_amax_zeroed) {
+    GPCA_CUDA_TRY(c, cudaMemsetAsync(amax, 0, sizeof(unsigned int), c->stream));
+    c->tc_amax_zeroed = true;
+  }
+  i8_colstats_kernel<<<nb, 256, 0, c->stream>>>(p.Bin, K, p.l, p.ld, p.f, p.e, c->ws_cpart.p, amax);
+  c->launches++;
+  GPCA_CUDA_TRY(c, cudaGetLastError());
+  i8_finalize_stats_kernel<<<1, 32, 0, c->stream>>>(c->ws_cpart.p, nb, cvec, amax, scales);
+  c->launches++;
+  GPCA_CUDA_TRY(c, cudaGetLastError());
+  {
+    const uint64_t total = (Kpad / 16) * NL;
+    const uint64_t blocks = (total + 255) / 256;
+    const int grid = (int)(blocks < (uint64_t)c->sm_count * 8 ? blocks : (uint64_t)c->sm_count * 8);
+    prep_b_i8_kernel<<<grid, 256, 0, c->stream>>>(p.Bin, K, Kpad, p.l, p.ld, p.f, scales, img);
+    c->launches++;
+    GPCA_CUDA_TRY(c, cudaGetLastError());
+  }
+  const uint32_t row_groups = (uint32_t)((rows + RT * 128 - 1) / (RT * 128));
+  const uint32_t slots = (uint32_t)c->sm_count * 2;
+  uint32_t ksplit = 1;
+  if (row_groups < 4 * slots) {
+    ksplit = (4 * slots + row_groups - 1) / row_groups;
+    const uint32_t max_split = (total_stages + 7) / 8;
+    if (ksplit > max_split) ksplit = max_split;
+    if (ksplit < 1) ksplit = 1;
+  }
+  const uint32_t min_split = (total_stages + MAX_STAGES_PER_ITEM - 1) / MAX_STAGES_PER_ITEM;   // int32 headroom
+  if (ksplit < min_split) ksplit = min_split;
+  const uint32_t spp = (total_stages + ksplit - 1) / ksplit;
+  ksplit = (total_stages + spp - 1) / spp;
+  const uint64_t n_items64 = (uint64_t)row_groups * ksplit;
+  if (n_items64 > 0x7fffffffull) {
+    c->set_error("sketch_i8: too many work items");
+    return GPCA_ERR_INVALID;
+  }
+  I8Params tp;
+  tp.bimg = img;
+  tp.rows = rows;
+  tp.total_stages = total_stages;
+  tp.stages_per_split = spp;
+  tp.ksplit = ksplit;
+  tp.row_groups = row_groups;
+  tp.n_items = (uint32_t)n_items64;
+  tp.a = p.a;
+  tp.b = p.b;
+  tp.cvec = cvec;
+  tp.scales = scales;
+  tp.out = p.out;
+  tp.ldo = p.ldo;
+  tp.l = p.l;
+  tp.partial = nullptr;
+  if (ksplit > 1) {
+    GPCA_CUDA_TRY(c, c->ws_partial.alloc((size_t)ksplit * rows * NL));
+    tp.partial = c->ws_partial.p;
+  }
+  CUtensorMap tmap;
+  {
+    EncodeTiledFn enc = get_encode_fn_i8();
+    const cuuint64_t dims[2] = {(cuuint64_t)(p.G.avail ? p.G.avail : p.G.pitch), (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)p.G.pitch};
+    const cuuint32_t box[2] = {64, 128};
+    const cuuint32_t estr[2] = {1, 1};
+    if (!enc || enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)p.G.p, dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+      c->set_error("sketch_i8: cuTensorMapEncodeTiled failed");
+      return GPCA_ERR_CUDA;
+    }
+  }
+  GPCA_CUDA_TRY(c, cudaFuncSetAttribute(sketch_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  const uint32_t grid = tp.n_items < slots ? tp.n_items : slots;
+  sketch_i8_kernel<<<grid, NUM_THREADS, SMEM_BYTES, c->stream>>>(tmap, tp);
+  c->launches++;
+  GPCA_CUDA_TRY(c, cudaGetLastError());
+  if (ksplit > 1) {
+    const uint64_t total = rows * NL;
+    const uint64_t blocks = (total + 255) / 256;
+    const int g2 = (int)(blocks < (uint64_t)c->sm_count * 8 ? blocks : (uint64_t)c->sm_count * 8);
+    sketch_reduce_i8_kernel<<<g2, 256, 0, c->stream>>>(tp.partial, (int)ksplit, rows, p.a, p.b, cvec, p.out, p.ldo, p.l);
+    c->launches++;
+    GPCA_CUDA_TRY(c, cudaGetLastError());
+  }
+  return GPCA_OK;
+}

@@ -51,7 +51,8 @@ const char* gpca_version(void);
 /* kernels launched by this context since creation / last reset (bench.py "gpu_launches") */
 uint64_t gpca_launch_count(const gpca_ctx* ctx);
 void gpca_reset_launch_count(gpca_ctx* ctx);
-/* 0 = SIMT fp32 path, 1 = tcgen05 path where the shape allows (default 1) */
+/* 0 = SIMT fp32 path, 1 = tcgen05 f16 path, 2 = tcgen05 i8 path (exact integer accumulation, l <= 32);
+ * engines 1/2 fall back to the next lower one for shapes they do not take */
 int gpca_set_sketch_engine(gpca_ctx* ctx, int engine);
 /* device time (ms) and algorithmic packed bytes of the sketch passes since the last reset */
 int gpca_sketch_stats(gpca_ctx* ctx, double* ms_total, double* packed_bytes_total, uint64_t* n_passes, int reset);

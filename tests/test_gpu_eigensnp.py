@@ -20,7 +20,7 @@ def _prep(ctx, n, m, pops, seed, missing=0.0):
     return standardized(g[idx], mean[idx], sd[idx])
 
 
-@pytest.mark.parametrize("engine", [0, 1])
+@pytest.mark.parametrize("engine", [0, 1, 2])
 def test_eigensnp_matches_oracle(gpu_ctx, engine):
     import genomic_pca_b200 as gp
     S = _prep(gpu_ctx, 1200, 5000, 5, seed=21)

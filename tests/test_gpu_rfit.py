@@ -28,7 +28,7 @@ def _prep(ctx, n, m, n_pops, seed, vcf=False):
     return standardized(g[idx], mean[idx], sd[idx])
 
 
-@pytest.mark.parametrize("engine", [0, 1])
+@pytest.mark.parametrize("engine", [0, 1, 2])
 @pytest.mark.parametrize("n,m,pops,k", [(600, 4000, 5, 4), (2504, 6000, 6, 5)])
 def test_rfit_matches_oracle_and_exact(gpu_ctx, engine, n, m, pops, k):
     S = _prep(gpu_ctx, n, m, pops, seed=n, vcf=True)

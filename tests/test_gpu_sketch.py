@@ -105,3 +105,22 @@ def test_sketch_tcgen05_with_missing(gpu_ctx):
     od, rd, on, rn = _run(gpu_ctx, S, 20, engine=1)
     assert _relerr(od, rd) < 1.5e-3
     assert _relerr(on, rn) < 1.5e-3
+
+
+@pytest.mark.parametrize("n,m,l", [(2504, 3000, 30), (700, 1500, 5), (256, 128 * 3 + 5, 17), (20000, 2000, 30),
+                                   (1000, 40000, 32)])
+def test_sketch_int8_engine_matches_dense(gpu_ctx, n, m, l):
+    """tcgen05 kind::i8 engine: exact int32 accumulation; the only rounding is the 16-bit quantisation of the dense
+    operand (relative to its global max)."""
+    S = _setup(gpu_ctx, n, m, seed=n + m + 2)
+    od, rd, on, rn = _run(gpu_ctx, S, l, engine=2)
+    assert _relerr(od, rd) < 3e-4
+    assert _relerr(on, rn) < 3e-4
+
+
+def test_sketch_int8_engine_missing_and_determinism(gpu_ctx):
+    S = _setup(gpu_ctx, 1500, 1200, seed=6, missing_rate=0.02)
+    od, rd, on, rn = _run(gpu_ctx, S, 20, engine=2)
+    assert _relerr(od, rd) < 3e-4 and _relerr(on, rn) < 3e-4
+    od2, _, on2, _ = _run(gpu_ctx, S, 20, engine=2)
+    assert np.array_equal(od, od2) and np.array_equal(on, on2)      # integer accumulation: bit-reproducible
