@@ -28,13 +28,13 @@ constexpr int A_TILE_BYTES = 128 * 64;
 constexpr int NUM_THREADS = 352;
 constexpr int NL = 32;             // logical columns
 constexpr int NM = 64;             // MMA N = hi | lo limbs
-constexpr int SA = 4, SB = 3, SLOTS = 4;
+constexpr int SA = 4, SB = 3, SLOTS = 2;   // a TMEM slot holds a chunk pair (128 fields) of both row tiles
 constexpr int A_STAGE_BYTES = RT * A_TILE_BYTES;
 constexpr int B_STAGE_BYTES = STAGE_FIELDS * NM;       // 1 byte per element
 constexpr int TMEM_COLS = 256;
 constexpr int D_COL0 = 0;                              // RT * 64 accumulator columns
-constexpr int A_COL0 = RT * NM;                        // SLOTS * RT * 16 columns
-static_assert(RT * NM + SLOTS * RT * 16 <= TMEM_COLS, "TMEM budget");
+constexpr int A_COL0 = RT * NM;                        // SLOTS * RT * 32 columns
+static_assert(RT * NM + SLOTS * RT * 32 <= TMEM_COLS, "TMEM budget");
 constexpr int SMEM_BYTES = SA * A_STAGE_BYTES + SB * B_STAGE_BYTES + 256 + 320;
 constexpr uint32_t MAX_STAGES_PER_ITEM = 20000;        // 3 * 128 * 256 * 20000 < 2^31: no int32 overflow
 
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) sketch_i8_kernel(const __grid_
         mbar_wait(bar_bfull(s), ph);
         const uint32_t bsm = b_ring + s * B_STAGE_BYTES;
 #pragma unroll
-        for (int q = 0; q < CHUNKS; ++q, ++cit) {
+        for (int q = 0; q < CHUNKS; q += 2, ++cit) {
           const int slot = cit % SLOTS;
           const uint32_t sph = (cit / SLOTS) & 1u;
           mbar_wait(bar_tfull(slot), sph);
@@ -179,9 +179,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) sketch_i8_kernel(const __grid_
 #pragma unroll
             for (int t = 0; t < RT; ++t) {
               const uint32_t d_t = tmem_base + D_COL0 + t * NM;
-              const uint32_t a_t = tmem_base + A_COL0 + (slot * RT + t) * 16;
+              const uint32_t a_t = tmem_base + A_COL0 + (slot * RT + t) * 32;
 #pragma unroll
-              for (int i = 0; i < 2; ++i) {
+              for (int i = 0; i < 4; ++i) {      // 4 MMAs of K = 32 cover the 128 fields of the pair
                 const uint32_t baddr = bsm + (uint32_t)((q * 2 + i) * (32 * NM));
                 const uint64_t bdesc = ((uint64_t)desc_hi << 32) | (uint64_t)(desc_lo_const | ((baddr >> 4) & 0x3FFFu));
                 tc_mma_ts_i8(d_t, a_t + 8 * i, bdesc, idesc, acc_flag | (uint32_t)i);
@@ -227,36 +227,27 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) sketch_i8_kernel(const __grid_
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_aempty(s));
 #pragma unroll
-        for (int q = 0; q < CHUNKS; q += 2, cit += 2) {
-          const int slot0 = cit % SLOTS, slot1 = (cit + 1) % SLOTS;
-          const uint32_t sph0 = (cit / SLOTS) & 1u, sph1 = ((cit + 1) / SLOTS) & 1u;
-          {
-            uint32_t r[16];
-            expand_word_u8(v[q].x, r + 0);
-            expand_word_u8(v[q].y, r + 4);
-            expand_word_u8(v[q].z, r + 8);
-            expand_word_u8(v[q].w, r + 12);
-            mbar_wait(bar_tempty(slot0), sph0 ^ 1u);
-            tc_fence_after();
-            tmem_st16(tmem_base + lane_addr + A_COL0 + (slot0 * RT + tile) * 16, r);
-          }
-          {
-            uint32_t r[16];
-            expand_word_u8(v[q + 1].x, r + 0);
-            expand_word_u8(v[q + 1].y, r + 4);
-            expand_word_u8(v[q + 1].z, r + 8);
-            expand_word_u8(v[q + 1].w, r + 12);
-            mbar_wait(bar_tempty(slot1), sph1 ^ 1u);
-            tc_fence_after();
-            tmem_st16(tmem_base + lane_addr + A_COL0 + (slot1 * RT + tile) * 16, r);
-          }
+        for (int q = 0; q < CHUNKS; q += 2, ++cit) {
+          const int slot = cit % SLOTS;
+          const uint32_t sph = (cit / SLOTS) & 1u;
+          uint32_t r0[16], r1[16];
+          expand_word_u8(v[q].x, r0 + 0);
+          expand_word_u8(v[q].y, r0 + 4);
+          expand_word_u8(v[q].z, r0 + 8);
+          expand_word_u8(v[q].w, r0 + 12);
+          expand_word_u8(v[q + 1].x, r1 + 0);
+          expand_word_u8(v[q + 1].y, r1 + 4);
+          expand_word_u8(v[q + 1].z, r1 + 8);
+          expand_word_u8(v[q + 1].w, r1 + 12);
+          mbar_wait(bar_tempty(slot), sph ^ 1u);      // the MMAs that read this slot have completed
+          tc_fence_after();
+          const uint32_t ta = tmem_base + lane_addr + A_COL0 + (slot * RT + tile) * 32;
+          tmem_st16(ta, r0);
+          tmem_st16(ta + 16, r1);
           tc_wait_st();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) {
-            mbar_arrive(bar_tfull(slot0));
-            mbar_arrive(bar_tfull(slot1));
-          }
+          if (lane == 0) mbar_arrive(bar_tfull(slot));
         }
       }
       // ---- epilogue
