@@ -312,7 +312,7 @@ def run_ours(args, rank, world):
     line = {
         "metric": "genotype_GBps_per_sketch_pass", "value": value, "unit": "GB/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f16xf32acc" if ctx_engine(ctx, args) else "f32",
+        "scaling": "weak", "vs_baseline": None, "dtype": {0: "f32", 1: "f16 x f16 -> f32 (tcgen05)", 2: "u8 x s8 -> s32 (tcgen05 kind::i8, exact)"}[ctx_engine(ctx, args)],
         "data": "synthetic",
         "config": {"workload": f"1000G-shape rfit k={K_COMPONENTS} oversample={OVERSAMPLE} q={POWER_ITERS}: "
                                f"{n} samples x {m} SNPs per GPU ({d_kept} after MAF 0.01), 2-bit packed, SNP-sharded",
@@ -333,7 +333,7 @@ def run_ours(args, rank, world):
 
 
 def ctx_engine(ctx, args):
-    return (args.engine if args.engine is not None else int(os.environ.get("GPCA_SKETCH_ENGINE", "1"))) == 1
+    return args.engine if args.engine is not None else int(os.environ.get("GPCA_SKETCH_ENGINE", "2"))
 
 
 def main():

@@ -67,7 +67,7 @@ struct gpca_ctx {
   cudaStream_t stream = nullptr;
   std::string err;
   uint64_t launches = 0;
-  int engine = 1;
+  int engine = 2;   // 0 SIMT fp32, 1 tcgen05 f16, 2 tcgen05 i8 (default; l > 32 falls back to 1)
 
   // collective hook / shard
   gpca_allreduce_fn allreduce = nullptr;
@@ -106,7 +106,8 @@ struct gpca_ctx {
   DevBuf<float> ws_bprep;      // prepared B' operand
   DevBuf<float> ws_partial;    // split-K partials
   DevBuf<float> ws_cvec;       // epilogue vector(s)
-  DevBuf<double> ws_f64;       // gram partials
+  DevBuf<double> ws_f64;       // f64 output staging
+  DevBuf<double> ws_gram;      // gram partials
   DevBuf<double> ws_cpart;     // column-sum partials
   DevBuf<double> ws_small;     // l x l matrices: G, evals, evecs, T
   DevBuf<uint8_t> ws_bytes;    // tcgen05 engine: fp16 B' image

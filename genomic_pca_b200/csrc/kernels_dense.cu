@@ -14,18 +14,25 @@
 // ------------------------------------------------------------------------------------------
 __global__ void gaussian_kernel(float* __restrict__ out, uint64_t rows, uint32_t cols, uint32_t ld, uint64_t seed,
                                 uint32_t stream, uint64_t row0) {
-  const uint64_t total = rows * ld;
+  const uint32_t groups = (ld + 3) / 4;          // one thread per (row, group of 4 columns): one Philox call
+  const uint64_t total = rows * groups;
   for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < total;
        t += (uint64_t)gridDim.x * blockDim.x) {
-    const uint64_t r = t / ld;
-    const uint32_t cidx = (uint32_t)(t - r * ld);
-    out[t] = (cidx < cols) ? philox_normal(seed, stream, row0 + r, cidx) : 0.0f;
+    const uint64_t r = t / groups;
+    const uint32_t cg = (uint32_t)(t - r * groups);
+    float z[4];
+    philox_normal4(seed, stream, row0 + r, cg, z);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t cidx = cg * 4 + j;
+      if (cidx < ld) out[r * ld + cidx] = (cidx < cols) ? z[j] : 0.0f;
+    }
   }
 }
 
 int launch_gaussian(gpca_ctx* c, float* d_out, uint64_t rows, uint32_t cols, uint32_t ld, uint64_t seed,
                     uint32_t stream, uint64_t row0) {
-  const uint64_t total = rows * ld;
+  const uint64_t total = rows * ((ld + 3) / 4);
   if (total == 0) return GPCA_OK;
   const int threads = 256;
   const uint64_t blocks = (total + threads - 1) / threads;
@@ -36,17 +43,23 @@ int launch_gaussian(gpca_ctx* c, float* d_out, uint64_t rows, uint32_t cols, uin
 }
 
 // ------------------------------------------------------------------------------------------
-// Gram: each CTA owns a contiguous range of rows, stages 64 rows at a time in shared memory and
-// accumulates a 64 x 64 (padded) f64 partial with a 4 x 4 register tile per thread; partials are
+// Gram: each CTA owns a contiguous range of rows, stages 64 rows at a time in shared memory and accumulates an
+// LP x LP (LP = 32 or 64, padded) f64 partial with a 4 x 4 register tile per thread.  For LP = 32 the 256 threads form
+// 4 groups that split the rows of a tile (all threads busy); the groups are summed through shared memory.  Partials are
 // then summed in a fixed order by gram_reduce_kernel (deterministic).
-constexpr int GRAM_LP = 64;
 constexpr int GRAM_ROWS = 64;
 
+template <int LP>
 __global__ void __launch_bounds__(256) gram_partial_kernel(const float* __restrict__ y, uint64_t n, uint32_t l,
                                                            uint32_t ld, uint64_t rows_per_cta,
                                                            double* __restrict__ partial) {
-  __shared__ __align__(16) float tile[GRAM_ROWS][GRAM_LP + 4];
-  const int ti = threadIdx.x / 16, tj = threadIdx.x % 16;
+  constexpr int TPD = LP / 4;               // threads per dimension of the output
+  constexpr int GROUPS = 256 / (TPD * TPD); // 4 for LP = 32, 1 for LP = 64
+  __shared__ __align__(16) float tile[GRAM_ROWS][LP + 4];
+  __shared__ double gsum[(GROUPS > 1) ? (GROUPS - 1) * LP * LP : 1];
+  const int grp = threadIdx.x / (TPD * TPD);
+  const int t = threadIdx.x % (TPD * TPD);
+  const int ti = t / TPD, tj = t % TPD;
   double acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -55,41 +68,57 @@ __global__ void __launch_bounds__(256) gram_partial_kernel(const float* __restri
   const uint64_t r_begin = blockIdx.x * rows_per_cta;
   uint64_t r_end = r_begin + rows_per_cta;
   if (r_end > n) r_end = n;
-  const bool need_i = (uint32_t)(ti * 4) < l, need_j = (uint32_t)(tj * 4) < l;
   for (uint64_t r0 = r_begin; r0 < r_end; r0 += GRAM_ROWS) {
-    for (int t = threadIdx.x; t < GRAM_ROWS * GRAM_LP; t += 256) {
-      const int rr = t / GRAM_LP, cc = t % GRAM_LP;
+    for (int e = threadIdx.x; e < GRAM_ROWS * LP; e += 256) {
+      const int rr = e / LP, cc = e % LP;
       const uint64_t r = r0 + rr;
       tile[rr][cc] = (r < r_end && (uint32_t)cc < l) ? y[r * ld + cc] : 0.0f;
     }
     __syncthreads();
-    if (need_i && need_j) {
 #pragma unroll 4
-      for (int rr = 0; rr < GRAM_ROWS; ++rr) {
-        const float4 a = *reinterpret_cast<const float4*>(&tile[rr][ti * 4]);
-        const float4 b = *reinterpret_cast<const float4*>(&tile[rr][tj * 4]);
-        const double av[4] = {a.x, a.y, a.z, a.w};
-        const double bv[4] = {b.x, b.y, b.z, b.w};
+    for (int rr = grp; rr < GRAM_ROWS; rr += GROUPS) {
+      const float4 a = *reinterpret_cast<const float4*>(&tile[rr][ti * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&tile[rr][tj * 4]);
+      const double av[4] = {a.x, a.y, a.z, a.w};
+      const double bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
-      }
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
     }
     __syncthreads();
   }
-  double* p = partial + (uint64_t)blockIdx.x * GRAM_LP * GRAM_LP;
+  if (GROUPS > 1) {
+    if (grp > 0) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) p[(ti * 4 + i) * GRAM_LP + tj * 4 + j] = acc[i][j];
+        for (int j = 0; j < 4; ++j) gsum[((grp - 1) * LP + ti * 4 + i) * LP + tj * 4 + j] = acc[i][j];
+    }
+    __syncthreads();
+    if (grp == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          for (int g = 0; g < GROUPS - 1; ++g) acc[i][j] += gsum[(g * LP + ti * 4 + i) * LP + tj * 4 + j];
+    }
+  }
+  if (grp == 0) {
+    double* p = partial + (uint64_t)blockIdx.x * LP * LP;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) p[(ti * 4 + i) * LP + tj * 4 + j] = acc[i][j];
+  }
 }
 
-__global__ void gram_reduce_kernel(const double* __restrict__ partial, int nparts, uint32_t l, double* __restrict__ g) {
+__global__ void gram_reduce_kernel(const double* __restrict__ partial, int nparts, uint32_t l, int lp,
+                                   double* __restrict__ g) {
   for (int t = threadIdx.x; t < (int)(l * l); t += blockDim.x) {
     const int i = t / l, j = t % l;
     double s = 0.0;
-    for (int p = 0; p < nparts; ++p) s += partial[(uint64_t)p * GRAM_LP * GRAM_LP + i * GRAM_LP + j];
+    for (int p = 0; p < nparts; ++p) s += partial[(uint64_t)p * lp * lp + i * lp + j];
     g[t] = s;
   }
 }
@@ -99,17 +128,21 @@ int launch_gram(gpca_ctx* c, const float* d_y, uint64_t n, uint32_t l, uint32_t 
     c->set_error("launch_gram: l must be in 1..64");
     return GPCA_ERR_INVALID;
   }
-  int nparts = (int)((n + 1023) / 1024);
+  const int lp = (l <= 32) ? 32 : 64;
+  int nparts = (int)((n + 255) / 256);
   if (nparts > c->sm_count * 4) nparts = c->sm_count * 4;
   if (nparts < 1) nparts = 1;
   uint64_t rows_per_cta = (n + nparts - 1) / nparts;
   rows_per_cta = round_up(rows_per_cta ? rows_per_cta : 1, GRAM_ROWS);
   nparts = (int)((n + rows_per_cta - 1) / rows_per_cta);
   if (nparts < 1) nparts = 1;
-  GPCA_CUDA_TRY(c, c->ws_f64.alloc((size_t)nparts * GRAM_LP * GRAM_LP + 4096));
-  gram_partial_kernel<<<nparts, 256, 0, c->stream>>>(d_y, n, l, ld, rows_per_cta, c->ws_f64.p);
+  GPCA_CUDA_TRY(c, c->ws_gram.alloc((size_t)nparts * lp * lp + 4096));
+  if (lp == 32)
+    gram_partial_kernel<32><<<nparts, 256, 0, c->stream>>>(d_y, n, l, ld, rows_per_cta, c->ws_gram.p);
+  else
+    gram_partial_kernel<64><<<nparts, 256, 0, c->stream>>>(d_y, n, l, ld, rows_per_cta, c->ws_gram.p);
   KLAUNCH_CHECK(c);
-  gram_reduce_kernel<<<1, 256, 0, c->stream>>>(c->ws_f64.p, nparts, l, d_g);
+  gram_reduce_kernel<<<1, 256, 0, c->stream>>>(c->ws_gram.p, nparts, l, lp, d_g);
   KLAUNCH_CHECK(c);
   return GPCA_OK;
 }
@@ -137,11 +170,19 @@ __global__ void __launch_bounds__(256) apply_right_kernel(const float* __restric
     const int rr = threadIdx.x >> 2, cg = threadIdx.x & 3;
     const uint64_t r = r0 + rr;
     if (r < n) {
-      for (uint32_t c2 = cg; c2 < l2; c2 += 4) {
-        double s = 0.0;
-        for (uint32_t cc = 0; cc < l; ++cc) s = fma((double)tile[rr * lp + cc], ts[cc * l2 + c2], s);
-        out[r * ldo + c2] = (float)s;
+      double acc[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[j] = 0.0;
+      for (uint32_t cc = 0; cc < l; ++cc) {
+        const double yv = (double)tile[rr * lp + cc];
+        const double* trow = ts + cc * l2 + cg;
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (cg + 4u * j < l2) acc[j] = fma(yv, trow[4 * j], acc[j]);
       }
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (cg + 4u * j < l2) out[r * ldo + cg + 4 * j] = (float)acc[j];
     }
   }
 }
@@ -160,7 +201,7 @@ int launch_apply_right(gpca_ctx* c, const float* d_y, uint64_t n, uint32_t l, ui
 
 // ------------------------------------------------------------------------------------------
 // Single-CTA two-sided cyclic Jacobi (round-robin pairing), f64, l <= 64.
-__global__ void __launch_bounds__(256) jacobi_eigh_kernel(const double* __restrict__ a_in, uint32_t l,
+__global__ void __launch_bounds__(128) jacobi_eigh_kernel(const double* __restrict__ a_in, uint32_t l,
                                                           double* __restrict__ evals, double* __restrict__ evecs) {
   constexpr int LP = 64;
   extern __shared__ double jsm[];
@@ -204,7 +245,7 @@ __global__ void __launch_bounds__(256) jacobi_eigh_kernel(const double* __restri
     double dg_t = 0.0;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) dg_t += red[w];
     __syncthreads();
-    if (off_t <= 1e-30 * dg_t || off_t == 0.0) break;
+    if (off_t <= 1e-28 * dg_t || off_t == 0.0) break;
     for (int round = 0; round < ne - 1; ++round) {
       // round-robin tournament: position 0 fixed, others rotate
       if ((int)threadIdx.x < npairs) {
@@ -288,7 +329,7 @@ int launch_jacobi_eigh(gpca_ctx* c, const double* d_a, uint32_t l, double* d_eva
   }
   const size_t smem = 2 * 64 * 65 * sizeof(double);
   GPCA_CUDA_TRY(c, cudaFuncSetAttribute(jacobi_eigh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  jacobi_eigh_kernel<<<1, 256, smem, c->stream>>>(d_a, l, d_evals, d_evecs);
+  jacobi_eigh_kernel<<<1, 128, smem, c->stream>>>(d_a, l, d_evals, d_evecs);
   KLAUNCH_CHECK(c);
   return GPCA_OK;
 }

@@ -30,11 +30,28 @@ __host__ __device__ inline Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint3
   return Philox4{c0, c1, c2, c3};
 }
 
-// One standard normal for element (row, col) of stream `stream` under `seed`.
-__device__ inline float philox_normal(uint64_t seed, uint32_t stream, uint64_t row, uint32_t col) {
-  const Philox4 r = philox4x32_10((uint32_t)row, (uint32_t)(row >> 32), col, stream, (uint32_t)seed,
+// Four standard normals for columns 4*cg .. 4*cg+3 of row `row` (one Philox call, two Box-Muller pairs):
+//   (x, y) -> sqrt(-2 ln u1) * {cos, sin}(2 pi u2),   (z, w) -> the same for the second pair.
+__device__ inline void philox_normal4(uint64_t seed, uint32_t stream, uint64_t row, uint32_t cg, float out[4]) {
+  const Philox4 r = philox4x32_10((uint32_t)row, (uint32_t)(row >> 32), cg, stream, (uint32_t)seed,
                                   (uint32_t)(seed >> 32));
-  const float u1 = ((float)(r.x >> 8) + 0.5f) * (1.0f / 16777216.0f);
-  const float u2 = (float)(r.y >> 8) * (1.0f / 16777216.0f);
-  return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+  const float u1a = ((float)(r.x >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  const float u2a = (float)(r.y >> 8) * (1.0f / 16777216.0f);
+  const float u1b = ((float)(r.z >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  const float u2b = (float)(r.w >> 8) * (1.0f / 16777216.0f);
+  const float ra = sqrtf(-2.0f * logf(u1a)), rb = sqrtf(-2.0f * logf(u1b));
+  float sa, ca, sb, cb;
+  sincospif(2.0f * u2a, &sa, &ca);
+  sincospif(2.0f * u2b, &sb, &cb);
+  out[0] = ra * ca;
+  out[1] = ra * sa;
+  out[2] = rb * cb;
+  out[3] = rb * sb;
+}
+
+// One standard normal for element (row, col) of stream `stream` under `seed` (column col = 4*cg + j).
+__device__ inline float philox_normal(uint64_t seed, uint32_t stream, uint64_t row, uint32_t col) {
+  float o[4];
+  philox_normal4(seed, stream, row, col >> 2, o);
+  return o[col & 3];
 }

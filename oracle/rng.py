@@ -44,26 +44,36 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
     return c0.astype(np.uint32), c1.astype(np.uint32), c2.astype(np.uint32), c3.astype(np.uint32)
 
 
+def _normals_from_keys(seed: int, stream: int, rows_u64: np.ndarray, n_cols: int) -> np.ndarray:
+    """rows_u64 [R,1] uint64 row keys -> f64 [R, n_cols].  One Philox call per (row, group of 4 columns):
+    columns 4g, 4g+1 = sqrt(-2 ln u1a) * (cos, sin)(2 pi u2a), columns 4g+2, 4g+3 = the same from the second pair."""
+    ng = (n_cols + 3) // 4
+    groups = np.arange(ng, dtype=np.uint64)[None, :]
+    x0, x1, x2, x3 = philox4x32_10(rows_u64 & _MASK, rows_u64 >> np.uint64(32), groups, np.uint64(stream),
+                                   seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+
+    def pair(a, b):
+        u1 = ((a >> np.uint32(8)).astype(np.float64) + 0.5) * (1.0 / 16777216.0)
+        u2 = (b >> np.uint32(8)).astype(np.float64) * (1.0 / 16777216.0)
+        rad = np.sqrt(-2.0 * np.log(u1))
+        return rad * np.cos(2.0 * np.pi * u2), rad * np.sin(2.0 * np.pi * u2)
+
+    c0, c1 = pair(x0, x1)
+    c2, c3 = pair(x2, x3)
+    out = np.stack([c0, c1, c2, c3], axis=2).reshape(rows_u64.shape[0], ng * 4)
+    return out[:, :n_cols]
+
+
 def gaussian_matrix(seed: int, stream: int, row0: int, n_rows: int, n_cols: int) -> np.ndarray:
     """f64 [n_rows, n_cols]; element (r, c) depends only on (seed, stream, row0+r, c)."""
     rows = (np.arange(n_rows, dtype=np.uint64) + np.uint64(row0))[:, None]
-    cols = np.arange(n_cols, dtype=np.uint64)[None, :]
-    x0, x1, _, _ = philox4x32_10(rows & _MASK, rows >> np.uint64(32), cols, np.uint64(stream),
-                                 seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
-    u1 = ((x0 >> np.uint32(8)).astype(np.float64) + 0.5) * (1.0 / 16777216.0)
-    u2 = (x1 >> np.uint32(8)).astype(np.float64) * (1.0 / 16777216.0)
-    return np.sqrt(-2.0 * np.log(u1)) * np.cos(2.0 * np.pi * u2)
+    return _normals_from_keys(seed, stream, rows, n_cols)
 
 
 def gaussian_rows(seed: int, stream: int, row_keys: np.ndarray, n_cols: int) -> np.ndarray:
     """Same generator with an explicit 64-bit key per row (EigenSNP condensed-feature test matrix)."""
     rows = np.asarray(row_keys, dtype=np.uint64)[:, None]
-    cols = np.arange(n_cols, dtype=np.uint64)[None, :]
-    x0, x1, _, _ = philox4x32_10(rows & _MASK, rows >> np.uint64(32), cols, np.uint64(stream),
-                                 seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
-    u1 = ((x0 >> np.uint32(8)).astype(np.float64) + 0.5) * (1.0 / 16777216.0)
-    u2 = (x1 >> np.uint32(8)).astype(np.float64) * (1.0 / 16777216.0)
-    return np.sqrt(-2.0 * np.log(u1)) * np.cos(2.0 * np.pi * u2)
+    return _normals_from_keys(seed, stream, rows, n_cols)
 
 
 def subset_keys(seed: int, stream: int, n: int) -> np.ndarray:
