@@ -6,6 +6,7 @@
 
 struct Small {  // f64 scratch for l x l work, all on device
   double *G, *evals, *evecs, *T;
+  int* flag;   // 1 = the Cholesky transform succeeded (eigen path skipped)
 };
 int get_small(gpca_ctx* c, Small& s);
 

@@ -18,11 +18,12 @@ static int fail(gpca_ctx* c, int code, const std::string& msg) {
 constexpr uint32_t STREAM_RFIT_OMEGA = 1;
 
 int get_small(gpca_ctx* c, Small& s) {
-  GPCA_CUDA_TRY(c, c->ws_small.alloc(4 * 64 * 64));
+  GPCA_CUDA_TRY(c, c->ws_small.alloc(4 * 64 * 64 + 8));
   s.G = c->ws_small.p;
   s.evals = s.G + 64 * 64;
   s.evecs = s.evals + 64 * 64;
   s.T = s.evecs + 64 * 64;
+  s.flag = reinterpret_cast<int*>(s.T + 64 * 64);
   return GPCA_OK;
 }
 
@@ -37,8 +38,11 @@ int orthonormalize(gpca_ctx* c, float* y, uint64_t n, uint32_t l, uint32_t ld, b
   for (int rep = 0; rep < 2; ++rep) {
     GPCA_TRY(launch_gram(c, y, n, l, ld, s.G));
     if (sharded) GPCA_TRY(driver_allreduce(c, s.G, (uint64_t)l * l, 1));
-    GPCA_TRY(launch_jacobi_eigh(c, s.G, l, s.evals, s.evecs));
-    GPCA_TRY(launch_make_orth_transform(c, s.evals, s.evecs, l, s.T, rep == 0 ? 1e-11 : 1e-13));
+    // CholeskyQR first (tens of microseconds); the eigen-based transform runs only if a pivot was unsafe
+    const double eps = rep == 0 ? 1e-11 : 1e-13;
+    GPCA_TRY(launch_chol_orth(c, s.G, l, s.T, eps, s.flag));
+    GPCA_TRY(launch_jacobi_eigh(c, s.G, l, s.evals, s.evecs, s.flag));
+    GPCA_TRY(launch_make_orth_transform(c, s.evals, s.evecs, l, s.T, eps, s.flag));
     GPCA_TRY(launch_apply_right(c, y, n, l, ld, s.T, l, y, ld));
   }
   return GPCA_OK;

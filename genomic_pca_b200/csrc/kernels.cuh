@@ -29,10 +29,13 @@ int launch_apply_right(gpca_ctx* c, const float* d_y, uint64_t n, uint32_t l, ui
                        uint32_t l2, float* d_out, uint32_t ldo);
 // single-CTA Jacobi eigensolver on a symmetric l x l f64 matrix (l <= 64):
 // evals descending, evecs as columns (row-major [l x l]).
-int launch_jacobi_eigh(gpca_ctx* c, const double* d_a, uint32_t l, double* d_evals, double* d_evecs);
+int launch_jacobi_eigh(gpca_ctx* c, const double* d_a, uint32_t l, double* d_evals, double* d_evecs,
+                       const int* d_skip_flag = nullptr);
+// CholeskyQR transform T = R^-1 with G = R^T R; *d_ok_flag = 1 on success, 0 when a pivot <= rel_eps * max diag
+int launch_chol_orth(gpca_ctx* c, const double* d_g, uint32_t l, double* d_t, double rel_eps, int* d_ok_flag);
 // T = V * diag(lambda^-1/2) with rank truncation (lambda <= eps*lambda_max -> column zeroed)
 int launch_make_orth_transform(gpca_ctx* c, const double* d_evals, const double* d_evecs, uint32_t l, double* d_t,
-                               double rel_eps);
+                               double rel_eps, const int* d_skip_flag = nullptr);
 int launch_f32_to_f64(gpca_ctx* c, const float* in, double* out, uint64_t n);
 int launch_scale_cols_to_f64(gpca_ctx* c, const float* in, uint64_t n, uint32_t k, uint32_t ld, double* out);
 

@@ -148,14 +148,20 @@ int launch_gram(gpca_ctx* c, const float* d_y, uint64_t n, uint32_t l, uint32_t 
 }
 
 // ------------------------------------------------------------------------------------------
-// out[r, :l2] = y[r, :l] * T   (T f64 in shared memory, f64 accumulation, fp32 store)
+// out[r, :l2] = y[r, :l] * T   (T f64 in shared memory, f64 accumulation, fp32 store).
+// Thread (row rr = tid/4, column lane cg = tid%4) owns the NOWN outputs cg, cg+4, ... in registers.
+template <int NOWN>
 __global__ void __launch_bounds__(256) apply_right_kernel(const float* __restrict__ y, uint64_t n, uint32_t l,
                                                           uint32_t ld, const double* __restrict__ t, uint32_t l2,
                                                           float* __restrict__ out, uint32_t ldo) {
   extern __shared__ double sm[];
-  double* ts = sm;                                            // [l][l2]
-  float* tile = reinterpret_cast<float*>(sm + l * l2);        // [64][l+1]
-  for (int i = threadIdx.x; i < (int)(l * l2); i += 256) ts[i] = t[i];
+  const int l2p = NOWN * 4;                                    // padded output width
+  double* ts = sm;                                             // [l][l2p] (zero padded)
+  float* tile = reinterpret_cast<float*>(sm + l * l2p);        // [64][l+1]
+  for (int i = threadIdx.x; i < (int)(l * l2p); i += 256) {
+    const int cc = i / l2p, c2 = i % l2p;
+    ts[i] = ((uint32_t)c2 < l2) ? t[cc * l2 + c2] : 0.0;
+  }
   const int lp = l + 1;
   const uint64_t ntiles = (n + 63) / 64;
   for (uint64_t tix = blockIdx.x; tix < ntiles; tix += gridDim.x) {
@@ -170,40 +176,53 @@ __global__ void __launch_bounds__(256) apply_right_kernel(const float* __restric
     const int rr = threadIdx.x >> 2, cg = threadIdx.x & 3;
     const uint64_t r = r0 + rr;
     if (r < n) {
-      double acc[16];
+      double acc[NOWN];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) acc[j] = 0.0;
+      for (int j = 0; j < NOWN; ++j) acc[j] = 0.0;
       for (uint32_t cc = 0; cc < l; ++cc) {
         const double yv = (double)tile[rr * lp + cc];
-        const double* trow = ts + cc * l2 + cg;
+        const double* trow = ts + cc * l2p + cg;
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (cg + 4u * j < l2) acc[j] = fma(yv, trow[4 * j], acc[j]);
+        for (int j = 0; j < NOWN; ++j) acc[j] = fma(yv, trow[4 * j], acc[j]);
       }
 #pragma unroll
-      for (int j = 0; j < 16; ++j)
+      for (int j = 0; j < NOWN; ++j)
         if (cg + 4u * j < l2) out[r * ldo + cg + 4 * j] = (float)acc[j];
     }
   }
 }
 
-int launch_apply_right(gpca_ctx* c, const float* d_y, uint64_t n, uint32_t l, uint32_t ld, const double* d_t,
-                       uint32_t l2, float* d_out, uint32_t ldo) {
-  if (n == 0 || l == 0 || l2 == 0) return GPCA_OK;
-  const size_t smem = (size_t)l * l2 * sizeof(double) + (size_t)64 * (l + 1) * sizeof(float);
-  if (smem > 48 * 1024) GPCA_CUDA_TRY(c, cudaFuncSetAttribute(apply_right_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+template <int NOWN>
+static int run_apply_right(gpca_ctx* c, const float* d_y, uint64_t n, uint32_t l, uint32_t ld, const double* d_t,
+                           uint32_t l2, float* d_out, uint32_t ldo) {
+  const size_t smem = (size_t)l * NOWN * 4 * sizeof(double) + (size_t)64 * (l + 1) * sizeof(float);
+  if (smem > 48 * 1024)
+    GPCA_CUDA_TRY(c, cudaFuncSetAttribute(apply_right_kernel<NOWN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const uint64_t ntiles = (n + 63) / 64;
   const int grid = (int)(ntiles < (uint64_t)c->sm_count * 4 ? ntiles : (uint64_t)c->sm_count * 4);
-  apply_right_kernel<<<grid, 256, smem, c->stream>>>(d_y, n, l, ld, d_t, l2, d_out, ldo);
+  apply_right_kernel<NOWN><<<grid, 256, smem, c->stream>>>(d_y, n, l, ld, d_t, l2, d_out, ldo);
   KLAUNCH_CHECK(c);
   return GPCA_OK;
 }
 
+int launch_apply_right(gpca_ctx* c, const float* d_y, uint64_t n, uint32_t l, uint32_t ld, const double* d_t,
+                       uint32_t l2, float* d_out, uint32_t ldo) {
+  if (n == 0 || l == 0 || l2 == 0) return GPCA_OK;
+  const uint32_t need = (l2 + 3) / 4;
+  if (need <= 2) return run_apply_right<2>(c, d_y, n, l, ld, d_t, l2, d_out, ldo);
+  if (need <= 5) return run_apply_right<5>(c, d_y, n, l, ld, d_t, l2, d_out, ldo);
+  if (need <= 8) return run_apply_right<8>(c, d_y, n, l, ld, d_t, l2, d_out, ldo);
+  if (need <= 12) return run_apply_right<12>(c, d_y, n, l, ld, d_t, l2, d_out, ldo);
+  return run_apply_right<16>(c, d_y, n, l, ld, d_t, l2, d_out, ldo);
+}
+
 // ------------------------------------------------------------------------------------------
 // Single-CTA two-sided cyclic Jacobi (round-robin pairing), f64, l <= 64.
-__global__ void __launch_bounds__(128) jacobi_eigh_kernel(const double* __restrict__ a_in, uint32_t l,
-                                                          double* __restrict__ evals, double* __restrict__ evecs) {
+__global__ void __launch_bounds__(256) jacobi_eigh_kernel(const double* __restrict__ a_in, uint32_t l,
+                                                          double* __restrict__ evals, double* __restrict__ evecs,
+                                                          const int* __restrict__ skip_flag) {
   constexpr int LP = 64;
+  if (skip_flag && *skip_flag) return;   // the Cholesky path already produced the transform
   extern __shared__ double jsm[];
   double (*A)[LP + 1] = reinterpret_cast<double (*)[LP + 1]>(jsm);
   double (*V)[LP + 1] = reinterpret_cast<double (*)[LP + 1]>(jsm + LP * (LP + 1));
@@ -322,21 +341,24 @@ __global__ void __launch_bounds__(128) jacobi_eigh_kernel(const double* __restri
   }
 }
 
-int launch_jacobi_eigh(gpca_ctx* c, const double* d_a, uint32_t l, double* d_evals, double* d_evecs) {
+int launch_jacobi_eigh(gpca_ctx* c, const double* d_a, uint32_t l, double* d_evals, double* d_evecs,
+                       const int* d_skip_flag) {
   if (l == 0 || l > 64) {
     c->set_error("jacobi_eigh: l must be in 1..64");
     return GPCA_ERR_INVALID;
   }
   const size_t smem = 2 * 64 * 65 * sizeof(double);
   GPCA_CUDA_TRY(c, cudaFuncSetAttribute(jacobi_eigh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  jacobi_eigh_kernel<<<1, 128, smem, c->stream>>>(d_a, l, d_evals, d_evecs);
+  jacobi_eigh_kernel<<<1, 256, smem, c->stream>>>(d_a, l, d_evals, d_evecs, d_skip_flag);
   KLAUNCH_CHECK(c);
   return GPCA_OK;
 }
 
 // ------------------------------------------------------------------------------------------
 __global__ void make_orth_transform_kernel(const double* __restrict__ evals, const double* __restrict__ evecs,
-                                           uint32_t l, double* __restrict__ t, double rel_eps) {
+                                           uint32_t l, double* __restrict__ t, double rel_eps,
+                                           const int* __restrict__ skip_flag) {
+  if (skip_flag && *skip_flag) return;
   const double lmax = evals[0];
   for (int i = threadIdx.x; i < (int)(l * l); i += blockDim.x) {
     const int j = i % l;
@@ -346,8 +368,8 @@ __global__ void make_orth_transform_kernel(const double* __restrict__ evals, con
 }
 
 int launch_make_orth_transform(gpca_ctx* c, const double* d_evals, const double* d_evecs, uint32_t l, double* d_t,
-                               double rel_eps) {
-  make_orth_transform_kernel<<<1, 256, 0, c->stream>>>(d_evals, d_evecs, l, d_t, rel_eps);
+                               double rel_eps, const int* d_skip_flag) {
+  make_orth_transform_kernel<<<1, 256, 0, c->stream>>>(d_evals, d_evecs, l, d_t, rel_eps, d_skip_flag);
   KLAUNCH_CHECK(c);
   return GPCA_OK;
 }
@@ -414,6 +436,75 @@ int launch_apply_flags(gpca_ctx* c, const float* d_x, uint64_t n, uint32_t k, ui
   const uint64_t blocks = (total + 255) / 256;
   const int grid = (int)(blocks < (uint64_t)c->sm_count * 16 ? blocks : (uint64_t)c->sm_count * 16);
   apply_flags_kernel<<<grid, 256, 0, c->stream>>>(d_x, n, k, ld, d_flags, d_out_f32, d_out_f64);
+  KLAUNCH_CHECK(c);
+  return GPCA_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// CholeskyQR transform: G = R^T R (upper R), T = R^-1, so that (Y T)^T (Y T) = I.  Single CTA, f64, l <= 64.
+// ok_flag = 1 on success; 0 when a pivot is not safely positive (near rank deficiency) -- the caller then runs the
+// eigen-based path (jacobi_eigh + make_orth_transform), which zeroes deficient directions instead.
+__global__ void __launch_bounds__(256) chol_orth_kernel(const double* __restrict__ g, uint32_t l, double* __restrict__ t,
+                                                        double rel_eps, int* __restrict__ ok_flag) {
+  constexpr int LP = 64;
+  __shared__ double A[LP][LP + 1];   // 33 KB
+  __shared__ int bad;
+  const int n = (int)l;
+  for (int e = threadIdx.x; e < LP * LP; e += blockDim.x) {
+    const int i = e / LP, j = e % LP;
+    A[i][j] = (i < n && j < n) ? 0.5 * (g[i * n + j] + g[j * n + i]) : 0.0;
+  }
+  if (threadIdx.x == 0) bad = 0;
+  __syncthreads();
+  double dmax = 0.0;
+  for (int i = 0; i < n; ++i) dmax = fmax(dmax, A[i][i]);
+  const double thr = rel_eps * dmax;
+  for (int k = 0; k < n; ++k) {
+    const double piv = A[k][k];
+    if (!(piv > thr) || !isfinite(piv)) {
+      if (threadIdx.x == 0) bad = 1;
+      break;                                     // uniform: every thread reads the same shared value
+    }
+    const double inv = 1.0 / sqrt(piv);
+    __syncthreads();
+    for (int j = k + (int)threadIdx.x; j < n; j += blockDim.x) A[k][j] *= inv;      // row k of R (incl. the diagonal)
+    __syncthreads();
+    const int m = n - k - 1;
+    for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
+      const int i = k + 1 + e / m, j = k + 1 + e % m;
+      if (j >= i) A[i][j] -= A[k][i] * A[k][j];
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  if (bad) {
+    if (threadIdx.x == 0) *ok_flag = 0;
+    return;
+  }
+  // T = R^-1 (upper triangular), one thread per column by back substitution
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    double col[LP];
+    for (int i = n - 1; i >= 0; --i) {
+      if (i > j) {
+        col[i] = 0.0;
+        continue;
+      }
+      double s = (i == j) ? 1.0 : 0.0;
+      for (int mm = i + 1; mm <= j; ++mm) s -= A[i][mm] * col[mm];
+      col[i] = s / A[i][i];
+    }
+    for (int i = 0; i < n; ++i) t[i * n + j] = col[i];
+  }
+  if (threadIdx.x == 0) *ok_flag = 1;
+}
+
+int launch_chol_orth(gpca_ctx* c, const double* d_g, uint32_t l, double* d_t, double rel_eps, int* d_ok_flag) {
+  if (l == 0 || l > 64) {
+    c->set_error("chol_orth: l must be in 1..64");
+    return GPCA_ERR_INVALID;
+  }
+  chol_orth_kernel<<<1, 256, 0, c->stream>>>(d_g, l, d_t, rel_eps, d_ok_flag);
   KLAUNCH_CHECK(c);
   return GPCA_OK;
 }
