@@ -13,6 +13,8 @@
 #define CHECK_CTX(c) \
   if (!(c)) return GPCA_ERR_INVALID;
 
+void gpca_destroy_cublas(void* h);   // eigensnp.cu
+
 static int fail(gpca_ctx* c, int code, const std::string& msg) {
   c->set_error(msg);
   return code;
@@ -53,6 +55,7 @@ extern "C" void gpca_destroy(gpca_ctx* c) {
   }
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->h_cnt) cudaFreeHost(c->h_cnt);
+  gpca_destroy_cublas(c->cublas);
   delete c;
 }
 

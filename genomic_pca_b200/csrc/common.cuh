@@ -114,6 +114,8 @@ struct gpca_ctx {
   bool tc_amax_zeroed = false;
   DevBuf<float> drv_a, drv_b, drv_c, drv_d;   // driver-level dense operands (kept across calls: no per-call cudaMalloc)
 
+  void* cublas = nullptr;      // cublasHandle_t, created on first EigenSNP call
+
   void set_error(const std::string& s) { err = s; }
 };
 

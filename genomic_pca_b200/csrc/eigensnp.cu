@@ -13,6 +13,7 @@
 #include <cublas_v2.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <vector>
@@ -128,13 +129,6 @@ __global__ void scale_cols_sqrt_kernel(float* __restrict__ x, uint64_t n, uint32
   }
 }
 
-struct CublasHandle {
-  cublasHandle_t h = nullptr;
-  ~CublasHandle() {
-    if (h) cublasDestroy(h);
-  }
-};
-
 int cublas_check(gpca_ctx* c, cublasStatus_t st, const char* what) {
   if (st == CUBLAS_STATUS_SUCCESS) return GPCA_OK;
   return fail(c, GPCA_ERR_CUDA, std::string("cuBLAS ") + what + " failed: " + std::to_string((int)st));
@@ -153,6 +147,10 @@ int sgemm_rm(gpca_ctx* c, cublasHandle_t h, bool transA, int m, int n, int k, co
 
 }  // namespace
 
+void gpca_destroy_cublas(void* h) {
+  if (h) cublasDestroy((cublasHandle_t)h);
+}
+
 extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const uint64_t* block_offsets,
                              uint64_t n_blocks, const uint64_t* block_snp_ids, float* scores, double* eigenvalues,
                              float* loadings, uint32_t* k_out) {
@@ -170,6 +168,16 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
   if (cpb_max + cfg->local_oversampling > 64 || k_req + cfg->global_oversampling > 64)
     return fail(c, GPCA_ERR_INVALID, "components + oversampling must be <= 64 in this build");
   const uint64_t seed = cfg->random_seed;
+  // optional stage timing (GPCA_TRACE=1): the reference prints a stage table too (src/main.rs:437-442)
+  const bool trace = getenv("GPCA_TRACE") != nullptr;
+  auto t_last = std::chrono::steady_clock::now();
+  auto stage = [&](const char* name) {
+    if (!trace) return;
+    cudaStreamSynchronize(c->stream);
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[gpca_eigensnp] %-28s %9.2f ms\n", name, std::chrono::duration<double, std::milli>(now - t_last).count());
+    t_last = now;
+  };
 
   // ---- slot layout: blocks contiguous, each starting at a multiple of 64 fields ------------------------
   std::vector<uint64_t> off(n_blocks + 1, 0);
@@ -256,6 +264,7 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
 
   Small s;
   GPCA_TRY(get_small(c, s));
+  stage("slot/subset copies");
 
   // ---- 2. local bases -------------------------------------------------------------------------------------
   std::vector<uint32_t> cp(n_blocks);
@@ -303,6 +312,7 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
     GPCA_TRY(launch_apply_right(c, Yb.p, m, lp, lp, s.T, cp[b], Ubuf.p + o * cpb_max, cpb_max));   // U_p = Q U_b[:, :c_p]
   }
 
+  stage("local bases");
   // ---- 3. condensed features (all N samples), Cn [N x R], then column standardisation -----------------------
   if (R == 0) return fail(c, GPCA_ERR_INVALID, "no condensed features");
   DevBuf<float> Cn;
@@ -338,9 +348,16 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
     GPCA_CUDA_TRY(c, cudaStreamSynchronize(c->stream));   // temporaries above are freed on scope exit
   }
 
+  stage("condense + standardise");
   // ---- 4. global randomized SVD of the condensed matrix (rows of C^T sharded by rank) ------------------------
-  CublasHandle cb;
-  GPCA_TRY(cublas_check(c, cublasCreate(&cb.h), "create"));
+  // the cuBLAS handle is created once per context (creation costs ~100 ms) and kept for later calls
+  struct { cublasHandle_t h; } cb;
+  if (!c->cublas) {
+    cublasHandle_t h = nullptr;
+    GPCA_TRY(cublas_check(c, cublasCreate(&h), "create"));
+    c->cublas = (void*)h;
+  }
+  cb.h = (cublasHandle_t)c->cublas;
   GPCA_TRY(cublas_check(c, cublasSetStream(cb.h, c->stream), "setStream"));
   GPCA_TRY(cublas_check(c, cublasSetMathMode(cb.h, CUBLAS_PEDANTIC_MATH), "setMathMode"));
   uint64_t R_total = R;
@@ -395,6 +412,7 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
   GPCA_CUDA_TRY(c, V.alloc(N * k));
   GPCA_TRY(launch_apply_right(c, Yg.p, N, lg, lg, s.T, k, V.p, k));     // V0 = Q V_b[:, :k]
 
+  stage("global rSVD");
   // ---- 5. refinement on the full genotype matrix ---------------------------------------------------------------
   GPCA_CUDA_TRY(c, L.alloc(Ds * k));
   GPCA_CUDA_TRY(c, Sc.alloc(N * k));
@@ -428,6 +446,7 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
     GPCA_TRY(launch_rotation_transform(c, s.evals, s.evecs, k, k, s.T, false));
     GPCA_TRY(launch_apply_right(c, L.p, Ds, k, k, s.T, k, L.p, k));          // loadings = L W
   }
+  stage("refinement");
   std::vector<double> h_lam(k, 0.0);
   if (passes == 0) {
     std::vector<double> hg((size_t)k * k);
@@ -468,6 +487,7 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
       for (uint32_t j = 0; j < k; ++j) loadings[(uint64_t)id * k + j] = flip[j] ? -h_l[sidx * k + j] : h_l[sidx * k + j];
     }
   }
+  stage("outputs");
   if (k_out) *k_out = k;
   return GPCA_OK;
 }

@@ -1,0 +1,37 @@
+"""EigenSNP at the UKB-array per-GPU shard shape (BASELINE config 4 / 8 GPUs): 500k samples x 87.5k SNPs,
+212 contiguous LD blocks, effective CLI defaults, k = 20.  Development / measurement aid (prints one JSON line)."""
+import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import bench, genomic_pca_b200 as gp
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 500_000
+m = int(sys.argv[2]) if len(sys.argv) > 2 else 87_500
+nblocks = int(sys.argv[3]) if len(sys.argv) > 3 else 212
+dev = torch.device("cuda", 0)
+t0 = time.perf_counter()
+payload = bench.synth_bed_device(torch, n, m, 0, dev)
+torch.cuda.synchronize()
+t_gen = time.perf_counter() - t0
+ctx = gp.Context(0)
+t0 = time.perf_counter()
+ctx.load_bed_device(payload.data_ptr(), n, m)
+keep, mean, sd, code = ctx.snp_qc(gp.QcConfig(0.98, 0.01, 1.0))   # HWE off: pooled structured populations fail HWE at this N (Wahlund effect)
+d = ctx.set_pca_snps_mask(keep, mean, sd)
+del payload
+torch.cuda.empty_cache()
+t_prep = time.perf_counter() - t0
+edges = np.linspace(0, d, nblocks + 1).astype(np.int64)
+blocks = [np.arange(edges[i], edges[i + 1], dtype=np.uint64) for i in range(nblocks)]
+cfg = gp.EigenSnpConfig(target_num_global_pcs=20)
+ctx.sketch_stats(reset=True)
+ctx.reset_launch_count()
+t0 = time.perf_counter()
+sc, ev, load = ctx.eigensnp(blocks, cfg)
+t_es = time.perf_counter() - t0
+ms, by, npass = ctx.sketch_stats(reset=True)
+print(json.dumps({"n": n, "snps": m, "pca_snps": d, "blocks": nblocks, "gen_s": round(t_gen, 2), "prep_s": round(t_prep, 3),
+                  "eigensnp_wall_s": round(t_es, 3), "sketch_ms": round(ms, 1), "sketch_passes": npass,
+                  "sketch_GB": round(by / 1e9, 1), "launches": ctx.launch_count,
+                  "eigenvalues_head": [round(float(x), 3) for x in ev[:4]], "finite": bool(np.isfinite(sc).all() and np.isfinite(load).all()),
+                  "mem_GB": round(torch.cuda.max_memory_allocated() / 1e9, 1)}))
