@@ -85,6 +85,7 @@ _sig("gpca_launch_count", C.c_uint64, C.c_void_p)
 _sig("gpca_reset_launch_count", None, C.c_void_p)
 _sig("gpca_set_sketch_engine", C.c_int, C.c_void_p, C.c_int)
 _sig("gpca_sketch_stats", C.c_int, C.c_void_p, _f64p, _f64p, _u64p, C.c_int)
+_sig("gpca_sketch_kernel_ms", C.c_double, C.c_void_p)
 _sig("gpca_set_allreduce", C.c_int, C.c_void_p, ALLREDUCE_FN, C.c_void_p)
 _sig("gpca_set_shard", C.c_int, C.c_void_p, C.c_uint64, C.c_uint64)
 _sig("gpca_load_bed", C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, _i64p, C.c_uint64)
@@ -204,6 +205,7 @@ class Context:
     def sketch_stats(self, reset=False):
         ms, by, n = C.c_double(), C.c_double(), C.c_uint64()
         self._chk(lib.gpca_sketch_stats(self._h, C.byref(ms), C.byref(by), C.byref(n), int(reset)))
+        self.last_kernel_ms = float(lib.gpca_sketch_kernel_ms(self._h))
         return ms.value, by.value, int(n.value)
 
     # -- ingest

@@ -53,6 +53,10 @@ extern "C" void gpca_destroy(gpca_ctx* c) {
     cudaEventDestroy(pr.first);
     cudaEventDestroy(pr.second);
   }
+  for (auto& pr : c->pending_kernel_events) {
+    cudaEventDestroy(pr.first);
+    cudaEventDestroy(pr.second);
+  }
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->h_cnt) cudaFreeHost(c->h_cnt);
   gpca_destroy_cublas(c->cublas);
@@ -492,6 +496,8 @@ extern "C" int gpca_sketch_sample_side(gpca_ctx* c, const float* dev_in, float* 
   return sketch_sample_side(c, dev_in, dev_out, l, ld, ld);
 }
 
+extern "C" double gpca_sketch_kernel_ms(gpca_ctx* c) { return c ? c->sk_kernel_ms_last : 0.0; }
+
 extern "C" int gpca_sketch_stats(gpca_ctx* c, double* ms_total, double* bytes_total, uint64_t* n_passes, int reset) {
   CHECK_CTX(c);
   GPCA_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
@@ -502,10 +508,19 @@ extern "C" int gpca_sketch_stats(gpca_ctx* c, double* ms_total, double* bytes_to
     cudaEventDestroy(pr.second);
   }
   c->pending_events.clear();
+  for (auto& pr : c->pending_kernel_events) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) c->sk_kernel_ms += ms;
+    cudaEventDestroy(pr.first);
+    cudaEventDestroy(pr.second);
+  }
+  c->pending_kernel_events.clear();
   if (ms_total) *ms_total = c->sk_ms;
   if (bytes_total) *bytes_total = c->sk_bytes;
   if (n_passes) *n_passes = c->sk_passes;
+  c->sk_kernel_ms_last = c->sk_kernel_ms;
   if (reset) {
+    c->sk_kernel_ms = 0;
     c->sk_ms = 0;
     c->sk_bytes = 0;
     c->sk_passes = 0;

@@ -101,6 +101,8 @@ struct gpca_ctx {
   uint64_t sk_passes = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_events;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_kernel_events;   // around the main sketch kernel only
+  double sk_kernel_ms = 0, sk_kernel_ms_last = 0;
 
   // scratch
   DevBuf<float> ws_bprep;      // prepared B' operand
@@ -117,6 +119,21 @@ struct gpca_ctx {
   void* cublas = nullptr;      // cublasHandle_t, created on first EigenSNP call
 
   void set_error(const std::string& s) { err = s; }
+};
+
+// CUDA-event bracket around the dominant (sketch) kernel alone: begin() before the launch, end() after it.
+struct KernelTimer {
+  gpca_ctx* c;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  explicit KernelTimer(gpca_ctx* ctx) : c(ctx) {
+    if (cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess) cudaEventRecord(e0, c->stream);
+  }
+  void end() {
+    if (e0 && e1) {
+      cudaEventRecord(e1, c->stream);
+      c->pending_kernel_events.push_back({e0, e1});
+    }
+  }
 };
 
 // ---- device helpers -------------------------------------------------------------------

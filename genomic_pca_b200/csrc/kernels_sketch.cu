@@ -230,8 +230,10 @@ static int run_simt(gpca_ctx* c, const SketchProblem& p, uint64_t Kpad) {
     partial = c->ws_partial.p;
   }
   dim3 grid((unsigned)row_tiles, (unsigned)nsplit);
+  KernelTimer kt(c);
   sketch_simt_kernel<NC><<<grid, 256, 0, c->stream>>>(p.G.p, p.G.pitch, rows, kchunks, per, c->ws_bprep.p, p.a, p.b,
                                                       c->ws_cvec.p, p.out, p.ldo, p.l, partial);
+  kt.end();
   KLAUNCH_CHECK(c);
   if (nsplit > 1) {
     const uint64_t total = rows * NC;

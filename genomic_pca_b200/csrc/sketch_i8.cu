@@ -537,7 +537,9 @@ int launch_sketch_i8(gpca_ctx* c, const SketchProblem& p) {
   }
   GPCA_CUDA_TRY(c, cudaFuncSetAttribute(sketch_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   const uint32_t grid = tp.n_items < slots ? tp.n_items : slots;
+  KernelTimer kt(c);
   sketch_i8_kernel<<<grid, NUM_THREADS, SMEM_BYTES, c->stream>>>(tmap, tp);
+  kt.end();
   c->launches++;
   GPCA_CUDA_TRY(c, cudaGetLastError());
   if (ksplit > 1) {

@@ -602,7 +602,9 @@ int run_tc(gpca_ctx* c, const SketchProblem& p) {
   }
   GPCA_CUDA_TRY(c, cudaFuncSetAttribute(sketch_tc_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   const uint32_t grid = tp.n_items < slots ? tp.n_items : slots;
+  KernelTimer kt(c);
   sketch_tc_kernel<NC><<<grid, NUM_THREADS, C::SMEM_BYTES, c->stream>>>(tmap, tp);
+  kt.end();
   c->launches++;
   GPCA_CUDA_TRY(c, cudaGetLastError());
   if (ksplit > 1) {

@@ -56,6 +56,9 @@ void gpca_reset_launch_count(gpca_ctx* ctx);
 int gpca_set_sketch_engine(gpca_ctx* ctx, int engine);
 /* device time (ms) and algorithmic packed bytes of the sketch passes since the last reset */
 int gpca_sketch_stats(gpca_ctx* ctx, double* ms_total, double* packed_bytes_total, uint64_t* n_passes, int reset);
+/* device time (ms) of the main sketch kernel launches alone (no operand prep / split-K reduce), as of the last
+ * gpca_sketch_stats call */
+double gpca_sketch_kernel_ms(gpca_ctx* ctx);
 
 /* Cross-shard sum hook (multi-GPU, SNP-sharded): called on the context's stream order with a
  * DEVICE buffer that must be replaced by its sum over all shards (fp32 or fp64).
