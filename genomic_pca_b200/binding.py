@@ -84,6 +84,7 @@ _sig("gpca_version", C.c_char_p)
 _sig("gpca_launch_count", C.c_uint64, C.c_void_p)
 _sig("gpca_reset_launch_count", None, C.c_void_p)
 _sig("gpca_set_sketch_engine", C.c_int, C.c_void_p, C.c_int)
+_sig("gpca_set_batch_blocks", C.c_int, C.c_void_p, C.c_int)
 _sig("gpca_sketch_stats", C.c_int, C.c_void_p, _f64p, _f64p, _u64p, C.c_int)
 _sig("gpca_sketch_kernel_ms", C.c_double, C.c_void_p)
 _sig("gpca_set_allreduce", C.c_int, C.c_void_p, ALLREDUCE_FN, C.c_void_p)
@@ -173,6 +174,9 @@ class Context:
     # -- configuration
     def set_sketch_engine(self, engine: int):
         self._chk(lib.gpca_set_sketch_engine(self._h, engine))
+
+    def set_batch_blocks(self, on: bool):
+        self._chk(lib.gpca_set_batch_blocks(self._h, 1 if on else 0))
 
     def set_shard(self, offset: int, total: int):
         self._chk(lib.gpca_set_shard(self._h, offset, total))

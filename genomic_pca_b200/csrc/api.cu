@@ -8,6 +8,7 @@
 
 #include "host_qc.h"
 #include "kernels.cuh"
+#include "sketch_tc.cuh"
 #include "parallel_for.h"
 
 #define CHECK_CTX(c) \
@@ -41,6 +42,8 @@ extern "C" int gpca_init(gpca_ctx** out, int device) {
   }
   const char* eng = getenv("GPCA_SKETCH_ENGINE");
   if (eng) c->engine = atoi(eng);
+  const char* bb = getenv("GPCA_BATCH_BLOCKS");
+  if (bb) c->batch_blocks = atoi(bb) != 0;
   *out = c;
   return GPCA_OK;
 }
@@ -72,6 +75,11 @@ extern "C" int gpca_set_sketch_engine(gpca_ctx* c, int engine) {
   CHECK_CTX(c);
   if (engine < 0 || engine > 2) return fail(c, GPCA_ERR_INVALID, "engine must be 0 (SIMT), 1 (tcgen05 f16) or 2 (tcgen05 i8)");
   c->engine = engine;
+  return GPCA_OK;
+}
+extern "C" int gpca_set_batch_blocks(gpca_ctx* c, int on) {
+  CHECK_CTX(c);
+  c->batch_blocks = on ? 1 : 0;
   return GPCA_OK;
 }
 extern "C" int gpca_set_allreduce(gpca_ctx* c, gpca_allreduce_fn fn, void* user) {
@@ -440,6 +448,19 @@ int timed_sketch(gpca_ctx* c, const SketchProblem& p) {
   GPCA_CUDA_TRY(c, cudaEventRecord(e1, c->stream));
   c->pending_events.push_back({e0, e1});
   c->sk_bytes += (double)p.G.rows * (double)((p.G.cols + 3) / 4);
+  c->sk_passes += 1;
+  return rc;
+}
+
+int timed_sketch_batch(gpca_ctx* c, const SketchBatch& sb) {
+  cudaEvent_t e0, e1;
+  GPCA_CUDA_TRY(c, cudaEventCreate(&e0));
+  GPCA_CUDA_TRY(c, cudaEventCreate(&e1));
+  GPCA_CUDA_TRY(c, cudaEventRecord(e0, c->stream));
+  const int rc = launch_sketch_i8_batch(c, sb);
+  GPCA_CUDA_TRY(c, cudaEventRecord(e1, c->stream));
+  c->pending_events.push_back({e0, e1});
+  c->sk_bytes += sb.bytes;
   c->sk_passes += 1;
   return rc;
 }

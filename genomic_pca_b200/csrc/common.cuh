@@ -68,6 +68,7 @@ struct gpca_ctx {
   std::string err;
   uint64_t launches = 0;
   int engine = 2;   // 0 SIMT fp32, 1 tcgen05 f16, 2 tcgen05 i8 (default; l > 32 falls back to 1)
+  int batch_blocks = 1;   // EigenSNP: all LD blocks per launch (needs engine 2); 0 = one block at a time
 
   // collective hook / shard
   gpca_allreduce_fn allreduce = nullptr;
@@ -113,6 +114,8 @@ struct gpca_ctx {
   DevBuf<double> ws_cpart;     // column-sum partials
   DevBuf<double> ws_small;     // l x l matrices: G, evals, evecs, T
   DevBuf<uint8_t> ws_bytes;    // tcgen05 engine: fp16 B' image
+  DevBuf<double> ws_batch;     // batched dense helpers: G / T / evecs / evals / flags per problem
+  DevBuf<float> ws_bstat;      // batched passes: per-block column sums, scales, amax words
   bool tc_amax_zeroed = false;
   DevBuf<float> drv_a, drv_b, drv_c, drv_d;   // driver-level dense operands (kept across calls: no per-call cudaMalloc)
 

@@ -3,6 +3,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "sketch_tc.cuh"
 
 struct Small {  // f64 scratch for l x l work, all on device
   double *G, *evals, *evecs, *T;
@@ -27,3 +28,5 @@ int sketch_snp_side(gpca_ctx* c, const float* dev_in, float* dev_out, uint32_t l
 int sketch_sample_side(gpca_ctx* c, const float* dev_in, float* dev_out, uint32_t l, uint32_t ld_in, uint32_t ld_out);
 // generic timed sketch on an arbitrary view (used by the EigenSNP driver)
 int timed_sketch(gpca_ctx* c, const SketchProblem& p);
+// one launch for all LD blocks (integer engine, item mode)
+int timed_sketch_batch(gpca_ctx* c, const SketchBatch& sb);

@@ -129,6 +129,22 @@ __global__ void scale_cols_sqrt_kernel(float* __restrict__ x, uint64_t n, uint32
   }
 }
 
+// out[id_of_slot[s]][j] = +-in[s][j]  (pad slots skipped)
+__global__ void scatter_loadings_kernel(const float* __restrict__ in, const int64_t* __restrict__ id_of_slot,
+                                        uint64_t n_slots, uint32_t k, const int* __restrict__ flags,
+                                        float* __restrict__ out) {
+  const uint64_t total = n_slots * k;
+  for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < total;
+       t += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t sidx = t / k;
+    const uint32_t j = (uint32_t)(t - sidx * k);
+    const int64_t id = id_of_slot[sidx];
+    if (id < 0) continue;
+    const float v = in[t];
+    out[(uint64_t)id * k + j] = flags[j] ? -v : v;
+  }
+}
+
 int cublas_check(gpca_ctx* c, cublasStatus_t st, const char* what) {
   if (st == CUBLAS_STATUS_SUCCESS) return GPCA_OK;
   return fail(c, GPCA_ERR_CUDA, std::string("cuBLAS ") + what + " failed: " + std::to_string((int)st));
@@ -246,8 +262,11 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
   GPCA_CUDA_TRY(c, et_store.alloc(Et.pitch * Et.rows));
   Es.p = es_store.p;
   Et.p = et_store.p;
+  stage("  allocations + tables");
   GPCA_TRY(launch_gather_rows(c, c->Gs, d_slot.p, Es));
+  stage("  gather slots");
   GPCA_TRY(launch_transpose(c, Es, Et));
+  stage("  transpose");
   if (Ns == N) {
     Ets = Et;
     Ess = Es;
@@ -280,6 +299,156 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
   DevBuf<float> Ubuf, Yb, Zb;
   GPCA_CUDA_TRY(c, Ubuf.alloc(Ds * cpb_max));
   GPCA_CUDA_TRY(c, cudaMemsetAsync(Ubuf.p, 0, Ds * cpb_max * sizeof(float), c->stream));
+  std::vector<uint32_t> lpv(n_blocks);
+  uint32_t lp_max = 0;
+  for (uint64_t b = 0; b < n_blocks; ++b) {
+    const uint64_t m = block_offsets[b + 1] - block_offsets[b];
+    lpv[b] = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(cp[b] + cfg->local_oversampling, m), Ns);
+    lp_max = std::max(lp_max, lpv[b]);
+  }
+  // All LD blocks in one launch per stage (integer engine, item mode) when the shapes allow it; otherwise one block
+  // at a time through the generic sketch entry (any engine, missing calls, tiny inputs).
+  const bool batched = c->batch_blocks && c->engine == 2 && !c->any_missing && sketch_i8_batch_supported(c) &&
+                       lp_max <= 32 && cpb_max <= 32 && Ns >= 128 && N >= 128 && Ds >= 128 && Ds / 4 < (1ull << 31) &&
+                       n_blocks < (1ull << 24);
+  const uint64_t rgN = (N + 255) / 256, rgS = (Ns + 255) / 256;
+  DevBuf<SketchBatchBlock> d_blkY;     // operands indexed by the block's SNPs (K = block SNPs)
+  std::vector<SketchBatchBlock> blkY;
+  uint32_t img_stages_Y = 0;
+  if (batched) {
+    blkY.resize(n_blocks);
+    for (uint64_t b = 0; b < n_blocks; ++b) {
+      const uint64_t m = block_offsets[b + 1] - block_offsets[b];
+      blkY[b].fe_off = off[b];
+      blkY[b].K = (uint32_t)m;
+      blkY[b].nst = (uint32_t)((m + 255) / 256);
+      blkY[b].img_st0 = img_stages_Y;
+      img_stages_Y += blkY[b].nst;
+    }
+  }
+  if (batched) {
+    const uint32_t LD = lp_max;
+    const uint32_t nstS = (uint32_t)((Ns + 255) / 256);
+    if ((uint64_t)n_blocks * nstS > 0x7fffffffull || n_blocks * rgS > 0x7fffffffull)
+      return fail(c, GPCA_ERR_INVALID, "too many LD blocks for one batch");
+    std::vector<DenseProb> yprob(n_blocks), zprob(n_blocks);
+    std::vector<uint32_t> streams(n_blocks);
+    std::vector<uint64_t> uoffs(n_blocks);
+    std::vector<SketchBatchBlock> blkZ(n_blocks);
+    std::vector<I8Item> it1, it2;
+    for (uint64_t b = 0; b < n_blocks; ++b) {
+      const uint64_t m = block_offsets[b + 1] - block_offsets[b];
+      yprob[b] = {off[b] * LD, (uint32_t)m, lpv[b]};
+      zprob[b] = {b * Ns * LD, (uint32_t)Ns, lpv[b]};
+      streams[b] = (uint32_t)(STREAM_LOCAL0 + c->shard_offset + block_snp_ids[block_offsets[b]]);
+      uoffs[b] = off[b] * cpb_max;
+      blkY[b].bin_off = off[b] * LD;
+      blkY[b].l = lpv[b];
+      blkZ[b].bin_off = b * Ns * LD;
+      blkZ[b].fe_off = 0;
+      blkZ[b].K = (uint32_t)Ns;
+      blkZ[b].l = lpv[b];
+      blkZ[b].img_st0 = (uint32_t)(b * nstS);
+      blkZ[b].nst = nstS;
+      for (uint64_t r0 = 0; r0 < m; r0 += 256) {   // rows = the block's SNPs, K = subset samples
+        I8Item it;
+        it.row0 = (uint32_t)(off[b] + r0);
+        it.nrows_l = (uint32_t)std::min<uint64_t>(256, m - r0) | (lpv[b] << 16);
+        it.kbyte0 = 0;
+        it.nst = nstS;
+        it.img_st0 = blkZ[b].img_st0;
+        it.blk = (uint32_t)b;
+        const uint64_t oo = (off[b] + r0) * LD;
+        it.out_off_lo = (uint32_t)oo;
+        it.out_off_hi = (uint32_t)(oo >> 32);
+        it1.push_back(it);
+      }
+    }
+    it2.reserve(rgS * n_blocks);
+    for (uint64_t rg = 0; rg < rgS; ++rg)          // rows = subset samples, K = the block's SNPs
+      for (uint64_t b = 0; b < n_blocks; ++b) {
+        I8Item it;
+        it.row0 = (uint32_t)(rg * 256);
+        it.nrows_l = (uint32_t)std::min<uint64_t>(256, Ns - rg * 256) | (lpv[b] << 16);
+        it.kbyte0 = (uint32_t)(off[b] / 4);
+        it.nst = blkY[b].nst;
+        it.img_st0 = blkY[b].img_st0;
+        it.blk = (uint32_t)b;
+        const uint64_t oo = (b * Ns + rg * 256) * LD;
+        it.out_off_lo = (uint32_t)oo;
+        it.out_off_hi = (uint32_t)(oo >> 32);
+        it2.push_back(it);
+      }
+    DevBuf<DenseProb> d_yprob, d_zprob;
+    DevBuf<uint32_t> d_streams, d_cp;
+    DevBuf<uint64_t> d_uoffs;
+    DevBuf<SketchBatchBlock> d_blkZ;
+    DevBuf<I8Item> d_it1, d_it2;
+    DevBuf<float> Yall, Zall;
+    GPCA_CUDA_TRY(c, d_yprob.alloc(n_blocks));
+    GPCA_CUDA_TRY(c, d_zprob.alloc(n_blocks));
+    GPCA_CUDA_TRY(c, d_streams.alloc(n_blocks));
+    GPCA_CUDA_TRY(c, d_cp.alloc(n_blocks));
+    GPCA_CUDA_TRY(c, d_uoffs.alloc(n_blocks));
+    GPCA_CUDA_TRY(c, d_blkZ.alloc(n_blocks));
+    GPCA_CUDA_TRY(c, d_blkY.alloc(n_blocks));
+    GPCA_CUDA_TRY(c, d_it1.alloc(it1.size()));
+    GPCA_CUDA_TRY(c, d_it2.alloc(it2.size()));
+    GPCA_CUDA_TRY(c, Yall.alloc(Ds * LD));
+    GPCA_CUDA_TRY(c, Zall.alloc(n_blocks * Ns * LD));
+    auto up = [&](void* dst, const void* src, size_t bytes) {
+      return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream);
+    };
+    GPCA_CUDA_TRY(c, up(d_yprob.p, yprob.data(), n_blocks * sizeof(DenseProb)));
+    GPCA_CUDA_TRY(c, up(d_zprob.p, zprob.data(), n_blocks * sizeof(DenseProb)));
+    GPCA_CUDA_TRY(c, up(d_streams.p, streams.data(), n_blocks * sizeof(uint32_t)));
+    GPCA_CUDA_TRY(c, up(d_cp.p, cp.data(), n_blocks * sizeof(uint32_t)));
+    GPCA_CUDA_TRY(c, up(d_uoffs.p, uoffs.data(), n_blocks * sizeof(uint64_t)));
+    GPCA_CUDA_TRY(c, up(d_blkZ.p, blkZ.data(), n_blocks * sizeof(SketchBatchBlock)));
+    GPCA_CUDA_TRY(c, up(d_blkY.p, blkY.data(), n_blocks * sizeof(SketchBatchBlock)));
+    GPCA_CUDA_TRY(c, up(d_it1.p, it1.data(), it1.size() * sizeof(I8Item)));
+    GPCA_CUDA_TRY(c, up(d_it2.p, it2.data(), it2.size() * sizeof(I8Item)));
+    GPCA_CUDA_TRY(c, cudaMemsetAsync(Yall.p, 0, Ds * LD * sizeof(float), c->stream));   // pad slots stay zero
+    DenseBatchWs ws;
+    GPCA_TRY(dense_batch_ws(c, (uint32_t)n_blocks, ws));
+    double bytes_blocks = 0.0;
+    for (uint64_t b = 0; b < n_blocks; ++b) bytes_blocks += (double)(block_offsets[b + 1] - block_offsets[b]);
+    SketchBatch p1;   // Y_b = X_b Z_b
+    p1.G = Ess; p1.G.avail = Ess.pitch;
+    p1.d_items = d_it1.p; p1.n_items = (uint32_t)it1.size();
+    p1.d_blocks = d_blkZ.p; p1.n_blocks = (uint32_t)n_blocks;
+    p1.total_img_stages = (uint32_t)(n_blocks * nstS); p1.max_K = (uint32_t)Ns;
+    p1.Bin = Zall.p; p1.ld = LD; p1.f = nullptr; p1.e = nullptr; p1.a = d_inv.p; p1.b = d_mu.p;
+    p1.out = Yall.p; p1.ldo = LD;
+    p1.bytes = bytes_blocks * (double)((Ns + 3) / 4);
+    SketchBatch p2;   // Z_b = X_b^T Y_b
+    p2.G = Ets; p2.G.avail = Ets.pitch;
+    p2.d_items = d_it2.p; p2.n_items = (uint32_t)it2.size();
+    p2.d_blocks = d_blkY.p; p2.n_blocks = (uint32_t)n_blocks;
+    p2.total_img_stages = img_stages_Y; p2.max_K = (uint32_t)max_m;
+    p2.Bin = Yall.p; p2.ld = LD; p2.f = d_inv.p; p2.e = d_mu.p; p2.a = nullptr; p2.b = nullptr;
+    p2.out = Zall.p; p2.ldo = LD;
+    p2.bytes = (double)Ns * bytes_blocks / 4.0;
+    const uint32_t nb = (uint32_t)n_blocks;
+    GPCA_TRY(launch_gaussian_batch(c, Zall.p, LD, d_zprob.p, nb, Ns, seed, d_streams.p));
+    GPCA_TRY(timed_sketch_batch(c, p1));                                               // Y = X Omega
+    for (uint32_t it = 0; it < cfg->local_power_iters; ++it) {
+      GPCA_TRY(orthonormalize_batch(c, Yall.p, LD, d_yprob.p, nb, max_m, lp_max, ws));
+      GPCA_TRY(timed_sketch_batch(c, p2));                                             // Z = X^T Q
+      GPCA_TRY(orthonormalize_batch(c, Zall.p, LD, d_zprob.p, nb, Ns, lp_max, ws));
+      GPCA_TRY(timed_sketch_batch(c, p1));                                             // Y = X Qz
+    }
+    GPCA_TRY(orthonormalize_batch(c, Yall.p, LD, d_yprob.p, nb, max_m, lp_max, ws));
+    GPCA_TRY(timed_sketch_batch(c, p2));                                               // B^T = X^T Q   [Ns x lp]
+    int np = 1;
+    GPCA_TRY(launch_gram_batch(c, Zall.p, LD, d_zprob.p, nb, Ns, &np));
+    GPCA_TRY(launch_chol_orth_batch(c, np, d_zprob.p, nb, 0.0, ws));                   // (sums the partials -> ws.G)
+    GPCA_TRY(launch_jacobi_eigh_batch(c, d_zprob.p, nb, ws, false));
+    GPCA_TRY(launch_rotation_batch(c, d_zprob.p, nb, d_cp.p, ws));
+    GPCA_TRY(launch_apply_right_batch(c, Yall.p, LD, d_yprob.p, nb, max_m, ws.T, d_cp.p, cpb_max, Ubuf.p, d_uoffs.p,
+                                      cpb_max));                                       // U_p = Q U_b[:, :c_p]
+    GPCA_CUDA_TRY(c, cudaStreamSynchronize(c->stream));   // host tables and the temporaries above go out of scope
+  } else {
   GPCA_CUDA_TRY(c, Yb.alloc(max_m * 64));
   GPCA_CUDA_TRY(c, Zb.alloc(Ns * 64));
   for (uint64_t b = 0; b < n_blocks; ++b) {
@@ -311,12 +480,51 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
     GPCA_TRY(launch_rotation_transform(c, s.evals, s.evecs, lp, cp[b], s.T, false));
     GPCA_TRY(launch_apply_right(c, Yb.p, m, lp, lp, s.T, cp[b], Ubuf.p + o * cpb_max, cpb_max));   // U_p = Q U_b[:, :c_p]
   }
+  }
 
   stage("local bases");
   // ---- 3. condensed features (all N samples), Cn [N x R], then column standardisation -----------------------
   if (R == 0) return fail(c, GPCA_ERR_INVALID, "no condensed features");
   DevBuf<float> Cn;
   GPCA_CUDA_TRY(c, Cn.alloc(N * R));
+  if (batched) {
+    if (rgN * n_blocks > 0x7fffffffull) return fail(c, GPCA_ERR_INVALID, "too many condensed-feature work items");
+    std::vector<I8Item> itc;
+    itc.reserve(rgN * n_blocks);
+    for (uint64_t b = 0; b < n_blocks; ++b) {
+      blkY[b].bin_off = off[b] * cpb_max;
+      blkY[b].l = cp[b];
+    }
+    for (uint64_t rg = 0; rg < rgN; ++rg)
+      for (uint64_t b = 0; b < n_blocks; ++b) {
+        I8Item it;
+        it.row0 = (uint32_t)(rg * 256);
+        it.nrows_l = (uint32_t)std::min<uint64_t>(256, N - rg * 256) | (cp[b] << 16);
+        it.kbyte0 = (uint32_t)(off[b] / 4);
+        it.nst = blkY[b].nst;
+        it.img_st0 = blkY[b].img_st0;
+        it.blk = (uint32_t)b;
+        const uint64_t oo = rg * 256 * R + roff[b];
+        it.out_off_lo = (uint32_t)oo;
+        it.out_off_hi = (uint32_t)(oo >> 32);
+        itc.push_back(it);
+      }
+    DevBuf<I8Item> d_itc;
+    GPCA_CUDA_TRY(c, d_itc.alloc(itc.size()));
+    GPCA_CUDA_TRY(c, cudaMemcpyAsync(d_itc.p, itc.data(), itc.size() * sizeof(I8Item), cudaMemcpyHostToDevice, c->stream));
+    GPCA_CUDA_TRY(c, cudaMemcpyAsync(d_blkY.p, blkY.data(), n_blocks * sizeof(SketchBatchBlock), cudaMemcpyHostToDevice,
+                                     c->stream));
+    SketchBatch pc;   // C_b = X_b^T U_b for all N samples, written into the block's columns of Cn
+    pc.G = Et; pc.G.avail = Et.pitch;
+    pc.d_items = d_itc.p; pc.n_items = (uint32_t)itc.size();
+    pc.d_blocks = d_blkY.p; pc.n_blocks = (uint32_t)n_blocks;
+    pc.total_img_stages = img_stages_Y; pc.max_K = (uint32_t)max_m;
+    pc.Bin = Ubuf.p; pc.ld = cpb_max; pc.f = d_inv.p; pc.e = d_mu.p; pc.a = nullptr; pc.b = nullptr;
+    pc.out = Cn.p; pc.ldo = (uint32_t)R;
+    pc.bytes = (double)N * (double)D / 4.0;
+    GPCA_TRY(timed_sketch_batch(c, pc));
+    GPCA_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  } else {
   for (uint64_t b = 0; b < n_blocks; ++b) {
     const uint64_t m = block_offsets[b + 1] - block_offsets[b];
     const uint64_t o = off[b];
@@ -326,6 +534,8 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
     p2.Bin = Ubuf.p + o * cpb_max; p2.out = Cn.p + roff[b]; p2.ldo = (uint32_t)R;
     GPCA_TRY(timed_sketch(c, p2));
   }
+  }
+  stage("  condensed features");
   {
     DevBuf<float> cmean, cinv;
     GPCA_CUDA_TRY(c, cmean.alloc(R));
@@ -392,9 +602,11 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
     KCHECK(c);
     GPCA_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   }
+  stage("  cublas handle + omega");
   // Y = Cz^T-side sketch: Yg[N x lg] = Cn[N x R] * Om[R x lg]
   GPCA_TRY(sgemm_rm(c, cb.h, false, (int)N, (int)lg, (int)R, Cn.p, (int)R, Om.p, (int)lg, Yg.p, (int)lg));
   GPCA_TRY(driver_allreduce(c, Yg.p, N * lg, 0));
+  stage("  first gemm");
   for (uint32_t it = 0; it < cfg->global_power_iters; ++it) {
     GPCA_TRY(orthonormalize(c, Yg.p, N, lg, lg, false, s));
     // Zg[R x lg] = Cn^T * Yg
@@ -402,6 +614,7 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
     GPCA_TRY(orthonormalize(c, Zg.p, R, lg, lg, true, s));
     GPCA_TRY(sgemm_rm(c, cb.h, false, (int)N, (int)lg, (int)R, Cn.p, (int)R, Zg.p, (int)lg, Yg.p, (int)lg));
     GPCA_TRY(driver_allreduce(c, Yg.p, N * lg, 0));
+    stage("  power iteration");
   }
   GPCA_TRY(orthonormalize(c, Yg.p, N, lg, lg, false, s));
   GPCA_TRY(sgemm_rm(c, cb.h, true, (int)R, (int)lg, (int)N, Cn.p, (int)R, Yg.p, (int)lg, Zg.p, (int)lg));   // B = Cz Q
@@ -470,23 +683,28 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
     scale_cols_sqrt_kernel<<<grid, 256, 0, c->stream>>>(V.p, N, k, d_lam.p);
     KCHECK(c);
   }
-  std::vector<float> h_sc(N * k), h_l(Ds * k);
-  GPCA_CUDA_TRY(c, cudaMemcpyAsync(h_sc.data(), V.p, N * k * 4, cudaMemcpyDeviceToHost, c->stream));
-  GPCA_CUDA_TRY(c, cudaMemcpyAsync(h_l.data(), L.p, Ds * k * 4, cudaMemcpyDeviceToHost, c->stream));
+  // sign convention and the slot -> PcaSnpId scatter of the loadings happen on the device; the host receives the
+  // final buffers only
+  DevBuf<int> d_flags;
+  GPCA_CUDA_TRY(c, d_flags.alloc(64));
+  GPCA_TRY(launch_sign_flags(c, V.p, N, k, k, d_flags.p));
+  if (scores) {
+    GPCA_TRY(launch_apply_flags(c, V.p, N, k, k, d_flags.p, V.p, nullptr));
+    GPCA_CUDA_TRY(c, cudaMemcpyAsync(scores, V.p, N * k * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  }
+  DevBuf<float> Lout;
+  if (loadings) {
+    GPCA_CUDA_TRY(c, Lout.alloc(D * k));
+    GPCA_CUDA_TRY(c, cudaMemsetAsync(Lout.p, 0, D * k * sizeof(float), c->stream));
+    const uint64_t tot = Ds * (uint64_t)k;
+    const int grid = (int)std::min<uint64_t>((tot + 255) / 256, (uint64_t)c->sm_count * 8);
+    scatter_loadings_kernel<<<grid, 256, 0, c->stream>>>(L.p, d_slot.p, Ds, k, d_flags.p, Lout.p);
+    KCHECK(c);
+    GPCA_CUDA_TRY(c, cudaMemcpyAsync(loadings, Lout.p, D * k * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  }
   GPCA_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-  std::vector<int> flip;
-  fix_signs_host(h_sc, N, k, flip);
-  if (scores) std::memcpy(scores, h_sc.data(), N * k * 4);
   if (eigenvalues)
     for (uint32_t j = 0; j < k; ++j) eigenvalues[j] = h_lam[j] / (double)(N - 1);
-  if (loadings) {
-    std::memset(loadings, 0, D * k * 4);
-    for (uint64_t sidx = 0; sidx < Ds; ++sidx) {
-      const int64_t id = id_of_slot[sidx];
-      if (id < 0) continue;
-      for (uint32_t j = 0; j < k; ++j) loadings[(uint64_t)id * k + j] = flip[j] ? -h_l[sidx * k + j] : h_l[sidx * k + j];
-    }
-  }
   stage("outputs");
   if (k_out) *k_out = k;
   return GPCA_OK;

@@ -37,6 +37,47 @@ int launch_chol_orth(gpca_ctx* c, const double* d_g, uint32_t l, double* d_t, do
 int launch_make_orth_transform(gpca_ctx* c, const double* d_evals, const double* d_evecs, uint32_t l, double* d_t,
                                double rel_eps, const int* d_skip_flag = nullptr);
 int launch_f32_to_f64(gpca_ctx* c, const float* in, double* out, uint64_t n);
+
+// ---- batched dense helpers: the same operations for many small problems (one per LD block) in one launch ----------
+// Problem b is the [rows x l] fp32 matrix at base + off with the shared row stride ld (l <= 32).
+struct DenseProb {
+  uint64_t off;
+  uint32_t rows;
+  uint32_t l;
+};
+struct DenseBatchWs {   // device scratch for n problems
+  double* G;       // [n][1024]  l x l Gram, compact
+  double* T;       // [n][1024]  transform
+  double* evecs;   // [n][1024]
+  double* evals;   // [n][32]
+  int* flags;      // [n]        1 = Cholesky transform valid
+};
+int dense_batch_ws(gpca_ctx* c, uint32_t n_probs, DenseBatchWs& ws);
+// out rows keyed by (seed, d_streams[b], r, col); columns >= l zeroed up to ld
+int launch_gaussian_batch(gpca_ctx* c, float* d_base, uint32_t ld, const DenseProb* d_probs, uint32_t n_probs,
+                          uint64_t max_rows, uint64_t seed, const uint32_t* d_streams);
+// Gram partials of every problem (into c->ws_gram); *nparts = partials per problem
+int launch_gram_batch(gpca_ctx* c, const float* d_base, uint32_t ld, const DenseProb* d_probs, uint32_t n_probs,
+                      uint64_t max_rows, int* nparts);
+// sums the partials -> ws.G, Cholesky transform -> ws.T, ws.flags
+int launch_chol_orth_batch(gpca_ctx* c, int nparts, const DenseProb* d_probs, uint32_t n_probs, double rel_eps,
+                           const DenseBatchWs& ws);
+// eigen-decomposition of ws.G -> ws.evals / ws.evecs (problems whose flag is set are skipped when use_flags)
+int launch_jacobi_eigh_batch(gpca_ctx* c, const DenseProb* d_probs, uint32_t n_probs, const DenseBatchWs& ws,
+                             bool use_flags);
+int launch_make_orth_transform_batch(gpca_ctx* c, const DenseProb* d_probs, uint32_t n_probs, double rel_eps,
+                                     const DenseBatchWs& ws);
+// ws.T_b [l x l2_b] = ws.evecs_b[:, :l2_b]
+int launch_rotation_batch(gpca_ctx* c, const DenseProb* d_probs, uint32_t n_probs, const uint32_t* d_l2,
+                          const DenseBatchWs& ws);
+// out_b = Y_b * T_b  (T_b [l x l2_b]; d_l2 == nullptr: l2_b = l).  d_out_offs == nullptr: out_b at d_out + off (in
+// place allowed when d_out == d_base and ldo == ld).
+int launch_apply_right_batch(gpca_ctx* c, const float* d_base, uint32_t ld, const DenseProb* d_probs,
+                             uint32_t n_probs, uint64_t max_rows, const double* d_t, const uint32_t* d_l2,
+                             uint32_t max_l2, float* d_out, const uint64_t* d_out_offs, uint32_t ldo);
+// two rounds of (Gram, CholeskyQR with guarded eigen fallback, apply), every problem in place
+int orthonormalize_batch(gpca_ctx* c, float* d_base, uint32_t ld, const DenseProb* d_probs, uint32_t n_probs,
+                         uint64_t max_rows, uint32_t max_l, const DenseBatchWs& ws);
 int launch_scale_cols_to_f64(gpca_ctx* c, const float* in, uint64_t n, uint32_t k, uint32_t ld, double* out);
 
 // ---- sketch (kernels_sketch.cu) -----------------------------------------------------------

@@ -50,9 +50,9 @@ int launch_gaussian(gpca_ctx* c, float* d_out, uint64_t rows, uint32_t cols, uin
 constexpr int GRAM_ROWS = 64;
 
 template <int LP>
-__global__ void __launch_bounds__(256) gram_partial_kernel(const float* __restrict__ y, uint64_t n, uint32_t l,
-                                                           uint32_t ld, uint64_t rows_per_cta,
-                                                           double* __restrict__ partial) {
+__device__ __forceinline__ void gram_partial_body(const float* __restrict__ y, uint32_t l, uint32_t ld,
+                                                  const uint64_t r_begin, const uint64_t r_end,
+                                                  double* __restrict__ p) {
   constexpr int TPD = LP / 4;               // threads per dimension of the output
   constexpr int GROUPS = 256 / (TPD * TPD); // 4 for LP = 32, 1 for LP = 64
   __shared__ __align__(16) float tile[GRAM_ROWS][LP + 4];
@@ -65,9 +65,6 @@ __global__ void __launch_bounds__(256) gram_partial_kernel(const float* __restri
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-  const uint64_t r_begin = blockIdx.x * rows_per_cta;
-  uint64_t r_end = r_begin + rows_per_cta;
-  if (r_end > n) r_end = n;
   for (uint64_t r0 = r_begin; r0 < r_end; r0 += GRAM_ROWS) {
     for (int e = threadIdx.x; e < GRAM_ROWS * LP; e += 256) {
       const int rr = e / LP, cc = e % LP;
@@ -105,12 +102,36 @@ __global__ void __launch_bounds__(256) gram_partial_kernel(const float* __restri
     }
   }
   if (grp == 0) {
-    double* p = partial + (uint64_t)blockIdx.x * LP * LP;
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) p[(ti * 4 + i) * LP + tj * 4 + j] = acc[i][j];
   }
+}
+
+template <int LP>
+__global__ void __launch_bounds__(256) gram_partial_kernel(const float* __restrict__ y, uint64_t n, uint32_t l,
+                                                           uint32_t ld, uint64_t rows_per_cta,
+                                                           double* __restrict__ partial) {
+  const uint64_t r_begin = blockIdx.x * rows_per_cta;
+  uint64_t r_end = r_begin + rows_per_cta;
+  if (r_end > n) r_end = n;
+  gram_partial_body<LP>(y, l, ld, r_begin, r_end, partial + (uint64_t)blockIdx.x * LP * LP);
+}
+
+// batched: grid = (parts, problems); partial of (problem b, part q) at [(b * parts + q) * 1024]
+__global__ void __launch_bounds__(256) gram_batch_kernel(const float* __restrict__ base, uint32_t ld,
+                                                         const DenseProb* __restrict__ probs,
+                                                         double* __restrict__ partial) {
+  const DenseProb pb = probs[blockIdx.y];
+  uint64_t per = (pb.rows + gridDim.x - 1) / gridDim.x;
+  per = (per + GRAM_ROWS - 1) / GRAM_ROWS * GRAM_ROWS;
+  uint64_t r_begin = (uint64_t)blockIdx.x * per;
+  uint64_t r_end = r_begin + per;
+  if (r_begin > pb.rows) r_begin = pb.rows;
+  if (r_end > pb.rows) r_end = pb.rows;
+  gram_partial_body<32>(base + pb.off, pb.l, ld, r_begin, r_end,
+                        partial + ((uint64_t)blockIdx.y * gridDim.x + blockIdx.x) * 1024);
 }
 
 __global__ void gram_reduce_kernel(const double* __restrict__ partial, int nparts, uint32_t l, int lp,
@@ -218,12 +239,10 @@ int launch_apply_right(gpca_ctx* c, const float* d_y, uint64_t n, uint32_t l, ui
 
 // ------------------------------------------------------------------------------------------
 // Single-CTA two-sided cyclic Jacobi (round-robin pairing), f64, l <= 64.
-__global__ void __launch_bounds__(256) jacobi_eigh_kernel(const double* __restrict__ a_in, uint32_t l,
-                                                          double* __restrict__ evals, double* __restrict__ evecs,
-                                                          const int* __restrict__ skip_flag) {
+__device__ __forceinline__ void jacobi_eigh_body(const double* __restrict__ a_in, uint32_t l,
+                                                 double* __restrict__ evals, double* __restrict__ evecs,
+                                                 double* jsm) {
   constexpr int LP = 64;
-  if (skip_flag && *skip_flag) return;   // the Cholesky path already produced the transform
-  extern __shared__ double jsm[];
   double (*A)[LP + 1] = reinterpret_cast<double (*)[LP + 1]>(jsm);
   double (*V)[LP + 1] = reinterpret_cast<double (*)[LP + 1]>(jsm + LP * (LP + 1));
   __shared__ double cs[LP / 2][2];
@@ -341,6 +360,25 @@ __global__ void __launch_bounds__(256) jacobi_eigh_kernel(const double* __restri
   }
 }
 
+__global__ void __launch_bounds__(256) jacobi_eigh_kernel(const double* __restrict__ a_in, uint32_t l,
+                                                          double* __restrict__ evals, double* __restrict__ evecs,
+                                                          const int* __restrict__ skip_flag) {
+  if (skip_flag && *skip_flag) return;   // the Cholesky path already produced the transform
+  extern __shared__ double jsm[];
+  jacobi_eigh_body(a_in, l, evals, evecs, jsm);
+}
+
+// batched: one CTA per problem; G_b at g + b*1024 (l x l compact), evals at + b*32, evecs at + b*1024
+__global__ void __launch_bounds__(256) jacobi_eigh_batch_kernel(const double* __restrict__ g,
+                                                                const DenseProb* __restrict__ probs,
+                                                                double* __restrict__ evals, double* __restrict__ evecs,
+                                                                const int* __restrict__ skip_flags) {
+  const uint32_t b = blockIdx.x;
+  if (skip_flags && skip_flags[b]) return;
+  extern __shared__ double jsm[];
+  jacobi_eigh_body(g + (size_t)b * 1024, probs[b].l, evals + (size_t)b * 32, evecs + (size_t)b * 1024, jsm);
+}
+
 int launch_jacobi_eigh(gpca_ctx* c, const double* d_a, uint32_t l, double* d_evals, double* d_evecs,
                        const int* d_skip_flag) {
   if (l == 0 || l > 64) {
@@ -445,18 +483,11 @@ int launch_apply_flags(gpca_ctx* c, const float* d_x, uint64_t n, uint32_t k, ui
 // CholeskyQR transform: G = R^T R (upper R), T = R^-1, so that (Y T)^T (Y T) = I.  Single CTA, f64, l <= 64.
 // ok_flag = 1 on success; 0 when a pivot is not safely positive (near rank deficiency) -- the caller then runs the
 // eigen-based path (jacobi_eigh + make_orth_transform), which zeroes deficient directions instead.
-__global__ void __launch_bounds__(256) chol_orth_kernel(const double* __restrict__ g, uint32_t l, double* __restrict__ t,
-                                                        double rel_eps, int* __restrict__ ok_flag) {
+// A (shared, symmetric, n x n valid) is overwritten by its upper Cholesky factor
+__device__ __forceinline__ void chol_orth_body(double (*A)[65], int* bad_p, const int n, double* __restrict__ t,
+                                               double rel_eps, int* __restrict__ ok_flag) {
   constexpr int LP = 64;
-  __shared__ double A[LP][LP + 1];   // 33 KB
-  __shared__ int bad;
-  const int n = (int)l;
-  for (int e = threadIdx.x; e < LP * LP; e += blockDim.x) {
-    const int i = e / LP, j = e % LP;
-    A[i][j] = (i < n && j < n) ? 0.5 * (g[i * n + j] + g[j * n + i]) : 0.0;
-  }
-  if (threadIdx.x == 0) bad = 0;
-  __syncthreads();
+  int& bad = *bad_p;
   double dmax = 0.0;
   for (int i = 0; i < n; ++i) dmax = fmax(dmax, A[i][i]);
   const double thr = rel_eps * dmax;
@@ -499,6 +530,49 @@ __global__ void __launch_bounds__(256) chol_orth_kernel(const double* __restrict
   if (threadIdx.x == 0) *ok_flag = 1;
 }
 
+__global__ void __launch_bounds__(256) chol_orth_kernel(const double* __restrict__ g, uint32_t l, double* __restrict__ t,
+                                                        double rel_eps, int* __restrict__ ok_flag) {
+  constexpr int LP = 64;
+  __shared__ double A[LP][LP + 1];   // 33 KB
+  __shared__ int bad;
+  const int n = (int)l;
+  for (int e = threadIdx.x; e < LP * LP; e += blockDim.x) {
+    const int i = e / LP, j = e % LP;
+    A[i][j] = (i < n && j < n) ? 0.5 * (g[i * n + j] + g[j * n + i]) : 0.0;
+  }
+  if (threadIdx.x == 0) bad = 0;
+  __syncthreads();
+  chol_orth_body(A, &bad, n, t, rel_eps, ok_flag);
+}
+
+// batched: one CTA per problem.  Sums the problem's Gram partials in a fixed order, stores the l x l Gram (for the
+// eigen fallback) and the Cholesky transform T_b, flag_b.
+__global__ void __launch_bounds__(256) chol_orth_batch_kernel(const double* __restrict__ partial, int nparts,
+                                                              const DenseProb* __restrict__ probs,
+                                                              double* __restrict__ g_out, double* __restrict__ t_out,
+                                                              double rel_eps, int* __restrict__ ok_flags) {
+  constexpr int LP = 64;
+  __shared__ double A[LP][LP + 1];
+  __shared__ int bad;
+  const uint32_t b = blockIdx.x;
+  const int n = (int)probs[b].l;
+  for (int e = threadIdx.x; e < LP * LP; e += blockDim.x) {
+    const int i = e / LP, j = e % LP;
+    double s = 0.0;
+    if (i < n && j < n) {
+      for (int q = 0; q < nparts; ++q) {
+        const double* pp = partial + ((uint64_t)b * nparts + q) * 1024;
+        s += 0.5 * (pp[i * 32 + j] + pp[j * 32 + i]);
+      }
+      g_out[(size_t)b * 1024 + i * n + j] = s;
+    }
+    A[i][j] = s;
+  }
+  if (threadIdx.x == 0) bad = 0;
+  __syncthreads();
+  chol_orth_body(A, &bad, n, t_out + (size_t)b * 1024, rel_eps, ok_flags + b);
+}
+
 int launch_chol_orth(gpca_ctx* c, const double* d_g, uint32_t l, double* d_t, double rel_eps, int* d_ok_flag) {
   if (l == 0 || l > 64) {
     c->set_error("chol_orth: l must be in 1..64");
@@ -506,5 +580,220 @@ int launch_chol_orth(gpca_ctx* c, const double* d_g, uint32_t l, double* d_t, do
   }
   chol_orth_kernel<<<1, 256, 0, c->stream>>>(d_g, l, d_t, rel_eps, d_ok_flag);
   KLAUNCH_CHECK(c);
+  return GPCA_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Batched variants for the per-LD-block local bases (EigenSNP): one launch covers every block.
+__global__ void gaussian_batch_kernel(float* __restrict__ base, uint32_t ld, const DenseProb* __restrict__ probs,
+                                      uint64_t seed, const uint32_t* __restrict__ streams) {
+  const DenseProb pb = probs[blockIdx.y];
+  float* out = base + pb.off;
+  const uint32_t stream = streams[blockIdx.y];
+  const uint32_t groups = (ld + 3) / 4;
+  const uint64_t total = (uint64_t)pb.rows * groups;
+  for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < total;
+       t += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t r = t / groups;
+    const uint32_t cg = (uint32_t)(t - r * groups);
+    float z[4];
+    philox_normal4(seed, stream, r, cg, z);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t cidx = cg * 4 + j;
+      if (cidx < ld) out[r * ld + cidx] = (cidx < pb.l) ? z[j] : 0.0f;
+    }
+  }
+}
+
+int launch_gaussian_batch(gpca_ctx* c, float* d_base, uint32_t ld, const DenseProb* d_probs, uint32_t n_probs,
+                          uint64_t max_rows, uint64_t seed, const uint32_t* d_streams) {
+  if (!n_probs || !max_rows) return GPCA_OK;
+  const uint64_t total = max_rows * ((ld + 3) / 4);
+  uint64_t gx = (total + 255) / 256;
+  const uint64_t cap = ((uint64_t)c->sm_count * 32 + n_probs - 1) / n_probs;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  dim3 grid((unsigned)gx, n_probs);
+  gaussian_batch_kernel<<<grid, 256, 0, c->stream>>>(d_base, ld, d_probs, seed, d_streams);
+  KLAUNCH_CHECK(c);
+  return GPCA_OK;
+}
+
+int dense_batch_ws(gpca_ctx* c, uint32_t n_probs, DenseBatchWs& ws) {
+  const size_t per = 3 * 1024 + 32 + 1;   // doubles per problem (flags stored in the last slot, as ints)
+  GPCA_CUDA_TRY(c, c->ws_batch.alloc((size_t)n_probs * per));
+  double* p = c->ws_batch.p;
+  ws.G = p;
+  ws.T = p + (size_t)n_probs * 1024;
+  ws.evecs = p + (size_t)n_probs * 2048;
+  ws.evals = p + (size_t)n_probs * 3072;
+  ws.flags = reinterpret_cast<int*>(p + (size_t)n_probs * (3072 + 32));
+  return GPCA_OK;
+}
+
+int launch_gram_batch(gpca_ctx* c, const float* d_base, uint32_t ld, const DenseProb* d_probs, uint32_t n_probs,
+                      uint64_t max_rows, int* nparts) {
+  int np = (int)((max_rows + 2047) / 2048);
+  const int cap = (c->sm_count * 16 + (int)n_probs - 1) / (int)n_probs;
+  if (np > cap) np = cap;
+  if (np > 64) np = 64;
+  if (np < 1) np = 1;
+  GPCA_CUDA_TRY(c, c->ws_gram.alloc((size_t)np * n_probs * 1024));
+  dim3 grid((unsigned)np, n_probs);
+  gram_batch_kernel<<<grid, 256, 0, c->stream>>>(d_base, ld, d_probs, c->ws_gram.p);
+  KLAUNCH_CHECK(c);
+  *nparts = np;
+  return GPCA_OK;
+}
+
+int launch_chol_orth_batch(gpca_ctx* c, int nparts, const DenseProb* d_probs, uint32_t n_probs, double rel_eps,
+                           const DenseBatchWs& ws) {
+  chol_orth_batch_kernel<<<n_probs, 256, 0, c->stream>>>(c->ws_gram.p, nparts, d_probs, ws.G, ws.T, rel_eps, ws.flags);
+  KLAUNCH_CHECK(c);
+  return GPCA_OK;
+}
+
+int launch_jacobi_eigh_batch(gpca_ctx* c, const DenseProb* d_probs, uint32_t n_probs, const DenseBatchWs& ws,
+                             bool use_flags) {
+  const size_t smem = 2 * 64 * 65 * sizeof(double);
+  GPCA_CUDA_TRY(c, cudaFuncSetAttribute(jacobi_eigh_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  jacobi_eigh_batch_kernel<<<n_probs, 256, smem, c->stream>>>(ws.G, d_probs, ws.evals, ws.evecs,
+                                                              use_flags ? ws.flags : nullptr);
+  KLAUNCH_CHECK(c);
+  return GPCA_OK;
+}
+
+__global__ void make_orth_transform_batch_kernel(const DenseProb* __restrict__ probs, const double* __restrict__ evals,
+                                                 const double* __restrict__ evecs, double* __restrict__ t,
+                                                 double rel_eps, const int* __restrict__ skip_flags) {
+  const uint32_t b = blockIdx.x;
+  if (skip_flags[b]) return;
+  const uint32_t l = probs[b].l;
+  const double* ev = evals + (size_t)b * 32;
+  const double lmax = ev[0];
+  for (int i = threadIdx.x; i < (int)(l * l); i += blockDim.x) {
+    const double lam = ev[i % l];
+    t[(size_t)b * 1024 + i] = (lam > rel_eps * lmax && lam > 0.0) ? evecs[(size_t)b * 1024 + i] / sqrt(lam) : 0.0;
+  }
+}
+
+int launch_make_orth_transform_batch(gpca_ctx* c, const DenseProb* d_probs, uint32_t n_probs, double rel_eps,
+                                     const DenseBatchWs& ws) {
+  make_orth_transform_batch_kernel<<<n_probs, 128, 0, c->stream>>>(d_probs, ws.evals, ws.evecs, ws.T, rel_eps, ws.flags);
+  KLAUNCH_CHECK(c);
+  return GPCA_OK;
+}
+
+__global__ void rotation_batch_kernel(const DenseProb* __restrict__ probs, const uint32_t* __restrict__ l2s,
+                                      const double* __restrict__ evecs, double* __restrict__ t) {
+  const uint32_t b = blockIdx.x;
+  const uint32_t l = probs[b].l, k = l2s[b];
+  for (int i = threadIdx.x; i < (int)(l * k); i += blockDim.x) {
+    const int r = i / k, j = i % k;
+    t[(size_t)b * 1024 + i] = evecs[(size_t)b * 1024 + r * l + j];
+  }
+}
+
+int launch_rotation_batch(gpca_ctx* c, const DenseProb* d_probs, uint32_t n_probs, const uint32_t* d_l2,
+                          const DenseBatchWs& ws) {
+  rotation_batch_kernel<<<n_probs, 128, 0, c->stream>>>(d_probs, d_l2, ws.evecs, ws.T);
+  KLAUNCH_CHECK(c);
+  return GPCA_OK;
+}
+
+// grid = (row tiles, problems)
+template <int NOWN>
+__global__ void __launch_bounds__(256) apply_right_batch_kernel(const float* __restrict__ base, uint32_t ld,
+                                                                const DenseProb* __restrict__ probs,
+                                                                const double* __restrict__ t_all,
+                                                                const uint32_t* __restrict__ l2s,
+                                                                float* __restrict__ out_base,
+                                                                const uint64_t* __restrict__ out_offs, uint32_t ldo) {
+  extern __shared__ double sm[];
+  const DenseProb pb = probs[blockIdx.y];
+  const uint32_t l = pb.l;
+  const uint32_t l2 = l2s ? l2s[blockIdx.y] : l;
+  const uint64_t n = pb.rows;
+  const float* y = base + pb.off;
+  float* out = out_base + (out_offs ? out_offs[blockIdx.y] : pb.off);
+  const double* t = t_all + (size_t)blockIdx.y * 1024;
+  const int l2p = NOWN * 4;
+  double* ts = sm;                                             // [32][l2p]
+  float* tile = reinterpret_cast<float*>(sm + 32 * l2p);       // [64][33]
+  for (int i = threadIdx.x; i < (int)(l * l2p); i += 256) {
+    const int cc = i / l2p, c2 = i % l2p;
+    ts[i] = ((uint32_t)c2 < l2) ? t[cc * l2 + c2] : 0.0;
+  }
+  const int lp = 33;
+  const uint64_t ntiles = (n + 63) / 64;
+  for (uint64_t tix = blockIdx.x; tix < ntiles; tix += gridDim.x) {
+    const uint64_t r0 = tix * 64;
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * (int)l; i += 256) {
+      const int rr = i / l, cc = i % l;
+      const uint64_t r = r0 + rr;
+      tile[rr * lp + cc] = (r < n) ? y[r * ld + cc] : 0.0f;
+    }
+    __syncthreads();
+    const int rr = threadIdx.x >> 2, cg = threadIdx.x & 3;
+    const uint64_t r = r0 + rr;
+    if (r < n) {
+      double acc[NOWN];
+#pragma unroll
+      for (int j = 0; j < NOWN; ++j) acc[j] = 0.0;
+      for (uint32_t cc = 0; cc < l; ++cc) {
+        const double yv = (double)tile[rr * lp + cc];
+        const double* trow = ts + cc * l2p + cg;
+#pragma unroll
+        for (int j = 0; j < NOWN; ++j) acc[j] = fma(yv, trow[4 * j], acc[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < NOWN; ++j)
+        if (cg + 4u * j < l2) out[r * ldo + cg + 4 * j] = (float)acc[j];
+    }
+  }
+}
+
+template <int NOWN>
+static int run_apply_right_batch(gpca_ctx* c, const float* d_base, uint32_t ld, const DenseProb* d_probs,
+                                 uint32_t n_probs, uint64_t max_rows, const double* d_t, const uint32_t* d_l2,
+                                 float* d_out, const uint64_t* d_out_offs, uint32_t ldo) {
+  const size_t smem = (size_t)32 * NOWN * 4 * sizeof(double) + (size_t)64 * 33 * sizeof(float);
+  uint64_t gx = (max_rows + 63) / 64;
+  const uint64_t cap = ((uint64_t)c->sm_count * 16 + n_probs - 1) / n_probs;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  dim3 grid((unsigned)gx, n_probs);
+  apply_right_batch_kernel<NOWN><<<grid, 256, smem, c->stream>>>(d_base, ld, d_probs, d_t, d_l2, d_out, d_out_offs, ldo);
+  KLAUNCH_CHECK(c);
+  return GPCA_OK;
+}
+
+int launch_apply_right_batch(gpca_ctx* c, const float* d_base, uint32_t ld, const DenseProb* d_probs,
+                             uint32_t n_probs, uint64_t max_rows, const double* d_t, const uint32_t* d_l2,
+                             uint32_t max_l2, float* d_out, const uint64_t* d_out_offs, uint32_t ldo) {
+  if (!n_probs || !max_rows || !max_l2) return GPCA_OK;
+  if (max_l2 > 32) {
+    c->set_error("apply_right_batch: l2 must be <= 32");
+    return GPCA_ERR_INVALID;
+  }
+  const uint32_t need = (max_l2 + 3) / 4;
+  if (need <= 2) return run_apply_right_batch<2>(c, d_base, ld, d_probs, n_probs, max_rows, d_t, d_l2, d_out, d_out_offs, ldo);
+  if (need <= 5) return run_apply_right_batch<5>(c, d_base, ld, d_probs, n_probs, max_rows, d_t, d_l2, d_out, d_out_offs, ldo);
+  return run_apply_right_batch<8>(c, d_base, ld, d_probs, n_probs, max_rows, d_t, d_l2, d_out, d_out_offs, ldo);
+}
+
+int orthonormalize_batch(gpca_ctx* c, float* d_base, uint32_t ld, const DenseProb* d_probs, uint32_t n_probs,
+                         uint64_t max_rows, uint32_t max_l, const DenseBatchWs& ws) {
+  for (int rep = 0; rep < 2; ++rep) {
+    int np = 1;
+    GPCA_TRY(launch_gram_batch(c, d_base, ld, d_probs, n_probs, max_rows, &np));
+    const double eps = rep == 0 ? 1e-11 : 1e-13;
+    GPCA_TRY(launch_chol_orth_batch(c, np, d_probs, n_probs, eps, ws));
+    GPCA_TRY(launch_jacobi_eigh_batch(c, d_probs, n_probs, ws, true));
+    GPCA_TRY(launch_make_orth_transform_batch(c, d_probs, n_probs, eps, ws));
+    GPCA_TRY(launch_apply_right_batch(c, d_base, ld, d_probs, n_probs, max_rows, ws.T, nullptr, max_l, d_base, nullptr, ld));
+  }
   return GPCA_OK;
 }

@@ -25,7 +25,7 @@ constexpr int RT = 2;              // row tiles of 128 rows per CTA
 constexpr int STAGE_FIELDS = 256;  // 64 B per row per stage
 constexpr int CHUNKS = 4;          // 64-field chunks per stage
 constexpr int A_TILE_BYTES = 128 * 64;
-constexpr int NUM_THREADS = 352;
+constexpr int NUM_THREADS = 384;   // 12 warps: a multiple of 4, so that warp & 3 is the TMEM lane quarter of the warp for every co-resident CTA (warp 11 idles)
 constexpr int NL = 32;             // logical columns
 constexpr int NM = 64;             // MMA N = hi | lo limbs
 constexpr int SA = 4, SB = 3, SLOTS = 2;   // a TMEM slot holds a chunk pair (128 fields) of both row tiles
@@ -52,13 +52,67 @@ struct I8Params {
   uint32_t total_stages, stages_per_split, ksplit, row_groups, n_items;
   const float* a;
   const float* b;
-  const float* cvec;
-  const float* scales;  // [0] = quantisation scale, [1] = dequantisation scale
+  const float* cvec;    // [32]            (item mode: [n_blocks][32])
+  const float* scales;  // [0] = quantisation scale, [1] = dequantisation scale   (item mode: [n_blocks][2])
   float* out;
   uint32_t ldo, l;
   float* partial;       // [ksplit][rows][32]
+  const I8Item* items;  // item mode (batched per-LD-block passes): explicit work list, no split-K partials
+  uint32_t dbg_reverse;
 };
 
+// What one work item covers.  Regular mode derives it from (k-split, row group); item mode reads it from the table.
+struct ItemInfo {
+  uint32_t row0;      // first row of the packed matrix
+  uint32_t nrows;     // valid rows (<= 256)
+  uint32_t kbyte0;    // first byte (4 fields) of the K range inside a packed row
+  uint32_t nst;       // stages of 256 fields
+  uint32_t img_st0;   // first stage of the operand image
+  uint32_t blk;       // operand block (column sums / scale), item mode
+  uint32_t l;         // logical output columns
+  uint32_t ks;        // k-split index, regular mode
+  uint64_t out_off;   // element offset of the item's first output row
+};
+
+template <bool ITEMS>
+__device__ __forceinline__ ItemInfo decode_item(const I8Params& p, uint32_t item) {
+  ItemInfo ii;
+  if (ITEMS) {
+    const uint4* q = reinterpret_cast<const uint4*>(p.items + item);
+    const uint4 i0 = __ldg(q), i1 = __ldg(q + 1);
+    ii.row0 = i0.x;
+    ii.nrows = i0.y & 0xffffu;
+    ii.l = i0.y >> 16;
+    ii.kbyte0 = i0.z;
+    ii.nst = i0.w;
+    ii.img_st0 = i1.x;
+    ii.blk = i1.y;
+    ii.out_off = (uint64_t)i1.z | ((uint64_t)i1.w << 32);
+    ii.ks = 0;
+  } else {
+    if (p.dbg_reverse && blockIdx.x >= gridDim.x / 2) {   // DEBUG: upper-half CTAs walk their own items backwards
+      const uint32_t last = blockIdx.x + ((p.n_items - 1 - blockIdx.x) / gridDim.x) * gridDim.x;
+      item = last - (item - blockIdx.x);
+    }
+    const uint32_t ks = item / p.row_groups, rg = item - ks * p.row_groups;
+    const uint32_t st0 = ks * p.stages_per_split;
+    uint32_t st1 = st0 + p.stages_per_split;
+    if (st1 > p.total_stages) st1 = p.total_stages;
+    ii.row0 = rg * (RT * 128);
+    const uint64_t left = p.rows - (uint64_t)ii.row0;
+    ii.nrows = left < (uint64_t)(RT * 128) ? (uint32_t)left : (uint32_t)(RT * 128);
+    ii.kbyte0 = st0 * 64;
+    ii.nst = st1 - st0;
+    ii.img_st0 = st0;
+    ii.blk = 0;
+    ii.l = p.l;
+    ii.ks = ks;
+    ii.out_off = (uint64_t)ii.row0 * p.ldo;
+  }
+  return ii;
+}
+
+template <bool ITEMS>
 __global__ void __launch_bounds__(NUM_THREADS, 2) sketch_i8_kernel(const __grid_constant__ CUtensorMap tmap,
                                                                     const I8Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -102,16 +156,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) sketch_i8_kernel(const __grid_
     tmem_alloc(tmem_slot, TMEM_COLS);
     tmem_relinquish();
   }
-  if (threadIdx.x >= 64 && threadIdx.x < 128) {
-    const int i = threadIdx.x - 64;
-    cv_s[i] = (i < NL) ? p.cvec[i] : 0.0f;
-  } else if (threadIdx.x == 128) {
-    cv_s[64] = p.scales[1];
+  if (!ITEMS) {
+    if (threadIdx.x >= 64 && threadIdx.x < 128) {
+      const int i = threadIdx.x - 64;
+      cv_s[i] = (i < NL) ? p.cvec[i] : 0.0f;
+    } else if (threadIdx.x == 128) {
+      cv_s[64] = p.scales[1];
+    }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const float s_scale = cv_s[64];
+  const float s_scale = ITEMS ? 0.0f : cv_s[64];
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
@@ -120,12 +176,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) sketch_i8_kernel(const __grid_
     const bool is_a = (warp == 0);
     uint32_t it = 0;
     for (uint32_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-      const uint32_t ks = item / p.row_groups, rg = item - ks * p.row_groups;
-      const uint32_t st0 = ks * p.stages_per_split;
-      uint32_t st1 = st0 + p.stages_per_split;
-      if (st1 > p.total_stages) st1 = p.total_stages;
-      const int row0 = (int)(rg * (RT * 128));
-      for (uint32_t st = st0; st < st1; ++st, ++it) {
+      const ItemInfo ii = decode_item<ITEMS>(p, item);
+      const int row0 = (int)ii.row0;
+      for (uint32_t st = 0; st < ii.nst; ++st, ++it) {
         if (is_a) {
           const int s = it % SA;
           const uint32_t ph = (it / SA) & 1u;
@@ -135,7 +188,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) sketch_i8_kernel(const __grid_
             mbar_arrive_expect_tx(bar_afull(s), A_STAGE_BYTES);
 #pragma unroll
             for (int t = 0; t < RT; ++t)
-              tma_load_2d(sbase + t * A_TILE_BYTES, &tmap, bar_afull(s), (int)(st * 64), row0 + t * 128);
+              tma_load_2d(sbase + t * A_TILE_BYTES, &tmap, bar_afull(s), (int)(ii.kbyte0 + st * 64), row0 + t * 128);
           }
         } else {
           const int s = it % SB;
@@ -143,7 +196,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) sketch_i8_kernel(const __grid_
           mbar_wait(bar_bempty(s), ph ^ 1u);
           if (elect_one()) {
             mbar_arrive_expect_tx(bar_bfull(s), B_STAGE_BYTES);
-            bulk_load_1d(b_ring + s * B_STAGE_BYTES, p.bimg + (size_t)st * B_STAGE_BYTES, B_STAGE_BYTES, bar_bfull(s));
+            bulk_load_1d(b_ring + s * B_STAGE_BYTES, p.bimg + (size_t)(ii.img_st0 + st) * B_STAGE_BYTES, B_STAGE_BYTES,
+                         bar_bfull(s));
           }
         }
         __syncwarp();
@@ -157,14 +211,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) sketch_i8_kernel(const __grid_
     const uint32_t desc_hi = (uint32_t)(128 >> 4) | (1u << 14);
     uint32_t it = 0, cit = 0, item_idx = 0;
     for (uint32_t item = blockIdx.x; item < p.n_items; item += gridDim.x, ++item_idx) {
-      const uint32_t ks = item / p.row_groups;
-      const uint32_t st0 = ks * p.stages_per_split;
-      uint32_t st1 = st0 + p.stages_per_split;
-      if (st1 > p.total_stages) st1 = p.total_stages;
+      const uint32_t nst = decode_item<ITEMS>(p, item).nst;
       mbar_wait(bar_accempty, (item_idx & 1u) ^ 1u);
       tc_fence_after();
       uint32_t acc_flag = 0;
-      for (uint32_t st = st0; st < st1; ++st, ++it) {
+      for (uint32_t st = 0; st < nst; ++st, ++it) {
         const int s = it % SB;
         const uint32_t ph = (it / SB) & 1u;
         mbar_wait(bar_bfull(s), ph);
@@ -207,11 +258,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) sketch_i8_kernel(const __grid_
     const uint32_t sw = (uint32_t)((row_in_tile >> 1) & 3);
     uint32_t it = 0, cit = 0, item_idx = 0;
     for (uint32_t item = blockIdx.x; item < p.n_items; item += gridDim.x, ++item_idx) {
-      const uint32_t ks = item / p.row_groups, rg = item - ks * p.row_groups;
-      const uint32_t st0 = ks * p.stages_per_split;
-      uint32_t st1 = st0 + p.stages_per_split;
-      if (st1 > p.total_stages) st1 = p.total_stages;
-      for (uint32_t st = st0; st < st1; ++st, ++it) {
+      const ItemInfo ii = decode_item<ITEMS>(p, item);
+      for (uint32_t st = 0; st < ii.nst; ++st, ++it) {
         const int s = it % SA;
         const uint32_t ph = (it / SA) & 1u;
         mbar_wait(bar_afull(s), ph);
@@ -224,8 +272,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) sketch_i8_kernel(const __grid_
                        : "=r"(v[q].x), "=r"(v[q].y), "=r"(v[q].z), "=r"(v[q].w)
                        : "r"(addr));
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_aempty(s));
 #pragma unroll
         for (int q = 0; q < CHUNKS; q += 2, ++cit) {
           const int slot = cit % SLOTS;
@@ -249,11 +295,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) sketch_i8_kernel(const __grid_
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_tfull(slot));
         }
+        // The stage is released only now: every register loaded from it has been consumed by the expansions above, so
+        // all of this warp's shared-memory reads have completed before the producer may let TMA overwrite the stage.
+        // (Releasing right after ISSUING the loads let the refill race with loads still in flight when two CTAs
+        // share an SM.)
+        if (lane == 0) mbar_arrive(bar_aempty(s));
       }
       // ---- epilogue
-      const uint64_t r = (uint64_t)rg * (RT * 128) + tile * 128 + row_in_tile;
+      const uint32_t lrow = (uint32_t)(tile * 128 + row_in_tile);
+      const bool live = lrow < ii.nrows;
+      const uint64_t r = (uint64_t)ii.row0 + lrow;
       float ar = 1.0f, br = 1.0f;
-      if (!p.partial && r < p.rows) {
+      if (!p.partial && live) {
         if (p.a) ar = __ldg(p.a + r);
         if (p.b) br = __ldg(p.b + r);
       }
@@ -266,10 +319,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) sketch_i8_kernel(const __grid_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_accempty);
-      if (r < p.rows) {
-        const double scale = (double)s_scale;
-        if (p.partial) {
-          float* dst = p.partial + ((uint64_t)ks * p.rows + r) * NL;
+      if (live) {
+        const double scale = ITEMS ? (double)__ldg(p.scales + 2 * ii.blk + 1) : (double)s_scale;
+        if (!ITEMS && p.partial) {
+          float* dst = p.partial + ((uint64_t)ii.ks * p.rows + r) * NL;
 #pragma unroll
           for (int c = 0; c < NL; c += 4) {
             float4 o;
@@ -280,18 +333,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) sketch_i8_kernel(const __grid_
             *reinterpret_cast<float4*>(dst + c) = o;
           }
         } else {
-          float* dst = p.out + r * p.ldo;
-          const bool vec2 = (p.ldo & 1u) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 7) == 0;
+          float* dst = p.out + ii.out_off + (uint64_t)lrow * p.ldo;
+          const float* cv = ITEMS ? p.cvec + (size_t)ii.blk * NL : cv_s;
+          const bool vec2 = (p.ldo & 1u) == 0 && (reinterpret_cast<uintptr_t>(p.out + ii.out_off) & 7) == 0;
 #pragma unroll
           for (int c = 0; c < NL; c += 2) {
-            const float v0 = ar * (float)((double)((long long)(int)hi[c] * 256 + (int)lo[c]) * scale) - br * cv_s[c];
-            const float v1 =
-                ar * (float)((double)((long long)(int)hi[c + 1] * 256 + (int)lo[c + 1]) * scale) - br * cv_s[c + 1];
-            if (vec2 && (uint32_t)c + 1 < p.l) {
+            const float c0 = ITEMS ? __ldg(cv + c) : cv[c];
+            const float c1 = ITEMS ? __ldg(cv + c + 1) : cv[c + 1];
+            const float v0 = ar * (float)((double)((long long)(int)hi[c] * 256 + (int)lo[c]) * scale) - br * c0;
+            const float v1 = ar * (float)((double)((long long)(int)hi[c + 1] * 256 + (int)lo[c + 1]) * scale) - br * c1;
+            if (vec2 && (uint32_t)c + 1 < ii.l) {
               *reinterpret_cast<float2*>(dst + c) = make_float2(v0, v1);
             } else {
-              if ((uint32_t)c < p.l) dst[c] = v0;
-              if ((uint32_t)c + 1 < p.l) dst[c + 1] = v1;
+              if ((uint32_t)c < ii.l) dst[c] = v0;
+              if ((uint32_t)c + 1 < ii.l) dst[c + 1] = v1;
             }
           }
         }
@@ -424,6 +479,123 @@ __global__ void sketch_reduce_i8_kernel(const float* __restrict__ partial, int n
   }
 }
 
+// ---- batched operand preparation (one launch for all LD blocks) ----------------------------------------------------
+// grid = (parts, blocks): column sums (f64 partials, summed in a fixed order afterwards) and max |f o Bin| per block
+__global__ void __launch_bounds__(256) i8_colstats_batch_kernel(const float* __restrict__ bin, uint32_t ld,
+                                                                const SketchBatchBlock* __restrict__ blocks,
+                                                                const float* __restrict__ f,
+                                                                const float* __restrict__ e,
+                                                                double* __restrict__ cpart,
+                                                                unsigned int* __restrict__ amax_bits) {
+  __shared__ double red[256];
+  __shared__ float redm[256];
+  const SketchBatchBlock bk = blocks[blockIdx.y];
+  const float* src = bin + bk.bin_off;
+  const float* fb = f ? f + bk.fe_off : nullptr;
+  const float* eb = e ? e + bk.fe_off : nullptr;
+  const int cidx = threadIdx.x & 31;
+  const int rr = threadIdx.x >> 5;
+  const bool c0 = (uint32_t)cidx < bk.l;
+  const uint64_t K = bk.K;
+  double acc0 = 0.0;
+  float mx = 0.0f;
+  const uint64_t stride = (uint64_t)gridDim.x * 8;
+  for (uint64_t k = (uint64_t)blockIdx.x * 8 + rr; k < K; k += 4 * stride) {
+    float x0[4], ek[4], fk[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint64_t kk = k + u * stride;
+      const bool live = kk < K;
+      x0[u] = (live && c0) ? src[kk * ld + cidx] : 0.0f;
+      ek[u] = (live && eb) ? eb[kk] : 1.0f;
+      fk[u] = (live && fb) ? fb[kk] : 1.0f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      acc0 += (double)(x0[u] * ek[u]);
+      mx = fmaxf(mx, fabsf(x0[u] * fk[u]));
+    }
+  }
+  red[threadIdx.x] = acc0;
+  redm[threadIdx.x] = mx;
+  __syncthreads();
+  if (rr == 0) {
+    double s0 = 0.0;
+    float m = 0.0f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      s0 += red[q * 32 + cidx];
+      m = fmaxf(m, redm[q * 32 + cidx]);
+    }
+    cpart[((uint64_t)blockIdx.y * gridDim.x + blockIdx.x) * 32 + cidx] = s0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (cidx == 0 && m > 0.0f && isfinite(m)) atomicMax(amax_bits + blockIdx.y, __float_as_uint(m));
+  }
+}
+
+// one warp per block
+__global__ void i8_finalize_stats_batch_kernel(const double* __restrict__ cpart, int nparts, uint32_t n_blocks,
+                                               float* __restrict__ cvec, unsigned int* __restrict__ amax_bits,
+                                               float* __restrict__ scales) {
+  const uint32_t b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int cidx = threadIdx.x & 31;
+  if (b >= n_blocks) return;
+  double s = 0.0;
+  for (int q = 0; q < nparts; ++q) s += cpart[((uint64_t)b * nparts + q) * 32 + cidx];
+  cvec[(uint64_t)b * 32 + cidx] = (float)s;
+  if (cidx == 0) {
+    const float m = __uint_as_float(amax_bits[b]);
+    scales[2 * b + 0] = (m > 0.0f) ? 32512.0f / m : 0.0f;
+    scales[2 * b + 1] = (m > 0.0f) ? m / 32512.0f : 0.0f;
+    amax_bits[b] = 0u;
+  }
+}
+
+// grid = (chunks, blocks); same image layout as prep_b_i8_kernel, written at the block's image stages
+__global__ void __launch_bounds__(256) prep_b_i8_batch_kernel(const float* __restrict__ bin, uint32_t ld,
+                                                              const SketchBatchBlock* __restrict__ blocks,
+                                                              const float* __restrict__ f,
+                                                              const float* __restrict__ scales,
+                                                              int8_t* __restrict__ img_all) {
+  const SketchBatchBlock bk = blocks[blockIdx.y];
+  const float* src = bin + bk.bin_off;
+  const float* fb = f ? f + bk.fe_off : nullptr;
+  const uint64_t K = bk.K;
+  const uint32_t l = bk.l;
+  const uint64_t Kpad = (uint64_t)bk.nst * STAGE_FIELDS;
+  int8_t* img = img_all + (size_t)bk.img_st0 * B_STAGE_BYTES;
+  const float qs = scales[2 * blockIdx.y];
+  const uint64_t total = (Kpad / 16) * NL;
+  for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < total;
+       t += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t n = (uint32_t)(t % NL);
+    const uint64_t kc = t / NL;
+    const uint64_t g = kc >> 1;
+    const uint32_t half_idx = (uint32_t)(kc & 1);
+    __align__(16) int8_t vhi[16], vlo[16];
+#pragma unroll
+    for (int ss = 0; ss < 16; ++ss) {
+      const int s = half_idx * 16 + ss;
+      const int cc = s >> 2, bb = s & 3;
+      const uint64_t k = g * 32 + 16 * (cc >> 2) + (cc & 3) + 4 * bb;
+      int q = 0;
+      if (k < K && n < l) {
+        float v = src[k * ld + n];
+        if (fb) v *= fb[k];
+        q = __float2int_rn(v * qs);
+        q = max(-32512, min(32512, q));
+      }
+      const int h = (q + 128) >> 8;
+      vhi[ss] = (int8_t)h;
+      vlo[ss] = (int8_t)(q - 256 * h);
+    }
+    const uint64_t base = g * 32 * NM + (uint64_t)half_idx * (NM * 16);
+    *reinterpret_cast<uint4*>(img + base + (n >> 3) * 128 + (n & 7) * 16) = *reinterpret_cast<const uint4*>(vhi);
+    *reinterpret_cast<uint4*>(img + base + ((n + 32) >> 3) * 128 + (n & 7) * 16) = *reinterpret_cast<const uint4*>(vlo);
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -492,6 +664,7 @@ int launch_sketch_i8(gpca_ctx* c, const SketchProblem& p) {
     if (ksplit > max_split) ksplit = max_split;
     if (ksplit < 1) ksplit = 1;
   }
+  if (const char* dbg = getenv("GPCA_DEBUG_KSPLIT")) ksplit = (uint32_t)atoi(dbg);
   const uint32_t min_split = (total_stages + MAX_STAGES_PER_ITEM - 1) / MAX_STAGES_PER_ITEM;   // int32 headroom
   if (ksplit < min_split) ksplit = min_split;
   const uint32_t spp = (total_stages + ksplit - 1) / ksplit;
@@ -517,6 +690,8 @@ int launch_sketch_i8(gpca_ctx* c, const SketchProblem& p) {
   tp.ldo = p.ldo;
   tp.l = p.l;
   tp.partial = nullptr;
+  tp.items = nullptr;
+  tp.dbg_reverse = getenv("GPCA_DEBUG_REVERSE") ? 1u : 0u;
   if (ksplit > 1) {
     GPCA_CUDA_TRY(c, c->ws_partial.alloc((size_t)ksplit * rows * NL));
     tp.partial = c->ws_partial.p;
@@ -535,10 +710,13 @@ int launch_sketch_i8(gpca_ctx* c, const SketchProblem& p) {
       return GPCA_ERR_CUDA;
     }
   }
-  GPCA_CUDA_TRY(c, cudaFuncSetAttribute(sketch_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  const uint32_t grid = tp.n_items < slots ? tp.n_items : slots;
+  int smem_bytes = SMEM_BYTES;
+  if (const char* dbg = getenv("GPCA_DEBUG_SMEM_EXTRA")) smem_bytes += atoi(dbg);
+  GPCA_CUDA_TRY(c, cudaFuncSetAttribute(sketch_i8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  uint32_t grid = tp.n_items < slots ? tp.n_items : slots;
+  if (const char* dbg = getenv("GPCA_DEBUG_GRID")) grid = (uint32_t)atoi(dbg);
   KernelTimer kt(c);
-  sketch_i8_kernel<<<grid, NUM_THREADS, SMEM_BYTES, c->stream>>>(tmap, tp);
+  sketch_i8_kernel<false><<<grid, NUM_THREADS, smem_bytes, c->stream>>>(tmap, tp);
   kt.end();
   c->launches++;
   GPCA_CUDA_TRY(c, cudaGetLastError());
@@ -550,5 +728,96 @@ int launch_sketch_i8(gpca_ctx* c, const SketchProblem& p) {
     c->launches++;
     GPCA_CUDA_TRY(c, cudaGetLastError());
   }
+  return GPCA_OK;
+}
+
+// ---- batched launch -------------------------------------------------------------------------------------------------
+bool sketch_i8_batch_supported(gpca_ctx* c) {
+  (void)c;
+  return get_encode_fn_i8() != nullptr;
+}
+
+int launch_sketch_i8_batch(gpca_ctx* c, const SketchBatch& sb) {
+  if (sb.n_items == 0 || sb.n_blocks == 0) return GPCA_OK;
+  if (sb.G.pitch % 16 != 0 || (reinterpret_cast<uintptr_t>(sb.G.p) & 15) != 0 || sb.G.rows < 128 ||
+      (sb.G.avail ? sb.G.avail : sb.G.pitch) < 64) {
+    c->set_error("sketch_i8_batch: unsupported matrix shape");
+    return GPCA_ERR_INVALID;
+  }
+  GPCA_CUDA_TRY(c, c->ws_bytes.alloc((size_t)sb.total_img_stages * B_STAGE_BYTES));
+  int8_t* img = reinterpret_cast<int8_t*>(c->ws_bytes.p);
+  int np = (int)((sb.max_K + 255) / 256);          // 32 rows of 8 per CTA at least
+  const int np_cap = (c->sm_count * 16 + (int)sb.n_blocks - 1) / (int)sb.n_blocks;
+  if (np > np_cap) np = np_cap;
+  if (np < 1) np = 1;
+  GPCA_CUDA_TRY(c, c->ws_cpart.alloc((size_t)np * sb.n_blocks * 32));
+  // per-block column sums [B][32], scales [B][2], amax bits [B]
+  const size_t need = (size_t)sb.n_blocks * (32 + 2 + 1);
+  if (c->ws_bstat.n < need) {
+    GPCA_CUDA_TRY(c, c->ws_bstat.alloc(need));
+    GPCA_CUDA_TRY(c, cudaMemsetAsync(c->ws_bstat.p, 0, need * sizeof(float), c->stream));
+  }
+  // layout is by the buffer's capacity so that a smaller later batch finds its amax words zeroed
+  const size_t cap_blocks = c->ws_bstat.n / 35;
+  float* cvec = c->ws_bstat.p;
+  float* scales = c->ws_bstat.p + cap_blocks * 32;
+  unsigned int* amax = reinterpret_cast<unsigned int*>(c->ws_bstat.p + cap_blocks * 34);
+  {
+    dim3 g1((unsigned)np, sb.n_blocks);
+    i8_colstats_batch_kernel<<<g1, 256, 0, c->stream>>>(sb.Bin, sb.ld, sb.d_blocks, sb.f, sb.e, c->ws_cpart.p, amax);
+    c->launches++;
+    GPCA_CUDA_TRY(c, cudaGetLastError());
+    i8_finalize_stats_batch_kernel<<<(sb.n_blocks + 7) / 8, 256, 0, c->stream>>>(c->ws_cpart.p, np, sb.n_blocks, cvec,
+                                                                                amax, scales);
+    c->launches++;
+    GPCA_CUDA_TRY(c, cudaGetLastError());
+    const uint64_t chunks = ((uint64_t)((sb.max_K + 255) / 256) * 256 / 16 * NL + 255) / 256;
+    unsigned gx = (unsigned)(chunks < 64 ? chunks : 64);
+    if (gx < 1) gx = 1;
+    dim3 g2(gx, sb.n_blocks);
+    prep_b_i8_batch_kernel<<<g2, 256, 0, c->stream>>>(sb.Bin, sb.ld, sb.d_blocks, sb.f, scales, img);
+    c->launches++;
+    GPCA_CUDA_TRY(c, cudaGetLastError());
+  }
+  I8Params tp;
+  tp.bimg = img;
+  tp.rows = sb.G.rows;
+  tp.total_stages = sb.total_img_stages;
+  tp.stages_per_split = 0;
+  tp.ksplit = 1;
+  tp.row_groups = 1;
+  tp.n_items = sb.n_items;
+  tp.a = sb.a;
+  tp.b = sb.b;
+  tp.cvec = cvec;
+  tp.scales = scales;
+  tp.out = sb.out;
+  tp.ldo = sb.ldo;
+  tp.l = 0;
+  tp.partial = nullptr;
+  tp.items = sb.d_items;
+  tp.dbg_reverse = 0;
+  CUtensorMap tmap;
+  {
+    EncodeTiledFn enc = get_encode_fn_i8();
+    const cuuint64_t dims[2] = {(cuuint64_t)(sb.G.avail ? sb.G.avail : sb.G.pitch), (cuuint64_t)sb.G.rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)sb.G.pitch};
+    const cuuint32_t box[2] = {64, 128};
+    const cuuint32_t estr[2] = {1, 1};
+    if (!enc || enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)sb.G.p, dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+      c->set_error("sketch_i8_batch: cuTensorMapEncodeTiled failed");
+      return GPCA_ERR_CUDA;
+    }
+  }
+  GPCA_CUDA_TRY(c, cudaFuncSetAttribute(sketch_i8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  const uint32_t slots = (uint32_t)c->sm_count * 2;
+  const uint32_t grid = tp.n_items < slots ? tp.n_items : slots;
+  KernelTimer kt(c);
+  sketch_i8_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, c->stream>>>(tmap, tp);
+  kt.end();
+  c->launches++;
+  GPCA_CUDA_TRY(c, cudaGetLastError());
   return GPCA_OK;
 }

@@ -30,7 +30,7 @@ constexpr int RT = 2;             // row tiles (of 128 rows) per CTA
 constexpr int STAGE_FIELDS = 256; // K fields per pipeline stage (64 B per row)
 constexpr int CHUNKS = 4;         // 64-field chunks per stage
 constexpr int A_TILE_BYTES = 128 * 64;
-constexpr int NUM_THREADS = 352;  // 11 warps
+constexpr int NUM_THREADS = 384;  // 12 warps: a multiple of 4, so that warp & 3 is the TMEM lane quarter of the warp for every co-resident CTA (warp 11 idles)
 
 template <int NC>
 struct Cfg {
@@ -253,8 +253,6 @@ sketch_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
                        : "=r"(v[q].x), "=r"(v[q].y), "=r"(v[q].z), "=r"(v[q].w)
                        : "r"(addr));
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_aempty(s));   // packed bytes are in registers: the stage may be refilled
         // two chunks per completion wait: the second chunk's expansion overlaps the first TMEM store in flight,
         // and one tcgen05.wait::st covers both stores before the two slots are published to the MMA issuer
 #pragma unroll
@@ -289,6 +287,10 @@ sketch_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
             mbar_arrive(bar_tfull(slot1));
           }
         }
+        // The stage is released only now: every register loaded from it has been consumed by the expansions above, so
+        // all of this warp's shared-memory reads have completed before TMA may overwrite the stage (releasing right
+        // after issuing the loads raced with loads still in flight when two CTAs share an SM).
+        if (lane == 0) mbar_arrive(bar_aempty(s));
       }
       // ---- epilogue of this work item ----
       const uint64_t r = (uint64_t)rg * (RT * 128) + tile * 128 + row_in_tile;

@@ -54,6 +54,10 @@ void gpca_reset_launch_count(gpca_ctx* ctx);
 /* 0 = SIMT fp32 path, 1 = tcgen05 f16 path, 2 = tcgen05 i8 path (exact integer accumulation, l <= 32);
  * engines 1/2 fall back to the next lower one for shapes they do not take */
 int gpca_set_sketch_engine(gpca_ctx* ctx, int engine);
+/* EigenSNP local bases / condensed features: 1 (default) = every LD block in one launch per stage (integer engine,
+ * no missing calls; other cases use the per-block path automatically), 0 = always one block at a time.
+ * Replaces the per-block loop inside EigenSNPCoreAlgorithm::compute_pca (call site src/main.rs:365). */
+int gpca_set_batch_blocks(gpca_ctx* ctx, int on);
 /* device time (ms) and algorithmic packed bytes of the sketch passes since the last reset */
 int gpca_sketch_stats(gpca_ctx* ctx, double* ms_total, double* packed_bytes_total, uint64_t* n_passes, int reset);
 /* device time (ms) of the main sketch kernel launches alone (no operand prep / split-K reduce), as of the last

@@ -124,3 +124,58 @@ def test_sketch_int8_engine_missing_and_determinism(gpu_ctx):
     assert _relerr(od, rd) < 3e-4 and _relerr(on, rn) < 3e-4
     od2, _, on2, _ = _run(gpu_ctx, S, 20, engine=2)
     assert np.array_equal(od, od2) and np.array_equal(on, on2)      # integer accumulation: bit-reproducible
+
+
+def _device_dataset(ctx, n, m):
+    """Synthetic .bed payload generated on the device (bench.py's generator): shapes too large for the numpy oracle."""
+    import bench
+    import genomic_pca_b200 as gp
+    dev = torch.device("cuda", 0)
+    payload = bench.synth_bed_device(torch, n, m, 0, dev)
+    ctx.load_bed_device(payload.data_ptr(), n, m)
+    keep, mean, sd, _ = ctx.snp_qc(gp.QcConfig(0.98, 0.0, 1.0))
+    return ctx.set_pca_snps_mask(keep, mean, sd)
+
+
+@pytest.mark.parametrize("engine", [1, 2])
+def test_tensor_engines_with_two_ctas_per_sm(gpu_ctx, engine):
+    """Shapes with more work items than SMs: two persistent CTAs share every SM and each walks several items.
+    (The small parity cases above never co-locate two CTAs.)  Checked against the SIMT engine, and run to run:
+    every reduction has a fixed order, so repeated passes must agree bit for bit."""
+    n, m, l = 4096, 100_000, 30
+    d = _device_dataset(gpu_ctx, n, m)
+    dev = torch.device("cuda", 0)
+    ext = torch.cuda.ExternalStream(gpu_ctx.stream)
+    with torch.cuda.stream(ext):
+        g = torch.Generator(device=dev)
+        g.manual_seed(5)
+        Bs = torch.randn(n, l, device=dev, generator=g)
+        Bd = torch.randn(d, l, device=dev, generator=g)
+        ext.synchronize()
+        for fn, src, rows in ((gpu_ctx.sketch_snp_side, Bs, d), (gpu_ctx.sketch_sample_side, Bd, n)):
+            outs = []
+            for eng in (0, engine, engine, engine):
+                gpu_ctx.set_sketch_engine(eng)
+                o = torch.empty(rows, l, device=dev)
+                fn(src.data_ptr(), o.data_ptr(), l, l)
+                gpu_ctx.synchronize()
+                outs.append(o.cpu().numpy())
+            ref = outs[0]
+            tol = 2e-3 if engine == 1 else 5e-4
+            assert np.abs(outs[1] - ref).max() / np.abs(ref).max() < tol
+            assert np.array_equal(outs[1], outs[2]) and np.array_equal(outs[1], outs[3])
+    gpu_ctx.set_sketch_engine(2)
+
+
+def test_rfit_reproducible_at_multi_item_scale(gpu_ctx):
+    """Same seed, same context -> identical eigenvalues and scores (2 CTAs per SM, several items per CTA)."""
+    _device_dataset(gpu_ctx, 4096, 100_000)
+    a = gpu_ctx.rfit(10, 10, 2, seed=42)
+    b = gpu_ctx.rfit(10, 10, 2, seed=42)
+    assert np.array_equal(a[1], b[1]) and np.array_equal(a[0], b[0])
+    gpu_ctx.set_sketch_engine(0)
+    c = gpu_ctx.rfit(10, 10, 2, seed=42)
+    gpu_ctx.set_sketch_engine(2)
+    from oracle import pca
+    assert np.abs(a[1] / c[1] - 1).max() < 1e-4
+    assert pca.subspace_angle(a[0], c[0]) < 1e-3
