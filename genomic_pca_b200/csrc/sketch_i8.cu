@@ -24,11 +24,15 @@ using namespace tcptx;
 constexpr int RT = 2;              // row tiles of 128 rows per CTA
 constexpr int STAGE_FIELDS = 256;  // 64 B per row per stage
 constexpr int CHUNKS = 4;          // 64-field chunks per stage
-constexpr int A_TILE_BYTES = 128 * 64;
+constexpr int A_ROW_BYTES = 128;   // bytes of a packed row per A stage = TMA box width: two 256-field stages.
+                                   // (64-byte boxes cap the TMA stream at ~2.6 TB/s when the row pitch is MBs --
+                                   //  one DRAM page per 64 B; 128-byte boxes reach ~5.1 TB/s, tools/probe/tma_bw_probe.cu)
+constexpr int HALVES = A_ROW_BYTES / 64;   // 256-field stages per A stage
+constexpr int A_TILE_BYTES = 128 * A_ROW_BYTES;
 constexpr int NUM_THREADS = 384;   // 12 warps: a multiple of 4, so that warp & 3 is the TMEM lane quarter of the warp for every co-resident CTA (warp 11 idles)
 constexpr int NL = 32;             // logical columns
 constexpr int NM = 64;             // MMA N = hi | lo limbs
-constexpr int SA = 4, SB = 3, SLOTS = 2;   // a TMEM slot holds a chunk pair (128 fields) of both row tiles
+constexpr int SA = 2, SB = 3, SLOTS = 2;   // a TMEM slot holds a chunk pair (128 fields) of both row tiles
 constexpr int A_STAGE_BYTES = RT * A_TILE_BYTES;
 constexpr int B_STAGE_BYTES = STAGE_FIELDS * NM;       // 1 byte per element
 constexpr int TMEM_COLS = 256;
@@ -178,8 +182,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) sketch_i8_kernel(const __grid_
     for (uint32_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const ItemInfo ii = decode_item<ITEMS>(p, item);
       const int row0 = (int)ii.row0;
-      for (uint32_t st = 0; st < ii.nst; ++st, ++it) {
-        if (is_a) {
+      if (is_a) {
+        const uint32_t n_ast = (ii.nst + HALVES - 1) / HALVES;
+        for (uint32_t a = 0; a < n_ast; ++a, ++it) {
           const int s = it % SA;
           const uint32_t ph = (it / SA) & 1u;
           mbar_wait(bar_aempty(s), ph ^ 1u);
@@ -188,9 +193,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) sketch_i8_kernel(const __grid_
             mbar_arrive_expect_tx(bar_afull(s), A_STAGE_BYTES);
 #pragma unroll
             for (int t = 0; t < RT; ++t)
-              tma_load_2d(sbase + t * A_TILE_BYTES, &tmap, bar_afull(s), (int)(ii.kbyte0 + st * 64), row0 + t * 128);
+              tma_load_2d(sbase + t * A_TILE_BYTES, &tmap, bar_afull(s), (int)(ii.kbyte0 + a * A_ROW_BYTES),
+                          row0 + t * 128);
           }
-        } else {
+          __syncwarp();
+        }
+      } else {
+        for (uint32_t st = 0; st < ii.nst; ++st, ++it) {
           const int s = it % SB;
           const uint32_t ph = (it / SB) & 1u;
           mbar_wait(bar_bempty(s), ph ^ 1u);
@@ -199,8 +208,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) sketch_i8_kernel(const __grid_
             bulk_load_1d(b_ring + s * B_STAGE_BYTES, p.bimg + (size_t)(ii.img_st0 + st) * B_STAGE_BYTES, B_STAGE_BYTES,
                          bar_bfull(s));
           }
+          __syncwarp();
         }
-        __syncwarp();
       }
     }
   } else if (warp == 1) {
@@ -255,45 +264,50 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) sketch_i8_kernel(const __grid_
     const int quarter = warp & 3;
     const int row_in_tile = quarter * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-    const uint32_t sw = (uint32_t)((row_in_tile >> 1) & 3);
+    const uint32_t sw = (uint32_t)(row_in_tile & 7);   // SWIZZLE_128B: 16-byte chunk c of row r sits at chunk c ^ (r & 7)
     uint32_t it = 0, cit = 0, item_idx = 0;
     for (uint32_t item = blockIdx.x; item < p.n_items; item += gridDim.x, ++item_idx) {
       const ItemInfo ii = decode_item<ITEMS>(p, item);
-      for (uint32_t st = 0; st < ii.nst; ++st, ++it) {
+      const uint32_t n_ast = (ii.nst + HALVES - 1) / HALVES;
+      for (uint32_t a = 0; a < n_ast; ++a, ++it) {
         const int s = it % SA;
         const uint32_t ph = (it / SA) & 1u;
         mbar_wait(bar_afull(s), ph);
-        const uint32_t arow = a_ring + s * A_STAGE_BYTES + tile * A_TILE_BYTES + row_in_tile * 64;
-        uint4 v[CHUNKS];
+        const uint32_t arow = a_ring + s * A_STAGE_BYTES + tile * A_TILE_BYTES + row_in_tile * A_ROW_BYTES;
 #pragma unroll
-        for (int q = 0; q < CHUNKS; ++q) {
-          const uint32_t addr = arow + (((uint32_t)q ^ sw) << 4);
-          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
-                       : "=r"(v[q].x), "=r"(v[q].y), "=r"(v[q].z), "=r"(v[q].w)
-                       : "r"(addr));
-        }
+        for (int h = 0; h < HALVES; ++h) {
+          if (a * HALVES + h >= ii.nst) break;     // odd stage count: the last A stage is half used
+          uint4 v[CHUNKS];
 #pragma unroll
-        for (int q = 0; q < CHUNKS; q += 2, ++cit) {
-          const int slot = cit % SLOTS;
-          const uint32_t sph = (cit / SLOTS) & 1u;
-          uint32_t r0[16], r1[16];
-          expand_word_u8(v[q].x, r0 + 0);
-          expand_word_u8(v[q].y, r0 + 4);
-          expand_word_u8(v[q].z, r0 + 8);
-          expand_word_u8(v[q].w, r0 + 12);
-          expand_word_u8(v[q + 1].x, r1 + 0);
-          expand_word_u8(v[q + 1].y, r1 + 4);
-          expand_word_u8(v[q + 1].z, r1 + 8);
-          expand_word_u8(v[q + 1].w, r1 + 12);
-          mbar_wait(bar_tempty(slot), sph ^ 1u);      // the MMAs that read this slot have completed
-          tc_fence_after();
-          const uint32_t ta = tmem_base + lane_addr + A_COL0 + (slot * RT + tile) * 32;
-          tmem_st16(ta, r0);
-          tmem_st16(ta + 16, r1);
-          tc_wait_st();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_tfull(slot));
+          for (int q = 0; q < CHUNKS; ++q) {
+            const uint32_t addr = arow + (((uint32_t)(h * CHUNKS + q) ^ sw) << 4);
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(v[q].x), "=r"(v[q].y), "=r"(v[q].z), "=r"(v[q].w)
+                         : "r"(addr));
+          }
+#pragma unroll
+          for (int q = 0; q < CHUNKS; q += 2, ++cit) {
+            const int slot = cit % SLOTS;
+            const uint32_t sph = (cit / SLOTS) & 1u;
+            uint32_t r0[16], r1[16];
+            expand_word_u8(v[q].x, r0 + 0);
+            expand_word_u8(v[q].y, r0 + 4);
+            expand_word_u8(v[q].z, r0 + 8);
+            expand_word_u8(v[q].w, r0 + 12);
+            expand_word_u8(v[q + 1].x, r1 + 0);
+            expand_word_u8(v[q + 1].y, r1 + 4);
+            expand_word_u8(v[q + 1].z, r1 + 8);
+            expand_word_u8(v[q + 1].w, r1 + 12);
+            mbar_wait(bar_tempty(slot), sph ^ 1u);      // the MMAs that read this slot have completed
+            tc_fence_after();
+            const uint32_t ta = tmem_base + lane_addr + A_COL0 + (slot * RT + tile) * 32;
+            tmem_st16(ta, r0);
+            tmem_st16(ta + 16, r1);
+            tc_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tfull(slot));
+          }
         }
         // The stage is released only now: every register loaded from it has been consumed by the expansions above, so
         // all of this warp's shared-memory reads have completed before the producer may let TMA overwrite the stage.
@@ -596,6 +610,13 @@ __global__ void __launch_bounds__(256) prep_b_i8_batch_kernel(const float* __res
   }
 }
 
+CUtensorMapL2promotion l2_promotion() {
+  const char* e = getenv("GPCA_DEBUG_L2PROMO");
+  const int v = e ? atoi(e) : 0;
+  return v == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : v == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                                                  : CU_TENSOR_MAP_L2_PROMOTION_NONE;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -701,10 +722,10 @@ int launch_sketch_i8(gpca_ctx* c, const SketchProblem& p) {
     EncodeTiledFn enc = get_encode_fn_i8();
     const cuuint64_t dims[2] = {(cuuint64_t)(p.G.avail ? p.G.avail : p.G.pitch), (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)p.G.pitch};
-    const cuuint32_t box[2] = {64, 128};
+    const cuuint32_t box[2] = {A_ROW_BYTES, 128};
     const cuuint32_t estr[2] = {1, 1};
     if (!enc || enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)p.G.p, dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, l2_promotion(),
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
       c->set_error("sketch_i8: cuTensorMapEncodeTiled failed");
       return GPCA_ERR_CUDA;
@@ -802,10 +823,10 @@ int launch_sketch_i8_batch(gpca_ctx* c, const SketchBatch& sb) {
     EncodeTiledFn enc = get_encode_fn_i8();
     const cuuint64_t dims[2] = {(cuuint64_t)(sb.G.avail ? sb.G.avail : sb.G.pitch), (cuuint64_t)sb.G.rows};
     const cuuint64_t strides[1] = {(cuuint64_t)sb.G.pitch};
-    const cuuint32_t box[2] = {64, 128};
+    const cuuint32_t box[2] = {A_ROW_BYTES, 128};
     const cuuint32_t estr[2] = {1, 1};
     if (!enc || enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)sb.G.p, dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, l2_promotion(),
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
       c->set_error("sketch_i8_batch: cuTensorMapEncodeTiled failed");
       return GPCA_ERR_CUDA;
