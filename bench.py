@@ -276,10 +276,12 @@ def run_ours(args, rank, world):
         del payload
         e2e_steps = max(1, min(args.steps, 3))
 
+        stats_out = (np.empty(m, dtype=np.uint8), np.empty(m, dtype=np.float32), np.empty(m, dtype=np.float32))
+
         def e2e_step():
-            ctx.load_bed_host_ptr(host.data_ptr(), n, m)
-            keep, mean, sd = ctx.vcf_maf_filter(0.01)
-            ctx.set_pca_snps_mask(keep, mean, sd)
+            # one streaming ingest call (H2D copy, counts, MAF filter on host threads, resident matrices), then rfit;
+            # the keep mask and the per-SNP mean / sd come back to the host as in the reference's VCF flow
+            keep, mean, sd, _, d_pca = ctx.ingest_bed(host.data_ptr(), n, m, qc=None, vcf_maf=0.01, out=stats_out)
             return ctx.rfit(K_COMPONENTS, OVERSAMPLE, power_iters=POWER_ITERS, seed=RFIT_SEED, want_loadings=False)
 
         e2e_step()
@@ -294,7 +296,7 @@ def run_ours(args, rank, world):
             dist.all_reduce(te_t, op=dist.ReduceOp.MAX)
         te = float(te_t.item())
         e2e = {"value": world * passes * bytes_per_pass / te / 1e9, "unit": "GB/s",
-               "h2d_bytes_per_step": int(m * bps), "d2h_bytes_per_step": int(n * K_COMPONENTS * 4 + m * 16),
+               "h2d_bytes_per_step": int(m * bps), "d2h_bytes_per_step": int(n * K_COMPONENTS * 8 + K_COMPONENTS * 8 + m * 16),
                "ms_per_step": te * 1e3, "steps": e2e_steps}
 
     if rank != 0:

@@ -101,6 +101,8 @@ _sig("gpca_vcf_maf_filter", C.c_int, C.c_void_p, C.c_double, _u8p, _f32p, _f32p)
 _sig("gpca_hwe_chi_squared_p_value", C.c_double, C.c_uint64, C.c_uint64, C.c_uint64)
 _sig("gpca_set_pca_snps", C.c_int, C.c_void_p, _u64p, C.c_uint64, _f32p, _f32p)
 _sig("gpca_set_pca_snps_mask", C.c_int, C.c_void_p, _u8p, _f32p, _f32p, _u64p)
+_sig("gpca_ingest_bed", C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p,
+     C.c_double, _u8p, _f32p, _f32p, _u8p, _u64p)
 _sig("gpca_get_standardized_block", C.c_int, C.c_void_p, _u64p, C.c_uint64, _u64p, C.c_uint64, _f32p)
 _sig("gpca_sketch_snp_side", C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32)
 _sig("gpca_sketch_sample_side", C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32)
@@ -249,6 +251,44 @@ class Context:
         out = [np.empty(max(m, 1), dtype=np.uint32) for _ in range(4)]
         self._chk(lib.gpca_snp_counts(self._h, *[_ptr(a, _u32p) for a in out]))
         return tuple(a[:m] for a in out)
+
+    def ingest_bed(self, payload, n_samples: int, n_snps: int, qc: QcConfig | None = None, vcf_maf: float = 0.01,
+                   keep_samples=None, want_stats=True, out=None):
+        """Load + filter + build the resident matrices in one streaming pass (gpca_ingest_bed).
+        `payload`: numpy uint8 array (SNP-major .bed payload without the magic) or an integer host address (e.g. a
+        pinned buffer).  `qc` given -> the PLINK QC ladder; otherwise the VCF MAF filter at `vcf_maf`.
+        `out`: optional preallocated (keep u8, mean f32, sd f32[, fail_code u8]) arrays of n_snps elements to fill
+        (returned as they are, keep as uint8) -- saves fresh allocations when the call is repeated.
+        Returns (keep, mean, sd, fail_code | None, n_pca)."""
+        if isinstance(payload, (int, np.integer)):
+            ptr = int(payload)
+        else:
+            payload = np.ascontiguousarray(payload, dtype=np.uint8)
+            ptr = payload.ctypes.data
+        ks = None if keep_samples is None else np.ascontiguousarray(keep_samples, dtype=np.int64)
+        m = int(n_snps)
+        n = C.c_uint64(0)
+        if out is not None:
+            keep, mean, sd = out[0], out[1], out[2]
+            code = out[3] if len(out) > 3 else None
+            assert keep.dtype == np.uint8 and mean.dtype == np.float32 and sd.dtype == np.float32
+            assert keep.size >= m and mean.size >= m and sd.size >= m and (code is None or code.size >= m)
+            self._chk(lib.gpca_ingest_bed(self._h, ptr, n_samples, n_snps, None if ks is None else ks.ctypes.data,
+                                          0 if ks is None else ks.size, None if qc is None else C.addressof(qc),
+                                          float(vcf_maf), _ptr(keep, _u8p), _ptr(mean, _f32p), _ptr(sd, _f32p),
+                                          _ptr(code, _u8p), C.byref(n)))
+            return keep, mean, sd, code, int(n.value)
+        keep = np.empty(max(m, 1), dtype=np.uint8) if want_stats else None
+        mean = np.empty(max(m, 1), dtype=np.float32) if want_stats else None
+        sd = np.empty(max(m, 1), dtype=np.float32) if want_stats else None
+        code = np.empty(max(m, 1), dtype=np.uint8) if (want_stats and qc is not None) else None
+        self._chk(lib.gpca_ingest_bed(self._h, ptr, n_samples, n_snps, None if ks is None else ks.ctypes.data,
+                                      0 if ks is None else ks.size, None if qc is None else C.addressof(qc),
+                                      float(vcf_maf), _ptr(keep, _u8p), _ptr(mean, _f32p), _ptr(sd, _f32p),
+                                      _ptr(code, _u8p), C.byref(n)))
+        if not want_stats:
+            return None, None, None, None, int(n.value)
+        return keep[:m].astype(bool), mean[:m], sd[:m], (None if code is None else code[:m]), int(n.value)
 
     def snp_qc(self, cfg: QcConfig | None = None):
         cfg = cfg or QcConfig()

@@ -1,6 +1,7 @@
 // api.cu -- the C ABI (include/gpca.h): context, ingest, statistics, sketch entry points.
 // The PCA drivers (rfit, EigenSNP) live in drivers.cu.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <atomic>
@@ -62,6 +63,7 @@ extern "C" void gpca_destroy(gpca_ctx* c) {
   }
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->h_cnt) cudaFreeHost(c->h_cnt);
+  if (c->h_up) cudaFreeHost(c->h_up);
   gpca_destroy_cublas(c->cublas);
   delete c;
 }
@@ -400,6 +402,258 @@ extern "C" int gpca_set_pca_snps_mask(gpca_ctx* c, const uint8_t* keep, const fl
     }
   }, 1);
   return build_pca_set(c, D);
+}
+
+// ---- one-call pipelined ingest ------------------------------------------------------------------------------------
+// gpca_load_bed + (gpca_snp_qc | gpca_vcf_maf_filter) + gpca_set_pca_snps_mask as ONE streaming pass: while chunk q
+// crosses PCIe, chunk q-1 is repitched and counted on the device, its 16-byte count records come back, the QC ladder
+// runs on host threads, and the rows that pass are recoded into the resident SNP-major matrix.  The host -> device copy
+// of the payload is the critical path; everything else hides behind it.  Replaces, for the data-preparation stage,
+// MicroarrayDataPreparer::prepare_data_for_eigen_snp_pca (src/prepare.rs:995-1098) / the VCF read + MAF filter
+// (src/vcf.rs:227-266, src/main.rs:176-212).
+extern "C" int gpca_ingest_bed(gpca_ctx* c, const uint8_t* host_payload, uint64_t n_in, uint64_t n_snps,
+                               const int64_t* keep_samples, uint64_t n_keep, const gpca_qc_cfg* cfg,
+                               double vcf_maf_threshold, uint8_t* keep_out, float* mean_out, float* sd_out,
+                               uint8_t* fail_code_out, uint64_t* n_pca_out) {
+  CHECK_CTX(c);
+  const auto t_entry = std::chrono::steady_clock::now();
+  GPCA_CUDA_TRY(c, cudaSetDevice(c->device));
+  if (!host_payload && n_snps) return fail(c, GPCA_ERR_INVALID, "null payload");
+  if (n_in == 0) return fail(c, GPCA_ERR_INVALID, "no samples");
+  const uint64_t N = keep_samples ? n_keep : n_in;
+  if (N == 0) return fail(c, GPCA_ERR_INVALID, "No samples passed QC.");  // prepare.rs:1010
+  if (keep_samples)
+    for (uint64_t i = 0; i < n_keep; ++i)
+      if (keep_samples[i] < 0 || (uint64_t)keep_samples[i] >= n_in || (i && keep_samples[i] <= keep_samples[i - 1]))
+        return fail(c, GPCA_ERR_INVALID, "keep_samples must be increasing indices into the FAM order");
+  if (n_snps == 0) return fail(c, GPCA_ERR_INVALID, "No SNPs passed all QC filters.");
+  c->vcf_mode = false;
+  GPCA_TRY(alloc_raw(c, N, n_snps));
+  const uint64_t M = n_snps;
+  DevBuf<int64_t> d_keep;
+  if (keep_samples) {
+    GPCA_CUDA_TRY(c, d_keep.alloc(n_keep));
+    GPCA_CUDA_TRY(c, cudaMemcpyAsync(d_keep.p, keep_samples, n_keep * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+  }
+  // outputs the caller did not ask for still exist internally
+  std::vector<uint8_t> keep_tmp;
+  std::vector<float> mean_tmp, sd_tmp;
+  if (!keep_out) { keep_tmp.resize(M); keep_out = keep_tmp.data(); }
+  if (!mean_out) { mean_tmp.resize(M); mean_out = mean_tmp.data(); }
+  if (!sd_out) { sd_tmp.resize(M); sd_out = sd_tmp.data(); }
+
+  const size_t in_pitch = (n_in + 3) / 4;
+  uint64_t rows_per_chunk = std::max<uint64_t>(1, (128ull << 20) / std::max<size_t>(in_pitch, 1));
+  if (const char* e = getenv("GPCA_INGEST_CHUNK_ROWS")) rows_per_chunk = std::max<uint64_t>(1, strtoull(e, nullptr, 10));
+  rows_per_chunk = std::min<uint64_t>(rows_per_chunk, M);
+  const uint64_t n_chunks = (M + rows_per_chunk - 1) / rows_per_chunk;
+
+  // device-side destinations (worst case: every SNP passes)
+  GPCA_CUDA_TRY(c, c->d_cnt.alloc(M));
+  GPCA_CUDA_TRY(c, c->d_mean.alloc(M));
+  GPCA_CUDA_TRY(c, c->d_sd.alloc(M));
+  GPCA_CUDA_TRY(c, c->d_inv_sd.alloc(M));
+  GPCA_CUDA_TRY(c, c->d_mu_inv_sd.alloc(M));
+  GPCA_CUDA_TRY(c, c->d_idx.alloc(M));
+  c->Gs.cols = N;
+  c->Gs.pitch = round_up((N + 3) / 4, 128);
+  GPCA_CUDA_TRY(c, c->gs_store.alloc(c->Gs.pitch * M));
+  c->Gs.p = c->gs_store.p;
+  if (c->h_cnt_cap < M) {
+    if (c->h_cnt) cudaFreeHost(c->h_cnt);
+    c->h_cnt = nullptr;
+    c->h_cnt_cap = 0;
+    GPCA_CUDA_TRY(c, cudaMallocHost((void**)&c->h_cnt, M * sizeof(uint4)));
+    c->h_cnt_cap = M;
+  }
+  // pinned staging for the per-chunk compacted vectors: idx (8) + mean, sd, 1/sd, mean/sd (4 x 4) bytes per SNP, x2
+  const size_t up_bytes = rows_per_chunk * 24;
+  if (c->h_up_cap < 2 * up_bytes) {
+    if (c->h_up) cudaFreeHost(c->h_up);
+    c->h_up = nullptr;
+    c->h_up_cap = 0;
+    GPCA_CUDA_TRY(c, cudaMallocHost((void**)&c->h_up, 2 * up_bytes));
+    c->h_up_cap = 2 * up_bytes;
+  }
+  DevBuf<uint8_t>* stage = c->ingest_stage;   // kept across calls (no per-call cudaMalloc / cudaFree)
+  cudaEvent_t stage_free[2] = {nullptr, nullptr}, up_free[2] = {nullptr, nullptr};
+  std::vector<cudaEvent_t> cnt_ready(n_chunks, nullptr);
+  auto cleanup = [&]() {
+    for (int i = 0; i < 2; ++i) {
+      if (stage_free[i]) cudaEventDestroy(stage_free[i]);
+      if (up_free[i]) cudaEventDestroy(up_free[i]);
+    }
+    for (auto e : cnt_ready)
+      if (e) cudaEventDestroy(e);
+  };
+  for (int i = 0; i < 2; ++i) {
+    GPCA_CUDA_TRY(c, stage[i].alloc(rows_per_chunk * in_pitch + 16));
+    cudaEventCreateWithFlags(&stage_free[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&up_free[i], cudaEventDisableTiming);
+  }
+  for (auto& e : cnt_ready) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+
+  c->h_counts.resize(M * 4);
+  c->pca_idx.resize(M);
+  c->h_mean.resize(M);
+  c->h_sd.resize(M);
+  c->h_inv.resize(M);
+  c->h_muinv.resize(M);
+  const uint32_t pad = (uint32_t)(c->raw_pitch * 4 - N);
+  const uint32_t n32 = (uint32_t)N;
+  uint64_t D = 0, nmiss_total = 0;
+  int rc = GPCA_OK;
+
+  const bool trace = getenv("GPCA_TRACE") != nullptr;
+  double t_wait_cnt = 0, t_conv = 0, t_qc = 0, t_compact = 0, t_upload = 0, t_stage_wait = 0, t_enqueue = 0;
+  auto now = []() { return std::chrono::steady_clock::now(); };
+  auto ms_since = [](std::chrono::steady_clock::time_point a) {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count();
+  };
+  const auto t_begin = now();
+  // host half of the pipeline for chunk q (its count records have been requested on the stream already)
+  auto process = [&](uint64_t q) -> int {
+    const uint64_t r0 = q * rows_per_chunk, nr = std::min<uint64_t>(rows_per_chunk, M - r0);
+    auto tp = now();
+    GPCA_CUDA_TRY(c, cudaEventSynchronize(cnt_ready[q]));
+    t_wait_cnt += ms_since(tp); tp = now();
+    uint32_t* hc = c->h_counts.data();
+    const uint4* hp = c->h_cnt;
+    parallel_for(nr, [=](uint64_t lo, uint64_t hi) {
+      for (uint64_t t = lo; t < hi; ++t) {
+        const uint64_t j = r0 + t;
+        const uint32_t miss = hp[j].x - pad, het = hp[j].y, d0 = hp[j].z;
+        const uint32_t nv = n32 - miss;
+        hc[4 * j + 0] = nv;
+        hc[4 * j + 1] = d0;
+        hc[4 * j + 2] = het;
+        hc[4 * j + 3] = nv - d0 - het;
+      }
+    });
+    t_conv += ms_since(tp); tp = now();
+    if (cfg)
+      host_snp_qc(N, nr, hc + 4 * r0, *cfg, keep_out + r0, mean_out + r0, sd_out + r0,
+                  fail_code_out ? fail_code_out + r0 : nullptr);
+    else
+      host_vcf_maf(N, nr, hc + 4 * r0, vcf_maf_threshold, keep_out + r0, mean_out + r0, sd_out + r0);
+    t_qc += ms_since(tp); tp = now();
+    // compaction of the chunk (serial: a few hundred thousand SNPs) straight into the pinned upload buffer
+    const int ub = (int)(q & 1);
+    GPCA_CUDA_TRY(c, cudaEventSynchronize(up_free[ub]));
+    uint8_t* ubase = c->h_up + (size_t)ub * up_bytes;
+    uint64_t* u_idx = reinterpret_cast<uint64_t*>(ubase);
+    float* u_mean = reinterpret_cast<float*>(ubase + rows_per_chunk * 8);
+    float* u_sd = u_mean + rows_per_chunk;
+    float* u_inv = u_sd + rows_per_chunk;
+    float* u_mu = u_inv + rows_per_chunk;
+    uint64_t kept = 0;
+    for (uint64_t t = 0; t < nr; ++t) {
+      const uint64_t j = r0 + t;
+      if (!keep_out[j]) continue;
+      const float m = mean_out[j], sdv = sd_out[j];
+      float inv = 0.f, mu = 0.f;
+      if (!(std::fabs(sdv) < 1e-9f)) {   // same f32 expressions as prepare.rs:1948-1949
+        inv = 1.0f / sdv;
+        mu = m * inv;
+      }
+      u_idx[kept] = j; u_mean[kept] = m; u_sd[kept] = sdv; u_inv[kept] = inv; u_mu[kept] = mu;
+      c->pca_idx[D + kept] = j; c->h_mean[D + kept] = m; c->h_sd[D + kept] = sdv;
+      c->h_inv[D + kept] = inv; c->h_muinv[D + kept] = mu;
+      nmiss_total += N - hc[4 * j];
+      ++kept;
+    }
+    t_compact += ms_since(tp); tp = now();
+    if (kept) {
+      auto up = [&](void* dst, const void* src, size_t bytes) {
+        return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream);
+      };
+      GPCA_CUDA_TRY(c, up(c->d_idx.p + D, u_idx, kept * 8));
+      GPCA_CUDA_TRY(c, up(c->d_mean.p + D, u_mean, kept * 4));
+      GPCA_CUDA_TRY(c, up(c->d_sd.p + D, u_sd, kept * 4));
+      GPCA_CUDA_TRY(c, up(c->d_inv_sd.p + D, u_inv, kept * 4));
+      GPCA_CUDA_TRY(c, up(c->d_mu_inv_sd.p + D, u_mu, kept * 4));
+      PackedMat view = c->Gs;
+      view.p = c->Gs.p + D * c->Gs.pitch;
+      view.rows = kept;
+      GPCA_TRY(launch_build_gs(c, c->raw.p, c->raw_pitch, c->d_idx.p + D, view));
+    }
+    GPCA_CUDA_TRY(c, cudaEventRecord(up_free[ub], c->stream));
+    t_upload += ms_since(tp);
+    D += kept;
+    return GPCA_OK;
+  };
+
+  for (uint64_t q = 0; q < n_chunks && rc == GPCA_OK; ++q) {
+    const int buf = (int)(q & 1);
+    const uint64_t r0 = q * rows_per_chunk, nr = std::min<uint64_t>(rows_per_chunk, M - r0);
+    auto tq = now();
+    cudaError_t e = cudaEventSynchronize(stage_free[buf]);
+    t_stage_wait += ms_since(tq); tq = now();
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(stage[buf].p, host_payload + r0 * in_pitch, nr * in_pitch, cudaMemcpyHostToDevice, c->stream);
+    if (e != cudaSuccess) {
+      rc = fail(c, GPCA_ERR_CUDA, std::string("ingest H2D: ") + cudaGetErrorString(e));
+      break;
+    }
+    rc = launch_repitch_gather(c, stage[buf].p, in_pitch, n_in, keep_samples ? d_keep.p : nullptr, N, nr,
+                               c->raw.p + r0 * c->raw_pitch, c->raw_pitch);
+    cudaEventRecord(stage_free[buf], c->stream);
+    if (rc == GPCA_OK) rc = launch_bed_counts(c, c->raw.p + r0 * c->raw_pitch, c->raw_pitch, nr, c->d_cnt.p + r0);
+    if (rc == GPCA_OK &&
+        cudaMemcpyAsync(c->h_cnt + r0, c->d_cnt.p + r0, nr * sizeof(uint4), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess)
+      rc = fail(c, GPCA_ERR_CUDA, "ingest: count read-back failed");
+    cudaEventRecord(cnt_ready[q], c->stream);
+    t_enqueue += ms_since(tq);
+    if (rc == GPCA_OK && q > 0) rc = process(q - 1);      // overlaps with chunk q's transfer
+  }
+  if (rc == GPCA_OK) rc = process(n_chunks - 1);
+  if (rc != GPCA_OK) {
+    cudaStreamSynchronize(c->stream);
+    cleanup();
+    reset_loaded(c);
+    return rc;
+  }
+  c->have_counts = true;
+  if (n_pca_out) *n_pca_out = D;
+  if (D == 0) {
+    cudaStreamSynchronize(c->stream);
+    cleanup();
+    return fail(c, GPCA_ERR_INVALID, "No SNPs passed all QC filters.");  // prepare.rs:1020
+  }
+  c->pca_idx.resize(D);
+  c->h_mean.resize(D);
+  c->h_sd.resize(D);
+  c->h_inv.resize(D);
+  c->h_muinv.resize(D);
+  c->any_missing = nmiss_total > 0;
+  c->D = D;
+  c->Gs.rows = D;
+  c->Gt.rows = N;
+  c->Gt.cols = D;
+  c->Gt.pitch = round_up((D + 3) / 4, 128);
+  size_t free_b = 0, total_b = 0;
+  cudaMemGetInfo(&free_b, &total_b);
+  if (c->gt_store.n < c->Gt.pitch * N && free_b < c->Gt.pitch * N + (8ull << 30)) {
+    cudaStreamSynchronize(c->stream);
+    c->raw.release();
+  }
+  cudaError_t ea = c->gt_store.alloc(c->Gt.pitch * N);
+  if (ea != cudaSuccess) {
+    cleanup();
+    return fail(c, GPCA_ERR_OOM, std::string("ingest: ") + cudaGetErrorString(ea));
+  }
+  c->Gt.p = c->gt_store.p;
+  const double t_loop = ms_since(t_begin);
+  rc = launch_transpose(c, c->Gs, c->Gt);
+  cudaStreamSynchronize(c->stream);
+  cleanup();
+  if (trace)
+    fprintf(stderr,
+            "[gpca_ingest_bed] chunks %llu  loop %.1f ms  total %.1f ms | stage wait %.1f  enqueue %.1f  count wait %.1f  "
+            "convert %.1f  qc %.1f  compact %.1f  upload+build %.1f  (since entry %.1f)\n",
+            (unsigned long long)n_chunks, t_loop, ms_since(t_begin), t_stage_wait, t_enqueue, t_wait_cnt, t_conv, t_qc,
+            t_compact, t_upload, ms_since(t_entry));
+  return rc;
 }
 
 // ---- accessor parity ---------------------------------------------------------------------------

@@ -125,10 +125,17 @@ extern "C" int gpca_rfit(gpca_ctx* c, uint32_t k, uint32_t oversample, uint32_t 
   GPCA_TRY(driver_allreduce(c, s.G, (uint64_t)l * l, 1));
   GPCA_TRY(launch_jacobi_eigh(c, s.G, l, s.evals, s.evecs));
   GPCA_TRY(launch_rotation_transform(c, s.evals, s.evecs, l, k, s.T, true));
-  GPCA_CUDA_TRY(c, R.alloc(D * k));
   GPCA_CUDA_TRY(c, Sc.alloc(N * k));
-  GPCA_TRY(launch_apply_right(c, Z.p, D, l, l, s.T, k, R.p, k));  // rotation = B V_b / s  [D x k]
-  GPCA_TRY(sketch_sample_side(c, R.p, Sc.p, k, k, k));            // transform(): scores = S^T rotation
+  if (loadings) {
+    GPCA_CUDA_TRY(c, R.alloc(D * k));
+    GPCA_TRY(launch_apply_right(c, Z.p, D, l, l, s.T, k, R.p, k));  // rotation = B V_b / s  [D x k]
+    GPCA_TRY(sketch_sample_side(c, R.p, Sc.p, k, k, k));            // transform(): scores = S^T rotation
+  } else {
+    // the rotation itself is not wanted: scores = S^T (B T) = (S^T B) T, which moves the multiplication by T from the
+    // D x l operand to the N x l result
+    GPCA_TRY(sketch_sample_side(c, Z.p, Y.p, l, l, l));
+    GPCA_TRY(launch_apply_right(c, Y.p, N, l, l, s.T, k, Sc.p, k));
+  }
 
   // sign convention, f32 -> f64 conversion and the flips of the loadings all happen on the device;
   // the host only receives the final buffers

@@ -119,6 +119,14 @@ int gpca_set_pca_snps(gpca_ctx* ctx, const uint64_t* snp_idx, uint64_t n_pca_snp
  * gpca_snp_qc / gpca_vcf_maf_filter filled (saves the host a gather over millions of SNPs). */
 int gpca_set_pca_snps_mask(gpca_ctx* ctx, const uint8_t* keep, const float* mean_all, const float* sd_all,
                            uint64_t* n_pca_out);
+/* One streaming pass that is equivalent to gpca_load_bed + gpca_snp_qc (cfg != NULL) or gpca_vcf_maf_filter
+ * (cfg == NULL, threshold = vcf_maf_threshold) + gpca_set_pca_snps_mask: while later chunks of the payload are still
+ * crossing PCIe, earlier chunks are counted on the device, filtered on host threads and recoded into the resident
+ * matrix.  keep / mean / sd / fail_code (n_snps each) may be NULL.  Stands in for the whole data-preparation stage
+ * (src/prepare.rs:995-1098 for .bed input; src/vcf.rs:227-266 + src/main.rs:176-212 for the VCF flow). */
+int gpca_ingest_bed(gpca_ctx* ctx, const uint8_t* host_payload, uint64_t n_in_samples, uint64_t n_snps,
+                    const int64_t* keep_samples, uint64_t n_keep, const gpca_qc_cfg* cfg, double vcf_maf_threshold,
+                    uint8_t* keep, float* mean, float* sd, uint8_t* fail_code, uint64_t* n_pca_out);
 
 /* ---- the accessor the GPU path makes unnecessary, kept for parity ---------------------- */
 /* get_standardized_snp_sample_block (src/prepare.rs:1839-2022): out[n_ids x n_samp] row-major

@@ -113,3 +113,58 @@ def test_set_pca_snps_mask_equals_index_form(gpu_ctx):
     assert n == idx.size == gpu_ctx.num_pca_snps
     z2 = gpu_ctx.get_standardized_snp_sample_block(ids)
     assert np.array_equal(z1, z2)
+
+
+@pytest.mark.parametrize("chunk_rows", [None, 97])
+@pytest.mark.parametrize("mode", ["qc", "vcf_maf"])
+def test_pipelined_ingest_equals_three_call_path(gpu_ctx, monkeypatch, mode, chunk_rows):
+    """gpca_ingest_bed (one streaming pass, chunked) against gpca_load_bed + QC/MAF filter + gpca_set_pca_snps_mask:
+    identical masks, f32 statistics and fail codes, identical counts, identical standardized blocks and rfit."""
+    import genomic_pca_b200 as gp
+    if chunk_rows:
+        monkeypatch.setenv("GPCA_INGEST_CHUNK_ROWS", str(chunk_rows))      # 1000 SNPs -> 11 chunks, last one short
+    n_in, m = 403, 1000
+    g, payload = make_dataset(n_in, m, n_pops=4, seed=77, missing_rate=0.01 if mode == "qc" else 0.0)
+    keep_samples = np.setdiff1d(np.arange(n_in), [3, 77, 401]).astype(np.int64)
+    cfg = gp.QcConfig(0.95, 0.02, 1e-6)
+    # reference path: three calls
+    gpu_ctx.load_bed(payload, n_in, m, keep_samples)
+    if mode == "qc":
+        keep0, mean0, sd0, code0 = gpu_ctx.snp_qc(cfg)
+    else:
+        keep0, mean0, sd0 = gpu_ctx.vcf_maf_filter(0.02)
+        code0 = None
+    d0 = gpu_ctx.set_pca_snps_mask(keep0, mean0, sd0)
+    counts0 = gpu_ctx.snp_counts()
+    ids = np.arange(0, d0, 7)
+    blk0 = gpu_ctx.get_standardized_snp_sample_block(ids) if mode == "vcf_maf" else None
+    r0 = gpu_ctx.rfit(3, 5, 2, seed=11)
+    # pipelined path on a fresh context
+    ctx2 = gp.Context(0)
+    keep1, mean1, sd1, code1, d1 = ctx2.ingest_bed(payload, n_in, m, qc=cfg if mode == "qc" else None, vcf_maf=0.02,
+                                                    keep_samples=keep_samples)
+    assert d1 == d0 and np.array_equal(keep1, keep0)
+    assert np.array_equal(mean1, mean0) and np.array_equal(sd1, sd0)
+    if mode == "qc":
+        assert np.array_equal(code1, code0)
+    assert ctx2.num_samples == keep_samples.size and ctx2.num_pca_snps == d0
+    counts1 = ctx2.snp_counts()
+    assert all(np.array_equal(a, b) for a, b in zip(counts0, counts1))
+    if blk0 is not None:
+        assert np.array_equal(ctx2.get_standardized_snp_sample_block(ids), blk0)
+    r1 = ctx2.rfit(3, 5, 2, seed=11)
+    assert np.array_equal(r1[1], r0[1]) and np.array_equal(r1[0], r0[0]) and np.array_equal(r1[2], r0[2])
+    # stats not requested
+    ctx3 = gp.Context(0)
+    out = ctx3.ingest_bed(payload, n_in, m, qc=cfg if mode == "qc" else None, vcf_maf=0.02, keep_samples=keep_samples,
+                          want_stats=False)
+    assert out[-1] == d0
+
+
+def test_pipelined_ingest_errors(gpu_ctx):
+    import genomic_pca_b200 as gp
+    g, payload = make_dataset(50, 40, seed=1)
+    with pytest.raises(gp.GpcaError):
+        gpu_ctx.ingest_bed(payload, 50, 40, vcf_maf=0.6)          # nothing can pass: maf <= 0.5
+    with pytest.raises(gp.GpcaError):
+        gpu_ctx.ingest_bed(payload, 50, 40, keep_samples=np.array([5, 2], dtype=np.int64))

@@ -43,6 +43,11 @@ def test_rfit_matches_oracle_and_exact(gpu_ctx, engine, n, m, pops, k):
     assert pca.subspace_angle(sc, sc_x) < 3e-3     # limited by the randomized method itself (oracle shows the same)
     # sign convention + column-wise agreement with the oracle
     assert np.abs(sc - sc_o).max() / np.abs(sc_o).max() < 5e-3
+    # scores-only call: the rotation is never formed (scores = (S^T B) T), same result
+    sc2, ev2, none = gpu_ctx.rfit(k, 10, power_iters=3, seed=42, want_loadings=False)
+    assert none is None and np.array_equal(ev2, ev)
+    assert pca.subspace_angle(sc2, sc_o) < ANGLE_TOL
+    assert np.abs(sc2 - sc).max() / np.abs(sc).max() < 2e-3
 
 
 def test_rfit_reference_argument_rules(gpu_ctx):

@@ -20,3 +20,17 @@ for rep in range(2):
     ctx.rfit(20, 10, power_iters=2, seed=42, want_loadings=False); t.append(time.perf_counter())
     names = ["load_bed(H2D+repitch)", "vcf_maf_filter(counts+host)", "numpy select", "set_pca_snps", "rfit"]
     print(rep, {k: round((b - a) * 1e3, 1) for k, a, b in zip(names, t[:-1], t[1:])}, "total", round((t[-1] - t[0]) * 1e3, 1))
+for rep in range(3):
+    t0 = time.perf_counter()
+    import ctypes as C
+    from genomic_pca_b200 import binding as B
+    keep = np.empty(m, dtype=np.uint8); mean = np.empty(m, dtype=np.float32); sd = np.empty(m, dtype=np.float32)
+    nn = C.c_uint64(0)
+    ta = time.perf_counter()
+    rc = B.lib.gpca_ingest_bed(ctx._h, host.data_ptr(), n, m, None, 0, None, 0.01, B._ptr(keep, B._u8p), B._ptr(mean, B._f32p), B._ptr(sd, B._f32p), None, C.byref(nn))
+    tb = time.perf_counter()
+    print("   raw C call ms", round((tb - ta) * 1e3, 1), "rc", rc)
+    t1 = time.perf_counter()
+    ctx.rfit(20, 10, power_iters=2, seed=42, want_loadings=False)
+    t2 = time.perf_counter()
+    print("pipelined", rep, {"ingest_bed": round((t1 - t0) * 1e3, 1), "rfit": round((t2 - t1) * 1e3, 1)}, "total", round((t2 - t0) * 1e3, 1))
