@@ -114,6 +114,11 @@ static void reset_loaded(gpca_ctx* c) {
   c->Gs = PackedMat();
   c->Gt = PackedMat();   // (the stores are kept: DevBuf::alloc reuses them when the next data set fits)
   c->any_missing = false;
+  c->es_store.release();
+  c->et_store.release();
+  c->ets_store.release();
+  c->ess_store.release();
+  c->es_cn.release();
 }
 
 // ---- ingest ------------------------------------------------------------------------------

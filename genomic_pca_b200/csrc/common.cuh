@@ -91,6 +91,8 @@ struct gpca_ctx {
   DevBuf<uint4> d_cnt;
   uint4* h_cnt = nullptr;      // pinned landing buffer for the count records
   uint64_t h_cnt_cap = 0;
+  DevBuf<uint8_t> es_store, et_store, ets_store, ess_store;   // EigenSNP slot-ordered / subset copies (kept across calls)
+  DevBuf<float> es_cn;                                        // EigenSNP condensed features
   DevBuf<uint8_t> ingest_stage[2];   // device staging of the raw payload chunks (gpca_ingest_bed)
   uint8_t* h_up = nullptr;     // pinned staging for the per-chunk compacted vectors (gpca_ingest_bed)
   size_t h_up_cap = 0;

@@ -228,7 +228,9 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
                                       (uint32_t)(seed >> 32));
       keys[i] = {r.x, i};
     }
-    std::sort(keys.begin(), keys.end());       // by key, ties by index (stable order of the oracle)
+    // the N_s smallest (key, index) pairs -- ties by index, the oracle's stable order; a selection is enough because
+    // the subset is then put in index order
+    std::nth_element(keys.begin(), keys.begin() + Ns, keys.end());
     for (uint64_t i = 0; i < Ns; ++i) sub[i] = (int64_t)keys[i].second;
     std::sort(sub.begin(), sub.end());
   }
@@ -254,7 +256,9 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
   GPCA_CUDA_TRY(c, cudaMemcpyAsync(d_slot.p, id_of_slot.data(), Ds * 8, cudaMemcpyHostToDevice, c->stream));
   GPCA_CUDA_TRY(c, cudaMemcpyAsync(d_sub.p, sub.data(), Ns * 8, cudaMemcpyHostToDevice, c->stream));
 
-  DevBuf<uint8_t> es_store, et_store, ets_store, ess_store;
+  // the slot-ordered copies are kept in the context between calls (allocating and freeing tens of GB per call costs
+  // more than every kernel of a call together); gpca_load_* / gpca_ingest_bed release them
+  DevBuf<uint8_t>&es_store = c->es_store, &et_store = c->et_store, &ets_store = c->ets_store, &ess_store = c->ess_store;
   PackedMat Es, Et, Ets, Ess;
   Es.rows = Ds; Es.cols = N; Es.pitch = c->Gs.pitch;
   Et.rows = N; Et.cols = Ds; Et.pitch = round_up((Ds + 3) / 4, 128);
@@ -485,7 +489,7 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
   stage("local bases");
   // ---- 3. condensed features (all N samples), Cn [N x R], then column standardisation -----------------------
   if (R == 0) return fail(c, GPCA_ERR_INVALID, "no condensed features");
-  DevBuf<float> Cn;
+  DevBuf<float>& Cn = c->es_cn;
   GPCA_CUDA_TRY(c, Cn.alloc(N * R));
   if (batched) {
     if (rgN * n_blocks > 0x7fffffffull) return fail(c, GPCA_ERR_INVALID, "too many condensed-feature work items");

@@ -258,50 +258,57 @@ int launch_build_gs(gpca_ctx* c, const uint8_t* d_raw, size_t raw_pitch, const u
 }
 
 // ------------------------------------------------------------------------------------------
-// 2-bit transpose.  A CTA moves a tile of 128 source rows x 64 source fields through shared
-// memory (one byte per field) and writes, for each of the 64 destination rows, 128 fields = 32 B.
+// 2-bit transpose.  A CTA moves a tile of 512 source rows x 512 source fields: every thread transposes 16 x 16 blocks
+// of 2-bit fields in registers (16 words in, 16 words out, four masked block-swap rounds), the 16 output words go to
+// their destination rows in shared memory (XOR-swizzled columns: conflict-free both ways), and each destination row
+// leaves as one 128-byte segment.  Reads are 128-byte segments per source row as well.  Every byte of the destination
+// rows is written (pitches are multiples of 128 B), so no memset is needed.
+__device__ __forceinline__ void transpose16x16_2bit(uint32_t (&x)[16]) {
+#pragma unroll
+  for (int s = 8; s >= 1; s >>= 1) {
+    const uint32_t mask = (s == 8) ? 0x0000FFFFu : (s == 4) ? 0x00FF00FFu : (s == 2) ? 0x0F0F0F0Fu : 0x33333333u;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      if (i & s) continue;
+      const uint32_t t = ((x[i] >> (2 * s)) ^ x[i + s]) & mask;   // upper-right block of row i <-> lower-left of row i+s
+      x[i + s] ^= t;
+      x[i] ^= t << (2 * s);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) transpose2bit_kernel(const uint8_t* __restrict__ src, size_t src_pitch,
                                                             uint64_t src_rows, uint64_t src_cols,
                                                             uint8_t* __restrict__ dst, size_t dst_pitch) {
-  __shared__ uint32_t tile[128][17];  // 64 bytes per row (+1 word pad)
-  const uint64_t tiles_c = (src_cols + 63) / 64;
-  const uint64_t tiles_r = (src_rows + 127) / 128;
+  extern __shared__ uint32_t tile[];   // [512 destination rows][32 words]
+  const uint64_t tiles_c = (src_cols + 511) / 512;
+  const uint64_t tiles_r = (src_rows + 511) / 512;
   const uint64_t ntiles = tiles_c * tiles_r;
   for (uint64_t tix = blockIdx.x; tix < ntiles; tix += gridDim.x) {
-    const uint64_t tr = tix / tiles_c, tc = tix - tr * tiles_c;
-    const uint64_t r0 = tr * 128, c0 = tc * 64;
-    // phase 1: 128 threads each load 16 B (64 fields) of one source row and spread to bytes
-    if (threadIdx.x < 128) {
-      const uint64_t r = r0 + threadIdx.x;
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (r < src_rows) v = ldg_nc_v4(src + r * src_pitch + c0 / 4);
-      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint32_t b = (w[j] >> (8 * q)) & 0xffu;  // 4 fields
-          tile[threadIdx.x][j * 4 + q] = (b & 3u) | ((b & 0xcu) << 6) | ((b & 0x30u) << 12) | ((b & 0xc0u) << 18);
-        }
-      }
-    }
-    __syncthreads();
-    // phase 2: thread -> (dest row n = tid%64, quarter q = tid/64 of 32 source rows) -> 8 bytes
-    {
-      const int n = threadIdx.x & 63;
-      const int q = threadIdx.x >> 6;
-      const uint8_t* tb = reinterpret_cast<const uint8_t*>(&tile[0][0]);
-      uint32_t lo = 0, hi = 0;
+    const uint64_t tc = tix / tiles_r, tr = tix - tc * tiles_r;   // consecutive CTAs write neighbouring 128-B segments
+    const uint64_t r0 = tr * 512, c0 = tc * 512;
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+      const int b = threadIdx.x + 256 * j;
+      const int cw = b & 31, rb = b >> 5;        // source word column (16 fields), source row block (16 rows)
+      uint32_t x[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        lo |= (uint32_t)tb[(32 * q + i) * 68 + n] << (2 * i);
-        hi |= (uint32_t)tb[(32 * q + 16 + i) * 68 + n] << (2 * i);
+        const uint64_t r = r0 + 16 * rb + i;
+        x[i] = (r < src_rows) ? __ldg(reinterpret_cast<const uint32_t*>(src + r * src_pitch + c0 / 4) + cw) : 0u;
       }
-      const uint64_t dn = c0 + n;
-      if (dn < src_cols) {
-        uint2* o = reinterpret_cast<uint2*>(dst + dn * dst_pitch + r0 / 4 + 8 * q);
-        *o = make_uint2(lo, hi);
-      }
+      transpose16x16_2bit(x);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) tile[(16 * cw + i) * 32 + (rb ^ cw)] = x[i];
+    }
+    __syncthreads();
+    // destination row dr (= source column c0 + dr): 32 words, word j holds source rows r0 + 16 j .. + 15
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int dr = warp; dr < 512; dr += 8) {
+      const uint64_t dn = c0 + dr;
+      if (dn >= src_cols) break;
+      const uint32_t v = tile[dr * 32 + (lane ^ ((dr >> 4) & 31))];
+      reinterpret_cast<uint32_t*>(dst + dn * dst_pitch + r0 / 4)[lane] = v;
     }
     __syncthreads();
   }
@@ -309,12 +316,17 @@ __global__ void __launch_bounds__(256) transpose2bit_kernel(const uint8_t* __res
 
 int launch_transpose(gpca_ctx* c, PackedMat gs, PackedMat gt) {
   if (gs.rows == 0 || gs.cols == 0) return GPCA_OK;
-  // dst pitch must cover round_up(src_rows,128)/4 bytes (true: pitch is a multiple of 128 B = 512 fields)
-  const uint64_t ntiles = ((gs.cols + 63) / 64) * ((gs.rows + 127) / 128);
-  const int grid = (int)(ntiles < (uint64_t)c->sm_count * 8 ? ntiles : (uint64_t)c->sm_count * 8);
-  // zero the destination first so that pad fields beyond src_rows are 0
-  GPCA_CUDA_TRY(c, cudaMemsetAsync(gt.p, 0, gt.pitch * gt.rows, c->stream));
-  transpose2bit_kernel<<<grid, 256, 0, c->stream>>>(gs.p, gs.pitch, gs.rows, gs.cols, gt.p, gt.pitch);
+  // the source pitch covers whole 128-byte column tiles and the destination pitch covers round_up(src_rows, 512) / 4
+  // bytes: both hold because every pitch is a multiple of 128 B
+  if (gs.pitch % 128 != 0 || gt.pitch % 128 != 0 || gt.pitch * 4 < gs.rows) {
+    c->set_error("transpose: pitches must be multiples of 128 bytes");
+    return GPCA_ERR_INVALID;
+  }
+  const uint64_t ntiles = ((gs.cols + 511) / 512) * ((gs.rows + 511) / 512);
+  const int grid = (int)(ntiles < (uint64_t)c->sm_count * 3 ? ntiles : (uint64_t)c->sm_count * 3);
+  const int smem = 512 * 32 * 4;
+  GPCA_CUDA_TRY(c, cudaFuncSetAttribute(transpose2bit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  transpose2bit_kernel<<<grid, 256, smem, c->stream>>>(gs.p, gs.pitch, gs.rows, gs.cols, gt.p, gt.pitch);
   KLAUNCH_CHECK(c);
   return GPCA_OK;
 }

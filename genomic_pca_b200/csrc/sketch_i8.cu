@@ -24,22 +24,29 @@ using namespace tcptx;
 constexpr int RT = 2;              // row tiles of 128 rows per CTA
 constexpr int STAGE_FIELDS = 256;  // 64 B per row per stage
 constexpr int CHUNKS = 4;          // 64-field chunks per stage
-constexpr int A_ROW_BYTES = 128;   // bytes of a packed row per A stage = TMA box width: two 256-field stages.
-                                   // (64-byte boxes cap the TMA stream at ~2.6 TB/s when the row pitch is MBs --
-                                   //  one DRAM page per 64 B; 128-byte boxes reach ~5.1 TB/s, tools/probe/tma_bw_probe.cu)
-constexpr int HALVES = A_ROW_BYTES / 64;   // 256-field stages per A stage
-constexpr int A_TILE_BYTES = 128 * A_ROW_BYTES;
+// Bytes of a packed row per A stage = TMA box width.  Regular passes use 128 (two 256-field stages per A stage): 64-byte
+// boxes cap the TMA stream at ~2.6 TB/s when the row pitch is MBs -- one DRAM page per 64 B -- while 128-byte boxes
+// reach ~5.1 TB/s (tools/probe/tma_bw_probe.cu).  Item mode (batched LD blocks: one or two stages per item, bound by
+// the latency of an item rather than by bandwidth) keeps 64-byte boxes so that four stages can be in flight.
+template <bool ITEMS>
+struct ACfg {
+  static constexpr int ROW_BYTES = ITEMS ? 64 : 128;
+  static constexpr int HALVES = ROW_BYTES / 64;          // 256-field stages per A stage
+  static constexpr int TILE_BYTES = 128 * ROW_BYTES;
+  static constexpr int STAGE_BYTES = 2 * TILE_BYTES;     // RT tiles
+  static constexpr int SA = 65536 / STAGE_BYTES;         // 64 KB of A stages either way
+};
 constexpr int NUM_THREADS = 384;   // 12 warps: a multiple of 4, so that warp & 3 is the TMEM lane quarter of the warp for every co-resident CTA (warp 11 idles)
 constexpr int NL = 32;             // logical columns
 constexpr int NM = 64;             // MMA N = hi | lo limbs
-constexpr int SA = 2, SB = 3, SLOTS = 2;   // a TMEM slot holds a chunk pair (128 fields) of both row tiles
-constexpr int A_STAGE_BYTES = RT * A_TILE_BYTES;
+constexpr int SB = 3, SLOTS = 2;   // a TMEM slot holds a chunk pair (128 fields) of both row tiles
+constexpr int A_RING_BYTES = 65536;
 constexpr int B_STAGE_BYTES = STAGE_FIELDS * NM;       // 1 byte per element
 constexpr int TMEM_COLS = 256;
 constexpr int D_COL0 = 0;                              // RT * 64 accumulator columns
 constexpr int A_COL0 = RT * NM;                        // SLOTS * RT * 32 columns
 static_assert(RT * NM + SLOTS * RT * 32 <= TMEM_COLS, "TMEM budget");
-constexpr int SMEM_BYTES = SA * A_STAGE_BYTES + SB * B_STAGE_BYTES + 256 + 320;
+constexpr int SMEM_BYTES = A_RING_BYTES + SB * B_STAGE_BYTES + 256 + 320;
 constexpr uint32_t MAX_STAGES_PER_ITEM = 20000;        // 3 * 128 * 256 * 20000 < 2^31: no int32 overflow
 
 // 16 fields of a word -> 4 registers of 4 x u8 (register j holds fields j, j+4, j+8, j+12)
@@ -122,7 +129,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) sketch_i8_kernel(const __grid_
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);
   const uint32_t a_ring = smem_base;
-  const uint32_t b_ring = smem_base + SA * A_STAGE_BYTES;
+  constexpr int A_ROW_BYTES = ACfg<ITEMS>::ROW_BYTES, HALVES = ACfg<ITEMS>::HALVES, A_TILE_BYTES = ACfg<ITEMS>::TILE_BYTES,
+                A_STAGE_BYTES = ACfg<ITEMS>::STAGE_BYTES, SA = ACfg<ITEMS>::SA;
+  static_assert(RT == 2 && SA * A_STAGE_BYTES == A_RING_BYTES && SA <= 4, "A ring layout");
+  const uint32_t b_ring = smem_base + A_RING_BYTES;
   const uint32_t bars = b_ring + SB * B_STAGE_BYTES;
   auto bar_afull = [&](int s) { return bars + 8u * s; };
   auto bar_aempty = [&](int s) { return bars + 8u * (4 + s); };
@@ -264,7 +274,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) sketch_i8_kernel(const __grid_
     const int quarter = warp & 3;
     const int row_in_tile = quarter * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-    const uint32_t sw = (uint32_t)(row_in_tile & 7);   // SWIZZLE_128B: 16-byte chunk c of row r sits at chunk c ^ (r & 7)
+    // 16-byte chunk c of row r sits at chunk c ^ (r & 7) under SWIZZLE_128B (128-byte rows) and at c ^ ((r >> 1) & 3)
+    // under SWIZZLE_64B (64-byte rows)
+    const uint32_t sw = (A_ROW_BYTES == 128) ? (uint32_t)(row_in_tile & 7) : (uint32_t)((row_in_tile >> 1) & 3);
     uint32_t it = 0, cit = 0, item_idx = 0;
     for (uint32_t item = blockIdx.x; item < p.n_items; item += gridDim.x, ++item_idx) {
       const ItemInfo ii = decode_item<ITEMS>(p, item);
@@ -722,7 +734,7 @@ int launch_sketch_i8(gpca_ctx* c, const SketchProblem& p) {
     EncodeTiledFn enc = get_encode_fn_i8();
     const cuuint64_t dims[2] = {(cuuint64_t)(p.G.avail ? p.G.avail : p.G.pitch), (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)p.G.pitch};
-    const cuuint32_t box[2] = {A_ROW_BYTES, 128};
+    const cuuint32_t box[2] = {ACfg<false>::ROW_BYTES, 128};
     const cuuint32_t estr[2] = {1, 1};
     if (!enc || enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)p.G.p, dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, l2_promotion(),
@@ -823,10 +835,10 @@ int launch_sketch_i8_batch(gpca_ctx* c, const SketchBatch& sb) {
     EncodeTiledFn enc = get_encode_fn_i8();
     const cuuint64_t dims[2] = {(cuuint64_t)(sb.G.avail ? sb.G.avail : sb.G.pitch), (cuuint64_t)sb.G.rows};
     const cuuint64_t strides[1] = {(cuuint64_t)sb.G.pitch};
-    const cuuint32_t box[2] = {A_ROW_BYTES, 128};
+    const cuuint32_t box[2] = {ACfg<true>::ROW_BYTES, 128};
     const cuuint32_t estr[2] = {1, 1};
     if (!enc || enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)sb.G.p, dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, l2_promotion(),
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, l2_promotion(),
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
       c->set_error("sketch_i8_batch: cuTensorMapEncodeTiled failed");
       return GPCA_ERR_CUDA;
