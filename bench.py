@@ -313,7 +313,7 @@ def run_ours(args, rank, world):
     ach_tf = flops_per_pass / t_kern / 1e12 if t_kern > 0 else 0.0
     eng = ctx_engine(ctx, args)
     roofline = {"bound": "hbm", "achieved": ach_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": ach_gbs / pk["hbm_gbs"], "traffic": TRAFFIC_NCU.get(eng), "peak_source": pk_src,
+                "frac": ach_gbs / pk["hbm_gbs"], "traffic": TRAFFIC_NCU.get(eng) if (n, m) == (2504, 10_000_000) else None, "peak_source": pk_src,
                 "kernel": {0: "sketch_simt_kernel", 1: "sketch_tc_kernel", 2: "sketch_i8_kernel"}[eng],
                 "ms_per_launch": t_kern * 1e3, "launches_per_step": passes,
                 "kernel_share_of_step": (sk_kernel_ms * 1e-3 / args.steps) / t_step,
@@ -351,9 +351,10 @@ def run_ours(args, rank, world):
         dist.destroy_process_group()
 
 
-# DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum, GB per launch, averaged over the sample-side and
-# snp-side launches of one rfit) from the committed ncu capture of the same workload: profiles/README.md
-TRAFFIC_NCU = {2: 8.16e9}
+# DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum, bytes per launch) of sketch_i8_kernel at config 3 from the
+# committed ncu capture (profiles/r1_ncu_full_sketch_i8_kernel_c3_final.csv): sample side 7.28 + 0.04 GB, snp side
+# 6.50 + 1.20 GB; one rfit runs 4 sample-side and 3 snp-side launches.  Only valid for the default workload.
+TRAFFIC_NCU = {2: (4 * 7.326e9 + 3 * 7.704e9) / 7}
 
 
 def ukb_shard_supplement(torch, gp, dev, pk):

@@ -69,7 +69,6 @@ struct I8Params {
   uint32_t ldo, l;
   float* partial;       // [ksplit][rows][32]
   const I8Item* items;  // item mode (batched per-LD-block passes): explicit work list, no split-K partials
-  uint32_t dbg_reverse;
 };
 
 // What one work item covers.  Regular mode derives it from (k-split, row group); item mode reads it from the table.
@@ -101,10 +100,6 @@ __device__ __forceinline__ ItemInfo decode_item(const I8Params& p, uint32_t item
     ii.out_off = (uint64_t)i1.z | ((uint64_t)i1.w << 32);
     ii.ks = 0;
   } else {
-    if (p.dbg_reverse && blockIdx.x >= gridDim.x / 2) {   // DEBUG: upper-half CTAs walk their own items backwards
-      const uint32_t last = blockIdx.x + ((p.n_items - 1 - blockIdx.x) / gridDim.x) * gridDim.x;
-      item = last - (item - blockIdx.x);
-    }
     const uint32_t ks = item / p.row_groups, rg = item - ks * p.row_groups;
     const uint32_t st0 = ks * p.stages_per_split;
     uint32_t st1 = st0 + p.stages_per_split;
@@ -724,7 +719,6 @@ int launch_sketch_i8(gpca_ctx* c, const SketchProblem& p) {
   tp.l = p.l;
   tp.partial = nullptr;
   tp.items = nullptr;
-  tp.dbg_reverse = getenv("GPCA_DEBUG_REVERSE") ? 1u : 0u;
   if (ksplit > 1) {
     GPCA_CUDA_TRY(c, c->ws_partial.alloc((size_t)ksplit * rows * NL));
     tp.partial = c->ws_partial.p;
@@ -829,7 +823,6 @@ int launch_sketch_i8_batch(gpca_ctx* c, const SketchBatch& sb) {
   tp.l = 0;
   tp.partial = nullptr;
   tp.items = sb.d_items;
-  tp.dbg_reverse = 0;
   CUtensorMap tmap;
   {
     EncodeTiledFn enc = get_encode_fn_i8();
