@@ -42,11 +42,19 @@ def parse_args():
     p.add_argument("--samples", type=int, default=2504)
     p.add_argument("--snps", type=int, default=10_000_000, help="SNPs per GPU (weak scaling)")
     p.add_argument("--engine", type=int, default=None)
+    p.add_argument("--components", type=int, default=None, help="k (default 20 = BASELINE config 3; config 5 uses 40)")
+    p.add_argument("--power-iters", type=int, default=None, help="q (default 2; config 5 uses 4)")
     p.add_argument("--cpu-snps", type=int, default=150_000, help="SNP rows of the CPU baseline sample")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu", action="store_true")
     p.add_argument("--no-ukb", action="store_true", help="skip the supplementary 500k x 87.5k shard measurement")
-    return p.parse_args()
+    a = p.parse_args()
+    global K_COMPONENTS, POWER_ITERS
+    if a.components is not None:
+        K_COMPONENTS = a.components
+    if a.power_iters is not None:
+        POWER_ITERS = a.power_iters
+    return a
 
 
 # ------------------------------------------------------------------------------------------
@@ -326,7 +334,7 @@ def run_ours(args, rank, world):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": {0: "f32", 1: "f16 x f16 -> f32 (tcgen05)", 2: "u8 x s8 -> s32 (tcgen05 kind::i8, exact)"}[ctx_engine(ctx, args)],
         "data": "synthetic",
-        "config": {"workload": f"1000G-shape rfit k={K_COMPONENTS} oversample={OVERSAMPLE} q={POWER_ITERS}: "
+        "config": {"workload": f"{'1000G-shape ' if (n, m) == (2504, 10_000_000) else ''}rfit k={K_COMPONENTS} oversample={OVERSAMPLE} q={POWER_ITERS}: "
                                f"{n} samples x {m} SNPs per GPU ({d_kept} after MAF 0.01), 2-bit packed, SNP-sharded",
                    "passes_per_step": passes, "bytes_per_pass": bytes_per_pass,
                    "l2": "inputs larger than L2 (packed shard >> 126 MB)" if bytes_per_pass > 2e8 else "input fits L2",

@@ -122,7 +122,7 @@ struct gpca_ctx {
   DevBuf<double> ws_batch;     // batched dense helpers: G / T / evecs / evals / flags per problem
   DevBuf<float> ws_bstat;      // batched passes: per-block column sums, scales, amax words
   bool tc_amax_zeroed = false;
-  DevBuf<float> drv_a, drv_b, drv_c, drv_d;   // driver-level dense operands (kept across calls: no per-call cudaMalloc)
+  DevBuf<float> drv_a, drv_b, drv_c, drv_d, drv_e;   // driver-level dense operands (kept across calls: no per-call cudaMalloc)
 
   void* cublas = nullptr;      // cublasHandle_t, created on first EigenSNP call
 

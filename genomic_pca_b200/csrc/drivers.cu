@@ -121,20 +121,21 @@ extern "C" int gpca_rfit(gpca_ctx* c, uint32_t k, uint32_t oversample, uint32_t 
   }
   GPCA_TRY(orthonormalize(c, Y.p, N, l, l, false, s));
   GPCA_TRY(sketch_snp_side(c, Y.p, Z.p, l, l, l));        // B = S Q   [D x l]
-  GPCA_TRY(launch_gram(c, Z.p, D, l, l, s.G));
-  GPCA_TRY(driver_allreduce(c, s.G, (uint64_t)l * l, 1));
+  // B^T B = Q^T (S^T B): the l x l matrix whose eigen-decomposition gives the singular values and the right factor of
+  // B comes from the sample-side sketch of B -- which is also all that the scores need (scores = S^T B V_b / s).  The
+  // D-row Gram of B and, when the rotation is not asked for, every D x l by l x k product disappear; on several GPUs
+  // S^T B is already summed over the shards, so no further exchange is needed.
+  DevBuf<float>& Y2 = c->drv_e;
+  GPCA_CUDA_TRY(c, Y2.alloc(N * l));
+  GPCA_TRY(sketch_sample_side(c, Z.p, Y2.p, l, l, l));    // S^T B   [N x l]
+  GPCA_TRY(launch_cross_gram(c, Y.p, Y2.p, N, l, l, s.G));
   GPCA_TRY(launch_jacobi_eigh(c, s.G, l, s.evals, s.evecs));
   GPCA_TRY(launch_rotation_transform(c, s.evals, s.evecs, l, k, s.T, true));
   GPCA_CUDA_TRY(c, Sc.alloc(N * k));
+  GPCA_TRY(launch_apply_right(c, Y2.p, N, l, l, s.T, k, Sc.p, k));   // transform(): scores = S^T rotation
   if (loadings) {
     GPCA_CUDA_TRY(c, R.alloc(D * k));
-    GPCA_TRY(launch_apply_right(c, Z.p, D, l, l, s.T, k, R.p, k));  // rotation = B V_b / s  [D x k]
-    GPCA_TRY(sketch_sample_side(c, R.p, Sc.p, k, k, k));            // transform(): scores = S^T rotation
-  } else {
-    // the rotation itself is not wanted: scores = S^T (B T) = (S^T B) T, which moves the multiplication by T from the
-    // D x l operand to the N x l result
-    GPCA_TRY(sketch_sample_side(c, Z.p, Y.p, l, l, l));
-    GPCA_TRY(launch_apply_right(c, Y.p, N, l, l, s.T, k, Sc.p, k));
+    GPCA_TRY(launch_apply_right(c, Z.p, D, l, l, s.T, k, R.p, k));   // rotation = B V_b / s  [D x k]
   }
 
   // sign convention, f32 -> f64 conversion and the flips of the loadings all happen on the device;

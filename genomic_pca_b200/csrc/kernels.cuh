@@ -24,6 +24,9 @@ int launch_gaussian(gpca_ctx* c, float* d_out, uint64_t rows, uint32_t cols, uin
                     uint32_t stream, uint64_t row0);
 // G[l x l] (f64, row-major) = Y^T Y, Y [n x l] fp32 with row stride ld.  Deterministic two-stage.
 int launch_gram(gpca_ctx* c, const float* d_y, uint64_t n, uint32_t l, uint32_t ld, double* d_g);
+// G[l x l] (f64) = A^T B for two [n x l] fp32 matrices with the same row stride
+int launch_cross_gram(gpca_ctx* c, const float* d_a, const float* d_b, uint64_t n, uint32_t l, uint32_t ld,
+                      double* d_g);
 // Y <- Y * T (T [l x l2] f64 row-major on device), in place allowed when d_out == d_y. out ld = ldo
 int launch_apply_right(gpca_ctx* c, const float* d_y, uint64_t n, uint32_t l, uint32_t ld, const double* d_t,
                        uint32_t l2, float* d_out, uint32_t ldo);

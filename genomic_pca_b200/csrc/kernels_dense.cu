@@ -136,12 +136,106 @@ __global__ void __launch_bounds__(256) gram_batch_kernel(const float* __restrict
 
 __global__ void gram_reduce_kernel(const double* __restrict__ partial, int nparts, uint32_t l, int lp,
                                    double* __restrict__ g) {
-  for (int t = threadIdx.x; t < (int)(l * l); t += blockDim.x) {
+  // one thread per output element; the partials are summed in index order (deterministic)
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < (int)(l * l); t += gridDim.x * blockDim.x) {
     const int i = t / l, j = t % l;
     double s = 0.0;
     for (int p = 0; p < nparts; ++p) s += partial[(uint64_t)p * lp * lp + i * lp + j];
     g[t] = s;
   }
+}
+
+// Cross Gram  G = A^T B  (A, B [n x l] fp32 with the same row stride), f64 accumulation; same tiling as the Gram.
+template <int LP>
+__global__ void __launch_bounds__(256) cross_gram_partial_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                                 uint64_t n, uint32_t l, uint32_t ld,
+                                                                 uint64_t rows_per_cta, double* __restrict__ partial) {
+  constexpr int TPD = LP / 4;
+  constexpr int GROUPS = 256 / (TPD * TPD);
+  __shared__ __align__(16) float ta[GRAM_ROWS][LP + 4];
+  __shared__ __align__(16) float tb[GRAM_ROWS][LP + 4];
+  __shared__ double gsum[(GROUPS > 1) ? (GROUPS - 1) * LP * LP : 1];
+  const int grp = threadIdx.x / (TPD * TPD);
+  const int t = threadIdx.x % (TPD * TPD);
+  const int ti = t / TPD, tj = t % TPD;
+  double acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+  const uint64_t r_begin = blockIdx.x * rows_per_cta;
+  uint64_t r_end = r_begin + rows_per_cta;
+  if (r_end > n) r_end = n;
+  for (uint64_t r0 = r_begin; r0 < r_end; r0 += GRAM_ROWS) {
+    for (int e = threadIdx.x; e < GRAM_ROWS * LP; e += 256) {
+      const int rr = e / LP, cc = e % LP;
+      const uint64_t r = r0 + rr;
+      const bool live = r < r_end && (uint32_t)cc < l;
+      ta[rr][cc] = live ? a[r * ld + cc] : 0.0f;
+      tb[rr][cc] = live ? b[r * ld + cc] : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int rr = grp; rr < GRAM_ROWS; rr += GROUPS) {
+      const float4 av4 = *reinterpret_cast<const float4*>(&ta[rr][ti * 4]);
+      const float4 bv4 = *reinterpret_cast<const float4*>(&tb[rr][tj * 4]);
+      const double av[4] = {av4.x, av4.y, av4.z, av4.w};
+      const double bv[4] = {bv4.x, bv4.y, bv4.z, bv4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  if (GROUPS > 1) {
+    if (grp > 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) gsum[((grp - 1) * LP + ti * 4 + i) * LP + tj * 4 + j] = acc[i][j];
+    }
+    __syncthreads();
+    if (grp == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          for (int g = 0; g < GROUPS - 1; ++g) acc[i][j] += gsum[(g * LP + ti * 4 + i) * LP + tj * 4 + j];
+    }
+  }
+  if (grp == 0) {
+    double* p = partial + (uint64_t)blockIdx.x * LP * LP;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) p[(ti * 4 + i) * LP + tj * 4 + j] = acc[i][j];
+  }
+}
+
+int launch_cross_gram(gpca_ctx* c, const float* d_a, const float* d_b, uint64_t n, uint32_t l, uint32_t ld,
+                      double* d_g) {
+  if (l == 0 || l > 64) {
+    c->set_error("launch_cross_gram: l must be in 1..64");
+    return GPCA_ERR_INVALID;
+  }
+  const int lp = (l <= 32) ? 32 : 64;
+  int nparts = (int)((n + 255) / 256);
+  if (nparts > c->sm_count * 4) nparts = c->sm_count * 4;
+  if (nparts < 1) nparts = 1;
+  uint64_t rows_per_cta = (n + nparts - 1) / nparts;
+  rows_per_cta = round_up(rows_per_cta ? rows_per_cta : 1, GRAM_ROWS);
+  nparts = (int)((n + rows_per_cta - 1) / rows_per_cta);
+  if (nparts < 1) nparts = 1;
+  GPCA_CUDA_TRY(c, c->ws_gram.alloc((size_t)nparts * lp * lp + 4096));
+  if (lp == 32)
+    cross_gram_partial_kernel<32><<<nparts, 256, 0, c->stream>>>(d_a, d_b, n, l, ld, rows_per_cta, c->ws_gram.p);
+  else
+    cross_gram_partial_kernel<64><<<nparts, 256, 0, c->stream>>>(d_a, d_b, n, l, ld, rows_per_cta, c->ws_gram.p);
+  KLAUNCH_CHECK(c);
+  gram_reduce_kernel<<<(l * l + 127) / 128, 128, 0, c->stream>>>(c->ws_gram.p, nparts, l, lp, d_g);
+  KLAUNCH_CHECK(c);
+  return GPCA_OK;
 }
 
 int launch_gram(gpca_ctx* c, const float* d_y, uint64_t n, uint32_t l, uint32_t ld, double* d_g) {
@@ -163,7 +257,7 @@ int launch_gram(gpca_ctx* c, const float* d_y, uint64_t n, uint32_t l, uint32_t 
   else
     gram_partial_kernel<64><<<nparts, 256, 0, c->stream>>>(d_y, n, l, ld, rows_per_cta, c->ws_gram.p);
   KLAUNCH_CHECK(c);
-  gram_reduce_kernel<<<1, 256, 0, c->stream>>>(c->ws_gram.p, nparts, l, lp, d_g);
+  gram_reduce_kernel<<<(l * l + 127) / 128, 128, 0, c->stream>>>(c->ws_gram.p, nparts, l, lp, d_g);
   KLAUNCH_CHECK(c);
   return GPCA_OK;
 }
