@@ -724,8 +724,10 @@ int timed_sketch_batch(gpca_ctx* c, const SketchBatch& sb) {
   return rc;
 }
 
-int sketch_snp_side(gpca_ctx* c, const float* dev_in, float* dev_out, uint32_t l, uint32_t ld_in, uint32_t ld_out) {
+int sketch_snp_side(gpca_ctx* c, const float* dev_in, float* dev_out, uint32_t l, uint32_t ld_in, uint32_t ld_out,
+                    bool emit_stats) {
   SketchProblem p;
+  p.emit_stats = emit_stats && ld_out == l;   // the consumer reads the output with the same row stride
   p.G = c->Gs;
   p.Bin = dev_in;
   p.l = l;
@@ -739,8 +741,10 @@ int sketch_snp_side(gpca_ctx* c, const float* dev_in, float* dev_out, uint32_t l
   return timed_sketch(c, p);
 }
 
-int sketch_sample_side(gpca_ctx* c, const float* dev_in, float* dev_out, uint32_t l, uint32_t ld_in, uint32_t ld_out) {
+int sketch_sample_side(gpca_ctx* c, const float* dev_in, float* dev_out, uint32_t l, uint32_t ld_in, uint32_t ld_out,
+                       bool use_stats) {
   SketchProblem p;
+  p.use_stats = use_stats;
   p.G = c->Gt;
   p.Bin = dev_in;
   p.l = l;
@@ -765,7 +769,7 @@ extern "C" int gpca_sketch_snp_side(gpca_ctx* c, const float* dev_in, float* dev
   GPCA_CUDA_TRY(c, cudaSetDevice(c->device));
   if (c->D == 0) return fail(c, GPCA_ERR_INVALID, "gpca_set_pca_snps has not been called");
   if (l == 0 || l > 64 || ld < l) return fail(c, GPCA_ERR_INVALID, "need 1 <= l <= 64 and ld >= l");
-  return sketch_snp_side(c, dev_in, dev_out, l, ld, ld);
+  return sketch_snp_side(c, dev_in, dev_out, l, ld, ld, false);
 }
 
 extern "C" int gpca_sketch_sample_side(gpca_ctx* c, const float* dev_in, float* dev_out, uint32_t l, uint32_t ld) {
@@ -773,7 +777,7 @@ extern "C" int gpca_sketch_sample_side(gpca_ctx* c, const float* dev_in, float* 
   GPCA_CUDA_TRY(c, cudaSetDevice(c->device));
   if (c->D == 0) return fail(c, GPCA_ERR_INVALID, "gpca_set_pca_snps has not been called");
   if (l == 0 || l > 64 || ld < l) return fail(c, GPCA_ERR_INVALID, "need 1 <= l <= 64 and ld >= l");
-  return sketch_sample_side(c, dev_in, dev_out, l, ld, ld);
+  return sketch_sample_side(c, dev_in, dev_out, l, ld, ld, false);
 }
 
 extern "C" double gpca_sketch_kernel_ms(gpca_ctx* c) { return c ? c->sk_kernel_ms_last : 0.0; }

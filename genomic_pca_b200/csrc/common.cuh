@@ -120,6 +120,11 @@ struct gpca_ctx {
   DevBuf<double> ws_small;     // l x l matrices: G, evals, evecs, T
   DevBuf<uint8_t> ws_bytes;    // tcgen05 engine: fp16 B' image
   DevBuf<double> ws_batch;     // batched dense helpers: G / T / evecs / evals / flags per problem
+  DevBuf<double> ws_stats;     // operand statistics produced as by-products (see SketchProblem::emit_stats)
+  const float* stats_for = nullptr;   // the matrix they describe (nullptr = none)
+  uint32_t stats_l = 0;
+  int stats_nparts = 0;
+  bool stats_pending = false;         // a producer left statistics that no consumer has taken (max-abs word not reset)
   DevBuf<float> ws_bstat;      // batched passes: per-block column sums, scales, amax words
   bool tc_amax_zeroed = false;
   DevBuf<float> drv_a, drv_b, drv_c, drv_d, drv_e;   // driver-level dense operands (kept across calls: no per-call cudaMalloc)

@@ -24,8 +24,13 @@ void fix_signs_host(std::vector<float>& scores, uint64_t n, uint32_t k, std::vec
 
 int driver_allreduce(gpca_ctx* c, void* buf, uint64_t count, int dtype);
 
-int sketch_snp_side(gpca_ctx* c, const float* dev_in, float* dev_out, uint32_t l, uint32_t ld_in, uint32_t ld_out);
-int sketch_sample_side(gpca_ctx* c, const float* dev_in, float* dev_out, uint32_t l, uint32_t ld_in, uint32_t ld_out);
+// emit_stats: also leave the operand statistics of the output (as the next sample-side pass needs them) in the context;
+// use_stats: the operand's statistics are in the context (it was produced by such a pass or by
+// launch_gaussian_with_stats and has not been modified since)
+int sketch_snp_side(gpca_ctx* c, const float* dev_in, float* dev_out, uint32_t l, uint32_t ld_in, uint32_t ld_out,
+                    bool emit_stats = false);
+int sketch_sample_side(gpca_ctx* c, const float* dev_in, float* dev_out, uint32_t l, uint32_t ld_in, uint32_t ld_out,
+                       bool use_stats = false);
 // generic timed sketch on an arbitrary view (used by the EigenSNP driver)
 int timed_sketch(gpca_ctx* c, const SketchProblem& p);
 // one launch for all LD blocks (integer engine, item mode)

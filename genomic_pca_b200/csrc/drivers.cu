@@ -110,24 +110,27 @@ extern "C" int gpca_rfit(gpca_ctx* c, uint32_t k, uint32_t oversample, uint32_t 
   GPCA_CUDA_TRY(c, Z.alloc(D * l));
 
   // Y = S^T Omega
-  GPCA_TRY(launch_gaussian(c, Z.p, D, l, l, seed, STREAM_RFIT_OMEGA, c->shard_offset));
-  GPCA_TRY(sketch_sample_side(c, Z.p, Y.p, l, l, l));
+  // (every D x l operand of a sample-side pass arrives with its column statistics: from the generator here, from the
+  //  epilogue of the snp-side pass below -- one sweep over a D x l matrix saved per pass)
+  GPCA_TRY(launch_gaussian_with_stats(c, Z.p, D, l, l, seed, STREAM_RFIT_OMEGA, c->shard_offset, c->d_inv_sd.p,
+                                      c->d_mu_inv_sd.p));
+  GPCA_TRY(sketch_sample_side(c, Z.p, Y.p, l, l, l, true));
   for (uint32_t it = 0; it < power_iters; ++it) {
     GPCA_TRY(orthonormalize(c, Y.p, N, l, l, false, s));
-    GPCA_TRY(sketch_snp_side(c, Y.p, Z.p, l, l, l));      // Z = S Q
+    GPCA_TRY(sketch_snp_side(c, Y.p, Z.p, l, l, l, true));   // Z = S Q
     // (range(S^T Z) does not depend on a column transform of Z; the snp-side basis is left unnormalised
     //  between the two half-steps, the sample side is re-orthonormalised every iteration)
-    GPCA_TRY(sketch_sample_side(c, Z.p, Y.p, l, l, l));   // Y = S^T Z
+    GPCA_TRY(sketch_sample_side(c, Z.p, Y.p, l, l, l, true));   // Y = S^T Z
   }
   GPCA_TRY(orthonormalize(c, Y.p, N, l, l, false, s));
-  GPCA_TRY(sketch_snp_side(c, Y.p, Z.p, l, l, l));        // B = S Q   [D x l]
+  GPCA_TRY(sketch_snp_side(c, Y.p, Z.p, l, l, l, true));  // B = S Q   [D x l]
   // B^T B = Q^T (S^T B): the l x l matrix whose eigen-decomposition gives the singular values and the right factor of
   // B comes from the sample-side sketch of B -- which is also all that the scores need (scores = S^T B V_b / s).  The
   // D-row Gram of B and, when the rotation is not asked for, every D x l by l x k product disappear; on several GPUs
   // S^T B is already summed over the shards, so no further exchange is needed.
   DevBuf<float>& Y2 = c->drv_e;
   GPCA_CUDA_TRY(c, Y2.alloc(N * l));
-  GPCA_TRY(sketch_sample_side(c, Z.p, Y2.p, l, l, l));    // S^T B   [N x l]
+  GPCA_TRY(sketch_sample_side(c, Z.p, Y2.p, l, l, l, true));    // S^T B   [N x l]
   GPCA_TRY(launch_cross_gram(c, Y.p, Y2.p, N, l, l, s.G));
   GPCA_TRY(launch_jacobi_eigh(c, s.G, l, s.evals, s.evecs));
   GPCA_TRY(launch_rotation_transform(c, s.evals, s.evecs, l, k, s.T, true));

@@ -22,6 +22,14 @@ int launch_std_block(gpca_ctx* c, PackedMat gs, const float* d_mean, const float
 // Gaussian test matrix: out[r][c] = N(0,1) keyed by (seed, stream, row0 + r, c); ld in floats
 int launch_gaussian(gpca_ctx* c, float* d_out, uint64_t rows, uint32_t cols, uint32_t ld, uint64_t seed,
                     uint32_t stream, uint64_t row0);
+// same matrix, and the operand statistics (column sums weighted by e, max |f o out|) left in the context for the
+// sketch pass that consumes it (cols <= 32)
+int launch_gaussian_with_stats(gpca_ctx* c, float* d_out, uint64_t rows, uint32_t cols, uint32_t ld, uint64_t seed,
+                               uint32_t stream, uint64_t row0, const float* d_f, const float* d_e);
+// context-held operand statistics (layout: [STATS_MAX_PARTS][32] f64 partial column sums, then the max-abs word)
+constexpr int STATS_MAX_PARTS = 4096;
+int stats_buffer(gpca_ctx* c, double** cpart, unsigned int** amax);
+int stats_begin_produce(gpca_ctx* c, unsigned int* amax);
 // G[l x l] (f64, row-major) = Y^T Y, Y [n x l] fp32 with row stride ld.  Deterministic two-stage.
 int launch_gram(gpca_ctx* c, const float* d_y, uint64_t n, uint32_t l, uint32_t ld, double* d_g);
 // G[l x l] (f64) = A^T B for two [n x l] fp32 matrices with the same row stride
@@ -94,6 +102,11 @@ struct SketchProblem {
   const float* b;         // [rows] per-row weight of the rank-one term (nullptr = 1)
   float* out;             // [rows x ldo]
   uint32_t ldo;
+  // Operand statistics as by-products (integer engine; ignored elsewhere).  A sample-side pass needs, for its operand
+  // W, the column sums e^T W and max |f o W|; when W was just produced by a snp-side pass (f = that pass's a, e = its
+  // b) or by the Gaussian generator, the producer computes them on the way out and one sweep over W is saved.
+  bool emit_stats = false;   // also leave the statistics of `out` (weights a, b) in the context
+  bool use_stats = false;    // Bin's statistics are in the context already
 };
 // out[r,:] = a_r * sum_k code(r,k) f_k Bin[k,:]  -  b_r * sum_k e_k Bin[k,:]  (+ missing correction)
 int launch_sketch(gpca_ctx* c, const SketchProblem& p);

@@ -42,6 +42,95 @@ int launch_gaussian(gpca_ctx* c, float* d_out, uint64_t rows, uint32_t cols, uin
   return GPCA_OK;
 }
 
+int stats_buffer(gpca_ctx* c, double** cpart, unsigned int** amax) {
+  const size_t need = (size_t)STATS_MAX_PARTS * 32 + 2;
+  if (c->ws_stats.n < need) {
+    GPCA_CUDA_TRY(c, c->ws_stats.alloc(need));
+    GPCA_CUDA_TRY(c, cudaMemsetAsync(c->ws_stats.p, 0, need * sizeof(double), c->stream));
+    c->stats_pending = false;
+  }
+  *cpart = c->ws_stats.p;
+  *amax = reinterpret_cast<unsigned int*>(c->ws_stats.p + (size_t)STATS_MAX_PARTS * 32);
+  return GPCA_OK;
+}
+
+// call before a producer accumulates into the max-abs word: statistics that nobody consumed (other engine, error
+// path) must not leak into the new ones
+int stats_begin_produce(gpca_ctx* c, unsigned int* amax) {
+  if (c->stats_pending) GPCA_CUDA_TRY(c, cudaMemsetAsync(amax, 0, sizeof(unsigned int), c->stream));
+  c->stats_pending = true;
+  c->stats_for = nullptr;
+  return GPCA_OK;
+}
+
+// Gaussian matrix + its operand statistics.  CTA b owns a contiguous range of rows; thread (rr = tid / 8, cg = tid % 8)
+// walks rows rr, rr + 32, ... of the range and owns columns 4 cg .. 4 cg + 3.
+__global__ void __launch_bounds__(256) gaussian_stats_kernel(float* __restrict__ out, uint64_t rows, uint32_t cols,
+                                                             uint32_t ld, uint64_t seed, uint32_t stream, uint64_t row0,
+                                                             const float* __restrict__ f, const float* __restrict__ e,
+                                                             uint64_t rows_per_cta, double* __restrict__ cpart,
+                                                             unsigned int* __restrict__ amax_bits) {
+  __shared__ double red[32][33];
+  __shared__ float redm[8];
+  const int rr = threadIdx.x >> 3, cg = threadIdx.x & 7;
+  const uint64_t r_begin = blockIdx.x * rows_per_cta;
+  uint64_t r_end = r_begin + rows_per_cta;
+  if (r_end > rows) r_end = rows;
+  double cs[4] = {0.0, 0.0, 0.0, 0.0};
+  float mx = 0.0f;
+  for (uint64_t r = r_begin + rr; r < r_end; r += 32) {
+    float z[4];
+    philox_normal4(seed, stream, row0 + r, (uint32_t)cg, z);
+    const float fr = f ? f[r] : 1.0f, er = e ? e[r] : 1.0f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t cidx = cg * 4 + j;
+      const float v = (cidx < cols) ? z[j] : 0.0f;
+      if (cidx < ld) out[r * ld + cidx] = v;
+      cs[j] += (double)(v * er);
+      mx = fmaxf(mx, fabsf(v * fr));
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) red[rr][cg * 4 + j] = cs[j];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) redm[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double s = 0.0;
+    for (int q = 0; q < 32; ++q) s += red[q][threadIdx.x];
+    cpart[(uint64_t)blockIdx.x * 32 + threadIdx.x] = s;
+    if (threadIdx.x == 0) {
+      float m = 0.0f;
+      for (int q = 0; q < 8; ++q) m = fmaxf(m, redm[q]);
+      if (m > 0.0f && isfinite(m)) atomicMax(amax_bits, __float_as_uint(m));
+    }
+  }
+}
+
+int launch_gaussian_with_stats(gpca_ctx* c, float* d_out, uint64_t rows, uint32_t cols, uint32_t ld, uint64_t seed,
+                               uint32_t stream, uint64_t row0, const float* d_f, const float* d_e) {
+  c->stats_for = nullptr;
+  if (cols > 32 || ld > 32 || rows == 0 || getenv("GPCA_DEBUG_NO_GAUSS_STATS")) return launch_gaussian(c, d_out, rows, cols, ld, seed, stream, row0);
+  double* cpart = nullptr;
+  unsigned int* amax = nullptr;
+  GPCA_TRY(stats_buffer(c, &cpart, &amax));
+  GPCA_TRY(stats_begin_produce(c, amax));
+  int nparts = c->sm_count * 8;
+  if (nparts > STATS_MAX_PARTS) nparts = STATS_MAX_PARTS;
+  uint64_t rows_per_cta = (rows + nparts - 1) / nparts;
+  rows_per_cta = round_up(rows_per_cta, 32);
+  nparts = (int)((rows + rows_per_cta - 1) / rows_per_cta);
+  gaussian_stats_kernel<<<nparts, 256, 0, c->stream>>>(d_out, rows, cols, ld, seed, stream, row0, d_f, d_e, rows_per_cta,
+                                                       cpart, amax);
+  KLAUNCH_CHECK(c);
+  c->stats_for = d_out;
+  c->stats_l = cols;
+  c->stats_nparts = nparts;
+  return GPCA_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // Gram: each CTA owns a contiguous range of rows, stages 64 rows at a time in shared memory and accumulates an
 // LP x LP (LP = 32 or 64, padded) f64 partial with a 4 x 4 register tile per thread.  For LP = 32 the 256 threads form

@@ -69,6 +69,8 @@ struct I8Params {
   uint32_t ldo, l;
   float* partial;       // [ksplit][rows][32]
   const I8Item* items;  // item mode (batched per-LD-block passes): explicit work list, no split-K partials
+  double* stat_cpart;   // regular mode, direct output: per-warp partial column sums of b_r * out[r,:]  ([grid*8][32])
+  unsigned int* stat_amax;   // and max |a_r * out[r,:]| (float bits)
 };
 
 // What one work item covers.  Regular mode derives it from (k-split, row group); item mode reads it from the table.
@@ -273,6 +275,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) sketch_i8_kernel(const __grid_
     // under SWIZZLE_64B (64-byte rows)
     const uint32_t sw = (A_ROW_BYTES == 128) ? (uint32_t)(row_in_tile & 7) : (uint32_t)((row_in_tile >> 1) & 3);
     uint32_t it = 0, cit = 0, item_idx = 0;
+    double stat_sum = 0.0;     // this lane's column of the by-product statistics (see SketchProblem::emit_stats)
+    float stat_max = 0.0f;
     for (uint32_t item = blockIdx.x; item < p.n_items; item += gridDim.x, ++item_idx) {
       const ItemInfo ii = decode_item<ITEMS>(p, item);
       const uint32_t n_ast = (ii.nst + HALVES - 1) / HALVES;
@@ -369,9 +373,39 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) sketch_i8_kernel(const __grid_
               if ((uint32_t)c < ii.l) dst[c] = v0;
               if ((uint32_t)c + 1 < ii.l) dst[c + 1] = v1;
             }
+            hi[c] = __float_as_uint(v0);       // kept for the statistics below
+            hi[c + 1] = __float_as_uint(v1);
           }
         }
       }
+      if (!ITEMS && p.stat_cpart) {
+        // by-product statistics of the rows just written: column sums of b_r * out[r,:] (butterfly over the warp's 32
+        // rows, lane c ends with column c; fixed order, so deterministic) and max |a_r * out[r,:]|
+        float x[NL];
+#pragma unroll
+        for (int c = 0; c < NL; ++c) {
+          const float v = (live && (uint32_t)c < ii.l) ? __uint_as_float(hi[c]) : 0.0f;
+          stat_max = fmaxf(stat_max, fabsf(ar * v));
+          x[c] = br * v;
+        }
+#pragma unroll
+        for (int sft = 16; sft >= 1; sft >>= 1) {
+          const bool up = (lane & sft) != 0;
+#pragma unroll
+          for (int i = 0; i < sft; ++i) {
+            const float keep = up ? x[i + sft] : x[i];
+            const float give = up ? x[i] : x[i + sft];
+            x[i] = keep + __shfl_xor_sync(0xffffffffu, give, sft);
+          }
+        }
+        stat_sum += (double)x[0];
+      }
+    }
+    if (!ITEMS && p.stat_cpart) {
+      p.stat_cpart[((size_t)blockIdx.x * 8 + (warp - 2)) * NL + lane] = stat_sum;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) stat_max = fmaxf(stat_max, __shfl_xor_sync(0xffffffffu, stat_max, o));
+      if (lane == 0 && stat_max > 0.0f && isfinite(stat_max)) atomicMax(p.stat_amax, __float_as_uint(stat_max));
     }
   }
   tc_fence_before();
@@ -430,19 +464,28 @@ __global__ void __launch_bounds__(256) i8_colstats_kernel(const float* __restric
   }
 }
 
-__global__ void i8_finalize_stats_kernel(const double* __restrict__ cpart, int nparts, float* __restrict__ cvec,
-                                         unsigned int* __restrict__ amax_bits, float* __restrict__ scales) {
-  const int cidx = threadIdx.x;
-  if (cidx < 32) {
-    double s = 0.0;
-    for (int q = 0; q < nparts; ++q) s += cpart[(uint64_t)q * 32 + cidx];
-    cvec[cidx] = (float)s;
-  }
-  if (cidx == 0) {
-    const float m = __uint_as_float(*amax_bits);
-    scales[0] = (m > 0.0f) ? 32512.0f / m : 0.0f;     // |q| <= 32512 = 127*256: both limbs fit s8
-    scales[1] = (m > 0.0f) ? m / 32512.0f : 0.0f;
-    *amax_bits = 0u;
+__global__ void __launch_bounds__(256) i8_finalize_stats_kernel(const double* __restrict__ cpart, int nparts,
+                                                                float* __restrict__ cvec,
+                                                                unsigned int* __restrict__ amax_bits,
+                                                                float* __restrict__ scales) {
+  // 8 groups of 32 lanes each sum every 8th partial; the 8 group sums are added in index order (deterministic)
+  __shared__ double red[8][32];
+  const int cidx = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  double s = 0.0;
+  for (int q = grp; q < nparts; q += 8) s += cpart[(uint64_t)q * 32 + cidx];
+  red[grp][cidx] = s;
+  __syncthreads();
+  if (grp == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) t += red[g][cidx];
+    cvec[cidx] = (float)t;
+    if (cidx == 0) {
+      const float m = __uint_as_float(*amax_bits);
+      scales[0] = (m > 0.0f) ? 32512.0f / m : 0.0f;     // |q| <= 32512 = 127*256: both limbs fit s8
+      scales[1] = (m > 0.0f) ? m / 32512.0f : 0.0f;
+      *amax_bits = 0u;
+    }
   }
 }
 
@@ -484,10 +527,16 @@ __global__ void __launch_bounds__(256) prep_b_i8_kernel(const float* __restrict_
   }
 }
 
-__global__ void sketch_reduce_i8_kernel(const float* __restrict__ partial, int nsplit, uint64_t rows,
-                                        const float* __restrict__ a, const float* __restrict__ b,
-                                        const float* __restrict__ cvec, float* __restrict__ out, uint32_t ldo, uint32_t l) {
+__global__ void __launch_bounds__(256) sketch_reduce_i8_kernel(const float* __restrict__ partial, int nsplit,
+                                                               uint64_t rows, const float* __restrict__ a,
+                                                               const float* __restrict__ b,
+                                                               const float* __restrict__ cvec, float* __restrict__ out,
+                                                               uint32_t ldo, uint32_t l, double* __restrict__ stat_cpart,
+                                                               unsigned int* __restrict__ stat_amax) {
+  __shared__ double sred[8][NL];
   const uint64_t total = rows * NL;
+  double ssum = 0.0;     // by-product statistics of the output (a thread always meets the same column: strides are
+  float smax = 0.0f;     // multiples of 32)
   for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < total;
        t += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t r = t / NL;
@@ -496,7 +545,24 @@ __global__ void sketch_reduce_i8_kernel(const float* __restrict__ partial, int n
     float s = 0.0f;
     for (int q = 0; q < nsplit; ++q) s += partial[((uint64_t)q * rows + r) * NL + cc];
     const float ar = a ? a[r] : 1.0f, br = b ? b[r] : 1.0f;
-    out[r * ldo + cc] = ar * s - br * cvec[cc];
+    const float v = ar * s - br * cvec[cc];
+    out[r * ldo + cc] = v;
+    ssum += (double)(br * v);
+    smax = fmaxf(smax, fabsf(ar * v));
+  }
+  if (stat_cpart) {
+    const int cidx = threadIdx.x & 31, w = threadIdx.x >> 5;
+    sred[w][cidx] = ssum;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) smax = fmaxf(smax, __shfl_xor_sync(0xffffffffu, smax, o));
+    if (cidx == 0 && smax > 0.0f && isfinite(smax)) atomicMax(stat_amax, __float_as_uint(smax));
+    __syncthreads();
+    if (w == 0) {
+      double t = 0.0;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) t += sred[g][cidx];
+      stat_cpart[(uint64_t)blockIdx.x * NL + cidx] = t;
+    }
   }
 }
 
@@ -669,12 +735,26 @@ int launch_sketch_i8(gpca_ctx* c, const SketchProblem& p) {
     GPCA_CUDA_TRY(c, cudaMemsetAsync(amax, 0, sizeof(unsigned int), c->stream));
     c->tc_amax_zeroed = true;
   }
-  i8_colstats_kernel<<<nb, 256, 0, c->stream>>>(p.Bin, K, p.l, p.ld, p.f, p.e, c->ws_cpart.p, amax);
-  c->launches++;
-  GPCA_CUDA_TRY(c, cudaGetLastError());
-  i8_finalize_stats_kernel<<<1, 32, 0, c->stream>>>(c->ws_cpart.p, nb, cvec, amax, scales);
-  c->launches++;
-  GPCA_CUDA_TRY(c, cudaGetLastError());
+  double* st_cpart = nullptr;
+  unsigned int* st_amax = nullptr;
+  GPCA_TRY(stats_buffer(c, &st_cpart, &st_amax));
+  bool have_stats = p.use_stats && c->stats_for == p.Bin && c->stats_l == p.l && c->stats_nparts > 0;
+  if (getenv("GPCA_DEBUG_NO_USE_STATS")) have_stats = false;
+  if (have_stats) {
+    // the producer of Bin left the partial column sums and the max-abs behind (SketchProblem::emit_stats)
+    i8_finalize_stats_kernel<<<1, 256, 0, c->stream>>>(st_cpart, c->stats_nparts, cvec, st_amax, scales);
+    c->launches++;
+    GPCA_CUDA_TRY(c, cudaGetLastError());
+    c->stats_pending = false;    // (the finalize kernel resets the max-abs word)
+  } else {
+    i8_colstats_kernel<<<nb, 256, 0, c->stream>>>(p.Bin, K, p.l, p.ld, p.f, p.e, c->ws_cpart.p, amax);
+    c->launches++;
+    GPCA_CUDA_TRY(c, cudaGetLastError());
+    i8_finalize_stats_kernel<<<1, 256, 0, c->stream>>>(c->ws_cpart.p, nb, cvec, amax, scales);
+    c->launches++;
+    GPCA_CUDA_TRY(c, cudaGetLastError());
+  }
+  c->stats_for = nullptr;
   {
     const uint64_t total = (Kpad / 16) * NL;
     const uint64_t blocks = (total + 255) / 256;
@@ -719,6 +799,10 @@ int launch_sketch_i8(gpca_ctx* c, const SketchProblem& p) {
   tp.l = p.l;
   tp.partial = nullptr;
   tp.items = nullptr;
+  const bool emit = p.emit_stats && !c->any_missing && !getenv("GPCA_DEBUG_NO_EMIT_STATS");
+  if (emit) GPCA_TRY(stats_begin_produce(c, st_amax));
+  tp.stat_cpart = (emit && ksplit == 1) ? st_cpart : nullptr;
+  tp.stat_amax = st_amax;
   if (ksplit > 1) {
     GPCA_CUDA_TRY(c, c->ws_partial.alloc((size_t)ksplit * rows * NL));
     tp.partial = c->ws_partial.p;
@@ -751,9 +835,17 @@ int launch_sketch_i8(gpca_ctx* c, const SketchProblem& p) {
     const uint64_t total = rows * NL;
     const uint64_t blocks = (total + 255) / 256;
     const int g2 = (int)(blocks < (uint64_t)c->sm_count * 8 ? blocks : (uint64_t)c->sm_count * 8);
-    sketch_reduce_i8_kernel<<<g2, 256, 0, c->stream>>>(tp.partial, (int)ksplit, rows, p.a, p.b, cvec, p.out, p.ldo, p.l);
+    sketch_reduce_i8_kernel<<<g2, 256, 0, c->stream>>>(tp.partial, (int)ksplit, rows, p.a, p.b, cvec, p.out, p.ldo, p.l,
+                                                       emit ? st_cpart : nullptr, st_amax);
     c->launches++;
     GPCA_CUDA_TRY(c, cudaGetLastError());
+    if (emit) c->stats_nparts = g2;
+  } else if (emit) {
+    c->stats_nparts = (int)grid * 8;
+  }
+  if (emit) {
+    c->stats_for = p.out;
+    c->stats_l = p.l;
   }
   return GPCA_OK;
 }
@@ -823,6 +915,8 @@ int launch_sketch_i8_batch(gpca_ctx* c, const SketchBatch& sb) {
   tp.l = 0;
   tp.partial = nullptr;
   tp.items = sb.d_items;
+  tp.stat_cpart = nullptr;
+  tp.stat_amax = nullptr;
   CUtensorMap tmap;
   {
     EncodeTiledFn enc = get_encode_fn_i8();
