@@ -197,6 +197,21 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def make_allreduce_hook(torch, dist, dev):
+    """The library's one exchange step (sum of a device buffer over the shards) bound to NCCL through torch.distributed,
+    on the library's own stream."""
+    def hook(ptr, count, dtype, stream):
+        es = torch.cuda.ExternalStream(stream, device=dev)
+        td = torch.float32 if dtype == 0 else torch.float64
+        iface = {"shape": (count,), "typestr": "<f4" if dtype == 0 else "<f8", "data": (ptr, False), "version": 2}
+        holder = type("P", (), {"__cuda_array_interface__": iface})()
+        t = torch.as_tensor(holder, device=dev)
+        assert t.dtype == td
+        with torch.cuda.stream(es):
+            dist.all_reduce(t)
+    return hook
+
+
 def run_ours(args, rank, world):
     import torch
     import torch.distributed as dist
@@ -217,16 +232,7 @@ def run_ours(args, rank, world):
     if args.engine is not None:
         ctx.set_sketch_engine(args.engine)
     if world > 1:
-        def hook(ptr, count, dtype, stream):
-            es = torch.cuda.ExternalStream(stream, device=dev)
-            td = torch.float32 if dtype == 0 else torch.float64
-            iface = {"shape": (count,), "typestr": "<f4" if dtype == 0 else "<f8", "data": (ptr, False), "version": 2}
-            holder = type("P", (), {"__cuda_array_interface__": iface})()
-            t = torch.as_tensor(holder, device=dev)
-            assert t.dtype == td
-            with torch.cuda.stream(es):
-                dist.all_reduce(t)
-        ctx.set_allreduce(hook)
+        ctx.set_allreduce(make_allreduce_hook(torch, dist, dev))
         ctx.set_shard(rank * m, world * m)
 
     def prepare_from_device():
@@ -307,6 +313,18 @@ def run_ours(args, rank, world):
                "h2d_bytes_per_step": int(m * bps), "d2h_bytes_per_step": int(n * K_COMPONENTS * 8 + K_COMPONENTS * 8 + m * 16),
                "ms_per_step": te * 1e3, "steps": e2e_steps}
 
+    # supplementary measurement at the shape the headline metric is quoted on (all ranks take part: on N GPUs it is
+    # the 500k-sample array with N x 87.5k SNPs, EigenSNP with the N x l exchange over NCCL)
+    ukb = None
+    if not args.no_ukb and (n, m) == (2504, 10_000_000):
+        ctx.close()
+        if not args.no_e2e:
+            del host
+        else:
+            del payload
+        torch.cuda.empty_cache()
+        ukb = ukb_shard_supplement(torch, gp, dev, peaks()[0], rank, world, dist if world > 1 else None)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -322,7 +340,8 @@ def run_ours(args, rank, world):
     eng = ctx_engine(ctx, args)
     roofline = {"bound": "hbm", "achieved": ach_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "frac": ach_gbs / pk["hbm_gbs"], "traffic": TRAFFIC_NCU.get(eng) if (n, m) == (2504, 10_000_000) else None, "peak_source": pk_src,
-                "kernel": {0: "sketch_simt_kernel", 1: "sketch_tc_kernel", 2: "sketch_i8_kernel"}[eng],
+                "kernel": {0: "sketch_simt_kernel", 1: "sketch_tc_kernel",
+                           2: "sketch_i8_kernel" if K_COMPONENTS + OVERSAMPLE <= 32 else "sketch_tc_kernel<64>"}[eng],
                 "ms_per_launch": t_kern * 1e3, "launches_per_step": passes,
                 "kernel_share_of_step": (sk_kernel_ms * 1e-3 / args.steps) / t_step,
                 "pass_level": {"ms_per_pass": t_pass * 1e3, "achieved": bytes_per_pass / t_pass / 1e9 if t_pass > 0 else 0.0,
@@ -342,13 +361,8 @@ def run_ours(args, rank, world):
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
         "eigenvalues_head": [float(x) for x in ev[:3]],
     }
-    if world == 1 and not args.no_ukb and (n, m) == (2504, 10_000_000):
-        ctx.close()
-        del ctx
-        if not args.no_e2e:
-            del host
-        torch.cuda.empty_cache()
-        line["ukb_shard"] = ukb_shard_supplement(torch, gp, dev, pk)
+    if ukb is not None:
+        line["ukb_shard"] = ukb
     if not args.no_cpu:
         dt, cp, cb = cpu_rfit_sample(n, args.cpu_snps)
         line["cpu_baseline"] = {"value": cp * cb / dt / 1e9, "unit": "GB/s", "cores": os.cpu_count() or 1,
@@ -365,14 +379,17 @@ def run_ours(args, rank, world):
 TRAFFIC_NCU = {2: (4 * 7.326e9 + 3 * 7.704e9) / 7}
 
 
-def ukb_shard_supplement(torch, gp, dev, pk):
+def ukb_shard_supplement(torch, gp, dev, pk, rank=0, world=1, dist=None):
     """Supplementary measurement at the shape the headline metric is quoted on: the per-GPU shard of BASELINE
     config 4 on 8 GPUs (500,000 samples x 87,500 SNPs).  The full config needs >= 2 GPUs in this round's
     two-orientation layout, so on one GPU its shard is measured: sketch-pass roofline fraction + EigenSNP wall time."""
     n, m, nblocks = 500_000, 87_500, 212
-    payload = synth_bed_device(torch, n, m, 0, dev)
+    payload = synth_bed_device(torch, n, m, rank * m, dev)
     torch.cuda.synchronize()
     ctx = gp.Context(dev.index or 0)
+    if world > 1:      # every rank holds one shard of SNPs / LD blocks of the same 500k samples
+        ctx.set_allreduce(make_allreduce_hook(torch, dist, dev))
+        ctx.set_shard(rank * m, world * m)
     ctx.load_bed_device(payload.data_ptr(), n, m)
     keep, mean, sd, _ = ctx.snp_qc(gp.QcConfig(0.98, 0.01, 1.0))     # HWE off: pooled structured populations fail it
     d = ctx.set_pca_snps_mask(keep, mean, sd)
@@ -393,12 +410,22 @@ def ukb_shard_supplement(torch, gp, dev, pk):
     blocks = [np.arange(edges[i], edges[i + 1], dtype=np.uint64) for i in range(nblocks)]
     cfg = gp.EigenSnpConfig(target_num_global_pcs=K_COMPONENTS)
     ctx.eigensnp(blocks, cfg)
+    if world > 1:
+        dist.barrier()
     t0 = time.perf_counter()
     sc, ev, load = ctx.eigensnp(blocks, cfg)
     t_es = time.perf_counter() - t0
+    if world > 1:      # max over ranks
+        tt = torch.tensor([t_es, t_rfit], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_es, t_rfit = float(tt[0].item()), float(tt[1].item())
     ctx.close()
     gbs = d * bps / t_kern / 1e9 if t_kern > 0 else 0.0
-    return {"shape": f"{n} samples x {m} SNPs on one GPU = the per-GPU shard of BASELINE config 4 (500k x 700k) on 8 GPUs",
+    shape = (f"{n} samples x {m} SNPs on one GPU = the per-GPU shard of BASELINE config 4 (500k x 700k) on 8 GPUs"
+             if world == 1 else
+             f"{n} samples x {world * m} SNPs ({world * nblocks} LD blocks) sharded over {world} GPUs"
+             + (" = BASELINE config 4" if world == 8 else ""))
+    return {"shape": shape, "n_gpus": world,
             "sketch_kernel_ms_per_launch": t_kern * 1e3, "sketch_kernel_GBps": gbs,
             "sketch_kernel_frac_of_hbm": gbs / pk["hbm_gbs"], "sketch_pass_ms": sk_ms / max(sk_n, 1),
             "rfit_k20_wall_s": t_rfit, "eigensnp_k20_212_blocks_wall_s": t_es,

@@ -1,0 +1,65 @@
+"""Sharded (one process per GPU, NCCL) rfit and EigenSNP against the same computation on one GPU.
+Run:  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/multi_gpu_check.py
+Every rank loads its contiguous shard of SNPs (whole LD blocks); rank 0 also runs the unsharded problem and compares:
+eigenvalues 1e-4 relative, score subspace angle < 1e-3 rad (the north-star tolerances)."""
+import json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch, torch.distributed as dist
+import bench, genomic_pca_b200 as gp
+from oracle import pca
+
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+local = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+n, m_shard, nblk_shard = 6000, 24_000, 40
+qc = gp.QcConfig(0.98, 0.0, 1.0)                 # keep every SNP: shards and the full run see the same set
+
+
+full_payload = bench.synth_bed_device(torch, n, world * m_shard, 0, dev)     # every rank generates the same matrix
+
+
+def load(ctx, snp0, m):
+    payload = full_payload[snp0:snp0 + m].contiguous()                       # ... and takes its rows
+    torch.cuda.synchronize()
+    ctx.load_bed_device(payload.data_ptr(), n, m)
+    keep, mean, sd, _ = ctx.snp_qc(qc)
+    return ctx.set_pca_snps_mask(keep, mean, sd)
+
+
+def blocks_for(d, nblk):
+    edges = np.linspace(0, d, nblk + 1).astype(np.int64)
+    return [np.arange(edges[i], edges[i + 1], dtype=np.uint64) for i in range(nblk)]
+
+
+ctx = gp.Context(local)
+ctx.set_allreduce(bench.make_allreduce_hook(torch, dist, dev))
+ctx.set_shard(rank * m_shard, world * m_shard)
+d = load(ctx, rank * m_shard, m_shard)
+assert d == m_shard
+sc_r, ev_r, _ = ctx.rfit(8, 10, power_iters=2, seed=42, want_loadings=False)
+cfg = gp.EigenSnpConfig(target_num_global_pcs=6, min_subset_size=1500, max_subset_size=3000, subset_factor=0.4)
+sc_e, ev_e, ld_e = ctx.eigensnp(blocks_for(d, nblk_shard), cfg)
+ctx.close()
+dist.barrier()
+out = {"world": world}
+if rank == 0:
+    full = gp.Context(local)
+    dfull = load(full, 0, world * m_shard)
+    sc0, ev0, _ = full.rfit(8, 10, power_iters=2, seed=42, want_loadings=False)
+    # the same blocks as the shards used, in global PcaSnpId numbering
+    blk = []
+    for r in range(world):
+        blk += [b + np.uint64(r * m_shard) for b in blocks_for(m_shard, nblk_shard)]
+    sc1, ev1, ld1 = full.eigensnp(blk, cfg)
+    out["rfit_ev_relerr"] = float(np.abs(ev_r / ev0 - 1).max())
+    out["rfit_angle"] = float(pca.subspace_angle(sc_r, sc0))
+    out["eigensnp_ev_relerr"] = float(np.abs(ev_e / ev1 - 1).max())
+    out["eigensnp_angle"] = float(pca.subspace_angle(sc_e, sc1))
+    out["eigensnp_loadings_angle_shard0"] = float(pca.subspace_angle(ld_e, ld1[:m_shard]))
+    out["ok"] = bool(out["rfit_ev_relerr"] < 1e-4 and out["rfit_angle"] < 1e-3 and out["eigensnp_ev_relerr"] < 1e-4
+                     and out["eigensnp_angle"] < 1e-3)
+    print(json.dumps(out), flush=True)
+dist.barrier()
+dist.destroy_process_group()
