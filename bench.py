@@ -118,32 +118,15 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------
 def synth_bed_device(torch, n_samples, n_snps, snp_offset, device):
     """Balding-Nichols genotypes generated on the device straight into PLINK .bed layout
-    (P = k+2 populations, ancestral AF ~ U(0.05,0.5), F_ST = 0.1, no missing calls).
-    The generator is re-seeded per 65,536-SNP chunk from (DATA_SEED, shard offset, chunk index)."""
+    (P = k+2 populations, ancestral AF ~ U(0.05,0.5), F_ST = 0.1, no missing calls) by the library's
+    counter-based generator (Philox keyed by (DATA_SEED, global SNP index, sample)): rows [a, b) of any shard are the
+    rows [a, b) of the whole matrix, whatever the number of GPUs."""
+    import genomic_pca_b200 as gp
     bps = (n_samples + 3) // 4
     out = torch.empty((n_snps, bps), dtype=torch.uint8, device=device)
-    pops = (torch.arange(n_samples, device=device) * N_POPS // n_samples)
-    chunk = int(min(65536, max(64, (1 << 27) // max(n_samples, 1))))   # ~128M genotypes of temporaries per chunk
-    fst = 0.1
-    pad = bps * 4 - n_samples
-    for c0 in range(0, n_snps, chunk):
-        c1 = min(c0 + chunk, n_snps)
-        g = torch.Generator(device=device)
-        g.manual_seed(DATA_SEED * 1000003 + (snp_offset // chunk) * 7919 + c0 // chunk)
-        m = c1 - c0
-        p_anc = 0.05 + 0.45 * torch.rand(m, 1, device=device, generator=g)
-        # population frequencies: normal approximation of the Balding-Nichols beta, clipped
-        z = torch.randn(m, N_POPS, device=device, generator=g)
-        p_pop = (p_anc + torch.sqrt(fst * p_anc * (1 - p_anc)) * z).clamp_(0.01, 0.99)
-        p = p_pop[:, pops]                                                   # [m, N]
-        a = (torch.rand(m, n_samples, device=device, generator=g) < p).to(torch.uint8)
-        a += (torch.rand(m, n_samples, device=device, generator=g) < p).to(torch.uint8)   # A1 dosage 0..2
-        code = torch.tensor([3, 2, 0], dtype=torch.uint8, device=device)[a.long()]        # count_a1: 0->11 1->10 2->00
-        if pad:
-            code = torch.cat([code, torch.zeros(m, pad, dtype=torch.uint8, device=device)], 1)
-        code = code.view(m, bps, 4)
-        out[c0:c1] = code[:, :, 0] | (code[:, :, 1] << 2) | (code[:, :, 2] << 4) | (code[:, :, 3] << 6)
-        del p, a, code, z, p_pop
+    gen = gp.Context(device.index or 0)
+    gen.synth_bed_device(out.data_ptr(), n_samples, n_snps, snp_offset, DATA_SEED, N_POPS, 0.1, 0.0)
+    gen.close()
     return out
 
 

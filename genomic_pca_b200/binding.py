@@ -85,6 +85,8 @@ _sig("gpca_launch_count", C.c_uint64, C.c_void_p)
 _sig("gpca_reset_launch_count", None, C.c_void_p)
 _sig("gpca_set_sketch_engine", C.c_int, C.c_void_p, C.c_int)
 _sig("gpca_set_batch_blocks", C.c_int, C.c_void_p, C.c_int)
+_sig("gpca_synth_bed_device", C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32,
+     C.c_double, C.c_double)
 _sig("gpca_sketch_stats", C.c_int, C.c_void_p, _f64p, _f64p, _u64p, C.c_int)
 _sig("gpca_sketch_kernel_ms", C.c_double, C.c_void_p)
 _sig("gpca_set_allreduce", C.c_int, C.c_void_p, ALLREDUCE_FN, C.c_void_p)
@@ -176,6 +178,12 @@ class Context:
     # -- configuration
     def set_sketch_engine(self, engine: int):
         self._chk(lib.gpca_set_sketch_engine(self._h, engine))
+
+    def synth_bed_device(self, dev_ptr: int, n_samples: int, n_snps: int, snp_offset: int = 0, seed: int = 20260101,
+                         n_pops: int = 22, fst: float = 0.1, missing_rate: float = 0.0):
+        """Benchmark input: structured synthetic genotypes written on the device in .bed layout (see gpca.h)."""
+        self._chk(lib.gpca_synth_bed_device(self._h, dev_ptr, n_samples, n_snps, snp_offset, seed, n_pops, fst,
+                                            missing_rate))
 
     def set_batch_blocks(self, on: bool):
         self._chk(lib.gpca_set_batch_blocks(self._h, 1 if on else 0))

@@ -119,6 +119,7 @@ static void reset_loaded(gpca_ctx* c) {
   c->ets_store.release();
   c->ess_store.release();
   c->es_cn.release();
+  c->es_pool.release();
 }
 
 // ---- ingest ------------------------------------------------------------------------------
@@ -659,6 +660,18 @@ extern "C" int gpca_ingest_bed(gpca_ctx* c, const uint8_t* host_payload, uint64_
             (unsigned long long)n_chunks, t_loop, ms_since(t_begin), t_stage_wait, t_enqueue, t_wait_cnt, t_conv, t_qc,
             t_compact, t_upload, ms_since(t_entry));
   return rc;
+}
+
+// ---- benchmark input ------------------------------------------------------------------------------------------
+extern "C" int gpca_synth_bed_device(gpca_ctx* c, uint8_t* dev_out, uint64_t n_samples, uint64_t n_snps,
+                                     uint64_t snp_offset, uint64_t seed, uint32_t n_pops, double fst,
+                                     double missing_rate) {
+  CHECK_CTX(c);
+  GPCA_CUDA_TRY(c, cudaSetDevice(c->device));
+  if (!dev_out || n_samples == 0) return fail(c, GPCA_ERR_INVALID, "synth: null output or no samples");
+  GPCA_TRY(launch_synth_bed(c, dev_out, n_samples, n_snps, snp_offset, seed, n_pops, (float)fst, (float)missing_rate));
+  GPCA_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return GPCA_OK;
 }
 
 // ---- accessor parity ---------------------------------------------------------------------------

@@ -49,6 +49,42 @@ struct DevBuf {
   }
 };
 
+// Call-scoped device temporaries that survive between calls: a driver asks for its buffers in the same order on
+// every call, so the k-th request reuses the k-th buffer (grown when needed) and no cudaMalloc / cudaFree remains on
+// the path of a repeated call.
+struct ScratchPool {
+  std::vector<DevBuf<uint8_t>*> bufs;
+  size_t next = 0;
+  ~ScratchPool() { release(); }
+  void reset() { next = 0; }
+  void release() {
+    for (auto* b : bufs) delete b;
+    bufs.clear();
+    next = 0;
+  }
+  cudaError_t get(size_t bytes, void** out) {
+    if (next >= bufs.size()) bufs.push_back(new DevBuf<uint8_t>());
+    DevBuf<uint8_t>* b = bufs[next++];
+    const cudaError_t e = b->alloc(bytes ? bytes : 1);
+    *out = b->p;
+    return e;
+  }
+};
+template <typename T>
+struct PoolBuf {       // DevBuf-shaped view of a pool buffer
+  ScratchPool* pool;
+  T* p = nullptr;
+  size_t n = 0;
+  explicit PoolBuf(ScratchPool* pl) : pool(pl) {}
+  cudaError_t alloc(size_t count) {
+    void* q = nullptr;
+    const cudaError_t e = pool->get(count * sizeof(T), &q);
+    p = static_cast<T*>(q);
+    n = (e == cudaSuccess) ? count : 0;
+    return e;
+  }
+};
+
 static inline size_t round_up(size_t x, size_t m) { return (x + m - 1) / m * m; }
 
 // Resident packed genotype matrix, dosage-coded 2-bit fields (0,1,2 = A1 dosage, 3 = missing),
@@ -92,6 +128,7 @@ struct gpca_ctx {
   uint4* h_cnt = nullptr;      // pinned landing buffer for the count records
   uint64_t h_cnt_cap = 0;
   DevBuf<uint8_t> es_store, et_store, ets_store, ess_store;   // EigenSNP slot-ordered / subset copies (kept across calls)
+  ScratchPool es_pool;                                        // EigenSNP call-scoped temporaries
   DevBuf<float> es_cn;                                        // EigenSNP condensed features
   DevBuf<uint8_t> ingest_stage[2];   // device staging of the raw payload chunks (gpca_ingest_bed)
   uint8_t* h_up = nullptr;     // pinned staging for the per-chunk compacted vectors (gpca_ingest_bed)

@@ -195,6 +195,7 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
     t_last = now;
   };
 
+  c->es_pool.reset();
   // ---- slot layout: blocks contiguous, each starting at a multiple of 64 fields ------------------------
   std::vector<uint64_t> off(n_blocks + 1, 0);
   std::vector<int64_t> id_of_slot;
@@ -245,8 +246,8 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
         mu_s[s] = mean * inv_s[s];
       }
     }
-  DevBuf<float> d_inv, d_mu;
-  DevBuf<int64_t> d_slot, d_sub;
+  PoolBuf<float> d_inv(&c->es_pool), d_mu(&c->es_pool);
+  PoolBuf<int64_t> d_slot(&c->es_pool), d_sub(&c->es_pool);
   GPCA_CUDA_TRY(c, d_inv.alloc(Ds));
   GPCA_CUDA_TRY(c, d_mu.alloc(Ds));
   GPCA_CUDA_TRY(c, d_slot.alloc(Ds));
@@ -300,7 +301,7 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
     max_m = std::max(max_m, m);
   }
   const uint64_t R = roff[n_blocks];
-  DevBuf<float> Ubuf, Yb, Zb;
+  PoolBuf<float> Ubuf(&c->es_pool), Yb(&c->es_pool), Zb(&c->es_pool);
   GPCA_CUDA_TRY(c, Ubuf.alloc(Ds * cpb_max));
   GPCA_CUDA_TRY(c, cudaMemsetAsync(Ubuf.p, 0, Ds * cpb_max * sizeof(float), c->stream));
   std::vector<uint32_t> lpv(n_blocks);
@@ -316,7 +317,7 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
                        lp_max <= 32 && cpb_max <= 32 && Ns >= 128 && N >= 128 && Ds >= 128 && Ds / 4 < (1ull << 31) &&
                        n_blocks < (1ull << 24);
   const uint64_t rgN = (N + 255) / 256, rgS = (Ns + 255) / 256;
-  DevBuf<SketchBatchBlock> d_blkY;     // operands indexed by the block's SNPs (K = block SNPs)
+  PoolBuf<SketchBatchBlock> d_blkY(&c->es_pool);     // operands indexed by the block's SNPs (K = block SNPs)
   std::vector<SketchBatchBlock> blkY;
   uint32_t img_stages_Y = 0;
   if (batched) {
@@ -383,12 +384,12 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
         it.out_off_hi = (uint32_t)(oo >> 32);
         it2.push_back(it);
       }
-    DevBuf<DenseProb> d_yprob, d_zprob;
-    DevBuf<uint32_t> d_streams, d_cp;
-    DevBuf<uint64_t> d_uoffs;
-    DevBuf<SketchBatchBlock> d_blkZ;
-    DevBuf<I8Item> d_it1, d_it2;
-    DevBuf<float> Yall, Zall;
+    PoolBuf<DenseProb> d_yprob(&c->es_pool), d_zprob(&c->es_pool);
+    PoolBuf<uint32_t> d_streams(&c->es_pool), d_cp(&c->es_pool);
+    PoolBuf<uint64_t> d_uoffs(&c->es_pool);
+    PoolBuf<SketchBatchBlock> d_blkZ(&c->es_pool);
+    PoolBuf<I8Item> d_it1(&c->es_pool), d_it2(&c->es_pool);
+    PoolBuf<float> Yall(&c->es_pool), Zall(&c->es_pool);
     GPCA_CUDA_TRY(c, d_yprob.alloc(n_blocks));
     GPCA_CUDA_TRY(c, d_zprob.alloc(n_blocks));
     GPCA_CUDA_TRY(c, d_streams.alloc(n_blocks));
@@ -513,7 +514,7 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
         it.out_off_hi = (uint32_t)(oo >> 32);
         itc.push_back(it);
       }
-    DevBuf<I8Item> d_itc;
+    PoolBuf<I8Item> d_itc(&c->es_pool);
     GPCA_CUDA_TRY(c, d_itc.alloc(itc.size()));
     GPCA_CUDA_TRY(c, cudaMemcpyAsync(d_itc.p, itc.data(), itc.size() * sizeof(I8Item), cudaMemcpyHostToDevice, c->stream));
     GPCA_CUDA_TRY(c, cudaMemcpyAsync(d_blkY.p, blkY.data(), n_blocks * sizeof(SketchBatchBlock), cudaMemcpyHostToDevice,
@@ -541,14 +542,14 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
   }
   stage("  condensed features");
   {
-    DevBuf<float> cmean, cinv;
+    PoolBuf<float> cmean(&c->es_pool), cinv(&c->es_pool);
     GPCA_CUDA_TRY(c, cmean.alloc(R));
     GPCA_CUDA_TRY(c, cinv.alloc(R));
     int nparts = (int)std::min<uint64_t>((N + 2047) / 2048, 64);
     if (nparts < 1) nparts = 1;
     const uint64_t rpc = (N + nparts - 1) / nparts;
     nparts = (int)((N + rpc - 1) / rpc);
-    DevBuf<double> part;
+    PoolBuf<double> part(&c->es_pool);
     GPCA_CUDA_TRY(c, part.alloc((size_t)nparts * R * 2));
     dim3 g1(nparts, (unsigned)((R + 255) / 256));
     col_moments_kernel<<<g1, 256, 0, c->stream>>>(Cn.p, N, (uint32_t)R, rpc, part.p);
@@ -576,7 +577,7 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
   GPCA_TRY(cublas_check(c, cublasSetMathMode(cb.h, CUBLAS_PEDANTIC_MATH), "setMathMode"));
   uint64_t R_total = R;
   if (c->allreduce) {   // total condensed rows over all shards (f64 scalar through the hook)
-    DevBuf<double> tmp;
+    PoolBuf<double> tmp(&c->es_pool);
     GPCA_CUDA_TRY(c, tmp.alloc(1));
     const double rr = (double)R;
     GPCA_CUDA_TRY(c, cudaMemcpyAsync(tmp.p, &rr, 8, cudaMemcpyHostToDevice, c->stream));
@@ -588,7 +589,7 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
   }
   const uint32_t lg = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(k_req + cfg->global_oversampling, R_total), N);
   const uint32_t k = std::min<uint32_t>(k_req, lg);
-  DevBuf<float> Om, Yg, Zg, V, L, Sc;
+  PoolBuf<float> Om(&c->es_pool), Yg(&c->es_pool), Zg(&c->es_pool), V(&c->es_pool), L(&c->es_pool), Sc(&c->es_pool);
   GPCA_CUDA_TRY(c, Om.alloc(R * lg));
   GPCA_CUDA_TRY(c, Yg.alloc(N * lg));
   GPCA_CUDA_TRY(c, Zg.alloc(R * lg));
@@ -597,7 +598,7 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
     for (uint64_t b = 0; b < n_blocks; ++b)
       for (uint32_t j = 0; j < cp[b]; ++j)
         keys[roff[b] + j] = (c->shard_offset + block_snp_ids[block_offsets[b]]) * 64ull + j;
-    DevBuf<uint64_t> d_keys;
+    PoolBuf<uint64_t> d_keys(&c->es_pool);
     GPCA_CUDA_TRY(c, d_keys.alloc(R));
     GPCA_CUDA_TRY(c, cudaMemcpyAsync(d_keys.p, keys.data(), R * 8, cudaMemcpyHostToDevice, c->stream));
     const uint64_t tot = R * lg;
@@ -639,7 +640,7 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
   SketchProblem f2;   // Sc = S^T L (rows = samples, K = slots)
   f2.G = Et; f2.G.avail = Et.pitch;
   f2.l = k; f2.ld = k; f2.f = d_inv.p; f2.e = d_mu.p; f2.a = nullptr; f2.b = nullptr; f2.ldo = k;
-  DevBuf<double> d_lam;
+  PoolBuf<double> d_lam(&c->es_pool);
   GPCA_CUDA_TRY(c, d_lam.alloc(64));
   const uint32_t passes = cfg->refine_pass_count;
   for (uint32_t pass = 0; pass < std::max<uint32_t>(passes, 1); ++pass) {
@@ -689,14 +690,14 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
   }
   // sign convention and the slot -> PcaSnpId scatter of the loadings happen on the device; the host receives the
   // final buffers only
-  DevBuf<int> d_flags;
+  PoolBuf<int> d_flags(&c->es_pool);
   GPCA_CUDA_TRY(c, d_flags.alloc(64));
   GPCA_TRY(launch_sign_flags(c, V.p, N, k, k, d_flags.p));
   if (scores) {
     GPCA_TRY(launch_apply_flags(c, V.p, N, k, k, d_flags.p, V.p, nullptr));
     GPCA_CUDA_TRY(c, cudaMemcpyAsync(scores, V.p, N * k * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   }
-  DevBuf<float> Lout;
+  PoolBuf<float> Lout(&c->es_pool);
   if (loadings) {
     GPCA_CUDA_TRY(c, Lout.alloc(D * k));
     GPCA_CUDA_TRY(c, cudaMemsetAsync(Lout.p, 0, D * k * sizeof(float), c->stream));

@@ -18,6 +18,10 @@ int launch_transpose(gpca_ctx* c, PackedMat gs, PackedMat gt);
 int launch_std_block(gpca_ctx* c, PackedMat gs, const float* d_mean, const float* d_sd, const uint64_t* d_ids,
                      uint64_t n_ids, const uint64_t* d_samp, uint64_t n_samp, float* d_out, int* d_missing_flag);
 
+// synthetic Balding-Nichols genotypes in .bed layout, keyed by (seed, global SNP index, sample): benchmark input
+int launch_synth_bed(gpca_ctx* c, uint8_t* d_out, uint64_t n_samples, uint64_t n_snps, uint64_t snp_offset, uint64_t seed,
+                     uint32_t n_pops, float fst, float missing_rate);
+
 // ---- dense helpers (kernels_dense.cu) ---------------------------------------------------
 // Gaussian test matrix: out[r][c] = N(0,1) keyed by (seed, stream, row0 + r, c); ld in floats
 int launch_gaussian(gpca_ctx* c, float* d_out, uint64_t rows, uint32_t cols, uint32_t ld, uint64_t seed,

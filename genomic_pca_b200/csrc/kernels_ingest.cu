@@ -6,6 +6,7 @@
 //   * pass 1 of perform_snp_qc_and_calc_std_params (src/prepare.rs:1232-1279): integer counts
 //   * get_standardized_snp_sample_block (src/prepare.rs:1884-2016)
 #include "kernels.cuh"
+#include "philox.cuh"
 
 #define KLAUNCH_CHECK(c)                                   \
   do {                                                     \
@@ -366,6 +367,77 @@ int launch_std_block(gpca_ctx* c, PackedMat gs, const float* d_mean, const float
   const int grid = (int)(blocks < (uint64_t)c->sm_count * 16 ? blocks : (uint64_t)c->sm_count * 16);
   std_block_kernel<<<grid, threads, 0, c->stream>>>(gs.p, gs.pitch, d_mean, d_sd, d_ids, n_ids, d_samp, n_samp, d_out,
                                                     d_missing_flag);
+  KLAUNCH_CHECK(c);
+  return GPCA_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Synthetic structured genotypes for benchmarks, written straight in PLINK .bed layout.
+// Counter-based: every value is a function of (seed, global SNP index, sample index) only, so any shard of SNPs
+// regenerates identically at any GPU count.  Balding-Nichols with the normal approximation of the beta:
+//   ancestral frequency p ~ U(0.05, 0.5), population frequency p_k = clamp(p + sqrt(F p (1-p)) z_k, 0.01, 0.99),
+//   genotype = Binomial(2, p_pop(sample)), optional missing calls (code 01) at `missing_rate`.
+// One thread per output byte (4 samples): two Philox calls -> 8 uniforms (2 per sample) + one for missingness.
+constexpr uint32_t SYNTH_STREAM_FREQ = 0x5EED0001u, SYNTH_STREAM_GENO = 0x5EED0002u, SYNTH_STREAM_MISS = 0x5EED0003u;
+
+__device__ __forceinline__ float synth_pop_freq(uint64_t seed, uint64_t snp, uint32_t pop, float fst) {
+  const Philox4 r = philox4x32_10((uint32_t)snp, (uint32_t)(snp >> 32), 0u, SYNTH_STREAM_FREQ, (uint32_t)seed,
+                                  (uint32_t)(seed >> 32));
+  const float p = 0.05f + 0.45f * ((float)(r.x >> 8) * (1.0f / 16777216.0f));
+  const float z = philox_normal(seed, SYNTH_STREAM_FREQ, snp, 4u + pop);   // columns 4.. : population deviates
+  const float q = p + sqrtf(fst * p * (1.0f - p)) * z;
+  return fminf(fmaxf(q, 0.01f), 0.99f);
+}
+
+__global__ void __launch_bounds__(256) synth_bed_kernel(uint8_t* __restrict__ out, uint64_t n_samples, uint64_t n_snps,
+                                                        uint64_t snp_offset, uint64_t seed, uint32_t n_pops, float fst,
+                                                        float missing_rate) {
+  const uint64_t bps = (n_samples + 3) / 4;
+  const uint64_t total = n_snps * bps;
+  for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < total;
+       t += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t j = t / bps, b = t - j * bps;
+    const uint64_t snp = snp_offset + j;
+    const Philox4 u0 = philox4x32_10((uint32_t)snp, (uint32_t)(snp >> 32), (uint32_t)(2 * b), SYNTH_STREAM_GENO,
+                                     (uint32_t)seed, (uint32_t)(seed >> 32));
+    const Philox4 u1 = philox4x32_10((uint32_t)snp, (uint32_t)(snp >> 32), (uint32_t)(2 * b + 1), SYNTH_STREAM_GENO,
+                                     (uint32_t)seed, (uint32_t)(seed >> 32));
+    const uint32_t u[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+    Philox4 um = {0, 0, 0, 0};
+    if (missing_rate > 0.0f)
+      um = philox4x32_10((uint32_t)snp, (uint32_t)(snp >> 32), (uint32_t)b, SYNTH_STREAM_MISS, (uint32_t)seed,
+                         (uint32_t)(seed >> 32));
+    const uint32_t umv[4] = {um.x, um.y, um.z, um.w};
+    uint32_t byte = 0;
+    uint32_t last_pop = 0xffffffffu;
+    float pf = 0.0f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint64_t i = 4 * b + q;
+      if (i >= n_samples) break;                       // pad fields stay 00 (as in a real .bed)
+      const uint32_t pop = (uint32_t)(i * n_pops / n_samples);
+      if (pop != last_pop) {
+        pf = synth_pop_freq(seed, snp, pop, fst);
+        last_pop = pop;
+      }
+      const uint32_t thr = (uint32_t)(pf * 16777216.0f);
+      const uint32_t dosage = ((u[2 * q] >> 8) < thr ? 1u : 0u) + ((u[2 * q + 1] >> 8) < thr ? 1u : 0u);
+      uint32_t code = dosage == 0 ? 3u : (dosage == 1 ? 2u : 0u);    // count_a1: 0 -> 11, 1 -> 10, 2 -> 00
+      if (missing_rate > 0.0f && (float)(umv[q] >> 8) * (1.0f / 16777216.0f) < missing_rate) code = 1u;
+      byte |= code << (2 * q);
+    }
+    out[t] = (uint8_t)byte;
+  }
+}
+
+int launch_synth_bed(gpca_ctx* c, uint8_t* d_out, uint64_t n_samples, uint64_t n_snps, uint64_t snp_offset, uint64_t seed,
+                     uint32_t n_pops, float fst, float missing_rate) {
+  const uint64_t total = n_snps * ((n_samples + 3) / 4);
+  if (total == 0) return GPCA_OK;
+  const uint64_t blocks = (total + 255) / 256;
+  const int grid = (int)(blocks < (uint64_t)c->sm_count * 16 ? blocks : (uint64_t)c->sm_count * 16);
+  synth_bed_kernel<<<grid, 256, 0, c->stream>>>(d_out, n_samples, n_snps, snp_offset, seed, n_pops ? n_pops : 1, fst,
+                                                missing_rate);
   KLAUNCH_CHECK(c);
   return GPCA_OK;
 }

@@ -191,6 +191,12 @@ int gpca_map_snps_to_ld_blocks(const char* const* snp_chrom, const int32_t* snp_
                                uint64_t n_blocks, int64_t* pca_pos, int64_t* block_of, uint64_t* n_pca,
                                uint64_t* n_blocks_out, uint64_t* sorted_block_order);
 
+/* Benchmark input (not on the reference's path): synthetic structured genotypes written on the
+ * device straight in .bed layout (n_snps rows of ceil(n_samples/4) bytes).  Counter-based (Philox keyed by seed, global
+ * SNP index = snp_offset + row, sample), so any shard of SNPs regenerates identically at any GPU count. */
+int gpca_synth_bed_device(gpca_ctx* ctx, uint8_t* dev_out, uint64_t n_samples, uint64_t n_snps, uint64_t snp_offset,
+                          uint64_t seed, uint32_t n_pops, double fst, double missing_rate);
+
 #ifdef __cplusplus
 }
 #endif

@@ -168,3 +168,37 @@ def test_pipelined_ingest_errors(gpu_ctx):
         gpu_ctx.ingest_bed(payload, 50, 40, vcf_maf=0.6)          # nothing can pass: maf <= 0.5
     with pytest.raises(gp.GpcaError):
         gpu_ctx.ingest_bed(payload, 50, 40, keep_samples=np.array([5, 2], dtype=np.int64))
+
+
+def test_synthetic_generator_is_counter_based(gpu_ctx):
+    """Benchmark input generator (gpca_synth_bed_device): deterministic, shard-consistent (any row range of the whole
+    matrix = the same rows generated as a shard), zero pad fields, missing rate and allele frequencies as requested."""
+    import torch
+    dev = torch.device("cuda", 0)
+    n, m = 1003, 5000                       # n % 4 = 3: one pad field per row
+    bps = (n + 3) // 4
+    full = torch.empty((m, bps), dtype=torch.uint8, device=dev)
+    gpu_ctx.synth_bed_device(full.data_ptr(), n, m, 0, seed=7, n_pops=5, fst=0.1, missing_rate=0.02)
+    again = torch.empty_like(full)
+    gpu_ctx.synth_bed_device(again.data_ptr(), n, m, 0, seed=7, n_pops=5, fst=0.1, missing_rate=0.02)
+    assert torch.equal(full, again)
+    shard = torch.empty((1200, bps), dtype=torch.uint8, device=dev)
+    gpu_ctx.synth_bed_device(shard.data_ptr(), n, 1200, 3100, seed=7, n_pops=5, fst=0.1, missing_rate=0.02)
+    assert torch.equal(shard, full[3100:4300])
+    other = torch.empty_like(full)
+    gpu_ctx.synth_bed_device(other.data_ptr(), n, m, 0, seed=8, n_pops=5, fst=0.1, missing_rate=0.02)
+    assert not torch.equal(other, full)
+    payload = full.cpu().numpy()
+    assert ((payload[:, -1] >> 6) == 0).all()                           # the pad field of every row is 00
+    d = bed.decode_count_a1(payload, n)                                # [m, n] int8, -127 = missing
+    miss = (d == -127).mean()
+    assert 0.015 < miss < 0.025
+    valid = np.where(d == -127, 0, d).sum(1) / (2.0 * (d != -127).sum(1))
+    assert 0.005 < valid.min() and valid.max() < 0.8 and 0.2 < valid.mean() < 0.35     # AF ~ U(0.05, 0.5) + drift
+    # population structure: between-population variance of allele frequencies ~ F_ST p (1 - p)
+    pops = np.arange(n) * 5 // n
+    g = np.where(d == -127, np.nan, d.astype(np.float64))
+    fpop = np.stack([np.nanmean(g[:, pops == k], axis=1) / 2 for k in range(5)], 1)
+    p = fpop.mean(1)
+    fst_hat = (fpop.var(1, ddof=1) / np.maximum(p * (1 - p), 1e-6)).mean()
+    assert 0.05 < fst_hat < 0.2
