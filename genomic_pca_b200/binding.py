@@ -85,6 +85,8 @@ _sig("gpca_launch_count", C.c_uint64, C.c_void_p)
 _sig("gpca_reset_launch_count", None, C.c_void_p)
 _sig("gpca_set_sketch_engine", C.c_int, C.c_void_p, C.c_int)
 _sig("gpca_set_batch_blocks", C.c_int, C.c_void_p, C.c_int)
+_sig("gpca_ingest_bed_file", C.c_int, C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p,
+     C.c_double, _u8p, _f32p, _f32p, _u8p, _u64p)
 _sig("gpca_synth_bed_device", C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32,
      C.c_double, C.c_double)
 _sig("gpca_sketch_stats", C.c_int, C.c_void_p, _f64p, _f64p, _u64p, C.c_int)
@@ -296,6 +298,22 @@ class Context:
                                       _ptr(code, _u8p), C.byref(n)))
         if not want_stats:
             return None, None, None, None, int(n.value)
+        return keep[:m].astype(bool), mean[:m], sd[:m], (None if code is None else code[:m]), int(n.value)
+
+    def ingest_bed_file(self, bed_path: str, n_samples: int, n_snps: int, qc: QcConfig | None = None,
+                        vcf_maf: float = 0.01, keep_samples=None):
+        """gpca_ingest_bed_file: the streaming ingest straight from a .bed file (magic and size checked)."""
+        ks = None if keep_samples is None else np.ascontiguousarray(keep_samples, dtype=np.int64)
+        m = int(n_snps)
+        keep = np.empty(max(m, 1), dtype=np.uint8)
+        mean = np.empty(max(m, 1), dtype=np.float32)
+        sd = np.empty(max(m, 1), dtype=np.float32)
+        code = np.empty(max(m, 1), dtype=np.uint8) if qc is not None else None
+        n = C.c_uint64(0)
+        self._chk(lib.gpca_ingest_bed_file(self._h, os.fsencode(bed_path), n_samples, n_snps,
+                                           None if ks is None else ks.ctypes.data, 0 if ks is None else ks.size,
+                                           None if qc is None else C.addressof(qc), float(vcf_maf), _ptr(keep, _u8p),
+                                           _ptr(mean, _f32p), _ptr(sd, _f32p), _ptr(code, _u8p), C.byref(n)))
         return keep[:m].astype(bool), mean[:m], sd[:m], (None if code is None else code[:m]), int(n.value)
 
     def snp_qc(self, cfg: QcConfig | None = None):

@@ -2,6 +2,9 @@
 // The PCA drivers (rfit, EigenSNP) live in drivers.cu.
 #include <algorithm>
 #include <chrono>
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <cmath>
 #include <cstring>
 #include <atomic>
@@ -64,6 +67,8 @@ extern "C" void gpca_destroy(gpca_ctx* c) {
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->h_cnt) cudaFreeHost(c->h_cnt);
   if (c->h_up) cudaFreeHost(c->h_up);
+  for (int i = 0; i < 2; ++i)
+    if (c->h_rd[i]) cudaFreeHost(c->h_rd[i]);
   gpca_destroy_cublas(c->cublas);
   delete c;
 }
@@ -417,14 +422,15 @@ extern "C" int gpca_set_pca_snps_mask(gpca_ctx* c, const uint8_t* keep, const fl
 // of the payload is the critical path; everything else hides behind it.  Replaces, for the data-preparation stage,
 // MicroarrayDataPreparer::prepare_data_for_eigen_snp_pca (src/prepare.rs:995-1098) / the VCF read + MAF filter
 // (src/vcf.rs:227-266, src/main.rs:176-212).
-extern "C" int gpca_ingest_bed(gpca_ctx* c, const uint8_t* host_payload, uint64_t n_in, uint64_t n_snps,
-                               const int64_t* keep_samples, uint64_t n_keep, const gpca_qc_cfg* cfg,
-                               double vcf_maf_threshold, uint8_t* keep_out, float* mean_out, float* sd_out,
-                               uint8_t* fail_code_out, uint64_t* n_pca_out) {
+// payload source: host memory (host_payload) or, when fd >= 0, a file read chunk by chunk into pinned buffers
+static int ingest_core(gpca_ctx* c, const uint8_t* host_payload, int fd, uint64_t file_offset, uint64_t n_in,
+                       uint64_t n_snps, const int64_t* keep_samples, uint64_t n_keep, const gpca_qc_cfg* cfg,
+                       double vcf_maf_threshold, uint8_t* keep_out, float* mean_out, float* sd_out,
+                       uint8_t* fail_code_out, uint64_t* n_pca_out) {
   CHECK_CTX(c);
   const auto t_entry = std::chrono::steady_clock::now();
   GPCA_CUDA_TRY(c, cudaSetDevice(c->device));
-  if (!host_payload && n_snps) return fail(c, GPCA_ERR_INVALID, "null payload");
+  if (!host_payload && fd < 0 && n_snps) return fail(c, GPCA_ERR_INVALID, "null payload");
   if (n_in == 0) return fail(c, GPCA_ERR_INVALID, "no samples");
   const uint64_t N = keep_samples ? n_keep : n_in;
   if (N == 0) return fail(c, GPCA_ERR_INVALID, "No samples passed QC.");  // prepare.rs:1010
@@ -476,10 +482,24 @@ extern "C" int gpca_ingest_bed(gpca_ctx* c, const uint8_t* host_payload, uint64_
   const size_t up_bytes = rows_per_chunk * 24;
   if (c->h_up_cap < 2 * up_bytes) {
     if (c->h_up) cudaFreeHost(c->h_up);
+  for (int i = 0; i < 2; ++i)
+    if (c->h_rd[i]) cudaFreeHost(c->h_rd[i]);
     c->h_up = nullptr;
     c->h_up_cap = 0;
     GPCA_CUDA_TRY(c, cudaMallocHost((void**)&c->h_up, 2 * up_bytes));
     c->h_up_cap = 2 * up_bytes;
+  }
+  if (fd >= 0) {   // two pinned read buffers, kept across calls
+    const size_t need = rows_per_chunk * in_pitch;
+    if (c->h_rd_cap < need) {
+      for (int i = 0; i < 2; ++i) {
+        if (c->h_rd[i]) cudaFreeHost(c->h_rd[i]);
+        c->h_rd[i] = nullptr;
+      }
+      c->h_rd_cap = 0;
+      for (int i = 0; i < 2; ++i) GPCA_CUDA_TRY(c, cudaMallocHost((void**)&c->h_rd[i], need));
+      c->h_rd_cap = need;
+    }
   }
   DevBuf<uint8_t>* stage = c->ingest_stage;   // kept across calls (no per-call cudaMalloc / cudaFree)
   cudaEvent_t stage_free[2] = {nullptr, nullptr}, up_free[2] = {nullptr, nullptr};
@@ -593,10 +613,26 @@ extern "C" int gpca_ingest_bed(gpca_ctx* c, const uint8_t* host_payload, uint64_
     const int buf = (int)(q & 1);
     const uint64_t r0 = q * rows_per_chunk, nr = std::min<uint64_t>(rows_per_chunk, M - r0);
     auto tq = now();
-    cudaError_t e = cudaEventSynchronize(stage_free[buf]);
+    cudaError_t e = cudaEventSynchronize(stage_free[buf]);   // (also: the copy out of pinned read buffer `buf` is done)
     t_stage_wait += ms_since(tq); tq = now();
+    const uint8_t* src = host_payload ? host_payload + r0 * in_pitch : nullptr;
+    if (e == cudaSuccess && fd >= 0) {
+      // the read of chunk q overlaps with the transfer and the device work of chunk q-1 (already enqueued)
+      size_t got = 0;
+      const size_t want = nr * in_pitch;
+      while (got < want) {
+        const ssize_t r = pread(fd, c->h_rd[buf] + got, want - got, (off_t)(file_offset + r0 * in_pitch + got));
+        if (r <= 0) break;
+        got += (size_t)r;
+      }
+      if (got != want) {
+        rc = fail(c, GPCA_ERR_INVALID, "ingest: short read from the .bed file");
+        break;
+      }
+      src = c->h_rd[buf];
+    }
     if (e == cudaSuccess)
-      e = cudaMemcpyAsync(stage[buf].p, host_payload + r0 * in_pitch, nr * in_pitch, cudaMemcpyHostToDevice, c->stream);
+      e = cudaMemcpyAsync(stage[buf].p, src, nr * in_pitch, cudaMemcpyHostToDevice, c->stream);
     if (e != cudaSuccess) {
       rc = fail(c, GPCA_ERR_CUDA, std::string("ingest H2D: ") + cudaGetErrorString(e));
       break;
@@ -659,6 +695,38 @@ extern "C" int gpca_ingest_bed(gpca_ctx* c, const uint8_t* host_payload, uint64_
             "convert %.1f  qc %.1f  compact %.1f  upload+build %.1f  (since entry %.1f)\n",
             (unsigned long long)n_chunks, t_loop, ms_since(t_begin), t_stage_wait, t_enqueue, t_wait_cnt, t_conv, t_qc,
             t_compact, t_upload, ms_since(t_entry));
+  return rc;
+}
+
+extern "C" int gpca_ingest_bed(gpca_ctx* c, const uint8_t* host_payload, uint64_t n_in, uint64_t n_snps,
+                               const int64_t* keep_samples, uint64_t n_keep, const gpca_qc_cfg* cfg,
+                               double vcf_maf_threshold, uint8_t* keep_out, float* mean_out, float* sd_out,
+                               uint8_t* fail_code_out, uint64_t* n_pca_out) {
+  return ingest_core(c, host_payload, -1, 0, n_in, n_snps, keep_samples, n_keep, cfg, vcf_maf_threshold, keep_out,
+                     mean_out, sd_out, fail_code_out, n_pca_out);
+}
+
+// Same pass straight from a PLINK .bed file: chunks are read into pinned buffers (never the whole file in host memory)
+// and the read of chunk q overlaps with the transfer / counting / QC of the chunks before it.
+extern "C" int gpca_ingest_bed_file(gpca_ctx* c, const char* bed_path, uint64_t n_in, uint64_t n_snps,
+                                    const int64_t* keep_samples, uint64_t n_keep, const gpca_qc_cfg* cfg,
+                                    double vcf_maf_threshold, uint8_t* keep_out, float* mean_out, float* sd_out,
+                                    uint8_t* fail_code_out, uint64_t* n_pca_out) {
+  CHECK_CTX(c);
+  if (!bed_path) return fail(c, GPCA_ERR_INVALID, "null path");
+  const int fd = open(bed_path, O_RDONLY);
+  if (fd < 0) return fail(c, GPCA_ERR_INVALID, std::string("Failed to open BED file '") + bed_path + "'");
+  uint8_t magic[3] = {0, 0, 0};
+  struct stat st;
+  int rc = GPCA_OK;
+  if (pread(fd, magic, 3, 0) != 3 || magic[0] != 0x6c || magic[1] != 0x1b || magic[2] != 0x01)
+    rc = fail(c, GPCA_ERR_INVALID, "not a SNP-major PLINK .bed (magic 6c 1b 01 expected)");
+  else if (fstat(fd, &st) != 0 || (uint64_t)st.st_size != 3 + ((n_in + 3) / 4) * n_snps)
+    rc = fail(c, GPCA_ERR_INVALID, "BED size does not match BIM/FAM");
+  else
+    rc = ingest_core(c, nullptr, fd, 3, n_in, n_snps, keep_samples, n_keep, cfg, vcf_maf_threshold, keep_out, mean_out,
+                     sd_out, fail_code_out, n_pca_out);
+  close(fd);
   return rc;
 }
 

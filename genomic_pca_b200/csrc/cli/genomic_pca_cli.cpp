@@ -437,19 +437,7 @@ int run_eigensnp(const Args& a) {
   }
   const uint64_t n_fam = iids.size(), m = sid.size();
   info("Initial metadata loaded: " + std::to_string(n_fam) + " samples, " + std::to_string(m) + " SNPs.");
-  // payload
-  std::vector<uint8_t> bed;
-  {
-    std::ifstream f(a.bed_file, std::ios::binary | std::ios::ate);
-    if (!f) die("Failed to open BED file '" + a.bed_file + "'");
-    const std::streamsize sz = f.tellg();
-    f.seekg(0);
-    bed.resize((size_t)sz);
-    f.read((char*)bed.data(), sz);
-  }
-  const uint64_t bps = (n_fam + 3) / 4;
-  if (bed.size() < 3 || bed[0] != 0x6c || bed[1] != 0x1b || bed[2] != 0x01) die("not a SNP-major PLINK .bed");
-  if (bed.size() != 3 + bps * m) die("BED size does not match BIM/FAM");
+  // (the payload is streamed from the file by gpca_ingest_bed_file below: never held in host memory as a whole)
   // sample QC (prepare.rs:1058-1096)
   std::vector<int64_t> keep_idx;
   bool use_keep = false;
@@ -468,11 +456,17 @@ int run_eigensnp(const Args& a) {
   }
   gpca_ctx* ctx = nullptr;
   if (gpca_init(&ctx, 0) != GPCA_OK) die("no sm_100 (B200) GPU available: this build has no CPU fallback");
-  check(ctx, gpca_load_bed(ctx, bed.data() + 3, n_fam, m, use_keep ? keep_idx.data() : nullptr, keep_idx.size()), "load_bed");
-  const uint64_t n = gpca_num_samples(ctx);
+  // load + SNP QC + resident matrices in one streaming pass over the file (prepare.rs:995-1098)
   std::vector<uint8_t> keep(m);
   std::vector<float> mean(m), sd(m);
-  check(ctx, gpca_snp_qc(ctx, &a.qc, keep.data(), mean.data(), sd.data(), nullptr), "snp_qc");
+  uint64_t n_qc_pass = 0;
+  {
+    const int rc = gpca_ingest_bed_file(ctx, a.bed_file.c_str(), n_fam, m, use_keep ? keep_idx.data() : nullptr,
+                                        keep_idx.size(), &a.qc, 0.0, keep.data(), mean.data(), sd.data(), nullptr,
+                                        &n_qc_pass);
+    if (rc != GPCA_OK) die(gpca_last_error(ctx));
+  }
+  const uint64_t n = gpca_num_samples(ctx);
   std::vector<uint64_t> qidx;
   for (uint64_t j = 0; j < m; ++j)
     if (keep[j]) qidx.push_back(j);
@@ -522,7 +516,9 @@ int run_eigensnp(const Args& a) {
       psd.push_back(sd[qidx[i]]);
       blocks[block_of[i]].push_back((uint64_t)pca_pos[i]);
     }
-  check(ctx, gpca_set_pca_snps(ctx, pca_orig.data(), n_pca, pmean.data(), psd.data()), "set_pca_snps");
+  // the ingest built the resident set from every SNP that passed QC; only when the LD blocks drop some of them is the
+  // set rebuilt from the mapped subset
+  if (n_pca != n_qc_pass) check(ctx, gpca_set_pca_snps(ctx, pca_orig.data(), n_pca, pmean.data(), psd.data()), "set_pca_snps");
   std::vector<uint64_t> offs(n_blk + 1, 0), flat;
   for (uint64_t b = 0; b < n_blk; ++b) {
     offs[b + 1] = offs[b] + blocks[b].size();

@@ -133,6 +133,8 @@ struct gpca_ctx {
   DevBuf<uint8_t> ingest_stage[2];   // device staging of the raw payload chunks (gpca_ingest_bed)
   uint8_t* h_up = nullptr;     // pinned staging for the per-chunk compacted vectors (gpca_ingest_bed)
   size_t h_up_cap = 0;
+  uint8_t* h_rd[2] = {nullptr, nullptr};   // pinned read buffers of gpca_ingest_bed_file
+  size_t h_rd_cap = 0;
   DevBuf<float> d_mean, d_sd;           // [D]
   DevBuf<float> d_inv_sd, d_mu_inv_sd;  // [D]  1/sd (0 if sd<1e-9) and mean/sd
   DevBuf<uint8_t> gs_store, gt_store;

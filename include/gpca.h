@@ -127,6 +127,13 @@ int gpca_set_pca_snps_mask(gpca_ctx* ctx, const uint8_t* keep, const float* mean
 int gpca_ingest_bed(gpca_ctx* ctx, const uint8_t* host_payload, uint64_t n_in_samples, uint64_t n_snps,
                     const int64_t* keep_samples, uint64_t n_keep, const gpca_qc_cfg* cfg, double vcf_maf_threshold,
                     uint8_t* keep, float* mean, float* sd, uint8_t* fail_code, uint64_t* n_pca_out);
+/* The same pass straight from a PLINK .bed file (magic and size are checked against n_in_samples x n_snps): chunks are
+ * read into pinned buffers and copied on, so the file is never held in host memory as a whole and the read overlaps
+ * with the transfer and the device work.  Replaces the IoService reader pool for this stage (src/prepare.rs:169-920,
+ * :923-993). */
+int gpca_ingest_bed_file(gpca_ctx* ctx, const char* bed_path, uint64_t n_in_samples, uint64_t n_snps,
+                         const int64_t* keep_samples, uint64_t n_keep, const gpca_qc_cfg* cfg, double vcf_maf_threshold,
+                         uint8_t* keep, float* mean, float* sd, uint8_t* fail_code, uint64_t* n_pca_out);
 
 /* ---- the accessor the GPU path makes unnecessary, kept for parity ---------------------- */
 /* get_standardized_snp_sample_block (src/prepare.rs:1839-2022): out[n_ids x n_samp] row-major

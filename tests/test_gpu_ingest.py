@@ -202,3 +202,31 @@ def test_synthetic_generator_is_counter_based(gpu_ctx):
     p = fpop.mean(1)
     fst_hat = (fpop.var(1, ddof=1) / np.maximum(p * (1 - p), 1e-6)).mean()
     assert 0.05 < fst_hat < 0.2
+
+
+def test_ingest_from_bed_file_equals_memory_ingest(gpu_ctx, tmp_path, monkeypatch):
+    """gpca_ingest_bed_file streams the .bed through pinned buffers: same masks / statistics / resident state as the
+    in-memory ingest; magic and size are checked."""
+    import genomic_pca_b200 as gp
+    monkeypatch.setenv("GPCA_INGEST_CHUNK_ROWS", "130")                    # 700 SNPs -> 6 chunks
+    n, m = 257, 700
+    g, payload = make_dataset(n, m, n_pops=3, seed=5, missing_rate=0.01)
+    cfg = gp.QcConfig(0.95, 0.02, 1e-6)
+    keep0, mean0, sd0, code0, d0 = gpu_ctx.ingest_bed(payload, n, m, qc=cfg)
+    r0 = gpu_ctx.rfit(3, 5, 2, seed=3)
+    path = tmp_path / "x.bed"
+    path.write_bytes(bytes([0x6C, 0x1B, 0x01]) + np.ascontiguousarray(payload).tobytes())
+    ctx2 = gp.Context(0)
+    keep1, mean1, sd1, code1, d1 = ctx2.ingest_bed_file(str(path), n, m, qc=cfg)
+    assert d1 == d0 and np.array_equal(keep1, keep0) and np.array_equal(code1, code0)
+    assert np.array_equal(mean1, mean0) and np.array_equal(sd1, sd0)
+    r1 = ctx2.rfit(3, 5, 2, seed=3)
+    assert np.array_equal(r1[1], r0[1]) and np.array_equal(r1[0], r0[0])
+    with pytest.raises(gp.GpcaError):
+        ctx2.ingest_bed_file(str(path), n, m + 1, qc=cfg)                  # size does not match
+    bad = tmp_path / "bad.bed"
+    bad.write_bytes(bytes([0x6C, 0x1B, 0x00]) + np.ascontiguousarray(payload).tobytes())
+    with pytest.raises(gp.GpcaError):
+        ctx2.ingest_bed_file(str(bad), n, m, qc=cfg)                       # individual-major / wrong magic
+    with pytest.raises(gp.GpcaError):
+        ctx2.ingest_bed_file(str(tmp_path / "missing.bed"), n, m, qc=cfg)
