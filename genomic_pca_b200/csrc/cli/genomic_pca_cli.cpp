@@ -24,6 +24,7 @@
 #include <set>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <unordered_set>
 #include <vector>
 
@@ -162,6 +163,40 @@ FILE* create_output(const std::string& prefix, const std::string& suffix) {
   return f;
 }
 
+// Rows are formatted by all host threads into per-block buffers (snprintf "%.6f" = the reference's `{:.6}`) and written
+// in order: at 1M rows x 20 columns the text formatting, not the file system, is the cost (main.rs:696-839).
+template <class RowFn>
+void write_rows_parallel(FILE* f, uint64_t n_rows, size_t bytes_per_row_hint, RowFn&& format_row) {
+  const uint64_t BLOCK = 1u << 16;     // rows per round of threads x chunk
+  unsigned hw = std::thread::hardware_concurrency();
+  if (hw == 0) hw = 4;
+  const uint64_t per_round = BLOCK * hw;
+  std::vector<std::string> bufs(hw);
+  for (uint64_t r0 = 0; r0 < n_rows; r0 += per_round) {
+    const uint64_t r1 = std::min<uint64_t>(n_rows, r0 + per_round);
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < hw; ++t) {
+      const uint64_t lo = r0 + (uint64_t)t * BLOCK, hi = std::min<uint64_t>(r1, lo + BLOCK);
+      bufs[t].clear();
+      if (lo >= hi) continue;
+      th.emplace_back([&, t, lo, hi] {
+        std::string& b = bufs[t];
+        b.reserve((size_t)(hi - lo) * bytes_per_row_hint);
+        for (uint64_t i = lo; i < hi; ++i) format_row(i, b);
+      });
+    }
+    for (auto& x : th) x.join();
+    for (unsigned t = 0; t < hw; ++t)
+      if (!bufs[t].empty()) fwrite(bufs[t].data(), 1, bufs[t].size(), f);
+  }
+}
+
+inline void append_f6(std::string& b, double v) {
+  char tmp[64];
+  const int len = snprintf(tmp, sizeof tmp, "\t%.6f", v);
+  b.append(tmp, (size_t)len);
+}
+
 template <class T>
 void write_pcs(const std::string& prefix, const std::string& suffix, const std::vector<std::string>& names,
                const T* scores, uint64_t n, uint32_t k) {
@@ -170,14 +205,14 @@ void write_pcs(const std::string& prefix, const std::string& suffix, const std::
   fputs("SampleID", f);
   for (uint32_t j = 1; j <= k; ++j) fprintf(f, "\tPC%u", j);
   fputc('\n', f);
-  for (uint64_t i = 0; i < names.size(); ++i) {
-    fputs(names[i].c_str(), f);
+  write_rows_parallel(f, names.size(), 16 + 12 * (size_t)k, [&](uint64_t i, std::string& b) {
+    b += names[i];
     for (uint32_t j = 0; j < k; ++j) {
-      if (i < n) fprintf(f, "\t%.6f", (double)scores[i * k + j]);
-      else fputs("\tNA", f);
+      if (i < n) append_f6(b, (double)scores[i * k + j]);
+      else b += "\tNA";
     }
-    fputc('\n', f);
-  }
+    b += '\n';
+  });
   fclose(f);
 }
 
@@ -545,12 +580,16 @@ int run_eigensnp(const Args& a) {
     fputs("VariantID\tChrom\tPos", f);
     for (uint32_t j = 1; j <= k_out; ++j) fprintf(f, "\tPC%u_loading", j);
     fputc('\n', f);
-    for (uint64_t i = 0; i < n_pca; ++i) {
+    write_rows_parallel(f, n_pca, 32 + 12 * (size_t)k_out, [&](uint64_t i, std::string& b) {
       const uint64_t o = pca_orig[i];
-      fprintf(f, "%s\t%s\t%llu", sid[o].c_str(), chrom[o].c_str(), (unsigned long long)(uint64_t)bp[o]);
-      for (uint32_t j = 0; j < k_out; ++j) fprintf(f, "\t%.6f", (double)loadings[i * k_out + j]);
-      fputc('\n', f);
-    }
+      b += sid[o];
+      b += '\t';
+      b += chrom[o];
+      b += '\t';
+      b += std::to_string((unsigned long long)(uint64_t)bp[o]);
+      for (uint32_t j = 0; j < k_out; ++j) append_f6(b, (double)loadings[i * k_out + j]);
+      b += '\n';
+    });
     fclose(f);
   }
   gpca_destroy(ctx);
