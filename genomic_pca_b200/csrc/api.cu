@@ -112,10 +112,8 @@ extern "C" int gpca_synchronize(gpca_ctx* c) {
 }
 
 static void reset_loaded(gpca_ctx* c) {
-  c->have_counts = false;
-  c->h_counts.clear();
+  c->have_counts = false;   // (the host vectors keep their storage: re-growing them would zero-fill hundreds of MB)
   c->D = 0;
-  c->pca_idx.clear();
   c->Gs = PackedMat();
   c->Gt = PackedMat();   // (the stores are kept: DevBuf::alloc reuses them when the next data set fits)
   c->any_missing = false;
@@ -519,12 +517,12 @@ static int ingest_core(gpca_ctx* c, const uint8_t* host_payload, int fd, uint64_
   }
   for (auto& e : cnt_ready) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
 
-  c->h_counts.resize(M * 4);
-  c->pca_idx.resize(M);
-  c->h_mean.resize(M);
-  c->h_sd.resize(M);
-  c->h_inv.resize(M);
-  c->h_muinv.resize(M);
+  if (c->h_counts.size() < M * 4) c->h_counts.resize(M * 4);
+  if (c->pca_idx.size() < M) c->pca_idx.resize(M);
+  if (c->h_mean.size() < M) c->h_mean.resize(M);
+  if (c->h_sd.size() < M) c->h_sd.resize(M);
+  if (c->h_inv.size() < M) c->h_inv.resize(M);
+  if (c->h_muinv.size() < M) c->h_muinv.resize(M);
   const uint32_t pad = (uint32_t)(c->raw_pitch * 4 - N);
   const uint32_t n32 = (uint32_t)N;
   uint64_t D = 0, nmiss_total = 0;
@@ -662,11 +660,7 @@ static int ingest_core(gpca_ctx* c, const uint8_t* host_payload, int fd, uint64_
     cleanup();
     return fail(c, GPCA_ERR_INVALID, "No SNPs passed all QC filters.");  // prepare.rs:1020
   }
-  c->pca_idx.resize(D);
-  c->h_mean.resize(D);
-  c->h_sd.resize(D);
-  c->h_inv.resize(D);
-  c->h_muinv.resize(D);
+  // (the host vectors stay at their capacity; only the first D entries are meaningful)
   c->any_missing = nmiss_total > 0;
   c->D = D;
   c->Gs.rows = D;
