@@ -63,71 +63,53 @@ int stats_begin_produce(gpca_ctx* c, unsigned int* amax) {
   return GPCA_OK;
 }
 
-// Gaussian matrix + its operand statistics.  CTA b owns a contiguous range of rows; thread (rr = tid / 8, cg = tid % 8)
-// walks rows rr, rr + 32, ... of the range and owns columns 4 cg .. 4 cg + 3.
+// Gaussian matrix + max |f o out| as a by-product (what the quantisation of the pass that consumes it needs).
+// Same element -> (row, column group) mapping as gaussian_kernel.
 __global__ void __launch_bounds__(256) gaussian_stats_kernel(float* __restrict__ out, uint64_t rows, uint32_t cols,
                                                              uint32_t ld, uint64_t seed, uint32_t stream, uint64_t row0,
-                                                             const float* __restrict__ f, const float* __restrict__ e,
-                                                             uint64_t rows_per_cta, double* __restrict__ cpart,
+                                                             const float* __restrict__ f,
                                                              unsigned int* __restrict__ amax_bits) {
-  __shared__ double red[32][33];
-  __shared__ float redm[8];
-  const int rr = threadIdx.x >> 3, cg = threadIdx.x & 7;
-  const uint64_t r_begin = blockIdx.x * rows_per_cta;
-  uint64_t r_end = r_begin + rows_per_cta;
-  if (r_end > rows) r_end = rows;
-  double cs[4] = {0.0, 0.0, 0.0, 0.0};
+  const uint32_t groups = (ld + 3) / 4;
+  const uint64_t total = rows * groups;
   float mx = 0.0f;
-  for (uint64_t r = r_begin + rr; r < r_end; r += 32) {
+  for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < total;
+       t += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t r = t / groups;
+    const uint32_t cg = (uint32_t)(t - r * groups);
     float z[4];
-    philox_normal4(seed, stream, row0 + r, (uint32_t)cg, z);
-    const float fr = f ? f[r] : 1.0f, er = e ? e[r] : 1.0f;
+    philox_normal4(seed, stream, row0 + r, cg, z);
+    const float fr = f ? f[r] : 1.0f;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const uint32_t cidx = cg * 4 + j;
       const float v = (cidx < cols) ? z[j] : 0.0f;
       if (cidx < ld) out[r * ld + cidx] = v;
-      cs[j] += (double)(v * er);
       mx = fmaxf(mx, fabsf(v * fr));
     }
   }
 #pragma unroll
-  for (int j = 0; j < 4; ++j) red[rr][cg * 4 + j] = cs[j];
-#pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  if ((threadIdx.x & 31) == 0) redm[threadIdx.x >> 5] = mx;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    double s = 0.0;
-    for (int q = 0; q < 32; ++q) s += red[q][threadIdx.x];
-    cpart[(uint64_t)blockIdx.x * 32 + threadIdx.x] = s;
-    if (threadIdx.x == 0) {
-      float m = 0.0f;
-      for (int q = 0; q < 8; ++q) m = fmaxf(m, redm[q]);
-      if (m > 0.0f && isfinite(m)) atomicMax(amax_bits, __float_as_uint(m));
-    }
-  }
+  if ((threadIdx.x & 31) == 0 && mx > 0.0f && isfinite(mx)) atomicMax(amax_bits, __float_as_uint(mx));
 }
 
 int launch_gaussian_with_stats(gpca_ctx* c, float* d_out, uint64_t rows, uint32_t cols, uint32_t ld, uint64_t seed,
                                uint32_t stream, uint64_t row0, const float* d_f, const float* d_e) {
+  (void)d_e;   // (the column sums are computed where the operand is quantised)
   c->stats_for = nullptr;
-  if (cols > 32 || ld > 32 || rows == 0 || getenv("GPCA_DEBUG_NO_GAUSS_STATS")) return launch_gaussian(c, d_out, rows, cols, ld, seed, stream, row0);
+  if (cols > 32 || ld > 32 || rows == 0 || getenv("GPCA_DEBUG_NO_GAUSS_STATS"))
+    return launch_gaussian(c, d_out, rows, cols, ld, seed, stream, row0);
   double* cpart = nullptr;
   unsigned int* amax = nullptr;
   GPCA_TRY(stats_buffer(c, &cpart, &amax));
   GPCA_TRY(stats_begin_produce(c, amax));
-  int nparts = c->sm_count * 8;
-  if (nparts > STATS_MAX_PARTS) nparts = STATS_MAX_PARTS;
-  uint64_t rows_per_cta = (rows + nparts - 1) / nparts;
-  rows_per_cta = round_up(rows_per_cta, 32);
-  nparts = (int)((rows + rows_per_cta - 1) / rows_per_cta);
-  gaussian_stats_kernel<<<nparts, 256, 0, c->stream>>>(d_out, rows, cols, ld, seed, stream, row0, d_f, d_e, rows_per_cta,
-                                                       cpart, amax);
+  const uint64_t total = rows * ((ld + 3) / 4);
+  const uint64_t blocks = (total + 255) / 256;
+  const int grid = (int)(blocks < (uint64_t)c->sm_count * 16 ? blocks : (uint64_t)c->sm_count * 16);
+  gaussian_stats_kernel<<<grid, 256, 0, c->stream>>>(d_out, rows, cols, ld, seed, stream, row0, d_f, amax);
   KLAUNCH_CHECK(c);
   c->stats_for = d_out;
   c->stats_l = cols;
-  c->stats_nparts = nparts;
+  c->stats_nparts = 1;
   return GPCA_OK;
 }
 

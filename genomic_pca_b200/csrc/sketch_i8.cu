@@ -69,8 +69,7 @@ struct I8Params {
   uint32_t ldo, l;
   float* partial;       // [ksplit][rows][32]
   const I8Item* items;  // item mode (batched per-LD-block passes): explicit work list, no split-K partials
-  double* stat_cpart;   // regular mode, direct output: per-warp partial column sums of b_r * out[r,:]  ([grid*8][32])
-  unsigned int* stat_amax;   // and max |a_r * out[r,:]| (float bits)
+  unsigned int* stat_amax;   // regular mode, direct output: max |a_r * out[r,:]| (float bits) as a by-product, or null
 };
 
 // What one work item covers.  Regular mode derives it from (k-split, row group); item mode reads it from the table.
@@ -275,8 +274,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) sketch_i8_kernel(const __grid_
     // under SWIZZLE_64B (64-byte rows)
     const uint32_t sw = (A_ROW_BYTES == 128) ? (uint32_t)(row_in_tile & 7) : (uint32_t)((row_in_tile >> 1) & 3);
     uint32_t it = 0, cit = 0, item_idx = 0;
-    double stat_sum = 0.0;     // this lane's column of the by-product statistics (see SketchProblem::emit_stats)
-    float stat_max = 0.0f;
+    float stat_max = 0.0f;     // by-product statistic of the output (see SketchProblem::emit_stats)
     for (uint32_t item = blockIdx.x; item < p.n_items; item += gridDim.x, ++item_idx) {
       const ItemInfo ii = decode_item<ITEMS>(p, item);
       const uint32_t n_ast = (ii.nst + HALVES - 1) / HALVES;
@@ -378,31 +376,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) sketch_i8_kernel(const __grid_
           }
         }
       }
-      if (!ITEMS && p.stat_cpart) {
-        // by-product statistics of the rows just written: column sums of b_r * out[r,:] (butterfly over the warp's 32
-        // rows, lane c ends with column c; fixed order, so deterministic) and max |a_r * out[r,:]|
-        float x[NL];
+      if (!ITEMS && p.stat_amax && live) {
+        // by-product statistic of the row just written: max |a_r * out[r,:]| (what the next pass's quantisation needs)
 #pragma unroll
-        for (int c = 0; c < NL; ++c) {
-          const float v = (live && (uint32_t)c < ii.l) ? __uint_as_float(hi[c]) : 0.0f;
-          stat_max = fmaxf(stat_max, fabsf(ar * v));
-          x[c] = br * v;
-        }
-#pragma unroll
-        for (int sft = 16; sft >= 1; sft >>= 1) {
-          const bool up = (lane & sft) != 0;
-#pragma unroll
-          for (int i = 0; i < sft; ++i) {
-            const float keep = up ? x[i + sft] : x[i];
-            const float give = up ? x[i] : x[i + sft];
-            x[i] = keep + __shfl_xor_sync(0xffffffffu, give, sft);
-          }
-        }
-        stat_sum += (double)x[0];
+        for (int c = 0; c < NL; ++c)
+          if ((uint32_t)c < ii.l) stat_max = fmaxf(stat_max, fabsf(ar * __uint_as_float(hi[c])));
       }
     }
-    if (!ITEMS && p.stat_cpart) {
-      p.stat_cpart[((size_t)blockIdx.x * 8 + (warp - 2)) * NL + lane] = stat_sum;
+    if (!ITEMS && p.stat_amax) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) stat_max = fmaxf(stat_max, __shfl_xor_sync(0xffffffffu, stat_max, o));
       if (lane == 0 && stat_max > 0.0f && isfinite(stat_max)) atomicMax(p.stat_amax, __float_as_uint(stat_max));
@@ -417,58 +398,41 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) sketch_i8_kernel(const __grid_
 }
 
 // ---- operand preparation ----------------------------------------------------------------------------------------
-// (column statistics reuse tc_colstats_kernel's twin below: cvec = e^T Bin in f64, amax = max |f o Bin|)
-__global__ void __launch_bounds__(256) i8_colstats_kernel(const float* __restrict__ bin, uint64_t K, uint32_t l,
-                                                          uint32_t ld, const float* __restrict__ f,
-                                                          const float* __restrict__ e, double* __restrict__ cpart,
-                                                          unsigned int* __restrict__ amax_bits) {
-  __shared__ double red[256];
-  __shared__ float redm[256];
+// max |f o Bin| (skipped when the producer of Bin already left it behind: SketchProblem::emit_stats)
+__global__ void __launch_bounds__(256) i8_amax_kernel(const float* __restrict__ bin, uint64_t K, uint32_t l, uint32_t ld,
+                                                      const float* __restrict__ f, unsigned int* __restrict__ amax_bits) {
   const int cidx = threadIdx.x & 31;
   const int rr = threadIdx.x >> 5;
   const bool c0 = (uint32_t)cidx < l;
-  double acc0 = 0.0;
   float mx = 0.0f;
   const uint64_t stride = (uint64_t)gridDim.x * 8;
   for (uint64_t k = (uint64_t)blockIdx.x * 8 + rr; k < K; k += 4 * stride) {
-    float x0[4], ek[4], fk[4];
+    float x0[4], fk[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const uint64_t kk = k + u * stride;
       const bool live = kk < K;
       x0[u] = (live && c0) ? bin[kk * ld + cidx] : 0.0f;
-      ek[u] = (live && e) ? e[kk] : 1.0f;
       fk[u] = (live && f) ? f[kk] : 1.0f;
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      acc0 += (double)(x0[u] * ek[u]);
-      mx = fmaxf(mx, fabsf(x0[u] * fk[u]));
-    }
+    for (int u = 0; u < 4; ++u) mx = fmaxf(mx, fabsf(x0[u] * fk[u]));
   }
-  red[threadIdx.x] = acc0;
-  redm[threadIdx.x] = mx;
-  __syncthreads();
-  if (rr == 0) {
-    double s0 = 0.0;
-    float m = 0.0f;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      s0 += red[q * 32 + cidx];
-      m = fmaxf(m, redm[q * 32 + cidx]);
-    }
-    cpart[(uint64_t)blockIdx.x * 32 + cidx] = s0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (cidx == 0 && m > 0.0f && isfinite(m)) atomicMax(amax_bits, __float_as_uint(m));
-  }
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (cidx == 0 && mx > 0.0f && isfinite(mx)) atomicMax(amax_bits, __float_as_uint(mx));
 }
 
-__global__ void __launch_bounds__(256) i8_finalize_stats_kernel(const double* __restrict__ cpart, int nparts,
-                                                                float* __restrict__ cvec,
-                                                                unsigned int* __restrict__ amax_bits,
-                                                                float* __restrict__ scales) {
-  // 8 groups of 32 lanes each sum every 8th partial; the 8 group sums are added in index order (deterministic)
+__global__ void i8_scale_kernel(unsigned int* __restrict__ amax_bits, float* __restrict__ scales) {
+  const float m = __uint_as_float(*amax_bits);
+  scales[0] = (m > 0.0f) ? 32512.0f / m : 0.0f;     // |q| <= 32512 = 127*256: both limbs fit s8
+  scales[1] = (m > 0.0f) ? m / 32512.0f : 0.0f;
+  *amax_bits = 0u;
+}
+
+// cvec = sum of the per-CTA partial column sums that prep_b_i8_kernel leaves (fixed order: deterministic)
+__global__ void __launch_bounds__(256) i8_cvec_kernel(const double* __restrict__ cpart, int nparts,
+                                                      float* __restrict__ cvec) {
   __shared__ double red[8][32];
   const int cidx = threadIdx.x & 31, grp = threadIdx.x >> 5;
   double s = 0.0;
@@ -480,12 +444,6 @@ __global__ void __launch_bounds__(256) i8_finalize_stats_kernel(const double* __
 #pragma unroll
     for (int g = 0; g < 8; ++g) t += red[g][cidx];
     cvec[cidx] = (float)t;
-    if (cidx == 0) {
-      const float m = __uint_as_float(*amax_bits);
-      scales[0] = (m > 0.0f) ? 32512.0f / m : 0.0f;     // |q| <= 32512 = 127*256: both limbs fit s8
-      scales[1] = (m > 0.0f) ? m / 32512.0f : 0.0f;
-      *amax_bits = 0u;
-    }
   }
 }
 
@@ -493,11 +451,16 @@ __global__ void __launch_bounds__(256) i8_finalize_stats_kernel(const double* __
 // c = s/4, b = s%4 (the order in which expand_word_u8 lays the fields into TMEM columns/bytes).
 // Element (slot s, column n in 0..63; n < 32: hi limb of logical column n, n >= 32: lo limb of column n-32) lives at
 //   g*32*64 + (s/16)*(64*16) + (n/8)*128 + (n%8)*16 + (s%16)       (UMMA K-major core matrices, no swizzle)
+// The column sums e^T Bin come along for free: a thread always meets the same column n (strides are multiples of 32),
+// sums e_k * Bin[k, n] over its chunks in f64, and the CTA leaves one partial per column.
 __global__ void __launch_bounds__(256) prep_b_i8_kernel(const float* __restrict__ bin, uint64_t K, uint64_t Kpad,
                                                         uint32_t l, uint32_t ld, const float* __restrict__ f,
-                                                        const float* __restrict__ scales, int8_t* __restrict__ img) {
+                                                        const float* __restrict__ e, const float* __restrict__ scales,
+                                                        int8_t* __restrict__ img, double* __restrict__ cpart) {
+  __shared__ double sred[8][NL];
   const uint64_t total = (Kpad / 16) * NL;   // one thread per (16-slot K chunk, logical column): writes 16 B hi + 16 B lo
   const float qs = scales[0];
+  double csum = 0.0;
   for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < total;
        t += (uint64_t)gridDim.x * blockDim.x) {
     const uint32_t n = (uint32_t)(t % NL);
@@ -513,6 +476,7 @@ __global__ void __launch_bounds__(256) prep_b_i8_kernel(const float* __restrict_
       int q = 0;
       if (k < K && n < l) {
         float v = bin[k * ld + n];
+        csum += (double)(e ? v * e[k] : v);
         if (f) v *= f[k];
         q = __float2int_rn(v * qs);
         q = max(-32512, min(32512, q));
@@ -525,18 +489,24 @@ __global__ void __launch_bounds__(256) prep_b_i8_kernel(const float* __restrict_
     *reinterpret_cast<uint4*>(img + base + (n >> 3) * 128 + (n & 7) * 16) = *reinterpret_cast<const uint4*>(vhi);
     *reinterpret_cast<uint4*>(img + base + ((n + 32) >> 3) * 128 + (n & 7) * 16) = *reinterpret_cast<const uint4*>(vlo);
   }
+  sred[threadIdx.x >> 5][threadIdx.x & 31] = csum;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sred[w][threadIdx.x];
+    cpart[(uint64_t)blockIdx.x * NL + threadIdx.x] = t;
+  }
 }
 
 __global__ void __launch_bounds__(256) sketch_reduce_i8_kernel(const float* __restrict__ partial, int nsplit,
                                                                uint64_t rows, const float* __restrict__ a,
                                                                const float* __restrict__ b,
                                                                const float* __restrict__ cvec, float* __restrict__ out,
-                                                               uint32_t ldo, uint32_t l, double* __restrict__ stat_cpart,
+                                                               uint32_t ldo, uint32_t l,
                                                                unsigned int* __restrict__ stat_amax) {
-  __shared__ double sred[8][NL];
   const uint64_t total = rows * NL;
-  double ssum = 0.0;     // by-product statistics of the output (a thread always meets the same column: strides are
-  float smax = 0.0f;     // multiples of 32)
+  float smax = 0.0f;     // by-product statistic of the output: max |a_r * out[r,:]|
   for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < total;
        t += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t r = t / NL;
@@ -547,22 +517,12 @@ __global__ void __launch_bounds__(256) sketch_reduce_i8_kernel(const float* __re
     const float ar = a ? a[r] : 1.0f, br = b ? b[r] : 1.0f;
     const float v = ar * s - br * cvec[cc];
     out[r * ldo + cc] = v;
-    ssum += (double)(br * v);
     smax = fmaxf(smax, fabsf(ar * v));
   }
-  if (stat_cpart) {
-    const int cidx = threadIdx.x & 31, w = threadIdx.x >> 5;
-    sred[w][cidx] = ssum;
+  if (stat_amax) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) smax = fmaxf(smax, __shfl_xor_sync(0xffffffffu, smax, o));
-    if (cidx == 0 && smax > 0.0f && isfinite(smax)) atomicMax(stat_amax, __float_as_uint(smax));
-    __syncthreads();
-    if (w == 0) {
-      double t = 0.0;
-#pragma unroll
-      for (int g = 0; g < 8; ++g) t += sred[g][cidx];
-      stat_cpart[(uint64_t)blockIdx.x * NL + cidx] = t;
-    }
+    if ((threadIdx.x & 31) == 0 && smax > 0.0f && isfinite(smax)) atomicMax(stat_amax, __float_as_uint(smax));
   }
 }
 
@@ -738,28 +698,30 @@ int launch_sketch_i8(gpca_ctx* c, const SketchProblem& p) {
   double* st_cpart = nullptr;
   unsigned int* st_amax = nullptr;
   GPCA_TRY(stats_buffer(c, &st_cpart, &st_amax));
-  bool have_stats = p.use_stats && c->stats_for == p.Bin && c->stats_l == p.l && c->stats_nparts > 0;
+  bool have_stats = p.use_stats && c->stats_for == p.Bin && c->stats_l == p.l;
   if (getenv("GPCA_DEBUG_NO_USE_STATS")) have_stats = false;
   if (have_stats) {
-    // the producer of Bin left the partial column sums and the max-abs behind (SketchProblem::emit_stats)
-    i8_finalize_stats_kernel<<<1, 256, 0, c->stream>>>(st_cpart, c->stats_nparts, cvec, st_amax, scales);
-    c->launches++;
-    GPCA_CUDA_TRY(c, cudaGetLastError());
-    c->stats_pending = false;    // (the finalize kernel resets the max-abs word)
+    // the producer of Bin left max |f o Bin| behind (SketchProblem::emit_stats): one sweep over the operand saved
+    i8_scale_kernel<<<1, 1, 0, c->stream>>>(st_amax, scales);
+    c->stats_pending = false;    // (the scale kernel resets the max-abs word)
   } else {
-    i8_colstats_kernel<<<nb, 256, 0, c->stream>>>(p.Bin, K, p.l, p.ld, p.f, p.e, c->ws_cpart.p, amax);
+    i8_amax_kernel<<<nb, 256, 0, c->stream>>>(p.Bin, K, p.l, p.ld, p.f, amax);
     c->launches++;
     GPCA_CUDA_TRY(c, cudaGetLastError());
-    i8_finalize_stats_kernel<<<1, 256, 0, c->stream>>>(c->ws_cpart.p, nb, cvec, amax, scales);
-    c->launches++;
-    GPCA_CUDA_TRY(c, cudaGetLastError());
+    i8_scale_kernel<<<1, 1, 0, c->stream>>>(amax, scales);
   }
+  c->launches++;
+  GPCA_CUDA_TRY(c, cudaGetLastError());
   c->stats_for = nullptr;
   {
     const uint64_t total = (Kpad / 16) * NL;
     const uint64_t blocks = (total + 255) / 256;
     const int grid = (int)(blocks < (uint64_t)c->sm_count * 8 ? blocks : (uint64_t)c->sm_count * 8);
-    prep_b_i8_kernel<<<grid, 256, 0, c->stream>>>(p.Bin, K, Kpad, p.l, p.ld, p.f, scales, img);
+    GPCA_CUDA_TRY(c, c->ws_cpart.alloc((size_t)grid * 64));
+    prep_b_i8_kernel<<<grid, 256, 0, c->stream>>>(p.Bin, K, Kpad, p.l, p.ld, p.f, p.e, scales, img, c->ws_cpart.p);
+    c->launches++;
+    GPCA_CUDA_TRY(c, cudaGetLastError());
+    i8_cvec_kernel<<<1, 256, 0, c->stream>>>(c->ws_cpart.p, grid, cvec);
     c->launches++;
     GPCA_CUDA_TRY(c, cudaGetLastError());
   }
@@ -801,8 +763,7 @@ int launch_sketch_i8(gpca_ctx* c, const SketchProblem& p) {
   tp.items = nullptr;
   const bool emit = p.emit_stats && !c->any_missing && !getenv("GPCA_DEBUG_NO_EMIT_STATS");
   if (emit) GPCA_TRY(stats_begin_produce(c, st_amax));
-  tp.stat_cpart = (emit && ksplit == 1) ? st_cpart : nullptr;
-  tp.stat_amax = st_amax;
+  tp.stat_amax = (emit && ksplit == 1) ? st_amax : nullptr;
   if (ksplit > 1) {
     GPCA_CUDA_TRY(c, c->ws_partial.alloc((size_t)ksplit * rows * NL));
     tp.partial = c->ws_partial.p;
@@ -836,12 +797,9 @@ int launch_sketch_i8(gpca_ctx* c, const SketchProblem& p) {
     const uint64_t blocks = (total + 255) / 256;
     const int g2 = (int)(blocks < (uint64_t)c->sm_count * 8 ? blocks : (uint64_t)c->sm_count * 8);
     sketch_reduce_i8_kernel<<<g2, 256, 0, c->stream>>>(tp.partial, (int)ksplit, rows, p.a, p.b, cvec, p.out, p.ldo, p.l,
-                                                       emit ? st_cpart : nullptr, st_amax);
+                                                       emit ? st_amax : nullptr);
     c->launches++;
     GPCA_CUDA_TRY(c, cudaGetLastError());
-    if (emit) c->stats_nparts = g2;
-  } else if (emit) {
-    c->stats_nparts = (int)grid * 8;
   }
   if (emit) {
     c->stats_for = p.out;
@@ -915,7 +873,6 @@ int launch_sketch_i8_batch(gpca_ctx* c, const SketchBatch& sb) {
   tp.l = 0;
   tp.partial = nullptr;
   tp.items = sb.d_items;
-  tp.stat_cpart = nullptr;
   tp.stat_amax = nullptr;
   CUtensorMap tmap;
   {
