@@ -458,36 +458,60 @@ __global__ void __launch_bounds__(256) prep_b_i8_kernel(const float* __restrict_
                                                         const float* __restrict__ e, const float* __restrict__ scales,
                                                         int8_t* __restrict__ img, double* __restrict__ cpart) {
   __shared__ double sred[8][NL];
-  const uint64_t total = (Kpad / 16) * NL;   // one thread per (16-slot K chunk, logical column): writes 16 B hi + 16 B lo
+  const uint64_t n_chunks = Kpad / 16;       // one warp per 16-slot K chunk, lane = logical column
   const float qs = scales[0];
+  const uint32_t n = threadIdx.x & 31u;
+  const bool col_live = n < l;
+  // per-k scale / weight vectors can be fetched 16 bytes at a time when they are 16-byte aligned (chunks start at
+  // multiples of 16 rows)
+  const bool vec_ok = (!f || (reinterpret_cast<uintptr_t>(f) & 15) == 0) && (!e || (reinterpret_cast<uintptr_t>(e) & 15) == 0);
   double csum = 0.0;
-  for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < total;
-       t += (uint64_t)gridDim.x * blockDim.x) {
-    const uint32_t n = (uint32_t)(t % NL);
-    const uint64_t kc = t / NL;               // global 16-slot chunk
+  const uint64_t warp0 = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t kc = warp0; kc < n_chunks; kc += nwarps) {
+    const uint64_t kb = kc * 16;               // the chunk's 16 operand rows are kb .. kb+15, in the order below
+    uint32_t whi[4] = {0, 0, 0, 0}, wlo[4] = {0, 0, 0, 0};
+    if (kb < K && col_live) {
+      const float* src = bin + kb * ld + n;
+      float fq[16], ek[16];
+      if (kb + 16 <= K && vec_ok) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 fv = f ? __ldg(reinterpret_cast<const float4*>(f + kb) + i) : make_float4(1.f, 1.f, 1.f, 1.f);
+          const float4 ev = e ? __ldg(reinterpret_cast<const float4*>(e + kb) + i) : make_float4(1.f, 1.f, 1.f, 1.f);
+          fq[4 * i + 0] = fv.x * qs; fq[4 * i + 1] = fv.y * qs; fq[4 * i + 2] = fv.z * qs; fq[4 * i + 3] = fv.w * qs;
+          ek[4 * i + 0] = ev.x; ek[4 * i + 1] = ev.y; ek[4 * i + 2] = ev.z; ek[4 * i + 3] = ev.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const bool live = kb + i < K;
+          fq[i] = live ? (f ? f[kb + i] : 1.0f) * qs : 0.0f;
+          ek[i] = live ? (e ? e[kb + i] : 1.0f) : 0.0f;
+        }
+      }
+      float part = 0.0f;                       // fp32 inside the chunk, f64 across chunks
+#pragma unroll
+      for (int ss = 0; ss < 16; ++ss) {
+        // K-slot ss of the chunk holds operand row (ss >> 2) + 4 * (ss & 3) -- the order in which expand_word_u8 lays
+        // the fields into the TMEM columns / bytes
+        const int kl = (ss >> 2) + 4 * (ss & 3);
+        const float v = (kb + kl < K) ? src[(size_t)kl * ld] : 0.0f;
+        part = fmaf(v, ek[kl], part);
+        int q = __float2int_rn(v * fq[kl]);
+        q = max(-32512, min(32512, q));
+        const int h = (q + 128) >> 8;          // floor((q+128)/256): lo = q - 256 h in [-128, 127]
+        const int lo = q - 256 * h;
+        whi[ss >> 2] |= (uint32_t)(h & 0xff) << (8 * (ss & 3));
+        wlo[ss >> 2] |= (uint32_t)(lo & 0xff) << (8 * (ss & 3));
+      }
+      csum += (double)part;
+    }
     const uint64_t g = kc >> 1;
     const uint32_t half_idx = (uint32_t)(kc & 1);
-    __align__(16) int8_t vhi[16], vlo[16];
-#pragma unroll
-    for (int ss = 0; ss < 16; ++ss) {
-      const int s = half_idx * 16 + ss;
-      const int cc = s >> 2, bb = s & 3;
-      const uint64_t k = g * 32 + 16 * (cc >> 2) + (cc & 3) + 4 * bb;
-      int q = 0;
-      if (k < K && n < l) {
-        float v = bin[k * ld + n];
-        csum += (double)(e ? v * e[k] : v);
-        if (f) v *= f[k];
-        q = __float2int_rn(v * qs);
-        q = max(-32512, min(32512, q));
-      }
-      const int h = (q + 128) >> 8;           // floor((q+128)/256): lo = q - 256 h in [-128, 127]
-      vhi[ss] = (int8_t)h;
-      vlo[ss] = (int8_t)(q - 256 * h);
-    }
     const uint64_t base = g * 32 * NM + (uint64_t)half_idx * (NM * 16);
-    *reinterpret_cast<uint4*>(img + base + (n >> 3) * 128 + (n & 7) * 16) = *reinterpret_cast<const uint4*>(vhi);
-    *reinterpret_cast<uint4*>(img + base + ((n + 32) >> 3) * 128 + (n & 7) * 16) = *reinterpret_cast<const uint4*>(vlo);
+    *reinterpret_cast<uint4*>(img + base + (n >> 3) * 128 + (n & 7) * 16) = make_uint4(whi[0], whi[1], whi[2], whi[3]);
+    *reinterpret_cast<uint4*>(img + base + ((n + 32) >> 3) * 128 + (n & 7) * 16) = make_uint4(wlo[0], wlo[1], wlo[2], wlo[3]);
   }
   sred[threadIdx.x >> 5][threadIdx.x & 31] = csum;
   __syncthreads();
