@@ -46,15 +46,23 @@ __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarr
 constexpr uint64_t L2_EVICT_FIRST = 0x12F0000000000000ull;   // createpolicy encodings (as used by CUTLASS TMA::CacheHintSm90)
 constexpr uint64_t L2_EVICT_LAST = 0x14F0000000000000ull;
 constexpr uint64_t L2_EVICT_NORMAL = 0x1000000000000000ull;
+// L2 policies of the two streams (overridable for A/B builds): packed genotypes are read once, the operand image is
+// shared by the CTAs that work on the same K range
+#ifndef GPCA_A_L2_HINT
+#define GPCA_A_L2_HINT L2_EVICT_NORMAL
+#endif
+#ifndef GPCA_B_L2_HINT
+#define GPCA_B_L2_HINT L2_EVICT_LAST
+#endif
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
-      "l"(map), "r"(bar), "r"(x), "r"(y), "l"(L2_EVICT_NORMAL)
+      "l"(map), "r"(bar), "r"(x), "r"(y), "l"(GPCA_A_L2_HINT)
       : "memory");
 }
 __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar), "l"(L2_EVICT_LAST)
+               "l"(src), "r"(bytes), "r"(bar), "l"(GPCA_B_L2_HINT)
                : "memory");
 }
 
