@@ -357,9 +357,9 @@ def run_ours(args, rank, world):
 
 
 # DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum, bytes per launch) of sketch_i8_kernel at config 3 from the
-# committed ncu capture (profiles/r1_ncu_full_sketch_i8_kernel_c3_final.csv): sample side 7.28 + 0.04 GB, snp side
-# 6.50 + 1.20 GB; one rfit runs 4 sample-side and 3 snp-side launches.  Only valid for the default workload.
-TRAFFIC_NCU = {2: (4 * 7.326e9 + 3 * 7.704e9) / 7}
+# committed ncu capture (profiles/r1_ncu_full_sketch_i8_kernel_c3_final.csv): sample side 7.335 + 0.050 GB, snp side
+# 6.497 + 1.245 GB; one rfit runs 4 sample-side and 3 snp-side launches.  Only valid for the default workload.
+TRAFFIC_NCU = {2: (4 * 7.385e9 + 3 * 7.7425e9) / 7}
 
 
 def ukb_shard_supplement(torch, gp, dev, pk, rank=0, world=1, dist=None):
