@@ -36,9 +36,19 @@ struct ACfg {
   static constexpr int STAGE_BYTES = 2 * TILE_BYTES;     // RT tiles
   static constexpr int SA = 65536 / STAGE_BYTES;         // 64 KB of A stages either way
 };
-constexpr int NUM_THREADS = 384;   // 12 warps: a multiple of 4, so that warp & 3 is the TMEM lane quarter of the warp for every co-resident CTA (warp 11 idles)
+constexpr int NUM_THREADS = 384;   // 12 warps: a multiple of 4, so that warp & 3 is the TMEM lane quarter of the warp for every co-resident CTA (warp 3 idles)
 constexpr int NL = 32;             // logical columns
 constexpr int NM = 64;             // MMA N = hi | lo limbs
+#ifndef GPCA_I8_REGSPLIT
+#define GPCA_I8_REGSPLIT 1
+#endif
+#if GPCA_I8_REGSPLIT
+#define REG_DEC() asm volatile("setmaxnreg.dec.sync.aligned.u32 32;")
+#define REG_INC() asm volatile("setmaxnreg.inc.sync.aligned.u32 104;")
+#else
+#define REG_DEC()
+#define REG_INC()
+#endif
 constexpr int SB = 3, SLOTS = 2;   // a TMEM slot holds a chunk pair (128 fields) of both row tiles
 constexpr int A_RING_BYTES = 65536;
 constexpr int B_STAGE_BYTES = STAGE_FIELDS * NM;       // 1 byte per element
@@ -181,8 +191,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) sketch_i8_kernel(const __grid_
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  if (warp == 0 || warp == 10) {
-    // ---- producers: warp 0 = packed genotype tiles (TMA 2-D), warp 10 = B image (1-D bulk copies)
+  // warpgroup 0 = the two producers, the MMA issuer and an idle warp; warpgroups 1 and 2 = the expanders of row tile
+  // 0 and 1.  Registers move from the first to the others (setmaxnreg works per warpgroup; every warp of the group
+  // executes it, at the top of its own role branch).
+  if (warp == 0 || warp == 2) {
+    REG_DEC();
+    // ---- producers: warp 0 = packed genotype tiles (TMA 2-D), warp 2 = B image (1-D bulk copies)
     const bool is_a = (warp == 0);
     uint32_t it = 0;
     for (uint32_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
@@ -219,6 +233,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) sketch_i8_kernel(const __grid_
       }
     }
   } else if (warp == 1) {
+    REG_DEC();
     // ---- MMA issuer: D = s32, A = u8 (TMEM), B = s8 (smem, K-major, no swizzle), M = 128, N = 64, K = 32
     const uint32_t idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(NM >> 3) << 17) | (8u << 24);
     // B descriptor: LBO = 64 rows * 16 B = 1024 B (next 16-wide K chunk), SBO = 128 B (next 8 columns), version 1
@@ -250,7 +265,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) sketch_i8_kernel(const __grid_
               for (int i = 0; i < 4; ++i) {      // 4 MMAs of K = 32 cover the 128 fields of the pair
                 const uint32_t baddr = bsm + (uint32_t)((q * 2 + i) * (32 * NM));
                 const uint64_t bdesc = ((uint64_t)desc_hi << 32) | (uint64_t)(desc_lo_const | ((baddr >> 4) & 0x3FFFu));
+#ifndef GPCA_KO_MMA
                 tc_mma_ts_i8(d_t, a_t + 8 * i, bdesc, idesc, acc_flag | (uint32_t)i);
+#else
+                if (i == 0 && GPCA_KO_MMA) tc_mma_ts_i8(d_t, a_t + 8 * i, bdesc, idesc, acc_flag | (uint32_t)i);
+#endif
               }
             }
             tc_commit(bar_tempty(slot));
@@ -264,9 +283,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) sketch_i8_kernel(const __grid_
       if (elect_one()) tc_commit(bar_accfull);
       __syncwarp();
     }
-  } else if (warp >= 2 && warp < 10) {
+  } else if (warp == 3) {
+    REG_DEC();
+  } else {
+    REG_INC();
     // ---- expanders + epilogue
-    const int tile = (warp - 2) >> 2;
+    const int tile = (warp - 4) >> 2;
     const int quarter = warp & 3;
     const int row_in_tile = quarter * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
@@ -299,6 +321,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) sketch_i8_kernel(const __grid_
             const int slot = cit % SLOTS;
             const uint32_t sph = (cit / SLOTS) & 1u;
             uint32_t r0[16], r1[16];
+#ifdef GPCA_KO_EXPAND
+#pragma unroll
+            for (int z = 0; z < 16; ++z) { r0[z] = (&v[q].x)[z & 3] + z; r1[z] = (&v[q + 1].x)[z & 3] + z; }
+#else
             expand_word_u8(v[q].x, r0 + 0);
             expand_word_u8(v[q].y, r0 + 4);
             expand_word_u8(v[q].z, r0 + 8);
@@ -307,12 +333,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) sketch_i8_kernel(const __grid_
             expand_word_u8(v[q + 1].y, r1 + 4);
             expand_word_u8(v[q + 1].z, r1 + 8);
             expand_word_u8(v[q + 1].w, r1 + 12);
+#endif
             mbar_wait(bar_tempty(slot), sph ^ 1u);      // the MMAs that read this slot have completed
             tc_fence_after();
             const uint32_t ta = tmem_base + lane_addr + A_COL0 + (slot * RT + tile) * 32;
+#ifndef GPCA_KO_STTM
             tmem_st16(ta, r0);
             tmem_st16(ta + 16, r1);
             tc_wait_st();
+#else
+            asm volatile("" :: "r"(r0[0] ^ r0[1] ^ r0[2] ^ r0[3] ^ r0[4] ^ r0[5] ^ r0[6] ^ r0[7] ^ r0[8] ^ r0[9] ^ r0[10] ^ r0[11] ^ r0[12] ^ r0[13] ^ r0[14] ^ r0[15] ^ r1[0] ^ r1[1] ^ r1[2] ^ r1[3] ^ r1[4] ^ r1[5] ^ r1[6] ^ r1[7] ^ r1[8] ^ r1[9] ^ r1[10] ^ r1[11] ^ r1[12] ^ r1[13] ^ r1[14] ^ r1[15]), "r"(ta));
+#endif
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tfull(slot));
