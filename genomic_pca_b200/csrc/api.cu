@@ -802,7 +802,7 @@ int timed_sketch_batch(gpca_ctx* c, const SketchBatch& sb) {
 int sketch_snp_side(gpca_ctx* c, const float* dev_in, float* dev_out, uint32_t l, uint32_t ld_in, uint32_t ld_out,
                     bool emit_stats) {
   SketchProblem p;
-  p.emit_stats = emit_stats && ld_out == l;   // the consumer reads the output with the same row stride
+  p.emit_stats = emit_stats;   // (the statistic is the max-abs over the l logical columns: independent of the stride)
   p.G = c->Gs;
   p.Bin = dev_in;
   p.l = l;

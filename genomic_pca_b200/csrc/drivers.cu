@@ -106,31 +106,34 @@ extern "C" int gpca_rfit(gpca_ctx* c, uint32_t k, uint32_t oversample, uint32_t 
   Small s;
   GPCA_TRY(get_small(c, s));
   DevBuf<float>&Y = c->drv_a, &Z = c->drv_b, &R = c->drv_c, &Sc = c->drv_d;
+  // rows of the D x l matrices are padded to a multiple of 8 floats: the snp-side sketch writes a row per thread, and
+  // 32-byte aligned rows let it use 32-byte stores (one full sector per store instead of four partial writes)
+  const uint32_t ldz = (l + 7u) & ~7u;
   GPCA_CUDA_TRY(c, Y.alloc(N * l));
-  GPCA_CUDA_TRY(c, Z.alloc(D * l));
+  GPCA_CUDA_TRY(c, Z.alloc(D * ldz));
 
   // Y = S^T Omega
   // (every D x l operand of a sample-side pass arrives with its column statistics: from the generator here, from the
   //  epilogue of the snp-side pass below -- one sweep over a D x l matrix saved per pass)
-  GPCA_TRY(launch_gaussian_with_stats(c, Z.p, D, l, l, seed, STREAM_RFIT_OMEGA, c->shard_offset, c->d_inv_sd.p,
+  GPCA_TRY(launch_gaussian_with_stats(c, Z.p, D, l, ldz, seed, STREAM_RFIT_OMEGA, c->shard_offset, c->d_inv_sd.p,
                                       c->d_mu_inv_sd.p));
-  GPCA_TRY(sketch_sample_side(c, Z.p, Y.p, l, l, l, true));
+  GPCA_TRY(sketch_sample_side(c, Z.p, Y.p, l, ldz, l, true));
   for (uint32_t it = 0; it < power_iters; ++it) {
     GPCA_TRY(orthonormalize(c, Y.p, N, l, l, false, s));
-    GPCA_TRY(sketch_snp_side(c, Y.p, Z.p, l, l, l, true));   // Z = S Q
+    GPCA_TRY(sketch_snp_side(c, Y.p, Z.p, l, l, ldz, true));   // Z = S Q
     // (range(S^T Z) does not depend on a column transform of Z; the snp-side basis is left unnormalised
     //  between the two half-steps, the sample side is re-orthonormalised every iteration)
-    GPCA_TRY(sketch_sample_side(c, Z.p, Y.p, l, l, l, true));   // Y = S^T Z
+    GPCA_TRY(sketch_sample_side(c, Z.p, Y.p, l, ldz, l, true));   // Y = S^T Z
   }
   GPCA_TRY(orthonormalize(c, Y.p, N, l, l, false, s));
-  GPCA_TRY(sketch_snp_side(c, Y.p, Z.p, l, l, l, true));  // B = S Q   [D x l]
+  GPCA_TRY(sketch_snp_side(c, Y.p, Z.p, l, l, ldz, true));  // B = S Q   [D x l]
   // B^T B = Q^T (S^T B): the l x l matrix whose eigen-decomposition gives the singular values and the right factor of
   // B comes from the sample-side sketch of B -- which is also all that the scores need (scores = S^T B V_b / s).  The
   // D-row Gram of B and, when the rotation is not asked for, every D x l by l x k product disappear; on several GPUs
   // S^T B is already summed over the shards, so no further exchange is needed.
   DevBuf<float>& Y2 = c->drv_e;
   GPCA_CUDA_TRY(c, Y2.alloc(N * l));
-  GPCA_TRY(sketch_sample_side(c, Z.p, Y2.p, l, l, l, true));    // S^T B   [N x l]
+  GPCA_TRY(sketch_sample_side(c, Z.p, Y2.p, l, ldz, l, true));    // S^T B   [N x l]
   GPCA_TRY(launch_cross_gram(c, Y.p, Y2.p, N, l, l, s.G));
   GPCA_TRY(launch_jacobi_eigh(c, s.G, l, s.evals, s.evecs));
   GPCA_TRY(launch_rotation_transform(c, s.evals, s.evecs, l, k, s.T, true));
@@ -138,7 +141,7 @@ extern "C" int gpca_rfit(gpca_ctx* c, uint32_t k, uint32_t oversample, uint32_t 
   GPCA_TRY(launch_apply_right(c, Y2.p, N, l, l, s.T, k, Sc.p, k));   // transform(): scores = S^T rotation
   if (loadings) {
     GPCA_CUDA_TRY(c, R.alloc(D * k));
-    GPCA_TRY(launch_apply_right(c, Z.p, D, l, l, s.T, k, R.p, k));   // rotation = B V_b / s  [D x k]
+    GPCA_TRY(launch_apply_right(c, Z.p, D, l, ldz, s.T, k, R.p, k));   // rotation = B V_b / s  [D x k]
   }
 
   // sign convention, f32 -> f64 conversion and the flips of the loadings all happen on the device;

@@ -6,7 +6,7 @@
 //     B = the dense operand quantised to 16-bit fixed point (relative to max|f o B|) and split into two
 //         signed 8-bit limbs q = 256*hi + lo, hi/lo in [-128,127]  ->  N = 64 columns (hi | lo) per MMA,
 //   with tcgen05.mma.kind::i8 (u8 x s8 -> s32, A from TMEM, B from smem).  The epilogue recombines
-//   (256*D_hi + D_lo) in f64, rescales, and applies the rank-one standardisation correction.
+//   256*D_hi + D_lo (int -> fp32, one FMA), rescales, and applies the rank-one standardisation correction.
 //
 // Why a second tensor engine: in the fp16 engine the ALU pipe (LOP3, 64 lanes/clk/SM) is the
 // co-limiter with HBM -- 9 ALU ops per 16 genotypes; here it is 4, TMEM store traffic is halved, a TMEM slot holds
@@ -48,6 +48,18 @@ constexpr int NM = 64;             // MMA N = hi | lo limbs
 #else
 #define REG_DEC()
 #define REG_INC()
+#endif
+// GPCA_I8_PROF: per-warp cycle accounting of the waits (printed by CTA 0 at the end of every launch; measurement builds only)
+#ifdef GPCA_I8_PROF
+#include <cstdio>
+#define PROF_DECL(...) uint32_t __VA_ARGS__
+#define PROF_T(x) const uint32_t x = prof_clock()
+#define PROF_ADD(acc, t0) acc += prof_clock() - (t0)
+__device__ __forceinline__ uint32_t prof_clock() { uint32_t c; asm volatile("mov.u32 %0, %%clock;" : "=r"(c)); return c; }
+#else
+#define PROF_DECL(...)
+#define PROF_T(x)
+#define PROF_ADD(acc, t0)
 #endif
 constexpr int SB = 3, SLOTS = 2;   // a TMEM slot holds a chunk pair (128 fields) of both row tiles
 constexpr int A_RING_BYTES = 65536;
@@ -199,6 +211,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) sketch_i8_kernel(const __grid_
     // ---- producers: warp 0 = packed genotype tiles (TMA 2-D), warp 2 = B image (1-D bulk copies)
     const bool is_a = (warp == 0);
     uint32_t it = 0;
+    PROF_DECL(c_wait = 0);
+    PROF_T(t_role);
     for (uint32_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const ItemInfo ii = decode_item<ITEMS>(p, item);
       const int row0 = (int)ii.row0;
@@ -207,7 +221,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) sketch_i8_kernel(const __grid_
         for (uint32_t a = 0; a < n_ast; ++a, ++it) {
           const int s = it % SA;
           const uint32_t ph = (it / SA) & 1u;
+          PROF_T(t0);
           mbar_wait(bar_aempty(s), ph ^ 1u);
+          PROF_ADD(c_wait, t0);
           if (elect_one()) {
             const uint32_t sbase = a_ring + s * A_STAGE_BYTES;
             mbar_arrive_expect_tx(bar_afull(s), A_STAGE_BYTES);
@@ -222,7 +238,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) sketch_i8_kernel(const __grid_
         for (uint32_t st = 0; st < ii.nst; ++st, ++it) {
           const int s = it % SB;
           const uint32_t ph = (it / SB) & 1u;
+          PROF_T(t0);
           mbar_wait(bar_bempty(s), ph ^ 1u);
+          PROF_ADD(c_wait, t0);
           if (elect_one()) {
             mbar_arrive_expect_tx(bar_bfull(s), B_STAGE_BYTES);
             bulk_load_1d(b_ring + s * B_STAGE_BYTES, p.bimg + (size_t)(ii.img_st0 + st) * B_STAGE_BYTES, B_STAGE_BYTES,
@@ -232,6 +250,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) sketch_i8_kernel(const __grid_
         }
       }
     }
+#ifdef GPCA_I8_PROF
+    if (blockIdx.x == 0 && lane == 0)
+      printf("PROF %s producer: total %u wait_empty %u\n", is_a ? "A" : "B", prof_clock() - t_role, c_wait);
+#endif
   } else if (warp == 1) {
     REG_DEC();
     // ---- MMA issuer: D = s32, A = u8 (TMEM), B = s8 (smem, K-major, no swizzle), M = 128, N = 64, K = 32
@@ -240,21 +262,29 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) sketch_i8_kernel(const __grid_
     const uint32_t desc_lo_const = (uint32_t)(1024 >> 4) << 16;
     const uint32_t desc_hi = (uint32_t)(128 >> 4) | (1u << 14);
     uint32_t it = 0, cit = 0, item_idx = 0;
+    PROF_DECL(c_acc = 0, c_bfull = 0, c_tfull = 0);
+    PROF_T(t_role);
     for (uint32_t item = blockIdx.x; item < p.n_items; item += gridDim.x, ++item_idx) {
       const uint32_t nst = decode_item<ITEMS>(p, item).nst;
+      PROF_T(t_a);
       mbar_wait(bar_accempty, (item_idx & 1u) ^ 1u);
+      PROF_ADD(c_acc, t_a);
       tc_fence_after();
       uint32_t acc_flag = 0;
       for (uint32_t st = 0; st < nst; ++st, ++it) {
         const int s = it % SB;
         const uint32_t ph = (it / SB) & 1u;
+        PROF_T(t_b);
         mbar_wait(bar_bfull(s), ph);
+        PROF_ADD(c_bfull, t_b);
         const uint32_t bsm = b_ring + s * B_STAGE_BYTES;
 #pragma unroll
         for (int q = 0; q < CHUNKS; q += 2, ++cit) {
           const int slot = cit % SLOTS;
           const uint32_t sph = (cit / SLOTS) & 1u;
+          PROF_T(t_t);
           mbar_wait(bar_tfull(slot), sph);
+          PROF_ADD(c_tfull, t_t);
           tc_fence_after();
           if (elect_one()) {
 #pragma unroll
@@ -283,6 +313,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) sketch_i8_kernel(const __grid_
       if (elect_one()) tc_commit(bar_accfull);
       __syncwarp();
     }
+#ifdef GPCA_I8_PROF
+    if (blockIdx.x == 0 && lane == 0)
+      printf("PROF issuer: total %u wait_accempty %u wait_bfull %u wait_tfull %u pairs %u\n", prof_clock() - t_role, c_acc,
+             c_bfull, c_tfull, cit);
+#endif
   } else if (warp == 3) {
     REG_DEC();
   } else {
@@ -297,13 +332,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) sketch_i8_kernel(const __grid_
     const uint32_t sw = (A_ROW_BYTES == 128) ? (uint32_t)(row_in_tile & 7) : (uint32_t)((row_in_tile >> 1) & 3);
     uint32_t it = 0, cit = 0, item_idx = 0;
     float stat_max = 0.0f;     // by-product statistic of the output (see SketchProblem::emit_stats)
+    PROF_DECL(c_afull = 0, c_tempty = 0, c_st = 0, c_epi = 0, c_accfull = 0, c_ldtm = 0, c_ab = 0);
+    PROF_T(t_role);
     for (uint32_t item = blockIdx.x; item < p.n_items; item += gridDim.x, ++item_idx) {
       const ItemInfo ii = decode_item<ITEMS>(p, item);
       const uint32_t n_ast = (ii.nst + HALVES - 1) / HALVES;
       for (uint32_t a = 0; a < n_ast; ++a, ++it) {
         const int s = it % SA;
         const uint32_t ph = (it / SA) & 1u;
+        PROF_T(t_af);
         mbar_wait(bar_afull(s), ph);
+        PROF_ADD(c_afull, t_af);
         const uint32_t arow = a_ring + s * A_STAGE_BYTES + tile * A_TILE_BYTES + row_in_tile * A_ROW_BYTES;
 #pragma unroll
         for (int h = 0; h < HALVES; ++h) {
@@ -334,13 +373,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) sketch_i8_kernel(const __grid_
             expand_word_u8(v[q + 1].z, r1 + 8);
             expand_word_u8(v[q + 1].w, r1 + 12);
 #endif
+            PROF_T(t_te);
             mbar_wait(bar_tempty(slot), sph ^ 1u);      // the MMAs that read this slot have completed
+            PROF_ADD(c_tempty, t_te);
             tc_fence_after();
+            PROF_T(t_st);
             const uint32_t ta = tmem_base + lane_addr + A_COL0 + (slot * RT + tile) * 32;
 #ifndef GPCA_KO_STTM
             tmem_st16(ta, r0);
             tmem_st16(ta + 16, r1);
             tc_wait_st();
+            PROF_ADD(c_st, t_st);
 #else
             asm volatile("" :: "r"(r0[0] ^ r0[1] ^ r0[2] ^ r0[3] ^ r0[4] ^ r0[5] ^ r0[6] ^ r0[7] ^ r0[8] ^ r0[9] ^ r0[10] ^ r0[11] ^ r0[12] ^ r0[13] ^ r0[14] ^ r0[15] ^ r1[0] ^ r1[1] ^ r1[2] ^ r1[3] ^ r1[4] ^ r1[5] ^ r1[6] ^ r1[7] ^ r1[8] ^ r1[9] ^ r1[10] ^ r1[11] ^ r1[12] ^ r1[13] ^ r1[14] ^ r1[15]), "r"(ta));
 #endif
@@ -356,6 +399,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) sketch_i8_kernel(const __grid_
         if (lane == 0) mbar_arrive(bar_aempty(s));
       }
       // ---- epilogue
+      PROF_T(t_epi);
       const uint32_t lrow = (uint32_t)(tile * 128 + row_in_tile);
       const bool live = lrow < ii.nrows;
       const uint64_t r = (uint64_t)ii.row0 + lrow;
@@ -364,46 +408,92 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) sketch_i8_kernel(const __grid_
         if (p.a) ar = __ldg(p.a + r);
         if (p.b) br = __ldg(p.b + r);
       }
+      PROF_T(t_acf);
       mbar_wait(bar_accfull, item_idx & 1u);
+      PROF_ADD(c_accfull, t_acf);
       tc_fence_after();
       uint32_t hi[32], lo[32];
+      PROF_T(t_ld);
       tmem_ld32(tmem_base + lane_addr + D_COL0 + tile * NM, hi);
       tmem_ld32(tmem_base + lane_addr + D_COL0 + tile * NM + 32, lo);
       tc_wait_ld();
+      PROF_ADD(c_ldtm, t_ld);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_accempty);
+#ifdef GPCA_I8_PROF
+      {   // time until the per-row factors (loaded before the accumulator wait) are in registers
+        PROF_T(t_ab);
+        asm volatile("" :: "f"(ar), "f"(br));
+        float dummy = ar + br;
+        asm volatile("" : "+f"(dummy));
+        PROF_ADD(c_ab, t_ab);
+      }
+#endif
       if (live) {
-        const double scale = ITEMS ? (double)__ldg(p.scales + 2 * ii.blk + 1) : (double)s_scale;
+        // 256 * D_hi + D_lo, rescaled: two int -> fp32 conversions and one FMA per element.  (An earlier version formed
+        // the 40-bit integer and went through f64 -- 3 quarter-rate conversions/DMULs per element, a third of the
+        // expander warps' time when an item is only 10 stages long.)  The fp32 rounding (2^-24 relative) is far below
+        // the 2^-15 quantisation of the operand and the expression is fixed, so results stay bit-reproducible.
+        const float sc_lo = ITEMS ? __ldg(p.scales + 2 * ii.blk + 1) : s_scale;
+        const float sc_hi = 256.0f * sc_lo;
         if (!ITEMS && p.partial) {
           float* dst = p.partial + ((uint64_t)ii.ks * p.rows + r) * NL;
 #pragma unroll
           for (int c = 0; c < NL; c += 4) {
             float4 o;
-            o.x = (float)((double)((long long)(int)hi[c + 0] * 256 + (int)lo[c + 0]) * scale);
-            o.y = (float)((double)((long long)(int)hi[c + 1] * 256 + (int)lo[c + 1]) * scale);
-            o.z = (float)((double)((long long)(int)hi[c + 2] * 256 + (int)lo[c + 2]) * scale);
-            o.w = (float)((double)((long long)(int)hi[c + 3] * 256 + (int)lo[c + 3]) * scale);
+            o.x = fmaf((float)(int)hi[c + 0], sc_hi, (float)(int)lo[c + 0] * sc_lo);
+            o.y = fmaf((float)(int)hi[c + 1], sc_hi, (float)(int)lo[c + 1] * sc_lo);
+            o.z = fmaf((float)(int)hi[c + 2], sc_hi, (float)(int)lo[c + 2] * sc_lo);
+            o.w = fmaf((float)(int)hi[c + 3], sc_hi, (float)(int)lo[c + 3] * sc_lo);
             *reinterpret_cast<float4*>(dst + c) = o;
           }
         } else {
           float* dst = p.out + ii.out_off + (uint64_t)lrow * p.ldo;
           const float* cv = ITEMS ? p.cvec + (size_t)ii.blk * NL : cv_s;
-          const bool vec2 = (p.ldo & 1u) == 0 && (reinterpret_cast<uintptr_t>(p.out + ii.out_off) & 7) == 0;
+          // widest aligned store the row stride allows.  A thread owns a whole output row, so every store instruction
+          // of a warp touches 32 different lines: with 32-byte stores (st.global.v8, sm_100) each one writes a full
+          // sector and a padded 32-float row takes 4 instructions (the pad columns inside the row stride get zeros).
+          const uintptr_t obase = reinterpret_cast<uintptr_t>(p.out + ii.out_off);
+#ifdef GPCA_I8_NO_V8
+          const bool vec8 = false;
+#else
+          const bool vec8 = (p.ldo & 7u) == 0 && (obase & 31) == 0;
+#endif
+          const bool vec4 = (p.ldo & 3u) == 0 && (obase & 15) == 0;
+          const bool vec2 = (p.ldo & 1u) == 0 && (obase & 7) == 0;
 #pragma unroll
-          for (int c = 0; c < NL; c += 2) {
-            const float c0 = ITEMS ? __ldg(cv + c) : cv[c];
-            const float c1 = ITEMS ? __ldg(cv + c + 1) : cv[c + 1];
-            const float v0 = ar * (float)((double)((long long)(int)hi[c] * 256 + (int)lo[c]) * scale) - br * c0;
-            const float v1 = ar * (float)((double)((long long)(int)hi[c + 1] * 256 + (int)lo[c + 1]) * scale) - br * c1;
-            if (vec2 && (uint32_t)c + 1 < ii.l) {
-              *reinterpret_cast<float2*>(dst + c) = make_float2(v0, v1);
-            } else {
-              if ((uint32_t)c < ii.l) dst[c] = v0;
-              if ((uint32_t)c + 1 < ii.l) dst[c + 1] = v1;
+          for (int c = 0; c < NL; c += 8) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float cj = ITEMS ? __ldg(cv + c + j) : cv[c + j];
+              v[j] = ar * fmaf((float)(int)hi[c + j], sc_hi, (float)(int)lo[c + j] * sc_lo) - br * cj;
+              if ((uint32_t)(c + j) >= ii.l) v[j] = 0.0f;
+              hi[c + j] = __float_as_uint(v[j]);       // kept for the statistics below
             }
-            hi[c] = __float_as_uint(v0);       // kept for the statistics below
-            hi[c + 1] = __float_as_uint(v1);
+            if (vec8 && (uint32_t)c < ii.l && (uint32_t)c + 8 <= p.ldo) {
+              asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + c), "f"(v[0]), "f"(v[1]),
+                           "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                           : "memory");
+            } else {
+#pragma unroll
+              for (int h = 0; h < 8; h += 4) {
+                if (vec4 && (uint32_t)(c + h) + 3 < ii.l) {
+                  *reinterpret_cast<float4*>(dst + c + h) = make_float4(v[h], v[h + 1], v[h + 2], v[h + 3]);
+                } else {
+#pragma unroll
+                  for (int j = h; j < h + 4; j += 2) {
+                    if (vec2 && (uint32_t)(c + j) + 1 < ii.l) {
+                      *reinterpret_cast<float2*>(dst + c + j) = make_float2(v[j], v[j + 1]);
+                    } else {
+                      if ((uint32_t)(c + j) < ii.l) dst[c + j] = v[j];
+                      if ((uint32_t)(c + j) + 1 < ii.l) dst[c + j + 1] = v[j + 1];
+                    }
+                  }
+                }
+              }
+            }
           }
         }
       }
@@ -413,7 +503,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) sketch_i8_kernel(const __grid_
         for (int c = 0; c < NL; ++c)
           if ((uint32_t)c < ii.l) stat_max = fmaxf(stat_max, fabsf(ar * __uint_as_float(hi[c])));
       }
+      PROF_ADD(c_epi, t_epi);
     }
+#ifdef GPCA_I8_PROF
+    if (blockIdx.x == 0 && lane == 0 && (warp & 3) == 0)
+      printf("PROF expander w%d: total %u wait_afull %u wait_tempty %u st_to_waitst %u epilogue %u (wait_accfull %u ldtm %u ab %u) pairs %u items %u\n",
+             warp, prof_clock() - t_role, c_afull, c_tempty, c_st, c_epi, c_accfull, c_ldtm, c_ab, cit, item_idx);
+#endif
     if (!ITEMS && p.stat_amax) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) stat_max = fmaxf(stat_max, __shfl_xor_sync(0xffffffffu, stat_max, o));

@@ -51,6 +51,12 @@ def child(shapes):
         out[f"{n}x{m}"] = {"step_ms": round(e0.elapsed_time(e1) / reps, 3), "kernel_ms": round(kern, 4),
                            "pass_ms": round(sk_ms / max(sk_n, 1), 4), "kernel_GBps": round(d * bps / kern / 1e6, 1),
                            "ev0": float(ev[0])}
+        if os.environ.get("AB_PROF"):
+            # one more step between two markers: the per-warp cycle accounting that a GPCA_I8_PROF build prints
+            print(f"MARK begin {n}x{m}", flush=True)
+            ctx.rfit(20, 10, power_iters=2, seed=42, want_loadings=False)
+            torch.cuda.synchronize()
+            print(f"MARK end {n}x{m}", flush=True)
         ctx.close()
         torch.cuda.empty_cache()
     print("RESULT " + json.dumps(out), flush=True)
@@ -70,7 +76,20 @@ def main():
             subprocess.check_call(["touch", os.path.join(CSRC, "sketch_i8.cu"), os.path.join(CSRC, "sketch_tc.cu")])
             subprocess.check_call(["make", "-C", CSRC, "-j8", f"EXTRA={v}", "../libgpca.so"], stdout=subprocess.DEVNULL)
             t0 = time.time()
-            p = subprocess.run([sys.executable, os.path.abspath(__file__), "--child"], capture_output=True, text=True)
+            env = dict(os.environ)
+            if "PROF" in v:
+                env["AB_PROF"] = "1"
+            p = subprocess.run([sys.executable, os.path.abspath(__file__), "--child"], capture_output=True, text=True,
+                               env=env)
+            if "PROF" in v:
+                on = False
+                for l in p.stdout.splitlines():
+                    if l.startswith("MARK begin"):
+                        on = True
+                    if on and (l.startswith("MARK") or l.startswith("PROF")):
+                        print("    " + l)
+                    if l.startswith("MARK end"):
+                        on = False
             res = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")]
             print(f"[{v or 'default'}] ({time.time() - t0:.0f}s) " + (res[0][7:] if res else "FAILED " + p.stderr[-400:]),
                   flush=True)
