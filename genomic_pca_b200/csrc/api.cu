@@ -67,6 +67,10 @@ extern "C" void gpca_destroy(gpca_ctx* c) {
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->h_cnt) cudaFreeHost(c->h_cnt);
   if (c->h_up) cudaFreeHost(c->h_up);
+  for (int i = 0; i < 2; ++i) {
+    if (c->h_dl[i]) cudaFreeHost(c->h_dl[i]);
+    if (c->ev_dl[i]) cudaEventDestroy(c->ev_dl[i]);
+  }
   for (int i = 0; i < 2; ++i)
     if (c->h_rd[i]) cudaFreeHost(c->h_rd[i]);
   gpca_destroy_cublas(c->cublas);

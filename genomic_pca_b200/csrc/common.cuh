@@ -135,6 +135,8 @@ struct gpca_ctx {
   size_t h_up_cap = 0;
   uint8_t* h_rd[2] = {nullptr, nullptr};   // pinned read buffers of gpca_ingest_bed_file
   size_t h_rd_cap = 0;
+  float* h_dl[2] = {nullptr, nullptr};     // pinned landing buffers of download_results (drivers.cu)
+  cudaEvent_t ev_dl[2] = {nullptr, nullptr};
   DevBuf<float> d_mean, d_sd;           // [D]
   DevBuf<float> d_inv_sd, d_mu_inv_sd;  // [D]  1/sd (0 if sd<1e-9) and mean/sd
   DevBuf<uint8_t> gs_store, gt_store;

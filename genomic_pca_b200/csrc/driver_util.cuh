@@ -24,6 +24,12 @@ void fix_signs_host(std::vector<float>& scores, uint64_t n, uint32_t k, std::vec
 
 int driver_allreduce(gpca_ctx* c, void* buf, uint64_t count, int dtype);
 
+// Results back to caller-owned (pageable) host memory: `count` floats from the device arrive in pinned landing buffers
+// chunk by chunk, and host threads copy (dst_f32) or widen (dst_f64) chunk q while chunk q+1 is on the bus.  Returns
+// after the last element has been written (the stream is idle by then).  A pageable cudaMemcpyAsync of the same data
+// ran at ~5 GB/s: 16 ms for the 500,000 x 20 f64 scores of one shard of BASELINE config 4.
+int download_results(gpca_ctx* c, const float* d_src, uint64_t count, float* dst_f32, double* dst_f64);
+
 // emit_stats: also leave the operand statistics of the output (as the next sample-side pass needs them) in the context;
 // use_stats: the operand's statistics are in the context (it was produced by such a pass or by
 // launch_gaussian_with_stats and has not been modified since)

@@ -9,6 +9,7 @@
 #include <random>
 
 #include "driver_util.cuh"
+#include "parallel_for.h"
 
 static int fail(gpca_ctx* c, int code, const std::string& msg) {
   c->set_error(msg);
@@ -31,6 +32,37 @@ int driver_allreduce(gpca_ctx* c, void* buf, uint64_t count, int dtype) {
   if (!c->allreduce) return GPCA_OK;
   if (c->allreduce(buf, count, dtype, (void*)c->stream, c->allreduce_user) != 0)
     return fail(c, GPCA_ERR_CUDA, "allreduce hook failed");
+  return GPCA_OK;
+}
+
+int download_results(gpca_ctx* c, const float* d_src, uint64_t count, float* dst_f32, double* dst_f64) {
+  constexpr uint64_t CH = 1u << 21;      // floats per chunk (8 MB)
+  if (count == 0 || (!dst_f32 && !dst_f64)) return GPCA_OK;
+  for (int i = 0; i < 2; ++i) {
+    if (!c->h_dl[i]) GPCA_CUDA_TRY(c, cudaMallocHost((void**)&c->h_dl[i], CH * sizeof(float)));
+    if (!c->ev_dl[i]) GPCA_CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_dl[i], cudaEventDisableTiming));
+  }
+  auto land = [&](uint64_t q) {          // chunk q has arrived in its buffer: hand it to the caller's memory
+    const uint64_t off = q * CH, cnt = std::min<uint64_t>(CH, count - off);
+    const float* src = c->h_dl[q & 1];
+    parallel_for(cnt, [&](uint64_t lo, uint64_t hi) {
+      if (dst_f32) std::memcpy(dst_f32 + off + lo, src + lo, (hi - lo) * sizeof(float));
+      if (dst_f64)
+        for (uint64_t i = lo; i < hi; ++i) dst_f64[off + i] = (double)src[i];
+    }, 1u << 17);
+  };
+  const uint64_t nch = (count + CH - 1) / CH;
+  for (uint64_t q = 0; q < nch; ++q) {
+    const uint64_t off = q * CH, cnt = std::min<uint64_t>(CH, count - off);
+    GPCA_CUDA_TRY(c, cudaMemcpyAsync(c->h_dl[q & 1], d_src + off, cnt * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    GPCA_CUDA_TRY(c, cudaEventRecord(c->ev_dl[q & 1], c->stream));
+    if (q > 0) {
+      GPCA_CUDA_TRY(c, cudaEventSynchronize(c->ev_dl[(q - 1) & 1]));
+      land(q - 1);
+    }
+  }
+  GPCA_CUDA_TRY(c, cudaEventSynchronize(c->ev_dl[(nch - 1) & 1]));
+  land(nch - 1);
   return GPCA_OK;
 }
 
@@ -152,13 +184,14 @@ extern "C" int gpca_rfit(gpca_ctx* c, uint32_t k, uint32_t oversample, uint32_t 
   GPCA_TRY(launch_sign_flags(c, Sc.p, N, k, k, d_flags.p));
   GPCA_CUDA_TRY(c, cudaMemcpyAsync(h_ev.data(), s.evals, l * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   if (scores) {
-    GPCA_CUDA_TRY(c, c->ws_f64.alloc(N * k));
-    GPCA_TRY(launch_apply_flags(c, Sc.p, N, k, k, d_flags.p, nullptr, c->ws_f64.p));
-    GPCA_CUDA_TRY(c, cudaMemcpyAsync(scores, c->ws_f64.p, N * k * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    // fp32 on the bus (the scores are computed in fp32; widening to the f64 the reference's API returns is exact and
+    // happens on host threads behind the transfer)
+    GPCA_TRY(launch_apply_flags(c, Sc.p, N, k, k, d_flags.p, Sc.p, nullptr));
+    GPCA_TRY(download_results(c, Sc.p, N * k, nullptr, scores));
   }
   if (loadings) {
     GPCA_TRY(launch_apply_flags(c, R.p, D, k, k, d_flags.p, R.p, nullptr));
-    GPCA_CUDA_TRY(c, cudaMemcpyAsync(loadings, R.p, D * k * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    GPCA_TRY(download_results(c, R.p, D * k, loadings, nullptr));
   }
   GPCA_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   if (eigenvalues)

@@ -695,7 +695,7 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
   GPCA_TRY(launch_sign_flags(c, V.p, N, k, k, d_flags.p));
   if (scores) {
     GPCA_TRY(launch_apply_flags(c, V.p, N, k, k, d_flags.p, V.p, nullptr));
-    GPCA_CUDA_TRY(c, cudaMemcpyAsync(scores, V.p, N * k * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    GPCA_TRY(download_results(c, V.p, N * k, scores, nullptr));
   }
   PoolBuf<float> Lout(&c->es_pool);
   if (loadings) {
@@ -705,7 +705,7 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
     const int grid = (int)std::min<uint64_t>((tot + 255) / 256, (uint64_t)c->sm_count * 8);
     scatter_loadings_kernel<<<grid, 256, 0, c->stream>>>(L.p, d_slot.p, Ds, k, d_flags.p, Lout.p);
     KCHECK(c);
-    GPCA_CUDA_TRY(c, cudaMemcpyAsync(loadings, Lout.p, D * k * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    GPCA_TRY(download_results(c, Lout.p, D * k, loadings, nullptr));
   }
   GPCA_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   if (eigenvalues)

@@ -126,7 +126,9 @@ __device__ __forceinline__ void gram_partial_body(const float* __restrict__ y, u
                                                   double* __restrict__ p) {
   constexpr int TPD = LP / 4;               // threads per dimension of the output
   constexpr int GROUPS = 256 / (TPD * TPD); // 4 for LP = 32, 1 for LP = 64
-  __shared__ __align__(16) float tile[GRAM_ROWS][LP + 4];
+  // the tile is widened to f64 once, while it is staged (the fp32 -> f64 conversion is a quarter-rate instruction: with
+  // fp32 tiles every thread converted 8 values per 16 FMAs and the kernel was conversion-bound)
+  __shared__ __align__(16) double tile[GRAM_ROWS][LP + 2];
   __shared__ double gsum[(GROUPS > 1) ? (GROUPS - 1) * LP * LP : 1];
   const int grp = threadIdx.x / (TPD * TPD);
   const int t = threadIdx.x % (TPD * TPD);
@@ -140,15 +142,17 @@ __device__ __forceinline__ void gram_partial_body(const float* __restrict__ y, u
     for (int e = threadIdx.x; e < GRAM_ROWS * LP; e += 256) {
       const int rr = e / LP, cc = e % LP;
       const uint64_t r = r0 + rr;
-      tile[rr][cc] = (r < r_end && (uint32_t)cc < l) ? y[r * ld + cc] : 0.0f;
+      tile[rr][cc] = (r < r_end && (uint32_t)cc < l) ? (double)y[r * ld + cc] : 0.0;
     }
     __syncthreads();
 #pragma unroll 4
     for (int rr = grp; rr < GRAM_ROWS; rr += GROUPS) {
-      const float4 a = *reinterpret_cast<const float4*>(&tile[rr][ti * 4]);
-      const float4 b = *reinterpret_cast<const float4*>(&tile[rr][tj * 4]);
-      const double av[4] = {a.x, a.y, a.z, a.w};
-      const double bv[4] = {b.x, b.y, b.z, b.w};
+      const double2 a0 = *reinterpret_cast<const double2*>(&tile[rr][ti * 4]);
+      const double2 a1 = *reinterpret_cast<const double2*>(&tile[rr][ti * 4 + 2]);
+      const double2 b0 = *reinterpret_cast<const double2*>(&tile[rr][tj * 4]);
+      const double2 b1 = *reinterpret_cast<const double2*>(&tile[rr][tj * 4 + 2]);
+      const double av[4] = {a0.x, a0.y, a1.x, a1.y};
+      const double bv[4] = {b0.x, b0.y, b1.x, b1.y};
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -205,14 +209,20 @@ __global__ void __launch_bounds__(256) gram_batch_kernel(const float* __restrict
                         partial + ((uint64_t)blockIdx.y * gridDim.x + blockIdx.x) * 1024);
 }
 
-__global__ void gram_reduce_kernel(const double* __restrict__ partial, int nparts, uint32_t l, int lp,
-                                   double* __restrict__ g) {
-  // one thread per output element; the partials are summed in index order (deterministic)
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < (int)(l * l); t += gridDim.x * blockDim.x) {
+__global__ void __launch_bounds__(256) gram_reduce_kernel(const double* __restrict__ partial, int nparts, uint32_t l,
+                                                          int lp, double* __restrict__ g) {
+  // one warp per output element: lane q sums the partials q, q+32, ... in index order, then a fixed butterfly
+  // (deterministic; a single thread walking hundreds of partials 8 KB apart took 80 us)
+  const int lane = threadIdx.x & 31;
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nw = (gridDim.x * blockDim.x) >> 5;
+  for (int t = w; t < (int)(l * l); t += nw) {
     const int i = t / l, j = t % l;
     double s = 0.0;
-    for (int p = 0; p < nparts; ++p) s += partial[(uint64_t)p * lp * lp + i * lp + j];
-    g[t] = s;
+    for (int p = lane; p < nparts; p += 32) s += partial[(uint64_t)p * lp * lp + i * lp + j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) g[t] = s;
   }
 }
 
@@ -223,8 +233,8 @@ __global__ void __launch_bounds__(256) cross_gram_partial_kernel(const float* __
                                                                  uint64_t rows_per_cta, double* __restrict__ partial) {
   constexpr int TPD = LP / 4;
   constexpr int GROUPS = 256 / (TPD * TPD);
-  __shared__ __align__(16) float ta[GRAM_ROWS][LP + 4];
-  __shared__ __align__(16) float tb[GRAM_ROWS][LP + 4];
+  __shared__ __align__(16) double ta[GRAM_ROWS / 2][LP + 2];      // (32-row tiles: two f64 tiles + the group sums in 48 KB)
+  __shared__ __align__(16) double tb[GRAM_ROWS / 2][LP + 2];
   __shared__ double gsum[(GROUPS > 1) ? (GROUPS - 1) * LP * LP : 1];
   const int grp = threadIdx.x / (TPD * TPD);
   const int t = threadIdx.x % (TPD * TPD);
@@ -237,21 +247,23 @@ __global__ void __launch_bounds__(256) cross_gram_partial_kernel(const float* __
   const uint64_t r_begin = blockIdx.x * rows_per_cta;
   uint64_t r_end = r_begin + rows_per_cta;
   if (r_end > n) r_end = n;
-  for (uint64_t r0 = r_begin; r0 < r_end; r0 += GRAM_ROWS) {
-    for (int e = threadIdx.x; e < GRAM_ROWS * LP; e += 256) {
+  for (uint64_t r0 = r_begin; r0 < r_end; r0 += GRAM_ROWS / 2) {
+    for (int e = threadIdx.x; e < (GRAM_ROWS / 2) * LP; e += 256) {
       const int rr = e / LP, cc = e % LP;
       const uint64_t r = r0 + rr;
       const bool live = r < r_end && (uint32_t)cc < l;
-      ta[rr][cc] = live ? a[r * ld + cc] : 0.0f;
-      tb[rr][cc] = live ? b[r * ld + cc] : 0.0f;
+      ta[rr][cc] = live ? (double)a[r * ld + cc] : 0.0;
+      tb[rr][cc] = live ? (double)b[r * ld + cc] : 0.0;
     }
     __syncthreads();
 #pragma unroll 4
-    for (int rr = grp; rr < GRAM_ROWS; rr += GROUPS) {
-      const float4 av4 = *reinterpret_cast<const float4*>(&ta[rr][ti * 4]);
-      const float4 bv4 = *reinterpret_cast<const float4*>(&tb[rr][tj * 4]);
-      const double av[4] = {av4.x, av4.y, av4.z, av4.w};
-      const double bv[4] = {bv4.x, bv4.y, bv4.z, bv4.w};
+    for (int rr = grp; rr < GRAM_ROWS / 2; rr += GROUPS) {
+      const double2 a0 = *reinterpret_cast<const double2*>(&ta[rr][ti * 4]);
+      const double2 a1 = *reinterpret_cast<const double2*>(&ta[rr][ti * 4 + 2]);
+      const double2 b0 = *reinterpret_cast<const double2*>(&tb[rr][tj * 4]);
+      const double2 b1 = *reinterpret_cast<const double2*>(&tb[rr][tj * 4 + 2]);
+      const double av[4] = {a0.x, a0.y, a1.x, a1.y};
+      const double bv[4] = {b0.x, b0.y, b1.x, b1.y};
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -304,7 +316,7 @@ int launch_cross_gram(gpca_ctx* c, const float* d_a, const float* d_b, uint64_t 
   else
     cross_gram_partial_kernel<64><<<nparts, 256, 0, c->stream>>>(d_a, d_b, n, l, ld, rows_per_cta, c->ws_gram.p);
   KLAUNCH_CHECK(c);
-  gram_reduce_kernel<<<(l * l + 127) / 128, 128, 0, c->stream>>>(c->ws_gram.p, nparts, l, lp, d_g);
+  gram_reduce_kernel<<<(l * l + 7) / 8, 256, 0, c->stream>>>(c->ws_gram.p, nparts, l, lp, d_g);
   KLAUNCH_CHECK(c);
   return GPCA_OK;
 }
@@ -328,52 +340,77 @@ int launch_gram(gpca_ctx* c, const float* d_y, uint64_t n, uint32_t l, uint32_t 
   else
     gram_partial_kernel<64><<<nparts, 256, 0, c->stream>>>(d_y, n, l, ld, rows_per_cta, c->ws_gram.p);
   KLAUNCH_CHECK(c);
-  gram_reduce_kernel<<<(l * l + 127) / 128, 128, 0, c->stream>>>(c->ws_gram.p, nparts, l, lp, d_g);
+  gram_reduce_kernel<<<(l * l + 7) / 8, 256, 0, c->stream>>>(c->ws_gram.p, nparts, l, lp, d_g);
   KLAUNCH_CHECK(c);
   return GPCA_OK;
 }
 
 // ------------------------------------------------------------------------------------------
 // out[r, :l2] = y[r, :l] * T   (T f64 in shared memory, f64 accumulation, fp32 store).
-// Thread (row rr = tid/4, column lane cg = tid%4) owns the NOWN outputs cg, cg+4, ... in registers.
+// 128-row tiles, widened to f64 while they are staged.  Thread (row pair rr = tid/4 and rr + 64, column lane cg = tid%4)
+// owns the column pairs 2cg + 8j + {0,1}, j < NOWN/2, of both rows: one 16-byte shared-memory load of T feeds four
+// FMAs (the first version -- one row, one 8-byte load per FMA, an fp32 -> f64 conversion per element and thread -- was
+// bound by the shared-memory pipe at 0.8 TB/s).
+constexpr int AR_ROWS = 128;
 template <int NOWN>
 __global__ void __launch_bounds__(256) apply_right_kernel(const float* __restrict__ y, uint64_t n, uint32_t l,
                                                           uint32_t ld, const double* __restrict__ t, uint32_t l2,
                                                           float* __restrict__ out, uint32_t ldo) {
-  extern __shared__ double sm[];
+  static_assert(NOWN % 2 == 0, "columns are owned in pairs");
+  extern __shared__ __align__(16) double sm[];
   const int l2p = NOWN * 4;                                    // padded output width
   double* ts = sm;                                             // [l][l2p] (zero padded)
-  float* tile = reinterpret_cast<float*>(sm + l * l2p);        // [64][l+1]
+  const int lp = (int)l + 1;
+  double* tile = sm + l * l2p;                                 // [AR_ROWS][l+1]
   for (int i = threadIdx.x; i < (int)(l * l2p); i += 256) {
     const int cc = i / l2p, c2 = i % l2p;
     ts[i] = ((uint32_t)c2 < l2) ? t[cc * l2 + c2] : 0.0;
   }
-  const int lp = l + 1;
-  const uint64_t ntiles = (n + 63) / 64;
+  const uint64_t ntiles = (n + AR_ROWS - 1) / AR_ROWS;
+  const bool vec2 = (ldo & 1u) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0;
   for (uint64_t tix = blockIdx.x; tix < ntiles; tix += gridDim.x) {
-    const uint64_t r0 = tix * 64;
+    const uint64_t r0 = tix * AR_ROWS;
     __syncthreads();
-    for (int i = threadIdx.x; i < 64 * (int)l; i += 256) {
-      const int rr = i / l, cc = i % l;
+    for (int i = threadIdx.x; i < AR_ROWS * (int)l; i += 256) {
+      const int rr = i / (int)l, cc = i % (int)l;
       const uint64_t r = r0 + rr;
-      tile[rr * lp + cc] = (r < n) ? y[r * ld + cc] : 0.0f;
+      tile[rr * lp + cc] = (r < n) ? (double)y[r * ld + cc] : 0.0;
     }
     __syncthreads();
     const int rr = threadIdx.x >> 2, cg = threadIdx.x & 3;
-    const uint64_t r = r0 + rr;
-    if (r < n) {
-      double acc[NOWN];
+    double acc0[NOWN], acc1[NOWN];
 #pragma unroll
-      for (int j = 0; j < NOWN; ++j) acc[j] = 0.0;
-      for (uint32_t cc = 0; cc < l; ++cc) {
-        const double yv = (double)tile[rr * lp + cc];
-        const double* trow = ts + cc * l2p + cg;
+    for (int j = 0; j < NOWN; ++j) acc0[j] = acc1[j] = 0.0;
+    const double* y0 = tile + rr * lp;
+    const double* y1 = tile + (rr + 64) * lp;
+    for (uint32_t cc = 0; cc < l; ++cc) {
+      const double a0 = y0[cc], a1 = y1[cc];
+      const double* trow = ts + cc * l2p + 2 * cg;
 #pragma unroll
-        for (int j = 0; j < NOWN; ++j) acc[j] = fma(yv, trow[4 * j], acc[j]);
+      for (int j = 0; j < NOWN / 2; ++j) {
+        const double2 tv = *reinterpret_cast<const double2*>(trow + 8 * j);
+        acc0[2 * j] = fma(a0, tv.x, acc0[2 * j]);
+        acc0[2 * j + 1] = fma(a0, tv.y, acc0[2 * j + 1]);
+        acc1[2 * j] = fma(a1, tv.x, acc1[2 * j]);
+        acc1[2 * j + 1] = fma(a1, tv.y, acc1[2 * j + 1]);
       }
+    }
 #pragma unroll
-      for (int j = 0; j < NOWN; ++j)
-        if (cg + 4u * j < l2) out[r * ldo + cg + 4 * j] = (float)acc[j];
+    for (int h = 0; h < 2; ++h) {
+      const uint64_t r = r0 + rr + 64 * h;
+      if (r >= n) continue;
+      const double* acc = h ? acc1 : acc0;
+      float* orow = out + r * ldo;
+#pragma unroll
+      for (int j = 0; j < NOWN / 2; ++j) {
+        const uint32_t c0 = 2 * cg + 8 * j;
+        if (vec2 && c0 + 1 < l2) {
+          *reinterpret_cast<float2*>(orow + c0) = make_float2((float)acc[2 * j], (float)acc[2 * j + 1]);
+        } else {
+          if (c0 < l2) orow[c0] = (float)acc[2 * j];
+          if (c0 + 1 < l2) orow[c0 + 1] = (float)acc[2 * j + 1];
+        }
+      }
     }
   }
 }
@@ -381,10 +418,10 @@ __global__ void __launch_bounds__(256) apply_right_kernel(const float* __restric
 template <int NOWN>
 static int run_apply_right(gpca_ctx* c, const float* d_y, uint64_t n, uint32_t l, uint32_t ld, const double* d_t,
                            uint32_t l2, float* d_out, uint32_t ldo) {
-  const size_t smem = (size_t)l * NOWN * 4 * sizeof(double) + (size_t)64 * (l + 1) * sizeof(float);
+  const size_t smem = ((size_t)l * NOWN * 4 + (size_t)AR_ROWS * (l + 1)) * sizeof(double);
   if (smem > 48 * 1024)
     GPCA_CUDA_TRY(c, cudaFuncSetAttribute(apply_right_kernel<NOWN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const uint64_t ntiles = (n + 63) / 64;
+  const uint64_t ntiles = (n + AR_ROWS - 1) / AR_ROWS;
   const int grid = (int)(ntiles < (uint64_t)c->sm_count * 4 ? ntiles : (uint64_t)c->sm_count * 4);
   apply_right_kernel<NOWN><<<grid, 256, smem, c->stream>>>(d_y, n, l, ld, d_t, l2, d_out, ldo);
   KLAUNCH_CHECK(c);
@@ -396,7 +433,7 @@ int launch_apply_right(gpca_ctx* c, const float* d_y, uint64_t n, uint32_t l, ui
   if (n == 0 || l == 0 || l2 == 0) return GPCA_OK;
   const uint32_t need = (l2 + 3) / 4;
   if (need <= 2) return run_apply_right<2>(c, d_y, n, l, ld, d_t, l2, d_out, ldo);
-  if (need <= 5) return run_apply_right<5>(c, d_y, n, l, ld, d_t, l2, d_out, ldo);
+  if (need <= 6) return run_apply_right<6>(c, d_y, n, l, ld, d_t, l2, d_out, ldo);
   if (need <= 8) return run_apply_right<8>(c, d_y, n, l, ld, d_t, l2, d_out, ldo);
   if (need <= 12) return run_apply_right<12>(c, d_y, n, l, ld, d_t, l2, d_out, ldo);
   return run_apply_right<16>(c, d_y, n, l, ld, d_t, l2, d_out, ldo);
@@ -579,35 +616,72 @@ int launch_make_orth_transform(gpca_ctx* c, const double* d_evals, const double*
 
 // ------------------------------------------------------------------------------------------
 // Sign convention on the device: flags[j] = 1 when the largest-|.| entry of column j (first one on ties) is negative.
-__global__ void __launch_bounds__(256) sign_flags_kernel(const float* __restrict__ x, uint64_t n, uint32_t k, uint32_t ld,
-                                                         int* __restrict__ flags) {
-  __shared__ float sv[256];
-  __shared__ unsigned long long si[256];
-  const uint32_t j = blockIdx.x;
-  float best = -1.0f;
-  unsigned long long bi = 0;
-  for (uint64_t i = threadIdx.x; i < n; i += blockDim.x) {
-    const float a = fabsf(x[i * ld + j]);
-    if (a > best) {
-      best = a;
-      bi = i;
+// Two steps: every CTA scans a strided set of rows with lane = column (coalesced row reads) and leaves its best
+// (|value|, row) per column; one small CTA then picks the winner per column in CTA order.  Ties go to the smaller row
+// index at every level, so the result does not depend on the grid.
+struct SignCand {
+  float a;
+  uint32_t pad;
+  unsigned long long i;
+};
+__device__ __forceinline__ bool sign_better(float a2, unsigned long long i2, float a1, unsigned long long i1) {
+  return a2 > a1 || (a2 == a1 && i2 < i1);
+}
+__global__ void __launch_bounds__(256) sign_flags_partial_kernel(const float* __restrict__ x, uint64_t n, uint32_t k,
+                                                                 uint32_t ld, SignCand* __restrict__ part) {
+  __shared__ float sv[8][32];
+  __shared__ unsigned long long si[8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint64_t gw = (uint64_t)blockIdx.x * 8 + w, nw = (uint64_t)gridDim.x * 8;
+  for (uint32_t c0 = 0; c0 < k; c0 += 32) {
+    const uint32_t j = c0 + lane;
+    float best = -1.0f;
+    unsigned long long bi = 0;
+    if (j < k) {
+      for (uint64_t i = gw; i < n; i += nw) {
+        const float a = fabsf(x[i * ld + j]);
+        if (a > best) {      // rows are visited in increasing order: the first maximum is kept
+          best = a;
+          bi = i;
+        }
+      }
     }
-  }
-  sv[threadIdx.x] = best;
-  si[threadIdx.x] = bi;
-  __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if ((int)threadIdx.x < o) {
-      const float b2 = sv[threadIdx.x + o];
-      const unsigned long long i2 = si[threadIdx.x + o];
-      if (b2 > sv[threadIdx.x] || (b2 == sv[threadIdx.x] && i2 < si[threadIdx.x])) {
-        sv[threadIdx.x] = b2;
-        si[threadIdx.x] = i2;
+    sv[w][lane] = best;
+    si[w][lane] = bi;
+    __syncthreads();
+    if (w == 0) {
+#pragma unroll
+      for (int q = 1; q < 8; ++q)
+        if (sign_better(sv[q][lane], si[q][lane], best, bi)) {
+          best = sv[q][lane];
+          bi = si[q][lane];
+        }
+      if (j < k) {
+        SignCand cnd;
+        cnd.a = best;
+        cnd.pad = 0;
+        cnd.i = bi;
+        part[(uint64_t)blockIdx.x * 64 + j] = cnd;
       }
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) flags[j] = (n && x[si[0] * ld + j] < 0.0f) ? 1 : 0;
+}
+
+__global__ void sign_flags_final_kernel(const float* __restrict__ x, uint64_t n, uint32_t k, uint32_t ld,
+                                        const SignCand* __restrict__ part, int nparts, int* __restrict__ flags) {
+  const uint32_t j = threadIdx.x;
+  if (j >= k) return;
+  float best = -1.0f;
+  unsigned long long bi = 0;
+  for (int q = 0; q < nparts; ++q) {
+    const SignCand cnd = part[(uint64_t)q * 64 + j];
+    if (sign_better(cnd.a, cnd.i, best, bi)) {
+      best = cnd.a;
+      bi = cnd.i;
+    }
+  }
+  flags[j] = (n && x[bi * ld + j] < 0.0f) ? 1 : 0;
 }
 
 __global__ void apply_flags_kernel(const float* __restrict__ x, uint64_t n, uint32_t k, uint32_t ld,
@@ -627,7 +701,18 @@ __global__ void apply_flags_kernel(const float* __restrict__ x, uint64_t n, uint
 
 int launch_sign_flags(gpca_ctx* c, const float* d_x, uint64_t n, uint32_t k, uint32_t ld, int* d_flags) {
   if (k == 0) return GPCA_OK;
-  sign_flags_kernel<<<k, 256, 0, c->stream>>>(d_x, n, k, ld, d_flags);
+  if (k > 64) {
+    c->set_error("launch_sign_flags: k must be <= 64");
+    return GPCA_ERR_INVALID;
+  }
+  int nparts = (int)std::min<uint64_t>((n + 63) / 64, (uint64_t)c->sm_count * 4);
+  if (nparts < 1) nparts = 1;
+  static_assert(sizeof(SignCand) == 2 * sizeof(double), "candidate records live in the f64 Gram workspace");
+  GPCA_CUDA_TRY(c, c->ws_gram.alloc((size_t)nparts * 64 * 2));
+  SignCand* part = reinterpret_cast<SignCand*>(c->ws_gram.p);
+  sign_flags_partial_kernel<<<nparts, 256, 0, c->stream>>>(d_x, n, k, ld, part);
+  KLAUNCH_CHECK(c);
+  sign_flags_final_kernel<<<1, 64, 0, c->stream>>>(d_x, n, k, ld, part, nparts, d_flags);
   KLAUNCH_CHECK(c);
   return GPCA_OK;
 }
