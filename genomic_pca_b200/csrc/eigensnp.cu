@@ -63,6 +63,71 @@ int launch_gather_rows(gpca_ctx* c, PackedMat src, const int64_t* d_idx, PackedM
   return GPCA_OK;
 }
 
+// Sample-major slot-ordered copy when every LD block is a run of consecutive PcaSnpIds (the normal case: blocks are
+// genomic intervals, src/prepare.rs:1424-1563): Et[n, 64q .. 64q+63] = Gt[n, first[q] .. first[q] + count[q] - 1], a
+// per-row shifted copy of 2-bit fields -- one 16-byte chunk per thread, two aligned 16-byte loads and a funnel shift.
+// (The general path gathers SNP-major rows and transposes the whole matrix: 16 ms for a 10.9 GB shard against ~4 ms.)
+__global__ void shift_fields_kernel(const uint8_t* __restrict__ src, size_t src_pitch, const int64_t* __restrict__ first,
+                                    const uint32_t* __restrict__ count, uint8_t* __restrict__ dst, size_t dst_pitch,
+                                    uint64_t n_rows, uint64_t n_chunks) {
+  const uint64_t cpr = dst_pitch / 16;
+  const uint64_t total = n_rows * cpr;
+  for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < total;
+       t += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t r = t / cpr, ci = t - r * cpr;
+    uint4 o = make_uint4(0, 0, 0, 0);
+    if (ci < n_chunks) {
+      const int64_t f0 = first[ci];
+      const uint32_t cnt = count[ci];
+      if (f0 >= 0 && cnt) {
+        const uint64_t byte0 = ((uint64_t)f0 >> 6) << 4;          // aligned 16-byte word holding field f0
+        const uint32_t sh = ((uint32_t)f0 & 63u) * 2u;            // bit offset inside it
+        const uint8_t* row = src + r * src_pitch;
+        const uint4 a = ldg_nc_v4(row + byte0);
+        uint4 b = make_uint4(0, 0, 0, 0);
+        if (sh && byte0 + 32 <= src_pitch) b = ldg_nc_v4(row + byte0 + 16);
+        uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        const uint32_t ws = sh >> 5, bs = sh & 31u;
+        uint32_t v[5];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {      // v[i] = w[i + ws] without dynamic indexing
+          v[i] = (ws == 0) ? w[i] : (ws == 1) ? w[i + 1] : (ws == 2) ? w[i + 2] : w[i + 3];
+        }
+        o.x = __funnelshift_r(v[0], v[1], bs);
+        o.y = __funnelshift_r(v[1], v[2], bs);
+        o.z = __funnelshift_r(v[2], v[3], bs);
+        o.w = __funnelshift_r(v[3], v[4], bs);
+        if (cnt < 64) {                    // fields beyond the block are padding: dosage code 0
+          const uint32_t keep_bits = cnt * 2u;
+          uint32_t* ow = &o.x;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t lo = 32u * i;
+            if (keep_bits <= lo) ow[i] = 0u;
+            else if (keep_bits < lo + 32u) ow[i] &= (1u << (keep_bits - lo)) - 1u;
+          }
+        }
+      }
+    }
+    *reinterpret_cast<uint4*>(dst + r * dst_pitch + ci * 16) = o;
+  }
+}
+
+// Block-diagonal operand of the grouped condensed-feature pass: dst [n_slots x 32] (zeroed by the caller), slot s of
+// block p gets U_p's row (src [n_slots x ld_src]) in columns col0(p) .. col0(p) + c_p - 1; padding slots stay zero.
+__global__ void block_diag_operand_kernel(const float* __restrict__ src, uint32_t ld_src, const int64_t* __restrict__ slot_id,
+                                          const uint32_t* __restrict__ col0, const uint32_t* __restrict__ cpn,
+                                          uint64_t n_slots, float* __restrict__ dst) {
+  const uint64_t total = n_slots * ld_src;
+  for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < total;
+       t += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t s = t / ld_src;
+    const uint32_t j = (uint32_t)(t - s * ld_src);
+    const uint64_t q = s >> 6;
+    if (slot_id[s] >= 0 && j < cpn[q]) dst[s * 32 + col0[q] + j] = src[t];
+  }
+}
+
 // Gaussian rows keyed by an explicit 64-bit key per row (condensed-feature test matrix)
 __global__ void gaussian_keyed_kernel(float* __restrict__ out, const uint64_t* __restrict__ keys, uint64_t rows,
                                       uint32_t cols, uint64_t seed, uint32_t stream) {
@@ -270,7 +335,40 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
   stage("  allocations + tables");
   GPCA_TRY(launch_gather_rows(c, c->Gs, d_slot.p, Es));
   stage("  gather slots");
-  GPCA_TRY(launch_transpose(c, Es, Et));
+  // blocks that are runs of consecutive PcaSnpIds: the sample-major copy is a shifted copy of Gt's rows
+  bool runs = !getenv("GPCA_DEBUG_NO_SHIFT_COPY");
+  for (uint64_t b = 0; b < n_blocks && runs; ++b)
+    for (uint64_t j = block_offsets[b] + 1; j < block_offsets[b + 1]; ++j)
+      if (block_snp_ids[j] != block_snp_ids[j - 1] + 1) {
+        runs = false;
+        break;
+      }
+  if (runs) {
+    const uint64_t n_chunks = Ds / 64;
+    std::vector<int64_t> h_first(n_chunks, -1);
+    std::vector<uint32_t> h_count(n_chunks, 0);
+    for (uint64_t b = 0; b < n_blocks; ++b) {
+      const uint64_t m = block_offsets[b + 1] - block_offsets[b];
+      const uint64_t id0 = block_snp_ids[block_offsets[b]];
+      for (uint64_t q = 0; q * 64 < m; ++q) {
+        h_first[off[b] / 64 + q] = (int64_t)(id0 + q * 64);
+        h_count[off[b] / 64 + q] = (uint32_t)std::min<uint64_t>(64, m - q * 64);
+      }
+    }
+    PoolBuf<int64_t> d_first(&c->es_pool);
+    PoolBuf<uint32_t> d_count(&c->es_pool);
+    GPCA_CUDA_TRY(c, d_first.alloc(n_chunks));
+    GPCA_CUDA_TRY(c, d_count.alloc(n_chunks));
+    GPCA_CUDA_TRY(c, cudaMemcpyAsync(d_first.p, h_first.data(), n_chunks * 8, cudaMemcpyHostToDevice, c->stream));
+    GPCA_CUDA_TRY(c, cudaMemcpyAsync(d_count.p, h_count.data(), n_chunks * 4, cudaMemcpyHostToDevice, c->stream));
+    const uint64_t total = Et.rows * (Et.pitch / 16);
+    const int grid = (int)std::min<uint64_t>((total + 255) / 256, (uint64_t)c->sm_count * 16);
+    shift_fields_kernel<<<grid, 256, 0, c->stream>>>(c->Gt.p, c->Gt.pitch, d_first.p, d_count.p, Et.p, Et.pitch, Et.rows,
+                                                     n_chunks);
+    KCHECK(c);
+  } else {
+    GPCA_TRY(launch_transpose(c, Es, Et));
+  }
   stage("  transpose");
   if (Ns == N) {
     Ets = Et;
@@ -493,23 +591,82 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
   DevBuf<float>& Cn = c->es_cn;
   GPCA_CUDA_TRY(c, Cn.alloc(N * R));
   if (batched) {
-    if (rgN * n_blocks > 0x7fffffffull) return fail(c, GPCA_ERR_INVALID, "too many condensed-feature work items");
-    std::vector<I8Item> itc;
-    itc.reserve(rgN * n_blocks);
+    // Consecutive blocks share a work item while their component counts fit the 32 accumulator columns: the operand
+    // of a group is block-diagonal (rows = the group's slot range, block p's components in its own columns), so one
+    // pass over the group's K range leaves every block's features in adjacent columns of Cn.  With one item per
+    // (row group, block) an item was two stages long and the launch was bound by the per-item hand-overs
+    // (13.6 ms for 10.9 GB at 500,000 x 87,500 / 212 blocks); groups of 4 blocks (4 x 7 columns) run 7-stage items.
+    struct Grp {
+      uint64_t b0, b1;
+      uint32_t l;
+    };
+    std::vector<Grp> grps;
+    const bool grouping = !getenv("GPCA_DEBUG_NO_GROUPS");
     for (uint64_t b = 0; b < n_blocks; ++b) {
-      blkY[b].bin_off = off[b] * cpb_max;
-      blkY[b].l = cp[b];
+      if (grouping && !grps.empty() && grps.back().l + cp[b] <= 32) {
+        grps.back().b1 = b + 1;
+        grps.back().l += cp[b];
+      } else {
+        grps.push_back({b, b + 1, cp[b]});
+      }
     }
+    const uint64_t n_grps = grps.size();
+    if (rgN * n_grps > 0x7fffffffull) return fail(c, GPCA_ERR_INVALID, "too many condensed-feature work items");
+    // block-diagonal operand [Ds x 32]: slot s of block p holds U_p's row in columns [col0(p), col0(p) + c_p)
+    const uint64_t n_chunks64 = Ds / 64;
+    std::vector<uint32_t> h_col0(n_chunks64, 0), h_cpn(n_chunks64, 0);
+    std::vector<SketchBatchBlock> blkG(n_grps);
+    uint32_t img_stages_G = 0, max_KG = 0;
+    for (uint64_t g = 0; g < n_grps; ++g) {
+      uint32_t col = 0;
+      for (uint64_t b = grps[g].b0; b < grps[g].b1; ++b) {
+        for (uint64_t q = off[b] / 64; q < off[b + 1] / 64; ++q) {
+          h_col0[q] = col;
+          h_cpn[q] = cp[b];
+        }
+        col += cp[b];
+      }
+      const uint64_t bl = grps[g].b1 - 1;
+      const uint64_t Kg = off[bl] + (block_offsets[bl + 1] - block_offsets[bl]) - off[grps[g].b0];
+      blkG[g].bin_off = off[grps[g].b0] * 32;
+      blkG[g].fe_off = off[grps[g].b0];
+      blkG[g].K = (uint32_t)Kg;
+      blkG[g].l = grps[g].l;
+      blkG[g].nst = (uint32_t)((Kg + 255) / 256);
+      blkG[g].img_st0 = img_stages_G;
+      img_stages_G += blkG[g].nst;
+      max_KG = std::max(max_KG, blkG[g].K);
+    }
+    PoolBuf<float> Ugrp(&c->es_pool);
+    PoolBuf<uint32_t> d_col0(&c->es_pool), d_cpn(&c->es_pool);
+    PoolBuf<SketchBatchBlock> d_blkG(&c->es_pool);
+    GPCA_CUDA_TRY(c, Ugrp.alloc(Ds * 32));
+    GPCA_CUDA_TRY(c, d_col0.alloc(n_chunks64));
+    GPCA_CUDA_TRY(c, d_cpn.alloc(n_chunks64));
+    GPCA_CUDA_TRY(c, d_blkG.alloc(n_grps));
+    GPCA_CUDA_TRY(c, cudaMemcpyAsync(d_col0.p, h_col0.data(), n_chunks64 * 4, cudaMemcpyHostToDevice, c->stream));
+    GPCA_CUDA_TRY(c, cudaMemcpyAsync(d_cpn.p, h_cpn.data(), n_chunks64 * 4, cudaMemcpyHostToDevice, c->stream));
+    GPCA_CUDA_TRY(c, cudaMemcpyAsync(d_blkG.p, blkG.data(), n_grps * sizeof(SketchBatchBlock), cudaMemcpyHostToDevice,
+                                     c->stream));
+    GPCA_CUDA_TRY(c, cudaMemsetAsync(Ugrp.p, 0, Ds * 32 * sizeof(float), c->stream));
+    {
+      const uint64_t tot = Ds * cpb_max;
+      const int grid = (int)std::min<uint64_t>((tot + 255) / 256, (uint64_t)c->sm_count * 8);
+      block_diag_operand_kernel<<<grid, 256, 0, c->stream>>>(Ubuf.p, cpb_max, d_slot.p, d_col0.p, d_cpn.p, Ds, Ugrp.p);
+      KCHECK(c);
+    }
+    std::vector<I8Item> itc;
+    itc.reserve(rgN * n_grps);
     for (uint64_t rg = 0; rg < rgN; ++rg)
-      for (uint64_t b = 0; b < n_blocks; ++b) {
+      for (uint64_t g = 0; g < n_grps; ++g) {
         I8Item it;
         it.row0 = (uint32_t)(rg * 256);
-        it.nrows_l = (uint32_t)std::min<uint64_t>(256, N - rg * 256) | (cp[b] << 16);
-        it.kbyte0 = (uint32_t)(off[b] / 4);
-        it.nst = blkY[b].nst;
-        it.img_st0 = blkY[b].img_st0;
-        it.blk = (uint32_t)b;
-        const uint64_t oo = rg * 256 * R + roff[b];
+        it.nrows_l = (uint32_t)std::min<uint64_t>(256, N - rg * 256) | (blkG[g].l << 16);
+        it.kbyte0 = (uint32_t)(off[grps[g].b0] / 4);
+        it.nst = blkG[g].nst;
+        it.img_st0 = blkG[g].img_st0;
+        it.blk = (uint32_t)g;
+        const uint64_t oo = rg * 256 * R + roff[grps[g].b0];
         it.out_off_lo = (uint32_t)oo;
         it.out_off_hi = (uint32_t)(oo >> 32);
         itc.push_back(it);
@@ -517,14 +674,12 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
     PoolBuf<I8Item> d_itc(&c->es_pool);
     GPCA_CUDA_TRY(c, d_itc.alloc(itc.size()));
     GPCA_CUDA_TRY(c, cudaMemcpyAsync(d_itc.p, itc.data(), itc.size() * sizeof(I8Item), cudaMemcpyHostToDevice, c->stream));
-    GPCA_CUDA_TRY(c, cudaMemcpyAsync(d_blkY.p, blkY.data(), n_blocks * sizeof(SketchBatchBlock), cudaMemcpyHostToDevice,
-                                     c->stream));
     SketchBatch pc;   // C_b = X_b^T U_b for all N samples, written into the block's columns of Cn
     pc.G = Et; pc.G.avail = Et.pitch;
     pc.d_items = d_itc.p; pc.n_items = (uint32_t)itc.size();
-    pc.d_blocks = d_blkY.p; pc.n_blocks = (uint32_t)n_blocks;
-    pc.total_img_stages = img_stages_Y; pc.max_K = (uint32_t)max_m;
-    pc.Bin = Ubuf.p; pc.ld = cpb_max; pc.f = d_inv.p; pc.e = d_mu.p; pc.a = nullptr; pc.b = nullptr;
+    pc.d_blocks = d_blkG.p; pc.n_blocks = (uint32_t)n_grps;
+    pc.total_img_stages = img_stages_G; pc.max_K = max_KG;
+    pc.Bin = Ugrp.p; pc.ld = 32; pc.f = d_inv.p; pc.e = d_mu.p; pc.a = nullptr; pc.b = nullptr;
     pc.out = Cn.p; pc.ldo = (uint32_t)R;
     pc.bytes = (double)N * (double)D / 4.0;
     GPCA_TRY(timed_sketch_batch(c, pc));
