@@ -129,6 +129,8 @@ struct gpca_ctx {
   uint64_t h_cnt_cap = 0;
   DevBuf<uint8_t> es_store, et_store, ets_store, ess_store;   // EigenSNP slot-ordered / subset copies (kept across calls)
   ScratchPool es_pool;                                        // EigenSNP call-scoped temporaries
+  std::vector<int64_t> es_subset;                             // the N_s-sample subset of the last EigenSNP call
+  uint64_t es_subset_n = 0, es_subset_seed = 0;
   DevBuf<float> es_cn;                                        // EigenSNP condensed features
   DevBuf<uint8_t> ingest_stage[2];   // device staging of the raw payload chunks (gpca_ingest_bed)
   uint8_t* h_up = nullptr;     // pinned staging for the per-chunk compacted vectors (gpca_ingest_bed)

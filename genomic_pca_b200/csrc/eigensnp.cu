@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "driver_util.cuh"
+#include "parallel_for.h"
 #include "philox.cuh"
 
 static int fail(gpca_ctx* c, int code, const std::string& msg) {
@@ -284,21 +285,30 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
   uint64_t Ns = (uint64_t)(cfg->subset_factor * (double)N);
   Ns = std::max<uint64_t>(cfg->min_subset_size, std::min<uint64_t>(Ns, cfg->max_subset_size));
   Ns = std::min<uint64_t>(Ns, N);
-  std::vector<int64_t> sub(Ns);
-  if (Ns == N) {
-    for (uint64_t i = 0; i < N; ++i) sub[i] = (int64_t)i;
-  } else {
-    std::vector<std::pair<uint32_t, uint64_t>> keys(N);
-    for (uint64_t i = 0; i < N; ++i) {
-      const Philox4 r = philox4x32_10((uint32_t)i, (uint32_t)(i >> 32), 0u, STREAM_SUBSET, (uint32_t)seed,
-                                      (uint32_t)(seed >> 32));
-      keys[i] = {r.x, i};
+  // (kept in the context: the subset depends only on N, N_s and the seed; the Philox keys are drawn on all host
+  //  threads and the selection is an nth_element -- ~8 ms single-threaded at N = 500,000)
+  std::vector<int64_t>& sub = c->es_subset;
+  if (!(c->es_subset_n == N && c->es_subset_seed == seed && sub.size() == Ns)) {
+    sub.assign(Ns, 0);
+    if (Ns == N) {
+      for (uint64_t i = 0; i < N; ++i) sub[i] = (int64_t)i;
+    } else {
+      std::vector<std::pair<uint32_t, uint64_t>> keys(N);
+      parallel_for(N, [&](uint64_t lo, uint64_t hi) {
+        for (uint64_t i = lo; i < hi; ++i) {
+          const Philox4 r = philox4x32_10((uint32_t)i, (uint32_t)(i >> 32), 0u, STREAM_SUBSET, (uint32_t)seed,
+                                          (uint32_t)(seed >> 32));
+          keys[i] = {r.x, i};
+        }
+      }, 1u << 14);
+      // the N_s smallest (key, index) pairs -- ties by index, the oracle's stable order; a selection is enough because
+      // the subset is then put in index order
+      std::nth_element(keys.begin(), keys.begin() + Ns, keys.end());
+      for (uint64_t i = 0; i < Ns; ++i) sub[i] = (int64_t)keys[i].second;
+      std::sort(sub.begin(), sub.end());
     }
-    // the N_s smallest (key, index) pairs -- ties by index, the oracle's stable order; a selection is enough because
-    // the subset is then put in index order
-    std::nth_element(keys.begin(), keys.begin() + Ns, keys.end());
-    for (uint64_t i = 0; i < Ns; ++i) sub[i] = (int64_t)keys[i].second;
-    std::sort(sub.begin(), sub.end());
+    c->es_subset_n = N;
+    c->es_subset_seed = seed;
   }
 
   // ---- device copies in slot order ----------------------------------------------------------------------

@@ -124,59 +124,69 @@ template <int LP>
 __device__ __forceinline__ void gram_partial_body(const float* __restrict__ y, uint32_t l, uint32_t ld,
                                                   const uint64_t r_begin, const uint64_t r_end,
                                                   double* __restrict__ p) {
-  constexpr int TPD = LP / 4;               // threads per dimension of the output
-  constexpr int GROUPS = 256 / (TPD * TPD); // 4 for LP = 32, 1 for LP = 64
+  // 4 x 4 output tiles, one per thread; only the ceil(l/4)^2 tiles that hold live columns are handed out, and the
+  // warps left over split the rows of a tile between them (8 row groups for l <= 20, 4 for l <= 32, ...) -- with the
+  // fixed 8 x 8 layout a 17-column Gram (EigenSNP's local bases) did 2.5x the useful FMAs.
+  constexpr int TROWS = (LP == 32) ? GRAM_ROWS : GRAM_ROWS / 2;      // rows staged at a time (f64: 17 KB either way)
   // the tile is widened to f64 once, while it is staged (the fp32 -> f64 conversion is a quarter-rate instruction: with
   // fp32 tiles every thread converted 8 values per 16 FMAs and the kernel was conversion-bound)
-  __shared__ __align__(16) double tile[GRAM_ROWS][LP + 2];
-  __shared__ double gsum[(GROUPS > 1) ? (GROUPS - 1) * LP * LP : 1];
-  const int grp = threadIdx.x / (TPD * TPD);
-  const int t = threadIdx.x % (TPD * TPD);
-  const int ti = t / TPD, tj = t % TPD;
+  __shared__ __align__(16) double tile[TROWS][LP + 2];
+  __shared__ double gsum[3072];                 // (groups - 1) x tiles x 16 <= 3072 for every split below
+  const int tr = ((int)l + 3) / 4;              // live tiles per dimension
+  const int tiles = tr * tr;
+  const int wpg = (tiles + 31) / 32;            // warps per row group: 1, 2, 3, 4, ... 8
+  const int groups = 8 / wpg;                   // 8, 4, 2, 2, 1 ...
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = warp / wpg;
+  const int t = (warp % wpg) * 32 + lane;
+  const bool active = grp < groups && t < tiles;
+  const int ti = active ? t / tr : 0, tj = active ? t % tr : 0;
   double acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-  for (uint64_t r0 = r_begin; r0 < r_end; r0 += GRAM_ROWS) {
-    for (int e = threadIdx.x; e < GRAM_ROWS * LP; e += 256) {
+  for (uint64_t r0 = r_begin; r0 < r_end; r0 += TROWS) {
+    for (int e = threadIdx.x; e < TROWS * LP; e += 256) {
       const int rr = e / LP, cc = e % LP;
       const uint64_t r = r0 + rr;
       tile[rr][cc] = (r < r_end && (uint32_t)cc < l) ? (double)y[r * ld + cc] : 0.0;
     }
     __syncthreads();
+    if (active) {
 #pragma unroll 4
-    for (int rr = grp; rr < GRAM_ROWS; rr += GROUPS) {
-      const double2 a0 = *reinterpret_cast<const double2*>(&tile[rr][ti * 4]);
-      const double2 a1 = *reinterpret_cast<const double2*>(&tile[rr][ti * 4 + 2]);
-      const double2 b0 = *reinterpret_cast<const double2*>(&tile[rr][tj * 4]);
-      const double2 b1 = *reinterpret_cast<const double2*>(&tile[rr][tj * 4 + 2]);
-      const double av[4] = {a0.x, a0.y, a1.x, a1.y};
-      const double bv[4] = {b0.x, b0.y, b1.x, b1.y};
+      for (int rr = grp; rr < TROWS; rr += groups) {
+        const double2 a0 = *reinterpret_cast<const double2*>(&tile[rr][ti * 4]);
+        const double2 a1 = *reinterpret_cast<const double2*>(&tile[rr][ti * 4 + 2]);
+        const double2 b0 = *reinterpret_cast<const double2*>(&tile[rr][tj * 4]);
+        const double2 b1 = *reinterpret_cast<const double2*>(&tile[rr][tj * 4 + 2]);
+        const double av[4] = {a0.x, a0.y, a1.x, a1.y};
+        const double bv[4] = {b0.x, b0.y, b1.x, b1.y};
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+          for (int j = 0; j < 4; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+      }
     }
     __syncthreads();
   }
-  if (GROUPS > 1) {
-    if (grp > 0) {
+  if (groups > 1) {
+    if (active && grp > 0) {
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) gsum[((grp - 1) * LP + ti * 4 + i) * LP + tj * 4 + j] = acc[i][j];
+        for (int j = 0; j < 4; ++j) gsum[((grp - 1) * tiles + t) * 16 + i * 4 + j] = acc[i][j];
     }
     __syncthreads();
-    if (grp == 0) {
+    if (active && grp == 0) {
+      for (int g = 0; g < groups - 1; ++g)      // fixed order: deterministic
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          for (int g = 0; g < GROUPS - 1; ++g) acc[i][j] += gsum[(g * LP + ti * 4 + i) * LP + tj * 4 + j];
+          for (int j = 0; j < 4; ++j) acc[i][j] += gsum[(g * tiles + t) * 16 + i * 4 + j];
     }
   }
-  if (grp == 0) {
+  if (active && grp == 0) {
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -952,7 +962,7 @@ int launch_rotation_batch(gpca_ctx* c, const DenseProb* d_probs, uint32_t n_prob
   return GPCA_OK;
 }
 
-// grid = (row tiles, problems)
+// grid = (row tiles, problems); same tiling as apply_right_kernel (128-row f64 tiles, row pairs, column pairs)
 template <int NOWN>
 __global__ void __launch_bounds__(256) apply_right_batch_kernel(const float* __restrict__ base, uint32_t ld,
                                                                 const DenseProb* __restrict__ probs,
@@ -960,7 +970,8 @@ __global__ void __launch_bounds__(256) apply_right_batch_kernel(const float* __r
                                                                 const uint32_t* __restrict__ l2s,
                                                                 float* __restrict__ out_base,
                                                                 const uint64_t* __restrict__ out_offs, uint32_t ldo) {
-  extern __shared__ double sm[];
+  static_assert(NOWN % 2 == 0, "columns are owned in pairs");
+  extern __shared__ __align__(16) double sm[];
   const DenseProb pb = probs[blockIdx.y];
   const uint32_t l = pb.l;
   const uint32_t l2 = l2s ? l2s[blockIdx.y] : l;
@@ -970,37 +981,57 @@ __global__ void __launch_bounds__(256) apply_right_batch_kernel(const float* __r
   const double* t = t_all + (size_t)blockIdx.y * 1024;
   const int l2p = NOWN * 4;
   double* ts = sm;                                             // [32][l2p]
-  float* tile = reinterpret_cast<float*>(sm + 32 * l2p);       // [64][33]
+  double* tile = sm + 32 * l2p;                                // [AR_ROWS][33]
   for (int i = threadIdx.x; i < (int)(l * l2p); i += 256) {
     const int cc = i / l2p, c2 = i % l2p;
     ts[i] = ((uint32_t)c2 < l2) ? t[cc * l2 + c2] : 0.0;
   }
   const int lp = 33;
-  const uint64_t ntiles = (n + 63) / 64;
+  const uint64_t ntiles = (n + AR_ROWS - 1) / AR_ROWS;
+  const bool vec2 = (ldo & 1u) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0;
   for (uint64_t tix = blockIdx.x; tix < ntiles; tix += gridDim.x) {
-    const uint64_t r0 = tix * 64;
+    const uint64_t r0 = tix * AR_ROWS;
     __syncthreads();
-    for (int i = threadIdx.x; i < 64 * (int)l; i += 256) {
-      const int rr = i / l, cc = i % l;
+    for (int i = threadIdx.x; i < AR_ROWS * (int)l; i += 256) {
+      const int rr = i / (int)l, cc = i % (int)l;
       const uint64_t r = r0 + rr;
-      tile[rr * lp + cc] = (r < n) ? y[r * ld + cc] : 0.0f;
+      tile[rr * lp + cc] = (r < n) ? (double)y[r * ld + cc] : 0.0;
     }
     __syncthreads();
     const int rr = threadIdx.x >> 2, cg = threadIdx.x & 3;
-    const uint64_t r = r0 + rr;
-    if (r < n) {
-      double acc[NOWN];
+    double acc0[NOWN], acc1[NOWN];
 #pragma unroll
-      for (int j = 0; j < NOWN; ++j) acc[j] = 0.0;
-      for (uint32_t cc = 0; cc < l; ++cc) {
-        const double yv = (double)tile[rr * lp + cc];
-        const double* trow = ts + cc * l2p + cg;
+    for (int j = 0; j < NOWN; ++j) acc0[j] = acc1[j] = 0.0;
+    const double* y0 = tile + rr * lp;
+    const double* y1 = tile + (rr + 64) * lp;
+    for (uint32_t cc = 0; cc < l; ++cc) {
+      const double a0 = y0[cc], a1 = y1[cc];
+      const double* trow = ts + cc * l2p + 2 * cg;
 #pragma unroll
-        for (int j = 0; j < NOWN; ++j) acc[j] = fma(yv, trow[4 * j], acc[j]);
+      for (int j = 0; j < NOWN / 2; ++j) {
+        const double2 tv = *reinterpret_cast<const double2*>(trow + 8 * j);
+        acc0[2 * j] = fma(a0, tv.x, acc0[2 * j]);
+        acc0[2 * j + 1] = fma(a0, tv.y, acc0[2 * j + 1]);
+        acc1[2 * j] = fma(a1, tv.x, acc1[2 * j]);
+        acc1[2 * j + 1] = fma(a1, tv.y, acc1[2 * j + 1]);
       }
+    }
 #pragma unroll
-      for (int j = 0; j < NOWN; ++j)
-        if (cg + 4u * j < l2) out[r * ldo + cg + 4 * j] = (float)acc[j];
+    for (int h = 0; h < 2; ++h) {
+      const uint64_t r = r0 + rr + 64 * h;
+      if (r >= n) continue;
+      const double* acc = h ? acc1 : acc0;
+      float* orow = out + r * ldo;
+#pragma unroll
+      for (int j = 0; j < NOWN / 2; ++j) {
+        const uint32_t c0 = 2 * cg + 8 * j;
+        if (vec2 && c0 + 1 < l2) {
+          *reinterpret_cast<float2*>(orow + c0) = make_float2((float)acc[2 * j], (float)acc[2 * j + 1]);
+        } else {
+          if (c0 < l2) orow[c0] = (float)acc[2 * j];
+          if (c0 + 1 < l2) orow[c0 + 1] = (float)acc[2 * j + 1];
+        }
+      }
     }
   }
 }
@@ -1009,8 +1040,11 @@ template <int NOWN>
 static int run_apply_right_batch(gpca_ctx* c, const float* d_base, uint32_t ld, const DenseProb* d_probs,
                                  uint32_t n_probs, uint64_t max_rows, const double* d_t, const uint32_t* d_l2,
                                  float* d_out, const uint64_t* d_out_offs, uint32_t ldo) {
-  const size_t smem = (size_t)32 * NOWN * 4 * sizeof(double) + (size_t)64 * 33 * sizeof(float);
-  uint64_t gx = (max_rows + 63) / 64;
+  const size_t smem = ((size_t)32 * NOWN * 4 + (size_t)AR_ROWS * 33) * sizeof(double);
+  if (smem > 48 * 1024)
+    GPCA_CUDA_TRY(c, cudaFuncSetAttribute(apply_right_batch_kernel<NOWN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)smem));
+  uint64_t gx = (max_rows + AR_ROWS - 1) / AR_ROWS;
   const uint64_t cap = ((uint64_t)c->sm_count * 16 + n_probs - 1) / n_probs;
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
@@ -1030,7 +1064,7 @@ int launch_apply_right_batch(gpca_ctx* c, const float* d_base, uint32_t ld, cons
   }
   const uint32_t need = (max_l2 + 3) / 4;
   if (need <= 2) return run_apply_right_batch<2>(c, d_base, ld, d_probs, n_probs, max_rows, d_t, d_l2, d_out, d_out_offs, ldo);
-  if (need <= 5) return run_apply_right_batch<5>(c, d_base, ld, d_probs, n_probs, max_rows, d_t, d_l2, d_out, d_out_offs, ldo);
+  if (need <= 6) return run_apply_right_batch<6>(c, d_base, ld, d_probs, n_probs, max_rows, d_t, d_l2, d_out, d_out_offs, ldo);
   return run_apply_right_batch<8>(c, d_base, ld, d_probs, n_probs, max_rows, d_t, d_l2, d_out, d_out_offs, ldo);
 }
 
