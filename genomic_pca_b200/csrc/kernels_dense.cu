@@ -146,13 +146,29 @@ __device__ __forceinline__ void gram_partial_body(const float* __restrict__ y, u
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-  for (uint64_t r0 = r_begin; r0 < r_end; r0 += TROWS) {
-    for (int e = threadIdx.x; e < TROWS * LP; e += 256) {
+  // The next tile's global loads are in flight while the current one is multiplied (registers -> f64 tile after the
+  // barrier): with load -> barrier -> multiply -> barrier in sequence the kernel ran at the global-memory latency
+  // (0.4 TB/s on the 37,500 x 17 per-block matrices of EigenSNP's local bases).
+  constexpr int NLD = TROWS * LP / 256;
+  float stg[NLD];
+  auto fetch = [&](uint64_t r0) {
+#pragma unroll
+    for (int q = 0; q < NLD; ++q) {
+      const int e = threadIdx.x + q * 256;
       const int rr = e / LP, cc = e % LP;
       const uint64_t r = r0 + rr;
-      tile[rr][cc] = (r < r_end && (uint32_t)cc < l) ? (double)y[r * ld + cc] : 0.0;
+      stg[q] = (r < r_end && (uint32_t)cc < l) ? __ldg(y + r * ld + cc) : 0.0f;
+    }
+  };
+  if (r_begin < r_end) fetch(r_begin);
+  for (uint64_t r0 = r_begin; r0 < r_end; r0 += TROWS) {
+#pragma unroll
+    for (int q = 0; q < NLD; ++q) {
+      const int e = threadIdx.x + q * 256;
+      tile[e / LP][e % LP] = (double)stg[q];
     }
     __syncthreads();
+    if (r0 + TROWS < r_end) fetch(r0 + TROWS);
     if (active) {
 #pragma unroll 4
       for (int rr = grp; rr < TROWS; rr += groups) {
@@ -195,7 +211,7 @@ __device__ __forceinline__ void gram_partial_body(const float* __restrict__ y, u
 }
 
 template <int LP>
-__global__ void __launch_bounds__(256) gram_partial_kernel(const float* __restrict__ y, uint64_t n, uint32_t l,
+__global__ void __launch_bounds__(256, 3) gram_partial_kernel(const float* __restrict__ y, uint64_t n, uint32_t l,
                                                            uint32_t ld, uint64_t rows_per_cta,
                                                            double* __restrict__ partial) {
   const uint64_t r_begin = blockIdx.x * rows_per_cta;
@@ -205,7 +221,7 @@ __global__ void __launch_bounds__(256) gram_partial_kernel(const float* __restri
 }
 
 // batched: grid = (parts, problems); partial of (problem b, part q) at [(b * parts + q) * 1024]
-__global__ void __launch_bounds__(256) gram_batch_kernel(const float* __restrict__ base, uint32_t ld,
+__global__ void __launch_bounds__(256, 3) gram_batch_kernel(const float* __restrict__ base, uint32_t ld,
                                                          const DenseProb* __restrict__ probs,
                                                          double* __restrict__ partial) {
   const DenseProb pb = probs[blockIdx.y];
@@ -258,12 +274,24 @@ __global__ void __launch_bounds__(256) cross_gram_partial_kernel(const float* __
   uint64_t r_end = r_begin + rows_per_cta;
   if (r_end > n) r_end = n;
   for (uint64_t r0 = r_begin; r0 < r_end; r0 += GRAM_ROWS / 2) {
-    for (int e = threadIdx.x; e < (GRAM_ROWS / 2) * LP; e += 256) {
-      const int rr = e / LP, cc = e % LP;
-      const uint64_t r = r0 + rr;
-      const bool live = r < r_end && (uint32_t)cc < l;
-      ta[rr][cc] = live ? (double)a[r * ld + cc] : 0.0;
-      tb[rr][cc] = live ? (double)b[r * ld + cc] : 0.0;
+    {
+      constexpr int NLD = (GRAM_ROWS / 2) * LP / 256;
+      float sa[NLD], sb[NLD];
+#pragma unroll
+      for (int q = 0; q < NLD; ++q) {
+        const int e = threadIdx.x + q * 256;
+        const int rr = e / LP, cc = e % LP;
+        const uint64_t r = r0 + rr;
+        const bool live = r < r_end && (uint32_t)cc < l;
+        sa[q] = live ? __ldg(a + r * ld + cc) : 0.0f;
+        sb[q] = live ? __ldg(b + r * ld + cc) : 0.0f;
+      }
+#pragma unroll
+      for (int q = 0; q < NLD; ++q) {
+        const int e = threadIdx.x + q * 256;
+        ta[e / LP][e % LP] = (double)sa[q];
+        tb[e / LP][e % LP] = (double)sb[q];
+      }
     }
     __syncthreads();
 #pragma unroll 4
@@ -378,15 +406,38 @@ __global__ void __launch_bounds__(256) apply_right_kernel(const float* __restric
   }
   const uint64_t ntiles = (n + AR_ROWS - 1) / AR_ROWS;
   const bool vec2 = (ldo & 1u) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0;
+  // warp = row, lane = column; for l <= 32 the next tile's loads are in flight while the current tile is multiplied
+  float stg[AR_ROWS / 8];
+  auto fetch = [&](uint64_t r0, uint32_t c0) {
+    const uint32_t cc = c0 + (threadIdx.x & 31);
+#pragma unroll
+    for (int q = 0; q < AR_ROWS / 8; ++q) {
+      const uint64_t r = r0 + (threadIdx.x >> 5) + 8 * q;
+      stg[q] = (r < n && cc < l) ? __ldg(y + r * ld + cc) : 0.0f;
+    }
+  };
+  if (l <= 32 && blockIdx.x < ntiles) fetch((uint64_t)blockIdx.x * AR_ROWS, 0);
   for (uint64_t tix = blockIdx.x; tix < ntiles; tix += gridDim.x) {
     const uint64_t r0 = tix * AR_ROWS;
     __syncthreads();
-    for (int i = threadIdx.x; i < AR_ROWS * (int)l; i += 256) {
-      const int rr = i / (int)l, cc = i % (int)l;
-      const uint64_t r = r0 + rr;
-      tile[rr * lp + cc] = (r < n) ? (double)y[r * ld + cc] : 0.0;
+    if (l <= 32) {      // registers prefetched during the previous tile's multiply -> f64 tile
+      const uint32_t cc = threadIdx.x & 31;
+      if (cc < l) {
+#pragma unroll
+        for (int q = 0; q < AR_ROWS / 8; ++q) tile[((threadIdx.x >> 5) + 8 * q) * lp + cc] = (double)stg[q];
+      }
+    } else {
+      for (uint32_t c0 = 0; c0 < l; c0 += 32) {
+        fetch(r0, c0);
+        const uint32_t cc = c0 + (threadIdx.x & 31);
+        if (cc < l) {
+#pragma unroll
+          for (int q = 0; q < AR_ROWS / 8; ++q) tile[((threadIdx.x >> 5) + 8 * q) * lp + cc] = (double)stg[q];
+        }
+      }
     }
     __syncthreads();
+    if (l <= 32 && tix + gridDim.x < ntiles) fetch((tix + gridDim.x) * AR_ROWS, 0);
     const int rr = threadIdx.x >> 2, cg = threadIdx.x & 3;
     double acc0[NOWN], acc1[NOWN];
 #pragma unroll
@@ -989,15 +1040,38 @@ __global__ void __launch_bounds__(256) apply_right_batch_kernel(const float* __r
   const int lp = 33;
   const uint64_t ntiles = (n + AR_ROWS - 1) / AR_ROWS;
   const bool vec2 = (ldo & 1u) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0;
+  // warp = row, lane = column; for l <= 32 the next tile's loads are in flight while the current tile is multiplied
+  float stg[AR_ROWS / 8];
+  auto fetch = [&](uint64_t r0, uint32_t c0) {
+    const uint32_t cc = c0 + (threadIdx.x & 31);
+#pragma unroll
+    for (int q = 0; q < AR_ROWS / 8; ++q) {
+      const uint64_t r = r0 + (threadIdx.x >> 5) + 8 * q;
+      stg[q] = (r < n && cc < l) ? __ldg(y + r * ld + cc) : 0.0f;
+    }
+  };
+  if (l <= 32 && blockIdx.x < ntiles) fetch((uint64_t)blockIdx.x * AR_ROWS, 0);
   for (uint64_t tix = blockIdx.x; tix < ntiles; tix += gridDim.x) {
     const uint64_t r0 = tix * AR_ROWS;
     __syncthreads();
-    for (int i = threadIdx.x; i < AR_ROWS * (int)l; i += 256) {
-      const int rr = i / (int)l, cc = i % (int)l;
-      const uint64_t r = r0 + rr;
-      tile[rr * lp + cc] = (r < n) ? (double)y[r * ld + cc] : 0.0;
+    if (l <= 32) {      // registers prefetched during the previous tile's multiply -> f64 tile
+      const uint32_t cc = threadIdx.x & 31;
+      if (cc < l) {
+#pragma unroll
+        for (int q = 0; q < AR_ROWS / 8; ++q) tile[((threadIdx.x >> 5) + 8 * q) * lp + cc] = (double)stg[q];
+      }
+    } else {
+      for (uint32_t c0 = 0; c0 < l; c0 += 32) {
+        fetch(r0, c0);
+        const uint32_t cc = c0 + (threadIdx.x & 31);
+        if (cc < l) {
+#pragma unroll
+          for (int q = 0; q < AR_ROWS / 8; ++q) tile[((threadIdx.x >> 5) + 8 * q) * lp + cc] = (double)stg[q];
+        }
+      }
     }
     __syncthreads();
+    if (l <= 32 && tix + gridDim.x < ntiles) fetch((tix + gridDim.x) * AR_ROWS, 0);
     const int rr = threadIdx.x >> 2, cg = threadIdx.x & 3;
     double acc0[NOWN], acc1[NOWN];
 #pragma unroll
