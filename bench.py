@@ -66,6 +66,9 @@ def peaks():
 
 
 class ClockSampler:
+    """SM clock, power and throttle reasons sampled DURING the timed region.  NVML is polled every 5 ms from a thread
+    (one rfit step is ~15 ms: `nvidia-smi -lms 100` sees one or two samples of a default run); nvidia-smi is the
+    fallback when pynvml is missing."""
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -73,8 +76,32 @@ class ClockSampler:
         self.index = index
         self.rows = []
         self.proc = None
+        self.nvml = None
+        self.stop_flag = False
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES-relative index -> NVML handle through the PCI bus id
+            import torch
+            bus = torch.cuda.get_device_properties(self.index).pci_bus_id if hasattr(
+                torch.cuda.get_device_properties(self.index), "pci_bus_id") else None
+            self.h = None
+            if bus is not None:
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    hh = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    if pynvml.nvmlDeviceGetPciInfo(hh).bus == bus:
+                        self.h = hh
+                        break
+            if self.h is None:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.nvml = pynvml
+            self.thr = threading.Thread(target=self._poll, daemon=True)
+            self.thr.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -84,11 +111,37 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        nv = self.nvml
+        while not self.stop_flag:
+            try:
+                self.rows.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM),
+                                  nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM),
+                                  nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h),
+                                  nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0))
+            except Exception:
+                pass
+            time.sleep(0.005)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thr.join(timeout=1.0)
+            nv = self.nvml
+            bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                    "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                    "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+            reasons = sorted(nm for nm, bit in bits.items() if any(r[2] & bit for r in self.rows))
+            sm = [r[0] for r in self.rows]
+            pw = [r[3] for r in self.rows]
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_min_mhz": float(min(sm)) if sm else None,
+                    "sm_max_mhz": float(max(r[1] for r in self.rows)) if self.rows else None, "reasons": reasons,
+                    "power_w": float(np.median(pw)) if pw else None, "samples": len(sm), "source": "nvml, 5 ms"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -112,7 +165,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 # ------------------------------------------------------------------------------------------
@@ -357,9 +410,9 @@ def run_ours(args, rank, world):
 
 
 # DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum, bytes per launch) of sketch_i8_kernel at config 3 from the
-# committed ncu capture (profiles/r1_ncu_full_sketch_i8_kernel_c3_final.csv): sample side 7.335 + 0.050 GB, snp side
-# 6.497 + 1.245 GB; one rfit runs 4 sample-side and 3 snp-side launches.  Only valid for the default workload.
-TRAFFIC_NCU = {2: (4 * 7.385e9 + 3 * 7.7425e9) / 7}
+# committed ncu capture (profiles/r1_ncu_full_sketch_i8_kernel_c3_final2.csv): sample side 7.378 + 0.040 GB, snp side
+# 6.480 + 1.268 GB; one rfit runs 4 sample-side and 3 snp-side launches.  Only valid for the default workload.
+TRAFFIC_NCU = {2: (4 * 7.418e9 + 3 * 7.748e9) / 7}
 
 
 def ukb_shard_supplement(torch, gp, dev, pk, rank=0, world=1, dist=None):
