@@ -804,8 +804,9 @@ int timed_sketch_batch(gpca_ctx* c, const SketchBatch& sb) {
 }
 
 int sketch_snp_side(gpca_ctx* c, const float* dev_in, float* dev_out, uint32_t l, uint32_t ld_in, uint32_t ld_out,
-                    bool emit_stats) {
+                    bool emit_stats, bool out_pad) {
   SketchProblem p;
+  p.out_pad = out_pad;
   p.emit_stats = emit_stats;   // (the statistic is the max-abs over the l logical columns: independent of the stride)
   p.G = c->Gs;
   p.Bin = dev_in;
@@ -848,7 +849,7 @@ extern "C" int gpca_sketch_snp_side(gpca_ctx* c, const float* dev_in, float* dev
   GPCA_CUDA_TRY(c, cudaSetDevice(c->device));
   if (c->D == 0) return fail(c, GPCA_ERR_INVALID, "gpca_set_pca_snps has not been called");
   if (l == 0 || l > 64 || ld < l) return fail(c, GPCA_ERR_INVALID, "need 1 <= l <= 64 and ld >= l");
-  return sketch_snp_side(c, dev_in, dev_out, l, ld, ld, false);
+  return sketch_snp_side(c, dev_in, dev_out, l, ld, ld, false, false);
 }
 
 extern "C" int gpca_sketch_sample_side(gpca_ctx* c, const float* dev_in, float* dev_out, uint32_t l, uint32_t ld) {

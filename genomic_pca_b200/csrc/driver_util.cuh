@@ -33,8 +33,9 @@ int download_results(gpca_ctx* c, const float* d_src, uint64_t count, float* dst
 // emit_stats: also leave the operand statistics of the output (as the next sample-side pass needs them) in the context;
 // use_stats: the operand's statistics are in the context (it was produced by such a pass or by
 // launch_gaussian_with_stats and has not been modified since)
+// out_pad: the caller owns columns [l, ld_out) of every output row as padding (they may be overwritten with zeros)
 int sketch_snp_side(gpca_ctx* c, const float* dev_in, float* dev_out, uint32_t l, uint32_t ld_in, uint32_t ld_out,
-                    bool emit_stats = false);
+                    bool emit_stats = false, bool out_pad = false);
 int sketch_sample_side(gpca_ctx* c, const float* dev_in, float* dev_out, uint32_t l, uint32_t ld_in, uint32_t ld_out,
                        bool use_stats = false);
 // generic timed sketch on an arbitrary view (used by the EigenSNP driver)

@@ -36,10 +36,15 @@ int driver_allreduce(gpca_ctx* c, void* buf, uint64_t count, int dtype) {
 }
 
 int download_results(gpca_ctx* c, const float* d_src, uint64_t count, float* dst_f32, double* dst_f64) {
-  constexpr uint64_t CH = 1u << 21;      // floats per chunk (8 MB)
+  constexpr uint64_t CH_MAX = 1u << 21;      // floats per chunk (8 MB landing buffers)
   if (count == 0 || (!dst_f32 && !dst_f64)) return GPCA_OK;
+  uint64_t CH = CH_MAX;
+  if (const char* e = getenv("GPCA_DEBUG_DOWNLOAD_CHUNK")) {   // tests: force many chunks on small results
+    const uint64_t v = strtoull(e, nullptr, 10);
+    if (v >= 1 && v <= CH_MAX) CH = v;
+  }
   for (int i = 0; i < 2; ++i) {
-    if (!c->h_dl[i]) GPCA_CUDA_TRY(c, cudaMallocHost((void**)&c->h_dl[i], CH * sizeof(float)));
+    if (!c->h_dl[i]) GPCA_CUDA_TRY(c, cudaMallocHost((void**)&c->h_dl[i], CH_MAX * sizeof(float)));
     if (!c->ev_dl[i]) GPCA_CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_dl[i], cudaEventDisableTiming));
   }
   auto land = [&](uint64_t q) {          // chunk q has arrived in its buffer: hand it to the caller's memory
@@ -152,13 +157,13 @@ extern "C" int gpca_rfit(gpca_ctx* c, uint32_t k, uint32_t oversample, uint32_t 
   GPCA_TRY(sketch_sample_side(c, Z.p, Y.p, l, ldz, l, true));
   for (uint32_t it = 0; it < power_iters; ++it) {
     GPCA_TRY(orthonormalize(c, Y.p, N, l, l, false, s));
-    GPCA_TRY(sketch_snp_side(c, Y.p, Z.p, l, l, ldz, true));   // Z = S Q
+    GPCA_TRY(sketch_snp_side(c, Y.p, Z.p, l, l, ldz, true, true));   // Z = S Q
     // (range(S^T Z) does not depend on a column transform of Z; the snp-side basis is left unnormalised
     //  between the two half-steps, the sample side is re-orthonormalised every iteration)
     GPCA_TRY(sketch_sample_side(c, Z.p, Y.p, l, ldz, l, true));   // Y = S^T Z
   }
   GPCA_TRY(orthonormalize(c, Y.p, N, l, l, false, s));
-  GPCA_TRY(sketch_snp_side(c, Y.p, Z.p, l, l, ldz, true));  // B = S Q   [D x l]
+  GPCA_TRY(sketch_snp_side(c, Y.p, Z.p, l, l, ldz, true, true));  // B = S Q   [D x l]
   // B^T B = Q^T (S^T B): the l x l matrix whose eigen-decomposition gives the singular values and the right factor of
   // B comes from the sample-side sketch of B -- which is also all that the scores need (scores = S^T B V_b / s).  The
   // D-row Gram of B and, when the rotation is not asked for, every D x l by l x k product disappear; on several GPUs

@@ -106,6 +106,7 @@ struct SketchProblem {
   const float* b;         // [rows] per-row weight of the rank-one term (nullptr = 1)
   float* out;             // [rows x ldo]
   uint32_t ldo;
+  bool out_pad = false;   // columns [l, ldo) of `out` are padding the pass may overwrite with zeros (wide row stores)
   // Operand statistics as by-products (integer engine; ignored elsewhere).  A sample-side pass needs, for its operand
   // W, the column sums e^T W and max |f o W|; when W was just produced by a snp-side pass (f = that pass's a, e = its
   // b) or by the Gaussian generator, the producer computes them on the way out and one sweep over W is saved.

@@ -92,6 +92,7 @@ struct I8Params {
   float* partial;       // [ksplit][rows][32]
   const I8Item* items;  // item mode (batched per-LD-block passes): explicit work list, no split-K partials
   unsigned int* stat_amax;   // regular mode, direct output: max |a_r * out[r,:]| (float bits) as a by-product, or null
+  uint32_t pad_cols;         // columns [l, pad_cols) of every output row are padding owned by this pass (SketchProblem::out_pad)
 };
 
 // What one work item covers.  Regular mode derives it from (k-split, row group); item mode reads it from the table.
@@ -472,7 +473,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) sketch_i8_kernel(const __grid_
               if ((uint32_t)(c + j) >= ii.l) v[j] = 0.0f;
               hi[c + j] = __float_as_uint(v[j]);       // kept for the statistics below
             }
-            if (vec8 && (uint32_t)c < ii.l && (uint32_t)c + 8 <= p.ldo) {
+            // (a 32-byte store may run past column l only into padding that belongs to this output: with a column view
+            //  into a wider matrix -- the condensed features of EigenSNP -- the neighbours' columns live there)
+            if (vec8 && ((uint32_t)c + 8 <= ii.l || ((uint32_t)c < ii.l && (uint32_t)c + 8 <= p.pad_cols))) {
               asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + c), "f"(v[0]), "f"(v[1]),
                            "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
                            : "memory");
@@ -915,6 +918,7 @@ int launch_sketch_i8(gpca_ctx* c, const SketchProblem& p) {
   const bool emit = p.emit_stats && !c->any_missing && !getenv("GPCA_DEBUG_NO_EMIT_STATS");
   if (emit) GPCA_TRY(stats_begin_produce(c, st_amax));
   tp.stat_amax = (emit && ksplit == 1) ? st_amax : nullptr;
+  tp.pad_cols = p.out_pad ? std::min<uint32_t>(p.ldo, (p.l + 7u) & ~7u) : 0;
   if (ksplit > 1) {
     GPCA_CUDA_TRY(c, c->ws_partial.alloc((size_t)ksplit * rows * NL));
     tp.partial = c->ws_partial.p;
@@ -1025,6 +1029,7 @@ int launch_sketch_i8_batch(gpca_ctx* c, const SketchBatch& sb) {
   tp.partial = nullptr;
   tp.items = sb.d_items;
   tp.stat_amax = nullptr;
+  tp.pad_cols = 0;
   CUtensorMap tmap;
   {
     EncodeTiledFn enc = get_encode_fn_i8();

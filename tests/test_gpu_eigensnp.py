@@ -171,3 +171,46 @@ def test_bed_to_eigensnp_flow_on_chr22_rows(gpu_ctx, golden_rows, tmp_path):
     lines = (tmp_path / "out.eigensnp.pca.tsv").read_text().splitlines()
     assert lines[0].split("\t")[:3] == ["SampleID", "PC1", "PC2"] and len(lines) == 65
     assert (tmp_path / "out.eigenvalues.tsv").read_text().splitlines()[0] == "PC\tEigenvalue"
+
+
+def test_eigensnp_shifted_copy_and_block_groups(gpu_ctx, monkeypatch):
+    """Blocks that are runs of consecutive SNP ids take the shifted-copy layout path and the grouped condensed-feature
+    pass.  The shifted copy must reproduce the gather + transpose layout exactly (same results bit for bit); grouping
+    changes the quantisation scale of the block-diagonal operand (one per group instead of one per block), so it is
+    compared within the parity tolerances.  Block sizes straddle the 64-field slot padding and the 256-field stage; the
+    component counts make groups of 1 to 4 blocks."""
+    import genomic_pca_b200 as gp
+    S = _prep(gpu_ctx, 1100, 4200, 5, seed=41)
+    d = S.shape[0]
+    sizes = [65, 63, 64, 1, 255, 257, 300, 130, 5, 700, 412, 412, 412, 412, 100]
+    edges = [0]
+    for sz in sizes:
+        if edges[-1] + sz < d:
+            edges.append(edges[-1] + sz)
+    edges.append(d)
+    blocks = [np.arange(edges[i], edges[i + 1]) for i in range(len(edges) - 1)]
+    cfg = gp.EigenSnpConfig(target_num_global_pcs=4, components_per_ld_block=7, subset_factor=0.5, min_subset_size=300,
+                            max_subset_size=700, local_oversampling=6, global_oversampling=8, random_seed=13,
+                            refine_pass_count=1)
+    gpu_ctx.set_sketch_engine(2)
+    gpu_ctx.set_batch_blocks(True)
+    for v in ("GPCA_DEBUG_NO_SHIFT_COPY", "GPCA_DEBUG_NO_GROUPS"):
+        monkeypatch.delenv(v, raising=False)
+    sc, ev, load = gpu_ctx.eigensnp(blocks, cfg)
+    # run to run: bit for bit (this configuration caught a wide row store of the sketch epilogue spilling zeros into the
+    # neighbouring blocks' columns of the condensed matrix -- a race between work items)
+    sc_r, ev_r, load_r = gpu_ctx.eigensnp(blocks, cfg)
+    assert np.array_equal(sc, sc_r) and np.array_equal(ev, ev_r) and np.array_equal(load, load_r)
+    monkeypatch.setenv("GPCA_DEBUG_NO_SHIFT_COPY", "1")
+    sc_t, ev_t, load_t = gpu_ctx.eigensnp(blocks, cfg)
+    assert np.array_equal(sc, sc_t) and np.array_equal(ev, ev_t) and np.array_equal(load, load_t)
+    monkeypatch.setenv("GPCA_DEBUG_NO_GROUPS", "1")
+    sc_g, ev_g, load_g = gpu_ctx.eigensnp(blocks, cfg)
+    assert np.abs(ev / ev_g - 1).max() < 1e-5
+    assert pca.subspace_angle(sc, sc_g) < 1e-4
+    assert pca.subspace_angle(load, load_g) < 1e-4
+    sc_o, ev_o, ld_o = pca.eigensnp(S, blocks, k=4, components_per_block=7, subset_factor=0.5, min_subset=300,
+                                    max_subset=700, local_oversampling=6, global_oversampling=8, seed=13,
+                                    refine_passes=1)
+    assert np.abs(ev / ev_o - 1).max() < 1e-4
+    assert pca.subspace_angle(sc, sc_o) < 1e-3

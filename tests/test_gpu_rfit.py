@@ -64,3 +64,18 @@ def test_rfit_reference_argument_rules(gpu_ctx):
     c = gpu_ctx.rfit(3, 10, seed=None)[1]
     # 3 populations -> 2 structured components; the third sits in the noise bulk and depends on Omega
     assert np.all(np.isfinite(c)) and np.abs(c[:2] / a[:2] - 1).max() < 0.05 and abs(c[2] / a[2] - 1) < 0.3
+
+
+def test_results_download_in_chunks(gpu_ctx, monkeypatch):
+    """Scores (widened to f64 on host threads) and loadings leave the device through pinned landing buffers in chunks;
+    a forced chunk of 1,000 floats (dozens of chunks, both buffers in use, ragged tail) must give the same arrays as the
+    single-chunk path, bit for bit."""
+    _prep(gpu_ctx, 700, 3000, 4, seed=3)
+    monkeypatch.delenv("GPCA_DEBUG_DOWNLOAD_CHUNK", raising=False)
+    sc1, ev1, ld1 = gpu_ctx.rfit(6, 10, power_iters=2, seed=11, want_loadings=True)
+    monkeypatch.setenv("GPCA_DEBUG_DOWNLOAD_CHUNK", "1000")
+    sc2, ev2, ld2 = gpu_ctx.rfit(6, 10, power_iters=2, seed=11, want_loadings=True)
+    assert sc1.dtype == np.float64 and ld1.dtype == np.float32
+    assert np.array_equal(sc1, sc2) and np.array_equal(ld1, ld2) and np.array_equal(ev1, ev2)
+    # the f64 scores are exactly the widened fp32 values
+    assert np.array_equal(sc1, sc1.astype(np.float32).astype(np.float64))
