@@ -376,12 +376,21 @@ class Context:
         self._chk(lib.gpca_synchronize(self._h))
 
     # -- drivers
-    def rfit(self, k, oversample=10, power_iters=2, seed=None, want_loadings=True):
+    def rfit(self, k, oversample=10, power_iters=2, seed=None, want_loadings=True, out=None):
+        """`out` = (scores f64 [N, k], eigenvalues f64 [k], loadings f32 [D, k] or None): caller-owned result buffers,
+        as the C ABI has them (a host that calls repeatedly allocates them once; fresh `np.zeros` arrays are mapped
+        lazily and page-fault while the results land -- 20,000 faults for the 500,000 x 20 f64 scores)."""
         n, d = self.num_samples, self.num_pca_snps
         kk = max(1, min(k, n))
-        scores = np.zeros((n, kk), dtype=np.float64)
-        ev = np.zeros(kk, dtype=np.float64)
-        load = np.zeros((d, kk), dtype=np.float32) if want_loadings else None
+        if out is not None:
+            scores, ev, load = out
+            assert scores.dtype == np.float64 and scores.shape == (n, kk) and scores.flags.c_contiguous
+            assert ev.dtype == np.float64 and ev.shape == (kk,)
+            assert load is None or (load.dtype == np.float32 and load.shape == (d, kk) and load.flags.c_contiguous)
+        else:
+            scores = np.zeros((n, kk), dtype=np.float64)
+            ev = np.zeros(kk, dtype=np.float64)
+            load = np.zeros((d, kk), dtype=np.float32) if want_loadings else None
         kout = C.c_uint32(0)
         self._chk(lib.gpca_rfit(self._h, k, oversample, power_iters, 0 if seed is None else int(seed),
                                 0 if seed is None else 1, _ptr(scores, _f64p), _ptr(ev, _f64p), _ptr(load, _f32p),
@@ -394,7 +403,8 @@ class Context:
                 load = load.reshape(-1)[:d * ko].reshape(d, ko)
         return scores, ev, load
 
-    def eigensnp(self, block_snp_ids, cfg: EigenSnpConfig | None = None):
+    def eigensnp(self, block_snp_ids, cfg: EigenSnpConfig | None = None, out=None):
+        """`out` = (scores f32 [N, k], eigenvalues f64 [k], loadings f32 [D, k]): caller-owned result buffers (see rfit)."""
         cfg = cfg or EigenSnpConfig()
         n, d = self.num_samples, self.num_pca_snps
         offs = np.zeros(len(block_snp_ids) + 1, dtype=np.uint64)
@@ -404,9 +414,15 @@ class Context:
                 if len(block_snp_ids) else np.zeros(0, dtype=np.uint64))
         flat = np.ascontiguousarray(flat, dtype=np.uint64)
         k = int(cfg.target_num_global_pcs)
-        scores = np.zeros((n, k), dtype=np.float32)
-        ev = np.zeros(k, dtype=np.float64)
-        load = np.zeros((d, k), dtype=np.float32)
+        if out is not None:
+            scores, ev, load = out
+            assert scores.dtype == np.float32 and scores.shape == (n, k) and scores.flags.c_contiguous
+            assert ev.dtype == np.float64 and ev.shape == (k,)
+            assert load.dtype == np.float32 and load.shape == (d, k) and load.flags.c_contiguous
+        else:
+            scores = np.zeros((n, k), dtype=np.float32)
+            ev = np.zeros(k, dtype=np.float64)
+            load = np.zeros((d, k), dtype=np.float32)
         kout = C.c_uint32(0)
         self._chk(lib.gpca_eigensnp(self._h, C.byref(cfg), _ptr(offs, _u64p), len(block_snp_ids), _ptr(flat, _u64p),
                                     _ptr(scores, _f32p), _ptr(ev, _f64p), _ptr(load, _f32p), C.byref(kout)))
