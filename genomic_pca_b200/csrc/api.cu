@@ -65,6 +65,7 @@ extern "C" void gpca_destroy(gpca_ctx* c) {
     cudaEventDestroy(pr.second);
   }
   if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->h_cnt) cudaFreeHost(c->h_cnt);
   if (c->h_up) cudaFreeHost(c->h_up);
   for (int i = 0; i < 2; ++i) {
@@ -473,6 +474,34 @@ static int ingest_core(gpca_ctx* c, const uint8_t* host_payload, int fd, uint64_
   c->Gs.pitch = round_up((N + 3) / 4, 128);
   GPCA_CUDA_TRY(c, c->gs_store.alloc(c->Gs.pitch * M));
   c->Gs.p = c->gs_store.p;
+  // Sample-major copy built behind the transfer: when memory allows (staging copy, Gs and a Gt whose row pitch covers
+  // all M SNPs at once) every chunk's complete 512-row tiles of Gs are transposed as soon as they exist; only the tail
+  // is left for the end of the call (the whole-matrix transpose was a 9 ms tail at 2,504 x 10M).  The pitch is then
+  // the one for M columns whatever the QC keeps; the matrix is zeroed once, columns past D stay zero.
+  bool incr_t = false;
+  uint64_t t_done = 0;
+  {
+    const size_t pitch_max = round_up((M + 3) / 4, 128);
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    if (!getenv("GPCA_DEBUG_NO_INCR_TRANSPOSE") &&
+        (c->gt_store.n >= pitch_max * N || free_b > pitch_max * N + (16ull << 30))) {
+      GPCA_CUDA_TRY(c, c->gt_store.alloc(pitch_max * N));
+      c->Gt.p = c->gt_store.p;
+      c->Gt.pitch = pitch_max;
+      c->Gt.rows = N;
+      GPCA_CUDA_TRY(c, cudaMemsetAsync(c->Gt.p, 0, pitch_max * N, c->stream));
+      incr_t = true;
+    }
+  }
+  auto transpose_rows = [&](uint64_t r_begin, uint64_t r_end) -> int {   // Gs rows [r_begin, r_end) -> Gt columns
+    if (r_end <= r_begin) return GPCA_OK;
+    PackedMat sv = c->Gs, dv = c->Gt;
+    sv.p = c->Gs.p + r_begin * c->Gs.pitch;
+    sv.rows = r_end - r_begin;
+    dv.p = c->Gt.p + r_begin / 4;          // r_begin is a multiple of 512: a multiple of 128 bytes
+    return launch_transpose(c, sv, dv);
+  };
   if (c->h_cnt_cap < M) {
     if (c->h_cnt) cudaFreeHost(c->h_cnt);
     c->h_cnt = nullptr;
@@ -504,12 +533,18 @@ static int ingest_core(gpca_ctx* c, const uint8_t* host_payload, int fd, uint64_
     }
   }
   DevBuf<uint8_t>* stage = c->ingest_stage;   // kept across calls (no per-call cudaMalloc / cudaFree)
-  cudaEvent_t stage_free[2] = {nullptr, nullptr}, up_free[2] = {nullptr, nullptr};
+  // The payload crosses PCIe on its own stream: on the compute stream every chunk's transfer queued behind the
+  // previous chunk's kernels (repitch, counts, recode, transpose tiles: ~0.45 ms per 128 MB chunk, 20 ms per 6.26 GB).
+  if (!c->copy_stream) GPCA_CUDA_TRY(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  const bool use_copy_stream = !getenv("GPCA_DEBUG_NO_COPY_STREAM");
+  cudaEvent_t stage_free[2] = {nullptr, nullptr}, up_free[2] = {nullptr, nullptr}, h2d_done[2] = {nullptr, nullptr};
   std::vector<cudaEvent_t> cnt_ready(n_chunks, nullptr);
   auto cleanup = [&]() {
+    cudaStreamSynchronize(c->copy_stream);
     for (int i = 0; i < 2; ++i) {
       if (stage_free[i]) cudaEventDestroy(stage_free[i]);
       if (up_free[i]) cudaEventDestroy(up_free[i]);
+      if (h2d_done[i]) cudaEventDestroy(h2d_done[i]);
     }
     for (auto e : cnt_ready)
       if (e) cudaEventDestroy(e);
@@ -518,6 +553,7 @@ static int ingest_core(gpca_ctx* c, const uint8_t* host_payload, int fd, uint64_
     GPCA_CUDA_TRY(c, stage[i].alloc(rows_per_chunk * in_pitch + 16));
     cudaEventCreateWithFlags(&stage_free[i], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&up_free[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h2d_done[i], cudaEventDisableTiming);
   }
   for (auto& e : cnt_ready) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
 
@@ -608,6 +644,11 @@ static int ingest_core(gpca_ctx* c, const uint8_t* host_payload, int fd, uint64_
     GPCA_CUDA_TRY(c, cudaEventRecord(up_free[ub], c->stream));
     t_upload += ms_since(tp);
     D += kept;
+    if (incr_t) {
+      const uint64_t t_end = D & ~511ull;
+      GPCA_TRY(transpose_rows(t_done, t_end));
+      if (t_end > t_done) t_done = t_end;
+    }
     return GPCA_OK;
   };
 
@@ -633,8 +674,16 @@ static int ingest_core(gpca_ctx* c, const uint8_t* host_payload, int fd, uint64_
       }
       src = c->h_rd[buf];
     }
-    if (e == cudaSuccess)
+    // staging buffer `buf` is free once the repitch of the chunk that used it last has run (compute stream)
+    if (use_copy_stream) {
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(c->copy_stream, stage_free[buf], 0);
+      if (e == cudaSuccess)
+        e = cudaMemcpyAsync(stage[buf].p, src, nr * in_pitch, cudaMemcpyHostToDevice, c->copy_stream);
+      if (e == cudaSuccess) e = cudaEventRecord(h2d_done[buf], c->copy_stream);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(c->stream, h2d_done[buf], 0);
+    } else if (e == cudaSuccess) {
       e = cudaMemcpyAsync(stage[buf].p, src, nr * in_pitch, cudaMemcpyHostToDevice, c->stream);
+    }
     if (e != cudaSuccess) {
       rc = fail(c, GPCA_ERR_CUDA, std::string("ingest H2D: ") + cudaGetErrorString(e));
       break;
@@ -670,21 +719,25 @@ static int ingest_core(gpca_ctx* c, const uint8_t* host_payload, int fd, uint64_
   c->Gs.rows = D;
   c->Gt.rows = N;
   c->Gt.cols = D;
-  c->Gt.pitch = round_up((D + 3) / 4, 128);
-  size_t free_b = 0, total_b = 0;
-  cudaMemGetInfo(&free_b, &total_b);
-  if (c->gt_store.n < c->Gt.pitch * N && free_b < c->Gt.pitch * N + (8ull << 30)) {
-    cudaStreamSynchronize(c->stream);
-    c->raw.release();
-  }
-  cudaError_t ea = c->gt_store.alloc(c->Gt.pitch * N);
-  if (ea != cudaSuccess) {
-    cleanup();
-    return fail(c, GPCA_ERR_OOM, std::string("ingest: ") + cudaGetErrorString(ea));
-  }
-  c->Gt.p = c->gt_store.p;
   const double t_loop = ms_since(t_begin);
-  rc = launch_transpose(c, c->Gs, c->Gt);
+  if (incr_t) {
+    rc = transpose_rows(t_done, D);        // the tail (fewer than 512 rows past the last complete tile)
+  } else {
+    c->Gt.pitch = round_up((D + 3) / 4, 128);
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    if (c->gt_store.n < c->Gt.pitch * N && free_b < c->Gt.pitch * N + (8ull << 30)) {
+      cudaStreamSynchronize(c->stream);
+      c->raw.release();
+    }
+    cudaError_t ea = c->gt_store.alloc(c->Gt.pitch * N);
+    if (ea != cudaSuccess) {
+      cleanup();
+      return fail(c, GPCA_ERR_OOM, std::string("ingest: ") + cudaGetErrorString(ea));
+    }
+    c->Gt.p = c->gt_store.p;
+    rc = launch_transpose(c, c->Gs, c->Gt);
+  }
   cudaStreamSynchronize(c->stream);
   cleanup();
   if (trace)

@@ -101,6 +101,7 @@ struct gpca_ctx {
   int device = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;   // H2D transfers of the streaming ingest (so that they do not queue behind kernels)
   std::string err;
   uint64_t launches = 0;
   int engine = 2;   // 0 SIMT fp32, 1 tcgen05 f16, 2 tcgen05 i8 (default; l > 32 falls back to 1)
