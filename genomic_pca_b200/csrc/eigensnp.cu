@@ -338,13 +338,6 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
   PackedMat Es, Et, Ets, Ess;
   Es.rows = Ds; Es.cols = N; Es.pitch = c->Gs.pitch;
   Et.rows = N; Et.cols = Ds; Et.pitch = round_up((Ds + 3) / 4, 128);
-  GPCA_CUDA_TRY(c, es_store.alloc(Es.pitch * Es.rows));
-  GPCA_CUDA_TRY(c, et_store.alloc(Et.pitch * Et.rows));
-  Es.p = es_store.p;
-  Et.p = et_store.p;
-  stage("  allocations + tables");
-  GPCA_TRY(launch_gather_rows(c, c->Gs, d_slot.p, Es));
-  stage("  gather slots");
   // blocks that are runs of consecutive PcaSnpIds: the sample-major copy is a shifted copy of Gt's rows
   bool runs = !getenv("GPCA_DEBUG_NO_SHIFT_COPY");
   for (uint64_t b = 0; b < n_blocks && runs; ++b)
@@ -353,6 +346,19 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
         runs = false;
         break;
       }
+  // ... and when the blocks also cover every PCA SNP, the refinement passes can run on the resident matrices in
+  // PcaSnpId order (Gs / Gt): the SNP-major slot copy Es is then not needed at all (a 3.6 ms gather and 10.9 GB at
+  // the config-4 shard), unless the subset is the whole sample set (Ess aliases Es)
+  bool all_covered = true;
+  for (uint64_t i = 0; i < D && all_covered; ++i) all_covered = seen[i] != 0;
+  const bool id_order = runs && all_covered && Ns != N && !getenv("GPCA_DEBUG_NO_ID_ORDER");
+  if (!id_order) GPCA_CUDA_TRY(c, es_store.alloc(Es.pitch * Es.rows));
+  GPCA_CUDA_TRY(c, et_store.alloc(Et.pitch * Et.rows));
+  Es.p = id_order ? nullptr : es_store.p;
+  Et.p = et_store.p;
+  stage("  allocations + tables");
+  if (!id_order) GPCA_TRY(launch_gather_rows(c, c->Gs, d_slot.p, Es));
+  stage("  gather slots");
   if (runs) {
     const uint64_t n_chunks = Ds / 64;
     std::vector<int64_t> h_first(n_chunks, -1);
@@ -797,14 +803,26 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
 
   stage("global rSVD");
   // ---- 5. refinement on the full genotype matrix ---------------------------------------------------------------
-  GPCA_CUDA_TRY(c, L.alloc(Ds * k));
+  // rows of the loadings: slots, or -- id_order -- the PCA SNPs themselves (resident Gs / Gt and their 1/sd, mean/sd)
+  const uint64_t Dl = id_order ? D : Ds;
+  const float* l_inv = id_order ? c->d_inv_sd.p : d_inv.p;
+  const float* l_mu = id_order ? c->d_mu_inv_sd.p : d_mu.p;
+  GPCA_CUDA_TRY(c, L.alloc(Dl * k));
   GPCA_CUDA_TRY(c, Sc.alloc(N * k));
-  SketchProblem f1;   // L = S V   (rows = slots, K = all samples)
-  f1.G = Es; f1.G.avail = Es.pitch;
-  f1.l = k; f1.ld = k; f1.f = nullptr; f1.e = nullptr; f1.a = d_inv.p; f1.b = d_mu.p; f1.ldo = k;
-  SketchProblem f2;   // Sc = S^T L (rows = samples, K = slots)
-  f2.G = Et; f2.G.avail = Et.pitch;
-  f2.l = k; f2.ld = k; f2.f = d_inv.p; f2.e = d_mu.p; f2.a = nullptr; f2.b = nullptr; f2.ldo = k;
+  SketchProblem f1;   // L = S V   (rows = slots / SNPs, K = all samples)
+  if (id_order) {
+    f1.G = c->Gs; f1.G.avail = c->Gs.pitch;
+  } else {
+    f1.G = Es; f1.G.avail = Es.pitch;
+  }
+  f1.l = k; f1.ld = k; f1.f = nullptr; f1.e = nullptr; f1.a = l_inv; f1.b = l_mu; f1.ldo = k;
+  SketchProblem f2;   // Sc = S^T L (rows = samples, K = slots / SNPs)
+  if (id_order) {
+    f2.G = c->Gt; f2.G.avail = c->Gt.pitch;
+  } else {
+    f2.G = Et; f2.G.avail = Et.pitch;
+  }
+  f2.l = k; f2.ld = k; f2.f = l_inv; f2.e = l_mu; f2.a = nullptr; f2.b = nullptr; f2.ldo = k;
   PoolBuf<double> d_lam(&c->es_pool);
   GPCA_CUDA_TRY(c, d_lam.alloc(64));
   const uint32_t passes = cfg->refine_pass_count;
@@ -813,11 +831,11 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
     GPCA_TRY(timed_sketch(c, f1));
     if (passes == 0) {
       // no refinement requested: loadings = normalised S V0, singular values = column norms
-      GPCA_TRY(launch_gram(c, L.p, Ds, k, k, s.G));
+      GPCA_TRY(launch_gram(c, L.p, Dl, k, k, s.G));
       GPCA_TRY(driver_allreduce(c, s.G, (uint64_t)k * k, 1));
       break;
     }
-    GPCA_TRY(orthonormalize(c, L.p, Ds, k, k, true, s));
+    GPCA_TRY(orthonormalize(c, L.p, Dl, k, k, true, s));
     f2.Bin = L.p; f2.out = Sc.p;
     GPCA_TRY(timed_sketch(c, f2));
     GPCA_TRY(driver_allreduce(c, Sc.p, N * (uint64_t)k, 0));
@@ -827,7 +845,7 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
     GPCA_TRY(launch_rotation_transform(c, s.evals, s.evecs, k, k, s.T, true));
     GPCA_TRY(launch_apply_right(c, Sc.p, N, k, k, s.T, k, V.p, k));          // V = Sc W / sigma (orthonormal)
     GPCA_TRY(launch_rotation_transform(c, s.evals, s.evecs, k, k, s.T, false));
-    GPCA_TRY(launch_apply_right(c, L.p, Ds, k, k, s.T, k, L.p, k));          // loadings = L W
+    GPCA_TRY(launch_apply_right(c, L.p, Dl, k, k, s.T, k, L.p, k));          // loadings = L W
   }
   stage("refinement");
   std::vector<double> h_lam(k, 0.0);
@@ -841,7 +859,7 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
       t[(size_t)j * k + j] = h_lam[j] > 0 ? 1.0 / std::sqrt(h_lam[j]) : 0.0;
     }
     GPCA_CUDA_TRY(c, cudaMemcpyAsync(s.T, t.data(), (size_t)k * k * 8, cudaMemcpyHostToDevice, c->stream));
-    GPCA_TRY(launch_apply_right(c, L.p, Ds, k, k, s.T, k, L.p, k));
+    GPCA_TRY(launch_apply_right(c, L.p, Dl, k, k, s.T, k, L.p, k));
     GPCA_CUDA_TRY(c, cudaMemcpyAsync(d_lam.p, h_lam.data(), k * 8, cudaMemcpyHostToDevice, c->stream));
   } else {
     GPCA_CUDA_TRY(c, cudaMemcpyAsync(h_lam.data(), d_lam.p, k * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -863,7 +881,10 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
     GPCA_TRY(download_results(c, V.p, N * k, scores, nullptr));
   }
   PoolBuf<float> Lout(&c->es_pool);
-  if (loadings) {
+  if (loadings && id_order) {      // already in PcaSnpId order: only the sign flips are left
+    GPCA_TRY(launch_apply_flags(c, L.p, D, k, k, d_flags.p, L.p, nullptr));
+    GPCA_TRY(download_results(c, L.p, D * k, loadings, nullptr));
+  } else if (loadings) {
     GPCA_CUDA_TRY(c, Lout.alloc(D * k));
     GPCA_CUDA_TRY(c, cudaMemsetAsync(Lout.p, 0, D * k * sizeof(float), c->stream));
     const uint64_t tot = Ds * (uint64_t)k;

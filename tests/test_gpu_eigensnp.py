@@ -194,16 +194,23 @@ def test_eigensnp_shifted_copy_and_block_groups(gpu_ctx, monkeypatch):
                             refine_pass_count=1)
     gpu_ctx.set_sketch_engine(2)
     gpu_ctx.set_batch_blocks(True)
-    for v in ("GPCA_DEBUG_NO_SHIFT_COPY", "GPCA_DEBUG_NO_GROUPS"):
+    for v in ("GPCA_DEBUG_NO_SHIFT_COPY", "GPCA_DEBUG_NO_GROUPS", "GPCA_DEBUG_NO_ID_ORDER"):
         monkeypatch.delenv(v, raising=False)
     sc, ev, load = gpu_ctx.eigensnp(blocks, cfg)
     # run to run: bit for bit (this configuration caught a wide row store of the sketch epilogue spilling zeros into the
     # neighbouring blocks' columns of the condensed matrix -- a race between work items)
     sc_r, ev_r, load_r = gpu_ctx.eigensnp(blocks, cfg)
     assert np.array_equal(sc, sc_r) and np.array_equal(ev, ev_r) and np.array_equal(load, load_r)
+    # refinement on the slot-ordered copies instead of the resident matrices in PcaSnpId order: same arithmetic in a
+    # different row order (only the f64 Gram partial sums are grouped differently)
+    monkeypatch.setenv("GPCA_DEBUG_NO_ID_ORDER", "1")
+    sc_s, ev_s, load_s = gpu_ctx.eigensnp(blocks, cfg)
+    assert np.abs(ev / ev_s - 1).max() < 1e-6
+    assert pca.subspace_angle(sc, sc_s) < 1e-5 and pca.subspace_angle(load, load_s) < 1e-5
+    # the shifted copy must reproduce the gather + transpose layout exactly
     monkeypatch.setenv("GPCA_DEBUG_NO_SHIFT_COPY", "1")
     sc_t, ev_t, load_t = gpu_ctx.eigensnp(blocks, cfg)
-    assert np.array_equal(sc, sc_t) and np.array_equal(ev, ev_t) and np.array_equal(load, load_t)
+    assert np.array_equal(sc_s, sc_t) and np.array_equal(ev_s, ev_t) and np.array_equal(load_s, load_t)
     monkeypatch.setenv("GPCA_DEBUG_NO_GROUPS", "1")
     sc_g, ev_g, load_g = gpu_ctx.eigensnp(blocks, cfg)
     assert np.abs(ev / ev_g - 1).max() < 1e-5
