@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(256) gaussian_stats_kernel(float* __restrict__
                                                              unsigned int* __restrict__ amax_bits) {
   const uint32_t groups = (ld + 3) / 4;
   const uint64_t total = rows * groups;
+  const bool vec4 = (ld & 3u) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
   float mx = 0.0f;
   for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < total;
        t += (uint64_t)gridDim.x * blockDim.x) {
@@ -79,12 +80,19 @@ __global__ void __launch_bounds__(256) gaussian_stats_kernel(float* __restrict__
     float z[4];
     philox_normal4(seed, stream, row0 + r, cg, z);
     const float fr = f ? f[r] : 1.0f;
+    float v[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const uint32_t cidx = cg * 4 + j;
-      const float v = (cidx < cols) ? z[j] : 0.0f;
-      if (cidx < ld) out[r * ld + cidx] = v;
-      mx = fmaxf(mx, fabsf(v * fr));
+      v[j] = (cidx < cols) ? z[j] : 0.0f;
+      mx = fmaxf(mx, fabsf(v[j] * fr));
+    }
+    if (vec4) {      // rows padded to a multiple of 4 floats: one 16-byte store per thread
+      *reinterpret_cast<float4*>(out + r * ld + cg * 4) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (cg * 4 + j < ld) out[r * ld + cg * 4 + j] = v[j];
     }
   }
 #pragma unroll
