@@ -79,3 +79,21 @@ def test_results_download_in_chunks(gpu_ctx, monkeypatch):
     assert np.array_equal(sc1, sc2) and np.array_equal(ld1, ld2) and np.array_equal(ev1, ev2)
     # the f64 scores are exactly the widened fp32 values
     assert np.array_equal(sc1, sc1.astype(np.float32).astype(np.float64))
+
+
+@pytest.mark.parametrize("k,oversample", [(24, 16), (40, 10), (12, 22)])
+def test_rfit_wide_sketch_matches_oracle(gpu_ctx, k, oversample):
+    """l = k + oversample in (32, 64]: the shape of BASELINE config 5 (k = 40, l = 50).  The default engine hands these
+    to the fp16 tensor engine (64 columns), and the N-side helpers run their 64-column variants (Gram tiles split over
+    3 to 8 warps per row group, Y.T with 12 / 16 owned columns)."""
+    S = _prep(gpu_ctx, 1500, 5000, k + 2, seed=100 + k, vcf=True)
+    gpu_ctx.set_sketch_engine(2)
+    sc, ev, ld = gpu_ctx.rfit(k, oversample, power_iters=2, seed=5)
+    sc_o, ev_o, ld_o = pca.rfit(S, k, oversample, seed=5, power_iters=2)
+    assert sc.shape == (1500, k) and ld.shape == (S.shape[0], k)
+    assert np.abs(ev / ev_o - 1).max() < EV_RTOL
+    assert pca.subspace_angle(sc, sc_o) < ANGLE_TOL
+    assert pca.subspace_angle(ld, ld_o) < ANGLE_TOL
+    # run to run
+    sc2, ev2, ld2 = gpu_ctx.rfit(k, oversample, power_iters=2, seed=5)
+    assert np.array_equal(ev, ev2) and np.array_equal(sc, sc2) and np.array_equal(ld, ld2)
