@@ -299,8 +299,10 @@ static int build_pca_set(gpca_ctx* c, uint64_t D) {
   const uint32_t* hc = c->h_counts.data();
   const uint64_t N = c->N;
   std::atomic<uint64_t> nmiss_total{0};
+  std::atomic<uint32_t> inv_max_bits{0};     // (bit patterns of non-negative floats order like the floats)
   parallel_for(D, [&, idx, mean, sd, inv, muinv, hc, N](uint64_t lo, uint64_t hi) {
     uint64_t nm = 0;
+    float imax = 0.f;
     for (uint64_t i = lo; i < hi; ++i) {
       // same f32 expressions as prepare.rs:1948-1949 (recip, mean*recip); sd < 1e-9 -> the row standardises to 0
       if (std::fabs(sd[i]) < 1e-9f) {
@@ -312,9 +314,18 @@ static int build_pca_set(gpca_ctx* c, uint64_t D) {
         muinv[i] = mean[i] * r;
       }
       nm += N - hc[4 * idx[i]];
+      imax = std::max(imax, std::fabs(inv[i]));
     }
     nmiss_total.fetch_add(nm);
+    uint32_t bits, cur = inv_max_bits.load();
+    std::memcpy(&bits, &imax, 4);
+    while (bits > cur && !inv_max_bits.compare_exchange_weak(cur, bits)) {
+    }
   });
+  {
+    const uint32_t bits = inv_max_bits.load();
+    std::memcpy(&c->inv_sd_max, &bits, 4);
+  }
   c->any_missing = nmiss_total.load() > 0;
   c->D = D;
   GPCA_CUDA_TRY(c, c->d_mean.alloc(D));
@@ -566,6 +577,7 @@ static int ingest_core(gpca_ctx* c, const uint8_t* host_payload, int fd, uint64_
   const uint32_t pad = (uint32_t)(c->raw_pitch * 4 - N);
   const uint32_t n32 = (uint32_t)N;
   uint64_t D = 0, nmiss_total = 0;
+  float inv_max = 0.f;
   int rc = GPCA_OK;
 
   const bool trace = getenv("GPCA_TRACE") != nullptr;
@@ -623,6 +635,7 @@ static int ingest_core(gpca_ctx* c, const uint8_t* host_payload, int fd, uint64_
       u_idx[kept] = j; u_mean[kept] = m; u_sd[kept] = sdv; u_inv[kept] = inv; u_mu[kept] = mu;
       c->pca_idx[D + kept] = j; c->h_mean[D + kept] = m; c->h_sd[D + kept] = sdv;
       c->h_inv[D + kept] = inv; c->h_muinv[D + kept] = mu;
+      inv_max = std::max(inv_max, std::fabs(inv));
       nmiss_total += N - hc[4 * j];
       ++kept;
     }
@@ -715,6 +728,7 @@ static int ingest_core(gpca_ctx* c, const uint8_t* host_payload, int fd, uint64_
   }
   // (the host vectors stay at their capacity; only the first D entries are meaningful)
   c->any_missing = nmiss_total > 0;
+  c->inv_sd_max = inv_max;
   c->D = D;
   c->Gs.rows = D;
   c->Gt.rows = N;
@@ -888,6 +902,33 @@ int sketch_sample_side(gpca_ctx* c, const float* dev_in, float* dev_out, uint32_
   p.b = nullptr;
   p.out = dev_out;
   p.ldo = ld_out;
+  GPCA_TRY(timed_sketch(c, p));
+  if (c->allreduce) {
+    if (ld_out != l) return fail(c, GPCA_ERR_INVALID, "sharded sample-side sketch needs ld == l");
+    if (c->allreduce(dev_out, c->N * (uint64_t)l, 0, (void*)c->stream, c->allreduce_user) != 0)
+      return fail(c, GPCA_ERR_CUDA, "allreduce hook failed");
+  }
+  return GPCA_OK;
+}
+
+int sketch_sample_side_gaussian(gpca_ctx* c, float* dev_scratch, float* dev_out, uint32_t l, uint32_t ld_in,
+                                uint32_t ld_out, uint64_t seed, uint32_t stream_id) {
+  SketchProblem p;
+  p.G = c->Gt;
+  p.Bin = dev_scratch;
+  p.l = l;
+  p.ld = ld_in;
+  p.f = c->d_inv_sd.p;
+  p.e = c->d_mu_inv_sd.p;
+  p.a = nullptr;
+  p.b = nullptr;
+  p.out = dev_out;
+  p.ldo = ld_out;
+  p.gen = true;
+  p.gen_seed = seed;
+  p.gen_stream = stream_id;
+  p.gen_row0 = c->shard_offset;
+  p.gen_amax = GPCA_NORMAL_ABS_MAX * c->inv_sd_max;
   GPCA_TRY(timed_sketch(c, p));
   if (c->allreduce) {
     if (ld_out != l) return fail(c, GPCA_ERR_INVALID, "sharded sample-side sketch needs ld == l");

@@ -124,6 +124,7 @@ struct gpca_ctx {
   uint64_t D = 0;
   std::vector<uint64_t> pca_idx;
   std::vector<float> h_mean, h_sd, h_inv, h_muinv;
+  float inv_sd_max = 0.f;      // max 1/sd over the PCA SNPs (bounds |f o Omega| for the generated test matrix)
   DevBuf<uint64_t> d_idx;
   DevBuf<uint4> d_cnt;
   uint4* h_cnt = nullptr;      // pinned landing buffer for the count records

@@ -38,6 +38,10 @@ int sketch_snp_side(gpca_ctx* c, const float* dev_in, float* dev_out, uint32_t l
                     bool emit_stats = false, bool out_pad = false);
 int sketch_sample_side(gpca_ctx* c, const float* dev_in, float* dev_out, uint32_t l, uint32_t ld_in, uint32_t ld_out,
                        bool use_stats = false);
+// Y = S^T Omega with Omega = the D x l Gaussian test matrix of (seed, stream): generated inside the operand preparation
+// when the integer engine runs (dev_scratch [D x ld_in] is only written by the other paths)
+int sketch_sample_side_gaussian(gpca_ctx* c, float* dev_scratch, float* dev_out, uint32_t l, uint32_t ld_in,
+                                uint32_t ld_out, uint64_t seed, uint32_t stream_id);
 // generic timed sketch on an arbitrary view (used by the EigenSNP driver)
 int timed_sketch(gpca_ctx* c, const SketchProblem& p);
 // one launch for all LD blocks (integer engine, item mode)

@@ -152,9 +152,9 @@ extern "C" int gpca_rfit(gpca_ctx* c, uint32_t k, uint32_t oversample, uint32_t 
   // Y = S^T Omega
   // (every D x l operand of a sample-side pass arrives with its column statistics: from the generator here, from the
   //  epilogue of the snp-side pass below -- one sweep over a D x l matrix saved per pass)
-  GPCA_TRY(launch_gaussian_with_stats(c, Z.p, D, l, ldz, seed, STREAM_RFIT_OMEGA, c->shard_offset, c->d_inv_sd.p,
-                                      c->d_mu_inv_sd.p));
-  GPCA_TRY(sketch_sample_side(c, Z.p, Y.p, l, ldz, l, true));
+  // (Omega is quantised straight from the generator when the integer engine runs: the D x l fp32 matrix is neither
+  //  written nor read back -- a 1.3 GB write and read at config 3)
+  GPCA_TRY(sketch_sample_side_gaussian(c, Z.p, Y.p, l, ldz, l, seed, STREAM_RFIT_OMEGA));
   for (uint32_t it = 0; it < power_iters; ++it) {
     GPCA_TRY(orthonormalize(c, Y.p, N, l, l, false, s));
     GPCA_TRY(sketch_snp_side(c, Y.p, Z.p, l, l, ldz, true, true));   // Z = S Q

@@ -96,6 +96,9 @@ int orthonormalize_batch(gpca_ctx* c, float* d_base, uint32_t ld, const DensePro
 int launch_scale_cols_to_f64(gpca_ctx* c, const float* in, uint64_t n, uint32_t k, uint32_t ld, double* out);
 
 // ---- sketch (kernels_sketch.cu) -----------------------------------------------------------
+// bound on |z| of the normals of philox_normal4 (philox.cuh): u1 >= 2^-25 -> radius <= sqrt(50 ln 2) = 5.887
+#define GPCA_NORMAL_ABS_MAX 5.9f
+
 struct SketchProblem {
   PackedMat G;            // [rows x K]
   const float* Bin;       // [K x ld] dense operand
@@ -110,6 +113,14 @@ struct SketchProblem {
   // Operand statistics as by-products (integer engine; ignored elsewhere).  A sample-side pass needs, for its operand
   // W, the column sums e^T W and max |f o W|; when W was just produced by a snp-side pass (f = that pass's a, e = its
   // b) or by the Gaussian generator, the producer computes them on the way out and one sweep over W is saved.
+  // Generated operand: Bin[k, n] = the standard normal that philox_normal4(gen_seed, gen_stream, gen_row0 + k, n/4)
+  // gives for column n (the test matrix Omega).  The integer engine quantises it straight from the generator -- the
+  // K x ld fp32 matrix is never written or read -- with the a-priori scale gen_amax >= max |f o Bin|; every other
+  // path fills `Bin` (which then must be writable scratch of K x ld floats) first.
+  bool gen = false;
+  uint64_t gen_seed = 0, gen_row0 = 0;
+  uint32_t gen_stream = 0;
+  float gen_amax = 0.f;
   bool emit_stats = false;   // also leave the statistics of `out` (weights a, b) in the context
   bool use_stats = false;    // Bin's statistics are in the context already
 };

@@ -268,6 +268,19 @@ int launch_sketch(gpca_ctx* c, const SketchProblem& p) {
     return GPCA_ERR_INVALID;
   }
   if (p.G.rows == 0 || p.G.cols == 0) return GPCA_OK;
+  if (p.gen) {
+    // generated operand: only the integer engine quantises it on the fly (and only without missing calls: the
+    // correction kernel reads Bin); everything else gets the matrix written into the caller's scratch first
+    const bool fused = c->engine == 2 && sketch_i8_supported(c, p) && !c->any_missing && p.gen_amax > 0.0f &&
+                       !getenv("GPCA_DEBUG_NO_GEN_FUSE");
+    if (!fused) {
+      GPCA_TRY(launch_gaussian(c, const_cast<float*>(p.Bin), p.G.cols, p.l, p.ld, p.gen_seed, p.gen_stream, p.gen_row0));
+      SketchProblem q = p;
+      q.gen = false;
+      q.use_stats = false;
+      return launch_sketch(c, q);
+    }
+  }
   int rc = GPCA_ERR_INVALID;
   bool done = false;
   if (c->engine == 2 && sketch_i8_supported(c, p)) {

@@ -30,6 +30,8 @@ __host__ __device__ inline Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint3
   return Philox4{c0, c1, c2, c3};
 }
 
+// (|z| of any generated normal is below GPCA_NORMAL_ABS_MAX, kernels.cuh: u1 >= 2^-25, so the Box-Muller radius is at
+//  most sqrt(50 ln 2) = 5.887)
 // Four standard normals for columns 4*cg .. 4*cg+3 of row `row` (one Philox call, two Box-Muller pairs):
 //   (x, y) -> sqrt(-2 ln u1) * {cos, sin}(2 pi u2),   (z, w) -> the same for the second pair.
 __device__ inline void philox_normal4(uint64_t seed, uint32_t stream, uint64_t row, uint32_t cg, float out[4]) {

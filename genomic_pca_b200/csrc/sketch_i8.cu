@@ -17,6 +17,7 @@
 
 #include "sketch_tc.cuh"
 #include "tc_ptx.cuh"
+#include "philox.cuh"
 
 namespace {
 using namespace tcptx;
@@ -653,6 +654,81 @@ __global__ void __launch_bounds__(256) prep_b_i8_kernel(const float* __restrict_
   }
 }
 
+// The same image straight from the generator (SketchProblem::gen): a warp owns a 16-row K chunk; lane L draws the four
+// Philox calls of row L/2, column groups 4(L%2) .. 4(L%2)+3 (every normal is generated exactly once), the 16 x 32
+// values cross the warp through shared memory, and lane n then quantises column n of the 16 rows as above.
+__global__ void __launch_bounds__(256) prep_b_i8_gauss_kernel(uint64_t seed, uint32_t stream, uint64_t row0, uint64_t K,
+                                                              uint64_t Kpad, uint32_t l, const float* __restrict__ f,
+                                                              const float* __restrict__ e,
+                                                              const float* __restrict__ scales,
+                                                              int8_t* __restrict__ img, double* __restrict__ cpart) {
+  __shared__ double sred[8][NL];
+  __shared__ float xch[8][16][33];
+  const uint64_t n_chunks = Kpad / 16;
+  const float qs = scales[0];
+  const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+  const uint32_t n = lane;
+  const bool col_live = n < l;
+  double csum = 0.0;
+  const uint64_t warp0 = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t kc = warp0; kc < n_chunks; kc += nwarps) {
+    const uint64_t kb = kc * 16;
+    uint32_t whi[4] = {0, 0, 0, 0}, wlo[4] = {0, 0, 0, 0};
+    if (kb < K) {      // warp-uniform
+      const uint32_t gr = lane >> 1;                      // row of the chunk this lane generates
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t cg = (lane & 1u) * 4 + i;
+        float z[4];
+        philox_normal4(seed, stream, row0 + kb + gr, cg, z);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) xch[wib][gr][cg * 4 + j] = z[j];
+      }
+      __syncwarp();
+      if (col_live) {
+        float part = 0.0f;
+#pragma unroll
+        for (int ss = 0; ss < 16; ++ss) {
+          const int kl = (ss >> 2) + 4 * (ss & 3);        // K-slot order of the expansion (see prep_b_i8_kernel)
+          const bool live = kb + kl < K;
+          const float v = live ? xch[wib][kl][n] : 0.0f;
+          const float fk = live ? (f ? __ldg(f + kb + kl) : 1.0f) : 0.0f;
+          const float ek = live ? (e ? __ldg(e + kb + kl) : 1.0f) : 0.0f;
+          part = fmaf(v, ek, part);
+          int q = __float2int_rn(v * (fk * qs));
+          q = max(-32512, min(32512, q));
+          const int h = (q + 128) >> 8;
+          const int lo = q - 256 * h;
+          whi[ss >> 2] |= (uint32_t)(h & 0xff) << (8 * (ss & 3));
+          wlo[ss >> 2] |= (uint32_t)(lo & 0xff) << (8 * (ss & 3));
+        }
+        csum += (double)part;
+      }
+    }
+    const uint64_t g = kc >> 1;
+    const uint32_t half_idx = (uint32_t)(kc & 1);
+    const uint64_t base = g * 32 * NM + (uint64_t)half_idx * (NM * 16);
+    *reinterpret_cast<uint4*>(img + base + (n >> 3) * 128 + (n & 7) * 16) = make_uint4(whi[0], whi[1], whi[2], whi[3]);
+    *reinterpret_cast<uint4*>(img + base + ((n + 32) >> 3) * 128 + (n & 7) * 16) = make_uint4(wlo[0], wlo[1], wlo[2], wlo[3]);
+  }
+  sred[threadIdx.x >> 5][threadIdx.x & 31] = csum;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sred[w][threadIdx.x];
+    cpart[(uint64_t)blockIdx.x * NL + threadIdx.x] = t;
+  }
+}
+
+// a-priori quantisation scale of a generated operand (amax >= max |f o Bin| by construction)
+__global__ void i8_set_scale_kernel(float amax, float* __restrict__ scales) {
+  scales[0] = (amax > 0.0f) ? 32512.0f / amax : 0.0f;
+  scales[1] = (amax > 0.0f) ? amax / 32512.0f : 0.0f;
+}
+
 __global__ void __launch_bounds__(256) sketch_reduce_i8_kernel(const float* __restrict__ partial, int nsplit,
                                                                uint64_t rows, const float* __restrict__ a,
                                                                const float* __restrict__ b,
@@ -854,7 +930,9 @@ int launch_sketch_i8(gpca_ctx* c, const SketchProblem& p) {
   GPCA_TRY(stats_buffer(c, &st_cpart, &st_amax));
   bool have_stats = p.use_stats && c->stats_for == p.Bin && c->stats_l == p.l;
   if (getenv("GPCA_DEBUG_NO_USE_STATS")) have_stats = false;
-  if (have_stats) {
+  if (p.gen) {
+    i8_set_scale_kernel<<<1, 1, 0, c->stream>>>(p.gen_amax, scales);
+  } else if (have_stats) {
     // the producer of Bin left max |f o Bin| behind (SketchProblem::emit_stats): one sweep over the operand saved
     i8_scale_kernel<<<1, 1, 0, c->stream>>>(st_amax, scales);
     c->stats_pending = false;    // (the scale kernel resets the max-abs word)
@@ -872,7 +950,11 @@ int launch_sketch_i8(gpca_ctx* c, const SketchProblem& p) {
     const uint64_t blocks = (total + 255) / 256;
     const int grid = (int)(blocks < (uint64_t)c->sm_count * 8 ? blocks : (uint64_t)c->sm_count * 8);
     GPCA_CUDA_TRY(c, c->ws_cpart.alloc((size_t)grid * 64));
-    prep_b_i8_kernel<<<grid, 256, 0, c->stream>>>(p.Bin, K, Kpad, p.l, p.ld, p.f, p.e, scales, img, c->ws_cpart.p);
+    if (p.gen)
+      prep_b_i8_gauss_kernel<<<grid, 256, 0, c->stream>>>(p.gen_seed, p.gen_stream, p.gen_row0, K, Kpad, p.l, p.f, p.e,
+                                                          scales, img, c->ws_cpart.p);
+    else
+      prep_b_i8_kernel<<<grid, 256, 0, c->stream>>>(p.Bin, K, Kpad, p.l, p.ld, p.f, p.e, scales, img, c->ws_cpart.p);
     c->launches++;
     GPCA_CUDA_TRY(c, cudaGetLastError());
     i8_cvec_kernel<<<1, 256, 0, c->stream>>>(c->ws_cpart.p, grid, cvec);

@@ -97,3 +97,27 @@ def test_rfit_wide_sketch_matches_oracle(gpu_ctx, k, oversample):
     # run to run
     sc2, ev2, ld2 = gpu_ctx.rfit(k, oversample, power_iters=2, seed=5)
     assert np.array_equal(ev, ev2) and np.array_equal(sc, sc2) and np.array_equal(ld, ld2)
+
+
+def test_rfit_generated_test_matrix_matches_materialised(gpu_ctx, monkeypatch):
+    """The first pass quantises the Gaussian test matrix straight from the Philox generator (a-priori scale from the
+    generator's |z| bound and max 1/sd) instead of writing it to memory, measuring its max and reading it back.  Same
+    normals, slightly coarser quantisation step: the two paths agree far inside the parity tolerances."""
+    S = _prep(gpu_ctx, 1300, 9000, 6, seed=77, vcf=True)
+    gpu_ctx.set_sketch_engine(2)
+    monkeypatch.delenv("GPCA_DEBUG_NO_GEN_FUSE", raising=False)
+    sc, ev, ld = gpu_ctx.rfit(5, 10, power_iters=2, seed=9)
+    monkeypatch.setenv("GPCA_DEBUG_NO_GEN_FUSE", "1")
+    sc_m, ev_m, ld_m = gpu_ctx.rfit(5, 10, power_iters=2, seed=9)
+    assert np.abs(ev / ev_m - 1).max() < 2e-5      # (the north-star tolerance is 1e-4)
+    assert pca.subspace_angle(sc, sc_m) < 2e-4 and pca.subspace_angle(ld, ld_m) < 2e-4
+    # with no power iteration the estimate depends on every rounding of the test matrix (a q = 0 randomized SVD is only
+    # accurate to ~1e-3 on the trailing components here): the two quantisations stay inside that
+    monkeypatch.delenv("GPCA_DEBUG_NO_GEN_FUSE", raising=False)
+    sc0, ev0, _ = gpu_ctx.rfit(5, 10, power_iters=0, seed=9)
+    monkeypatch.setenv("GPCA_DEBUG_NO_GEN_FUSE", "1")
+    sc0_m, ev0_m, _ = gpu_ctx.rfit(5, 10, power_iters=0, seed=9)
+    assert np.abs(ev0 / ev0_m - 1).max() < 2e-3
+    assert pca.subspace_angle(sc0[:, :3], sc0_m[:, :3]) < 5e-3
+    sc_o, ev_o, _ = pca.rfit(S, 5, 10, seed=9, power_iters=0)
+    assert np.abs(ev0 / ev_o - 1).max() < 2e-3 and np.abs(ev0_m / ev_o - 1).max() < 2e-3
