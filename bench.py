@@ -112,16 +112,24 @@ class ClockSampler:
             self.proc = None
 
     def _poll(self):
+        # (an NVML query takes milliseconds while the GPU is busy: two queries per sample, the power every fourth one,
+        #  the maximum clock once)
         nv = self.nvml
+        try:
+            mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+        except Exception:
+            mx = None
+        it, pw = 0, None
         while not self.stop_flag:
             try:
-                self.rows.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM),
-                                  nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM),
-                                  nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h),
-                                  nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0))
+                if it % 4 == 0:
+                    pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                self.rows.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM), mx,
+                                  nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h), pw))
             except Exception:
                 pass
-            time.sleep(0.005)
+            it += 1
+            time.sleep(0.002)
 
     def _read(self):
         for line in self.proc.stdout:
@@ -138,10 +146,11 @@ class ClockSampler:
                     "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
             reasons = sorted(nm for nm, bit in bits.items() if any(r[2] & bit for r in self.rows))
             sm = [r[0] for r in self.rows]
-            pw = [r[3] for r in self.rows]
+            pw = [r[3] for r in self.rows if r[3] is not None]
             return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_min_mhz": float(min(sm)) if sm else None,
-                    "sm_max_mhz": float(max(r[1] for r in self.rows)) if self.rows else None, "reasons": reasons,
-                    "power_w": float(np.median(pw)) if pw else None, "samples": len(sm), "source": "nvml, 5 ms"}
+                    "sm_max_mhz": float(max(r[1] for r in self.rows if r[1] is not None)) if any(
+                        r[1] is not None for r in self.rows) else None, "reasons": reasons,
+                    "power_w": float(np.median(pw)) if pw else None, "samples": len(sm), "source": "nvml, 2 ms"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
