@@ -405,6 +405,7 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
   stage("slot/subset copies");
 
   // ---- 2. local bases -------------------------------------------------------------------------------------
+  const bool orth_both = getenv("GPCA_DEBUG_LOCAL_ORTH_BOTH") != nullptr;   // (A/B: re-orthonormalise both sides)
   std::vector<uint32_t> cp(n_blocks);
   std::vector<uint64_t> roff(n_blocks + 1, 0);
   uint64_t max_m = 0;
@@ -554,8 +555,11 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
     for (uint32_t it = 0; it < cfg->local_power_iters; ++it) {
       GPCA_TRY(orthonormalize_batch(c, Yall.p, LD, d_yprob.p, nb, max_m, lp_max, ws));
       GPCA_TRY(timed_sketch_batch(c, p2));                                             // Z = X^T Q
-      GPCA_TRY(orthonormalize_batch(c, Zall.p, LD, d_zprob.p, nb, Ns, lp_max, ws));
-      GPCA_TRY(timed_sketch_batch(c, p1));                                             // Y = X Qz
+      // (range(X Z) does not depend on a column transform of Z: as in gpca_rfit only one side -- the small one, the
+      //  block's SNPs -- is re-orthonormalised per iteration; CholeskyQR2 on the N_s-row iterates of all blocks was
+      //  four Gram and four Y.T launches over 8 M rows, half of this stage)
+      if (orth_both) GPCA_TRY(orthonormalize_batch(c, Zall.p, LD, d_zprob.p, nb, Ns, lp_max, ws));
+      GPCA_TRY(timed_sketch_batch(c, p1));                                             // Y = X Z
     }
     GPCA_TRY(orthonormalize_batch(c, Yall.p, LD, d_yprob.p, nb, max_m, lp_max, ws));
     GPCA_TRY(timed_sketch_batch(c, p2));                                               // B^T = X^T Q   [Ns x lp]
@@ -588,8 +592,8 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
       GPCA_TRY(orthonormalize(c, Yb.p, m, lp, lp, false, s));
       p2.Bin = Yb.p; p2.out = Zb.p;
       GPCA_TRY(timed_sketch(c, p2));                             // Z = X^T Q
-      GPCA_TRY(orthonormalize(c, Zb.p, Ns, lp, lp, false, s));
-      GPCA_TRY(timed_sketch(c, p1));                             // Y = X Qz
+      if (orth_both) GPCA_TRY(orthonormalize(c, Zb.p, Ns, lp, lp, false, s));
+      GPCA_TRY(timed_sketch(c, p1));                             // Y = X Z
     }
     GPCA_TRY(orthonormalize(c, Yb.p, m, lp, lp, false, s));
     p2.Bin = Yb.p; p2.out = Zb.p;
