@@ -788,7 +788,9 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
   GPCA_TRY(driver_allreduce(c, Yg.p, N * lg, 0));
   stage("  first gemm");
   for (uint32_t it = 0; it < cfg->global_power_iters; ++it) {
-    GPCA_TRY(orthonormalize(c, Yg.p, N, lg, lg, false, s));
+    // (only the small side -- the R condensed rows -- is re-orthonormalised inside the iteration; the N-row iterate is
+    //  orthonormalised once, in front of the projection)
+    if (orth_both) GPCA_TRY(orthonormalize(c, Yg.p, N, lg, lg, false, s));
     // Zg[R x lg] = Cn^T * Yg
     GPCA_TRY(sgemm_rm(c, cb.h, true, (int)R, (int)lg, (int)N, Cn.p, (int)R, Yg.p, (int)lg, Zg.p, (int)lg));
     GPCA_TRY(orthonormalize(c, Zg.p, R, lg, lg, true, s));
