@@ -36,8 +36,8 @@ N_POPS = K_COMPONENTS + 2
 def parse_args():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=5)
-    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--steps", type=int, default=None, help="timed steps (default 20; 3 for --impl reference)")
+    p.add_argument("--warmup", type=int, default=None, help="untimed steps (default 5; 1 for --impl reference)")
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--samples", type=int, default=2504)
     p.add_argument("--snps", type=int, default=10_000_000, help="SNPs per GPU (weak scaling)")
@@ -49,6 +49,12 @@ def parse_args():
     p.add_argument("--no-cpu", action="store_true")
     p.add_argument("--no-ukb", action="store_true", help="skip the supplementary 500k x 87.5k shard measurement")
     a = p.parse_args()
+    # defaults: a timed region long enough (~0.3 s) for the clock sampler to see the run under load; the CPU arm's steps
+    # are seconds each
+    if a.steps is None:
+        a.steps = 3 if a.impl == "reference" else 20
+    if a.warmup is None:
+        a.warmup = 1 if a.impl == "reference" else 5
     global K_COMPONENTS, POWER_ITERS
     if a.components is not None:
         K_COMPONENTS = a.components
