@@ -155,12 +155,22 @@ extern "C" int gpca_rfit(gpca_ctx* c, uint32_t k, uint32_t oversample, uint32_t 
   // (Omega is quantised straight from the generator when the integer engine runs: the D x l fp32 matrix is neither
   //  written nor read back -- a 1.3 GB write and read at config 3)
   GPCA_TRY(sketch_sample_side_gaussian(c, Z.p, Y.p, l, ldz, l, seed, STREAM_RFIT_OMEGA));
+  // One side is re-orthonormalised per iteration, the other is left as it comes (range(S^T Z) does not depend on a
+  // column transform of Z, nor range(S Y) on one of Y): the side with fewer rows on this device -- the samples at the
+  // 1000G shape, the shard's SNPs at the 500,000-sample shapes (the l x l Gram of a sharded D side is summed over the
+  // shards through the allreduce hook).
+  const bool orth_snp_side = D < N && !getenv("GPCA_DEBUG_ORTH_SAMPLE_SIDE");
   for (uint32_t it = 0; it < power_iters; ++it) {
-    GPCA_TRY(orthonormalize(c, Y.p, N, l, l, false, s));
-    GPCA_TRY(sketch_snp_side(c, Y.p, Z.p, l, l, ldz, true, true));   // Z = S Q
-    // (range(S^T Z) does not depend on a column transform of Z; the snp-side basis is left unnormalised
-    //  between the two half-steps, the sample side is re-orthonormalised every iteration)
-    GPCA_TRY(sketch_sample_side(c, Z.p, Y.p, l, ldz, l, true));   // Y = S^T Z
+    if (!orth_snp_side) {
+      GPCA_TRY(orthonormalize(c, Y.p, N, l, l, false, s));
+      GPCA_TRY(sketch_snp_side(c, Y.p, Z.p, l, l, ldz, true, true));   // Z = S Q
+      GPCA_TRY(sketch_sample_side(c, Z.p, Y.p, l, ldz, l, true));      // Y = S^T Z
+    } else {
+      GPCA_TRY(sketch_snp_side(c, Y.p, Z.p, l, l, ldz, false, true));  // Z = S Y
+      GPCA_TRY(orthonormalize(c, Z.p, D, l, ldz, c->allreduce != nullptr, s));
+      c->stats_for = nullptr;                                          // (any statistics of Z are stale now)
+      GPCA_TRY(sketch_sample_side(c, Z.p, Y.p, l, ldz, l, false));     // Y = S^T Q_z
+    }
   }
   GPCA_TRY(orthonormalize(c, Y.p, N, l, l, false, s));
   GPCA_TRY(sketch_snp_side(c, Y.p, Z.p, l, l, ldz, true, true));  // B = S Q   [D x l]

@@ -121,3 +121,22 @@ def test_rfit_generated_test_matrix_matches_materialised(gpu_ctx, monkeypatch):
     assert pca.subspace_angle(sc0[:, :3], sc0_m[:, :3]) < 5e-3
     sc_o, ev_o, _ = pca.rfit(S, 5, 10, seed=9, power_iters=0)
     assert np.abs(ev0 / ev_o - 1).max() < 2e-3 and np.abs(ev0_m / ev_o - 1).max() < 2e-3
+
+
+@pytest.mark.parametrize("engine", [0, 2])
+def test_rfit_more_samples_than_snps(gpu_ctx, engine, monkeypatch):
+    """N > D: the power iteration re-orthonormalises the SNP side (the one with fewer rows) instead of the sample side.
+    Same subspace either way: parity with the oracle (which orthonormalises the sample side) and with the other
+    ordering (GPCA_DEBUG_ORTH_SAMPLE_SIDE)."""
+    S = _prep(gpu_ctx, 3000, 1400, 5, seed=17, vcf=True)
+    assert S.shape[0] < 3000
+    gpu_ctx.set_sketch_engine(engine)
+    monkeypatch.delenv("GPCA_DEBUG_ORTH_SAMPLE_SIDE", raising=False)
+    sc, ev, ld = gpu_ctx.rfit(4, 10, power_iters=2, seed=3)
+    sc_o, ev_o, ld_o = pca.rfit(S, 4, 10, seed=3, power_iters=2)
+    assert np.abs(ev / ev_o - 1).max() < EV_RTOL
+    assert pca.subspace_angle(sc, sc_o) < ANGLE_TOL and pca.subspace_angle(ld, ld_o) < ANGLE_TOL
+    monkeypatch.setenv("GPCA_DEBUG_ORTH_SAMPLE_SIDE", "1")
+    sc_s, ev_s, ld_s = gpu_ctx.rfit(4, 10, power_iters=2, seed=3)
+    assert np.abs(ev / ev_s - 1).max() < EV_RTOL
+    assert pca.subspace_angle(sc, sc_s) < ANGLE_TOL and pca.subspace_angle(ld, ld_s) < ANGLE_TOL
