@@ -27,15 +27,19 @@ def _orth_eig(y, allreduce=None):
     return y
 
 
-def rfit_sharded(S_loc, k, oversample, seed, power_iters, row0, d_total, allreduce):
-    """Mirror of gpca_rfit for one shard S_loc [D_loc, N]; allreduce(x) returns the sum over shards."""
+def rfit_sharded(S_loc, k, oversample, seed, power_iters, row0, d_total, allreduce, orth_snp_side=False):
+    """Mirror of gpca_rfit for one shard S_loc [D_loc, N]; allreduce(x) returns the sum over shards.
+    orth_snp_side: the variant gpca_rfit takes when a device holds fewer SNPs than samples -- the D-side iterate is
+    re-orthonormalised (its l x l Gram summed over the shards) and the N-side one is left as it comes."""
     d_loc, n = S_loc.shape
     l = min(k + oversample, n, d_total)
     omega = rng.gaussian_matrix(seed, pca.STREAM_RFIT_OMEGA, row0, d_loc, l)
     y = allreduce(S_loc.T @ omega)
     for _ in range(power_iters):
-        q = _orth_eig(y)
-        z = S_loc @ q
+        if orth_snp_side:
+            z = _orth_eig(S_loc @ y, allreduce)
+        else:
+            z = S_loc @ _orth_eig(y)
         y = allreduce(S_loc.T @ z)
     q = _orth_eig(y)
     b = S_loc @ q
@@ -47,17 +51,17 @@ def rfit_sharded(S_loc, k, oversample, seed, power_iters, row0, d_total, allredu
     return scores, w[:k] / (n - 1), rot
 
 
-def _make():
-    g, _ = synth.balding_nichols(300, 2400, n_pops=5, seed=3)
+def _make(n=300, m=2400):
+    g, _ = synth.balding_nichols(n, m, n_pops=5, seed=3)
     keep, mean, sd, _ = bed.snp_qc_and_std_params(g, max_hwe_p=1.0)
     return pca.standardize_dense(g[keep], mean[keep].astype(np.float64), sd[keep].astype(np.float64))
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, shape=(300, 2400), orth_snp_side=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    S = _make()
+    S = _make(*shape)
     d = S.shape[0]
     bounds = [d * r // world for r in range(world + 1)]
     lo, hi = bounds[rank], bounds[rank + 1]
@@ -67,7 +71,7 @@ def _worker(rank, world, port, out):
         dist.all_reduce(t)
         return t.numpy()
 
-    sc, ev, rot = rfit_sharded(S[lo:hi], 4, 10, 42, 2, lo, d, allreduce)
+    sc, ev, rot = rfit_sharded(S[lo:hi], 4, 10, 42, 2, lo, d, allreduce, orth_snp_side)
     np.savez(os.path.join(out, f"r{rank}.npz"), sc=sc, ev=ev, rot=rot, lo=lo, hi=hi)
     dist.destroy_process_group()
 
@@ -89,6 +93,31 @@ def test_snp_sharded_rfit_two_ranks_gloo(tmp_path):
     one = rfit_sharded(S, 4, 10, 42, 2, 0, S.shape[0], lambda x: x)
     assert np.abs(r0["ev"] / one[1] - 1).max() < 1e-10
     assert pca.subspace_angle(r0["sc"], one[0]) < 1e-7
+    sc_o, ev_o, rot_o = pca.rfit(S, 4, 10, seed=42, power_iters=2)
+    assert np.abs(r0["ev"] / ev_o - 1).max() < 1e-8
+    assert pca.subspace_angle(r0["sc"], sc_o) < 1e-6
+    assert pca.subspace_angle(rot, rot_o) < 1e-6
+
+
+def test_snp_sharded_rfit_snp_side_orthonormalisation_gloo(tmp_path):
+    """More samples than SNPs per device: the sharded D-side iterate is orthonormalised through an l x l Gram
+    allreduce (drivers.cu, orth_snp_side).  Two gloo ranks against one shard and against the oracle."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    shape = (900, 700)
+    mp.spawn(_worker, args=(2, port, str(tmp_path), shape, True), nprocs=2, join=True)
+    S = _make(*shape)
+    assert S.shape[0] < S.shape[1]
+    r0 = np.load(tmp_path / "r0.npz")
+    r1 = np.load(tmp_path / "r1.npz")
+    assert np.allclose(r0["sc"], r1["sc"], rtol=0, atol=1e-9)
+    assert np.array_equal(r0["ev"], r1["ev"])
+    rot = np.concatenate([r0["rot"], r1["rot"]])
+    one = rfit_sharded(S, 4, 10, 42, 2, 0, S.shape[0], lambda x: x, True)
+    assert np.abs(r0["ev"] / one[1] - 1).max() < 1e-10
+    assert pca.subspace_angle(r0["sc"], one[0]) < 1e-7
+    # the oracle orthonormalises the sample side: same subspace
     sc_o, ev_o, rot_o = pca.rfit(S, 4, 10, seed=42, power_iters=2)
     assert np.abs(r0["ev"] / ev_o - 1).max() < 1e-8
     assert pca.subspace_angle(r0["sc"], sc_o) < 1e-6
