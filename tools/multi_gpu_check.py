@@ -13,7 +13,11 @@ local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
-n, m_shard, nblk_shard = 6000, 24_000, 40
+# default: more SNPs than samples per device; `python ... multi_gpu_check.py 20000 8000 20` covers the other case (the
+# rfit power iteration then orthonormalises the sharded SNP side through the Gram allreduce)
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 6000
+m_shard = int(sys.argv[2]) if len(sys.argv) > 2 else 24_000
+nblk_shard = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 qc = gp.QcConfig(0.98, 0.0, 1.0)                 # keep every SNP: shards and the full run see the same set
 
 
@@ -43,7 +47,7 @@ cfg = gp.EigenSnpConfig(target_num_global_pcs=6, min_subset_size=1500, max_subse
 sc_e, ev_e, ld_e = ctx.eigensnp(blocks_for(d, nblk_shard), cfg)
 ctx.close()
 dist.barrier()
-out = {"world": world}
+out = {"world": world, "n": n, "m_shard": m_shard}
 if rank == 0:
     full = gp.Context(local)
     dfull = load(full, 0, world * m_shard)
