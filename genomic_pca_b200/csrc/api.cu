@@ -622,22 +622,52 @@ static int ingest_core(gpca_ctx* c, const uint8_t* host_payload, int fd, uint64_
     float* u_sd = u_mean + rows_per_chunk;
     float* u_inv = u_sd + rows_per_chunk;
     float* u_mu = u_inv + rows_per_chunk;
-    uint64_t kept = 0;
-    for (uint64_t t = 0; t < nr; ++t) {
-      const uint64_t j = r0 + t;
-      if (!keep_out[j]) continue;
-      const float m = mean_out[j], sdv = sd_out[j];
-      float inv = 0.f, mu = 0.f;
-      if (!(std::fabs(sdv) < 1e-9f)) {   // same f32 expressions as prepare.rs:1948-1949
-        inv = 1.0f / sdv;
-        mu = m * inv;
+    // Compaction on all host threads: the kept SNPs of fixed 8,192-row blocks are counted, the block offsets are a
+    // short serial prefix sum, and every block then writes its survivors at its offset (serially this loop was 1.3 ms
+    // per 128 MB chunk -- with it the host half of the pipeline took longer than the chunk's 2.4 ms on the bus).
+    constexpr uint64_t CB = 8192;
+    const uint64_t ncb = (nr + CB - 1) / CB;
+    std::vector<uint64_t> cb_off(ncb + 1, 0), cb_miss(ncb, 0);
+    std::vector<float> cb_inv(ncb, 0.f);
+    parallel_for(ncb, [&](uint64_t lo, uint64_t hi) {
+      for (uint64_t b = lo; b < hi; ++b) {
+        uint64_t cnt = 0;
+        const uint64_t t1 = std::min<uint64_t>(nr, (b + 1) * CB);
+        for (uint64_t t = b * CB; t < t1; ++t) cnt += keep_out[r0 + t] ? 1 : 0;
+        cb_off[b + 1] = cnt;
       }
-      u_idx[kept] = j; u_mean[kept] = m; u_sd[kept] = sdv; u_inv[kept] = inv; u_mu[kept] = mu;
-      c->pca_idx[D + kept] = j; c->h_mean[D + kept] = m; c->h_sd[D + kept] = sdv;
-      c->h_inv[D + kept] = inv; c->h_muinv[D + kept] = mu;
-      inv_max = std::max(inv_max, std::fabs(inv));
-      nmiss_total += N - hc[4 * j];
-      ++kept;
+    }, 1);
+    for (uint64_t b = 0; b < ncb; ++b) cb_off[b + 1] += cb_off[b];
+    const uint64_t kept = cb_off[ncb];
+    const uint64_t D0 = D;
+    parallel_for(ncb, [&](uint64_t lo, uint64_t hi) {
+      for (uint64_t b = lo; b < hi; ++b) {
+        uint64_t w = cb_off[b], nm = 0;
+        float imax = 0.f;
+        const uint64_t t1 = std::min<uint64_t>(nr, (b + 1) * CB);
+        for (uint64_t t = b * CB; t < t1; ++t) {
+          const uint64_t j = r0 + t;
+          if (!keep_out[j]) continue;
+          const float m = mean_out[j], sdv = sd_out[j];
+          float inv = 0.f, mu = 0.f;
+          if (!(std::fabs(sdv) < 1e-9f)) {   // same f32 expressions as prepare.rs:1948-1949
+            inv = 1.0f / sdv;
+            mu = m * inv;
+          }
+          u_idx[w] = j; u_mean[w] = m; u_sd[w] = sdv; u_inv[w] = inv; u_mu[w] = mu;
+          c->pca_idx[D0 + w] = j; c->h_mean[D0 + w] = m; c->h_sd[D0 + w] = sdv;
+          c->h_inv[D0 + w] = inv; c->h_muinv[D0 + w] = mu;
+          imax = std::max(imax, std::fabs(inv));
+          nm += N - hc[4 * j];
+          ++w;
+        }
+        cb_miss[b] = nm;
+        cb_inv[b] = imax;
+      }
+    }, 1);
+    for (uint64_t b = 0; b < ncb; ++b) {
+      nmiss_total += cb_miss[b];
+      inv_max = std::max(inv_max, cb_inv[b]);
     }
     t_compact += ms_since(tp); tp = now();
     if (kept) {
