@@ -1,18 +1,24 @@
 #!/usr/bin/env python
-"""bench.py -- the hot path (randomized-SVD sketch passes of the rfit PCA) on synthetic data.
+"""bench.py -- the hot path (randomized-SVD sketch passes of the rfit / EigenSNP PCA) on synthetic data.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--snps M] [--samples N]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-One "step" = one complete rfit PCA (1 + 2q + 2 sketch passes over the resident 2-bit matrix, the
-re-orthonormalisations and the small eigensolves) on the workload named in config.workload.
-metric = genotype GB/s per sketch pass = packed genotype bytes streamed by the sketch passes / time.
-  value : inputs resident in HBM when the timed region starts (device-timed, CUDA events, max over ranks)
-  e2e   : the same PCA through the C ABI from HOST buffers (pinned .bed payload -> H2D -> counts ->
-          QC -> resident build -> rfit -> scores back on the host), H2D/D2H inside the timed region.
-N > 1 (torchrun): SNP-sharded, one rank per GPU, weak scaling (per-GPU shard fixed); the N x l sketch
-is summed over ranks with NCCL after every sample-side pass (the path's one exchange step).
+Workload = BASELINE.json config 4, the configuration the metric is quoted on: 500,000 samples x 700,000 SNPs, 2-bit
+packed (87.5 GB), k = 20, STRONG-scaled over the GPUs -- rank r owns the SNPs of LD blocks [r B/N, (r+1) B/N) of
+B = 1,696 blocks; the one exchange is the sum of the N x l sketch after every sample-side pass (NCCL, issued by the
+library on its own stream).
+One "step" = one complete rfit PCA (k = 20, oversample 10, q = 2: 7 sketch passes over the resident 2-bit matrix, the
+re-orthonormalisations, the small eigensolves, scores back on the host).
+metric = genotype GB/s per sketch pass = packed bytes all ranks stream per pass x passes / step time.
+  value : matrix resident in HBM when the timed region starts (CUDA events on the library's stream, max over ranks)
+  e2e   : the same PCA through the C ABI from HOST buffers: gpca_ingest_bed of each rank's shard from pinned host memory
+          (H2D, counts, QC ladder on host threads, both resident orientations) + gpca_rfit + scores on the host.
+Extra records in the same line: "eigensnp" (the EigenSNP mode of the same configuration, device-resident and e2e) and
+"c3" (BASELINE config 3, 2,504 x 10M rfit on rank 0's GPU: the round-1 headline, with `parity_at_scale` against an
+exact f64 eigen-decomposition of the GRM).
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -31,33 +37,45 @@ OVERSAMPLE = 10
 POWER_ITERS = 2
 RFIT_SEED = 42
 N_POPS = K_COMPONENTS + 2
+FST, FST_GRADE = 0.1, 1.0        # graded drift: distinct structural eigenvalues (gpca.h, gpca_synth_bed_device)
+C4_SAMPLES, C4_SNPS, C4_BLOCKS = 500_000, 700_000, 1696
+C3_SAMPLES, C3_SNPS = 2504, 10_000_000
 
 
 def parse_args():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=None, help="timed steps (default 20; 3 for --impl reference)")
-    p.add_argument("--warmup", type=int, default=None, help="untimed steps (default 5; 1 for --impl reference)")
+    p.add_argument("--steps", type=int, default=None, help="timed rfit steps (default 10; 2 for --impl reference)")
+    p.add_argument("--warmup", type=int, default=None, help="untimed steps (default 3; 0 for --impl reference)")
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    p.add_argument("--samples", type=int, default=2504)
-    p.add_argument("--snps", type=int, default=10_000_000, help="SNPs per GPU (weak scaling)")
+    p.add_argument("--samples", type=int, default=C4_SAMPLES)
+    p.add_argument("--snps", type=int, default=C4_SNPS, help="SNPs of the WHOLE job (strong scaling: split over the GPUs)")
+    p.add_argument("--blocks", type=int, default=C4_BLOCKS, help="LD blocks of the whole job")
     p.add_argument("--engine", type=int, default=None)
-    p.add_argument("--components", type=int, default=None, help="k (default 20 = BASELINE config 3; config 5 uses 40)")
-    p.add_argument("--power-iters", type=int, default=None, help="q (default 2; config 5 uses 4)")
-    p.add_argument("--cpu-snps", type=int, default=150_000, help="SNP rows of the CPU baseline sample")
+    p.add_argument("--components", type=int, default=None, help="k (default 20)")
+    p.add_argument("--power-iters", type=int, default=None, help="q (default 2)")
+    p.add_argument("--cpu-snps", type=int, default=None,
+                   help="SNP rows of the CPU sample (default 512; --impl reference: up to 1024, scaled down so that\n"
+                        "steps + warmup stay within ~2 minutes of CPU time)")
+    p.add_argument("--e2e-steps", type=int, default=2)
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu", action="store_true")
-    p.add_argument("--no-ukb", action="store_true", help="skip the supplementary 500k x 87.5k shard measurement")
+    p.add_argument("--no-eigensnp", action="store_true")
+    p.add_argument("--no-c3", action="store_true", help="skip the config-3 record")
+    p.add_argument("--no-parity", action="store_true", help="skip parity_at_scale of the config-3 record")
+    p.add_argument("--c3-snps", type=int, default=C3_SNPS)
     a = p.parse_args()
-    # defaults: a timed region long enough (~0.3 s) for the clock sampler to see the run under load; the CPU arm's steps
-    # are seconds each
     if a.steps is None:
-        a.steps = 3 if a.impl == "reference" else 20
+        a.steps = 2 if a.impl == "reference" else 10
     if a.warmup is None:
-        a.warmup = 1 if a.impl == "reference" else 5
-    global K_COMPONENTS, POWER_ITERS
+        a.warmup = 0 if a.impl == "reference" else 3
+    if a.cpu_snps is None:
+        # one rfit over 500,000 samples x 1,024 SNPs takes ~20 s on 8-16 host cores (most of it LAPACK QR of N x l)
+        a.cpu_snps = 512 if a.impl != "reference" else max(64, min(1024, int(1024 * 6 / max(a.steps + a.warmup, 1))))
+    global K_COMPONENTS, POWER_ITERS, N_POPS
     if a.components is not None:
         K_COMPONENTS = a.components
+        N_POPS = K_COMPONENTS + 2
     if a.power_iters is not None:
         POWER_ITERS = a.power_iters
     return a
@@ -183,31 +201,43 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
+
 # ------------------------------------------------------------------------------------------
-def synth_bed_device(torch, n_samples, n_snps, snp_offset, device):
-    """Balding-Nichols genotypes generated on the device straight into PLINK .bed layout
-    (P = k+2 populations, ancestral AF ~ U(0.05,0.5), F_ST = 0.1, no missing calls) by the library's
+def synth_bed_device(torch, n_samples, n_snps, snp_offset, device, fst_grade=FST_GRADE):
+    """Balding-Nichols genotypes generated on the device straight into PLINK .bed layout (P = k+2
+    populations, ancestral AF ~ U(0.05,0.5), F_ST = 0.1 graded over the populations, no missing calls) by the library's
     counter-based generator (Philox keyed by (DATA_SEED, global SNP index, sample)): rows [a, b) of any shard are the
-    rows [a, b) of the whole matrix, whatever the number of GPUs."""
+    rows [a, b) of the whole matrix, whatever the number of GPUs.  (tests / tools; the bench itself draws the payload
+    into host memory, HostPayload.)"""
     import genomic_pca_b200 as gp
     bps = (n_samples + 3) // 4
     out = torch.empty((n_snps, bps), dtype=torch.uint8, device=device)
     gen = gp.Context(device.index or 0)
-    gen.synth_bed_device(out.data_ptr(), n_samples, n_snps, snp_offset, DATA_SEED, N_POPS, 0.1, 0.0)
+    gen.synth_bed_device(out.data_ptr(), n_samples, n_snps, snp_offset, DATA_SEED, N_POPS, FST, 0.0, fst_grade)
     gen.close()
     return out
 
 
-def cpu_rfit_sample(n_samples, n_snps, steps=1):
+def shard_of(rank, world, n_blocks_total, m_total):
+    """Strong scaling: rank's LD blocks [b0, b1) of the whole job and the SNP rows [s0, s1) they cover."""
+    edges = np.linspace(0, m_total, n_blocks_total + 1).astype(np.int64)
+    b0, b1 = rank * n_blocks_total // world, (rank + 1) * n_blocks_total // world
+    return b0, b1, int(edges[b0]), int(edges[b1])
+
+
+def cpu_rfit_sample(n_samples, n_snps, steps=1, warmup=0):
     """The reference's CPU algorithm (oracle restatement: f64 matrix, OpenBLAS GEMMs, numpy QR/eigh)
-    timed on a bounded sample of the same workload.  Returns (seconds per step, passes, bytes per pass)."""
+    timed on a bounded sample of the same workload (the sample is drawn once, outside the timed region).
+    Returns (seconds per step, passes, bytes per pass)."""
     from oracle import pca, synth
-    g = np.concatenate([synth.balding_nichols(n_samples, min(20000, n_snps - c0), n_pops=N_POPS, seed=7 + c0)[0]
-                        for c0 in range(0, n_snps, 20000)])
+    g = np.concatenate([synth.balding_nichols(n_samples, min(512, n_snps - c0), n_pops=N_POPS, seed=7 + c0)[0]
+                        for c0 in range(0, n_snps, 512)])
     mean = g.mean(1)
     sd = g.std(1, ddof=1)
     ok = sd > 1e-9
     g = g[ok]
+    for _ in range(warmup):
+        pca.rfit(pca.standardize_dense(g, mean[ok], sd[ok]), K_COMPONENTS, OVERSAMPLE, seed=RFIT_SEED, power_iters=POWER_ITERS)
     t0 = time.perf_counter()
     for _ in range(steps):
         # build_matrix (vcf.rs:317-345: u8 -> f64) + standardise + rfit + transform, as the reference does per run
@@ -218,29 +248,33 @@ def cpu_rfit_sample(n_samples, n_snps, steps=1):
     return dt, passes, g.shape[0] * ((n_samples + 3) // 4)
 
 
-# ------------------------------------------------------------------------------------------
+def blas_threads(n):
+    """torchrun exports OMP_NUM_THREADS=1 for nproc > 1: the CPU arm sets its BLAS threads itself and records them."""
+    try:
+        from threadpoolctl import threadpool_limits
+        return threadpool_limits(limits=n)
+    except Exception:
+        return None
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    per_step = []
-    for _ in range(args.warmup if args.warmup < 2 else 1):
-        cpu_rfit_sample(args.samples, args.cpu_snps)
-    for _ in range(args.steps):
-        dt, passes, bpp = cpu_rfit_sample(args.samples, args.cpu_snps)
-        per_step.append(dt)
-    dt = float(np.mean(per_step))
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lim = blas_threads(cores)
+    n = args.samples
+    dt, passes, bpp = cpu_rfit_sample(n, args.cpu_snps, steps=args.steps, warmup=min(args.warmup, 1))
     val = passes * bpp / dt / 1e9
     line = {
         "impl": "reference", "metric": "genotype_GBps_per_sketch_pass", "value": val, "unit": "GB/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"rfit k={K_COMPONENTS} oversample={OVERSAMPLE} q={POWER_ITERS}, "
-                               f"{args.samples} samples x {args.cpu_snps} SNPs (bounded CPU sample of the "
-                               f"1000G-shape config: {args.samples} x {args.snps})",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"rfit k={K_COMPONENTS} oversample={OVERSAMPLE} q={POWER_ITERS}: {n} samples x "
+                               f"{args.cpu_snps} SNPs (bounded CPU sample of BASELINE config 4, {n} x {args.snps})",
                    "passes_per_step": passes},
         "cpu_baseline": {"value": val, "unit": "GB/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.samples} samples x {args.cpu_snps} SNPs, numpy/OpenBLAS f64 restatement "
+                         "blas_threads": cores if lim is not None else os.environ.get("OMP_NUM_THREADS", "default"),
+                         "sample": f"{n} samples x {args.cpu_snps} SNPs, numpy/OpenBLAS f64 restatement "
                                    "(reference binary cannot be built here: no cargo/rustc)"},
         "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -248,19 +282,190 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
-def make_allreduce_hook(torch, dist, dev):
-    """The library's one exchange step (sum of a device buffer over the shards) bound to NCCL through torch.distributed,
-    on the library's own stream."""
-    def hook(ptr, count, dtype, stream):
-        es = torch.cuda.ExternalStream(stream, device=dev)
-        td = torch.float32 if dtype == 0 else torch.float64
-        iface = {"shape": (count,), "typestr": "<f4" if dtype == 0 else "<f8", "data": (ptr, False), "version": 2}
-        holder = type("P", (), {"__cuda_array_interface__": iface})()
-        t = torch.as_tensor(holder, device=dev)
-        assert t.dtype == td
-        with torch.cuda.stream(es):
-            dist.all_reduce(t)
-    return hook
+# ------------------------------------------------------------------------------------------
+class HostPayload:
+    """The rank's rows of the .bed payload in pinned host memory (what a host would have read from the file)."""
+
+    def __init__(self, ctx, n, m, snp_offset):
+        self.ctx, self.n, self.m = ctx, n, m
+        self.bps = (n + 3) // 4
+        self.nbytes = self.m * self.bps
+        t0 = time.perf_counter()
+        self.ptr = ctx.host_alloc(self.nbytes)
+        self.alloc_s = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        ctx.synth_bed_host(self.ptr, n, m, snp_offset, DATA_SEED, N_POPS, FST, 0.0, FST_GRADE)
+        self.fill_s = time.perf_counter() - t0
+
+    def free(self):
+        if self.ptr:
+            self.ctx.host_free(self.ptr, self.nbytes)
+            self.ptr = 0
+
+
+def max_over_ranks(torch, dist, dev, world, vals):
+    t = torch.tensor(vals, device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(x) for x in t.tolist()]
+
+
+def sum_over_ranks(torch, dist, dev, world, vals):
+    t = torch.tensor(vals, device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return [float(x) for x in t.tolist()]
+
+
+def timed_rfit(torch, dist, ctx, dev, world, steps, warmup, rfit_out, sample_clocks=None):
+    """K rfit calls on the resident matrix; device time between CUDA events on the library's stream, max over ranks."""
+    def step():
+        return ctx.rfit(K_COMPONENTS, OVERSAMPLE, power_iters=POWER_ITERS, seed=RFIT_SEED, want_loadings=False,
+                        out=rfit_out)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        step()
+    ctx.sketch_stats(reset=True)
+    ctx.reset_launch_count()
+    coll0 = ctx.collective_count
+    barrier()
+    if sample_clocks is not None:
+        sample_clocks.start()
+    lib_stream = torch.cuda.ExternalStream(ctx.stream, device=dev)      # the stream the kernels are launched on
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(lib_stream)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        sc, ev, _ = step()
+    ev1.record(lib_stream)
+    barrier()
+    wall = time.perf_counter() - t0
+    dev_s = ev0.elapsed_time(ev1) * 1e-3
+    clocks = sample_clocks.stop() if sample_clocks is not None else None
+    launches = ctx.launch_count
+    sk_ms, sk_bytes, sk_n = ctx.sketch_stats(reset=True)
+    sk_kernel_ms = ctx.last_kernel_ms
+    t_step = max_over_ranks(torch, dist, dev, world, [dev_s / steps])[0]
+    return {"t_step": t_step, "wall_per_step": wall / steps, "clocks": clocks, "launches": launches, "sk_ms": sk_ms,
+            "sk_n": sk_n, "sk_kernel_ms": sk_kernel_ms, "eigenvalues": ev, "scores": sc,
+            "collectives_per_step": (ctx.collective_count - coll0) / steps}
+
+
+def e2e_loop(torch, dist, dev, world, fn, steps):
+    """wall clock around `steps` calls of fn (each: ingest from pinned host memory + PCA + results on the host),
+    barrier + synchronize on both sides, max over ranks"""
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fn()
+    barrier()
+    te = (time.perf_counter() - t0) / steps
+    return max_over_ranks(torch, dist, dev, world, [te])[0]
+
+
+def subspace_angle(a, b):
+    """largest principal angle (rad) between the column spaces of two [n x k] matrices (float64 numpy)"""
+    qa, _ = np.linalg.qr(np.asarray(a, dtype=np.float64))
+    qb, _ = np.linalg.qr(np.asarray(b, dtype=np.float64))
+    resid = qa - qb @ (qb.T @ qa)
+    s = np.linalg.svd(resid, compute_uv=False)
+    return float(np.arcsin(min(1.0, s[0])))
+
+
+def exact_pca_f64(torch, payload, n, keep, mean, sd, k, chunk=32768):
+    """Exact PCA of the standardized matrix for parity_at_scale: the N x N Gram matrix S^T S accumulated in float64 by
+    torch over chunks of SNP rows decoded from the .bed payload (count_a1: 00 -> 2, 10 -> 1, 11 -> 0), then eigh.
+    Test infrastructure, independent of the library's kernels.  Returns (explained variance [k], V [n x k])."""
+    dev = payload.device
+    bps = payload.shape[1]
+    lut = torch.tensor([2.0, float("nan"), 1.0, 0.0], dtype=torch.float64, device=dev)
+    shifts = torch.tensor([0, 2, 4, 6], dtype=torch.uint8, device=dev)
+    idx = torch.as_tensor(np.nonzero(keep)[0], device=dev)
+    mu = torch.as_tensor(mean[keep].astype(np.float64), device=dev)
+    isd = 1.0 / torch.as_tensor(sd[keep].astype(np.float64), device=dev)
+    gram = torch.zeros((n, n), dtype=torch.float64, device=dev)
+    for c0 in range(0, idx.numel(), chunk):
+        rows = idx[c0:c0 + chunk]
+        b = payload.index_select(0, rows)
+        codes = ((b.unsqueeze(-1) >> shifts) & 3).reshape(rows.numel(), bps * 4)[:, :n].long()
+        s = (lut[codes] - mu[c0:c0 + chunk, None]) * isd[c0:c0 + chunk, None]
+        gram.addmm_(s.t(), s)
+        del b, codes, s
+    evals, evecs = torch.linalg.eigh(gram)
+    top = torch.argsort(evals, descending=True)[:k]
+    return (evals[top] / (n - 1)).cpu().numpy(), evecs[:, top].cpu().numpy()
+
+
+# ------------------------------------------------------------------------------------------
+def run_c3(args, torch, gp, dev, pk, pk_src):
+    """BASELINE config 3 (1000G shape, 2,504 x 10M, rfit k=20) on one GPU: device-resident step time, the sketch
+    kernel's roofline, e2e from pinned host memory, and parity_at_scale against the exact f64 PCA."""
+    n, m = C3_SAMPLES, args.c3_snps
+    bps = (n + 3) // 4
+    ctx = gp.Context(dev.index or 0)
+    if args.engine is not None:
+        ctx.set_sketch_engine(args.engine)
+    ctx.set_sketch_timing(True)
+    host = HostPayload(ctx, n, m, 0)
+    stats_out = (np.empty(m, dtype=np.uint8), np.empty(m, dtype=np.float32), np.empty(m, dtype=np.float32))
+    rfit_out = (np.ones((n, K_COMPONENTS), dtype=np.float64), np.ones(K_COMPONENTS, dtype=np.float64), None)
+
+    def ingest():
+        return ctx.ingest_bed(host.ptr, n, m, qc=None, vcf_maf=0.01, out=stats_out)
+
+    keep, mean, sd, _, d_kept = ingest()
+    r = timed_rfit(torch, None, ctx, dev, 1, max(args.steps, 10), max(args.warmup, 3), rfit_out)
+    passes = 2 * POWER_ITERS + 3
+    bytes_per_pass = d_kept * bps
+    t_kern = r["sk_kernel_ms"] / max(r["sk_n"], 1) * 1e-3
+    rec = {"workload": f"1000G-shape rfit k={K_COMPONENTS} oversample={OVERSAMPLE} q={POWER_ITERS}: {n} samples x {m} SNPs "
+                       f"({d_kept} after MAF 0.01) on one GPU",
+           "ms_per_step": r["t_step"] * 1e3, "value": passes * bytes_per_pass / r["t_step"] / 1e9, "unit": "GB/s",
+           "gpu_launches": int(r["launches"]),
+           "roofline": {"bound": "hbm", "kernel": "sketch_i8_kernel", "achieved": bytes_per_pass / t_kern / 1e9 if t_kern else 0.0,
+                        "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": bytes_per_pass / t_kern / 1e9 / pk["hbm_gbs"] if t_kern else 0.0,
+                        "ms_per_launch": t_kern * 1e3, "peak_source": pk_src,
+                        "kernel_share_of_step": (r["sk_kernel_ms"] * 1e-3 / max(args.steps, 10)) / r["t_step"]},
+           "eigenvalues_head": [float(x) for x in r["eigenvalues"][:3]]}
+    if not args.no_e2e:
+        def e2e_step():
+            ingest()
+            ctx.rfit(K_COMPONENTS, OVERSAMPLE, power_iters=POWER_ITERS, seed=RFIT_SEED, want_loadings=False, out=rfit_out)
+        e2e_step()
+        te = e2e_loop(torch, None, dev, 1, e2e_step, 3)
+        rec["e2e"] = {"value": passes * bytes_per_pass / te / 1e9, "unit": "GB/s", "ms_per_step": te * 1e3, "steps": 3,
+                      "h2d_bytes_per_step": int(m * bps), "d2h_bytes_per_step": int(n * K_COMPONENTS * 8 + m * 16)}
+    if not args.no_parity:
+        sc, ev, _ = ctx.rfit(K_COMPONENTS, OVERSAMPLE, power_iters=POWER_ITERS, seed=RFIT_SEED, want_loadings=False)
+        ctx.close()
+        ctx = None
+        t0 = time.perf_counter()
+        payload = torch.empty((m, bps), dtype=torch.uint8, device=dev)
+        gen = gp.Context(dev.index or 0)
+        gen.synth_bed_device(payload.data_ptr(), n, m, 0, DATA_SEED, N_POPS, FST, 0.0, FST_GRADE)
+        gen.close()
+        ev_x, v_x = exact_pca_f64(torch, payload, n, np.asarray(keep[:m], dtype=bool), mean[:m], sd[:m], K_COMPONENTS)
+        del payload
+        torch.cuda.empty_cache()
+        rec["parity_at_scale"] = {
+            "against": "exact f64 eigen-decomposition of the N x N GRM of the standardized matrix (torch f64, chunked)",
+            "shape": f"{n} x {d_kept}", "eigenvalue_max_rel_err": float(np.max(np.abs(ev / ev_x - 1.0))),
+            "score_subspace_angle_rad": subspace_angle(sc, v_x), "tolerance": "1e-4 relative / 1e-3 rad",
+            "eigenvalue_gap_k_to_k1": None, "seconds": time.perf_counter() - t0}
+    if ctx is not None:
+        ctx.close()
+    host.free()
+    return rec
 
 
 def run_ours(args, rank, world):
@@ -273,229 +478,166 @@ def run_ours(args, rank, world):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-
-    n, m = args.samples, args.snps
+    pk, pk_src = peaks()
+    n, m_total, nb_total = args.samples, args.snps, args.blocks
     bps = (n + 3) // 4
-    payload = synth_bed_device(torch, n, m, rank * m, dev)
-    torch.cuda.synchronize()
+    b0, b1, s0, s1 = shard_of(rank, world, nb_total, m_total)
+    m = s1 - s0
+    nb = b1 - b0
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    host_threads = max(1, cores // max(local_world, 1))
 
     ctx = gp.Context(local_rank)
     if args.engine is not None:
         ctx.set_sketch_engine(args.engine)
+    ctx.set_host_threads(host_threads)
+    ctx.set_sketch_timing(True)
     if world > 1:
-        ctx.set_allreduce(make_allreduce_hook(torch, dist, dev))
-        ctx.set_shard(rank * m, world * m)
+        # the library's own NCCL communicator: rank 0 creates the id, torch.distributed only carries the bytes
+        box = [gp.binding.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        ctx.comm_init(box[0], rank, world)
+        ctx.set_shard(s0, m_total)
+    host = HostPayload(ctx, n, m, s0)
 
-    def prepare_from_device():
-        ctx.load_bed_device(payload.data_ptr(), n, m)
-        keep, mean, sd = ctx.vcf_maf_filter(0.01)
-        return ctx.set_pca_snps_mask(keep, mean, sd)
-
-    d_kept = prepare_from_device()
-    passes = 2 * POWER_ITERS + 3
-    bytes_per_pass = d_kept * bps                          # algorithmic: M_loc * ceil(N/4)
-    flops_per_pass = 2.0 * n * d_kept * (K_COMPONENTS + OVERSAMPLE)
-
-    # caller-owned result buffers, allocated (and touched) once, as a host application would
+    # ---- rfit: resident step time (value) and e2e ------------------------------------------------
+    stats_out = (np.empty(m, dtype=np.uint8), np.empty(m, dtype=np.float32), np.empty(m, dtype=np.float32),
+                 np.empty(m, dtype=np.uint8))
     rfit_out = (np.ones((n, K_COMPONENTS), dtype=np.float64), np.ones(K_COMPONENTS, dtype=np.float64), None)
+    t0 = time.perf_counter()
+    keep, mean, sd, _, d_kept = ctx.ingest_bed(host.ptr, n, m, qc=None, vcf_maf=0.01, out=stats_out[:3])
+    t_first_ingest = time.perf_counter() - t0
+    resident_rfit = ctx.resident_snp_rows
+    passes = 2 * POWER_ITERS + 3
+    bytes_per_pass = d_kept * bps                          # this rank's algorithmic bytes: M_loc * ceil(N/4)
+    job_bytes_per_pass, = sum_over_ranks(torch, dist, dev, world, [float(bytes_per_pass)])
+    d_total, = sum_over_ranks(torch, dist, dev, world, [float(d_kept)])
+    r = timed_rfit(torch, dist, ctx, dev, world, args.steps, args.warmup, rfit_out, ClockSampler(local_rank))
+    t_step = r["t_step"]
+    value = passes * job_bytes_per_pass / t_step / 1e9
+    e2e = None
+    if not args.no_e2e:
+        def e2e_rfit():
+            ctx.ingest_bed(host.ptr, n, m, qc=None, vcf_maf=0.01, out=stats_out[:3])
+            ctx.rfit(K_COMPONENTS, OVERSAMPLE, power_iters=POWER_ITERS, seed=RFIT_SEED, want_loadings=False, out=rfit_out)
+        te = e2e_loop(torch, dist, dev, world, e2e_rfit, args.e2e_steps)
+        e2e = {"value": passes * job_bytes_per_pass / te / 1e9, "unit": "GB/s", "ms_per_step": te * 1e3,
+               "steps": args.e2e_steps, "h2d_bytes_per_step": int(m_total * bps),
+               "d2h_bytes_per_step": int(world * (n * K_COMPONENTS * 8 + K_COMPONENTS * 8) + m_total * 16),
+               "pca_wall_s": te, "includes": "gpca_ingest_bed of every rank's shard from pinned host memory + gpca_rfit + "
+                                             "scores / eigenvalues on the host"}
 
-    def step():
-        return ctx.rfit(K_COMPONENTS, OVERSAMPLE, power_iters=POWER_ITERS, seed=RFIT_SEED, want_loadings=False,
-                        out=rfit_out)
+    # ---- EigenSNP on the same configuration --------------------------------------------------------
+    es = None
+    if not args.no_eigensnp:
+        cfg = gp.EigenSnpConfig(target_num_global_pcs=K_COMPONENTS)
+        ctx.set_memory_reserve(gp.binding.eigensnp_workspace_bytes(n, m, nb, cfg))
+        qc = gp.QcConfig(0.98, 0.01, 1.0)                 # HWE off: pooled structured populations fail it
 
-    def barrier():
+        def es_ingest():
+            return ctx.ingest_bed(host.ptr, n, m, qc=qc, out=stats_out)
+
+        _, _, _, _, d_es = es_ingest()
+        edges = np.linspace(0, d_es, nb + 1).astype(np.int64)
+        blocks = [np.arange(edges[i], edges[i + 1], dtype=np.uint64) for i in range(nb)]
+        es_out = (np.ones((n, K_COMPONENTS), dtype=np.float32), np.ones(K_COMPONENTS, dtype=np.float64),
+                  np.ones((d_es, K_COMPONENTS), dtype=np.float32))
+        ctx.eigensnp(blocks, cfg, out=es_out)
+        reps = 3
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        step()
-    ctx.sketch_stats(reset=True)
-    ctx.reset_launch_count()
-    sampler = ClockSampler(local_rank)
-    barrier()
-    sampler.start()
-    lib_stream = torch.cuda.ExternalStream(ctx.stream, device=dev)      # the stream the kernels are launched on
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(lib_stream)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        sc, ev, _ = step()
-    ev1.record(lib_stream)
-    barrier()
-    wall = time.perf_counter() - t0
-    dev_s = ev0.elapsed_time(ev1) * 1e-3
-    clocks = sampler.stop()
-    launches = ctx.launch_count
-    sk_ms, sk_bytes, sk_n = ctx.sketch_stats(reset=True)
-    sk_kernel_ms = ctx.last_kernel_ms
-    # device time between CUDA events on the library's stream (the wall clock is kept as a cross-check)
-    t_step = torch.tensor([dev_s / args.steps], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t_step, op=dist.ReduceOp.MAX)
-    t_step = float(t_step.item())
-    value = world * passes * bytes_per_pass / t_step / 1e9
-
-    # ---- e2e through the C ABI from pinned host memory --------------------------------------
-    e2e = None
-    if not args.no_e2e:
-        host = torch.empty((m, bps), dtype=torch.uint8, pin_memory=True)
-        host.copy_(payload)
-        torch.cuda.synchronize()
-        del payload
-        e2e_steps = max(1, min(args.steps, 3))
-
-        stats_out = (np.empty(m, dtype=np.uint8), np.empty(m, dtype=np.float32), np.empty(m, dtype=np.float32))
-
-        def e2e_step():
-            # one streaming ingest call (H2D copy, counts, MAF filter on host threads, resident matrices), then rfit;
-            # the keep mask and the per-SNP mean / sd come back to the host as in the reference's VCF flow
-            keep, mean, sd, _, d_pca = ctx.ingest_bed(host.data_ptr(), n, m, qc=None, vcf_maf=0.01, out=stats_out)
-            return ctx.rfit(K_COMPONENTS, OVERSAMPLE, power_iters=POWER_ITERS, seed=RFIT_SEED, want_loadings=False,
-                            out=rfit_out)
-
-        e2e_step()
-        barrier()
+        ctx.reset_launch_count()
         t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            sc2, ev2, _ = e2e_step()
-        barrier()
-        te = (time.perf_counter() - t0) / e2e_steps
-        te_t = torch.tensor([te], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(te_t, op=dist.ReduceOp.MAX)
-        te = float(te_t.item())
-        e2e = {"value": world * passes * bytes_per_pass / te / 1e9, "unit": "GB/s",
-               "h2d_bytes_per_step": int(m * bps), "d2h_bytes_per_step": int(n * K_COMPONENTS * 8 + K_COMPONENTS * 8 + m * 16),
-               "ms_per_step": te * 1e3, "steps": e2e_steps}
-
-    # supplementary measurement at the shape the headline metric is quoted on (all ranks take part: on N GPUs it is
-    # the 500k-sample array with N x 87.5k SNPs, EigenSNP with the N x l exchange over NCCL)
-    ukb = None
-    if not args.no_ukb and (n, m) == (2504, 10_000_000):
-        ctx.close()
+        for _ in range(reps):
+            sc_es, ev_es, _ = ctx.eigensnp(blocks, cfg, out=es_out)
+        t_es = (time.perf_counter() - t0) / reps
+        es_launches = ctx.launch_count // reps
+        t_es, = max_over_ranks(torch, dist, dev, world, [t_es])
+        es = {"workload": f"EigenSNP k={K_COMPONENTS}, {nb_total} LD blocks, effective defaults of src/main.rs:545-588",
+              "resident_wall_s": t_es, "gpu_launches": int(es_launches), "resident_snp_rows_frac": ctx.resident_snp_rows / max(d_es, 1),
+              "eigenvalues_head": [float(x) for x in ev_es[:3]]}
         if not args.no_e2e:
-            del host
-        else:
-            del payload
-        torch.cuda.empty_cache()
-        ukb = ukb_shard_supplement(torch, gp, dev, peaks()[0], rank, world, dist if world > 1 else None)
+            def e2e_es():
+                es_ingest()
+                ctx.eigensnp(blocks, cfg, out=es_out)
+            te_es = e2e_loop(torch, dist, dev, world, e2e_es, args.e2e_steps)
+            es["e2e"] = {"pca_wall_s": te_es, "ms_per_step": te_es * 1e3, "steps": args.e2e_steps,
+                         "h2d_bytes_per_step": int(m_total * bps),
+                         "d2h_bytes_per_step": int(world * n * K_COMPONENTS * 4 + m_total * (16 + K_COMPONENTS * 4))}
+    ctx.close()
+    host.free()
+    torch.cuda.empty_cache()
 
+    c3 = None
+    if not args.no_c3 and rank == 0:
+        try:
+            c3 = run_c3(args, torch, gp, dev, pk, pk_src)
+        except Exception as e:  # the headline record must not be lost to a failure of the supplementary one
+            c3 = {"error": repr(e)}
+    if world > 1:
+        dist.barrier()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    pk, pk_src = peaks()
     # dominant kernel = the sketch kernel; its launches are bracketed by CUDA events on the library's stream
-    # (one launch per pass); the pass-level figure also contains operand prep and the split-K reduce.
-    t_kern = (sk_kernel_ms / max(sk_n, 1)) * 1e-3
-    t_pass = (sk_ms / max(sk_n, 1)) * 1e-3
-    ach_gbs = bytes_per_pass / t_kern / 1e9 if t_kern > 0 else 0.0
-    ach_tf = flops_per_pass / t_kern / 1e12 if t_kern > 0 else 0.0
-    eng = ctx_engine(ctx, args)
-    roofline = {"bound": "hbm", "achieved": ach_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": ach_gbs / pk["hbm_gbs"], "traffic": TRAFFIC_NCU.get(eng) if (n, m) == (2504, 10_000_000) else None, "peak_source": pk_src,
-                "kernel": {0: "sketch_simt_kernel", 1: "sketch_tc_kernel",
-                           2: "sketch_i8_kernel" if K_COMPONENTS + OVERSAMPLE <= 32 else "sketch_tc_kernel<64>"}[eng],
-                "ms_per_launch": t_kern * 1e3, "launches_per_step": passes,
-                "kernel_share_of_step": (sk_kernel_ms * 1e-3 / args.steps) / t_step,
-                "pass_level": {"ms_per_pass": t_pass * 1e3, "achieved": bytes_per_pass / t_pass / 1e9 if t_pass > 0 else 0.0,
-                               "frac": (bytes_per_pass / t_pass / 1e9) / pk["hbm_gbs"] if t_pass > 0 else 0.0,
+    # (one launch per pass and resident segment); the pass-level figure also contains operand prep and the split-K reduce.
+    t_kern = (r["sk_kernel_ms"] / max(r["sk_n"], 1)) * 1e-3
+    t_pass = (r["sk_ms"] / max(r["sk_n"], 1)) * 1e-3
+    bpl = bytes_per_pass * passes * args.steps / max(r["sk_n"], 1)      # bytes per launch (== bytes_per_pass when unsegmented)
+    ach_gbs = bpl / t_kern / 1e9 if t_kern > 0 else 0.0
+    flops_per_launch = 2.0 * 4.0 * bpl * (K_COMPONENTS + OVERSAMPLE)
+    ach_tf = flops_per_launch / t_kern / 1e12 if t_kern > 0 else 0.0
+    l = K_COMPONENTS + OVERSAMPLE
+    eng = args.engine if args.engine is not None else int(os.environ.get("GPCA_SKETCH_ENGINE", "2"))
+    kernel_name = {0: "sketch_simt_kernel", 1: "sketch_tc_kernel", 2: "sketch_i8_kernel" if l <= 32 else "sketch_tc_kernel<64>"}[eng]
+    roofline = {"bound": "hbm", "achieved": ach_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach_gbs / pk["hbm_gbs"],
+                "traffic": None, "traffic_note": "see profiles/ (ncu --set full capture of the same kernel at this shape)",
+                "peak_source": pk_src, "kernel": kernel_name, "ms_per_launch": t_kern * 1e3,
+                "launches_per_step": r["sk_n"] / args.steps, "bytes_per_launch": bpl,
+                "kernel_share_of_step": (r["sk_kernel_ms"] * 1e-3 / args.steps) / t_step,
+                "pass_level": {"ms_per_pass": t_pass * 1e3, "achieved": bpl / t_pass / 1e9 if t_pass > 0 else 0.0,
+                               "frac": (bpl / t_pass / 1e9) / pk["hbm_gbs"] if t_pass > 0 else 0.0,
                                "note": "operand prep + sketch kernel + split-K reduce"},
                 "tensor_achieved_tflops": ach_tf, "tensor_frac_of_sustained_bf16": ach_tf / pk["bf16_tflops_sustained"]}
     line = {
         "metric": "genotype_GBps_per_sketch_pass", "value": value, "unit": "GB/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": {0: "f32", 1: "f16 x f16 -> f32 (tcgen05)", 2: "u8 x s8 -> s32 (tcgen05 kind::i8, exact)"}[ctx_engine(ctx, args)],
+        "scaling": "strong", "vs_baseline": None,
+        "dtype": {0: "f32", 1: "f16 x f16 -> f32 (tcgen05)", 2: "u8 x s8 -> s32 (tcgen05 kind::i8, exact)"}[eng],
         "data": "synthetic",
-        "config": {"workload": f"{'1000G-shape ' if (n, m) == (2504, 10_000_000) else ''}rfit k={K_COMPONENTS} oversample={OVERSAMPLE} q={POWER_ITERS}: "
-                               f"{n} samples x {m} SNPs per GPU ({d_kept} after MAF 0.01), 2-bit packed, SNP-sharded",
-                   "passes_per_step": passes, "bytes_per_pass": bytes_per_pass,
+        "config": {"workload": f"{'BASELINE config 4: ' if (n, m_total) == (C4_SAMPLES, C4_SNPS) else ''}rfit k={K_COMPONENTS} "
+                               f"oversample={OVERSAMPLE} q={POWER_ITERS} on {n} samples x {m_total} SNPs ({int(d_total)} after MAF 0.01), "
+                               f"2-bit packed, SNPs / {nb_total} LD blocks split over {world} GPU(s)",
+                   "passes_per_step": passes, "bytes_per_pass": job_bytes_per_pass,
                    "l2": "inputs larger than L2 (packed shard >> 126 MB)" if bytes_per_pass > 2e8 else "input fits L2",
-                   "pca_wall_s": t_step, "host_wall_s_per_step": wall / args.steps},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-        "eigenvalues_head": [float(x) for x in ev[:3]],
+                   "pca_wall_s": t_step, "host_wall_s_per_step": r["wall_per_step"], "host_threads_per_rank": host_threads,
+                   "exchange": "ncclAllReduce issued by the library (gpca_comm_init)" if world > 1 else "none (one shard)",
+                   "collectives_per_step": r["collectives_per_step"],
+                   "resident_snp_rows_frac_rank0": resident_rfit / max(d_kept, 1),
+                   "payload_setup_s": {"pinned_alloc": host.alloc_s, "synthesise": host.fill_s, "first_ingest": t_first_ingest}},
+        "clocks": r["clocks"], "e2e": e2e, "gpu_launches": int(r["launches"]), "roofline": roofline,
+        "eigenvalues_head": [float(x) for x in r["eigenvalues"][:3]],
     }
-    if ukb is not None:
-        line["ukb_shard"] = ukb
+    if es is not None:
+        line["eigensnp"] = es
+    if c3 is not None:
+        line["c3"] = c3
+        if isinstance(c3, dict) and "parity_at_scale" in c3:
+            line["parity_at_scale"] = c3["parity_at_scale"]
     if not args.no_cpu:
+        lim = blas_threads(cores)
         dt, cp, cb = cpu_rfit_sample(n, args.cpu_snps)
-        line["cpu_baseline"] = {"value": cp * cb / dt / 1e9, "unit": "GB/s", "cores": os.cpu_count() or 1,
-                                "kind": "port", "sample": f"{n} samples x {args.cpu_snps} SNPs, one rfit "
+        line["cpu_baseline"] = {"value": cp * cb / dt / 1e9, "unit": "GB/s", "cores": cores, "kind": "port",
+                                "blas_threads": cores if lim is not None else os.environ.get("OMP_NUM_THREADS", "default"),
+                                "sample": f"{n} samples x {args.cpu_snps} SNPs, one rfit "
                                 f"(numpy/OpenBLAS f64 restatement of the reference's CPU path), {dt:.1f} s"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
-
-
-# DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum, bytes per launch) of sketch_i8_kernel at config 3 from the
-# committed ncu capture (profiles/r1_ncu_full_sketch_i8_kernel_c3_final2.csv): sample side 7.378 + 0.040 GB, snp side
-# 6.480 + 1.268 GB; one rfit runs 4 sample-side and 3 snp-side launches.  Only valid for the default workload.
-TRAFFIC_NCU = {2: (4 * 7.418e9 + 3 * 7.748e9) / 7}
-
-
-def ukb_shard_supplement(torch, gp, dev, pk, rank=0, world=1, dist=None):
-    """Supplementary measurement at the shape the headline metric is quoted on: the per-GPU shard of BASELINE
-    config 4 on 8 GPUs (500,000 samples x 87,500 SNPs).  The full config needs >= 2 GPUs in this round's
-    two-orientation layout, so on one GPU its shard is measured: sketch-pass roofline fraction + EigenSNP wall time."""
-    n, m, nblocks = 500_000, 87_500, 212
-    payload = synth_bed_device(torch, n, m, rank * m, dev)
-    torch.cuda.synchronize()
-    ctx = gp.Context(dev.index or 0)
-    if world > 1:      # every rank holds one shard of SNPs / LD blocks of the same 500k samples
-        ctx.set_allreduce(make_allreduce_hook(torch, dist, dev))
-        ctx.set_shard(rank * m, world * m)
-    ctx.load_bed_device(payload.data_ptr(), n, m)
-    keep, mean, sd, _ = ctx.snp_qc(gp.QcConfig(0.98, 0.01, 1.0))     # HWE off: pooled structured populations fail it
-    d = ctx.set_pca_snps_mask(keep, mean, sd)
-    del payload
-    torch.cuda.empty_cache()
-    bps = (n + 3) // 4
-    # caller-owned result buffers, allocated and touched once (see Context.rfit)
-    rfit_out = (np.ones((n, K_COMPONENTS), dtype=np.float64), np.ones(K_COMPONENTS, dtype=np.float64), None)
-    for _ in range(2):
-        ctx.rfit(K_COMPONENTS, OVERSAMPLE, power_iters=POWER_ITERS, seed=RFIT_SEED, want_loadings=False, out=rfit_out)
-    ctx.sketch_stats(reset=True)
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    reps = 3
-    for _ in range(reps):
-        ctx.rfit(K_COMPONENTS, OVERSAMPLE, power_iters=POWER_ITERS, seed=RFIT_SEED, want_loadings=False, out=rfit_out)
-    t_rfit = (time.perf_counter() - t0) / reps
-    sk_ms, _, sk_n = ctx.sketch_stats(reset=True)
-    t_kern = ctx.last_kernel_ms / max(sk_n, 1) * 1e-3
-    edges = np.linspace(0, d, nblocks + 1).astype(np.int64)
-    blocks = [np.arange(edges[i], edges[i + 1], dtype=np.uint64) for i in range(nblocks)]
-    cfg = gp.EigenSnpConfig(target_num_global_pcs=K_COMPONENTS)
-    es_out = (np.ones((n, K_COMPONENTS), dtype=np.float32), np.ones(K_COMPONENTS, dtype=np.float64),
-              np.ones((d, K_COMPONENTS), dtype=np.float32))
-    ctx.eigensnp(blocks, cfg, out=es_out)
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    sc, ev, load = ctx.eigensnp(blocks, cfg, out=es_out)
-    t_es = time.perf_counter() - t0
-    if world > 1:      # max over ranks
-        tt = torch.tensor([t_es, t_rfit], device=dev, dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_es, t_rfit = float(tt[0].item()), float(tt[1].item())
-    ctx.close()
-    gbs = d * bps / t_kern / 1e9 if t_kern > 0 else 0.0
-    shape = (f"{n} samples x {m} SNPs on one GPU = the per-GPU shard of BASELINE config 4 (500k x 700k) on 8 GPUs"
-             if world == 1 else
-             f"{n} samples x {world * m} SNPs ({world * nblocks} LD blocks) sharded over {world} GPUs"
-             + (" = BASELINE config 4" if world == 8 else ""))
-    return {"shape": shape, "n_gpus": world,
-            "sketch_kernel_ms_per_launch": t_kern * 1e3, "sketch_kernel_GBps": gbs,
-            "sketch_kernel_frac_of_hbm": gbs / pk["hbm_gbs"], "sketch_pass_ms": sk_ms / max(sk_n, 1),
-            "rfit_k20_wall_s": t_rfit, "eigensnp_k20_212_blocks_wall_s": t_es,
-            "eigensnp_eigenvalues_head": [float(x) for x in ev[:3]]}
-
-
-def ctx_engine(ctx, args):
-    return args.engine if args.engine is not None else int(os.environ.get("GPCA_SKETCH_ENGINE", "2"))
 
 
 def main():

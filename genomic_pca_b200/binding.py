@@ -88,10 +88,25 @@ _sig("gpca_set_batch_blocks", C.c_int, C.c_void_p, C.c_int)
 _sig("gpca_ingest_bed_file", C.c_int, C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p,
      C.c_double, _u8p, _f32p, _f32p, _u8p, _u64p)
 _sig("gpca_synth_bed_device", C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32,
-     C.c_double, C.c_double)
+     C.c_double, C.c_double, C.c_double)
 _sig("gpca_sketch_stats", C.c_int, C.c_void_p, _f64p, _f64p, _u64p, C.c_int)
 _sig("gpca_sketch_kernel_ms", C.c_double, C.c_void_p)
 _sig("gpca_set_allreduce", C.c_int, C.c_void_p, ALLREDUCE_FN, C.c_void_p)
+_sig("gpca_set_host_threads", C.c_int, C.c_void_p, C.c_uint32)
+_sig("gpca_set_sketch_timing", C.c_int, C.c_void_p, C.c_int)
+_sig("gpca_set_memory_reserve", C.c_int, C.c_void_p, C.c_uint64)
+_sig("gpca_resident_snp_rows", C.c_uint64, C.c_void_p)
+_sig("gpca_eigensnp_workspace_bytes", C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p)
+_sig("gpca_set_ingest_mask", C.c_int, C.c_void_p, _u8p, C.c_uint64)
+_sig("gpca_synth_bed_host", C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32,
+     C.c_double, C.c_double, C.c_double)
+_sig("gpca_host_alloc", C.c_void_p, C.c_void_p, C.c_uint64)
+_sig("gpca_host_free", None, C.c_void_p, C.c_void_p, C.c_uint64)
+_sig("gpca_comm_unique_id", C.c_int, _u8p)
+_sig("gpca_comm_init", C.c_int, C.c_void_p, _u8p, C.c_int, C.c_int)
+_sig("gpca_comm_finalize", C.c_int, C.c_void_p)
+_sig("gpca_comm_world", C.c_int, C.c_void_p)
+_sig("gpca_collective_count", C.c_uint64, C.c_void_p)
 _sig("gpca_set_shard", C.c_int, C.c_void_p, C.c_uint64, C.c_uint64)
 _sig("gpca_load_bed", C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, _i64p, C.c_uint64)
 _sig("gpca_load_bed_device", C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64)
@@ -119,6 +134,23 @@ _sig("gpca_eigensnp", C.c_int, C.c_void_p, C.POINTER(EigenSnpConfig), _u64p, C.c
      _u32p)
 _sig("gpca_map_snps_to_ld_blocks", C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int32), C.c_uint64,
      C.POINTER(C.c_char_p), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_uint64, _i64p, _i64p, _u64p, _u64p, _u64p)
+
+
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id() -> bytes:
+    """ncclGetUniqueId through the library (one rank calls it, the host hands the bytes to the others)."""
+    buf = (C.c_uint8 * COMM_ID_BYTES)()
+    rc = lib.gpca_comm_unique_id(buf)
+    if rc != 0:
+        raise GpcaError(rc, "gpca_comm_unique_id: NCCL not available")
+    return bytes(buf)
+
+
+def eigensnp_workspace_bytes(n_samples: int, n_pca_snps: int, n_blocks: int, cfg=None) -> int:
+    return int(lib.gpca_eigensnp_workspace_bytes(int(n_samples), int(n_pca_snps), int(n_blocks),
+                                                 None if cfg is None else C.addressof(cfg)))
 
 
 def _ptr(a, t):
@@ -182,10 +214,64 @@ class Context:
         self._chk(lib.gpca_set_sketch_engine(self._h, engine))
 
     def synth_bed_device(self, dev_ptr: int, n_samples: int, n_snps: int, snp_offset: int = 0, seed: int = 20260101,
-                         n_pops: int = 22, fst: float = 0.1, missing_rate: float = 0.0):
+                         n_pops: int = 22, fst: float = 0.1, missing_rate: float = 0.0, fst_grade: float = 0.0):
         """Benchmark input: structured synthetic genotypes written on the device in .bed layout (see gpca.h)."""
         self._chk(lib.gpca_synth_bed_device(self._h, dev_ptr, n_samples, n_snps, snp_offset, seed, n_pops, fst,
-                                            missing_rate))
+                                            missing_rate, fst_grade))
+
+    def synth_bed_host(self, host_ptr: int, n_samples: int, n_snps: int, snp_offset: int = 0, seed: int = 20260101,
+                       n_pops: int = 22, fst: float = 0.1, missing_rate: float = 0.0, fst_grade: float = 0.0):
+        """The same rows as synth_bed_device, written to host memory (stands in for a .bed file read by the host)."""
+        self._chk(lib.gpca_synth_bed_host(self._h, host_ptr, n_samples, n_snps, snp_offset, seed, n_pops, fst,
+                                          missing_rate, fst_grade))
+
+    def set_host_threads(self, n: int):
+        self._chk(lib.gpca_set_host_threads(self._h, int(n)))
+
+    def set_sketch_timing(self, on: bool):
+        self._chk(lib.gpca_set_sketch_timing(self._h, 1 if on else 0))
+
+    def set_memory_reserve(self, nbytes: int):
+        self._chk(lib.gpca_set_memory_reserve(self._h, int(nbytes)))
+
+    @property
+    def resident_snp_rows(self) -> int:
+        """Rows of the SNP-major matrix that are resident (== num_pca_snps unless the two orientations did not fit)."""
+        return int(lib.gpca_resident_snp_rows(self._h))
+
+    def host_alloc(self, nbytes: int) -> int:
+        """Pinned host buffer (huge pages, registered with CUDA); returns its address.  Free with host_free."""
+        p = lib.gpca_host_alloc(self._h, int(nbytes))
+        if not p:
+            raise GpcaError(-5, (lib.gpca_last_error(self._h) or b"").decode())
+        return int(p)
+
+    def host_free(self, ptr: int, nbytes: int):
+        lib.gpca_host_free(self._h, C.c_void_p(ptr), int(nbytes))
+
+    def set_ingest_mask(self, mask):
+        """Pre-selection of loaded rows for the next ingest (None clears it)."""
+        if mask is None:
+            self._chk(lib.gpca_set_ingest_mask(self._h, None, 0))
+            return
+        mask = np.ascontiguousarray(mask, dtype=np.uint8)
+        self._chk(lib.gpca_set_ingest_mask(self._h, _ptr(mask, _u8p), mask.size))
+
+    # -- the library's own exchange (NCCL)
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        buf = (C.c_uint8 * COMM_ID_BYTES).from_buffer_copy(unique_id)
+        self._chk(lib.gpca_comm_init(self._h, buf, int(rank), int(world)))
+
+    def comm_finalize(self):
+        self._chk(lib.gpca_comm_finalize(self._h))
+
+    @property
+    def comm_world(self) -> int:
+        return int(lib.gpca_comm_world(self._h))
+
+    @property
+    def collective_count(self) -> int:
+        return int(lib.gpca_collective_count(self._h))
 
     def set_batch_blocks(self, on: bool):
         self._chk(lib.gpca_set_batch_blocks(self._h, 1 if on else 0))

@@ -3,22 +3,24 @@
 #include <algorithm>
 #include <chrono>
 #include <fcntl.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
 #include <cmath>
 #include <cstring>
 #include <atomic>
+#include <functional>
 #include <new>
 
 #include "host_qc.h"
 #include "kernels.cuh"
 #include "sketch_tc.cuh"
+#include "driver_util.cuh"
 #include "parallel_for.h"
 
 #define CHECK_CTX(c) \
   if (!(c)) return GPCA_ERR_INVALID;
 
-void gpca_destroy_cublas(void* h);   // eigensnp.cu
 
 static int fail(gpca_ctx* c, int code, const std::string& msg) {
   c->set_error(msg);
@@ -48,6 +50,8 @@ extern "C" int gpca_init(gpca_ctx** out, int device) {
   if (eng) c->engine = atoi(eng);
   const char* bb = getenv("GPCA_BATCH_BLOCKS");
   if (bb) c->batch_blocks = atoi(bb) != 0;
+  if (const char* ht = getenv("GPCA_HOST_THREADS")) c->host_threads = (unsigned)std::max(0, atoi(ht));
+  if (const char* st = getenv("GPCA_SKETCH_TIMING")) c->sk_timing = atoi(st) != 0;
   *out = c;
   return GPCA_OK;
 }
@@ -72,9 +76,9 @@ extern "C" void gpca_destroy(gpca_ctx* c) {
     if (c->h_dl[i]) cudaFreeHost(c->h_dl[i]);
     if (c->ev_dl[i]) cudaEventDestroy(c->ev_dl[i]);
   }
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < gpca_ctx::INGEST_STAGES; ++i)
     if (c->h_rd[i]) cudaFreeHost(c->h_rd[i]);
-  gpca_destroy_cublas(c->cublas);
+  gpca_comm_destroy(c);
   delete c;
 }
 
@@ -94,6 +98,33 @@ extern "C" int gpca_set_batch_blocks(gpca_ctx* c, int on) {
   c->batch_blocks = on ? 1 : 0;
   return GPCA_OK;
 }
+extern "C" int gpca_set_host_threads(gpca_ctx* c, uint32_t n) {
+  CHECK_CTX(c);
+  if (c->host_threads != n) c->pool.reset();      // re-created at the new size on next use
+  c->host_threads = n;
+  return GPCA_OK;
+}
+extern "C" int gpca_set_sketch_timing(gpca_ctx* c, int on) {
+  CHECK_CTX(c);
+  c->sk_timing = on != 0;
+  return GPCA_OK;
+}
+extern "C" int gpca_set_memory_reserve(gpca_ctx* c, uint64_t bytes) {
+  CHECK_CTX(c);
+  c->mem_reserve = bytes;
+  return GPCA_OK;
+}
+extern "C" int gpca_set_ingest_mask(gpca_ctx* c, const uint8_t* mask, uint64_t n_snps) {
+  CHECK_CTX(c);
+  if (!mask || n_snps == 0) {
+    c->ingest_mask.clear();
+    return GPCA_OK;
+  }
+  c->ingest_mask.assign(mask, mask + n_snps);
+  return GPCA_OK;
+}
+extern "C" uint64_t gpca_collective_count(const gpca_ctx* c) { return c ? c->collectives : 0; }
+extern "C" uint64_t gpca_resident_snp_rows(const gpca_ctx* c) { return c ? (c->gs_win_rows ? c->gs_res_rows : c->D) : 0; }
 extern "C" int gpca_set_allreduce(gpca_ctx* c, gpca_allreduce_fn fn, void* user) {
   CHECK_CTX(c);
   c->allreduce = fn;
@@ -122,6 +153,8 @@ static void reset_loaded(gpca_ctx* c) {
   c->Gs = PackedMat();
   c->Gt = PackedMat();   // (the stores are kept: DevBuf::alloc reuses them when the next data set fits)
   c->any_missing = false;
+  c->gs_res_rows = 0;
+  c->gs_win_rows = 0;
   c->es_store.release();
   c->et_store.release();
   c->ets_store.release();
@@ -222,20 +255,32 @@ extern "C" int gpca_load_u8_variant_major(gpca_ctx* c, const uint8_t* host_dosag
   return GPCA_OK;
 }
 
+static int alloc_mapped(gpca_ctx* c, void** host, void** dev, size_t bytes) {
+  GPCA_CUDA_TRY(c, cudaHostAlloc(host, bytes, cudaHostAllocMapped));
+  GPCA_CUDA_TRY(c, cudaHostGetDevicePointer(dev, *host, 0));
+  return GPCA_OK;
+}
+
+static int ensure_count_buffer(gpca_ctx* c, uint64_t M) {
+  if (c->h_cnt_cap >= M && c->h_cnt) return GPCA_OK;
+  if (c->h_cnt) cudaFreeHost(c->h_cnt);
+  c->h_cnt = nullptr;
+  c->h_cnt_dev = nullptr;
+  c->h_cnt_cap = 0;
+  GPCA_TRY(alloc_mapped(c, (void**)&c->h_cnt, (void**)&c->h_cnt_dev, std::max<uint64_t>(M, 1) * sizeof(uint4)));
+  c->h_cnt_cap = M;
+  return GPCA_OK;
+}
+
 // ---- statistics ----------------------------------------------------------------------------
 static int ensure_counts(gpca_ctx* c) {
   if (c->have_counts) return GPCA_OK;
+  GPCA_HOST_POOL(c);
   if (!c->raw.p) return fail(c, GPCA_ERR_INVALID, "no genotype payload loaded (or it was released)");
   const uint64_t M = c->M;
   GPCA_CUDA_TRY(c, c->d_cnt.alloc(std::max<uint64_t>(M, 1)));
   GPCA_TRY(launch_bed_counts(c, c->raw.p, c->raw_pitch, M, c->d_cnt.p));
-  if (c->h_cnt_cap < M) {   // pinned landing buffer for the 16 B/SNP count records, kept across calls
-    if (c->h_cnt) cudaFreeHost(c->h_cnt);
-    c->h_cnt = nullptr;
-    c->h_cnt_cap = 0;
-    GPCA_CUDA_TRY(c, cudaMallocHost((void**)&c->h_cnt, std::max<uint64_t>(M, 1) * sizeof(uint4)));
-    c->h_cnt_cap = M;
-  }
+  GPCA_TRY(ensure_count_buffer(c, M));   // pinned landing buffer for the 16 B/SNP count records, kept across calls
   GPCA_CUDA_TRY(c, cudaMemcpyAsync(c->h_cnt, c->d_cnt.p, M * sizeof(uint4), cudaMemcpyDeviceToHost, c->stream));
   GPCA_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   const uint32_t pad = (uint32_t)(c->raw_pitch * 4 - c->N);  // pad fields were written as 01
@@ -273,6 +318,7 @@ extern "C" int gpca_snp_qc(gpca_ctx* c, const gpca_qc_cfg* cfg, uint8_t* keep, f
                            uint8_t* fail_code) {
   CHECK_CTX(c);
   if (!cfg || !keep) return fail(c, GPCA_ERR_INVALID, "cfg/keep null");
+  GPCA_HOST_POOL(c);
   GPCA_TRY(ensure_counts(c));
   host_snp_qc(c->N, c->M, c->h_counts.data(), *cfg, keep, mean, sd, fail_code);
   return GPCA_OK;
@@ -281,19 +327,21 @@ extern "C" int gpca_snp_qc(gpca_ctx* c, const gpca_qc_cfg* cfg, uint8_t* keep, f
 extern "C" int gpca_vcf_maf_filter(gpca_ctx* c, double maf_threshold, uint8_t* keep, float* mean, float* sd) {
   CHECK_CTX(c);
   if (!keep) return fail(c, GPCA_ERR_INVALID, "keep null");
+  GPCA_HOST_POOL(c);
   GPCA_TRY(ensure_counts(c));
   host_vcf_maf(c->N, c->M, c->h_counts.data(), maf_threshold, keep, mean, sd);
   return GPCA_OK;
 }
 
 // ---- PCA SNP set -----------------------------------------------------------------------------
-static int build_pca_set(gpca_ctx* c, uint64_t D) {
-  // c->pca_idx, c->h_mean, c->h_sd are filled; derive the device-side vectors and the resident copies
+// c->pca_idx, c->h_mean, c->h_sd hold the new set: derive 1/sd, mean/sd, the missing-call flag and the device vectors
+static int derive_pca_vectors(gpca_ctx* c, uint64_t D) {
+  GPCA_HOST_POOL(c);
   const uint64_t* idx = c->pca_idx.data();
   const float* mean = c->h_mean.data();
   const float* sd = c->h_sd.data();
-  c->h_inv.resize(D);
-  c->h_muinv.resize(D);
+  c->h_inv.resize(std::max<size_t>(c->h_inv.size(), D));
+  c->h_muinv.resize(std::max<size_t>(c->h_muinv.size(), D));
   float* inv = c->h_inv.data();
   float* muinv = c->h_muinv.data();
   const uint32_t* hc = c->h_counts.data();
@@ -327,7 +375,6 @@ static int build_pca_set(gpca_ctx* c, uint64_t D) {
     std::memcpy(&c->inv_sd_max, &bits, 4);
   }
   c->any_missing = nmiss_total.load() > 0;
-  c->D = D;
   GPCA_CUDA_TRY(c, c->d_mean.alloc(D));
   GPCA_CUDA_TRY(c, c->d_sd.alloc(D));
   GPCA_CUDA_TRY(c, c->d_inv_sd.alloc(D));
@@ -338,17 +385,27 @@ static int build_pca_set(gpca_ctx* c, uint64_t D) {
   GPCA_CUDA_TRY(c, cudaMemcpyAsync(c->d_sd.p, sd, D * 4, cudaMemcpyHostToDevice, c->stream));
   GPCA_CUDA_TRY(c, cudaMemcpyAsync(c->d_inv_sd.p, inv, D * 4, cudaMemcpyHostToDevice, c->stream));
   GPCA_CUDA_TRY(c, cudaMemcpyAsync(c->d_mu_inv_sd.p, muinv, D * 4, cudaMemcpyHostToDevice, c->stream));
+  return GPCA_OK;
+}
+
+static int build_pca_set(gpca_ctx* c, uint64_t D) {
+  // c->pca_idx, c->h_mean, c->h_sd are filled; derive the device-side vectors and the resident copies
+  GPCA_TRY(derive_pca_vectors(c, D));
+  c->D = D;
   c->Gs.rows = D;
   c->Gs.cols = c->N;
   c->Gs.pitch = round_up((c->N + 3) / 4, 128);
   c->Gt.rows = c->N;
   c->Gt.cols = D;
   c->Gt.pitch = round_up((D + 3) / 4, 128);
+  c->gs_res_rows = D;
+  c->gs_win_rows = 0;
   GPCA_CUDA_TRY(c, c->gs_store.alloc(c->Gs.pitch * D));
   c->Gs.p = c->gs_store.p;
   GPCA_TRY(launch_build_gs(c, c->raw.p, c->raw_pitch, c->d_idx.p, c->Gs));
   // the PLINK-coded staging copy is only needed again for a different SNP selection; under memory pressure
-  // (three copies would not fit comfortably) it is released before the transposed copy is allocated
+  // (three copies would not fit comfortably) it is released before the transposed copy is allocated -- a later
+  // gpca_set_pca_snps then narrows the resident set instead (reselect_resident)
   size_t free_b = 0, total_b = 0;
   cudaMemGetInfo(&free_b, &total_b);
   if (c->gt_store.n < c->Gt.pitch * c->N && free_b < c->Gt.pitch * c->N + (8ull << 30)) {
@@ -362,11 +419,74 @@ static int build_pca_set(gpca_ctx* c, uint64_t D) {
   return GPCA_OK;
 }
 
+// A new PCA SNP set when no staging copy of the payload exists (after the streaming ingest, or when build_pca_set
+// released it): the set can only be narrowed.  The kept rows of the SNP-major matrix move up in place (chunk by chunk
+// through a temporary: a row's source is never above its destination's chunk), the vectors are re-derived and the
+// sample-major matrix is transposed again.  This is the call the EigenSNP workflow makes after mapping the QC'd SNPs
+// to LD blocks (src/prepare.rs:1424-1563 drops SNPs outside every block).
+static int reselect_resident(gpca_ctx* c, const uint64_t* snp_idx, uint64_t Dn, const float* mean, const float* sd) {
+  if (c->D == 0 || !c->Gs.p) return fail(c, GPCA_ERR_INVALID, "no genotype payload loaded");
+  if (c->gs_win_rows)
+    return fail(c, GPCA_ERR_INVALID,
+                "the SNP-major matrix is only partly resident: pass the SNP selection to the ingest (gpca_set_ingest_mask) "
+                "instead of narrowing it afterwards");
+  const uint64_t Do = c->D;
+  std::vector<int64_t> pos(Dn);
+  {
+    uint64_t j = 0;
+    for (uint64_t i = 0; i < Dn; ++i) {
+      while (j < Do && c->pca_idx[j] < snp_idx[i]) ++j;
+      if (j >= Do || c->pca_idx[j] != snp_idx[i])
+        return fail(c, GPCA_ERR_INVALID,
+                    "after a streaming ingest gpca_set_pca_snps can only narrow the resident SNP set (SNP not resident)");
+      pos[i] = (int64_t)j++;
+    }
+  }
+  const size_t pitch = c->Gs.pitch;
+  const uint64_t chunk_rows = std::max<uint64_t>(512, (256ull << 20) / pitch);
+  DevBuf<uint8_t> tmp;
+  DevBuf<int64_t> d_pos;
+  GPCA_CUDA_TRY(c, tmp.alloc(std::min<uint64_t>(chunk_rows, Dn) * pitch));
+  GPCA_CUDA_TRY(c, d_pos.alloc(Dn));
+  GPCA_CUDA_TRY(c, cudaMemcpyAsync(d_pos.p, pos.data(), Dn * 8, cudaMemcpyHostToDevice, c->stream));
+  for (uint64_t n0 = 0; n0 < Dn; n0 += chunk_rows) {
+    const uint64_t nr = std::min<uint64_t>(chunk_rows, Dn - n0);
+    PackedMat dst = c->Gs;
+    dst.p = tmp.p;
+    dst.rows = nr;
+    GPCA_TRY(launch_gather_rows(c, c->Gs, d_pos.p + n0, dst));
+    GPCA_CUDA_TRY(c, cudaMemcpyAsync(c->Gs.p + n0 * pitch, tmp.p, nr * pitch, cudaMemcpyDeviceToDevice, c->stream));
+  }
+  const uint64_t old_written = std::min<uint64_t>(c->Gt.pitch, round_up(Do, 512) / 4);
+  c->pca_idx.assign(snp_idx, snp_idx + Dn);
+  c->h_mean.assign(mean, mean + Dn);
+  c->h_sd.assign(sd, sd + Dn);
+  GPCA_TRY(derive_pca_vectors(c, Dn));
+  c->D = Dn;
+  c->Gs.rows = Dn;
+  c->Gt.cols = Dn;
+  c->gs_res_rows = Dn;
+  GPCA_TRY(launch_transpose(c, c->Gs, c->Gt));
+  const uint64_t new_written = std::min<uint64_t>(c->Gt.pitch, round_up(Dn, 512) / 4);
+  if (new_written < old_written)
+    GPCA_CUDA_TRY(c, cudaMemset2DAsync(c->Gt.p + new_written, c->Gt.pitch, 0, old_written - new_written, c->N, c->stream));
+  GPCA_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  // the EigenSNP copies cached in the context describe the old set
+  c->es_store.release();
+  c->et_store.release();
+  c->ets_store.release();
+  c->ess_store.release();
+  c->es_cn.release();
+  c->es_pool.release();
+  return GPCA_OK;
+}
+
 extern "C" int gpca_set_pca_snps(gpca_ctx* c, const uint64_t* snp_idx, uint64_t D, const float* mean,
                                  const float* sd) {
   CHECK_CTX(c);
   GPCA_CUDA_TRY(c, cudaSetDevice(c->device));
-  if (!c->raw.p) return fail(c, GPCA_ERR_INVALID, "no genotype payload loaded (or it was released)");
+  GPCA_HOST_POOL(c);
+  if (!c->raw.p && c->D == 0) return fail(c, GPCA_ERR_INVALID, "no genotype payload loaded");
   if (D == 0) return fail(c, GPCA_ERR_INVALID, "No SNPs passed all QC filters.");  // prepare.rs:1020
   if (!snp_idx || !mean || !sd) return fail(c, GPCA_ERR_INVALID, "null argument");
   std::atomic<int> bad{0};
@@ -376,6 +496,7 @@ extern "C" int gpca_set_pca_snps(gpca_ctx* c, const uint64_t* snp_idx, uint64_t 
       if (snp_idx[i] >= M || (i && snp_idx[i] <= snp_idx[i - 1])) bad.store(1);
   });
   if (bad.load()) return fail(c, GPCA_ERR_INVALID, "snp_idx must be strictly increasing and < num_snps");
+  if (!c->raw.p) return reselect_resident(c, snp_idx, D, mean, sd);
   GPCA_TRY(ensure_counts(c));
   c->pca_idx.assign(snp_idx, snp_idx + D);
   c->h_mean.assign(mean, mean + D);
@@ -387,7 +508,8 @@ extern "C" int gpca_set_pca_snps_mask(gpca_ctx* c, const uint8_t* keep, const fl
                                       uint64_t* n_pca_out) {
   CHECK_CTX(c);
   GPCA_CUDA_TRY(c, cudaSetDevice(c->device));
-  if (!c->raw.p) return fail(c, GPCA_ERR_INVALID, "no genotype payload loaded (or it was released)");
+  GPCA_HOST_POOL(c);
+  if (!c->raw.p && c->D == 0) return fail(c, GPCA_ERR_INVALID, "no genotype payload loaded");
   if (!keep || !mean_all || !sd_all) return fail(c, GPCA_ERR_INVALID, "null argument");
   GPCA_TRY(ensure_counts(c));
   const uint64_t M = c->M;
@@ -407,12 +529,21 @@ extern "C" int gpca_set_pca_snps_mask(gpca_ctx* c, const uint8_t* keep, const fl
   const uint64_t D = cnt[nch];
   if (n_pca_out) *n_pca_out = D;
   if (D == 0) return fail(c, GPCA_ERR_INVALID, "No SNPs passed all QC filters.");  // prepare.rs:1020
-  c->pca_idx.resize(D);
-  c->h_mean.resize(D);
-  c->h_sd.resize(D);
-  uint64_t* pi = c->pca_idx.data();
-  float* pm = c->h_mean.data();
-  float* ps = c->h_sd.data();
+  std::vector<uint64_t> sel_idx;
+  std::vector<float> sel_mean, sel_sd;
+  const bool narrow = !c->raw.p;      // no staging copy: narrow the resident set (reselect_resident)
+  if (narrow) {
+    sel_idx.resize(D);
+    sel_mean.resize(D);
+    sel_sd.resize(D);
+  } else {
+    c->pca_idx.resize(D);
+    c->h_mean.resize(D);
+    c->h_sd.resize(D);
+  }
+  uint64_t* pi = narrow ? sel_idx.data() : c->pca_idx.data();
+  float* pm = narrow ? sel_mean.data() : c->h_mean.data();
+  float* ps = narrow ? sel_sd.data() : c->h_sd.data();
   parallel_for(nch, [&, keep, M, mean_all, sd_all, pi, pm, ps](uint64_t lo, uint64_t hi) {
     for (uint64_t q = lo; q < hi; ++q) {
       uint64_t o = cnt[q];
@@ -426,22 +557,59 @@ extern "C" int gpca_set_pca_snps_mask(gpca_ctx* c, const uint8_t* keep, const fl
         }
     }
   }, 1);
+  if (narrow) return reselect_resident(c, pi, D, pm, ps);
   return build_pca_set(c, D);
 }
 
 // ---- one-call pipelined ingest ------------------------------------------------------------------------------------
-// gpca_load_bed + (gpca_snp_qc | gpca_vcf_maf_filter) + gpca_set_pca_snps_mask as ONE streaming pass: while chunk q
-// crosses PCIe, chunk q-1 is repitched and counted on the device, its 16-byte count records come back, the QC ladder
-// runs on host threads, and the rows that pass are recoded into the resident SNP-major matrix.  The host -> device copy
-// of the payload is the critical path; everything else hides behind it.  Replaces, for the data-preparation stage,
-// MicroarrayDataPreparer::prepare_data_for_eigen_snp_pca (src/prepare.rs:995-1098) / the VCF read + MAF filter
-// (src/vcf.rs:227-266, src/main.rs:176-212).
+// gpca_load_bed + (gpca_snp_qc | gpca_vcf_maf_filter) + gpca_set_pca_snps_mask as ONE streaming pass.  The host ->
+// device copy of the payload is the critical path and runs back to back on its own stream, up to INGEST_LAG chunks
+// ahead of the host; behind it, per chunk:
+//   device: counts straight from the staged rows (file pitch, unaligned) -> 16-byte records written into MAPPED pinned
+//           host memory by the kernel (no copy in the transfer queue)
+//   host:   count records -> QC ladder on the pool threads -> compaction of the kept SNPs' index / mean / sd / 1/sd /
+//           mean/sd into mapped pinned memory
+//   device: a small kernel fetches those vectors, the kept rows are recoded from the staging buffer into the SNP-major
+//           resident matrix, and every complete 512-row tile of it is transposed into the sample-major one.
+// No full-size staging copy exists: at most three copies of a CHUNK (stage, optional sample-gathered copy) beside the
+// two resident orientations.  When even those two do not fit (mem_reserve is left free for the drivers), the SNP-major
+// matrix keeps only its first rows resident (gpca_ctx::gs_res_rows) and later rows pass through a ring window.
+// Replaces, for the data-preparation stage, MicroarrayDataPreparer::prepare_data_for_eigen_snp_pca
+// (src/prepare.rs:995-1098) / the VCF read + MAF filter (src/vcf.rs:227-266, src/main.rs:176-212).
 // payload source: host memory (host_payload) or, when fd >= 0, a file read chunk by chunk into pinned buffers
+// Gs rows [r_begin, r_end) (logical; both multiples of 512 except the very last end) -> Gt columns, following the
+// physical placement of the rows (resident part, then the ring window)
+static int transpose_gs_rows(gpca_ctx* c, uint64_t r_begin, uint64_t r_end) {
+  const uint64_t res = c->gs_res_rows, win = c->gs_win_rows;
+  uint64_t r = r_begin;
+  while (r < r_end) {
+    uint64_t seg_end, phys;
+    if (r < res || win == 0) {
+      seg_end = win ? std::min(r_end, res) : r_end;
+      phys = r;
+    } else {
+      const uint64_t off = (r - res) % win;
+      seg_end = std::min(r_end, r + (win - off));
+      phys = res + off;
+    }
+    PackedMat sv = c->Gs, dv = c->Gt;
+    sv.p = c->Gs.p + phys * c->Gs.pitch;
+    sv.rows = seg_end - r;
+    dv.p = c->Gt.p + r / 4;          // r is a multiple of 512: a multiple of 128 bytes
+    GPCA_TRY(launch_transpose(c, sv, dv));
+    r = seg_end;
+  }
+  return GPCA_OK;
+}
+
 static int ingest_core(gpca_ctx* c, const uint8_t* host_payload, int fd, uint64_t file_offset, uint64_t n_in,
                        uint64_t n_snps, const int64_t* keep_samples, uint64_t n_keep, const gpca_qc_cfg* cfg,
                        double vcf_maf_threshold, uint8_t* keep_out, float* mean_out, float* sd_out,
                        uint8_t* fail_code_out, uint64_t* n_pca_out) {
   CHECK_CTX(c);
+  GPCA_HOST_POOL(c);
+  constexpr int NS = gpca_ctx::INGEST_STAGES;
+  constexpr uint64_t LAG = 2;       // payload chunks in the transfer queue ahead of the host (NS >= LAG + 2)
   const auto t_entry = std::chrono::steady_clock::now();
   GPCA_CUDA_TRY(c, cudaSetDevice(c->device));
   if (!host_payload && fd < 0 && n_snps) return fail(c, GPCA_ERR_INVALID, "null payload");
@@ -453,8 +621,17 @@ static int ingest_core(gpca_ctx* c, const uint8_t* host_payload, int fd, uint64_
       if (keep_samples[i] < 0 || (uint64_t)keep_samples[i] >= n_in || (i && keep_samples[i] <= keep_samples[i - 1]))
         return fail(c, GPCA_ERR_INVALID, "keep_samples must be increasing indices into the FAM order");
   if (n_snps == 0) return fail(c, GPCA_ERR_INVALID, "No SNPs passed all QC filters.");
+  const uint8_t* pre_mask = nullptr;
+  if (!c->ingest_mask.empty()) {
+    if (c->ingest_mask.size() != n_snps) return fail(c, GPCA_ERR_INVALID, "ingest mask length != n_snps");
+    pre_mask = c->ingest_mask.data();
+  }
   c->vcf_mode = false;
-  GPCA_TRY(alloc_raw(c, N, n_snps));
+  reset_loaded(c);
+  c->raw.release();                 // (the three-call path's staging copy, if an earlier data set left one)
+  c->raw_pitch = 0;
+  c->N = N;
+  c->M = n_snps;
   const uint64_t M = n_snps;
   DevBuf<int64_t> d_keep;
   if (keep_samples) {
@@ -469,90 +646,99 @@ static int ingest_core(gpca_ctx* c, const uint8_t* host_payload, int fd, uint64_
   if (!sd_out) { sd_tmp.resize(M); sd_out = sd_tmp.data(); }
 
   const size_t in_pitch = (n_in + 3) / 4;
+  const size_t gather_pitch = round_up((N + 3) / 4, 16);
   uint64_t rows_per_chunk = std::max<uint64_t>(1, (128ull << 20) / std::max<size_t>(in_pitch, 1));
   if (const char* e = getenv("GPCA_INGEST_CHUNK_ROWS")) rows_per_chunk = std::max<uint64_t>(1, strtoull(e, nullptr, 10));
   rows_per_chunk = std::min<uint64_t>(rows_per_chunk, M);
   const uint64_t n_chunks = (M + rows_per_chunk - 1) / rows_per_chunk;
 
   // device-side destinations (worst case: every SNP passes)
-  GPCA_CUDA_TRY(c, c->d_cnt.alloc(M));
   GPCA_CUDA_TRY(c, c->d_mean.alloc(M));
   GPCA_CUDA_TRY(c, c->d_sd.alloc(M));
   GPCA_CUDA_TRY(c, c->d_inv_sd.alloc(M));
   GPCA_CUDA_TRY(c, c->d_mu_inv_sd.alloc(M));
   GPCA_CUDA_TRY(c, c->d_idx.alloc(M));
-  c->Gs.cols = N;
-  c->Gs.pitch = round_up((N + 3) / 4, 128);
-  GPCA_CUDA_TRY(c, c->gs_store.alloc(c->Gs.pitch * M));
-  c->Gs.p = c->gs_store.p;
-  // Sample-major copy built behind the transfer: when memory allows (staging copy, Gs and a Gt whose row pitch covers
-  // all M SNPs at once) every chunk's complete 512-row tiles of Gs are transposed as soon as they exist; only the tail
-  // is left for the end of the call (the whole-matrix transpose was a 9 ms tail at 2,504 x 10M).  The pitch is then
-  // the one for M columns whatever the QC keeps; the matrix is zeroed once, columns past D stay zero.
-  bool incr_t = false;
-  uint64_t t_done = 0;
-  {
-    const size_t pitch_max = round_up((M + 3) / 4, 128);
-    size_t free_b = 0, total_b = 0;
-    cudaMemGetInfo(&free_b, &total_b);
-    if (!getenv("GPCA_DEBUG_NO_INCR_TRANSPOSE") &&
-        (c->gt_store.n >= pitch_max * N || free_b > pitch_max * N + (16ull << 30))) {
-      GPCA_CUDA_TRY(c, c->gt_store.alloc(pitch_max * N));
-      c->Gt.p = c->gt_store.p;
-      c->Gt.pitch = pitch_max;
-      c->Gt.rows = N;
-      GPCA_CUDA_TRY(c, cudaMemsetAsync(c->Gt.p, 0, pitch_max * N, c->stream));
-      incr_t = true;
-    }
+  GPCA_TRY(ensure_count_buffer(c, M));
+  DevBuf<uint8_t>* stage = c->ingest_stage;   // kept across calls (no per-call cudaMalloc / cudaFree)
+  for (int i = 0; i < NS; ++i) {
+    GPCA_CUDA_TRY(c, stage[i].alloc(rows_per_chunk * in_pitch + 64));
+    if (keep_samples) GPCA_CUDA_TRY(c, c->ingest_gather[i].alloc(rows_per_chunk * gather_pitch + 64));
   }
-  auto transpose_rows = [&](uint64_t r_begin, uint64_t r_end) -> int {   // Gs rows [r_begin, r_end) -> Gt columns
-    if (r_end <= r_begin) return GPCA_OK;
-    PackedMat sv = c->Gs, dv = c->Gt;
-    sv.p = c->Gs.p + r_begin * c->Gs.pitch;
-    sv.rows = r_end - r_begin;
-    dv.p = c->Gt.p + r_begin / 4;          // r_begin is a multiple of 512: a multiple of 128 bytes
-    return launch_transpose(c, sv, dv);
-  };
-  if (c->h_cnt_cap < M) {
-    if (c->h_cnt) cudaFreeHost(c->h_cnt);
-    c->h_cnt = nullptr;
-    c->h_cnt_cap = 0;
-    GPCA_CUDA_TRY(c, cudaMallocHost((void**)&c->h_cnt, M * sizeof(uint4)));
-    c->h_cnt_cap = M;
-  }
-  // pinned staging for the per-chunk compacted vectors: idx (8) + mean, sd, 1/sd, mean/sd (4 x 4) bytes per SNP, x2
-  const size_t up_bytes = rows_per_chunk * 24;
-  if (c->h_up_cap < 2 * up_bytes) {
+  // pinned + mapped staging for the per-chunk compacted vectors: idx (8) + mean, sd, 1/sd, mean/sd (4 x 4) bytes per SNP
+  const size_t up_bytes = round_up(rows_per_chunk * 24, 256);
+  if (c->h_up_cap < NS * up_bytes) {
     if (c->h_up) cudaFreeHost(c->h_up);
-  for (int i = 0; i < 2; ++i)
-    if (c->h_rd[i]) cudaFreeHost(c->h_rd[i]);
     c->h_up = nullptr;
+    c->h_up_dev = nullptr;
     c->h_up_cap = 0;
-    GPCA_CUDA_TRY(c, cudaMallocHost((void**)&c->h_up, 2 * up_bytes));
-    c->h_up_cap = 2 * up_bytes;
+    GPCA_TRY(alloc_mapped(c, (void**)&c->h_up, (void**)&c->h_up_dev, NS * up_bytes));
+    c->h_up_cap = NS * up_bytes;
   }
-  if (fd >= 0) {   // two pinned read buffers, kept across calls
+  if (fd >= 0) {   // pinned read buffers, kept across calls
     const size_t need = rows_per_chunk * in_pitch;
     if (c->h_rd_cap < need) {
-      for (int i = 0; i < 2; ++i) {
+      for (int i = 0; i < NS; ++i) {
         if (c->h_rd[i]) cudaFreeHost(c->h_rd[i]);
         c->h_rd[i] = nullptr;
       }
       c->h_rd_cap = 0;
-      for (int i = 0; i < 2; ++i) GPCA_CUDA_TRY(c, cudaMallocHost((void**)&c->h_rd[i], need));
+      for (int i = 0; i < NS; ++i) GPCA_CUDA_TRY(c, cudaMallocHost((void**)&c->h_rd[i], need));
       c->h_rd_cap = need;
     }
   }
-  DevBuf<uint8_t>* stage = c->ingest_stage;   // kept across calls (no per-call cudaMalloc / cudaFree)
+
+  // ---- layout of the two resident orientations under the memory budget ---------------------------------------------
+  // Gt's pitch covers all M columns whatever the QC keeps (tiles are transposed while the count of survivors is still
+  // open); columns past D are zeroed at the end.
+  c->Gs.cols = N;
+  c->Gs.pitch = round_up((N + 3) / 4, 128);
+  c->Gt.pitch = round_up((M + 3) / 4, 128);
+  c->Gt.rows = N;
+  {
+    const size_t gs_full = c->Gs.pitch * M, gt_full = c->Gt.pitch * N;
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    size_t avail = free_b + c->gs_store.n + c->gt_store.n;     // (stores of an earlier data set are reused or replaced)
+    if (const char* e = getenv("GPCA_DEBUG_MEM_BUDGET")) avail = std::min<size_t>(avail, strtoull(e, nullptr, 10));
+    uint64_t res = M, win = 0;
+    if (gs_full + gt_full + c->mem_reserve > avail) {
+      win = round_up(2 * rows_per_chunk + 1024, 512);
+      const uint64_t win_target = round_up(std::max<uint64_t>(1, (4ull << 30) / c->Gs.pitch), 512);   // ~4 GB of rows
+      win = std::max(win, win_target);
+      if (const char* e = getenv("GPCA_DEBUG_WINDOW_ROWS"))      // tests: a small window on a small matrix
+        win = round_up(std::max<uint64_t>(strtoull(e, nullptr, 10), rows_per_chunk + 1024), 512);
+      const size_t fixed = gt_full + c->mem_reserve + win * c->Gs.pitch;
+      res = fixed < avail ? ((avail - fixed) / c->Gs.pitch) & ~511ull : 0;
+      if (res + win >= M) {      // the window alone covers the rest: everything is resident after all
+        res = M;
+        win = 0;
+      }
+      if (gt_full + std::min<size_t>(gs_full, win * c->Gs.pitch) + (1ull << 30) > avail)
+        return fail(c, GPCA_ERR_OOM, "ingest: the sample-major matrix does not fit on this device (shard the SNPs over more GPUs)");
+    }
+    const size_t gs_bytes = win ? (res + win) * c->Gs.pitch : gs_full;
+    // release before re-allocating (the old and the new store together may not fit), and give back what a smaller
+    // layout no longer needs (the reserve is for the drivers)
+    if (c->gs_store.n < gs_bytes || c->gs_store.n > gs_bytes + (1ull << 30)) c->gs_store.release();
+    if (c->gt_store.n < gt_full || c->gt_store.n > gt_full + (1ull << 30)) c->gt_store.release();
+    GPCA_CUDA_TRY(c, c->gt_store.alloc(gt_full));
+    GPCA_CUDA_TRY(c, c->gs_store.alloc(gs_bytes));
+    c->Gs.p = c->gs_store.p;
+    c->Gt.p = c->gt_store.p;
+    c->gs_res_rows = res;
+    c->gs_win_rows = win;
+  }
+  uint64_t t_done = 0;
+
   // The payload crosses PCIe on its own stream: on the compute stream every chunk's transfer queued behind the
-  // previous chunk's kernels (repitch, counts, recode, transpose tiles: ~0.45 ms per 128 MB chunk, 20 ms per 6.26 GB).
+  // previous chunk's kernels.
   if (!c->copy_stream) GPCA_CUDA_TRY(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-  const bool use_copy_stream = !getenv("GPCA_DEBUG_NO_COPY_STREAM");
-  cudaEvent_t stage_free[2] = {nullptr, nullptr}, up_free[2] = {nullptr, nullptr}, h2d_done[2] = {nullptr, nullptr};
+  cudaEvent_t stage_free[NS], up_free[NS], h2d_done[NS];
+  for (int i = 0; i < NS; ++i) stage_free[i] = up_free[i] = h2d_done[i] = nullptr;
   std::vector<cudaEvent_t> cnt_ready(n_chunks, nullptr);
   auto cleanup = [&]() {
     cudaStreamSynchronize(c->copy_stream);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NS; ++i) {
       if (stage_free[i]) cudaEventDestroy(stage_free[i]);
       if (up_free[i]) cudaEventDestroy(up_free[i]);
       if (h2d_done[i]) cudaEventDestroy(h2d_done[i]);
@@ -560,8 +746,7 @@ static int ingest_core(gpca_ctx* c, const uint8_t* host_payload, int fd, uint64_
     for (auto e : cnt_ready)
       if (e) cudaEventDestroy(e);
   };
-  for (int i = 0; i < 2; ++i) {
-    GPCA_CUDA_TRY(c, stage[i].alloc(rows_per_chunk * in_pitch + 16));
+  for (int i = 0; i < NS; ++i) {
     cudaEventCreateWithFlags(&stage_free[i], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&up_free[i], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h2d_done[i], cudaEventDisableTiming);
@@ -574,7 +759,6 @@ static int ingest_core(gpca_ctx* c, const uint8_t* host_payload, int fd, uint64_
   if (c->h_sd.size() < M) c->h_sd.resize(M);
   if (c->h_inv.size() < M) c->h_inv.resize(M);
   if (c->h_muinv.size() < M) c->h_muinv.resize(M);
-  const uint32_t pad = (uint32_t)(c->raw_pitch * 4 - N);
   const uint32_t n32 = (uint32_t)N;
   uint64_t D = 0, nmiss_total = 0;
   float inv_max = 0.f;
@@ -587,8 +771,56 @@ static int ingest_core(gpca_ctx* c, const uint8_t* host_payload, int fd, uint64_
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count();
   };
   const auto t_begin = now();
-  // host half of the pipeline for chunk q (its count records have been requested on the stream already)
+  // the rows of chunk q as the device sees them (staged file rows, or their sample-gathered copy)
+  auto chunk_src = [&](uint64_t q, const uint8_t*& p, size_t& pitch) {
+    const int sl = (int)(q % NS);
+    if (keep_samples) {
+      p = c->ingest_gather[sl].p;
+      pitch = gather_pitch;
+    } else {
+      p = stage[sl].p;
+      pitch = in_pitch;
+    }
+  };
+  // device half, part 1: transfer of chunk q and its counts
+  auto enqueue = [&](uint64_t q) -> int {
+    const int sl = (int)(q % NS);
+    const uint64_t r0 = q * rows_per_chunk, nr = std::min<uint64_t>(rows_per_chunk, M - r0);
+    auto tq = now();
+    const uint8_t* src = host_payload ? host_payload + r0 * in_pitch : nullptr;
+    if (fd >= 0) {
+      // the pinned read buffer is free once the copy that last used it has run; the read of chunk q then overlaps with
+      // the transfers and the device work of the chunks before it
+      GPCA_CUDA_TRY(c, cudaEventSynchronize(h2d_done[sl]));
+      t_stage_wait += ms_since(tq); tq = now();
+      size_t got = 0;
+      const size_t want = nr * in_pitch;
+      while (got < want) {
+        const ssize_t r = pread(fd, c->h_rd[sl] + got, want - got, (off_t)(file_offset + r0 * in_pitch + got));
+        if (r <= 0) break;
+        got += (size_t)r;
+      }
+      if (got != want) return fail(c, GPCA_ERR_INVALID, "ingest: short read from the .bed file");
+      src = c->h_rd[sl];
+    }
+    // staging buffer `sl` is free once the recode of the chunk that used it last has run (compute stream)
+    GPCA_CUDA_TRY(c, cudaStreamWaitEvent(c->copy_stream, stage_free[sl], 0));
+    GPCA_CUDA_TRY(c, cudaMemcpyAsync(stage[sl].p, src, nr * in_pitch, cudaMemcpyHostToDevice, c->copy_stream));
+    GPCA_CUDA_TRY(c, cudaEventRecord(h2d_done[sl], c->copy_stream));
+    GPCA_CUDA_TRY(c, cudaStreamWaitEvent(c->stream, h2d_done[sl], 0));
+    if (keep_samples)
+      GPCA_TRY(launch_repitch_gather(c, stage[sl].p, in_pitch, n_in, d_keep.p, N, nr, c->ingest_gather[sl].p, gather_pitch));
+    const uint8_t* cs;
+    size_t cp;
+    chunk_src(q, cs, cp);
+    GPCA_TRY(launch_chunk_counts(c, cs, cp, N, nr, c->h_cnt_dev + r0));
+    GPCA_CUDA_TRY(c, cudaEventRecord(cnt_ready[q], c->stream));
+    t_enqueue += ms_since(tq);
+    return GPCA_OK;
+  };
+  // host half of the pipeline for chunk q, then device half part 2 (recode of the kept rows, transposes)
   auto process = [&](uint64_t q) -> int {
+    const int sl = (int)(q % NS);
     const uint64_t r0 = q * rows_per_chunk, nr = std::min<uint64_t>(rows_per_chunk, M - r0);
     auto tp = now();
     GPCA_CUDA_TRY(c, cudaEventSynchronize(cnt_ready[q]));
@@ -598,7 +830,7 @@ static int ingest_core(gpca_ctx* c, const uint8_t* host_payload, int fd, uint64_
     parallel_for(nr, [=](uint64_t lo, uint64_t hi) {
       for (uint64_t t = lo; t < hi; ++t) {
         const uint64_t j = r0 + t;
-        const uint32_t miss = hp[j].x - pad, het = hp[j].y, d0 = hp[j].z;
+        const uint32_t miss = hp[j].x, het = hp[j].y, d0 = hp[j].z;
         const uint32_t nv = n32 - miss;
         hc[4 * j + 0] = nv;
         hc[4 * j + 1] = d0;
@@ -612,19 +844,25 @@ static int ingest_core(gpca_ctx* c, const uint8_t* host_payload, int fd, uint64_
                   fail_code_out ? fail_code_out + r0 : nullptr);
     else
       host_vcf_maf(N, nr, hc + 4 * r0, vcf_maf_threshold, keep_out + r0, mean_out + r0, sd_out + r0);
+    if (pre_mask)      // rows outside the caller's pre-selection are dropped whatever the QC says (fail code 7)
+      for (uint64_t t = 0; t < nr; ++t)
+        if (!pre_mask[r0 + t] && keep_out[r0 + t]) {
+          keep_out[r0 + t] = 0;
+          mean_out[r0 + t] = 0.f;
+          sd_out[r0 + t] = 0.f;
+          if (fail_code_out) fail_code_out[r0 + t] = 7;
+        }
     t_qc += ms_since(tp); tp = now();
-    // compaction of the chunk (serial: a few hundred thousand SNPs) straight into the pinned upload buffer
-    const int ub = (int)(q & 1);
-    GPCA_CUDA_TRY(c, cudaEventSynchronize(up_free[ub]));
-    uint8_t* ubase = c->h_up + (size_t)ub * up_bytes;
+    GPCA_CUDA_TRY(c, cudaEventSynchronize(up_free[sl]));
+    const size_t uoff = (size_t)sl * up_bytes;
+    uint8_t* ubase = c->h_up + uoff;
     uint64_t* u_idx = reinterpret_cast<uint64_t*>(ubase);
     float* u_mean = reinterpret_cast<float*>(ubase + rows_per_chunk * 8);
     float* u_sd = u_mean + rows_per_chunk;
     float* u_inv = u_sd + rows_per_chunk;
     float* u_mu = u_inv + rows_per_chunk;
-    // Compaction on all host threads: the kept SNPs of fixed 8,192-row blocks are counted, the block offsets are a
-    // short serial prefix sum, and every block then writes its survivors at its offset (serially this loop was 1.3 ms
-    // per 128 MB chunk -- with it the host half of the pipeline took longer than the chunk's 2.4 ms on the bus).
+    // Compaction on the pool threads: the kept SNPs of fixed 8,192-row blocks are counted, the block offsets are a
+    // short serial prefix sum, and every block then writes its survivors at its offset.
     constexpr uint64_t CB = 8192;
     const uint64_t ncb = (nr + CB - 1) / CB;
     std::vector<uint64_t> cb_off(ncb + 1, 0), cb_miss(ncb, 0);
@@ -671,78 +909,34 @@ static int ingest_core(gpca_ctx* c, const uint8_t* host_payload, int fd, uint64_
     }
     t_compact += ms_since(tp); tp = now();
     if (kept) {
-      auto up = [&](void* dst, const void* src, size_t bytes) {
-        return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream);
-      };
-      GPCA_CUDA_TRY(c, up(c->d_idx.p + D, u_idx, kept * 8));
-      GPCA_CUDA_TRY(c, up(c->d_mean.p + D, u_mean, kept * 4));
-      GPCA_CUDA_TRY(c, up(c->d_sd.p + D, u_sd, kept * 4));
-      GPCA_CUDA_TRY(c, up(c->d_inv_sd.p + D, u_inv, kept * 4));
-      GPCA_CUDA_TRY(c, up(c->d_mu_inv_sd.p + D, u_mu, kept * 4));
-      PackedMat view = c->Gs;
-      view.p = c->Gs.p + D * c->Gs.pitch;
-      view.rows = kept;
-      GPCA_TRY(launch_build_gs(c, c->raw.p, c->raw_pitch, c->d_idx.p + D, view));
+      const uint8_t* ud = c->h_up_dev + uoff;
+      const float* d_um = reinterpret_cast<const float*>(ud + rows_per_chunk * 8);
+      GPCA_TRY(launch_fetch_kept(c, reinterpret_cast<const uint64_t*>(ud), d_um, d_um + rows_per_chunk,
+                                 d_um + 2 * rows_per_chunk, d_um + 3 * rows_per_chunk, kept, c->d_idx.p + D,
+                                 c->d_mean.p + D, c->d_sd.p + D, c->d_inv_sd.p + D, c->d_mu_inv_sd.p + D));
+      const uint8_t* cs;
+      size_t cp;
+      chunk_src(q, cs, cp);
+      GPCA_TRY(launch_build_gs_chunk(c, cs, cp, N, r0, c->d_idx.p + D, kept, c->Gs.p, c->Gs.pitch, D, c->gs_res_rows,
+                                     c->gs_win_rows));
     }
-    GPCA_CUDA_TRY(c, cudaEventRecord(up_free[ub], c->stream));
+    GPCA_CUDA_TRY(c, cudaEventRecord(up_free[sl], c->stream));
+    GPCA_CUDA_TRY(c, cudaEventRecord(stage_free[sl], c->stream));
     t_upload += ms_since(tp);
     D += kept;
-    if (incr_t) {
-      const uint64_t t_end = D & ~511ull;
-      GPCA_TRY(transpose_rows(t_done, t_end));
-      if (t_end > t_done) t_done = t_end;
+    const uint64_t t_end = D & ~511ull;
+    if (t_end > t_done) {
+      GPCA_TRY(transpose_gs_rows(c, t_done, t_end));
+      t_done = t_end;
     }
     return GPCA_OK;
   };
 
   for (uint64_t q = 0; q < n_chunks && rc == GPCA_OK; ++q) {
-    const int buf = (int)(q & 1);
-    const uint64_t r0 = q * rows_per_chunk, nr = std::min<uint64_t>(rows_per_chunk, M - r0);
-    auto tq = now();
-    cudaError_t e = cudaEventSynchronize(stage_free[buf]);   // (also: the copy out of pinned read buffer `buf` is done)
-    t_stage_wait += ms_since(tq); tq = now();
-    const uint8_t* src = host_payload ? host_payload + r0 * in_pitch : nullptr;
-    if (e == cudaSuccess && fd >= 0) {
-      // the read of chunk q overlaps with the transfer and the device work of chunk q-1 (already enqueued)
-      size_t got = 0;
-      const size_t want = nr * in_pitch;
-      while (got < want) {
-        const ssize_t r = pread(fd, c->h_rd[buf] + got, want - got, (off_t)(file_offset + r0 * in_pitch + got));
-        if (r <= 0) break;
-        got += (size_t)r;
-      }
-      if (got != want) {
-        rc = fail(c, GPCA_ERR_INVALID, "ingest: short read from the .bed file");
-        break;
-      }
-      src = c->h_rd[buf];
-    }
-    // staging buffer `buf` is free once the repitch of the chunk that used it last has run (compute stream)
-    if (use_copy_stream) {
-      if (e == cudaSuccess) e = cudaStreamWaitEvent(c->copy_stream, stage_free[buf], 0);
-      if (e == cudaSuccess)
-        e = cudaMemcpyAsync(stage[buf].p, src, nr * in_pitch, cudaMemcpyHostToDevice, c->copy_stream);
-      if (e == cudaSuccess) e = cudaEventRecord(h2d_done[buf], c->copy_stream);
-      if (e == cudaSuccess) e = cudaStreamWaitEvent(c->stream, h2d_done[buf], 0);
-    } else if (e == cudaSuccess) {
-      e = cudaMemcpyAsync(stage[buf].p, src, nr * in_pitch, cudaMemcpyHostToDevice, c->stream);
-    }
-    if (e != cudaSuccess) {
-      rc = fail(c, GPCA_ERR_CUDA, std::string("ingest H2D: ") + cudaGetErrorString(e));
-      break;
-    }
-    rc = launch_repitch_gather(c, stage[buf].p, in_pitch, n_in, keep_samples ? d_keep.p : nullptr, N, nr,
-                               c->raw.p + r0 * c->raw_pitch, c->raw_pitch);
-    cudaEventRecord(stage_free[buf], c->stream);
-    if (rc == GPCA_OK) rc = launch_bed_counts(c, c->raw.p + r0 * c->raw_pitch, c->raw_pitch, nr, c->d_cnt.p + r0);
-    if (rc == GPCA_OK &&
-        cudaMemcpyAsync(c->h_cnt + r0, c->d_cnt.p + r0, nr * sizeof(uint4), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess)
-      rc = fail(c, GPCA_ERR_CUDA, "ingest: count read-back failed");
-    cudaEventRecord(cnt_ready[q], c->stream);
-    t_enqueue += ms_since(tq);
-    if (rc == GPCA_OK && q > 0) rc = process(q - 1);      // overlaps with chunk q's transfer
+    rc = enqueue(q);
+    if (rc == GPCA_OK && q >= LAG) rc = process(q - LAG);
   }
-  if (rc == GPCA_OK) rc = process(n_chunks - 1);
+  for (uint64_t q = (n_chunks > LAG ? n_chunks - LAG : 0); q < n_chunks && rc == GPCA_OK; ++q) rc = process(q);
   if (rc != GPCA_OK) {
     cudaStreamSynchronize(c->stream);
     cleanup();
@@ -761,35 +955,27 @@ static int ingest_core(gpca_ctx* c, const uint8_t* host_payload, int fd, uint64_
   c->inv_sd_max = inv_max;
   c->D = D;
   c->Gs.rows = D;
-  c->Gt.rows = N;
   c->Gt.cols = D;
+  if (c->gs_res_rows >= D) {       // everything ended up in the resident part
+    c->gs_res_rows = D;
+  }
   const double t_loop = ms_since(t_begin);
-  if (incr_t) {
-    rc = transpose_rows(t_done, D);        // the tail (fewer than 512 rows past the last complete tile)
-  } else {
-    c->Gt.pitch = round_up((D + 3) / 4, 128);
-    size_t free_b = 0, total_b = 0;
-    cudaMemGetInfo(&free_b, &total_b);
-    if (c->gt_store.n < c->Gt.pitch * N && free_b < c->Gt.pitch * N + (8ull << 30)) {
-      cudaStreamSynchronize(c->stream);
-      c->raw.release();
-    }
-    cudaError_t ea = c->gt_store.alloc(c->Gt.pitch * N);
-    if (ea != cudaSuccess) {
-      cleanup();
-      return fail(c, GPCA_ERR_OOM, std::string("ingest: ") + cudaGetErrorString(ea));
-    }
-    c->Gt.p = c->gt_store.p;
-    rc = launch_transpose(c, c->Gs, c->Gt);
+  rc = transpose_gs_rows(c, t_done, D);        // the tail (fewer than 512 rows past the last complete tile)
+  {
+    // columns of Gt past the last transposed tile were never written: zero them (a strided memset of the row tails)
+    const size_t written = std::min<size_t>(c->Gt.pitch, round_up(D, 512) / 4);
+    if (rc == GPCA_OK && written < c->Gt.pitch)
+      GPCA_CUDA_TRY(c, cudaMemset2DAsync(c->Gt.p + written, c->Gt.pitch, 0, c->Gt.pitch - written, N, c->stream));
   }
   cudaStreamSynchronize(c->stream);
   cleanup();
   if (trace)
     fprintf(stderr,
             "[gpca_ingest_bed] chunks %llu  loop %.1f ms  total %.1f ms | stage wait %.1f  enqueue %.1f  count wait %.1f  "
-            "convert %.1f  qc %.1f  compact %.1f  upload+build %.1f  (since entry %.1f)\n",
+            "convert %.1f  qc %.1f  compact %.1f  fetch+build %.1f  (since entry %.1f)  Gs resident rows %llu of %llu, window %llu\n",
             (unsigned long long)n_chunks, t_loop, ms_since(t_begin), t_stage_wait, t_enqueue, t_wait_cnt, t_conv, t_qc,
-            t_compact, t_upload, ms_since(t_entry));
+            t_compact, t_upload, ms_since(t_entry), (unsigned long long)c->gs_res_rows, (unsigned long long)D,
+            (unsigned long long)c->gs_win_rows);
   return rc;
 }
 
@@ -825,16 +1011,91 @@ extern "C" int gpca_ingest_bed_file(gpca_ctx* c, const char* bed_path, uint64_t 
   return rc;
 }
 
+// ---- pinned host buffers for large payloads ----------------------------------------------------------------------
+// cudaMallocHost pins 4 KB pages one fault at a time (measured 2.4 GB/s: 36 s for the 87.5 GB payload of 500,000 x
+// 700,000).  Here: anonymous memory advised to transparent huge pages, first-touched on the context's host threads,
+// then registered with CUDA in one call.
+extern "C" void* gpca_host_alloc(gpca_ctx* c, uint64_t bytes) {
+  if (!c || bytes == 0) return nullptr;
+  GPCA_HOST_POOL(c);
+  const uint64_t HP = 2ull << 20;
+  const uint64_t len = round_up(bytes, HP);
+  void* p = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+  if (p == MAP_FAILED) {
+    c->set_error("gpca_host_alloc: mmap failed");
+    return nullptr;
+  }
+  madvise(p, len, MADV_HUGEPAGE);
+  uint8_t* b = static_cast<uint8_t*>(p);
+  parallel_for(len / 4096, [b](uint64_t lo, uint64_t hi) {
+    for (uint64_t i = lo; i < hi; ++i) b[i * 4096] = 0;
+  }, 1u << 12);
+  if (cudaSetDevice(c->device) != cudaSuccess || cudaHostRegister(p, len, cudaHostRegisterPortable) != cudaSuccess) {
+    cudaGetLastError();
+    munmap(p, len);
+    c->set_error("gpca_host_alloc: cudaHostRegister failed");
+    return nullptr;
+  }
+  return p;
+}
+extern "C" void gpca_host_free(gpca_ctx* c, void* p, uint64_t bytes) {
+  if (!p) return;
+  if (c) cudaSetDevice(c->device);
+  cudaHostUnregister(p);
+  munmap(p, round_up(bytes, 2ull << 20));
+}
+
 // ---- benchmark input ------------------------------------------------------------------------------------------
 extern "C" int gpca_synth_bed_device(gpca_ctx* c, uint8_t* dev_out, uint64_t n_samples, uint64_t n_snps,
                                      uint64_t snp_offset, uint64_t seed, uint32_t n_pops, double fst,
-                                     double missing_rate) {
+                                     double missing_rate, double fst_grade) {
   CHECK_CTX(c);
   GPCA_CUDA_TRY(c, cudaSetDevice(c->device));
   if (!dev_out || n_samples == 0) return fail(c, GPCA_ERR_INVALID, "synth: null output or no samples");
-  GPCA_TRY(launch_synth_bed(c, dev_out, n_samples, n_snps, snp_offset, seed, n_pops, (float)fst, (float)missing_rate));
+  GPCA_TRY(launch_synth_bed(c, dev_out, n_samples, n_snps, snp_offset, seed, n_pops, (float)fst, (float)missing_rate,
+                            (float)fst_grade));
   GPCA_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   return GPCA_OK;
+}
+
+// the same generator into HOST memory (chunks are generated on the device and copied back): the payload a host would
+// have read from a .bed file, for shapes whose payload does not fit on the device next to the resident matrices
+extern "C" int gpca_synth_bed_host(gpca_ctx* c, uint8_t* host_out, uint64_t n_samples, uint64_t n_snps,
+                                   uint64_t snp_offset, uint64_t seed, uint32_t n_pops, double fst, double missing_rate,
+                                   double fst_grade) {
+  CHECK_CTX(c);
+  GPCA_CUDA_TRY(c, cudaSetDevice(c->device));
+  if (!host_out || n_samples == 0) return fail(c, GPCA_ERR_INVALID, "synth: null output or no samples");
+  const uint64_t bps = (n_samples + 3) / 4;
+  const uint64_t rows_per_chunk = std::max<uint64_t>(1, (1ull << 30) / bps);
+  DevBuf<uint8_t> buf[2];
+  cudaEvent_t done[2] = {nullptr, nullptr};
+  for (int i = 0; i < 2; ++i) {
+    GPCA_CUDA_TRY(c, buf[i].alloc(std::min(rows_per_chunk, n_snps) * bps));
+    GPCA_CUDA_TRY(c, cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+  }
+  if (!c->copy_stream) GPCA_CUDA_TRY(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  cudaEvent_t gen_done = nullptr;
+  GPCA_CUDA_TRY(c, cudaEventCreateWithFlags(&gen_done, cudaEventDisableTiming));
+  int rc = GPCA_OK;
+  uint64_t q = 0;
+  for (uint64_t r0 = 0; r0 < n_snps && rc == GPCA_OK; r0 += rows_per_chunk, ++q) {
+    const int b = (int)(q & 1);
+    const uint64_t nr = std::min(rows_per_chunk, n_snps - r0);
+    cudaStreamWaitEvent(c->stream, done[b], 0);      // the copy that last read this buffer has run
+    rc = launch_synth_bed(c, buf[b].p, n_samples, nr, snp_offset + r0, seed, n_pops, (float)fst, (float)missing_rate,
+                          (float)fst_grade);
+    cudaEventRecord(gen_done, c->stream);
+    cudaStreamWaitEvent(c->copy_stream, gen_done, 0);
+    if (cudaMemcpyAsync(host_out + r0 * bps, buf[b].p, nr * bps, cudaMemcpyDeviceToHost, c->copy_stream) != cudaSuccess)
+      rc = fail(c, GPCA_ERR_CUDA, "synth: copy to the host failed");
+    cudaEventRecord(done[b], c->copy_stream);
+  }
+  cudaStreamSynchronize(c->copy_stream);
+  cudaStreamSynchronize(c->stream);
+  for (int i = 0; i < 2; ++i) cudaEventDestroy(done[i]);
+  cudaEventDestroy(gen_done);
+  return rc;
 }
 
 // ---- accessor parity ---------------------------------------------------------------------------
@@ -863,7 +1124,7 @@ extern "C" int gpca_get_standardized_block(gpca_ctx* c, const uint64_t* ids, uin
     GPCA_CUDA_TRY(c, cudaMemcpyAsync(d_samp.p, samp, n_samp * 8, cudaMemcpyHostToDevice, c->stream));
   }
   GPCA_CUDA_TRY(c, cudaMemsetAsync(d_flag.p, 0, sizeof(int), c->stream));
-  GPCA_TRY(launch_std_block(c, c->Gs, c->d_mean.p, c->d_sd.p, d_ids.p, n_ids, samp ? d_samp.p : nullptr, n_samp,
+  GPCA_TRY(launch_std_block(c, c->Gs, c->gs_win_rows ? c->gs_res_rows : c->D, c->Gt, c->d_mean.p, c->d_sd.p, d_ids.p, n_ids, samp ? d_samp.p : nullptr, n_samp,
                             d_out.p, d_flag.p));
   int flag = 0;
   GPCA_CUDA_TRY(c, cudaMemcpyAsync(&flag, d_flag.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -874,14 +1135,34 @@ extern "C" int gpca_get_standardized_block(gpca_ctx* c, const uint64_t* ids, uin
 }
 
 // ---- sketch passes ---------------------------------------------------------------------------------
-int timed_sketch(gpca_ctx* c, const SketchProblem& p) {
-  cudaEvent_t e0, e1;
-  GPCA_CUDA_TRY(c, cudaEventCreate(&e0));
-  GPCA_CUDA_TRY(c, cudaEventCreate(&e1));
-  GPCA_CUDA_TRY(c, cudaEventRecord(e0, c->stream));
-  const int rc = launch_sketch(c, p);
+// Device times of the passes are collected only on request (gpca_set_sketch_timing): a long-lived host that never polls
+// gpca_sketch_stats must not accumulate events.
+static int timing_begin(gpca_ctx* c, cudaEvent_t* e0, cudaEvent_t* e1) {
+  *e0 = *e1 = nullptr;
+  if (!c->sk_timing) return GPCA_OK;
+  if (c->pending_events.size() > 8192) {     // never polled: fold what has finished into the totals
+    GPCA_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    double a = 0, b = 0;
+    uint64_t n = 0;
+    GPCA_TRY(gpca_sketch_stats(c, &a, &b, &n, 0));
+  }
+  GPCA_CUDA_TRY(c, cudaEventCreate(e0));
+  GPCA_CUDA_TRY(c, cudaEventCreate(e1));
+  GPCA_CUDA_TRY(c, cudaEventRecord(*e0, c->stream));
+  return GPCA_OK;
+}
+static int timing_end(gpca_ctx* c, cudaEvent_t e0, cudaEvent_t e1) {
+  if (!e0) return GPCA_OK;
   GPCA_CUDA_TRY(c, cudaEventRecord(e1, c->stream));
   c->pending_events.push_back({e0, e1});
+  return GPCA_OK;
+}
+
+int timed_sketch(gpca_ctx* c, const SketchProblem& p) {
+  cudaEvent_t e0, e1;
+  GPCA_TRY(timing_begin(c, &e0, &e1));
+  const int rc = launch_sketch(c, p);
+  GPCA_TRY(timing_end(c, e0, e1));
   c->sk_bytes += (double)p.G.rows * (double)((p.G.cols + 3) / 4);
   c->sk_passes += 1;
   return rc;
@@ -889,33 +1170,60 @@ int timed_sketch(gpca_ctx* c, const SketchProblem& p) {
 
 int timed_sketch_batch(gpca_ctx* c, const SketchBatch& sb) {
   cudaEvent_t e0, e1;
-  GPCA_CUDA_TRY(c, cudaEventCreate(&e0));
-  GPCA_CUDA_TRY(c, cudaEventCreate(&e1));
-  GPCA_CUDA_TRY(c, cudaEventRecord(e0, c->stream));
+  GPCA_TRY(timing_begin(c, &e0, &e1));
   const int rc = launch_sketch_i8_batch(c, sb);
-  GPCA_CUDA_TRY(c, cudaEventRecord(e1, c->stream));
-  c->pending_events.push_back({e0, e1});
+  GPCA_TRY(timing_end(c, e0, e1));
   c->sk_bytes += sb.bytes;
   c->sk_passes += 1;
   return rc;
 }
 
+// A pass over the SNP-major matrix, segment by segment: the resident rows as they are, the rest re-created window by
+// window from the sample-major matrix (gpca_ctx::gs_res_rows).  fn(view, first logical row) runs on each segment.
+int for_each_gs_segment(gpca_ctx* c, const std::function<int(const PackedMat&, uint64_t)>& fn) {
+  const uint64_t D = c->D;
+  const uint64_t res = c->gs_win_rows ? std::min<uint64_t>(c->gs_res_rows, D) : D;
+  if (res) {
+    PackedMat v = c->Gs;
+    v.rows = res;
+    v.avail = c->Gs.pitch;
+    GPCA_TRY(fn(v, 0));
+  }
+  for (uint64_t r = res; r < D; r += c->gs_win_rows) {
+    const uint64_t nr = std::min<uint64_t>(c->gs_win_rows, D - r);
+    PackedMat sv = c->Gt, dv = c->Gs;
+    sv.p = c->Gt.p + r / 4;               // r is a multiple of 512 (res and the window are)
+    sv.cols = nr;
+    dv.p = c->Gs.p + c->gs_res_rows * c->Gs.pitch;
+    dv.rows = nr;
+    dv.avail = c->Gs.pitch;
+    // the transpose reads Gt columns [r, r + nr) -- the last 512-column tile may run past nr inside Gt's row: those
+    // fields are other SNPs' or zero pads, and land in window rows past nr that the pass does not read
+    GPCA_TRY(launch_transpose(c, sv, dv));
+    GPCA_TRY(fn(dv, r));
+  }
+  return GPCA_OK;
+}
+
 int sketch_snp_side(gpca_ctx* c, const float* dev_in, float* dev_out, uint32_t l, uint32_t ld_in, uint32_t ld_out,
                     bool emit_stats, bool out_pad) {
-  SketchProblem p;
-  p.out_pad = out_pad;
-  p.emit_stats = emit_stats;   // (the statistic is the max-abs over the l logical columns: independent of the stride)
-  p.G = c->Gs;
-  p.Bin = dev_in;
-  p.l = l;
-  p.ld = ld_in;
-  p.f = nullptr;
-  p.e = nullptr;
-  p.a = c->d_inv_sd.p;
-  p.b = c->d_mu_inv_sd.p;
-  p.out = dev_out;
-  p.ldo = ld_out;
-  return timed_sketch(c, p);
+  const bool whole = c->gs_win_rows == 0 || c->gs_res_rows >= c->D;
+  return for_each_gs_segment(c, [&](const PackedMat& g, uint64_t row0) -> int {
+    SketchProblem p;
+    p.out_pad = out_pad;
+    p.emit_stats = emit_stats && whole;   // (the statistic is the max-abs over the l logical columns: independent of the stride)
+    p.G = g;
+    p.Bin = dev_in;
+    p.l = l;
+    p.ld = ld_in;
+    p.f = nullptr;
+    p.e = nullptr;
+    p.a = c->d_inv_sd.p + row0;
+    p.b = c->d_mu_inv_sd.p + row0;
+    p.out = dev_out + row0 * ld_out;
+    p.ldo = ld_out;
+    return timed_sketch(c, p);
+  });
 }
 
 int sketch_sample_side(gpca_ctx* c, const float* dev_in, float* dev_out, uint32_t l, uint32_t ld_in, uint32_t ld_out,
@@ -933,10 +1241,9 @@ int sketch_sample_side(gpca_ctx* c, const float* dev_in, float* dev_out, uint32_
   p.out = dev_out;
   p.ldo = ld_out;
   GPCA_TRY(timed_sketch(c, p));
-  if (c->allreduce) {
+  if (c->sharded()) {
     if (ld_out != l) return fail(c, GPCA_ERR_INVALID, "sharded sample-side sketch needs ld == l");
-    if (c->allreduce(dev_out, c->N * (uint64_t)l, 0, (void*)c->stream, c->allreduce_user) != 0)
-      return fail(c, GPCA_ERR_CUDA, "allreduce hook failed");
+    GPCA_TRY(driver_allreduce(c, dev_out, c->N * (uint64_t)l, 0));
   }
   return GPCA_OK;
 }
@@ -960,10 +1267,9 @@ int sketch_sample_side_gaussian(gpca_ctx* c, float* dev_scratch, float* dev_out,
   p.gen_row0 = c->shard_offset;
   p.gen_amax = GPCA_NORMAL_ABS_MAX * c->inv_sd_max;
   GPCA_TRY(timed_sketch(c, p));
-  if (c->allreduce) {
+  if (c->sharded()) {
     if (ld_out != l) return fail(c, GPCA_ERR_INVALID, "sharded sample-side sketch needs ld == l");
-    if (c->allreduce(dev_out, c->N * (uint64_t)l, 0, (void*)c->stream, c->allreduce_user) != 0)
-      return fail(c, GPCA_ERR_CUDA, "allreduce hook failed");
+    GPCA_TRY(driver_allreduce(c, dev_out, c->N * (uint64_t)l, 0));
   }
   return GPCA_OK;
 }

@@ -4,10 +4,12 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <memory>
 #include <string>
 #include <vector>
 
 #include "../../include/gpca.h"
+#include "parallel_for.h"
 
 #define GPCA_CUDA_TRY(ctx, expr)                                                         \
   do {                                                                                   \
@@ -107,10 +109,16 @@ struct gpca_ctx {
   int engine = 2;   // 0 SIMT fp32, 1 tcgen05 f16, 2 tcgen05 i8 (default; l > 32 falls back to 1)
   int batch_blocks = 1;   // EigenSNP: all LD blocks per launch (needs engine 2); 0 = one block at a time
 
-  // collective hook / shard
+  // exchange between shards: the library's own NCCL communicator (gpca_comm_init, comm.cu) or a host-provided hook
   gpca_allreduce_fn allreduce = nullptr;
   void* allreduce_user = nullptr;
+  void* nccl_comm = nullptr;           // ncclComm_t
+  int comm_rank = 0, comm_world = 1;
+  uint64_t collectives = 0;            // collectives issued since creation (bench / tests)
+  uint64_t shard_vote_D = 0;           // gpca_rfit: the shard size the cached side decision was made for
+  int shard_vote_snp_side = -1;
   uint64_t shard_offset = 0, shard_total = 0;
+  bool sharded() const { return allreduce != nullptr || nccl_comm != nullptr; }
 
   // loaded (pre-QC) data, PLINK-coded, kept samples only, pad fields = 01
   uint64_t N = 0, M = 0;
@@ -127,27 +135,43 @@ struct gpca_ctx {
   float inv_sd_max = 0.f;      // max 1/sd over the PCA SNPs (bounds |f o Omega| for the generated test matrix)
   DevBuf<uint64_t> d_idx;
   DevBuf<uint4> d_cnt;
-  uint4* h_cnt = nullptr;      // pinned landing buffer for the count records
+  // count records of gpca_snp_counts / the streaming ingest: pinned AND mapped, so that the ingest's count kernel
+  // writes them straight into host memory (h_cnt_dev = the device-side address of the same pages)
+  uint4* h_cnt = nullptr;
+  uint4* h_cnt_dev = nullptr;
   uint64_t h_cnt_cap = 0;
   DevBuf<uint8_t> es_store, et_store, ets_store, ess_store;   // EigenSNP slot-ordered / subset copies (kept across calls)
   ScratchPool es_pool;                                        // EigenSNP call-scoped temporaries
   std::vector<int64_t> es_subset;                             // the N_s-sample subset of the last EigenSNP call
   uint64_t es_subset_n = 0, es_subset_seed = 0;
   DevBuf<float> es_cn;                                        // EigenSNP condensed features
-  DevBuf<uint8_t> ingest_stage[2];   // device staging of the raw payload chunks (gpca_ingest_bed)
-  uint8_t* h_up = nullptr;     // pinned staging for the per-chunk compacted vectors (gpca_ingest_bed)
+  // streaming ingest (gpca_ingest_bed): a ring of device staging buffers for the payload chunks, the sample-gathered
+  // copy of a chunk when a keep-list is given, pinned+mapped staging of the per-chunk compacted vectors, pinned read
+  // buffers of gpca_ingest_bed_file
+  static constexpr int INGEST_STAGES = 4;
+  DevBuf<uint8_t> ingest_stage[INGEST_STAGES], ingest_gather[INGEST_STAGES];
+  uint8_t* h_up = nullptr;
+  uint8_t* h_up_dev = nullptr;
   size_t h_up_cap = 0;
-  uint8_t* h_rd[2] = {nullptr, nullptr};   // pinned read buffers of gpca_ingest_bed_file
+  uint8_t* h_rd[INGEST_STAGES] = {nullptr, nullptr, nullptr, nullptr};
   size_t h_rd_cap = 0;
+  std::vector<uint8_t> ingest_mask;        // optional pre-selection of loaded rows for the next ingest (gpca_set_ingest_mask)
+  size_t mem_reserve = 6ull << 30;         // device bytes the ingest leaves free for the drivers' working buffers
   float* h_dl[2] = {nullptr, nullptr};     // pinned landing buffers of download_results (drivers.cu)
   cudaEvent_t ev_dl[2] = {nullptr, nullptr};
   DevBuf<float> d_mean, d_sd;           // [D]
   DevBuf<float> d_inv_sd, d_mu_inv_sd;  // [D]  1/sd (0 if sd<1e-9) and mean/sd
   DevBuf<uint8_t> gs_store, gt_store;
   PackedMat Gs, Gt;                     // [D x N] and [N x D]
+  // Residency of the SNP-major copy.  Both orientations resident is the fast layout; when they do not fit (500,000 x
+  // 700,000 on one GPU: 2 x 87.5 GB) Gt stays whole and Gs keeps only its first gs_res_rows rows, followed in the same
+  // allocation by a window of gs_win_rows rows: the ingest builds later rows through it as a ring, and a pass over
+  // the SNP-major matrix re-creates the non-resident rows window by window from Gt (for_each_gs_segment, api.cu).
+  uint64_t gs_res_rows = 0, gs_win_rows = 0;
   bool any_missing = false;
 
-  // sketch statistics
+  // sketch statistics (bytes and passes always; device times only when sk_timing is on: gpca_set_sketch_timing)
+  bool sk_timing = false;
   double sk_ms = 0, sk_bytes = 0;
   uint64_t sk_passes = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -176,14 +200,25 @@ struct gpca_ctx {
 
   void* cublas = nullptr;      // cublasHandle_t, created on first EigenSNP call
 
+  // host threads of this context (parallel_for.h): a persistent pool, created on first use
+  unsigned host_threads = 0;   // 0 = every CPU the process may run on
+  std::unique_ptr<HostPool> pool;
+  HostPool* host_pool() {
+    if (!pool) pool.reset(new HostPool(host_threads ? host_threads : host_cpu_count()));
+    return pool.get();
+  }
+
   void set_error(const std::string& s) { err = s; }
 };
+// installs the context's host-thread pool for the parallel_for calls of one entry point
+#define GPCA_HOST_POOL(c) HostPoolScope _host_pool_scope((c)->host_pool())
 
 // CUDA-event bracket around the dominant (sketch) kernel alone: begin() before the launch, end() after it.
 struct KernelTimer {
   gpca_ctx* c;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   explicit KernelTimer(gpca_ctx* ctx) : c(ctx) {
+    if (!c->sk_timing) return;       // opt-in: a long-lived host never polls gpca_sketch_stats
     if (cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess) cudaEventRecord(e0, c->stream);
   }
   void end() {

@@ -1,5 +1,6 @@
 // driver_util.cuh -- helpers shared by the PCA drivers (drivers.cu, eigensnp.cu).
 #pragma once
+#include <functional>
 #include <vector>
 
 #include "kernels.cuh"
@@ -22,7 +23,8 @@ int launch_rotation_transform(gpca_ctx* c, const double* evals, const double* ev
 
 void fix_signs_host(std::vector<float>& scores, uint64_t n, uint32_t k, std::vector<int>& flip);
 
-int driver_allreduce(gpca_ctx* c, void* buf, uint64_t count, int dtype);
+int driver_allreduce(gpca_ctx* c, void* buf, uint64_t count, int dtype);   // comm.cu
+int driver_broadcast0(gpca_ctx* c, void* buf, uint64_t bytes);              // comm.cu
 
 // Results back to caller-owned (pageable) host memory: `count` floats from the device arrive in pinned landing buffers
 // chunk by chunk, and host threads copy (dst_f32) or widen (dst_f64) chunk q while chunk q+1 is on the bus.  Returns
@@ -42,6 +44,9 @@ int sketch_sample_side(gpca_ctx* c, const float* dev_in, float* dev_out, uint32_
 // when the integer engine runs (dev_scratch [D x ld_in] is only written by the other paths)
 int sketch_sample_side_gaussian(gpca_ctx* c, float* dev_scratch, float* dev_out, uint32_t l, uint32_t ld_in,
                                 uint32_t ld_out, uint64_t seed, uint32_t stream_id);
+// a pass over the SNP-major matrix in segments (resident rows, then windows re-created from the sample-major matrix)
+int for_each_gs_segment(gpca_ctx* c, const std::function<int(const PackedMat&, uint64_t)>& fn);
+void gpca_comm_destroy(gpca_ctx* c);   // comm.cu
 // generic timed sketch on an arbitrary view (used by the EigenSNP driver)
 int timed_sketch(gpca_ctx* c, const SketchProblem& p);
 // one launch for all LD blocks (integer engine, item mode)

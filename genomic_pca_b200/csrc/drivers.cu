@@ -28,13 +28,6 @@ int get_small(gpca_ctx* c, Small& s) {
   return GPCA_OK;
 }
 
-int driver_allreduce(gpca_ctx* c, void* buf, uint64_t count, int dtype) {
-  if (!c->allreduce) return GPCA_OK;
-  if (c->allreduce(buf, count, dtype, (void*)c->stream, c->allreduce_user) != 0)
-    return fail(c, GPCA_ERR_CUDA, "allreduce hook failed");
-  return GPCA_OK;
-}
-
 int download_results(gpca_ctx* c, const float* d_src, uint64_t count, float* dst_f32, double* dst_f64) {
   constexpr uint64_t CH_MAX = 1u << 21;      // floats per chunk (8 MB landing buffers)
   if (count == 0 || (!dst_f32 && !dst_f64)) return GPCA_OK;
@@ -126,6 +119,7 @@ extern "C" int gpca_rfit(gpca_ctx* c, uint32_t k, uint32_t oversample, uint32_t 
                          int has_seed, double* scores, double* eigenvalues, float* loadings, uint32_t* k_out) {
   if (!c) return GPCA_ERR_INVALID;
   GPCA_CUDA_TRY(c, cudaSetDevice(c->device));
+  GPCA_HOST_POOL(c);
   if (c->D == 0) return fail(c, GPCA_ERR_INVALID, "gpca_set_pca_snps has not been called");
   if (k == 0) return fail(c, GPCA_ERR_INVALID, "Number of components (-k) must be > 0.");  // main.rs:607
   const uint64_t N = c->N, D = c->D;
@@ -136,12 +130,22 @@ extern "C" int gpca_rfit(gpca_ctx* c, uint32_t k, uint32_t oversample, uint32_t 
   uint64_t l64 = std::min<uint64_t>((uint64_t)k + oversample, maxk);
   if (l64 > 64) return fail(c, GPCA_ERR_INVALID, "k + oversample must be <= 64 in this build");
   const uint32_t l = (uint32_t)l64;
+  Small s;
+  GPCA_TRY(get_small(c, s));
   if (!has_seed) {
     std::random_device rd;
     seed = ((uint64_t)rd() << 32) ^ rd() ^ (uint64_t)std::chrono::steady_clock::now().time_since_epoch().count();
+    if (c->sharded()) {
+      // every shard must sketch with the same test matrix: shard 0's entropy seed goes to all of them.  The host hook
+      // has no broadcast, so there an explicit seed is required.
+      if (!c->nccl_comm)
+        return fail(c, GPCA_ERR_INVALID, "sharded gpca_rfit through the allreduce hook needs an explicit seed (has_seed = 1)");
+      GPCA_CUDA_TRY(c, cudaMemcpyAsync(s.G, &seed, 8, cudaMemcpyHostToDevice, c->stream));
+      GPCA_TRY(driver_broadcast0(c, s.G, 8));
+      GPCA_CUDA_TRY(c, cudaMemcpyAsync(&seed, s.G, 8, cudaMemcpyDeviceToHost, c->stream));
+      GPCA_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    }
   }
-  Small s;
-  GPCA_TRY(get_small(c, s));
   DevBuf<float>&Y = c->drv_a, &Z = c->drv_b, &R = c->drv_c, &Sc = c->drv_d;
   // rows of the D x l matrices are padded to a multiple of 8 floats: the snp-side sketch writes a row per thread, and
   // 32-byte aligned rows let it use 32-byte stores (one full sector per store instead of four partial writes)
@@ -159,7 +163,22 @@ extern "C" int gpca_rfit(gpca_ctx* c, uint32_t k, uint32_t oversample, uint32_t 
   // column transform of Z, nor range(S Y) on one of Y): the side with fewer rows on this device -- the samples at the
   // 1000G shape, the shard's SNPs at the 500,000-sample shapes (the l x l Gram of a sharded D side is summed over the
   // shards through the allreduce hook).
-  const bool orth_snp_side = D < N && !getenv("GPCA_DEBUG_ORTH_SAMPLE_SIDE");
+  // Sharded, the choice must be the same on every shard (it decides whether the l x l Gram allreduce is issued): it is
+  // made from the MEAN shard size, which every shard learns from one two-number allreduce (cached per shard size).
+  bool orth_snp_side = D < N;
+  if (c->sharded()) {
+    if (c->shard_vote_snp_side < 0 || c->shard_vote_D != D) {
+      double h[2] = {(double)D, 1.0};
+      GPCA_CUDA_TRY(c, cudaMemcpyAsync(s.G, h, 16, cudaMemcpyHostToDevice, c->stream));
+      GPCA_TRY(driver_allreduce(c, s.G, 2, 1));
+      GPCA_CUDA_TRY(c, cudaMemcpyAsync(h, s.G, 16, cudaMemcpyDeviceToHost, c->stream));
+      GPCA_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+      c->shard_vote_snp_side = (h[1] > 0.0 && h[0] / h[1] < (double)N) ? 1 : 0;
+      c->shard_vote_D = D;
+    }
+    orth_snp_side = c->shard_vote_snp_side == 1;
+  }
+  if (getenv("GPCA_DEBUG_ORTH_SAMPLE_SIDE")) orth_snp_side = false;
   for (uint32_t it = 0; it < power_iters; ++it) {
     if (!orth_snp_side) {
       GPCA_TRY(orthonormalize(c, Y.p, N, l, l, false, s));
@@ -167,7 +186,7 @@ extern "C" int gpca_rfit(gpca_ctx* c, uint32_t k, uint32_t oversample, uint32_t 
       GPCA_TRY(sketch_sample_side(c, Z.p, Y.p, l, ldz, l, true));      // Y = S^T Z
     } else {
       GPCA_TRY(sketch_snp_side(c, Y.p, Z.p, l, l, ldz, false, true));  // Z = S Y
-      GPCA_TRY(orthonormalize(c, Z.p, D, l, ldz, c->allreduce != nullptr, s));
+      GPCA_TRY(orthonormalize(c, Z.p, D, l, ldz, c->sharded(), s));
       c->stats_for = nullptr;                                          // (any statistics of Z are stale now)
       GPCA_TRY(sketch_sample_side(c, Z.p, Y.p, l, ldz, l, false));     // Y = S^T Q_z
     }

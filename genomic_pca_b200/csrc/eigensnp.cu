@@ -38,32 +38,6 @@ constexpr uint32_t STREAM_GLOBAL = 2;
 constexpr uint32_t STREAM_SUBSET = 100;
 constexpr uint32_t STREAM_LOCAL0 = 1000;
 
-// dst row i = src row idx[i] (idx < 0 -> zero row); 16-byte chunks
-__global__ void gather_rows_kernel(const uint8_t* __restrict__ src, size_t src_pitch, const int64_t* __restrict__ idx,
-                                   uint8_t* __restrict__ dst, size_t dst_pitch, uint64_t n_rows, size_t copy_bytes) {
-  const uint64_t cpr = dst_pitch / 16;
-  const uint64_t total = n_rows * cpr;
-  for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < total;
-       t += (uint64_t)gridDim.x * blockDim.x) {
-    const uint64_t r = t / cpr, ci = t - r * cpr;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    const int64_t s = idx[r];
-    if (s >= 0 && ci * 16 < copy_bytes) v = ldg_nc_v4(src + (uint64_t)s * src_pitch + ci * 16);
-    *reinterpret_cast<uint4*>(dst + r * dst_pitch + ci * 16) = v;
-  }
-}
-
-int launch_gather_rows(gpca_ctx* c, PackedMat src, const int64_t* d_idx, PackedMat dst) {
-  const uint64_t total = dst.rows * (dst.pitch / 16);
-  if (!total) return GPCA_OK;
-  const uint64_t blocks = (total + 255) / 256;
-  const int grid = (int)std::min<uint64_t>(blocks, (uint64_t)c->sm_count * 16);
-  gather_rows_kernel<<<grid, 256, 0, c->stream>>>(src.p, src.pitch, d_idx, dst.p, dst.pitch, dst.rows,
-                                                  std::min(src.pitch, dst.pitch));
-  KCHECK(c);
-  return GPCA_OK;
-}
-
 // Sample-major slot-ordered copy when every LD block is a run of consecutive PcaSnpIds (the normal case: blocks are
 // genomic intervals, src/prepare.rs:1424-1563): Et[n, 64q .. 64q+63] = Gt[n, first[q] .. first[q] + count[q] - 1], a
 // per-row shifted copy of 2-bit fields -- one 16-byte chunk per thread, two aligned 16-byte loads and a funnel shift.
@@ -114,18 +88,19 @@ __global__ void shift_fields_kernel(const uint8_t* __restrict__ src, size_t src_
   }
 }
 
-// Block-diagonal operand of the grouped condensed-feature pass: dst [n_slots x 32] (zeroed by the caller), slot s of
-// block p gets U_p's row (src [n_slots x ld_src]) in columns col0(p) .. col0(p) + c_p - 1; padding slots stay zero.
-__global__ void block_diag_operand_kernel(const float* __restrict__ src, uint32_t ld_src, const int64_t* __restrict__ slot_id,
-                                          const uint32_t* __restrict__ col0, const uint32_t* __restrict__ cpn,
-                                          uint64_t n_slots, float* __restrict__ dst) {
-  const uint64_t total = n_slots * ld_src;
+// Block-diagonal operand of the grouped condensed-feature pass: dst [positions x 32] (zeroed by the caller); a
+// position of block p gets U_p's row (src [positions x ld_src]) in columns col0(p) .. col0(p) + c_p - 1; positions
+// outside every block (padding slots) stay zero.
+__global__ void block_diag_operand_kernel(const float* __restrict__ src, uint32_t ld_src,
+                                          const uint32_t* __restrict__ blk_of_pos, const uint32_t* __restrict__ col0,
+                                          const uint32_t* __restrict__ cpn, uint64_t n_pos, float* __restrict__ dst) {
+  const uint64_t total = n_pos * ld_src;
   for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < total;
        t += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t s = t / ld_src;
     const uint32_t j = (uint32_t)(t - s * ld_src);
-    const uint64_t q = s >> 6;
-    if (slot_id[s] >= 0 && j < cpn[q]) dst[s * 32 + col0[q] + j] = src[t];
+    const uint32_t b = blk_of_pos[s];
+    if (b != 0xffffffffu && j < cpn[b]) dst[s * 32 + col0[b] + j] = src[t];
   }
 }
 
@@ -233,6 +208,24 @@ void gpca_destroy_cublas(void* h) {
   if (h) cublasDestroy((cublasHandle_t)h);
 }
 
+extern "C" uint64_t gpca_eigensnp_workspace_bytes(uint64_t N, uint64_t D, uint64_t n_blocks, const gpca_eigensnp_cfg* cfg) {
+  gpca_eigensnp_cfg d;
+  if (!cfg) {
+    gpca_eigensnp_default_cfg(&d);
+    cfg = &d;
+  }
+  uint64_t Ns = (uint64_t)(cfg->subset_factor * (double)N);
+  Ns = std::min<uint64_t>(N, std::max<uint64_t>(cfg->min_subset_size, std::min<uint64_t>(Ns, cfg->max_subset_size)));
+  const uint64_t cpb = cfg->components_per_ld_block, LD = cpb + cfg->local_oversampling;
+  const uint64_t R = n_blocks * cpb, lg = cfg->target_num_global_pcs + cfg->global_oversampling;
+  uint64_t b = N * R * 4;                                                  // condensed features
+  b += Ns * round_up((D + 3) / 4 + 64, 128) + D * round_up((Ns + 3) / 4, 128);   // subset copies, both orientations
+  b += n_blocks * Ns * LD * 4 + D * (LD + cpb + 32) * 4;                   // per-block iterates, bases, grouped operand
+  b += N * lg * 4 * 4 + R * lg * 4 * 2 + D * lg * 4;                       // global iterates, scores, loadings
+  b += (D + N) * 64 * 2 + (3ull << 30);                                    // operand images, split-K partials, slack
+  return b;
+}
+
 extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const uint64_t* block_offsets,
                              uint64_t n_blocks, const uint64_t* block_snp_ids, float* scores, double* eigenvalues,
                              float* loadings, uint32_t* k_out) {
@@ -262,25 +255,6 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
   };
 
   c->es_pool.reset();
-  // ---- slot layout: blocks contiguous, each starting at a multiple of 64 fields ------------------------
-  std::vector<uint64_t> off(n_blocks + 1, 0);
-  std::vector<int64_t> id_of_slot;
-  std::vector<uint8_t> seen(D, 0);
-  for (uint64_t b = 0; b < n_blocks; ++b) {
-    const uint64_t m = block_offsets[b + 1] - block_offsets[b];
-    if (m == 0) return fail(c, GPCA_ERR_INVALID, "empty LD block");
-    off[b] = id_of_slot.size();
-    for (uint64_t j = 0; j < m; ++j) {
-      const uint64_t id = block_snp_ids[block_offsets[b] + j];
-      if (id >= D || seen[id]) return fail(c, GPCA_ERR_INVALID, "block SNP id out of range or listed twice");
-      seen[id] = 1;
-      id_of_slot.push_back((int64_t)id);
-    }
-    while (id_of_slot.size() % 64) id_of_slot.push_back(-1);
-  }
-  off[n_blocks] = id_of_slot.size();
-  const uint64_t Ds = id_of_slot.size();
-
   // ---- subset of samples for the local bases ----------------------------------------------------------
   uint64_t Ns = (uint64_t)(cfg->subset_factor * (double)N);
   Ns = std::max<uint64_t>(cfg->min_subset_size, std::min<uint64_t>(Ns, cfg->max_subset_size));
@@ -311,87 +285,151 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
     c->es_subset_seed = seed;
   }
 
-  // ---- device copies in slot order ----------------------------------------------------------------------
-  std::vector<float> inv_s(Ds, 0.f), mu_s(Ds, 0.f);
-  for (uint64_t s = 0; s < Ds; ++s)
-    if (id_of_slot[s] >= 0) {
-      const float sd = c->h_sd[id_of_slot[s]], mean = c->h_mean[id_of_slot[s]];
-      if (!(std::fabs(sd) < 1e-9f)) {
-        inv_s[s] = 1.0f / sd;
-        mu_s[s] = mean * inv_s[s];
-      }
-    }
-  PoolBuf<float> d_inv(&c->es_pool), d_mu(&c->es_pool);
-  PoolBuf<int64_t> d_slot(&c->es_pool), d_sub(&c->es_pool);
-  GPCA_CUDA_TRY(c, d_inv.alloc(Ds));
-  GPCA_CUDA_TRY(c, d_mu.alloc(Ds));
-  GPCA_CUDA_TRY(c, d_slot.alloc(Ds));
-  GPCA_CUDA_TRY(c, d_sub.alloc(Ns));
-  GPCA_CUDA_TRY(c, cudaMemcpyAsync(d_inv.p, inv_s.data(), Ds * 4, cudaMemcpyHostToDevice, c->stream));
-  GPCA_CUDA_TRY(c, cudaMemcpyAsync(d_mu.p, mu_s.data(), Ds * 4, cudaMemcpyHostToDevice, c->stream));
-  GPCA_CUDA_TRY(c, cudaMemcpyAsync(d_slot.p, id_of_slot.data(), Ds * 8, cudaMemcpyHostToDevice, c->stream));
-  GPCA_CUDA_TRY(c, cudaMemcpyAsync(d_sub.p, sub.data(), Ns * 8, cudaMemcpyHostToDevice, c->stream));
-
-  // the slot-ordered copies are kept in the context between calls (allocating and freeing tens of GB per call costs
-  // more than every kernel of a call together); gpca_load_* / gpca_ingest_bed release them
-  DevBuf<uint8_t>&es_store = c->es_store, &et_store = c->et_store, &ets_store = c->ets_store, &ess_store = c->ess_store;
-  PackedMat Es, Et, Ets, Ess;
-  Es.rows = Ds; Es.cols = N; Es.pitch = c->Gs.pitch;
-  Et.rows = N; Et.cols = Ds; Et.pitch = round_up((Ds + 3) / 4, 128);
-  // blocks that are runs of consecutive PcaSnpIds: the sample-major copy is a shifted copy of Gt's rows
+  // ---- positions: where a block's SNPs sit in the matrices the per-block passes read ---------------------------------
+  // Two layouts.  ID ORDER: when every LD block is a run of consecutive PcaSnpIds (blocks are genomic intervals,
+  // src/prepare.rs:1424-1563 -- the normal case) and the blocks cover every PCA SNP, a block's positions are its
+  // PcaSnpIds and every pass runs on the resident matrices themselves (Gs / Gt and their 1/sd, mean/sd vectors): no
+  // slot-ordered copy of the packed matrix exists (at 500,000 x 700,000 each copy is 87.5 GB).  A block then starts at
+  // an arbitrary field of a sample-major row; a K range starts at the 64-field boundary below it and the operand image
+  // gets zero rows for the fields in front of the block (SketchBatchBlock::kskip).  SLOT ORDER (any block list, and the
+  // one-block-at-a-time path): blocks are laid out contiguously, each starting at a multiple of 64 positions, in
+  // gathered copies Es / Et of the resident matrices.
+  std::vector<uint8_t> seen(D, 0);
   bool runs = !getenv("GPCA_DEBUG_NO_SHIFT_COPY");
-  for (uint64_t b = 0; b < n_blocks && runs; ++b)
-    for (uint64_t j = block_offsets[b] + 1; j < block_offsets[b + 1]; ++j)
-      if (block_snp_ids[j] != block_snp_ids[j - 1] + 1) {
-        runs = false;
-        break;
-      }
-  // ... and when the blocks also cover every PCA SNP, the refinement passes can run on the resident matrices in
-  // PcaSnpId order (Gs / Gt): the SNP-major slot copy Es is then not needed at all (a 3.6 ms gather and 10.9 GB at
-  // the config-4 shard), unless the subset is the whole sample set (Ess aliases Es)
-  bool all_covered = true;
-  for (uint64_t i = 0; i < D && all_covered; ++i) all_covered = seen[i] != 0;
-  const bool id_order = runs && all_covered && Ns != N && !getenv("GPCA_DEBUG_NO_ID_ORDER");
-  if (!id_order) GPCA_CUDA_TRY(c, es_store.alloc(Es.pitch * Es.rows));
-  GPCA_CUDA_TRY(c, et_store.alloc(Et.pitch * Et.rows));
-  Es.p = id_order ? nullptr : es_store.p;
-  Et.p = et_store.p;
-  stage("  allocations + tables");
-  if (!id_order) GPCA_TRY(launch_gather_rows(c, c->Gs, d_slot.p, Es));
-  stage("  gather slots");
-  if (runs) {
-    const uint64_t n_chunks = Ds / 64;
-    std::vector<int64_t> h_first(n_chunks, -1);
-    std::vector<uint32_t> h_count(n_chunks, 0);
-    for (uint64_t b = 0; b < n_blocks; ++b) {
-      const uint64_t m = block_offsets[b + 1] - block_offsets[b];
-      const uint64_t id0 = block_snp_ids[block_offsets[b]];
-      for (uint64_t q = 0; q * 64 < m; ++q) {
-        h_first[off[b] / 64 + q] = (int64_t)(id0 + q * 64);
-        h_count[off[b] / 64 + q] = (uint32_t)std::min<uint64_t>(64, m - q * 64);
-      }
+  uint64_t max_m = 0, n_listed = 0;
+  for (uint64_t b = 0; b < n_blocks; ++b) {
+    const uint64_t m = block_offsets[b + 1] - block_offsets[b];
+    if (m == 0) return fail(c, GPCA_ERR_INVALID, "empty LD block");
+    max_m = std::max(max_m, m);
+    for (uint64_t j = block_offsets[b]; j < block_offsets[b + 1]; ++j) {
+      const uint64_t id = block_snp_ids[j];
+      if (id >= D || seen[id]) return fail(c, GPCA_ERR_INVALID, "block SNP id out of range or listed twice");
+      seen[id] = 1;
+      if (j > block_offsets[b] && id != block_snp_ids[j - 1] + 1) runs = false;
     }
-    PoolBuf<int64_t> d_first(&c->es_pool);
-    PoolBuf<uint32_t> d_count(&c->es_pool);
-    GPCA_CUDA_TRY(c, d_first.alloc(n_chunks));
-    GPCA_CUDA_TRY(c, d_count.alloc(n_chunks));
-    GPCA_CUDA_TRY(c, cudaMemcpyAsync(d_first.p, h_first.data(), n_chunks * 8, cudaMemcpyHostToDevice, c->stream));
-    GPCA_CUDA_TRY(c, cudaMemcpyAsync(d_count.p, h_count.data(), n_chunks * 4, cudaMemcpyHostToDevice, c->stream));
-    const uint64_t total = Et.rows * (Et.pitch / 16);
-    const int grid = (int)std::min<uint64_t>((total + 255) / 256, (uint64_t)c->sm_count * 16);
-    shift_fields_kernel<<<grid, 256, 0, c->stream>>>(c->Gt.p, c->Gt.pitch, d_first.p, d_count.p, Et.p, Et.pitch, Et.rows,
-                                                     n_chunks);
-    KCHECK(c);
-  } else {
-    GPCA_TRY(launch_transpose(c, Es, Et));
+    n_listed += m;
   }
-  stage("  transpose");
+  const bool all_covered = n_listed == D;
+  const uint32_t lp_cap = (uint32_t)std::min<uint64_t>(cpb_max + cfg->local_oversampling, std::min<uint64_t>(max_m, Ns));
+  // All LD blocks in one launch per stage (integer engine, item mode) when the shapes allow it; otherwise one block
+  // at a time through the generic sketch entry (any engine, missing calls, tiny inputs).
+  const bool batched = c->batch_blocks && c->engine == 2 && !c->any_missing && sketch_i8_batch_supported(c) &&
+                       lp_cap <= 32 && cpb_max <= 32 && Ns >= 128 && N >= 128 && D >= 128 && D / 4 < (1ull << 31) &&
+                       n_blocks < (1ull << 24);
+  const bool gs_whole = c->gs_win_rows == 0 || c->gs_res_rows >= D;
+  const bool id_order = runs && all_covered && batched && (Ns != N || gs_whole) && !getenv("GPCA_DEBUG_NO_ID_ORDER");
+  if (!id_order && !gs_whole)
+    return fail(c, GPCA_ERR_OOM,
+                "EigenSNP on a partly resident SNP-major matrix needs LD blocks that are runs of consecutive PCA SNPs "
+                "covering every PCA SNP, without missing calls (otherwise: more GPUs or a smaller memory reserve)");
+  std::vector<uint64_t> boff(n_blocks + 1, 0);     // first position of every block
+  std::vector<int64_t> id_of_slot;                 // slot order only: PcaSnpId of a position (-1 = padding)
+  uint64_t P = 0;                                  // number of positions
+  if (id_order) {
+    for (uint64_t b = 0; b < n_blocks; ++b) boff[b] = block_snp_ids[block_offsets[b]];
+    boff[n_blocks] = D;
+    P = D;
+  } else {
+    id_of_slot.reserve(D + 64 * n_blocks);
+    for (uint64_t b = 0; b < n_blocks; ++b) {
+      boff[b] = id_of_slot.size();
+      for (uint64_t j = block_offsets[b]; j < block_offsets[b + 1]; ++j) id_of_slot.push_back((int64_t)block_snp_ids[j]);
+      while (id_of_slot.size() % 64) id_of_slot.push_back(-1);
+    }
+    boff[n_blocks] = id_of_slot.size();
+    P = id_of_slot.size();
+  }
+  std::vector<uint32_t> blk_of_pos(P, 0xffffffffu);      // block of a position (padding: none)
+  for (uint64_t b = 0; b < n_blocks; ++b) {
+    const uint64_t m = block_offsets[b + 1] - block_offsets[b];
+    std::fill(blk_of_pos.begin() + boff[b], blk_of_pos.begin() + boff[b] + m, (uint32_t)b);
+  }
+
+  // ---- per-position vectors and the matrices over positions -----------------------------------------------------------
+  PoolBuf<float> d_inv_slot(&c->es_pool), d_mu_slot(&c->es_pool);
+  PoolBuf<int64_t> d_slot(&c->es_pool), d_sub(&c->es_pool);
+  PoolBuf<uint32_t> d_blk_of_pos(&c->es_pool);
+  GPCA_CUDA_TRY(c, d_sub.alloc(Ns));
+  GPCA_CUDA_TRY(c, d_blk_of_pos.alloc(P));
+  GPCA_CUDA_TRY(c, cudaMemcpyAsync(d_sub.p, sub.data(), Ns * 8, cudaMemcpyHostToDevice, c->stream));
+  GPCA_CUDA_TRY(c, cudaMemcpyAsync(d_blk_of_pos.p, blk_of_pos.data(), P * 4, cudaMemcpyHostToDevice, c->stream));
+  std::vector<float> inv_s, mu_s;
+  if (!id_order) {
+    inv_s.assign(P, 0.f);
+    mu_s.assign(P, 0.f);
+    for (uint64_t q = 0; q < P; ++q)
+      if (id_of_slot[q] >= 0) {
+        const float sd = c->h_sd[id_of_slot[q]], mean = c->h_mean[id_of_slot[q]];
+        if (!(std::fabs(sd) < 1e-9f)) {
+          inv_s[q] = 1.0f / sd;
+          mu_s[q] = mean * inv_s[q];
+        }
+      }
+    GPCA_CUDA_TRY(c, d_inv_slot.alloc(P));
+    GPCA_CUDA_TRY(c, d_mu_slot.alloc(P));
+    GPCA_CUDA_TRY(c, d_slot.alloc(P));
+    GPCA_CUDA_TRY(c, cudaMemcpyAsync(d_inv_slot.p, inv_s.data(), P * 4, cudaMemcpyHostToDevice, c->stream));
+    GPCA_CUDA_TRY(c, cudaMemcpyAsync(d_mu_slot.p, mu_s.data(), P * 4, cudaMemcpyHostToDevice, c->stream));
+    GPCA_CUDA_TRY(c, cudaMemcpyAsync(d_slot.p, id_of_slot.data(), P * 8, cudaMemcpyHostToDevice, c->stream));
+  }
+  const float* d_inv_p = id_order ? c->d_inv_sd.p : d_inv_slot.p;     // 1/sd, mean/sd per position
+  const float* d_mu_p = id_order ? c->d_mu_inv_sd.p : d_mu_slot.p;
+  struct { const float* p; } d_inv{d_inv_p}, d_mu{d_mu_p};
+
+  // the gathered / subset copies are kept in the context between calls (allocating and freeing tens of GB per call
+  // costs more than every kernel of a call together); gpca_load_* / gpca_ingest_bed release them
+  DevBuf<uint8_t>&es_store = c->es_store, &et_store = c->et_store, &ets_store = c->ets_store, &ess_store = c->ess_store;
+  PackedMat Es, Et, Ets, Ess;      // SNP-major / sample-major over positions, and their N_s-sample subsets
+  if (id_order) {
+    Es = c->Gs; Es.avail = c->Gs.pitch;      // (possibly only partly resident: read through for_each_gs_segment)
+    Et = c->Gt; Et.avail = c->Gt.pitch;
+    stage("  allocations + tables");
+  } else {
+    Es.rows = P; Es.cols = N; Es.pitch = c->Gs.pitch;
+    Et.rows = N; Et.cols = P; Et.pitch = round_up((P + 3) / 4, 128);
+    GPCA_CUDA_TRY(c, es_store.alloc(Es.pitch * Es.rows));
+    GPCA_CUDA_TRY(c, et_store.alloc(Et.pitch * Et.rows));
+    Es.p = es_store.p;
+    Et.p = et_store.p;
+    stage("  allocations + tables");
+    GPCA_TRY(launch_gather_rows(c, c->Gs, d_slot.p, Es));
+    stage("  gather slots");
+    if (runs) {
+      // blocks that are runs of consecutive PcaSnpIds: the sample-major copy is a shifted copy of Gt's rows
+      const uint64_t n_chunks = P / 64;
+      std::vector<int64_t> h_first(n_chunks, -1);
+      std::vector<uint32_t> h_count(n_chunks, 0);
+      for (uint64_t b = 0; b < n_blocks; ++b) {
+        const uint64_t m = block_offsets[b + 1] - block_offsets[b];
+        const uint64_t id0 = block_snp_ids[block_offsets[b]];
+        for (uint64_t q = 0; q * 64 < m; ++q) {
+          h_first[boff[b] / 64 + q] = (int64_t)(id0 + q * 64);
+          h_count[boff[b] / 64 + q] = (uint32_t)std::min<uint64_t>(64, m - q * 64);
+        }
+      }
+      PoolBuf<int64_t> d_first(&c->es_pool);
+      PoolBuf<uint32_t> d_count(&c->es_pool);
+      GPCA_CUDA_TRY(c, d_first.alloc(n_chunks));
+      GPCA_CUDA_TRY(c, d_count.alloc(n_chunks));
+      GPCA_CUDA_TRY(c, cudaMemcpyAsync(d_first.p, h_first.data(), n_chunks * 8, cudaMemcpyHostToDevice, c->stream));
+      GPCA_CUDA_TRY(c, cudaMemcpyAsync(d_count.p, h_count.data(), n_chunks * 4, cudaMemcpyHostToDevice, c->stream));
+      const uint64_t total = Et.rows * (Et.pitch / 16);
+      const int grid = (int)std::min<uint64_t>((total + 255) / 256, (uint64_t)c->sm_count * 16);
+      shift_fields_kernel<<<grid, 256, 0, c->stream>>>(c->Gt.p, c->Gt.pitch, d_first.p, d_count.p, Et.p, Et.pitch,
+                                                       Et.rows, n_chunks);
+      KCHECK(c);
+      GPCA_CUDA_TRY(c, cudaStreamSynchronize(c->stream));   // (host tables above go out of scope)
+    } else {
+      GPCA_TRY(launch_transpose(c, Es, Et));
+    }
+    stage("  transpose");
+  }
   if (Ns == N) {
     Ets = Et;
     Ess = Es;
   } else {
-    Ets.rows = Ns; Ets.cols = Ds; Ets.pitch = Et.pitch;
-    Ess.rows = Ds; Ess.cols = Ns; Ess.pitch = round_up((Ns + 3) / 4, 128);
+    Ets.rows = Ns; Ets.cols = P; Ets.pitch = Et.pitch; Ets.avail = Et.pitch;
+    Ess.rows = P; Ess.cols = Ns; Ess.pitch = round_up((Ns + 3) / 4, 128); Ess.avail = Ess.pitch;
     GPCA_CUDA_TRY(c, ets_store.alloc(Ets.pitch * Ets.rows));
     GPCA_CUDA_TRY(c, ess_store.alloc(Ess.pitch * Ess.rows));
     Ets.p = ets_store.p;
@@ -399,6 +437,8 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
     GPCA_TRY(launch_gather_rows(c, Et, d_sub.p, Ets));
     GPCA_TRY(launch_transpose(c, Ets, Ess));
   }
+  const uint64_t Ds = P;      // (positions; the name the per-block code below uses)
+  const std::vector<uint64_t>& off = boff;
 
   Small s;
   GPCA_TRY(get_small(c, s));
@@ -408,12 +448,10 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
   const bool orth_both = getenv("GPCA_DEBUG_LOCAL_ORTH_BOTH") != nullptr;   // (A/B: re-orthonormalise both sides)
   std::vector<uint32_t> cp(n_blocks);
   std::vector<uint64_t> roff(n_blocks + 1, 0);
-  uint64_t max_m = 0;
   for (uint64_t b = 0; b < n_blocks; ++b) {
     const uint64_t m = block_offsets[b + 1] - block_offsets[b];
     cp[b] = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(cpb_max, m), Ns);
     roff[b + 1] = roff[b] + cp[b];
-    max_m = std::max(max_m, m);
   }
   const uint64_t R = roff[n_blocks];
   PoolBuf<float> Ubuf(&c->es_pool), Yb(&c->es_pool), Zb(&c->es_pool);
@@ -426,11 +464,6 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
     lpv[b] = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(cp[b] + cfg->local_oversampling, m), Ns);
     lp_max = std::max(lp_max, lpv[b]);
   }
-  // All LD blocks in one launch per stage (integer engine, item mode) when the shapes allow it; otherwise one block
-  // at a time through the generic sketch entry (any engine, missing calls, tiny inputs).
-  const bool batched = c->batch_blocks && c->engine == 2 && !c->any_missing && sketch_i8_batch_supported(c) &&
-                       lp_max <= 32 && cpb_max <= 32 && Ns >= 128 && N >= 128 && Ds >= 128 && Ds / 4 < (1ull << 31) &&
-                       n_blocks < (1ull << 24);
   const uint64_t rgN = (N + 255) / 256, rgS = (Ns + 255) / 256;
   PoolBuf<SketchBatchBlock> d_blkY(&c->es_pool);     // operands indexed by the block's SNPs (K = block SNPs)
   std::vector<SketchBatchBlock> blkY;
@@ -439,9 +472,13 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
     blkY.resize(n_blocks);
     for (uint64_t b = 0; b < n_blocks; ++b) {
       const uint64_t m = block_offsets[b + 1] - block_offsets[b];
-      blkY[b].fe_off = off[b];
-      blkY[b].K = (uint32_t)m;
-      blkY[b].nst = (uint32_t)((m + 255) / 256);
+      // the K range starts at the 64-field (16-byte) boundary at or below the block's first position; the operand rows
+      // in front of the block are zeroed in the image (slot order: blocks start on such a boundary, kskip = 0)
+      const uint64_t ka = off[b] & ~63ull;
+      blkY[b].fe_off = ka;
+      blkY[b].kskip = (uint32_t)(off[b] - ka);
+      blkY[b].K = (uint32_t)(off[b] - ka + m);
+      blkY[b].nst = (blkY[b].K + 255) / 256;
       blkY[b].img_st0 = img_stages_Y;
       img_stages_Y += blkY[b].nst;
     }
@@ -462,9 +499,10 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
       zprob[b] = {b * Ns * LD, (uint32_t)Ns, lpv[b]};
       streams[b] = (uint32_t)(STREAM_LOCAL0 + c->shard_offset + block_snp_ids[block_offsets[b]]);
       uoffs[b] = off[b] * cpb_max;
-      blkY[b].bin_off = off[b] * LD;
+      blkY[b].bin_off = (off[b] & ~63ull) * LD;
       blkY[b].l = lpv[b];
       blkZ[b].bin_off = b * Ns * LD;
+      blkZ[b].kskip = 0;
       blkZ[b].fe_off = 0;
       blkZ[b].K = (uint32_t)Ns;
       blkZ[b].l = lpv[b];
@@ -490,7 +528,7 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
         I8Item it;
         it.row0 = (uint32_t)(rg * 256);
         it.nrows_l = (uint32_t)std::min<uint64_t>(256, Ns - rg * 256) | (lpv[b] << 16);
-        it.kbyte0 = (uint32_t)(off[b] / 4);
+        it.kbyte0 = (uint32_t)((off[b] & ~63ull) / 4);
         it.nst = blkY[b].nst;
         it.img_st0 = blkY[b].img_st0;
         it.blk = (uint32_t)b;
@@ -545,7 +583,7 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
     p2.G = Ets; p2.G.avail = Ets.pitch;
     p2.d_items = d_it2.p; p2.n_items = (uint32_t)it2.size();
     p2.d_blocks = d_blkY.p; p2.n_blocks = (uint32_t)n_blocks;
-    p2.total_img_stages = img_stages_Y; p2.max_K = (uint32_t)max_m;
+    p2.total_img_stages = img_stages_Y; p2.max_K = (uint32_t)max_m + 64;
     p2.Bin = Yall.p; p2.ld = LD; p2.f = d_inv.p; p2.e = d_mu.p; p2.a = nullptr; p2.b = nullptr;
     p2.out = Zall.p; p2.ldo = LD;
     p2.bytes = (double)Ns * bytes_blocks / 4.0;
@@ -623,7 +661,10 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
     std::vector<Grp> grps;
     const bool grouping = !getenv("GPCA_DEBUG_NO_GROUPS");
     for (uint64_t b = 0; b < n_blocks; ++b) {
-      if (grouping && !grps.empty() && grps.back().l + cp[b] <= 32) {
+      // (id order: a group's K range is one run of positions, so only blocks that follow each other there can share it;
+      //  slot order lays consecutive blocks out next to each other, separated by zero padding)
+      const bool adjacent = b > 0 && (!id_order || off[b] == off[b - 1] + (block_offsets[b] - block_offsets[b - 1]));
+      if (grouping && !grps.empty() && adjacent && grps.back().l + cp[b] <= 32) {
         grps.back().b1 = b + 1;
         grps.back().l += cp[b];
       } else {
@@ -632,24 +673,24 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
     }
     const uint64_t n_grps = grps.size();
     if (rgN * n_grps > 0x7fffffffull) return fail(c, GPCA_ERR_INVALID, "too many condensed-feature work items");
-    // block-diagonal operand [Ds x 32]: slot s of block p holds U_p's row in columns [col0(p), col0(p) + c_p)
-    const uint64_t n_chunks64 = Ds / 64;
-    std::vector<uint32_t> h_col0(n_chunks64, 0), h_cpn(n_chunks64, 0);
+    // block-diagonal operand [positions x 32]: a position of block p holds U_p's row in columns [col0(p), col0(p) + c_p)
+    std::vector<uint32_t> h_col0(n_blocks, 0);
     std::vector<SketchBatchBlock> blkG(n_grps);
+    std::vector<uint64_t> grp_ka(n_grps);
     uint32_t img_stages_G = 0, max_KG = 0;
     for (uint64_t g = 0; g < n_grps; ++g) {
       uint32_t col = 0;
       for (uint64_t b = grps[g].b0; b < grps[g].b1; ++b) {
-        for (uint64_t q = off[b] / 64; q < off[b + 1] / 64; ++q) {
-          h_col0[q] = col;
-          h_cpn[q] = cp[b];
-        }
+        h_col0[b] = col;
         col += cp[b];
       }
       const uint64_t bl = grps[g].b1 - 1;
-      const uint64_t Kg = off[bl] + (block_offsets[bl + 1] - block_offsets[bl]) - off[grps[g].b0];
-      blkG[g].bin_off = off[grps[g].b0] * 32;
-      blkG[g].fe_off = off[grps[g].b0];
+      const uint64_t ka = off[grps[g].b0] & ~63ull;      // K range from the 64-field boundary below the group
+      const uint64_t Kg = off[bl] + (block_offsets[bl + 1] - block_offsets[bl]) - ka;
+      grp_ka[g] = ka;
+      blkG[g].bin_off = ka * 32;
+      blkG[g].fe_off = ka;
+      blkG[g].kskip = (uint32_t)(off[grps[g].b0] - ka);
       blkG[g].K = (uint32_t)Kg;
       blkG[g].l = grps[g].l;
       blkG[g].nst = (uint32_t)((Kg + 255) / 256);
@@ -661,18 +702,18 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
     PoolBuf<uint32_t> d_col0(&c->es_pool), d_cpn(&c->es_pool);
     PoolBuf<SketchBatchBlock> d_blkG(&c->es_pool);
     GPCA_CUDA_TRY(c, Ugrp.alloc(Ds * 32));
-    GPCA_CUDA_TRY(c, d_col0.alloc(n_chunks64));
-    GPCA_CUDA_TRY(c, d_cpn.alloc(n_chunks64));
+    GPCA_CUDA_TRY(c, d_col0.alloc(n_blocks));
+    GPCA_CUDA_TRY(c, d_cpn.alloc(n_blocks));
     GPCA_CUDA_TRY(c, d_blkG.alloc(n_grps));
-    GPCA_CUDA_TRY(c, cudaMemcpyAsync(d_col0.p, h_col0.data(), n_chunks64 * 4, cudaMemcpyHostToDevice, c->stream));
-    GPCA_CUDA_TRY(c, cudaMemcpyAsync(d_cpn.p, h_cpn.data(), n_chunks64 * 4, cudaMemcpyHostToDevice, c->stream));
+    GPCA_CUDA_TRY(c, cudaMemcpyAsync(d_col0.p, h_col0.data(), n_blocks * 4, cudaMemcpyHostToDevice, c->stream));
+    GPCA_CUDA_TRY(c, cudaMemcpyAsync(d_cpn.p, cp.data(), n_blocks * 4, cudaMemcpyHostToDevice, c->stream));
     GPCA_CUDA_TRY(c, cudaMemcpyAsync(d_blkG.p, blkG.data(), n_grps * sizeof(SketchBatchBlock), cudaMemcpyHostToDevice,
                                      c->stream));
     GPCA_CUDA_TRY(c, cudaMemsetAsync(Ugrp.p, 0, Ds * 32 * sizeof(float), c->stream));
     {
       const uint64_t tot = Ds * cpb_max;
       const int grid = (int)std::min<uint64_t>((tot + 255) / 256, (uint64_t)c->sm_count * 8);
-      block_diag_operand_kernel<<<grid, 256, 0, c->stream>>>(Ubuf.p, cpb_max, d_slot.p, d_col0.p, d_cpn.p, Ds, Ugrp.p);
+      block_diag_operand_kernel<<<grid, 256, 0, c->stream>>>(Ubuf.p, cpb_max, d_blk_of_pos.p, d_col0.p, d_cpn.p, Ds, Ugrp.p);
       KCHECK(c);
     }
     std::vector<I8Item> itc;
@@ -682,7 +723,7 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
         I8Item it;
         it.row0 = (uint32_t)(rg * 256);
         it.nrows_l = (uint32_t)std::min<uint64_t>(256, N - rg * 256) | (blkG[g].l << 16);
-        it.kbyte0 = (uint32_t)(off[grps[g].b0] / 4);
+        it.kbyte0 = (uint32_t)(grp_ka[g] / 4);
         it.nst = blkG[g].nst;
         it.img_st0 = blkG[g].img_st0;
         it.blk = (uint32_t)g;
@@ -751,7 +792,7 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
   GPCA_TRY(cublas_check(c, cublasSetStream(cb.h, c->stream), "setStream"));
   GPCA_TRY(cublas_check(c, cublasSetMathMode(cb.h, CUBLAS_PEDANTIC_MATH), "setMathMode"));
   uint64_t R_total = R;
-  if (c->allreduce) {   // total condensed rows over all shards (f64 scalar through the hook)
+  if (c->sharded()) {   // total condensed rows over all shards (f64 scalar through the exchange)
     PoolBuf<double> tmp(&c->es_pool);
     GPCA_CUDA_TRY(c, tmp.alloc(1));
     const double rr = (double)R;
@@ -816,11 +857,7 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
   GPCA_CUDA_TRY(c, L.alloc(Dl * k));
   GPCA_CUDA_TRY(c, Sc.alloc(N * k));
   SketchProblem f1;   // L = S V   (rows = slots / SNPs, K = all samples)
-  if (id_order) {
-    f1.G = c->Gs; f1.G.avail = c->Gs.pitch;
-  } else {
-    f1.G = Es; f1.G.avail = Es.pitch;
-  }
+  f1.G = Es; f1.G.avail = Es.pitch;      // (id order: the resident matrix, read segment by segment below)
   f1.l = k; f1.ld = k; f1.f = nullptr; f1.e = nullptr; f1.a = l_inv; f1.b = l_mu; f1.ldo = k;
   SketchProblem f2;   // Sc = S^T L (rows = samples, K = slots / SNPs)
   if (id_order) {
@@ -834,7 +871,18 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
   const uint32_t passes = cfg->refine_pass_count;
   for (uint32_t pass = 0; pass < std::max<uint32_t>(passes, 1); ++pass) {
     f1.Bin = V.p; f1.out = L.p;
-    GPCA_TRY(timed_sketch(c, f1));
+    if (id_order) {
+      GPCA_TRY(for_each_gs_segment(c, [&](const PackedMat& g, uint64_t row0) -> int {
+        SketchProblem q = f1;
+        q.G = g;
+        q.a = l_inv + row0;
+        q.b = l_mu + row0;
+        q.out = L.p + row0 * k;
+        return timed_sketch(c, q);
+      }));
+    } else {
+      GPCA_TRY(timed_sketch(c, f1));
+    }
     if (passes == 0) {
       // no refinement requested: loadings = normalised S V0, singular values = column norms
       GPCA_TRY(launch_gram(c, L.p, Dl, k, k, s.G));

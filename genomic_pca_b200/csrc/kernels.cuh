@@ -12,15 +12,25 @@ int launch_u8_to_plink(gpca_ctx* c, const uint8_t* d_in, uint64_t N, uint64_t M,
 int launch_bed_counts(gpca_ctx* c, const uint8_t* d_raw, size_t pitch, uint64_t M, uint4* d_out);
 // gather rows + recode PLINK -> dosage-coded, zero pads: Gs
 int launch_build_gs(gpca_ctx* c, const uint8_t* d_raw, size_t raw_pitch, const uint64_t* d_idx, PackedMat gs);
+// streaming ingest: counts / recode straight from a staged chunk whose rows sit at the file's (unaligned) pitch
+int launch_chunk_counts(gpca_ctx* c, const uint8_t* d_src, size_t pitch, uint64_t N, uint64_t M, uint4* out);
+int launch_fetch_kept(gpca_ctx* c, const uint64_t* u_idx, const float* u_mean, const float* u_sd, const float* u_inv,
+                      const float* u_mu, uint64_t kept, uint64_t* d_idx, float* d_mean, float* d_sd, float* d_inv,
+                      float* d_mu);
+int launch_build_gs_chunk(gpca_ctx* c, const uint8_t* d_src, size_t pitch, uint64_t N, uint64_t row_base,
+                          const uint64_t* d_idx, uint64_t kept, uint8_t* gs, size_t gs_pitch, uint64_t dst_row0,
+                          uint64_t res_rows, uint64_t win_rows);
+// dst row i = src row d_idx[i] (idx < 0 -> zero row)
+int launch_gather_rows(gpca_ctx* c, PackedMat src, const int64_t* d_idx, PackedMat dst);
 // 2-bit transpose: Gt[n][d] = Gs[d][n]
 int launch_transpose(gpca_ctx* c, PackedMat gs, PackedMat gt);
 // standardized block (accessor parity): out[i][j] = fma(x, 1/sd, -mean/sd); flag set if any missing
-int launch_std_block(gpca_ctx* c, PackedMat gs, const float* d_mean, const float* d_sd, const uint64_t* d_ids,
+int launch_std_block(gpca_ctx* c, PackedMat gs, uint64_t gs_rows, PackedMat gt, const float* d_mean, const float* d_sd, const uint64_t* d_ids,
                      uint64_t n_ids, const uint64_t* d_samp, uint64_t n_samp, float* d_out, int* d_missing_flag);
 
 // synthetic Balding-Nichols genotypes in .bed layout, keyed by (seed, global SNP index, sample): benchmark input
 int launch_synth_bed(gpca_ctx* c, uint8_t* d_out, uint64_t n_samples, uint64_t n_snps, uint64_t snp_offset, uint64_t seed,
-                     uint32_t n_pops, float fst, float missing_rate);
+                     uint32_t n_pops, float fst, float missing_rate, float fst_grade);
 
 // ---- dense helpers (kernels_dense.cu) ---------------------------------------------------
 // Gaussian test matrix: out[r][c] = N(0,1) keyed by (seed, stream, row0 + r, c); ld in floats

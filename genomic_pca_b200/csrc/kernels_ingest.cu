@@ -5,6 +5,8 @@
 //   * bed-reader reads with count_a1 (src/prepare.rs:622-629, 682-687): 00->2, 01->missing, 10->1, 11->0
 //   * pass 1 of perform_snp_qc_and_calc_std_params (src/prepare.rs:1232-1279): integer counts
 //   * get_standardized_snp_sample_block (src/prepare.rs:1884-2016)
+#include <algorithm>
+
 #include "kernels.cuh"
 #include "philox.cuh"
 
@@ -261,6 +263,227 @@ int launch_build_gs(gpca_ctx* c, const uint8_t* d_raw, size_t raw_pitch, const u
 }
 
 // ------------------------------------------------------------------------------------------
+// Streaming ingest (gpca_ingest_bed): the chunk that has just crossed PCIe is counted and recoded straight from its
+// staging buffer -- rows at the FILE's pitch ceil(N/4), which is rarely 16-byte aligned -- so no re-pitched copy of
+// the payload exists any more (it was a third full-size copy of the matrix next to Gs and Gt, and two more sweeps).
+// 16 bytes [16 ci, 16 ci + 16) of a row that starts at any byte address: two aligned 128-bit loads and a funnel
+// shift; 2-bit fields at or past `n_fields` read as 00.  The buffer must be readable 16 bytes past its last row.
+__device__ __forceinline__ uint4 load_row_chunk(const uint8_t* row, uint64_t n_fields, uint64_t ci) {
+  const uintptr_t ua = reinterpret_cast<uintptr_t>(row) + ci * 16;
+  const uint4* a0 = reinterpret_cast<const uint4*>(ua & ~(uintptr_t)15);
+  const uint32_t sh = (uint32_t)(ua & 15);
+  uint4 r = ldg_nc_v4(a0);
+  if (sh) {
+    const uint4 b = ldg_nc_v4(a0 + 1);
+    const uint32_t w[8] = {r.x, r.y, r.z, r.w, b.x, b.y, b.z, b.w};
+    const uint32_t ws = sh >> 2, bs = (sh & 3u) * 8u;
+    uint32_t v[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) v[i] = (ws == 0) ? w[i] : (ws == 1) ? w[i + 1] : (ws == 2) ? w[i + 2] : w[i + 3];
+    r.x = __funnelshift_r(v[0], v[1], bs);
+    r.y = __funnelshift_r(v[1], v[2], bs);
+    r.z = __funnelshift_r(v[2], v[3], bs);
+    r.w = __funnelshift_r(v[3], v[4], bs);
+  }
+  const uint64_t f0 = ci * 64;
+  if (f0 + 64 > n_fields) {
+    uint32_t* rw = &r.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint64_t k0 = f0 + 16u * j;
+      if (k0 >= n_fields) rw[j] = 0u;
+      else if (k0 + 16 > n_fields) rw[j] &= (1u << (2 * (int)(n_fields - k0))) - 1u;
+    }
+  }
+  return r;
+}
+
+// K-a on a staged chunk: out[row] = {n(01), n(10), n(11), 0} over the row's first N fields.  `out` may be mapped
+// pinned host memory (the 16-byte records then land on the host without a copy in the transfer queue).
+template <int GROUP>
+__global__ void __launch_bounds__(256) chunk_counts_kernel(const uint8_t* __restrict__ src, size_t pitch, uint64_t N,
+                                                           uint64_t M, uint4* __restrict__ out) {
+  const int chunks = (int)((N + 63) / 64);
+  if constexpr (GROUP > 0) {
+    constexpr int GPW = 32 / GROUP;
+    const uint64_t warp_id = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x % GROUP;
+    const int sub = (threadIdx.x & 31) / GROUP;
+    for (uint64_t base = warp_id * GPW; base < M; base += nwarps * GPW) {
+      const uint64_t row = base + sub;
+      const bool live = row < M;
+      const uint8_t* p = src + (live ? row : 0) * pitch;
+      uint32_t c01 = 0, c10 = 0, c11 = 0;
+      for (int i = lane; live && i < chunks; i += GROUP) {
+        const uint4 v = load_row_chunk(p, N, (uint64_t)i);
+        count_word(v.x, c01, c10, c11);
+        count_word(v.y, c01, c10, c11);
+        count_word(v.z, c01, c10, c11);
+        count_word(v.w, c01, c10, c11);
+      }
+#pragma unroll
+      for (int o = GROUP / 2; o > 0; o >>= 1) {
+        c01 += __shfl_xor_sync(0xffffffffu, c01, o);
+        c10 += __shfl_xor_sync(0xffffffffu, c10, o);
+        c11 += __shfl_xor_sync(0xffffffffu, c11, o);
+      }
+      if (lane == 0 && live) out[row] = make_uint4(c01, c10, c11, 0u);
+    }
+  } else {
+    __shared__ uint32_t s[3][8];
+    for (uint64_t row = blockIdx.x; row < M; row += gridDim.x) {
+      const uint8_t* p = src + row * pitch;
+      uint32_t c01 = 0, c10 = 0, c11 = 0;
+      for (int i = threadIdx.x; i < chunks; i += blockDim.x) {
+        const uint4 v = load_row_chunk(p, N, (uint64_t)i);
+        count_word(v.x, c01, c10, c11);
+        count_word(v.y, c01, c10, c11);
+        count_word(v.z, c01, c10, c11);
+        count_word(v.w, c01, c10, c11);
+      }
+      c01 = warp_sum_u32(c01);
+      c10 = warp_sum_u32(c10);
+      c11 = warp_sum_u32(c11);
+      const int wid = threadIdx.x >> 5;
+      if ((threadIdx.x & 31) == 0) {
+        s[0][wid] = c01;
+        s[1][wid] = c10;
+        s[2][wid] = c11;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        uint32_t t0 = 0, t1 = 0, t2 = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+          t0 += s[0][w];
+          t1 += s[1][w];
+          t2 += s[2][w];
+        }
+        out[row] = make_uint4(t0, t1, t2, 0u);
+      }
+      __syncthreads();
+    }
+  }
+}
+
+int launch_chunk_counts(gpca_ctx* c, const uint8_t* d_src, size_t pitch, uint64_t N, uint64_t M, uint4* out) {
+  if (M == 0) return GPCA_OK;
+  const int threads = 256;
+  const int chunks = (int)((N + 63) / 64);
+  const int grid_full = c->sm_count * 8;
+  if (chunks <= 128) {
+    uint64_t need = (M * 8 + threads - 1) / threads;
+    int grid = (int)(need < (uint64_t)grid_full ? need : (uint64_t)grid_full);
+    chunk_counts_kernel<8><<<grid, threads, 0, c->stream>>>(d_src, pitch, N, M, out);
+  } else if (chunks <= 1024) {
+    uint64_t need = (M * 32 + threads - 1) / threads;
+    int grid = (int)(need < (uint64_t)grid_full ? need : (uint64_t)grid_full);
+    chunk_counts_kernel<32><<<grid, threads, 0, c->stream>>>(d_src, pitch, N, M, out);
+  } else {
+    int grid = (int)(M < (uint64_t)grid_full ? M : (uint64_t)grid_full);
+    chunk_counts_kernel<0><<<grid, threads, 0, c->stream>>>(d_src, pitch, N, M, out);
+  }
+  KLAUNCH_CHECK(c);
+  return GPCA_OK;
+}
+
+// The per-SNP vectors of the rows a chunk keeps (index, mean, sd, 1/sd, mean/sd), compacted by the host into mapped
+// pinned memory, are fetched by this kernel -- no small copies queue up in front of the next payload chunk.
+__global__ void fetch_kept_kernel(const uint64_t* __restrict__ u_idx, const float* __restrict__ u_mean,
+                                  const float* __restrict__ u_sd, const float* __restrict__ u_inv,
+                                  const float* __restrict__ u_mu, uint64_t kept, uint64_t* __restrict__ d_idx,
+                                  float* __restrict__ d_mean, float* __restrict__ d_sd, float* __restrict__ d_inv,
+                                  float* __restrict__ d_mu) {
+  for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < kept; t += (uint64_t)gridDim.x * blockDim.x) {
+    d_idx[t] = u_idx[t];
+    d_mean[t] = u_mean[t];
+    d_sd[t] = u_sd[t];
+    d_inv[t] = u_inv[t];
+    d_mu[t] = u_mu[t];
+  }
+}
+
+int launch_fetch_kept(gpca_ctx* c, const uint64_t* u_idx, const float* u_mean, const float* u_sd, const float* u_inv,
+                      const float* u_mu, uint64_t kept, uint64_t* d_idx, float* d_mean, float* d_sd, float* d_inv,
+                      float* d_mu) {
+  if (kept == 0) return GPCA_OK;
+  const int grid = (int)std::min<uint64_t>((kept + 255) / 256, (uint64_t)c->sm_count * 4);
+  fetch_kept_kernel<<<grid, 256, 0, c->stream>>>(u_idx, u_mean, u_sd, u_inv, u_mu, kept, d_idx, d_mean, d_sd, d_inv, d_mu);
+  KLAUNCH_CHECK(c);
+  return GPCA_OK;
+}
+
+// Kept rows of the staged chunk -> rows [dst_row0, dst_row0 + kept) of the SNP-major resident matrix, recoded to
+// dosage codes with zero pads.  d_idx holds loaded-row indices; the chunk starts at loaded row `row_base`.
+// Destination rows at or past res_rows live in a ring of win_rows rows behind the resident part (GsLayout, common.cuh).
+__global__ void build_gs_chunk_kernel(const uint8_t* __restrict__ src, size_t pitch, uint64_t N, uint64_t row_base,
+                                      const uint64_t* __restrict__ idx, uint64_t kept, uint8_t* __restrict__ gs,
+                                      size_t gs_pitch, uint64_t dst_row0, uint64_t res_rows, uint64_t win_rows) {
+  const uint64_t chunks_per_row = gs_pitch / 16;
+  const uint64_t total = kept * chunks_per_row;
+  for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < total;
+       t += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t w = t / chunks_per_row;
+    const uint64_t ci = t - w * chunks_per_row;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (ci * 64 < N) {
+      v = load_row_chunk(src + (idx[w] - row_base) * pitch, N, ci);
+      uint32_t x[4] = {recode_word(v.x), recode_word(v.y), recode_word(v.z), recode_word(v.w)};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {      // (recoding turns the 00 pads into code 2: clear them again)
+        const uint64_t k0 = ci * 64 + (uint64_t)j * 16;
+        if (k0 >= N) x[j] = 0;
+        else if (k0 + 16 > N) x[j] &= (1u << (2 * (int)(N - k0))) - 1u;
+      }
+      v = make_uint4(x[0], x[1], x[2], x[3]);
+    }
+    uint64_t drow = dst_row0 + w;
+    if (drow >= res_rows && win_rows) drow = res_rows + (drow - res_rows) % win_rows;
+    *reinterpret_cast<uint4*>(gs + drow * gs_pitch + ci * 16) = v;
+  }
+}
+
+int launch_build_gs_chunk(gpca_ctx* c, const uint8_t* d_src, size_t pitch, uint64_t N, uint64_t row_base,
+                          const uint64_t* d_idx, uint64_t kept, uint8_t* gs, size_t gs_pitch, uint64_t dst_row0,
+                          uint64_t res_rows, uint64_t win_rows) {
+  if (kept == 0) return GPCA_OK;
+  const uint64_t total = kept * (gs_pitch / 16);
+  const uint64_t blocks = (total + 255) / 256;
+  const int grid = (int)(blocks < (uint64_t)c->sm_count * 16 ? blocks : (uint64_t)c->sm_count * 16);
+  build_gs_chunk_kernel<<<grid, 256, 0, c->stream>>>(d_src, pitch, N, row_base, d_idx, kept, gs, gs_pitch, dst_row0,
+                                                     res_rows, win_rows);
+  KLAUNCH_CHECK(c);
+  return GPCA_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// dst row i = src row idx[i] (idx < 0 -> zero row); 16-byte chunks
+__global__ void gather_rows_kernel(const uint8_t* __restrict__ src, size_t src_pitch, const int64_t* __restrict__ idx,
+                                   uint8_t* __restrict__ dst, size_t dst_pitch, uint64_t n_rows, size_t copy_bytes) {
+  const uint64_t cpr = dst_pitch / 16;
+  const uint64_t total = n_rows * cpr;
+  for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < total;
+       t += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t r = t / cpr, ci = t - r * cpr;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    const int64_t s = idx[r];
+    if (s >= 0 && ci * 16 < copy_bytes) v = ldg_nc_v4(src + (uint64_t)s * src_pitch + ci * 16);
+    *reinterpret_cast<uint4*>(dst + r * dst_pitch + ci * 16) = v;
+  }
+}
+
+int launch_gather_rows(gpca_ctx* c, PackedMat src, const int64_t* d_idx, PackedMat dst) {
+  const uint64_t total = dst.rows * (dst.pitch / 16);
+  if (!total) return GPCA_OK;
+  const uint64_t blocks = (total + 255) / 256;
+  const int grid = (int)std::min<uint64_t>(blocks, (uint64_t)c->sm_count * 16);
+  gather_rows_kernel<<<grid, 256, 0, c->stream>>>(src.p, src.pitch, d_idx, dst.p, dst.pitch, dst.rows,
+                                                  std::min(src.pitch, dst.pitch));
+  KLAUNCH_CHECK(c);
+  return GPCA_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // 2-bit transpose.  A CTA moves a tile of 512 source rows x 512 source fields: every thread transposes 16 x 16 blocks
 // of 2-bit fields in registers (16 words in, 16 words out, four masked block-swap rounds), the 16 output words go to
 // their destination rows in shared memory (XOR-swizzled columns: conflict-free both ways), and each destination row
@@ -336,7 +559,10 @@ int launch_transpose(gpca_ctx* c, PackedMat gs, PackedMat gt) {
 
 // ------------------------------------------------------------------------------------------
 // Accessor parity kernel (prepare.rs:1884-2016): f32 fma standardisation of a gathered block.
-__global__ void std_block_kernel(const uint8_t* __restrict__ gs, size_t pitch, const float* __restrict__ mean,
+// SNP rows at or past gs_rows are not resident in the SNP-major matrix (gpca_ctx::gs_res_rows): their fields are read
+// from the sample-major one.
+__global__ void std_block_kernel(const uint8_t* __restrict__ gs, size_t pitch, uint64_t gs_rows,
+                                 const uint8_t* __restrict__ gt, size_t gt_pitch, const float* __restrict__ mean,
                                  const float* __restrict__ sd, const uint64_t* __restrict__ ids, uint64_t n_ids,
                                  const uint64_t* __restrict__ samp, uint64_t n_samp, float* __restrict__ out,
                                  int* __restrict__ missing_flag) {
@@ -346,7 +572,8 @@ __global__ void std_block_kernel(const uint8_t* __restrict__ gs, size_t pitch, c
     const uint64_t i = t / n_samp, j = t - i * n_samp;
     const uint64_t id = ids[i];
     const uint64_t s = samp ? samp[j] : j;
-    const uint32_t code = (gs[id * pitch + (s >> 2)] >> (2 * (s & 3))) & 3u;
+    const uint32_t code = id < gs_rows ? (gs[id * pitch + (s >> 2)] >> (2 * (s & 3))) & 3u
+                                       : (gt[s * gt_pitch + (id >> 2)] >> (2 * (id & 3))) & 3u;
     const float m = mean[id], sdev = sd[id];
     float z = 0.0f;
     if (code == 3u) {
@@ -360,14 +587,14 @@ __global__ void std_block_kernel(const uint8_t* __restrict__ gs, size_t pitch, c
   }
 }
 
-int launch_std_block(gpca_ctx* c, PackedMat gs, const float* d_mean, const float* d_sd, const uint64_t* d_ids,
+int launch_std_block(gpca_ctx* c, PackedMat gs, uint64_t gs_rows, PackedMat gt, const float* d_mean, const float* d_sd, const uint64_t* d_ids,
                      uint64_t n_ids, const uint64_t* d_samp, uint64_t n_samp, float* d_out, int* d_missing_flag) {
   const uint64_t total = n_ids * n_samp;
   if (total == 0) return GPCA_OK;
   const int threads = 256;
   const uint64_t blocks = (total + threads - 1) / threads;
   const int grid = (int)(blocks < (uint64_t)c->sm_count * 16 ? blocks : (uint64_t)c->sm_count * 16);
-  std_block_kernel<<<grid, threads, 0, c->stream>>>(gs.p, gs.pitch, d_mean, d_sd, d_ids, n_ids, d_samp, n_samp, d_out,
+  std_block_kernel<<<grid, threads, 0, c->stream>>>(gs.p, gs.pitch, gs_rows, gt.p, gt.pitch, d_mean, d_sd, d_ids, n_ids, d_samp, n_samp, d_out,
                                                     d_missing_flag);
   KLAUNCH_CHECK(c);
   return GPCA_OK;
@@ -382,6 +609,13 @@ int launch_std_block(gpca_ctx* c, PackedMat gs, const float* d_mean, const float
 // One thread per output byte (4 samples): two Philox calls -> 8 uniforms (2 per sample) + one for missingness.
 constexpr uint32_t SYNTH_STREAM_FREQ = 0x5EED0001u, SYNTH_STREAM_GENO = 0x5EED0002u, SYNTH_STREAM_MISS = 0x5EED0003u;
 
+// fst_grade > 0 grades the drift of the populations: F_ST of population k = fst * (1 + grade * (0.5 - k / (P - 1))),
+// so that the P - 1 structural eigenvalues of the standardized matrix are distinct (with equal populations and one
+// F_ST they form one degenerate cluster, and a top-k subspace that cuts through it is not defined).
+__device__ __forceinline__ float synth_pop_fst(uint32_t pop, uint32_t n_pops, float fst, float grade) {
+  if (grade == 0.0f || n_pops < 2) return fst;
+  return fst * (1.0f + grade * (0.5f - (float)pop / (float)(n_pops - 1)));
+}
 __device__ __forceinline__ float synth_pop_freq(uint64_t seed, uint64_t snp, uint32_t pop, float fst) {
   const Philox4 r = philox4x32_10((uint32_t)snp, (uint32_t)(snp >> 32), 0u, SYNTH_STREAM_FREQ, (uint32_t)seed,
                                   (uint32_t)(seed >> 32));
@@ -393,7 +627,7 @@ __device__ __forceinline__ float synth_pop_freq(uint64_t seed, uint64_t snp, uin
 
 __global__ void __launch_bounds__(256) synth_bed_kernel(uint8_t* __restrict__ out, uint64_t n_samples, uint64_t n_snps,
                                                         uint64_t snp_offset, uint64_t seed, uint32_t n_pops, float fst,
-                                                        float missing_rate) {
+                                                        float missing_rate, float fst_grade) {
   const uint64_t bps = (n_samples + 3) / 4;
   const uint64_t total = n_snps * bps;
   for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < total;
@@ -419,7 +653,7 @@ __global__ void __launch_bounds__(256) synth_bed_kernel(uint8_t* __restrict__ ou
       if (i >= n_samples) break;                       // pad fields stay 00 (as in a real .bed)
       const uint32_t pop = (uint32_t)(i * n_pops / n_samples);
       if (pop != last_pop) {
-        pf = synth_pop_freq(seed, snp, pop, fst);
+        pf = synth_pop_freq(seed, snp, pop, synth_pop_fst(pop, n_pops, fst, fst_grade));
         last_pop = pop;
       }
       const uint32_t thr = (uint32_t)(pf * 16777216.0f);
@@ -433,13 +667,13 @@ __global__ void __launch_bounds__(256) synth_bed_kernel(uint8_t* __restrict__ ou
 }
 
 int launch_synth_bed(gpca_ctx* c, uint8_t* d_out, uint64_t n_samples, uint64_t n_snps, uint64_t snp_offset, uint64_t seed,
-                     uint32_t n_pops, float fst, float missing_rate) {
+                     uint32_t n_pops, float fst, float missing_rate, float fst_grade) {
   const uint64_t total = n_snps * ((n_samples + 3) / 4);
   if (total == 0) return GPCA_OK;
   const uint64_t blocks = (total + 255) / 256;
   const int grid = (int)(blocks < (uint64_t)c->sm_count * 16 ? blocks : (uint64_t)c->sm_count * 16);
   synth_bed_kernel<<<grid, 256, 0, c->stream>>>(d_out, n_samples, n_snps, snp_offset, seed, n_pops ? n_pops : 1, fst,
-                                                missing_rate);
+                                                missing_rate, fst_grade);
   KLAUNCH_CHECK(c);
   return GPCA_OK;
 }

@@ -782,7 +782,7 @@ __global__ void __launch_bounds__(256) i8_colstats_batch_kernel(const float* __r
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const uint64_t kk = k + u * stride;
-      const bool live = kk < K;
+      const bool live = kk < K && kk >= bk.kskip;
       x0[u] = (live && c0) ? src[kk * ld + cidx] : 0.0f;
       ek[u] = (live && eb) ? eb[kk] : 1.0f;
       fk[u] = (live && fb) ? fb[kk] : 1.0f;
@@ -857,7 +857,7 @@ __global__ void __launch_bounds__(256) prep_b_i8_batch_kernel(const float* __res
       const int cc = s >> 2, bb = s & 3;
       const uint64_t k = g * 32 + 16 * (cc >> 2) + (cc & 3) + 4 * bb;
       int q = 0;
-      if (k < K && n < l) {
+      if (k < K && k >= bk.kskip && n < l) {
         float v = src[k * ld + n];
         if (fb) v *= fb[k];
         q = __float2int_rn(v * qs);

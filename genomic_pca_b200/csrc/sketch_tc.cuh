@@ -30,6 +30,8 @@ struct SketchBatchBlock {  // operand of one block
   uint32_t K;              // rows of the operand (= fields of the K range)
   uint32_t l;              // logical columns (<= 32)
   uint32_t img_st0, nst;   // image stages [img_st0, img_st0 + nst), nst = ceil(K / 256)
+  uint32_t kskip = 0;      // the first kskip rows count as zero: fields in front of a block whose K range had to start
+  uint32_t pad_ = 0;       //   at the 16-byte boundary below the block's first field
 };
 struct SketchBatch {
   PackedMat G;                       // the whole packed matrix the items index into

@@ -33,6 +33,7 @@ extern "C" {
 #endif
 
 typedef struct gpca_ctx gpca_ctx;
+struct gpca_eigensnp_cfg_s;
 
 enum {
   GPCA_OK = 0,
@@ -63,6 +64,46 @@ int gpca_sketch_stats(gpca_ctx* ctx, double* ms_total, double* packed_bytes_tota
 /* device time (ms) of the main sketch kernel launches alone (no operand prep / split-K reduce), as of the last
  * gpca_sketch_stats call */
 double gpca_sketch_kernel_ms(gpca_ctx* ctx);
+
+/* Host threads this context may use for its host-side stages (QC ladder, compaction, widening of results): 0 = every
+ * CPU the process may run on (default; GPCA_HOST_THREADS overrides).  With one process per GPU the host sets
+ * cores / ranks so that the ranks do not oversubscribe the machine.  Stands in for `--threads` of the reference CLI
+ * (src/main.rs:103-106, the global rayon pool). */
+int gpca_set_host_threads(gpca_ctx* ctx, uint32_t n_threads);
+/* 1 = record CUDA events around every sketch pass so that gpca_sketch_stats / gpca_sketch_kernel_ms report device
+ * times (benchmarks); 0 (default) = no events are created on the production path. */
+int gpca_set_sketch_timing(gpca_ctx* ctx, int on);
+/* Device bytes the next ingest must leave free for the drivers' working buffers (default 6 GiB; gpca_eigensnp needs
+ * about gpca_eigensnp_workspace_bytes).  When both orientations of the packed matrix plus this reserve do not fit, the
+ * ingest keeps the sample-major copy whole and only the first rows of the SNP-major copy resident
+ * (gpca_resident_snp_rows); the passes re-create the rest window by window. */
+int gpca_set_memory_reserve(gpca_ctx* ctx, uint64_t bytes);
+uint64_t gpca_resident_snp_rows(const gpca_ctx* ctx);
+/* Working memory gpca_eigensnp needs on the device for n_samples x n_pca_snps in n_blocks LD blocks (an upper
+ * estimate; pass it to gpca_set_memory_reserve before the ingest). */
+uint64_t gpca_eigensnp_workspace_bytes(uint64_t n_samples, uint64_t n_pca_snps, uint64_t n_blocks,
+                                       const struct gpca_eigensnp_cfg_s* cfg);
+
+/* Pinned host memory for large payloads (a host that reads the .bed itself and hands it to gpca_ingest_bed): anonymous
+ * memory on transparent huge pages, first-touched on the context's host threads and registered with CUDA -- several
+ * times faster to obtain than cudaMallocHost for tens of GB.  Stands in for the reference's Mmap of the .bed
+ * (bed-reader, src/prepare.rs:491). */
+void* gpca_host_alloc(gpca_ctx* ctx, uint64_t bytes);
+void gpca_host_free(gpca_ctx* ctx, void* p, uint64_t bytes);
+
+/* ---- exchange between shards (multi-GPU) ------------------------------------------------ */
+/* The library's own communicator: NCCL over NVLink / NVSwitch, bound at run time (libnccl.so.2).  One context = one
+ * rank; the contexts may live in threads of one process or in one process each.  One rank calls gpca_comm_unique_id,
+ * the host passes the id bytes to the others (MPI, a file, torch.distributed ...), every rank calls gpca_comm_init;
+ * from then on the library issues its collectives (sum of the N x l sketch after a sample-side pass, l x l Grams) on
+ * its own stream.  Nothing in the reference corresponds to this (single process). */
+#define GPCA_COMM_ID_BYTES 128
+int gpca_comm_unique_id(uint8_t* id_out /* GPCA_COMM_ID_BYTES */);
+int gpca_comm_init(gpca_ctx* ctx, const uint8_t* id /* GPCA_COMM_ID_BYTES */, int rank, int world);
+int gpca_comm_finalize(gpca_ctx* ctx);
+int gpca_comm_world(const gpca_ctx* ctx);
+/* collectives issued by this context since creation (either transport) */
+uint64_t gpca_collective_count(const gpca_ctx* ctx);
 
 /* Cross-shard sum hook (multi-GPU, SNP-sharded): called on the context's stream order with a
  * DEVICE buffer that must be replaced by its sum over all shards (fp32 or fp64).
@@ -115,6 +156,10 @@ double gpca_hwe_chi_squared_p_value(uint64_t hom1, uint64_t het, uint64_t hom2);
  * standardisation parameters; builds the resident device copies used by every sketch pass.
  * Mirrors MicroarrayGenotypeAccessor::new (src/prepare.rs:1783-1822). */
 int gpca_set_pca_snps(gpca_ctx* ctx, const uint64_t* snp_idx, uint64_t n_pca_snps, const float* mean, const float* sd);
+/* After gpca_ingest_bed (which keeps no staging copy of the payload) both calls can only NARROW the resident set: the
+ * kept rows move up inside the resident matrices.  This is the EigenSNP workflow's step that drops QC'd SNPs outside
+ * every LD block (src/prepare.rs:1424-1563); hosts that know the selection up front pass it to the ingest instead
+ * (gpca_set_ingest_mask). */
 /* Same, selecting every loaded SNP with keep[j] != 0 and taking mean/sd from the full-length arrays that
  * gpca_snp_qc / gpca_vcf_maf_filter filled (saves the host a gather over millions of SNPs). */
 int gpca_set_pca_snps_mask(gpca_ctx* ctx, const uint8_t* keep, const float* mean_all, const float* sd_all,
@@ -127,6 +172,10 @@ int gpca_set_pca_snps_mask(gpca_ctx* ctx, const uint8_t* keep, const float* mean
 int gpca_ingest_bed(gpca_ctx* ctx, const uint8_t* host_payload, uint64_t n_in_samples, uint64_t n_snps,
                     const int64_t* keep_samples, uint64_t n_keep, const gpca_qc_cfg* cfg, double vcf_maf_threshold,
                     uint8_t* keep, float* mean, float* sd, uint8_t* fail_code, uint64_t* n_pca_out);
+/* Optional pre-selection for the next gpca_ingest_bed / gpca_ingest_bed_file: loaded rows with mask[j] == 0 are dropped
+ * whatever the QC says (fail code 7) -- e.g. SNPs that lie in no LD block (src/prepare.rs:1447-1463 depends only on
+ * chromosome / position, so the host can evaluate it before the genotypes are read).  NULL clears it. */
+int gpca_set_ingest_mask(gpca_ctx* ctx, const uint8_t* mask, uint64_t n_snps);
 /* The same pass straight from a PLINK .bed file (magic and size are checked against n_in_samples x n_snps): chunks are
  * read into pinned buffers and copied on, so the file is never held in host memory as a whole and the read overlaps
  * with the transfer and the device work.  Replaces the IoService reader pool for this stage (src/prepare.rs:169-920,
@@ -161,7 +210,7 @@ void* gpca_get_stream(gpca_ctx* ctx);
 int gpca_rfit(gpca_ctx* ctx, uint32_t k, uint32_t oversample, uint32_t power_iters, uint64_t seed, int has_seed,
               double* scores, double* eigenvalues, float* loadings, uint32_t* k_out);
 
-typedef struct {                         /* EigenSNPCoreAlgorithmConfig, src/main.rs:311-327 */
+typedef struct gpca_eigensnp_cfg_s {     /* EigenSNPCoreAlgorithmConfig, src/main.rs:311-327 */
   uint32_t target_num_global_pcs;        /* --eigensnp-k-global            10    */
   uint32_t components_per_ld_block;      /* --eigensnp-components-per-block 7    */
   double subset_factor;                  /* --eigensnp-subset-factor       0.075 */
@@ -200,9 +249,14 @@ int gpca_map_snps_to_ld_blocks(const char* const* snp_chrom, const int32_t* snp_
 
 /* Benchmark input (not on the reference's path): synthetic structured genotypes written on the
  * device straight in .bed layout (n_snps rows of ceil(n_samples/4) bytes).  Counter-based (Philox keyed by seed, global
- * SNP index = snp_offset + row, sample), so any shard of SNPs regenerates identically at any GPU count. */
+ * SNP index = snp_offset + row, sample), so any shard of SNPs regenerates identically at any GPU count.
+ * fst_grade > 0 gives population k the drift fst * (1 + fst_grade * (0.5 - k / (n_pops - 1))): distinct structural
+ * eigenvalues, so that a top-k subspace is well defined for any k (0 = one F_ST for all: a degenerate cluster). */
 int gpca_synth_bed_device(gpca_ctx* ctx, uint8_t* dev_out, uint64_t n_samples, uint64_t n_snps, uint64_t snp_offset,
-                          uint64_t seed, uint32_t n_pops, double fst, double missing_rate);
+                          uint64_t seed, uint32_t n_pops, double fst, double missing_rate, double fst_grade);
+/* the same rows into host memory (generated on the device chunk by chunk): stands in for a .bed file read by the host */
+int gpca_synth_bed_host(gpca_ctx* ctx, uint8_t* host_out, uint64_t n_samples, uint64_t n_snps, uint64_t snp_offset,
+                        uint64_t seed, uint32_t n_pops, double fst, double missing_rate, double fst_grade);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,118 @@
+"""Parity at a BASELINE shape: 2,504 samples x 1,000,000 SNPs (a tenth of config 3's SNPs, its full sample count),
+generated on the device.  gpca_rfit / gpca_eigensnp against the EXACT float64 eigen-decomposition of the N x N Gram
+matrix of the standardized matrix, accumulated by torch in float64 from the decoded .bed payload (test infrastructure:
+no kernel of the library is involved in the reference side).  Tolerances are the north star's: eigenvalues 1e-4
+relative, principal subspace angle < 1e-3 rad."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pca
+
+pytestmark = pytest.mark.gpu
+
+N, M = 2504, 1_000_000
+SEED = 20260101
+
+
+def record(name, **vals):
+    """the measured distances, kept beside the run (gpurun_out/ travels back from the GPU box)"""
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(d):
+        with open(os.path.join(d, "scale_parity.jsonl"), "a") as f:
+            f.write(json.dumps({"test": name, **vals}) + "\n")
+
+
+def exact_pca_torch(torch, payload, n, keep, mean, sd, k, chunk=32768):
+    """count_a1 decode (00 -> 2, 01 -> missing, 10 -> 1, 11 -> 0; src/prepare.rs:622-629), standardisation with the
+    library's f32 mean / sd widened to f64, Gram matrix in f64, eigh.  Returns (explained variance [k], V [n x k])."""
+    dev = payload.device
+    bps = payload.shape[1]
+    lut = torch.tensor([2.0, float("nan"), 1.0, 0.0], dtype=torch.float64, device=dev)
+    shifts = torch.tensor([0, 2, 4, 6], dtype=torch.uint8, device=dev)
+    idx = torch.as_tensor(np.nonzero(keep)[0], device=dev)
+    mu = torch.as_tensor(mean[keep].astype(np.float64), device=dev)
+    isd = 1.0 / torch.as_tensor(sd[keep].astype(np.float64), device=dev)
+    gram = torch.zeros((n, n), dtype=torch.float64, device=dev)
+    for c0 in range(0, idx.numel(), chunk):
+        rows = idx[c0:c0 + chunk]
+        b = payload.index_select(0, rows)
+        codes = ((b.unsqueeze(-1) >> shifts) & 3).reshape(rows.numel(), bps * 4)[:, :n].long()
+        s = (lut[codes] - mu[c0:c0 + chunk, None]) * isd[c0:c0 + chunk, None]
+        assert not torch.isnan(s).any()
+        gram.addmm_(s.t(), s)
+    evals, evecs = torch.linalg.eigh(gram)
+    top = torch.argsort(evals, descending=True)[:k]
+    return (evals[top] / (n - 1)).cpu().numpy(), evecs[:, top].cpu().numpy()
+
+
+@pytest.fixture(scope="module")
+def scale_case():
+    """(torch payload on the device, per n_pops) -> generated once per population count"""
+    import torch
+    import genomic_pca_b200 as gp
+    cache = {}
+
+    def get(n_pops):
+        if n_pops not in cache:
+            dev = torch.device("cuda", 0)
+            payload = torch.empty((M, (N + 3) // 4), dtype=torch.uint8, device=dev)
+            gen = gp.Context(0)
+            gen.synth_bed_device(payload.data_ptr(), N, M, 0, SEED, n_pops, 0.1, 0.0, 1.0)    # graded F_ST: distinct eigenvalues
+            gen.close()
+            torch.cuda.synchronize()
+            cache.clear()            # one payload (626 MB) at a time
+            cache[n_pops] = payload
+        return cache[n_pops]
+    return get
+
+
+def test_rfit_at_scale_against_exact_f64_pca(scale_case):
+    """k = 20 of 21 structural components (22 populations, graded drift): the cut goes through the structural part of
+    the spectrum, where only distinct eigenvalues make the top-k subspace well defined."""
+    import torch
+    import genomic_pca_b200 as gp
+    payload = scale_case(22)
+    ctx = gp.Context(0)
+    ctx.load_bed_device(payload.data_ptr(), N, M)
+    keep, mean, sd = ctx.vcf_maf_filter(0.01)
+    d = ctx.set_pca_snps_mask(keep, mean, sd)
+    assert d > 0.9 * M
+    sc, ev, _ = ctx.rfit(20, 10, power_iters=2, seed=42, want_loadings=False)
+    ctx.close()
+    ev_x, v_x = exact_pca_torch(torch, payload, N, keep, mean, sd, 21)
+    record("rfit", ev_rel=float(np.abs(ev / ev_x[:20] - 1).max()), angle=pca.subspace_angle(sc, v_x[:, :20]),
+           gap_20_21=float(ev_x[19] / ev_x[20]), ev_head=[float(x) for x in ev_x[:3]], ev_tail=[float(x) for x in ev_x[18:21]])
+    assert ev_x[19] / ev_x[20] > 1.01                   # the generator's grading: a real gap at the cut
+    assert np.abs(ev / ev_x[:20] - 1).max() < 1e-4
+    assert pca.subspace_angle(sc, v_x[:, :20]) < 1e-3
+
+
+def test_eigensnp_at_scale_against_exact_f64_pca(scale_case):
+    """EigenSNP with the reference's effective defaults (src/main.rs:545-588), k = 10 = every structural component of
+    11 populations, 2,427 LD blocks of ~412 SNPs (runs of consecutive PCA SNPs: the layout without gathered copies)."""
+    import torch
+    import genomic_pca_b200 as gp
+    payload = scale_case(11)
+    ctx = gp.Context(0)
+    ctx.load_bed_device(payload.data_ptr(), N, M)
+    keep, mean, sd, _ = ctx.snp_qc(gp.QcConfig(0.98, 0.01, 1.0))
+    d = ctx.set_pca_snps_mask(keep, mean, sd)
+    nb = d // 412
+    edges = np.linspace(0, d, nb + 1).astype(np.int64)
+    blocks = [np.arange(edges[i], edges[i + 1], dtype=np.uint64) for i in range(nb)]
+    sc, ev, load = ctx.eigensnp(blocks, gp.EigenSnpConfig(target_num_global_pcs=10))
+    sc3, ev3, load3 = ctx.eigensnp(blocks, gp.EigenSnpConfig(target_num_global_pcs=10, refine_pass_count=3))
+    ctx.close()
+    ev_x, v_x = exact_pca_torch(torch, payload, N, keep, mean, sd, 10)
+    record("eigensnp", ev_rel=float(np.abs(ev / ev_x - 1).max()), angle=pca.subspace_angle(sc, v_x),
+           ev_rel_refine3=float(np.abs(ev3 / ev_x - 1).max()), angle_refine3=pca.subspace_angle(sc3, v_x),
+           ev_head=[float(x) for x in ev_x[:3]])
+    assert np.abs(ev / ev_x - 1).max() < 1e-4
+    assert pca.subspace_angle(sc, v_x) < 1e-3
+    assert np.abs(ev3 / ev_x - 1).max() < 1e-4
+    assert pca.subspace_angle(sc3, v_x) < 1e-3
+    l64 = load.astype(np.float64)
+    assert np.abs(l64.T @ l64 - np.eye(10)).max() < 1e-3          # orthonormal loadings

@@ -28,6 +28,7 @@ def child(shapes):
         payload = bench.synth_bed_device(torch, n, m, 0, dev)
         torch.cuda.synchronize()
         ctx = gp.Context(0)
+        ctx.set_sketch_timing(True)
         ctx.load_bed_device(payload.data_ptr(), n, m)
         keep, mean, sd = ctx.vcf_maf_filter(0.01)
         d = ctx.set_pca_snps_mask(keep, mean, sd)

@@ -14,6 +14,7 @@ payload = bench.synth_bed_device(torch, n, m, 0, dev)
 torch.cuda.synchronize()
 t_gen = time.perf_counter() - t0
 ctx = gp.Context(0)
+ctx.set_sketch_timing(True)
 t0 = time.perf_counter()
 ctx.load_bed_device(payload.data_ptr(), n, m)
 keep, mean, sd, code = ctx.snp_qc(gp.QcConfig(0.98, 0.01, 1.0))   # HWE off: pooled structured populations fail HWE at this N (Wahlund effect)
