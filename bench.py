@@ -447,6 +447,7 @@ def run_c3(args, torch, gp, dev, pk, pk_src):
                       "h2d_bytes_per_step": int(m * bps), "d2h_bytes_per_step": int(n * K_COMPONENTS * 8 + m * 16)}
     if not args.no_parity:
         sc, ev, _ = ctx.rfit(K_COMPONENTS, OVERSAMPLE, power_iters=POWER_ITERS, seed=RFIT_SEED, want_loadings=False)
+        sc5, ev5, _ = ctx.rfit(K_COMPONENTS, OVERSAMPLE, power_iters=5, seed=RFIT_SEED, want_loadings=False)
         ctx.close()
         ctx = None
         t0 = time.perf_counter()
@@ -454,14 +455,23 @@ def run_c3(args, torch, gp, dev, pk, pk_src):
         gen = gp.Context(dev.index or 0)
         gen.synth_bed_device(payload.data_ptr(), n, m, 0, DATA_SEED, N_POPS, FST, 0.0, FST_GRADE)
         gen.close()
-        ev_x, v_x = exact_pca_f64(torch, payload, n, np.asarray(keep[:m], dtype=bool), mean[:m], sd[:m], K_COMPONENTS)
+        ev_x, v_x = exact_pca_f64(torch, payload, n, np.asarray(keep[:m], dtype=bool), mean[:m], sd[:m], K_COMPONENTS + 1)
         del payload
         torch.cuda.empty_cache()
+        k = K_COMPONENTS
         rec["parity_at_scale"] = {
-            "against": "exact f64 eigen-decomposition of the N x N GRM of the standardized matrix (torch f64, chunked)",
-            "shape": f"{n} x {d_kept}", "eigenvalue_max_rel_err": float(np.max(np.abs(ev / ev_x - 1.0))),
-            "score_subspace_angle_rad": subspace_angle(sc, v_x), "tolerance": "1e-4 relative / 1e-3 rad",
-            "eigenvalue_gap_k_to_k1": None, "seconds": time.perf_counter() - t0}
+            "against": "exact f64 eigen-decomposition of the N x N Gram matrix of the standardized matrix (torch f64, "
+                       "chunked over the decoded .bed payload; no library kernel on that side)",
+            "shape": f"{n} x {d_kept}", "tolerance": "1e-4 relative / 1e-3 rad",
+            "converged_q5": {"eigenvalue_max_rel_err": float(np.max(np.abs(ev5 / ev_x[:k] - 1.0))),
+                             "score_subspace_angle_rad": subspace_angle(sc5, v_x[:, :k])},
+            "benchmark_q%d" % POWER_ITERS: {"eigenvalue_max_rel_err": float(np.max(np.abs(ev / ev_x[:k] - 1.0))),
+                                            "score_subspace_angle_rad": subspace_angle(sc, v_x[:, :k]),
+                                            "leading_8_eigenvalue_max_rel_err": float(np.max(np.abs(ev[:8] / ev_x[:8] - 1.0))),
+                                            "note": "q = 2 is the reference's default: the randomized method itself has not "
+                                                    "converged on the trailing components (Ritz values approach from below, "
+                                                    "geometrically in q); the converged run is the arithmetic check"},
+            "eigenvalue_gap_k_to_k1": float(ev_x[k - 1] / ev_x[k]), "seconds": time.perf_counter() - t0}
     if ctx is not None:
         ctx.close()
     host.free()
@@ -531,41 +541,46 @@ def run_ours(args, rank, world):
     # ---- EigenSNP on the same configuration --------------------------------------------------------
     es = None
     if not args.no_eigensnp:
-        cfg = gp.EigenSnpConfig(target_num_global_pcs=K_COMPONENTS)
-        ctx.set_memory_reserve(gp.binding.eigensnp_workspace_bytes(n, m, nb, cfg))
-        qc = gp.QcConfig(0.98, 0.01, 1.0)                 # HWE off: pooled structured populations fail it
+        try:
+            cfg = gp.EigenSnpConfig(target_num_global_pcs=K_COMPONENTS)
+            ctx.set_memory_reserve(gp.binding.eigensnp_workspace_bytes(n, m, nb, cfg))
+            qc = gp.QcConfig(0.98, 0.01, 1.0)                 # HWE off: pooled structured populations fail it
 
-        def es_ingest():
-            return ctx.ingest_bed(host.ptr, n, m, qc=qc, out=stats_out)
+            def es_ingest():
+                return ctx.ingest_bed(host.ptr, n, m, qc=qc, out=stats_out)
 
-        _, _, _, _, d_es = es_ingest()
-        edges = np.linspace(0, d_es, nb + 1).astype(np.int64)
-        blocks = [np.arange(edges[i], edges[i + 1], dtype=np.uint64) for i in range(nb)]
-        es_out = (np.ones((n, K_COMPONENTS), dtype=np.float32), np.ones(K_COMPONENTS, dtype=np.float64),
-                  np.ones((d_es, K_COMPONENTS), dtype=np.float32))
-        ctx.eigensnp(blocks, cfg, out=es_out)
-        reps = 3
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        ctx.reset_launch_count()
-        t0 = time.perf_counter()
-        for _ in range(reps):
-            sc_es, ev_es, _ = ctx.eigensnp(blocks, cfg, out=es_out)
-        t_es = (time.perf_counter() - t0) / reps
-        es_launches = ctx.launch_count // reps
-        t_es, = max_over_ranks(torch, dist, dev, world, [t_es])
-        es = {"workload": f"EigenSNP k={K_COMPONENTS}, {nb_total} LD blocks, effective defaults of src/main.rs:545-588",
-              "resident_wall_s": t_es, "gpu_launches": int(es_launches), "resident_snp_rows_frac": ctx.resident_snp_rows / max(d_es, 1),
-              "eigenvalues_head": [float(x) for x in ev_es[:3]]}
-        if not args.no_e2e:
-            def e2e_es():
-                es_ingest()
-                ctx.eigensnp(blocks, cfg, out=es_out)
-            te_es = e2e_loop(torch, dist, dev, world, e2e_es, args.e2e_steps)
-            es["e2e"] = {"pca_wall_s": te_es, "ms_per_step": te_es * 1e3, "steps": args.e2e_steps,
-                         "h2d_bytes_per_step": int(m_total * bps),
-                         "d2h_bytes_per_step": int(world * n * K_COMPONENTS * 4 + m_total * (16 + K_COMPONENTS * 4))}
+            _, _, _, _, d_es = es_ingest()
+            edges = np.linspace(0, d_es, nb + 1).astype(np.int64)
+            blocks = [np.arange(edges[i], edges[i + 1], dtype=np.uint64) for i in range(nb)]
+            es_out = (np.ones((n, K_COMPONENTS), dtype=np.float32), np.ones(K_COMPONENTS, dtype=np.float64),
+                      np.ones((d_es, K_COMPONENTS), dtype=np.float32))
+            ctx.eigensnp(blocks, cfg, out=es_out)
+            reps = 3
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            ctx.reset_launch_count()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                sc_es, ev_es, _ = ctx.eigensnp(blocks, cfg, out=es_out)
+            t_es = (time.perf_counter() - t0) / reps
+            es_launches = ctx.launch_count // reps
+            t_es, = max_over_ranks(torch, dist, dev, world, [t_es])
+            es = {"workload": f"EigenSNP k={K_COMPONENTS}, {nb_total} LD blocks, effective defaults of src/main.rs:545-588",
+                  "resident_wall_s": t_es, "gpu_launches": int(es_launches), "resident_snp_rows_frac": ctx.resident_snp_rows / max(d_es, 1),
+                  "eigenvalues_head": [float(x) for x in ev_es[:3]]}
+            if not args.no_e2e:
+                def e2e_es():
+                    es_ingest()
+                    ctx.eigensnp(blocks, cfg, out=es_out)
+                te_es = e2e_loop(torch, dist, dev, world, e2e_es, args.e2e_steps)
+                es["e2e"] = {"pca_wall_s": te_es, "ms_per_step": te_es * 1e3, "steps": args.e2e_steps,
+                             "h2d_bytes_per_step": int(m_total * bps),
+                             "d2h_bytes_per_step": int(world * n * K_COMPONENTS * 4 + m_total * (16 + K_COMPONENTS * 4))}
+        except Exception as e:       # the headline record must not be lost to the second mode
+            es = {"error": repr(e)}
+            if world > 1:
+                raise
     ctx.close()
     host.free()
     torch.cuda.empty_cache()

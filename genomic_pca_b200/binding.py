@@ -87,6 +87,8 @@ _sig("gpca_set_sketch_engine", C.c_int, C.c_void_p, C.c_int)
 _sig("gpca_set_batch_blocks", C.c_int, C.c_void_p, C.c_int)
 _sig("gpca_ingest_bed_file", C.c_int, C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p,
      C.c_double, _u8p, _f32p, _f32p, _u8p, _u64p)
+_sig("gpca_ingest_bed_file_rows", C.c_int, C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p,
+     C.c_uint64, C.c_void_p, C.c_double, _u8p, _f32p, _f32p, _u8p, _u64p)
 _sig("gpca_synth_bed_device", C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32,
      C.c_double, C.c_double, C.c_double)
 _sig("gpca_sketch_stats", C.c_int, C.c_void_p, _f64p, _f64p, _u64p, C.c_int)

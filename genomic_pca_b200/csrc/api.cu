@@ -713,7 +713,7 @@ static int ingest_core(gpca_ctx* c, const uint8_t* host_payload, int fd, uint64_
         res = M;
         win = 0;
       }
-      if (gt_full + std::min<size_t>(gs_full, win * c->Gs.pitch) + (1ull << 30) > avail)
+      if (gt_full + std::min<size_t>(gs_full, win * c->Gs.pitch) > avail)
         return fail(c, GPCA_ERR_OOM, "ingest: the sample-major matrix does not fit on this device (shard the SNPs over more GPUs)");
     }
     const size_t gs_bytes = win ? (res + win) * c->Gs.pitch : gs_full;
@@ -988,27 +988,41 @@ extern "C" int gpca_ingest_bed(gpca_ctx* c, const uint8_t* host_payload, uint64_
 }
 
 // Same pass straight from a PLINK .bed file: chunks are read into pinned buffers (never the whole file in host memory)
-// and the read of chunk q overlaps with the transfer / counting / QC of the chunks before it.
-extern "C" int gpca_ingest_bed_file(gpca_ctx* c, const char* bed_path, uint64_t n_in, uint64_t n_snps,
-                                    const int64_t* keep_samples, uint64_t n_keep, const gpca_qc_cfg* cfg,
-                                    double vcf_maf_threshold, uint8_t* keep_out, float* mean_out, float* sd_out,
-                                    uint8_t* fail_code_out, uint64_t* n_pca_out) {
+// and the read of chunk q overlaps with the transfer / counting / QC of the chunks before it.  The _rows form takes
+// rows [first_row, first_row + n_rows) of the file: one shard of a multi-GPU run (outputs and the ingest mask are
+// indexed by the row inside the range).
+extern "C" int gpca_ingest_bed_file_rows(gpca_ctx* c, const char* bed_path, uint64_t n_in, uint64_t n_snps_in_file,
+                                         uint64_t first_row, uint64_t n_rows, const int64_t* keep_samples,
+                                         uint64_t n_keep, const gpca_qc_cfg* cfg, double vcf_maf_threshold,
+                                         uint8_t* keep_out, float* mean_out, float* sd_out, uint8_t* fail_code_out,
+                                         uint64_t* n_pca_out) {
   CHECK_CTX(c);
   if (!bed_path) return fail(c, GPCA_ERR_INVALID, "null path");
+  if (first_row > n_snps_in_file || n_rows > n_snps_in_file - first_row)
+    return fail(c, GPCA_ERR_INVALID, "row range outside the .bed file");
   const int fd = open(bed_path, O_RDONLY);
   if (fd < 0) return fail(c, GPCA_ERR_INVALID, std::string("Failed to open BED file '") + bed_path + "'");
   uint8_t magic[3] = {0, 0, 0};
   struct stat st;
   int rc = GPCA_OK;
+  const uint64_t in_pitch = (n_in + 3) / 4;
   if (pread(fd, magic, 3, 0) != 3 || magic[0] != 0x6c || magic[1] != 0x1b || magic[2] != 0x01)
     rc = fail(c, GPCA_ERR_INVALID, "not a SNP-major PLINK .bed (magic 6c 1b 01 expected)");
-  else if (fstat(fd, &st) != 0 || (uint64_t)st.st_size != 3 + ((n_in + 3) / 4) * n_snps)
+  else if (fstat(fd, &st) != 0 || (uint64_t)st.st_size != 3 + in_pitch * n_snps_in_file)
     rc = fail(c, GPCA_ERR_INVALID, "BED size does not match BIM/FAM");
   else
-    rc = ingest_core(c, nullptr, fd, 3, n_in, n_snps, keep_samples, n_keep, cfg, vcf_maf_threshold, keep_out, mean_out,
-                     sd_out, fail_code_out, n_pca_out);
+    rc = ingest_core(c, nullptr, fd, 3 + first_row * in_pitch, n_in, n_rows, keep_samples, n_keep, cfg,
+                     vcf_maf_threshold, keep_out, mean_out, sd_out, fail_code_out, n_pca_out);
   close(fd);
   return rc;
+}
+
+extern "C" int gpca_ingest_bed_file(gpca_ctx* c, const char* bed_path, uint64_t n_in, uint64_t n_snps,
+                                    const int64_t* keep_samples, uint64_t n_keep, const gpca_qc_cfg* cfg,
+                                    double vcf_maf_threshold, uint8_t* keep_out, float* mean_out, float* sd_out,
+                                    uint8_t* fail_code_out, uint64_t* n_pca_out) {
+  return gpca_ingest_bed_file_rows(c, bed_path, n_in, n_snps, 0, n_snps, keep_samples, n_keep, cfg, vcf_maf_threshold,
+                                   keep_out, mean_out, sd_out, fail_code_out, n_pca_out);
 }
 
 // ---- pinned host buffers for large payloads ----------------------------------------------------------------------

@@ -222,7 +222,9 @@ extern "C" uint64_t gpca_eigensnp_workspace_bytes(uint64_t N, uint64_t D, uint64
   b += Ns * round_up((D + 3) / 4 + 64, 128) + D * round_up((Ns + 3) / 4, 128);   // subset copies, both orientations
   b += n_blocks * Ns * LD * 4 + D * (LD + cpb + 32) * 4;                   // per-block iterates, bases, grouped operand
   b += N * lg * 4 * 4 + R * lg * 4 * 2 + D * lg * 4;                       // global iterates, scores, loadings
-  b += (D + N) * 64 * 2 + (3ull << 30);                                    // operand images, split-K partials, slack
+  b += n_blocks * round_up(Ns, 256) * 64 + (D + 64 * n_blocks + N) * 64 * 2;   // operand images of the per-block passes
+  b += n_blocks * (3 * 1024 + 64) * 8 * 2 + (D + N) * 32 * 4 * 4;          // per-block small matrices, split-K partials
+  b += 6ull << 30;                                                         // Gram partials, staging, allocator slack
   return b;
 }
 

@@ -184,6 +184,13 @@ int gpca_ingest_bed_file(gpca_ctx* ctx, const char* bed_path, uint64_t n_in_samp
                          const int64_t* keep_samples, uint64_t n_keep, const gpca_qc_cfg* cfg, double vcf_maf_threshold,
                          uint8_t* keep, float* mean, float* sd, uint8_t* fail_code, uint64_t* n_pca_out);
 
+/* Rows [first_row, first_row + n_rows) of the file only -- the shard of one GPU of a multi-GPU run; keep / mean / sd /
+ * fail_code (n_rows each) and the ingest mask are indexed by the row inside the range. */
+int gpca_ingest_bed_file_rows(gpca_ctx* ctx, const char* bed_path, uint64_t n_in_samples, uint64_t n_snps_in_file,
+                              uint64_t first_row, uint64_t n_rows, const int64_t* keep_samples, uint64_t n_keep,
+                              const gpca_qc_cfg* cfg, double vcf_maf_threshold, uint8_t* keep, float* mean, float* sd,
+                              uint8_t* fail_code, uint64_t* n_pca_out);
+
 /* ---- the accessor the GPU path makes unnecessary, kept for parity ---------------------- */
 /* get_standardized_snp_sample_block (src/prepare.rs:1839-2022): out[n_ids x n_samp] row-major
  * f32, z = fma(x, 1/sd, -mean/sd); sd < 1e-9 -> 0; any missing call -> GPCA_ERR_MISSING. */

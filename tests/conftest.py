@@ -22,6 +22,18 @@ def golden_rows():
 
 
 @pytest.fixture(scope="session")
+def golden_full():
+    """The whole chr22_subset50 fixture (64 samples x 1,066,557 SNPs) with the keep mask that the reference's own QC
+    ladder (tests/pca.py:86-105) gives for it -- tests/golden/make_golden.py."""
+    z = np.load(os.path.join(GOLDEN, "chr22_subset50_full.npz"))
+    d = {k: z[k] for k in z.files}
+    m = d["payload"].shape[0]
+    d["keep_ref"] = np.unpackbits(d["keep_ref_bits"])[:m].astype(bool)
+    d["keep_rust"] = np.unpackbits(d["keep_rust_bits"])[:m].astype(bool)
+    return d
+
+
+@pytest.fixture(scope="session")
 def gpu_ctx():
     import genomic_pca_b200 as gp
     ctx = gp.Context(0)

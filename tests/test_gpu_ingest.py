@@ -230,3 +230,21 @@ def test_ingest_from_bed_file_equals_memory_ingest(gpu_ctx, tmp_path, monkeypatc
         ctx2.ingest_bed_file(str(bad), n, m, qc=cfg)                       # individual-major / wrong magic
     with pytest.raises(gp.GpcaError):
         ctx2.ingest_bed_file(str(tmp_path / "missing.bed"), n, m, qc=cfg)
+
+
+def test_whole_fixture_qc_mask_equals_reference_ladder(golden_full):
+    """Every variant of the reference's bundled fixture through the streaming ingest (counts on the GPU, f64 ladder on
+    host threads): the keep mask must be the one the reference's own ladder (tests/pca.py:86-105) produced -- all
+    1,066,557 decisions, 177,570 kept."""
+    import genomic_pca_b200 as gp
+    n = int(golden_full["n_samples"])
+    payload = golden_full["payload"]
+    ctx = gp.Context(0)
+    keep, mean, sd, code, d = ctx.ingest_bed(payload, n, payload.shape[0], qc=gp.QcConfig(0.98, 0.01, 1e-6))
+    assert d == 177570
+    assert np.array_equal(keep, golden_full["keep_ref"])
+    # and through the three-call path
+    ctx.load_bed(payload, n, payload.shape[0])
+    keep3, *_ = ctx.snp_qc(gp.QcConfig(0.98, 0.01, 1e-6))
+    assert np.array_equal(keep3, golden_full["keep_ref"])
+    ctx.close()
