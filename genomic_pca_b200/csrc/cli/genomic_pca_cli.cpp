@@ -43,6 +43,7 @@ struct Args {
   bool eigensnp = false;
   bool write_eigenvalues = false;
   uint32_t rfit_power_iters = 2;
+  long gpus = 1;            // (extension) GPUs to shard the SNPs / LD blocks over; 0 = every visible one
   gpca_qc_cfg qc{0.98, 0.01, 1e-6};
   gpca_eigensnp_cfg es;
 };
@@ -59,7 +60,7 @@ void usage() {
           "Genomic PCA Tool from VCF or BED/LD-block files (B200-native hot path).\n\n"
           "Usage: genomic_pca --out <OUTPUT_PREFIX> [OPTIONS]\n\n"
           "  -o, --out <PREFIX>            Output file prefix (required)\n"
-          "  -t, --threads <N>             accepted for compatibility (host-side loops use all cores)\n"
+          "  -t, --threads <N>             host threads for the host-side stages (default: all cores, split over the GPUs)\n"
           "      --log-level <LEVEL>       accepted for compatibility\n"
           "  -d, --vcf-dir <DIR>           Directory containing VCF files (required unless --eigensnp)\n"
           "  -k, --components <K>          Number of principal components (VCF workflow)\n"
@@ -77,7 +78,9 @@ void usage() {
           "      --eigensnp-local-power-iter <N> (2)  --eigensnp-seed <N> (2025)\n"
           "      --eigensnp-snp-strip-size <N> (2000)  --eigensnp-refine-passes <N> (1)\n"
           "      --eigensnp-collect-diagnostics\n"
-          "      --write-eigenvalues       (extension) also write the rfit eigenvalues\n");
+          "      --write-eigenvalues       (extension) also write the rfit eigenvalues\n"
+          "      --gpus <N>                (extension) shard the SNPs / whole LD blocks over N GPUs, NCCL exchange of the\n"
+          "                                sample-side sketch (0 = every visible GPU; default 1)\n");
 }
 
 Args parse(int argc, char** argv) {
@@ -129,6 +132,7 @@ Args parse(int argc, char** argv) {
     else if (f == "--eigensnp-refine-passes") a.es.refine_pass_count = (uint32_t)atol(val().c_str());
     else if (f == "--eigensnp-collect-diagnostics") a.es.collect_diagnostics = 1;
     else if (f == "--write-eigenvalues") a.write_eigenvalues = true;
+    else if (f == "--gpus") a.gpus = atol(val().c_str());
     else die("unexpected argument '" + f + "' (see --help)");
   }
   if (a.out.empty()) die("the following required arguments were not provided: --out <OUTPUT_PREFIX>");
@@ -225,6 +229,59 @@ void write_eigenvalues(const std::string& prefix, const std::vector<double>& ev)
 
 void check(gpca_ctx* ctx, int rc, const char* what) {
   if (rc != GPCA_OK) die(std::string(what) + " failed: " + gpca_last_error(ctx));
+}
+
+// ---- multi-GPU plumbing: one context per GPU, one host thread per context (src/main.rs has nothing to mirror: the
+// reference is a single CPU process).  The contexts are created first (device g for g = 0, 1, ... until gpca_init
+// refuses), joined into one NCCL communicator by the library, and every stage of a workflow runs as one thread per shard.
+struct Shards {
+  std::vector<gpca_ctx*> ctx;
+  int n() const { return (int)ctx.size(); }
+};
+
+Shards open_shards(long want, long threads) {
+  Shards s;
+  const long cap = want > 0 ? want : 1024;
+  for (long g = 0; g < cap; ++g) {
+    gpca_ctx* c = nullptr;
+    if (gpca_init(&c, (int)g) != GPCA_OK) break;
+    s.ctx.push_back(c);
+  }
+  if (s.ctx.empty()) die("no sm_100 (B200) GPU available: this build has no CPU fallback");
+  if (want > 0 && (long)s.ctx.size() < want)
+    die("--gpus " + std::to_string(want) + " requested but only " + std::to_string(s.ctx.size()) + " B200 GPU(s) are visible");
+  unsigned hw = std::thread::hardware_concurrency();
+  if (hw == 0) hw = 4;
+  const unsigned per = (unsigned)std::max<long>(1, (threads > 0 ? threads : (long)hw) / (long)s.ctx.size());
+  for (gpca_ctx* c : s.ctx) gpca_set_host_threads(c, per);
+  if (s.n() > 1) {
+    uint8_t id[GPCA_COMM_ID_BYTES];
+    if (gpca_comm_unique_id(id) != GPCA_OK) die("NCCL is not available (libnccl.so.2): cannot use more than one GPU");
+    std::vector<std::thread> th;
+    std::vector<int> rc(s.n(), 0);
+    for (int g = 0; g < s.n(); ++g) th.emplace_back([&, g] { rc[g] = gpca_comm_init(s.ctx[g], id, g, s.n()); });
+    for (auto& t : th) t.join();
+    for (int g = 0; g < s.n(); ++g) check(s.ctx[g], rc[g], "gpca_comm_init");
+    info("Sharding over " + std::to_string(s.n()) + " GPUs (NCCL exchange issued by the library).");
+  }
+  return s;
+}
+
+// fn(g) on one thread per shard; a failure on any shard ends the run with its message
+template <class F>
+void for_each_shard(const Shards& s, F&& fn) {
+  if (s.n() == 1) {
+    fn(0);
+    return;
+  }
+  std::vector<std::thread> th;
+  for (int g = 0; g < s.n(); ++g) th.emplace_back([&fn, g] { fn(g); });
+  for (auto& t : th) t.join();
+}
+
+void close_shards(Shards& s) {
+  for (gpca_ctx* c : s.ctx) gpca_destroy(c);
+  s.ctx.clear();
 }
 
 // ---------------------------------------------------------------------------------------------- VCF workflow
@@ -390,14 +447,28 @@ int run_vcf(const Args& a) {
   info("Aggregated " + std::to_string(dvar) + " variants in total across all VCFs.");
   if (a.components == 0) die("Number of components (-k) must be > 0.");                              // main.rs:607
   if (n < 2) die("PCA requires at least 2 samples, found " + std::to_string(n) + ".");               // main.rs:614
-  gpca_ctx* ctx = nullptr;
-  if (gpca_init(&ctx, 0) != GPCA_OK) die("no sm_100 (B200) GPU available: this build has no CPU fallback");
-  check(ctx, gpca_load_u8_variant_major(ctx, dosage.data(), n, dvar), "load");
-  std::vector<uint8_t> keep(dvar);
-  std::vector<float> mean(dvar), sd(dvar);
-  check(ctx, gpca_vcf_maf_filter(ctx, maf_thr, keep.data(), mean.data(), sd.data()), "maf filter");
+  // Variants are split into contiguous ranges, one per GPU; every shard filters its range, and the rfit passes exchange
+  // the N x l sketch (the scores are the same on every shard; shard 0's copy is written).
+  Shards sh = open_shards(a.gpus, a.threads);
+  const int G = sh.n();
+  std::vector<uint64_t> v0(G + 1);
+  for (int g = 0; g <= G; ++g) v0[g] = dvar * (uint64_t)g / (uint64_t)G;
+  std::vector<uint64_t> kept(G, 0);
+  for_each_shard(sh, [&](int g) {
+    gpca_ctx* ctx = sh.ctx[g];
+    const uint64_t dv = v0[g + 1] - v0[g];
+    check(ctx, gpca_load_u8_variant_major(ctx, dosage.data() + v0[g] * n, n, dv), "load");
+    std::vector<uint8_t> keep(dv);
+    std::vector<float> mean(dv), sd(dv);
+    check(ctx, gpca_vcf_maf_filter(ctx, maf_thr, keep.data(), mean.data(), sd.data()), "maf filter");
+    check(ctx, gpca_set_pca_snps_mask(ctx, keep.data(), mean.data(), sd.data(), &kept[g]), "set_pca_snps");
+  });
   uint64_t d_kept = 0;
-  check(ctx, gpca_set_pca_snps_mask(ctx, keep.data(), mean.data(), sd.data(), &d_kept), "set_pca_snps");
+  std::vector<uint64_t> koff(G, 0);
+  for (int g = 0; g < G; ++g) {
+    koff[g] = d_kept;
+    d_kept += kept[g];
+  }
   uint32_t k = (uint32_t)a.components;
   const uint64_t maxk = std::min<uint64_t>(n, d_kept);
   if (k > maxk) {
@@ -407,16 +478,27 @@ int run_vcf(const Args& a) {
   std::vector<double> scores(n * k), ev(k);
   uint32_t k_out = 0;
   const auto t0 = std::chrono::steady_clock::now();
-  check(ctx, gpca_rfit(ctx, k, 10 /* main.rs:636 */, a.rfit_power_iters, a.rfit_seed, a.has_seed ? 1 : 0, scores.data(),
-                       ev.data(), nullptr, &k_out), "rfit");
+  for_each_shard(sh, [&](int g) {
+    gpca_ctx* ctx = sh.ctx[g];
+    if (G > 1) check(ctx, gpca_set_shard(ctx, koff[g], d_kept), "set_shard");
+    std::vector<double> sc_g, ev_g;
+    if (g != 0) {
+      sc_g.resize(n * k);
+      ev_g.resize(k);
+    }
+    uint32_t ko = 0;
+    check(ctx, gpca_rfit(ctx, k, 10 /* main.rs:636 */, a.rfit_power_iters, a.rfit_seed, a.has_seed ? 1 : 0,
+                         g == 0 ? scores.data() : sc_g.data(), g == 0 ? ev.data() : ev_g.data(), nullptr, &ko), "rfit");
+    if (g == 0) k_out = ko;
+  });
   const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-  info("VCF PCA computation (rfit on GPU) completed in " + std::to_string(ms) + " ms.");
+  info("VCF PCA computation (rfit on " + std::to_string(G) + " GPU(s)) completed in " + std::to_string(ms) + " ms.");
   make_parent_dirs(a.out);
   write_pcs<double>(a.out, "vcf.pca.tsv", samples, scores.data(), n, k_out);
   ev.resize(k_out);
   write_eigenvalues(a.out, a.write_eigenvalues ? ev : std::vector<double>());   // reference writes a header-only file (main.rs:676)
   warn("Loadings output for VCF-based PCA is currently skipped (as in the reference, main.rs:233).");
-  gpca_destroy(ctx);
+  close_shards(sh);
   return 0;
 }
 
@@ -489,24 +571,7 @@ int run_eigensnp(const Args& a) {
   } else {
     warn("No external sample ID list provided; using all " + std::to_string(n_fam) + " initial samples.");
   }
-  gpca_ctx* ctx = nullptr;
-  if (gpca_init(&ctx, 0) != GPCA_OK) die("no sm_100 (B200) GPU available: this build has no CPU fallback");
-  // load + SNP QC + resident matrices in one streaming pass over the file (prepare.rs:995-1098)
-  std::vector<uint8_t> keep(m);
-  std::vector<float> mean(m), sd(m);
-  uint64_t n_qc_pass = 0;
-  {
-    const int rc = gpca_ingest_bed_file(ctx, a.bed_file.c_str(), n_fam, m, use_keep ? keep_idx.data() : nullptr,
-                                        keep_idx.size(), &a.qc, 0.0, keep.data(), mean.data(), sd.data(), nullptr,
-                                        &n_qc_pass);
-    if (rc != GPCA_OK) die(gpca_last_error(ctx));
-  }
-  const uint64_t n = gpca_num_samples(ctx);
-  std::vector<uint64_t> qidx;
-  for (uint64_t j = 0; j < m; ++j)
-    if (keep[j]) qidx.push_back(j);
-  info("SNP QC & Stats calculation complete. " + std::to_string(qidx.size()) + " / " + std::to_string(m) + " initial SNPs passed all filters.");
-  if (qidx.empty()) die("No SNPs passed all QC filters.");                                // prepare.rs:1020
+  const uint64_t n = use_keep ? keep_idx.size() : n_fam;
   // LD block file (prepare.rs:1565-1607)
   std::vector<std::string> bchr;
   std::vector<int32_t> bstart, bend;
@@ -524,75 +589,182 @@ int run_eigensnp(const Args& a) {
       bend.push_back((int32_t)atol(p[2].c_str()));
     }
   }
-  std::vector<std::string> qchr_s(qidx.size());
-  std::vector<const char*> qchr(qidx.size()), bchr_c(bchr.size());
-  std::vector<int32_t> qbp(qidx.size());
-  for (size_t i = 0; i < qidx.size(); ++i) {
-    qchr_s[i] = normalize_chromosome_name(chrom[qidx[i]]);
-    qchr[i] = qchr_s[i].c_str();
-    qbp[i] = bp[qidx[i]];
-  }
+  std::vector<const char*> bchr_c(bchr.size());
   for (size_t b = 0; b < bchr.size(); ++b) bchr_c[b] = bchr[b].c_str();
-  std::vector<int64_t> pca_pos(qidx.size()), block_of(qidx.size());
-  std::vector<uint64_t> order(std::max<size_t>(bchr.size(), 1));
-  uint64_t n_pca = 0, n_blk = 0;
-  if (gpca_map_snps_to_ld_blocks(qchr.data(), qbp.data(), qidx.size(), bchr_c.data(), bstart.data(), bend.data(), bchr.size(),
-                                 pca_pos.data(), block_of.data(), &n_pca, &n_blk, order.data()) != GPCA_OK)
-    die("LD block mapping failed");
-  if (n_pca == 0) die("No SNPs mapped to LD blocks or all resulting blocks were empty.");  // prepare.rs:1031
-  info("LD Mapping: " + std::to_string(n_pca) + " unique SNPs (D_blocked) mapped to " + std::to_string(n_blk) + " LD blocks.");
-  std::vector<uint64_t> pca_orig;
-  std::vector<float> pmean, psd;
-  std::vector<std::vector<uint64_t>> blocks(n_blk);
-  for (size_t i = 0; i < qidx.size(); ++i)
-    if (pca_pos[i] >= 0) {
-      pca_orig.push_back(qidx[i]);
-      pmean.push_back(mean[qidx[i]]);
-      psd.push_back(sd[qidx[i]]);
-      blocks[block_of[i]].push_back((uint64_t)pca_pos[i]);
+  std::vector<std::string> nchr(m);
+  for (uint64_t j = 0; j < m; ++j) nchr[j] = normalize_chromosome_name(chrom[j]);
+  // SNP -> first matching block (prepare.rs:1447-1463) depends only on chromosome / position, so it is evaluated for
+  // EVERY BIM row before the genotypes are read: rows outside every block never reach the resident matrices (the
+  // ingest mask), and whole blocks can be dealt to the GPUs.  The numbering of PcaSnpIds and the tag-sorted block
+  // lists (prepare.rs:1465-1549) are made from the rows that also pass QC, per shard, after the ingest.
+  auto map_rows = [&](const std::vector<uint64_t>& rows, std::vector<int64_t>& pca_pos, std::vector<int64_t>& block_of,
+                      uint64_t& n_pca, uint64_t& n_blk) {
+    std::vector<const char*> qchr(rows.size());
+    std::vector<int32_t> qbp(rows.size());
+    for (size_t i = 0; i < rows.size(); ++i) {
+      qchr[i] = nchr[rows[i]].c_str();
+      qbp[i] = bp[rows[i]];
     }
-  // the ingest built the resident set from every SNP that passed QC; only when the LD blocks drop some of them is the
-  // set rebuilt from the mapped subset
-  if (n_pca != n_qc_pass) check(ctx, gpca_set_pca_snps(ctx, pca_orig.data(), n_pca, pmean.data(), psd.data()), "set_pca_snps");
-  std::vector<uint64_t> offs(n_blk + 1, 0), flat;
-  for (uint64_t b = 0; b < n_blk; ++b) {
-    offs[b + 1] = offs[b] + blocks[b].size();
-    flat.insert(flat.end(), blocks[b].begin(), blocks[b].end());
+    pca_pos.assign(rows.size(), -1);
+    block_of.assign(rows.size(), -1);
+    std::vector<uint64_t> order(std::max<size_t>(bchr.size(), 1));
+    if (gpca_map_snps_to_ld_blocks(qchr.data(), qbp.data(), rows.size(), bchr_c.data(), bstart.data(), bend.data(),
+                                   bchr.size(), pca_pos.data(), block_of.data(), &n_pca, &n_blk, order.data()) != GPCA_OK)
+      die("LD block mapping failed");
+  };
+  std::vector<uint64_t> all_rows(m);
+  for (uint64_t j = 0; j < m; ++j) all_rows[j] = j;
+  std::vector<int64_t> pos_all, blk_all;
+  uint64_t n_in_blocks = 0, n_blk_all = 0;
+  map_rows(all_rows, pos_all, blk_all, n_in_blocks, n_blk_all);
+  if (n_in_blocks == 0) die("No SNPs mapped to LD blocks or all resulting blocks were empty.");  // prepare.rs:1031
+
+  Shards sh = open_shards(a.gpus, a.threads);
+  const int G = sh.n();
+  // whole blocks to GPUs: blocks in the order of their first BIM row, cut where the running SNP count passes g/G
+  std::vector<uint64_t> blk_first(n_blk_all, m), blk_count(n_blk_all, 0);
+  for (uint64_t j = 0; j < m; ++j)
+    if (blk_all[j] >= 0) {
+      blk_first[blk_all[j]] = std::min<uint64_t>(blk_first[blk_all[j]], j);
+      blk_count[blk_all[j]]++;
+    }
+  std::vector<uint64_t> by_row(n_blk_all);
+  for (uint64_t b = 0; b < n_blk_all; ++b) by_row[b] = b;
+  std::sort(by_row.begin(), by_row.end(), [&](uint64_t x, uint64_t y) { return blk_first[x] < blk_first[y]; });
+  std::vector<int> shard_of_blk(n_blk_all, 0);
+  {
+    uint64_t run = 0;
+    for (uint64_t q = 0; q < n_blk_all; ++q) {
+      const uint64_t b = by_row[q];
+      shard_of_blk[b] = (int)std::min<uint64_t>(G - 1, run * (uint64_t)G / n_in_blocks);
+      run += blk_count[b];
+    }
   }
+  struct ShardData {
+    uint64_t row0 = 0, row1 = 0, n_blocks = 0;
+    std::vector<uint8_t> mask, keep;
+    std::vector<float> mean, sd;
+    uint64_t n_kept = 0, id_offset = 0;
+    std::vector<uint64_t> pca_orig;                 // BIM row of every local PcaSnpId
+    std::vector<uint64_t> offs, flat;               // LD blocks, local ids, tag-sorted
+    std::vector<float> scores, loadings;
+    std::vector<double> ev;
+    uint32_t k_out = 0;
+  };
+  std::vector<ShardData> sd_(G);
+  for (int g = 0; g < G; ++g) sd_[g].row0 = m;
+  for (uint64_t j = 0; j < m; ++j)
+    if (blk_all[j] >= 0) {
+      ShardData& d = sd_[shard_of_blk[blk_all[j]]];
+      d.row0 = std::min(d.row0, j);
+      d.row1 = std::max(d.row1, j + 1);
+    }
+  for (int g = 0; g < G; ++g) {
+    ShardData& d = sd_[g];
+    if (d.row1 <= d.row0) die("fewer LD blocks with SNPs than GPUs: use a smaller --gpus");
+    const uint64_t nr = d.row1 - d.row0;
+    d.mask.assign(nr, 0);
+    std::set<int64_t> blks;
+    for (uint64_t j = d.row0; j < d.row1; ++j)
+      if (blk_all[j] >= 0 && shard_of_blk[blk_all[j]] == g) {
+        d.mask[j - d.row0] = 1;
+        blks.insert(blk_all[j]);
+      }
+    d.n_blocks = blks.size();
+    d.keep.resize(nr);
+    d.mean.resize(nr);
+    d.sd.resize(nr);
+  }
+  // load + SNP QC + resident matrices in one streaming pass over each shard's rows of the file (prepare.rs:995-1098);
+  // the memory the EigenSNP driver will need is left free (decides whether both orientations stay resident)
+  for_each_shard(sh, [&](int g) {
+    gpca_ctx* ctx = sh.ctx[g];
+    ShardData& d = sd_[g];
+    const uint64_t nr = d.row1 - d.row0;
+    check(ctx, gpca_set_memory_reserve(ctx, gpca_eigensnp_workspace_bytes(n, nr, d.n_blocks, &a.es)), "memory reserve");
+    check(ctx, gpca_set_ingest_mask(ctx, d.mask.data(), nr), "ingest mask");
+    const int rc = gpca_ingest_bed_file_rows(ctx, a.bed_file.c_str(), n_fam, m, d.row0, nr,
+                                             use_keep ? keep_idx.data() : nullptr, keep_idx.size(), &a.qc, 0.0,
+                                             d.keep.data(), d.mean.data(), d.sd.data(), nullptr, &d.n_kept);
+    if (rc != GPCA_OK) die(gpca_last_error(ctx));
+  });
+  uint64_t n_pca = 0, n_blk = 0;
+  for (int g = 0; g < G; ++g) {
+    ShardData& d = sd_[g];
+    d.id_offset = n_pca;
+    std::vector<uint64_t> rows;
+    for (uint64_t t = 0; t < d.keep.size(); ++t)
+      if (d.keep[t]) rows.push_back(d.row0 + t);
+    std::vector<int64_t> pca_pos, block_of;
+    uint64_t np = 0, nb = 0;
+    map_rows(rows, pca_pos, block_of, np, nb);
+    if (np != rows.size()) die("internal: a SNP that passed the ingest mask lies in no LD block");
+    std::vector<std::vector<uint64_t>> blocks(nb);
+    for (size_t i = 0; i < rows.size(); ++i) blocks[block_of[i]].push_back((uint64_t)pca_pos[i]);
+    d.pca_orig = rows;
+    d.offs.assign(nb + 1, 0);
+    for (uint64_t b = 0; b < nb; ++b) {
+      d.offs[b + 1] = d.offs[b] + blocks[b].size();
+      d.flat.insert(d.flat.end(), blocks[b].begin(), blocks[b].end());
+    }
+    n_pca += np;
+    n_blk += nb;
+  }
+  info("SNP QC & Stats calculation complete. " + std::to_string(n_pca) + " / " + std::to_string(m) +
+       " initial SNPs passed all filters and lie in an LD block.");
+  if (n_pca == 0) die("No SNPs passed all QC filters.");                                  // prepare.rs:1020
+  info("LD Mapping: " + std::to_string(n_pca) + " unique SNPs (D_blocked) mapped to " + std::to_string(n_blk) + " LD blocks.");
   const uint32_t k = a.es.target_num_global_pcs;
-  std::vector<float> scores(n * k), loadings(n_pca * k);
-  std::vector<double> ev(k);
-  uint32_t k_out = 0;
   const auto t0 = std::chrono::steady_clock::now();
-  check(ctx, gpca_eigensnp(ctx, &a.es, offs.data(), n_blk, flat.data(), scores.data(), ev.data(), loadings.data(), &k_out), "eigensnp");
+  for_each_shard(sh, [&](int g) {
+    gpca_ctx* ctx = sh.ctx[g];
+    ShardData& d = sd_[g];
+    if (G > 1) check(ctx, gpca_set_shard(ctx, d.id_offset, n_pca), "set_shard");
+    d.scores.resize(n * k);
+    d.loadings.resize(d.n_kept * k);
+    d.ev.resize(k);
+    check(ctx, gpca_eigensnp(ctx, &a.es, d.offs.data(), d.offs.size() - 1, d.flat.data(), d.scores.data(), d.ev.data(),
+                             d.loadings.data(), &d.k_out), "eigensnp");
+  });
   const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   info("EigenSNP PCA algorithm completed in " + std::to_string(ms) + " ms.");
-  // outputs (main.rs:382-408)
+  const uint32_t k_out = sd_[0].k_out;
+  // outputs (main.rs:382-408); the scores and eigenvalues are the same on every shard
   make_parent_dirs(a.out);
   std::vector<std::string> names;
   if (use_keep) for (int64_t i : keep_idx) names.push_back(iids[i]);
   else names = iids;
-  write_pcs<float>(a.out, "eigensnp.pca.tsv", names, scores.data(), n, k_out);
-  ev.resize(k_out);
+  write_pcs<float>(a.out, "eigensnp.pca.tsv", names, sd_[0].scores.data(), n, k_out);
+  std::vector<double> ev(sd_[0].ev.begin(), sd_[0].ev.begin() + k_out);
   write_eigenvalues(a.out, ev);
   if (k_out > 0) {
+    // loadings rows in increasing BIM index (PcaSnpId order, prepare.rs:1465-1486): the shards' row ranges are merged
+    struct Ref { uint64_t orig; int g; uint64_t local; };
+    std::vector<Ref> refs;
+    refs.reserve(n_pca);
+    for (int g = 0; g < G; ++g)
+      for (uint64_t i = 0; i < sd_[g].pca_orig.size(); ++i) refs.push_back({sd_[g].pca_orig[i], g, i});
+    if (!std::is_sorted(refs.begin(), refs.end(), [](const Ref& x, const Ref& y) { return x.orig < y.orig; }))
+      std::sort(refs.begin(), refs.end(), [](const Ref& x, const Ref& y) { return x.orig < y.orig; });
     FILE* f = create_output(a.out, "eigensnp.loadings.tsv");
     fputs("VariantID\tChrom\tPos", f);
     for (uint32_t j = 1; j <= k_out; ++j) fprintf(f, "\tPC%u_loading", j);
     fputc('\n', f);
     write_rows_parallel(f, n_pca, 32 + 12 * (size_t)k_out, [&](uint64_t i, std::string& b) {
-      const uint64_t o = pca_orig[i];
+      const Ref& r = refs[i];
+      const uint64_t o = r.orig;
       b += sid[o];
       b += '\t';
       b += chrom[o];
       b += '\t';
       b += std::to_string((unsigned long long)(uint64_t)bp[o]);
-      for (uint32_t j = 0; j < k_out; ++j) append_f6(b, (double)loadings[i * k_out + j]);
+      const float* row = sd_[r.g].loadings.data() + r.local * k_out;
+      for (uint32_t j = 0; j < k_out; ++j) append_f6(b, (double)row[j]);
       b += '\n';
     });
     fclose(f);
   }
-  gpca_destroy(ctx);
+  close_shards(sh);
   return 0;
 }
 

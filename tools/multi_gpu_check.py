@@ -1,4 +1,5 @@
-"""Sharded (one process per GPU, NCCL) rfit and EigenSNP against the same computation on one GPU.
+"""Sharded (one process per GPU, the library's own NCCL communicator) rfit and EigenSNP against the same computation on
+one GPU.
 Run:  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/multi_gpu_check.py
 Every rank loads its contiguous shard of SNPs (whole LD blocks); rank 0 also runs the unsharded problem and compares:
 eigenvalues 1e-4 relative, score subspace angle < 1e-3 rad (the north-star tolerances)."""
@@ -38,16 +39,21 @@ def blocks_for(d, nblk):
 
 
 ctx = gp.Context(local)
-ctx.set_allreduce(bench.make_allreduce_hook(torch, dist, dev))
+box = [gp.binding.comm_unique_id() if rank == 0 else None]       # torch.distributed only carries the id bytes
+dist.broadcast_object_list(box, src=0)
+ctx.comm_init(box[0], rank, world)
+assert ctx.comm_world == world
 ctx.set_shard(rank * m_shard, world * m_shard)
 d = load(ctx, rank * m_shard, m_shard)
 assert d == m_shard
 sc_r, ev_r, _ = ctx.rfit(8, 10, power_iters=2, seed=42, want_loadings=False)
 cfg = gp.EigenSnpConfig(target_num_global_pcs=6, min_subset_size=1500, max_subset_size=3000, subset_factor=0.4)
 sc_e, ev_e, ld_e = ctx.eigensnp(blocks_for(d, nblk_shard), cfg)
+n_coll = ctx.collective_count
+sc_n, ev_n, _ = ctx.rfit(8, 10, power_iters=2, seed=None, want_loadings=False)     # entropy seed: broadcast from rank 0
 ctx.close()
 dist.barrier()
-out = {"world": world, "n": n, "m_shard": m_shard}
+out = {"world": world, "n": n, "m_shard": m_shard, "collectives": n_coll}
 if rank == 0:
     full = gp.Context(local)
     dfull = load(full, 0, world * m_shard)
@@ -62,7 +68,8 @@ if rank == 0:
     out["eigensnp_ev_relerr"] = float(np.abs(ev_e / ev1 - 1).max())
     out["eigensnp_angle"] = float(pca.subspace_angle(sc_e, sc1))
     out["eigensnp_loadings_angle_shard0"] = float(pca.subspace_angle(ld_e, ld1[:m_shard]))
-    out["ok"] = bool(out["rfit_ev_relerr"] < 1e-4 and out["rfit_angle"] < 1e-3 and out["eigensnp_ev_relerr"] < 1e-4
+    out["rfit_entropy_seed_ev_relerr"] = float(np.abs(ev_n / ev0 - 1).max())
+    out["ok"] = bool(out["rfit_entropy_seed_ev_relerr"] < 1e-3 and out["rfit_ev_relerr"] < 1e-4 and out["rfit_angle"] < 1e-3 and out["eigensnp_ev_relerr"] < 1e-4
                      and out["eigensnp_angle"] < 1e-3)
     print(json.dumps(out), flush=True)
 dist.barrier()
