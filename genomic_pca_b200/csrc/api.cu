@@ -60,6 +60,7 @@ extern "C" void gpca_destroy(gpca_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  gpca_comm_destroy(c);      // before the stream it issued its collectives on goes away
   for (auto& pr : c->pending_events) {
     cudaEventDestroy(pr.first);
     cudaEventDestroy(pr.second);
@@ -78,7 +79,6 @@ extern "C" void gpca_destroy(gpca_ctx* c) {
   }
   for (int i = 0; i < gpca_ctx::INGEST_STAGES; ++i)
     if (c->h_rd[i]) cudaFreeHost(c->h_rd[i]);
-  gpca_comm_destroy(c);
   delete c;
 }
 

@@ -83,6 +83,13 @@ void usage() {
           "                                sample-side sketch (0 = every visible GPU; default 1)\n");
 }
 
+// Rust `{:.6}` (src/main.rs:721,755,779,832) = the exact decimal expansion rounded half-to-even to six places, which
+// is what glibc's "%.6f" prints -- except NaN, which Rust spells "NaN" (no sign) where C prints "nan" / "-nan".
+// Negative zero keeps its sign and the infinities are "inf" / "-inf" in both.
+inline int format_f6(char* out, size_t cap, double v) {
+  if (v != v) return snprintf(out, cap, "NaN");
+  return snprintf(out, cap, "%.6f", v);
+}
 Args parse(int argc, char** argv) {
   Args a;
   gpca_eigensnp_default_cfg(&a.es);
@@ -102,6 +109,16 @@ Args parse(int argc, char** argv) {
     }
     auto val = [&]() -> std::string { return has_inline ? inline_val : need(i); };
     if (f == "-h" || f == "--help") { usage(); exit(0); }
+    else if (f == "--format-f6") {      // (test hook) the writers' number formatting: one value per argument, as f64 and as f32
+      for (int j = i + 1; j < argc; ++j) {
+        char t64[400], t32[400];
+        const double v = strtod(argv[j], nullptr);
+        format_f6(t64, sizeof t64, v);
+        format_f6(t32, sizeof t32, (double)(float)v);
+        printf("%s\t%s\n", t64, t32);
+      }
+      exit(0);
+    }
     else if (f == "-V" || f == "--version") { printf("genomic_pca %s\n", gpca_version()); exit(0); }
     else if (f == "-o" || f == "--out") a.out = val();
     else if (f == "-t" || f == "--threads") a.threads = atol(val().c_str());
@@ -196,9 +213,10 @@ void write_rows_parallel(FILE* f, uint64_t n_rows, size_t bytes_per_row_hint, Ro
 }
 
 inline void append_f6(std::string& b, double v) {
-  char tmp[64];
-  const int len = snprintf(tmp, sizeof tmp, "\t%.6f", v);
-  b.append(tmp, (size_t)len);
+  char tmp[400];      // (1e308 has 309 integer digits)
+  tmp[0] = '\t';
+  const int len = format_f6(tmp + 1, sizeof tmp - 1, v);
+  b.append(tmp, (size_t)len + 1);
 }
 
 template <class T>
@@ -223,7 +241,11 @@ void write_pcs(const std::string& prefix, const std::string& suffix, const std::
 void write_eigenvalues(const std::string& prefix, const std::vector<double>& ev) {
   FILE* f = create_output(prefix, "eigenvalues.tsv");
   fputs("PC\tEigenvalue\n", f);
-  for (size_t i = 0; i < ev.size(); ++i) fprintf(f, "%zu\t%.6f\n", i + 1, ev[i]);
+  for (size_t i = 0; i < ev.size(); ++i) {
+    char tmp[400];
+    format_f6(tmp, sizeof tmp, ev[i]);
+    fprintf(f, "%zu\t%s\n", i + 1, tmp);
+  }
   fclose(f);
 }
 

@@ -112,6 +112,11 @@ def prepare_data_for_eigen_snp(ctx: Context, payload, fam_iids, bim_chrom, bim_b
 
 # ---- output writers (src/main.rs:696-839), byte-compatible formats -----------------------------
 def _fmt6(x):
+    """Rust `format!("{:.6}", x)` (src/main.rs:721,755,779,832): the exact decimal expansion of the binary value rounded
+    half-to-even to six places -- what Python's / C's "%.6f" print too -- except that Rust spells a NaN "NaN" (no
+    sign) where C prints "nan" / "-nan".  Negative zero keeps its sign ("-0.000000"); infinities are "inf" / "-inf"."""
+    if x != x:
+        return "NaN"
     return f"{x:.6f}"
 
 

@@ -39,6 +39,50 @@ def test_cli_argument_surface():
     assert r.returncode != 0 and "--out" in r.stderr
 
 
+# value -> what Rust's `format!("{:.6}", v)` prints (src/main.rs:721,755,779,832): exact decimal expansion of the binary
+# value, round-half-to-even at the sixth place, sign of negative zero kept, "NaN" / "inf" / "-inf"
+RUST_F6 = [
+    ("0", "0.000000"), ("-0.0", "-0.000000"), ("1.5", "1.500000"), ("-2.25", "-2.250000"),
+    ("2.5e-7", "0.000000"), ("5e-7", "0.000000"), ("1.5e-6", "0.000002"), ("-1e-7", "-0.000000"),
+    ("0.0078125", "0.007812"),          # exact tie (2^-7): half-to-even keeps the even digit
+    ("0.0234375", "0.023438"),          # exact tie, odd digit rounds up
+    ("0.9999995", "1.000000"),          # the f64 nearest to it is 0.99999950000000002...: above the tie
+    ("0.9999994", "0.999999"),
+    ("123456.7890125", "123456.789012"),
+    ("1e21", "1000000000000000000000.000000"),
+    ("nan", "NaN"), ("-nan", "NaN"), ("inf", "inf"), ("-inf", "-inf"),
+]
+
+
+def test_writers_number_format_is_rusts():
+    """The CLI's and the Python writers' `{:.6}`: byte for byte what the reference's writers print, including the edge
+    values (ties, negative zero, infinities, NaN) -- and for f32 inputs (EigenSNP scores / loadings are f32 widened to
+    their exact value, as Rust prints an f32)."""
+    from genomic_pca_b200 import plink
+    r = _run("--format-f6", *[v for v, _ in RUST_F6], "0.1", "16777217")
+    assert r.returncode == 0, r.stderr
+    rows = [ln.split("\t") for ln in r.stdout.splitlines()]
+    assert [row[0] for row in rows[:len(RUST_F6)]] == [want for _, want in RUST_F6]
+    assert rows[-2] == ["0.100000", "0.100000"] and rows[-1] == ["16777217.000000", "16777216.000000"]
+    for v, want in RUST_F6:
+        assert plink._fmt6(float(v)) == want, v
+    # an independent statement of the rule for random values: exact decimal expansion, half-to-even at 1e-6
+    from decimal import Decimal, ROUND_HALF_EVEN
+    rng = np.random.default_rng(5)
+    vals = np.concatenate([rng.standard_normal(200) * 10.0 ** rng.integers(-8, 6, 200),
+                           (rng.integers(-10**6, 10**6, 50) * 2 + 1) / 2.0 ** 21])       # exact ties among them
+    r = _run("--format-f6", *[repr(float(v)) for v in vals])
+    got = [ln.split("\t")[0] for ln in r.stdout.splitlines()]
+    for v, g in zip(vals, got):
+        want = str(Decimal(float(v)).quantize(Decimal("0.000001"), rounding=ROUND_HALF_EVEN))
+        if float(v) < 0 and want.lstrip("-") == "0.000000":
+            want = "-0.000000"
+        assert g == want == plink._fmt6(float(v)), (v, g, want)
+    assert plink._fmt6(float(np.float32(0.1))) == "0.100000"
+    # exact expansion of an f32 that is not an f64-rounded decimal: 0.3f = 0.300000011920928955078125
+    assert plink._fmt6(float(np.float32(0.3)) * 1e0) == "0.300000"
+
+
 def _write_plink(tmp, g, payload, chrom="1"):
     m, n = g.shape
     (tmp / "d.bed").write_bytes(bytes([0x6C, 0x1B, 0x01]) + payload.tobytes())
