@@ -303,6 +303,28 @@ class HostPayload:
             self.ptr = 0
 
 
+class PinnedArrays:
+    """Caller-owned result buffers in pinned host memory (gpca_host_alloc): the library then lands scores / loadings
+    straight off the bus instead of through its pinned staging buffers and host threads."""
+
+    def __init__(self, ctx):
+        self.ctx, self.held = ctx, []
+
+    def ones(self, shape, dtype):
+        nbytes = max(int(np.prod(shape)) * np.dtype(dtype).itemsize, 8)
+        ptr = self.ctx.host_alloc(nbytes)
+        self.held.append((ptr, nbytes))
+        arr = np.ctypeslib.as_array((ctypes.c_uint8 * nbytes).from_address(ptr))[:int(np.prod(shape)) * np.dtype(dtype).itemsize]
+        arr = arr.view(dtype).reshape(shape)
+        arr[...] = 1
+        return arr
+
+    def free(self):
+        for ptr, nbytes in self.held:
+            self.ctx.host_free(ptr, nbytes)
+        self.held = []
+
+
 def max_over_ranks(torch, dist, dev, world, vals):
     t = torch.tensor(vals, device=dev, dtype=torch.float64)
     if world > 1:
@@ -317,11 +339,11 @@ def sum_over_ranks(torch, dist, dev, world, vals):
     return [float(x) for x in t.tolist()]
 
 
-def timed_rfit(torch, dist, ctx, dev, world, steps, warmup, rfit_out, sample_clocks=None):
+def timed_rfit(torch, dist, ctx, dev, world, steps, warmup, rfit_out, sample_clocks=None, want_scores=True):
     """K rfit calls on the resident matrix; device time between CUDA events on the library's stream, max over ranks."""
     def step():
         return ctx.rfit(K_COMPONENTS, OVERSAMPLE, power_iters=POWER_ITERS, seed=RFIT_SEED, want_loadings=False,
-                        out=rfit_out)
+                        out=rfit_out, want_scores=want_scores)
 
     def barrier():
         if world > 1:
@@ -417,8 +439,9 @@ def run_c3(args, torch, gp, dev, pk, pk_src):
         ctx.set_sketch_engine(args.engine)
     ctx.set_sketch_timing(True)
     host = HostPayload(ctx, n, m, 0)
+    pinned = PinnedArrays(ctx)
     stats_out = (np.empty(m, dtype=np.uint8), np.empty(m, dtype=np.float32), np.empty(m, dtype=np.float32))
-    rfit_out = (np.ones((n, K_COMPONENTS), dtype=np.float64), np.ones(K_COMPONENTS, dtype=np.float64), None)
+    rfit_out = (pinned.ones((n, K_COMPONENTS), np.float64), np.ones(K_COMPONENTS, dtype=np.float64), None)
 
     def ingest():
         return ctx.ingest_bed(host.ptr, n, m, qc=None, vcf_maf=0.01, out=stats_out)
@@ -472,9 +495,12 @@ def run_c3(args, torch, gp, dev, pk, pk_src):
                                                     "converged on the trailing components (Ritz values approach from below, "
                                                     "geometrically in q); the converged run is the arithmetic check"},
             "eigenvalue_gap_k_to_k1": float(ev_x[k - 1] / ev_x[k]), "seconds": time.perf_counter() - t0}
-    if ctx is not None:
-        ctx.close()
+    if ctx is None:
+        ctx = gp.Context(dev.index or 0)      # (only to give the pinned buffers back)
+        pinned.ctx = host.ctx = ctx
+    pinned.free()
     host.free()
+    ctx.close()
     return rec
 
 
@@ -499,6 +525,7 @@ def run_ours(args, rank, world):
     host_threads = max(1, cores // max(local_world, 1))
 
     ctx = gp.Context(local_rank)
+    numa_cpus = ctx.bind_host_to_device() if local_world > 1 else 0     # payload pages NUMA-local to the rank's GPU
     if args.engine is not None:
         ctx.set_sketch_engine(args.engine)
     ctx.set_host_threads(host_threads)
@@ -510,11 +537,12 @@ def run_ours(args, rank, world):
         ctx.comm_init(box[0], rank, world)
         ctx.set_shard(s0, m_total)
     host = HostPayload(ctx, n, m, s0)
+    pinned = PinnedArrays(ctx)
 
     # ---- rfit: resident step time (value) and e2e ------------------------------------------------
     stats_out = (np.empty(m, dtype=np.uint8), np.empty(m, dtype=np.float32), np.empty(m, dtype=np.float32),
                  np.empty(m, dtype=np.uint8))
-    rfit_out = (np.ones((n, K_COMPONENTS), dtype=np.float64), np.ones(K_COMPONENTS, dtype=np.float64), None)
+    rfit_out = (pinned.ones((n, K_COMPONENTS), np.float64), np.ones(K_COMPONENTS, dtype=np.float64), None)
     t0 = time.perf_counter()
     keep, mean, sd, _, d_kept = ctx.ingest_bed(host.ptr, n, m, qc=None, vcf_maf=0.01, out=stats_out[:3])
     t_first_ingest = time.perf_counter() - t0
@@ -523,18 +551,21 @@ def run_ours(args, rank, world):
     bytes_per_pass = d_kept * bps                          # this rank's algorithmic bytes: M_loc * ceil(N/4)
     job_bytes_per_pass, = sum_over_ranks(torch, dist, dev, world, [float(bytes_per_pass)])
     d_total, = sum_over_ranks(torch, dist, dev, world, [float(d_kept)])
-    r = timed_rfit(torch, dist, ctx, dev, world, args.steps, args.warmup, rfit_out, ClockSampler(local_rank))
+    # the scores are the same on every shard: rank 0's copy goes to the host (what the CLI writes), the others pass NULL
+    want_sc = rank == 0
+    r = timed_rfit(torch, dist, ctx, dev, world, args.steps, args.warmup, rfit_out, ClockSampler(local_rank), want_sc)
     t_step = r["t_step"]
     value = passes * job_bytes_per_pass / t_step / 1e9
     e2e = None
     if not args.no_e2e:
         def e2e_rfit():
             ctx.ingest_bed(host.ptr, n, m, qc=None, vcf_maf=0.01, out=stats_out[:3])
-            ctx.rfit(K_COMPONENTS, OVERSAMPLE, power_iters=POWER_ITERS, seed=RFIT_SEED, want_loadings=False, out=rfit_out)
+            ctx.rfit(K_COMPONENTS, OVERSAMPLE, power_iters=POWER_ITERS, seed=RFIT_SEED, want_loadings=False, out=rfit_out,
+                     want_scores=want_sc)
         te = e2e_loop(torch, dist, dev, world, e2e_rfit, args.e2e_steps)
         e2e = {"value": passes * job_bytes_per_pass / te / 1e9, "unit": "GB/s", "ms_per_step": te * 1e3,
                "steps": args.e2e_steps, "h2d_bytes_per_step": int(m_total * bps),
-               "d2h_bytes_per_step": int(world * (n * K_COMPONENTS * 8 + K_COMPONENTS * 8) + m_total * 16),
+               "d2h_bytes_per_step": int(n * K_COMPONENTS * 4 + world * K_COMPONENTS * 8 + m_total * 16),
                "pca_wall_s": te, "includes": "gpca_ingest_bed of every rank's shard from pinned host memory + gpca_rfit + "
                                              "scores / eigenvalues on the host"}
 
@@ -552,9 +583,9 @@ def run_ours(args, rank, world):
             _, _, _, _, d_es = es_ingest()
             edges = np.linspace(0, d_es, nb + 1).astype(np.int64)
             blocks = [np.arange(edges[i], edges[i + 1], dtype=np.uint64) for i in range(nb)]
-            es_out = (np.ones((n, K_COMPONENTS), dtype=np.float32), np.ones(K_COMPONENTS, dtype=np.float64),
-                      np.ones((d_es, K_COMPONENTS), dtype=np.float32))
-            ctx.eigensnp(blocks, cfg, out=es_out)
+            es_out = (pinned.ones((n, K_COMPONENTS), np.float32), np.ones(K_COMPONENTS, dtype=np.float64),
+                      pinned.ones((d_es, K_COMPONENTS), np.float32))
+            ctx.eigensnp(blocks, cfg, out=es_out, want_scores=want_sc)
             reps = 3
             if world > 1:
                 dist.barrier()
@@ -562,7 +593,7 @@ def run_ours(args, rank, world):
             ctx.reset_launch_count()
             t0 = time.perf_counter()
             for _ in range(reps):
-                sc_es, ev_es, _ = ctx.eigensnp(blocks, cfg, out=es_out)
+                sc_es, ev_es, _ = ctx.eigensnp(blocks, cfg, out=es_out, want_scores=want_sc)
             t_es = (time.perf_counter() - t0) / reps
             es_launches = ctx.launch_count // reps
             t_es, = max_over_ranks(torch, dist, dev, world, [t_es])
@@ -572,17 +603,18 @@ def run_ours(args, rank, world):
             if not args.no_e2e:
                 def e2e_es():
                     es_ingest()
-                    ctx.eigensnp(blocks, cfg, out=es_out)
+                    ctx.eigensnp(blocks, cfg, out=es_out, want_scores=want_sc)
                 te_es = e2e_loop(torch, dist, dev, world, e2e_es, args.e2e_steps)
                 es["e2e"] = {"pca_wall_s": te_es, "ms_per_step": te_es * 1e3, "steps": args.e2e_steps,
                              "h2d_bytes_per_step": int(m_total * bps),
-                             "d2h_bytes_per_step": int(world * n * K_COMPONENTS * 4 + m_total * (16 + K_COMPONENTS * 4))}
+                             "d2h_bytes_per_step": int(n * K_COMPONENTS * 4 + m_total * (16 + K_COMPONENTS * 4))}
         except Exception as e:       # the headline record must not be lost to the second mode
             es = {"error": repr(e)}
             if world > 1:
                 raise
-    ctx.close()
+    pinned.free()
     host.free()
+    ctx.close()
     torch.cuda.empty_cache()
 
     c3 = None
@@ -630,6 +662,8 @@ def run_ours(args, rank, world):
                    "passes_per_step": passes, "bytes_per_pass": job_bytes_per_pass,
                    "l2": "inputs larger than L2 (packed shard >> 126 MB)" if bytes_per_pass > 2e8 else "input fits L2",
                    "pca_wall_s": t_step, "host_wall_s_per_step": r["wall_per_step"], "host_threads_per_rank": host_threads,
+                   "numa_local_cpus_rank0": numa_cpus,
+                   "result_buffers": "caller-owned pinned host memory (gpca_host_alloc); scores requested on rank 0 only",
                    "exchange": "ncclAllReduce issued by the library (gpca_comm_init)" if world > 1 else "none (one shard)",
                    "collectives_per_step": r["collectives_per_step"],
                    "resident_snp_rows_frac_rank0": resident_rfit / max(d_kept, 1),

@@ -96,6 +96,7 @@ _sig("gpca_sketch_kernel_ms", C.c_double, C.c_void_p)
 _sig("gpca_set_allreduce", C.c_int, C.c_void_p, ALLREDUCE_FN, C.c_void_p)
 _sig("gpca_set_host_threads", C.c_int, C.c_void_p, C.c_uint32)
 _sig("gpca_set_sketch_timing", C.c_int, C.c_void_p, C.c_int)
+_sig("gpca_bind_host_to_device", C.c_int, C.c_void_p)
 _sig("gpca_set_memory_reserve", C.c_int, C.c_void_p, C.c_uint64)
 _sig("gpca_resident_snp_rows", C.c_uint64, C.c_void_p)
 _sig("gpca_eigensnp_workspace_bytes", C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p)
@@ -127,6 +128,8 @@ _sig("gpca_ingest_bed", C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64,
 _sig("gpca_get_standardized_block", C.c_int, C.c_void_p, _u64p, C.c_uint64, _u64p, C.c_uint64, _f32p)
 _sig("gpca_sketch_snp_side", C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32)
 _sig("gpca_sketch_sample_side", C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32)
+_sig("gpca_dense_product", C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, C.c_void_p, C.c_uint32,
+     C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32)
 _sig("gpca_synchronize", C.c_int, C.c_void_p)
 _sig("gpca_get_stream", C.c_void_p, C.c_void_p)
 _sig("gpca_rfit", C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_int, _f64p, _f64p, _f32p,
@@ -134,6 +137,7 @@ _sig("gpca_rfit", C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_u
 _sig("gpca_eigensnp_default_cfg", None, C.POINTER(EigenSnpConfig))
 _sig("gpca_eigensnp", C.c_int, C.c_void_p, C.POINTER(EigenSnpConfig), _u64p, C.c_uint64, _u64p, _f32p, _f64p, _f32p,
      _u32p)
+_sig("gpca_eigensnp_diagnostics", C.c_char_p, C.c_void_p)
 _sig("gpca_map_snps_to_ld_blocks", C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int32), C.c_uint64,
      C.POINTER(C.c_char_p), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_uint64, _i64p, _i64p, _u64p, _u64p, _u64p)
 
@@ -230,6 +234,10 @@ class Context:
     def set_host_threads(self, n: int):
         self._chk(lib.gpca_set_host_threads(self._h, int(n)))
 
+    def bind_host_to_device(self) -> int:
+        """Bind this thread (and the threads created from it) to the CPUs next to the GPU; returns their number."""
+        return int(lib.gpca_bind_host_to_device(self._h))
+
     def set_sketch_timing(self, on: bool):
         self._chk(lib.gpca_set_sketch_timing(self._h, 1 if on else 0))
 
@@ -270,6 +278,11 @@ class Context:
     @property
     def comm_world(self) -> int:
         return int(lib.gpca_comm_world(self._h))
+
+    @property
+    def eigensnp_diagnostics(self) -> str:
+        """JSON record of the last eigensnp() call made with collect_diagnostics=1 ("" if none)."""
+        return (lib.gpca_eigensnp_diagnostics(self._h) or b"").decode()
 
     @property
     def collective_count(self) -> int:
@@ -456,6 +469,11 @@ class Context:
     def sketch_sample_side(self, in_ptr: int, out_ptr: int, l: int, ld: int):
         self._chk(lib.gpca_sketch_sample_side(self._h, in_ptr, out_ptr, l, ld))
 
+    def dense_product(self, c_ptr, n, r, ldc, cols_mode, in_ptr, l, ld, out_ptr, ldo, f=0, e=0, a=0, b=0):
+        """gpca_dense_product on device pointers (0 = NULL for the optional scale vectors)."""
+        self._chk(lib.gpca_dense_product(self._h, c_ptr, n, r, ldc, 1 if cols_mode else 0, in_ptr, l, ld, f or None,
+                                         e or None, a or None, b or None, out_ptr, ldo))
+
     @property
     def stream(self) -> int:
         return int(lib.gpca_get_stream(self._h) or 0)
@@ -464,35 +482,41 @@ class Context:
         self._chk(lib.gpca_synchronize(self._h))
 
     # -- drivers
-    def rfit(self, k, oversample=10, power_iters=2, seed=None, want_loadings=True, out=None):
+    def rfit(self, k, oversample=10, power_iters=2, seed=None, want_loadings=True, out=None, want_scores=True):
         """`out` = (scores f64 [N, k], eigenvalues f64 [k], loadings f32 [D, k] or None): caller-owned result buffers,
         as the C ABI has them (a host that calls repeatedly allocates them once; fresh `np.zeros` arrays are mapped
-        lazily and page-fault while the results land -- 20,000 faults for the 500,000 x 20 f64 scores)."""
+        lazily and page-fault while the results land -- 20,000 faults for the 500,000 x 20 f64 scores).
+        `want_scores=False` passes NULL for the scores (a shard of a multi-GPU run whose copy of the -- identical --
+        scores nobody reads: the 40 MB download and the widening to f64 are then skipped)."""
         n, d = self.num_samples, self.num_pca_snps
         kk = max(1, min(k, n))
         if out is not None:
             scores, ev, load = out
-            assert scores.dtype == np.float64 and scores.shape == (n, kk) and scores.flags.c_contiguous
+            assert scores is None or (scores.dtype == np.float64 and scores.shape == (n, kk) and scores.flags.c_contiguous)
             assert ev.dtype == np.float64 and ev.shape == (kk,)
             assert load is None or (load.dtype == np.float32 and load.shape == (d, kk) and load.flags.c_contiguous)
         else:
-            scores = np.zeros((n, kk), dtype=np.float64)
+            scores = np.zeros((n, kk), dtype=np.float64) if want_scores else None
             ev = np.zeros(kk, dtype=np.float64)
             load = np.zeros((d, kk), dtype=np.float32) if want_loadings else None
+        if not want_scores:
+            scores = None
         kout = C.c_uint32(0)
         self._chk(lib.gpca_rfit(self._h, k, oversample, power_iters, 0 if seed is None else int(seed),
                                 0 if seed is None else 1, _ptr(scores, _f64p), _ptr(ev, _f64p), _ptr(load, _f32p),
                                 C.byref(kout)))
         ko = int(kout.value)
         if ko != kk:
-            scores = scores.reshape(-1)[:n * ko].reshape(n, ko)
+            if scores is not None:
+                scores = scores.reshape(-1)[:n * ko].reshape(n, ko)
             ev = ev[:ko]
             if load is not None:
                 load = load.reshape(-1)[:d * ko].reshape(d, ko)
         return scores, ev, load
 
-    def eigensnp(self, block_snp_ids, cfg: EigenSnpConfig | None = None, out=None):
-        """`out` = (scores f32 [N, k], eigenvalues f64 [k], loadings f32 [D, k]): caller-owned result buffers (see rfit)."""
+    def eigensnp(self, block_snp_ids, cfg: EigenSnpConfig | None = None, out=None, want_scores=True):
+        """`out` = (scores f32 [N, k] or None, eigenvalues f64 [k], loadings f32 [D, k]): caller-owned result buffers
+        (see rfit; `want_scores=False` as there)."""
         cfg = cfg or EigenSnpConfig()
         n, d = self.num_samples, self.num_pca_snps
         offs = np.zeros(len(block_snp_ids) + 1, dtype=np.uint64)
@@ -504,19 +528,22 @@ class Context:
         k = int(cfg.target_num_global_pcs)
         if out is not None:
             scores, ev, load = out
-            assert scores.dtype == np.float32 and scores.shape == (n, k) and scores.flags.c_contiguous
+            assert scores is None or (scores.dtype == np.float32 and scores.shape == (n, k) and scores.flags.c_contiguous)
             assert ev.dtype == np.float64 and ev.shape == (k,)
             assert load.dtype == np.float32 and load.shape == (d, k) and load.flags.c_contiguous
         else:
-            scores = np.zeros((n, k), dtype=np.float32)
+            scores = np.zeros((n, k), dtype=np.float32) if want_scores else None
             ev = np.zeros(k, dtype=np.float64)
             load = np.zeros((d, k), dtype=np.float32)
+        if not want_scores:
+            scores = None
         kout = C.c_uint32(0)
         self._chk(lib.gpca_eigensnp(self._h, C.byref(cfg), _ptr(offs, _u64p), len(block_snp_ids), _ptr(flat, _u64p),
                                     _ptr(scores, _f32p), _ptr(ev, _f64p), _ptr(load, _f32p), C.byref(kout)))
         ko = int(kout.value)
         if ko != k:
-            scores = scores.reshape(-1)[:n * ko].reshape(n, ko)
+            if scores is not None:
+                scores = scores.reshape(-1)[:n * ko].reshape(n, ko)
             ev = ev[:ko]
             load = load.reshape(-1)[:d * ko].reshape(d, ko)
         return scores, ev, load

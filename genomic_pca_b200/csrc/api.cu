@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <chrono>
 #include <fcntl.h>
+#include <sched.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -15,6 +16,7 @@
 #include "host_qc.h"
 #include "kernels.cuh"
 #include "sketch_tc.cuh"
+#include "dense_tc.cuh"
 #include "driver_util.cuh"
 #include "parallel_for.h"
 
@@ -104,6 +106,46 @@ extern "C" int gpca_set_host_threads(gpca_ctx* c, uint32_t n) {
   c->host_threads = n;
   return GPCA_OK;
 }
+// The calling thread (and every thread it creates afterwards: the context's host pool, the caller's own workers) is
+// bound to the CPUs next to the context's GPU, as sysfs reports them for the PCI device.  Pinned payload buffers that
+// are first touched after this call then live in that NUMA node's memory: with one process per GPU on a two-socket
+// host, half of the ranks otherwise stream their payload across the socket interconnect.
+extern "C" int gpca_bind_host_to_device(gpca_ctx* c) {
+  CHECK_CTX(c);
+  char bus[32] = {0};
+  if (cudaDeviceGetPCIBusId(bus, sizeof bus, c->device) != cudaSuccess) return 0;
+  for (char* p = bus; *p; ++p) *p = (char)tolower((unsigned char)*p);
+  const std::string path = std::string("/sys/bus/pci/devices/") + bus + "/local_cpulist";
+  FILE* f = fopen(path.c_str(), "r");
+  if (!f) return 0;
+  char line[4096] = {0};
+  const bool ok = fgets(line, sizeof line, f) != nullptr;
+  fclose(f);
+  if (!ok) return 0;
+  cpu_set_t allowed, want;
+  CPU_ZERO(&allowed);
+  CPU_ZERO(&want);
+  if (sched_getaffinity(0, sizeof allowed, &allowed) != 0) return 0;
+  int n = 0;
+  for (char* tok = strtok(line, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+    int lo = 0, hi = 0;
+    if (sscanf(tok, "%d-%d", &lo, &hi) == 2) {
+    } else if (sscanf(tok, "%d", &lo) == 1) {
+      hi = lo;
+    } else {
+      continue;
+    }
+    for (int cpu = lo; cpu <= hi && cpu < CPU_SETSIZE; ++cpu)
+      if (CPU_ISSET(cpu, &allowed)) {
+        CPU_SET(cpu, &want);
+        ++n;
+      }
+  }
+  if (n == 0 || n == CPU_COUNT(&allowed)) return n;      // nothing to narrow (one NUMA node, or no overlap)
+  if (sched_setaffinity(0, sizeof want, &want) != 0) return 0;
+  c->pool.reset();                                       // (re-created on the bound CPUs on next use)
+  return n;
+}
 extern "C" int gpca_set_sketch_timing(gpca_ctx* c, int on) {
   CHECK_CTX(c);
   c->sk_timing = on != 0;
@@ -147,7 +189,20 @@ extern "C" int gpca_synchronize(gpca_ctx* c) {
   return GPCA_OK;
 }
 
-static void reset_loaded(gpca_ctx* c) {
+// working buffers of gpca_eigensnp that survive between calls (their CONTENT is rebuilt by every call)
+static void release_eigensnp_buffers(gpca_ctx* c) {
+  c->es_store.release();
+  c->et_store.release();
+  c->ets_store.release();
+  c->ess_store.release();
+  c->es_cn.release();
+  c->es_pool.release();
+}
+static size_t eigensnp_buffer_bytes(const gpca_ctx* c) {
+  return c->es_store.n + c->et_store.n + c->ets_store.n + c->ess_store.n + c->es_cn.n * sizeof(float) + c->es_pool.bytes();
+}
+
+static void reset_loaded(gpca_ctx* c, bool keep_eigensnp_buffers = false) {
   c->have_counts = false;   // (the host vectors keep their storage: re-growing them would zero-fill hundreds of MB)
   c->D = 0;
   c->Gs = PackedMat();
@@ -155,12 +210,7 @@ static void reset_loaded(gpca_ctx* c) {
   c->any_missing = false;
   c->gs_res_rows = 0;
   c->gs_win_rows = 0;
-  c->es_store.release();
-  c->et_store.release();
-  c->ets_store.release();
-  c->ess_store.release();
-  c->es_cn.release();
-  c->es_pool.release();
+  if (!keep_eigensnp_buffers) release_eigensnp_buffers(c);
 }
 
 // ---- ingest ------------------------------------------------------------------------------
@@ -627,7 +677,9 @@ static int ingest_core(gpca_ctx* c, const uint8_t* host_payload, int fd, uint64_
     pre_mask = c->ingest_mask.data();
   }
   c->vcf_mode = false;
-  reset_loaded(c);
+  // (a host that ingests and runs EigenSNP repeatedly keeps the driver's working buffers: freeing and re-allocating
+  //  tens of GB per call costs more than the call's kernels; they are given up below if the matrices need the room)
+  reset_loaded(c, true);
   c->raw.release();                 // (the three-call path's staging copy, if an earlier data set left one)
   c->raw_pitch = 0;
   c->N = N;
@@ -699,15 +751,25 @@ static int ingest_core(gpca_ctx* c, const uint8_t* host_payload, int fd, uint64_
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
     size_t avail = free_b + c->gs_store.n + c->gt_store.n;     // (stores of an earlier data set are reused or replaced)
+    // the reserve is for the drivers' working buffers: what gpca_eigensnp already holds from an earlier call counts
+    size_t reserve = c->mem_reserve > eigensnp_buffer_bytes(c) ? c->mem_reserve - eigensnp_buffer_bytes(c) : 0;
+    if (gs_full + gt_full + reserve > avail && eigensnp_buffer_bytes(c) > 0) {
+      // ... unless both orientations only fit without them (they are re-allocated inside the reserve when needed)
+      GPCA_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+      release_eigensnp_buffers(c);
+      cudaMemGetInfo(&free_b, &total_b);
+      avail = free_b + c->gs_store.n + c->gt_store.n;
+      reserve = c->mem_reserve;
+    }
     if (const char* e = getenv("GPCA_DEBUG_MEM_BUDGET")) avail = std::min<size_t>(avail, strtoull(e, nullptr, 10));
     uint64_t res = M, win = 0;
-    if (gs_full + gt_full + c->mem_reserve > avail) {
+    if (gs_full + gt_full + reserve > avail) {
       win = round_up(2 * rows_per_chunk + 1024, 512);
       const uint64_t win_target = round_up(std::max<uint64_t>(1, (4ull << 30) / c->Gs.pitch), 512);   // ~4 GB of rows
       win = std::max(win, win_target);
       if (const char* e = getenv("GPCA_DEBUG_WINDOW_ROWS"))      // tests: a small window on a small matrix
         win = round_up(std::max<uint64_t>(strtoull(e, nullptr, 10), rows_per_chunk + 1024), 512);
-      const size_t fixed = gt_full + c->mem_reserve + win * c->Gs.pitch;
+      const size_t fixed = gt_full + reserve + win * c->Gs.pitch;
       res = fixed < avail ? ((avail - fixed) / c->Gs.pitch) & ~511ull : 0;
       if (res + win >= M) {      // the window alone covers the rest: everything is resident after all
         res = M;
@@ -1304,6 +1366,17 @@ extern "C" int gpca_sketch_sample_side(gpca_ctx* c, const float* dev_in, float* 
   return sketch_sample_side(c, dev_in, dev_out, l, ld, ld, false);
 }
 
+extern "C" int gpca_dense_product(gpca_ctx* c, const float* dev_c, uint64_t n, uint64_t r, uint32_t ldc, int cols_mode,
+                                  const float* dev_in, uint32_t l, uint32_t ld, const float* dev_f, const float* dev_e,
+                                  const float* dev_a, const float* dev_b, float* dev_out, uint32_t ldo) {
+  CHECK_CTX(c);
+  GPCA_CUDA_TRY(c, cudaSetDevice(c->device));
+  if (!dev_c || !dev_in || !dev_out || l == 0 || l > 64 || ld < l || ldo < l || ldc < r)
+    return fail(c, GPCA_ERR_INVALID, "gpca_dense_product: bad argument");
+  DenseProduct dp{dev_c, n, r, ldc, cols_mode != 0, dev_in, l, ld, dev_f, dev_e, dev_a, dev_b, dev_out, ldo};
+  return launch_dense_product(c, dp);
+}
+
 extern "C" double gpca_sketch_kernel_ms(gpca_ctx* c) { return c ? c->sk_kernel_ms_last : 0.0; }
 
 extern "C" int gpca_sketch_stats(gpca_ctx* c, double* ms_total, double* bytes_total, uint64_t* n_passes, int reset) {
@@ -1316,13 +1389,22 @@ extern "C" int gpca_sketch_stats(gpca_ctx* c, double* ms_total, double* bytes_to
     cudaEventDestroy(pr.second);
   }
   c->pending_events.clear();
-  for (auto& pr : c->pending_kernel_events) {
+  const bool trace_launches = getenv("GPCA_TRACE_SKETCH") != nullptr;
+  for (size_t i = 0; i < c->pending_kernel_events.size(); ++i) {
+    auto& pr = c->pending_kernel_events[i];
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) c->sk_kernel_ms += ms;
+    if (trace_launches && i < c->pending_kernel_notes.size()) {
+      const auto& nt = c->pending_kernel_notes[i];
+      const double gb = (double)nt.rows * (double)((nt.K + 3) / 4) * 1e-9;
+      fprintf(stderr, "[sketch kernel] rows %llu K %llu ksplit %u items %u: %.3f ms  %.1f GB/s\n",
+              (unsigned long long)nt.rows, (unsigned long long)nt.K, nt.ksplit, nt.items, ms, ms > 0 ? gb / (ms * 1e-3) : 0.0);
+    }
     cudaEventDestroy(pr.first);
     cudaEventDestroy(pr.second);
   }
   c->pending_kernel_events.clear();
+  c->pending_kernel_notes.clear();
   if (ms_total) *ms_total = c->sk_ms;
   if (bytes_total) *bytes_total = c->sk_bytes;
   if (n_passes) *n_passes = c->sk_passes;

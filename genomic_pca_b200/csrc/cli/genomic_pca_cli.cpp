@@ -503,14 +503,11 @@ int run_vcf(const Args& a) {
   for_each_shard(sh, [&](int g) {
     gpca_ctx* ctx = sh.ctx[g];
     if (G > 1) check(ctx, gpca_set_shard(ctx, koff[g], d_kept), "set_shard");
-    std::vector<double> sc_g, ev_g;
-    if (g != 0) {
-      sc_g.resize(n * k);
-      ev_g.resize(k);
-    }
+    std::vector<double> ev_g(g != 0 ? k : 0);
     uint32_t ko = 0;
+    // (the scores are the same on every shard: only shard 0's copy is brought to the host)
     check(ctx, gpca_rfit(ctx, k, 10 /* main.rs:636 */, a.rfit_power_iters, a.rfit_seed, a.has_seed ? 1 : 0,
-                         g == 0 ? scores.data() : sc_g.data(), g == 0 ? ev.data() : ev_g.data(), nullptr, &ko), "rfit");
+                         g == 0 ? scores.data() : nullptr, g == 0 ? ev.data() : ev_g.data(), nullptr, &ko), "rfit");
     if (g == 0) k_out = ko;
   });
   const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -742,10 +739,10 @@ int run_eigensnp(const Args& a) {
     gpca_ctx* ctx = sh.ctx[g];
     ShardData& d = sd_[g];
     if (G > 1) check(ctx, gpca_set_shard(ctx, d.id_offset, n_pca), "set_shard");
-    d.scores.resize(n * k);
+    if (g == 0) d.scores.resize(n * k);       // (the same on every shard: only shard 0's copy is brought to the host)
     d.loadings.resize(d.n_kept * k);
     d.ev.resize(k);
-    check(ctx, gpca_eigensnp(ctx, &a.es, d.offs.data(), d.offs.size() - 1, d.flat.data(), d.scores.data(), d.ev.data(),
+    check(ctx, gpca_eigensnp(ctx, &a.es, d.offs.data(), d.offs.size() - 1, d.flat.data(), g == 0 ? d.scores.data() : nullptr, d.ev.data(),
                              d.loadings.data(), &d.k_out), "eigensnp");
   });
   const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -785,6 +782,26 @@ int run_eigensnp(const Args& a) {
       b += '\n';
     });
     fclose(f);
+  }
+  if (a.es.collect_diagnostics) {      // main.rs:411-430
+    const std::string fn = a.out + ".eigensnp_diagnostics.json";
+    info("Writing EigenSNP diagnostics to " + fn + "...");
+    FILE* f = fopen(fn.c_str(), "w");
+    if (!f) {
+      warn("Failed to write EigenSNP diagnostics to " + fn);
+    } else {
+      if (G == 1) {
+        fputs(gpca_eigensnp_diagnostics(sh.ctx[0]), f);
+      } else {
+        fputs("{\"shards\": [\n", f);
+        for (int g = 0; g < G; ++g) {
+          fputs(gpca_eigensnp_diagnostics(sh.ctx[g]), f);
+          if (g + 1 < G) fputs(",\n", f);
+        }
+        fputs("]}\n", f);
+      }
+      fclose(f);
+    }
   }
   close_shards(sh);
   return 0;

@@ -59,6 +59,11 @@ struct ScratchPool {
   size_t next = 0;
   ~ScratchPool() { release(); }
   void reset() { next = 0; }
+  size_t bytes() const {
+    size_t t = 0;
+    for (auto* b : bufs) t += b->n;
+    return t;
+  }
   void release() {
     for (auto* b : bufs) delete b;
     bufs.clear();
@@ -145,6 +150,7 @@ struct gpca_ctx {
   std::vector<int64_t> es_subset;                             // the N_s-sample subset of the last EigenSNP call
   uint64_t es_subset_n = 0, es_subset_seed = 0;
   DevBuf<float> es_cn;                                        // EigenSNP condensed features
+  std::string es_diag_json;                                   // diagnostics of the last gpca_eigensnp call that collected them
   // streaming ingest (gpca_ingest_bed): a ring of device staging buffers for the payload chunks, the sample-gathered
   // copy of a chunk when a keep-list is given, pinned+mapped staging of the per-chunk compacted vectors, pinned read
   // buffers of gpca_ingest_bed_file
@@ -177,6 +183,8 @@ struct gpca_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_events;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_kernel_events;   // around the main sketch kernel only
+  struct KernelNote { uint64_t rows, K; uint32_t ksplit, items; };        // what each timed launch covered (GPCA_TRACE_SKETCH)
+  std::vector<KernelNote> pending_kernel_notes;
   double sk_kernel_ms = 0, sk_kernel_ms_last = 0;
 
   // scratch
@@ -197,8 +205,6 @@ struct gpca_ctx {
   DevBuf<float> ws_bstat;      // batched passes: per-block column sums, scales, amax words
   bool tc_amax_zeroed = false;
   DevBuf<float> drv_a, drv_b, drv_c, drv_d, drv_e;   // driver-level dense operands (kept across calls: no per-call cudaMalloc)
-
-  void* cublas = nullptr;      // cublasHandle_t, created on first EigenSNP call
 
   // host threads of this context (parallel_for.h): a persistent pool, created on first use
   unsigned host_threads = 0;   // 0 = every CPU the process may run on
@@ -221,10 +227,11 @@ struct KernelTimer {
     if (!c->sk_timing) return;       // opt-in: a long-lived host never polls gpca_sketch_stats
     if (cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess) cudaEventRecord(e0, c->stream);
   }
-  void end() {
+  void end(uint64_t rows = 0, uint64_t K = 0, uint32_t ksplit = 0, uint32_t items = 0) {
     if (e0 && e1) {
       cudaEventRecord(e1, c->stream);
       c->pending_kernel_events.push_back({e0, e1});
+      c->pending_kernel_notes.push_back({rows, K, ksplit, items});
     }
   }
 };

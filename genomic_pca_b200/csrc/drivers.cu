@@ -28,9 +28,41 @@ int get_small(gpca_ctx* c, Small& s) {
   return GPCA_OK;
 }
 
+__global__ void f32_to_f64_kernel(const float* __restrict__ in, double* __restrict__ out, uint64_t n) {
+  for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < n; t += (uint64_t)gridDim.x * blockDim.x)
+    out[t] = (double)in[t];
+}
+int launch_f32_to_f64(gpca_ctx* c, const float* in, double* out, uint64_t n) {
+  if (n == 0) return GPCA_OK;
+  const int grid = (int)std::min<uint64_t>((n + 255) / 256, (uint64_t)c->sm_count * 8);
+  f32_to_f64_kernel<<<grid, 256, 0, c->stream>>>(in, out, n);
+  c->launches++;
+  GPCA_CUDA_TRY(c, cudaGetLastError());
+  return GPCA_OK;
+}
+
 int download_results(gpca_ctx* c, const float* d_src, uint64_t count, float* dst_f32, double* dst_f64) {
   constexpr uint64_t CH_MAX = 1u << 21;      // floats per chunk (8 MB landing buffers)
   if (count == 0 || (!dst_f32 && !dst_f64)) return GPCA_OK;
+  {
+    // a caller-owned buffer that is pinned (cudaHostRegister / gpca_host_alloc) takes the results straight off the bus:
+    // f32 as they are, f64 widened on the device first
+    void* dst = dst_f32 ? (void*)dst_f32 : (void*)dst_f64;
+    cudaPointerAttributes at;
+    const bool pinned = cudaPointerGetAttributes(&at, dst) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    cudaGetLastError();      // (an unregistered pointer is not an error here)
+    if (pinned && !getenv("GPCA_DEBUG_DOWNLOAD_CHUNK")) {
+      if (dst_f32) {
+        GPCA_CUDA_TRY(c, cudaMemcpyAsync(dst_f32, d_src, count * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+      } else {
+        GPCA_CUDA_TRY(c, c->ws_f64.alloc(count));
+        GPCA_TRY(launch_f32_to_f64(c, d_src, c->ws_f64.p, count));
+        GPCA_CUDA_TRY(c, cudaMemcpyAsync(dst_f64, c->ws_f64.p, count * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      }
+      GPCA_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+      return GPCA_OK;
+    }
+  }
   uint64_t CH = CH_MAX;
   if (const char* e = getenv("GPCA_DEBUG_DOWNLOAD_CHUNK")) {   // tests: force many chunks on small results
     const uint64_t v = strtoull(e, nullptr, 10);

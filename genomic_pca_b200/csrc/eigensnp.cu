@@ -8,16 +8,15 @@
 //   4. global randomized SVD of the condensed matrix -> initial sample-side vectors V [N x k]
 //   5. refine passes: L = orth(S V); Sc = S^T L; small eigensolve -> V, loadings, singular values
 // Every product with genotypes is a sketch pass on the resident 2-bit matrices (no accessor round trips,
-// no f32 strips: src/prepare.rs:1839-2022 is what this makes unnecessary); the dense condensed matrix uses
-// cuBLAS SGEMM (a plain library GEMM).
-#include <cublas_v2.h>
-
+// no f32 strips: src/prepare.rs:1839-2022 is what this makes unnecessary); the products with the dense condensed
+// matrix run on the split-bf16 tcgen05 engine of dense_tc.cu, with the column standardisation folded in.
 #include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstring>
 #include <vector>
 
+#include "dense_tc.cuh"
 #include "driver_util.cuh"
 #include "parallel_for.h"
 #include "philox.cuh"
@@ -115,8 +114,9 @@ __global__ void gaussian_keyed_kernel(float* __restrict__ out, const uint64_t* _
   }
 }
 
-// per-column mean / sd (ddof = 1) of X [n x r] row-major, f64 accumulation; then z = (x - mean) / sd in place
-__global__ void __launch_bounds__(256) col_moments_kernel(const float* __restrict__ x, uint64_t n, uint32_t r,
+// per-column mean and 1/sd (ddof = 1) of X [n x r] row-major with row stride ld, f64 accumulation.  The standardised
+// matrix z = (x - mean) / sd is never written: the products with it take mean / sd as operand scales (dense_tc.cu).
+__global__ void __launch_bounds__(256) col_moments_kernel(const float* __restrict__ x, uint64_t n, uint32_t r, uint32_t ld,
                                                           uint64_t rows_per_cta, double* __restrict__ part) {
   // grid.x = row chunks, grid.y = column tiles of 256
   const uint32_t col = blockIdx.y * 256 + threadIdx.x;
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(256) col_moments_kernel(const float* __restric
   double s = 0.0, ss = 0.0;
   if (col < r)
     for (uint64_t i = r0; i < r1; ++i) {
-      const double v = (double)x[i * r + col];
+      const double v = (double)x[i * ld + col];
       s += v;
       ss += v * v;
     }
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(256) col_moments_kernel(const float* __restric
   }
 }
 __global__ void col_finalize_kernel(const double* __restrict__ part, int nparts, uint64_t n, uint32_t r,
-                                    float* __restrict__ mean, float* __restrict__ inv_sd) {
+                                    float* __restrict__ mean, float* __restrict__ inv_sd, float* __restrict__ mean_inv_sd) {
   const uint32_t col = blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= r) return;
   double s = 0.0, ss = 0.0;
@@ -147,17 +147,10 @@ __global__ void col_finalize_kernel(const double* __restrict__ part, int nparts,
   double var = (n > 1) ? (ss - (double)n * m * m) / (double)(n - 1) : 0.0;
   if (var < 0.0) var = 0.0;
   const double sd = sqrt(var);
+  const double inv = (sd > 1e-12) ? 1.0 / sd : 0.0;
   mean[col] = (float)m;
-  inv_sd[col] = (sd > 1e-12) ? (float)(1.0 / sd) : 0.0f;
-}
-__global__ void col_apply_kernel(float* __restrict__ x, uint64_t n, uint32_t r, const float* __restrict__ mean,
-                                 const float* __restrict__ inv_sd) {
-  const uint64_t total = n * r;
-  for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < total;
-       t += (uint64_t)gridDim.x * blockDim.x) {
-    const uint32_t col = (uint32_t)(t % r);
-    x[t] = (x[t] - mean[col]) * inv_sd[col];
-  }
+  inv_sd[col] = (float)inv;
+  mean_inv_sd[col] = (float)(m * inv);
 }
 
 // out[n x k] = in[n x k] * diag(scale[k]) in place (f64 scale vector on device, sqrt applied)
@@ -186,27 +179,7 @@ __global__ void scatter_loadings_kernel(const float* __restrict__ in, const int6
   }
 }
 
-int cublas_check(gpca_ctx* c, cublasStatus_t st, const char* what) {
-  if (st == CUBLAS_STATUS_SUCCESS) return GPCA_OK;
-  return fail(c, GPCA_ERR_CUDA, std::string("cuBLAS ") + what + " failed: " + std::to_string((int)st));
-}
-
-// row-major C[m x n] = op(A) * B with A row-major [m x k] (or [k x m] when transA), B row-major [k x n]
-int sgemm_rm(gpca_ctx* c, cublasHandle_t h, bool transA, int m, int n, int k, const float* A, int lda, const float* B,
-             int ldb, float* C, int ldc) {
-  const float one = 1.0f, zero = 0.0f;
-  // column-major view: C^T[n x m] = B^T[n x k] * op(A)^T
-  cublasStatus_t st = cublasSgemm(h, CUBLAS_OP_N, transA ? CUBLAS_OP_T : CUBLAS_OP_N, n, m, k, &one, B, ldb, A, lda,
-                                  &zero, C, ldc);
-  c->launches++;
-  return cublas_check(c, st, "Sgemm");
-}
-
 }  // namespace
-
-void gpca_destroy_cublas(void* h) {
-  if (h) cublasDestroy((cublasHandle_t)h);
-}
 
 extern "C" uint64_t gpca_eigensnp_workspace_bytes(uint64_t N, uint64_t D, uint64_t n_blocks, const gpca_eigensnp_cfg* cfg) {
   gpca_eigensnp_cfg d;
@@ -245,16 +218,30 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
   if (cpb_max + cfg->local_oversampling > 64 || k_req + cfg->global_oversampling > 64)
     return fail(c, GPCA_ERR_INVALID, "components + oversampling must be <= 64 in this build");
   const uint64_t seed = cfg->random_seed;
-  // optional stage timing (GPCA_TRACE=1): the reference prints a stage table too (src/main.rs:437-442)
+  // optional stage timing (GPCA_TRACE=1): the reference prints a stage table too (src/main.rs:437-442).  With
+  // cfg->collect_diagnostics (--eigensnp-collect-diagnostics, src/main.rs:411-430) the stage times and the shape of the
+  // run are kept as a JSON document (gpca_eigensnp_diagnostics); the stream is then synchronised at every stage.
   const bool trace = getenv("GPCA_TRACE") != nullptr;
-  auto t_last = std::chrono::steady_clock::now();
+  const bool diag = cfg->collect_diagnostics != 0;
+  std::vector<std::pair<std::string, double>> diag_stages;
+  const auto t_call = std::chrono::steady_clock::now();
+  auto t_last = t_call;
   auto stage = [&](const char* name) {
-    if (!trace) return;
-    if (strcmp(getenv("GPCA_TRACE"), "2") != 0) cudaStreamSynchronize(c->stream);   // "2": host-side times only
+    if (!trace && !diag) return;
+    if (diag || strcmp(getenv("GPCA_TRACE"), "2") != 0) cudaStreamSynchronize(c->stream);   // "2": host-side times only
     const auto now = std::chrono::steady_clock::now();
-    fprintf(stderr, "[gpca_eigensnp] %-28s %9.2f ms\n", name, std::chrono::duration<double, std::milli>(now - t_last).count());
+    const double ms = std::chrono::duration<double, std::milli>(now - t_last).count();
+    if (trace) fprintf(stderr, "[gpca_eigensnp] %-28s %9.2f ms\n", name, ms);
+    if (diag) {
+      std::string nm(name);
+      nm.erase(0, nm.find_first_not_of(' '));
+      diag_stages.push_back({nm, ms});
+    }
     t_last = now;
   };
+  const uint64_t launches0 = c->launches, collectives0 = c->collectives;
+  const double sk_bytes0 = c->sk_bytes;
+  const uint64_t sk_passes0 = c->sk_passes;
 
   c->es_pool.reset();
   // ---- subset of samples for the local bases ----------------------------------------------------------
@@ -648,8 +635,12 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
   stage("local bases");
   // ---- 3. condensed features (all N samples), Cn [N x R], then column standardisation -----------------------
   if (R == 0) return fail(c, GPCA_ERR_INVALID, "no condensed features");
+  // (row stride a multiple of 4 floats: 16-byte row pitch for the TMA loads of the dense products; pad columns zero)
+  const uint32_t ldc = (uint32_t)round_up(R, 4);
   DevBuf<float>& Cn = c->es_cn;
-  GPCA_CUDA_TRY(c, Cn.alloc(N * R));
+  GPCA_CUDA_TRY(c, Cn.alloc(N * ldc));
+  if (ldc != R)
+    GPCA_CUDA_TRY(c, cudaMemset2DAsync(Cn.p + R, (size_t)ldc * 4, 0, (size_t)(ldc - R) * 4, N, c->stream));
   if (batched) {
     // Consecutive blocks share a work item while their component counts fit the 32 accumulator columns: the operand
     // of a group is block-diagonal (rows = the group's slot range, block p's components in its own columns), so one
@@ -729,7 +720,7 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
         it.nst = blkG[g].nst;
         it.img_st0 = blkG[g].img_st0;
         it.blk = (uint32_t)g;
-        const uint64_t oo = rg * 256 * R + roff[grps[g].b0];
+        const uint64_t oo = rg * 256 * (uint64_t)ldc + roff[grps[g].b0];
         it.out_off_lo = (uint32_t)oo;
         it.out_off_hi = (uint32_t)(oo >> 32);
         itc.push_back(it);
@@ -743,7 +734,7 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
     pc.d_blocks = d_blkG.p; pc.n_blocks = (uint32_t)n_grps;
     pc.total_img_stages = img_stages_G; pc.max_K = max_KG;
     pc.Bin = Ugrp.p; pc.ld = 32; pc.f = d_inv.p; pc.e = d_mu.p; pc.a = nullptr; pc.b = nullptr;
-    pc.out = Cn.p; pc.ldo = (uint32_t)R;
+    pc.out = Cn.p; pc.ldo = ldc;
     pc.bytes = (double)N * (double)D / 4.0;
     GPCA_TRY(timed_sketch_batch(c, pc));
     GPCA_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
@@ -754,15 +745,17 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
     SketchProblem p2;
     p2.G.p = Et.p + o / 4; p2.G.pitch = Et.pitch; p2.G.rows = N; p2.G.cols = m; p2.G.avail = Et.pitch - o / 4;
     p2.l = cp[b]; p2.ld = cpb_max; p2.f = d_inv.p + o; p2.e = d_mu.p + o; p2.a = nullptr; p2.b = nullptr;
-    p2.Bin = Ubuf.p + o * cpb_max; p2.out = Cn.p + roff[b]; p2.ldo = (uint32_t)R;
+    p2.Bin = Ubuf.p + o * cpb_max; p2.out = Cn.p + roff[b]; p2.ldo = ldc;
     GPCA_TRY(timed_sketch(c, p2));
   }
   }
   stage("  condensed features");
+  // column moments of the condensed matrix (one read-only sweep); its standardised form is never written
+  PoolBuf<float> cmean(&c->es_pool), cinv(&c->es_pool), cmuinv(&c->es_pool);
   {
-    PoolBuf<float> cmean(&c->es_pool), cinv(&c->es_pool);
     GPCA_CUDA_TRY(c, cmean.alloc(R));
     GPCA_CUDA_TRY(c, cinv.alloc(R));
+    GPCA_CUDA_TRY(c, cmuinv.alloc(R));
     int nparts = (int)std::min<uint64_t>((N + 2047) / 2048, 64);
     if (nparts < 1) nparts = 1;
     const uint64_t rpc = (N + nparts - 1) / nparts;
@@ -770,29 +763,15 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
     PoolBuf<double> part(&c->es_pool);
     GPCA_CUDA_TRY(c, part.alloc((size_t)nparts * R * 2));
     dim3 g1(nparts, (unsigned)((R + 255) / 256));
-    col_moments_kernel<<<g1, 256, 0, c->stream>>>(Cn.p, N, (uint32_t)R, rpc, part.p);
+    col_moments_kernel<<<g1, 256, 0, c->stream>>>(Cn.p, N, (uint32_t)R, ldc, rpc, part.p);
     KCHECK(c);
-    col_finalize_kernel<<<(unsigned)((R + 255) / 256), 256, 0, c->stream>>>(part.p, nparts, N, (uint32_t)R, cmean.p, cinv.p);
+    col_finalize_kernel<<<(unsigned)((R + 255) / 256), 256, 0, c->stream>>>(part.p, nparts, N, (uint32_t)R, cmean.p, cinv.p,
+                                                                           cmuinv.p);
     KCHECK(c);
-    const uint64_t tot = N * R;
-    const int grid = (int)std::min<uint64_t>((tot + 255) / 256, (uint64_t)c->sm_count * 16);
-    col_apply_kernel<<<grid, 256, 0, c->stream>>>(Cn.p, N, (uint32_t)R, cmean.p, cinv.p);
-    KCHECK(c);
-    GPCA_CUDA_TRY(c, cudaStreamSynchronize(c->stream));   // temporaries above are freed on scope exit
   }
 
   stage("condense + standardise");
   // ---- 4. global randomized SVD of the condensed matrix (rows of C^T sharded by rank) ------------------------
-  // the cuBLAS handle is created once per context (creation costs ~100 ms) and kept for later calls
-  struct { cublasHandle_t h; } cb;
-  if (!c->cublas) {
-    cublasHandle_t h = nullptr;
-    GPCA_TRY(cublas_check(c, cublasCreate(&h), "create"));
-    c->cublas = (void*)h;
-  }
-  cb.h = (cublasHandle_t)c->cublas;
-  GPCA_TRY(cublas_check(c, cublasSetStream(cb.h, c->stream), "setStream"));
-  GPCA_TRY(cublas_check(c, cublasSetMathMode(cb.h, CUBLAS_PEDANTIC_MATH), "setMathMode"));
   uint64_t R_total = R;
   if (c->sharded()) {   // total condensed rows over all shards (f64 scalar through the exchange)
     PoolBuf<double> tmp(&c->es_pool);
@@ -825,24 +804,33 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
     KCHECK(c);
     GPCA_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   }
-  stage("  cublas handle + omega");
-  // Y = Cz^T-side sketch: Yg[N x lg] = Cn[N x R] * Om[R x lg]
-  GPCA_TRY(sgemm_rm(c, cb.h, false, (int)N, (int)lg, (int)R, Cn.p, (int)R, Om.p, (int)lg, Yg.p, (int)lg));
+  stage("  omega");
+  // products with the standardised condensed matrix Cz = (Cn - 1 mean^T) diag(1/sd), through its scales:
+  //   Cz   W = Cn (W / sd) - 1 (mean / sd)^T W             [N x lg]   (rows = samples)
+  //   Cz^T Y = diag(1/sd) Cn^T Y - (mean / sd) (1^T Y)      [R x lg]   (rows = condensed features)
+  auto cz_times = [&](const float* w, float* y) -> int {
+    DenseProduct dp{Cn.p, N, R, ldc, false, w, lg, lg, cinv.p, cmuinv.p, nullptr, nullptr, y, lg};
+    return launch_dense_product(c, dp);
+  };
+  auto czt_times = [&](const float* y, float* z) -> int {
+    DenseProduct dp{Cn.p, N, R, ldc, true, y, lg, lg, nullptr, nullptr, cinv.p, cmuinv.p, z, lg};
+    return launch_dense_product(c, dp);
+  };
+  GPCA_TRY(cz_times(Om.p, Yg.p));                                        // Yg = Cz Omega
   GPCA_TRY(driver_allreduce(c, Yg.p, N * lg, 0));
   stage("  first gemm");
   for (uint32_t it = 0; it < cfg->global_power_iters; ++it) {
     // (only the small side -- the R condensed rows -- is re-orthonormalised inside the iteration; the N-row iterate is
     //  orthonormalised once, in front of the projection)
     if (orth_both) GPCA_TRY(orthonormalize(c, Yg.p, N, lg, lg, false, s));
-    // Zg[R x lg] = Cn^T * Yg
-    GPCA_TRY(sgemm_rm(c, cb.h, true, (int)R, (int)lg, (int)N, Cn.p, (int)R, Yg.p, (int)lg, Zg.p, (int)lg));
+    GPCA_TRY(czt_times(Yg.p, Zg.p));                                     // Zg = Cz^T Yg
     GPCA_TRY(orthonormalize(c, Zg.p, R, lg, lg, true, s));
-    GPCA_TRY(sgemm_rm(c, cb.h, false, (int)N, (int)lg, (int)R, Cn.p, (int)R, Zg.p, (int)lg, Yg.p, (int)lg));
+    GPCA_TRY(cz_times(Zg.p, Yg.p));                                      // Yg = Cz Q_z
     GPCA_TRY(driver_allreduce(c, Yg.p, N * lg, 0));
     stage("  power iteration");
   }
   GPCA_TRY(orthonormalize(c, Yg.p, N, lg, lg, false, s));
-  GPCA_TRY(sgemm_rm(c, cb.h, true, (int)R, (int)lg, (int)N, Cn.p, (int)R, Yg.p, (int)lg, Zg.p, (int)lg));   // B = Cz Q
+  GPCA_TRY(czt_times(Yg.p, Zg.p));                                       // B = Cz^T Q
   GPCA_TRY(launch_gram(c, Zg.p, R, lg, lg, s.G));
   GPCA_TRY(driver_allreduce(c, s.G, (uint64_t)lg * lg, 1));
   GPCA_TRY(launch_jacobi_eigh(c, s.G, lg, s.evals, s.evecs));
@@ -953,6 +941,47 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
   if (eigenvalues)
     for (uint32_t j = 0; j < k; ++j) eigenvalues[j] = h_lam[j] / (double)(N - 1);
   stage("outputs");
+  if (diag) {
+    char buf[512];
+    std::string j = "{\n  \"producer\": \"";
+    j += gpca_version();
+    j += "\",\n";
+    snprintf(buf, sizeof buf,
+             "  \"num_qc_samples\": %llu,\n  \"num_pca_snps\": %llu,\n  \"num_ld_blocks\": %llu,\n"
+             "  \"subset_samples\": %llu,\n  \"condensed_features\": %llu,\n  \"condensed_features_all_shards\": %llu,\n"
+             "  \"global_sketch_columns\": %u,\n  \"components\": %u,\n",
+             (unsigned long long)N, (unsigned long long)D, (unsigned long long)n_blocks, (unsigned long long)Ns,
+             (unsigned long long)R, (unsigned long long)R_total, lg, k);
+    j += buf;
+    snprintf(buf, sizeof buf,
+             "  \"layout\": \"%s\",\n  \"blocks_per_launch\": %s,\n  \"snp_major_rows_resident\": %llu,\n"
+             "  \"shards\": %d,\n  \"shard_offset\": %llu,\n  \"refine_passes\": %u,\n",
+             id_order ? "id order (resident matrices)" : "slot order (gathered copies)", batched ? "true" : "false",
+             (unsigned long long)(c->gs_win_rows ? c->gs_res_rows : D), c->comm_world, (unsigned long long)c->shard_offset, passes);
+    j += buf;
+    snprintf(buf, sizeof buf,
+             "  \"kernel_launches\": %llu,\n  \"collectives\": %llu,\n  \"sketch_passes\": %llu,\n"
+             "  \"packed_genotype_bytes_streamed\": %.0f,\n  \"total_ms\": %.3f,\n",
+             (unsigned long long)(c->launches - launches0), (unsigned long long)(c->collectives - collectives0),
+             (unsigned long long)(c->sk_passes - sk_passes0), c->sk_bytes - sk_bytes0,
+             std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count());
+    j += buf;
+    j += "  \"eigenvalues\": [";
+    for (uint32_t q = 0; q < k; ++q) {
+      snprintf(buf, sizeof buf, "%s%.9g", q ? ", " : "", h_lam[q] / (double)(N - 1));
+      j += buf;
+    }
+    j += "],\n  \"stages_ms\": [\n";
+    for (size_t q = 0; q < diag_stages.size(); ++q) {
+      snprintf(buf, sizeof buf, "    {\"stage\": \"%s\", \"ms\": %.3f}%s\n", diag_stages[q].first.c_str(), diag_stages[q].second,
+               q + 1 < diag_stages.size() ? "," : "");
+      j += buf;
+    }
+    j += "  ]\n}\n";
+    c->es_diag_json = j;
+  }
   if (k_out) *k_out = k;
   return GPCA_OK;
 }
+
+extern "C" const char* gpca_eigensnp_diagnostics(const gpca_ctx* c) { return c ? c->es_diag_json.c_str() : ""; }

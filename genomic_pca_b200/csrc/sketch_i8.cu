@@ -1055,7 +1055,7 @@ int launch_sketch_i8(gpca_ctx* c, const SketchProblem& p) {
   if (const char* dbg = getenv("GPCA_DEBUG_GRID")) grid = (uint32_t)atoi(dbg);
   KernelTimer kt(c);
   sketch_i8_kernel<false><<<grid, NUM_THREADS, smem_bytes, c->stream>>>(tmap, tp);
-  kt.end();
+  kt.end(rows, K, ksplit, tp.n_items);
   c->launches++;
   GPCA_CUDA_TRY(c, cudaGetLastError());
   if (ksplit > 1) {

@@ -70,6 +70,11 @@ double gpca_sketch_kernel_ms(gpca_ctx* ctx);
  * cores / ranks so that the ranks do not oversubscribe the machine.  Stands in for `--threads` of the reference CLI
  * (src/main.rs:103-106, the global rayon pool). */
 int gpca_set_host_threads(gpca_ctx* ctx, uint32_t n_threads);
+/* Binds the calling thread -- and the threads created from it afterwards (the context's host pool) -- to the CPUs that
+ * sysfs lists next to the context's GPU (/sys/bus/pci/devices/<bus id>/local_cpulist), so that pinned payload buffers
+ * first touched afterwards (gpca_host_alloc) are NUMA-local to the GPU.  Call it once, right after gpca_init, from the
+ * thread that drives the context.  Returns the number of CPUs in the set (0: not available, nothing changed). */
+int gpca_bind_host_to_device(gpca_ctx* ctx);
 /* 1 = record CUDA events around every sketch pass so that gpca_sketch_stats / gpca_sketch_kernel_ms report device
  * times (benchmarks); 0 (default) = no events are created on the production path. */
 int gpca_set_sketch_timing(gpca_ctx* ctx, int on);
@@ -205,6 +210,15 @@ int gpca_get_standardized_block(gpca_ctx* ctx, const uint64_t* pca_snp_ids, uint
  * l <= 64.  ld = row stride in floats of both dense operands. */
 int gpca_sketch_snp_side(gpca_ctx* ctx, const float* dev_in, float* dev_out, uint32_t l, uint32_t ld);
 int gpca_sketch_sample_side(gpca_ctx* ctx, const float* dev_in, float* dev_out, uint32_t l, uint32_t ld);
+/* Product with a dense fp32 matrix C [n x r] (row stride ldc floats) on the device -- the condensed-feature matrix of
+ * EigenSNP's global randomized SVD (configured at src/main.rs:317-318), exported so that the kernel can be tested alone:
+ *   cols_mode = 0: dev_out[n x l] = a o (C   (f o dev_in[r x l])) - b (x) (e^T dev_in)     (rows = samples)
+ *   cols_mode = 1: dev_out[r x l] = a o (C^T (f o dev_in[n x l])) - b (x) (e^T dev_in)     (rows = columns of C)
+ * f / e index the reduction axis, a / b the output rows; any of them may be NULL (= 1).  Split-bf16 tensor-core
+ * arithmetic (about 2^-16 relative) for l <= 32 and ldc % 4 == 0, plain fp32/f64 otherwise. */
+int gpca_dense_product(gpca_ctx* ctx, const float* dev_c, uint64_t n, uint64_t r, uint32_t ldc, int cols_mode,
+                       const float* dev_in, uint32_t l, uint32_t ld, const float* dev_f, const float* dev_e,
+                       const float* dev_a, const float* dev_b, float* dev_out, uint32_t ldo);
 int gpca_synchronize(gpca_ctx* ctx);
 /* the CUDA stream (cudaStream_t) every kernel of this context is launched on -- for CUDA-event timing */
 void* gpca_get_stream(gpca_ctx* ctx);
@@ -213,7 +227,10 @@ void* gpca_get_stream(gpca_ctx* ctx);
 /* Replaces pca_runner::run_genomic_pca = PCA::rfit + PCA::transform (src/main.rs:598-679).
  * scores[N x k_out] f64 row-major (the reference's Array2<f64>), explained variance
  * eigenvalues[k_out] = s^2/(N-1), loadings[D x k_out] f32 (rotation; may be NULL).
- * oversample: src/main.rs:636 (10).  has_seed=0 mirrors `--rfit-seed` absent (entropy seed). */
+ * oversample: src/main.rs:636 (10).  has_seed=0 mirrors `--rfit-seed` absent (entropy seed; with the library's
+ * communicator shard 0's seed is broadcast, with the host hook an explicit seed is required).
+ * scores / eigenvalues may be NULL: the shards of a multi-GPU run all hold the same scores, and a host that reads
+ * them from one shard passes NULL on the others (no download, no widening to f64 there). */
 int gpca_rfit(gpca_ctx* ctx, uint32_t k, uint32_t oversample, uint32_t power_iters, uint64_t seed, int has_seed,
               double* scores, double* eigenvalues, float* loadings, uint32_t* k_out);
 
@@ -230,7 +247,7 @@ typedef struct gpca_eigensnp_cfg_s {     /* EigenSNPCoreAlgorithmConfig, src/mai
   uint64_t random_seed;                  /* --eigensnp-seed                2025  */
   uint32_t snp_processing_strip_size;    /* --eigensnp-snp-strip-size      2000 (accepted, unused: no strips on GPU) */
   uint32_t refine_pass_count;            /* --eigensnp-refine-passes       1     */
-  uint32_t collect_diagnostics;          /* accepted, ignored */
+  uint32_t collect_diagnostics;          /* --eigensnp-collect-diagnostics: keep a JSON record of the run (below) */
 } gpca_eigensnp_cfg;
 void gpca_eigensnp_default_cfg(gpca_eigensnp_cfg* cfg);
 
@@ -239,9 +256,17 @@ void gpca_eigensnp_default_cfg(gpca_eigensnp_cfg* cfg);
  * block_snp_ids[block_offsets[b] .. block_offsets[b+1]) (sorted within a block),
  * i.e. Vec<LdBlockSpecification> flattened (src/prepare.rs:1526-1549).
  * scores[N x k_out] f32, eigenvalues[k_out] f64, loadings[D x k_out] f32
- * (final_sample_principal_component_scores / _eigenvalues / final_snp_principal_component_loadings). */
+ * (final_sample_principal_component_scores / _eigenvalues / final_snp_principal_component_loadings).
+ * scores / eigenvalues / loadings may be NULL (see gpca_rfit). */
 int gpca_eigensnp(gpca_ctx* ctx, const gpca_eigensnp_cfg* cfg, const uint64_t* block_offsets, uint64_t n_blocks,
                   const uint64_t* block_snp_ids, float* scores, double* eigenvalues, float* loadings, uint32_t* k_out);
+
+/* Diagnostics of the last gpca_eigensnp call made with cfg->collect_diagnostics != 0, as a JSON document (shape of the
+ * run, layout decisions, per-stage device times, launches, collectives, eigenvalues); "" if none.  Stands in for the
+ * `<prefix>.eigensnp_diagnostics.json` the reference writes behind its eigensnp-diagnostics feature
+ * (src/main.rs:411-430) -- the schema of the external crate's FullPcaRunDetailedDiagnostics is not known here, so this
+ * is the library's own.  The pointer is valid until the next gpca_eigensnp / gpca_destroy on the context. */
+const char* gpca_eigensnp_diagnostics(const gpca_ctx* ctx);
 
 /* ---- host-side helpers of the path (no GPU needed) -------------------------------------- */
 /* map_snps_to_ld_blocks (src/prepare.rs:1424-1563) over parsed blocks.  Inputs per QC'd SNP

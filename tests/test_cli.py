@@ -100,8 +100,13 @@ def test_cli_eigensnp_workflow(tmp_path, gpu_ctx):
     out = tmp_path / "res" / "run"
     r = _run("--eigensnp", "--bed-file", str(tmp_path / "d.bed"), "--ld-block-file", str(tmp_path / "ld.txt"),
              "-o", str(out), "--eigensnp-k-global", "3", "--eigensnp-min-subset-size", "100",
-             "--eigensnp-max-subset-size", "300", "--eigensnp-subset-factor", "0.5", "--eigensnp-seed", "9")
+             "--eigensnp-max-subset-size", "300", "--eigensnp-subset-factor", "0.5", "--eigensnp-seed", "9",
+             "--eigensnp-collect-diagnostics")
     assert r.returncode == 0, r.stderr
+    import json
+    diag = json.loads((tmp_path / "res" / "run.eigensnp_diagnostics.json").read_text())      # main.rs:411-430
+    assert diag["num_qc_samples"] == 400 and diag["num_ld_blocks"] == 3 and diag["components"] == 3
+    assert [s["stage"] for s in diag["stages_ms"]][-1] == "outputs" and diag["kernel_launches"] > 0
     pcs = (tmp_path / "res" / "run.eigensnp.pca.tsv").read_text().splitlines()
     assert pcs[0] == "SampleID\tPC1\tPC2\tPC3" and len(pcs) == 401 and pcs[1].split("\t")[0] == "S0"
     evs = (tmp_path / "res" / "run.eigenvalues.tsv").read_text().splitlines()

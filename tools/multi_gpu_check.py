@@ -52,6 +52,10 @@ sc_e, ev_e, ld_e = ctx.eigensnp(blocks_for(d, nblk_shard), cfg)
 n_coll = ctx.collective_count
 sc_n, ev_n, _ = ctx.rfit(8, 10, power_iters=2, seed=None, want_loadings=False)     # entropy seed: broadcast from rank 0
 ctx.close()
+# the entropy seed came from rank 0: every rank must have sketched with the same test matrix -> identical scores
+same = [None] * world
+dist.all_gather_object(same, (ev_n.tobytes(), sc_n.tobytes()))
+entropy_seed_ranks_agree = all(x == same[0] for x in same)
 dist.barrier()
 out = {"world": world, "n": n, "m_shard": m_shard, "collectives": n_coll}
 if rank == 0:
@@ -68,8 +72,11 @@ if rank == 0:
     out["eigensnp_ev_relerr"] = float(np.abs(ev_e / ev1 - 1).max())
     out["eigensnp_angle"] = float(pca.subspace_angle(sc_e, sc1))
     out["eigensnp_loadings_angle_shard0"] = float(pca.subspace_angle(ld_e, ld1[:m_shard]))
+    # (a different test matrix: agreement only to the accuracy of the randomized method itself at k = 8, l = 18 on 21
+    #  structural components)
     out["rfit_entropy_seed_ev_relerr"] = float(np.abs(ev_n / ev0 - 1).max())
-    out["ok"] = bool(out["rfit_entropy_seed_ev_relerr"] < 1e-3 and out["rfit_ev_relerr"] < 1e-4 and out["rfit_angle"] < 1e-3 and out["eigensnp_ev_relerr"] < 1e-4
+    out["rfit_entropy_seed_ranks_agree"] = bool(entropy_seed_ranks_agree)
+    out["ok"] = bool(out["rfit_entropy_seed_ev_relerr"] < 0.1 and entropy_seed_ranks_agree and out["rfit_ev_relerr"] < 1e-4 and out["rfit_angle"] < 1e-3 and out["eigensnp_ev_relerr"] < 1e-4
                      and out["eigensnp_angle"] < 1e-3)
     print(json.dumps(out), flush=True)
 dist.barrier()
