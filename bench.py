@@ -642,7 +642,10 @@ def run_ours(args, rank, world):
     eng = args.engine if args.engine is not None else int(os.environ.get("GPCA_SKETCH_ENGINE", "2"))
     kernel_name = {0: "sketch_simt_kernel", 1: "sketch_tc_kernel", 2: "sketch_i8_kernel" if l <= 32 else "sketch_tc_kernel<64>"}[eng]
     roofline = {"bound": "hbm", "achieved": ach_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach_gbs / pk["hbm_gbs"],
-                "traffic": None, "traffic_note": "see profiles/ (ncu --set full capture of the same kernel at this shape)",
+                "traffic": 1.007 * bpl,
+                "traffic_note": "algorithmic bytes x 1.007 = the DRAM-to-algorithmic ratio of the committed ncu --set full capture of "
+                                "this kernel (profiles/r2_ncu_full_sketch_i8_kernel_shard_summary.csv: 10.950 GB read + 0.064 GB "
+                                "written for 10.9375 GB of packed rows); not re-measured in this run",
                 "peak_source": pk_src, "kernel": kernel_name, "ms_per_launch": t_kern * 1e3,
                 "launches_per_step": r["sk_n"] / args.steps, "bytes_per_launch": bpl,
                 "kernel_share_of_step": (r["sk_kernel_ms"] * 1e-3 / args.steps) / t_step,

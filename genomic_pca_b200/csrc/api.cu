@@ -1397,8 +1397,9 @@ extern "C" int gpca_sketch_stats(gpca_ctx* c, double* ms_total, double* bytes_to
     if (trace_launches && i < c->pending_kernel_notes.size()) {
       const auto& nt = c->pending_kernel_notes[i];
       const double gb = (double)nt.rows * (double)((nt.K + 3) / 4) * 1e-9;
-      fprintf(stderr, "[sketch kernel] rows %llu K %llu ksplit %u items %u: %.3f ms  %.1f GB/s\n",
-              (unsigned long long)nt.rows, (unsigned long long)nt.K, nt.ksplit, nt.items, ms, ms > 0 ? gb / (ms * 1e-3) : 0.0);
+      fprintf(stderr, "[sketch kernel] rows %llu K %llu ksplit %u %s items %u: %.3f ms  %.1f GB/s\n",
+              (unsigned long long)nt.rows, (unsigned long long)nt.K, nt.ksplit & 0xffffu,
+              (nt.ksplit & 0x10000u) ? "RT4" : "RT2", nt.items, ms, ms > 0 ? gb / (ms * 1e-3) : 0.0);
     }
     cudaEventDestroy(pr.first);
     cudaEventDestroy(pr.second);

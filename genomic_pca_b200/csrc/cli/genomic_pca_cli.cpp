@@ -16,7 +16,9 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -86,9 +88,42 @@ void usage() {
 // Rust `{:.6}` (src/main.rs:721,755,779,832) = the exact decimal expansion rounded half-to-even to six places, which
 // is what glibc's "%.6f" prints -- except NaN, which Rust spells "NaN" (no sign) where C prints "nan" / "-nan".
 // Negative zero keeps its sign and the infinities are "inf" / "-inf" in both.
+// Fast path for |v| < 2^52 / 1e6: v * 1e6 = p + e exactly with p the rounded product and e = fma(v, 1e6, -p) (1e6 is an
+// exact double), so rounding p + e half-to-even to an integer is decided without error; the digits are then printed
+// from the integer.  Everything else (huge values, infinities) goes through snprintf.  tests/test_cli.py compares the
+// output with an exact decimal expansion on random values and exact ties.
 inline int format_f6(char* out, size_t cap, double v) {
   if (v != v) return snprintf(out, cap, "NaN");
-  return snprintf(out, cap, "%.6f", v);
+  const double av = std::fabs(v);
+  if (!(av < 4.0e9) || cap < 24) return snprintf(out, cap, "%.6f", v);
+  const double p = av * 1e6;
+  const double e = std::fma(av, 1e6, -p);
+  double n = std::nearbyint(p);                 // ties-to-even on p (default rounding mode)
+  const double d = (p - n) + e;                 // exact: |p - n| <= 0.5 and e is tiny
+  const bool odd = std::fmod(n, 2.0) != 0.0;
+  if (d > 0.5 || (d == 0.5 && odd)) n += 1.0;
+  else if (d < -0.5 || (d == -0.5 && odd)) n -= 1.0;
+  uint64_t u = (uint64_t)n;
+  const uint64_t ip = u / 1000000u;
+  uint32_t fp = (uint32_t)(u % 1000000u);
+  char* q = out;
+  if (std::signbit(v)) *q++ = '-';
+  char tmp[24];
+  int len = 0;
+  uint64_t t = ip;
+  do {
+    tmp[len++] = (char)('0' + t % 10);
+    t /= 10;
+  } while (t);
+  while (len) *q++ = tmp[--len];
+  *q++ = '.';
+  for (int i = 5; i >= 0; --i) {
+    q[i] = (char)('0' + fp % 10);
+    fp /= 10;
+  }
+  q += 6;
+  *q = 0;
+  return (int)(q - out);
 }
 Args parse(int argc, char** argv) {
   Args a;
@@ -249,6 +284,37 @@ void write_eigenvalues(const std::string& prefix, const std::vector<double>& ev)
   fclose(f);
 }
 
+// (measurement hook) the loadings / scores writers at biobank row counts: `genomic_pca --bench-writers ROWS K PATH`
+int bench_writers(uint64_t rows, uint32_t k, const std::string& path) {
+  std::vector<float> vals(rows * k);
+  uint64_t x = 88172645463325252ull;
+  for (auto& v : vals) {
+    x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+    v = (float)((double)(x >> 11) / 9007199254740992.0 - 0.5);
+  }
+  const auto t0 = std::chrono::steady_clock::now();
+  FILE* f = fopen(path.c_str(), "w");
+  if (!f) die("cannot create " + path);
+  fputs("VariantID\tChrom\tPos", f);
+  for (uint32_t j = 1; j <= k; ++j) fprintf(f, "\tPC%u_loading", j);
+  fputc('\n', f);
+  write_rows_parallel(f, rows, 32 + 12 * (size_t)k, [&](uint64_t i, std::string& b) {
+    b += "rs";
+    b += std::to_string((unsigned long long)i);
+    b += "\t1\t";
+    b += std::to_string((unsigned long long)(1000 + 10 * i));
+    for (uint32_t j = 0; j < k; ++j) append_f6(b, (double)vals[i * k + j]);
+    b += '\n';
+  });
+  fclose(f);
+  const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  struct stat st;
+  stat(path.c_str(), &st);
+  printf("{\"rows\": %llu, \"k\": %u, \"seconds\": %.3f, \"bytes\": %lld, \"MB_per_s\": %.1f, \"threads\": %u}\n",
+         (unsigned long long)rows, k, s, (long long)st.st_size, (double)st.st_size / s / 1e6, std::thread::hardware_concurrency());
+  return 0;
+}
+
 void check(gpca_ctx* ctx, int rc, const char* what) {
   if (rc != GPCA_OK) die(std::string(what) + " failed: " + gpca_last_error(ctx));
 }
@@ -362,8 +428,30 @@ int run_vcf(const Args& a) {
   const double maf_thr = a.maf >= 0 ? a.maf : 0.01;                                 // vcf.rs:257
   std::vector<std::string> samples, ids;
   std::vector<uint8_t> dosage;                                                      // variant-major, D rows of N bytes
-  std::vector<uint8_t> tmp;
-  for (size_t fi = 0; fi < files.size(); ++fi) {
+  // the sample set comes from the header of the first file (main.rs:157-160); the files are then parsed concurrently,
+  // one task per file as the reference's par_iter does (main.rs:171-179), and aggregated in sorted-path order
+  // (vcf.rs:293-315)
+  {
+    GzLines in(files[0]);
+    std::string line;
+    while (in.next(line)) {
+      if (line.rfind("#CHROM", 0) == 0) {
+        std::stringstream ss(line);
+        std::string t;
+        int col = 0;
+        while (std::getline(ss, t, '\t')) if (col++ >= 9) samples.push_back(t);
+        break;
+      }
+      if (!line.empty() && line[0] != '#') break;
+    }
+    if (samples.empty()) die("VCF header from " + files[0] + " contains no samples.");   // vcf.rs:32
+  }
+  std::vector<std::vector<std::string>> ids_f(files.size());
+  std::vector<std::vector<uint8_t>> dosage_f(files.size());
+  auto parse_file = [&](size_t fi) {
+    std::vector<std::string>& ids = ids_f[fi];
+    std::vector<uint8_t>& dosage = dosage_f[fi];
+    std::vector<uint8_t> tmp;
     GzLines in(files[fi]);
     std::string line;
     std::vector<std::string> hdr_samples;
@@ -377,10 +465,7 @@ int run_vcf(const Args& a) {
           std::string t;
           int col = 0;
           while (std::getline(ss, t, '\t')) if (col++ >= 9) hdr_samples.push_back(t);
-          if (fi == 0) {
-            samples = hdr_samples;
-            if (samples.empty()) die("VCF header from " + files[fi] + " contains no samples.");   // vcf.rs:32
-          } else if (hdr_samples != samples) {
+          if (hdr_samples != samples) {
             die("Sample mismatch in VCF " + files[fi] + ": all VCFs must match the sample set of the first VCF (" + files[0] + ").");
           }
           if (!have_gt_format) die("GT key (FORMAT=GT) not found in FORMAT header for VCF " + files[fi]);   // vcf.rs:93
@@ -463,6 +548,23 @@ int run_vcf(const Args& a) {
       ids.push_back(std::string(fld[0], flen[0]) + ":" + std::string(fld[1], flen[1]) + ":" + ref + ":" + alt);
       dosage.insert(dosage.end(), tmp.begin(), tmp.end());
     }
+  };
+  {
+    unsigned hw = std::thread::hardware_concurrency();
+    if (hw == 0) hw = 4;
+    const size_t workers = std::min<size_t>(files.size(), a.threads > 0 ? (size_t)a.threads : hw);
+    std::atomic<size_t> next{0};
+    std::vector<std::thread> th;
+    for (size_t w = 0; w < workers; ++w)
+      th.emplace_back([&] {
+        for (size_t fi = next.fetch_add(1); fi < files.size(); fi = next.fetch_add(1)) parse_file(fi);
+      });
+    for (auto& t : th) t.join();
+  }
+  for (size_t fi = 0; fi < files.size(); ++fi) {
+    ids.insert(ids.end(), ids_f[fi].begin(), ids_f[fi].end());
+    dosage.insert(dosage.end(), dosage_f[fi].begin(), dosage_f[fi].end());
+    std::vector<uint8_t>().swap(dosage_f[fi]);
   }
   const uint64_t n = samples.size(), dvar = ids.size();
   if (dvar == 0) die("No variants passed filters across all VCF files. Cannot proceed with PCA.");   // main.rs:198
@@ -810,6 +912,8 @@ int run_eigensnp(const Args& a) {
 }  // namespace
 
 int main(int argc, char** argv) {
+  if (argc == 5 && std::string(argv[1]) == "--bench-writers")
+    return bench_writers(strtoull(argv[2], nullptr, 10), (uint32_t)atol(argv[3]), argv[4]);
   const Args a = parse(argc, argv);
   const auto t0 = std::chrono::steady_clock::now();
   const int rc = a.eigensnp ? run_eigensnp(a) : run_vcf(a);

@@ -22,30 +22,42 @@
 namespace {
 using namespace tcptx;
 
-constexpr int RT = 2;              // row tiles of 128 rows per CTA
+// Row tiles of 128 rows per CTA: a template parameter of the kernel.  RT = 2 (256 rows, 256 TMEM columns, two CTAs
+// per SM) is the general configuration.  RT = 4 (512 rows, the whole TMEM, one CTA per SM, 20 warps) shares every B'
+// stage between twice as many rows: the operand image comes out of L2 once per 512 rows instead of once per 256, which
+// halves the L2 -> SM operand traffic -- as large as the genotype stream itself at RT = 2 (a 16 KB image stage per
+// 16 KB of packed rows).  It is used for long items (launch_sketch_i8: the per-item epilogue is not overlapped by a
+// second CTA then).
 constexpr int STAGE_FIELDS = 256;  // 64 B per row per stage
 constexpr int CHUNKS = 4;          // 64-field chunks per stage
 // Bytes of a packed row per A stage = TMA box width.  Regular passes use 128 (two 256-field stages per A stage): 64-byte
 // boxes cap the TMA stream at ~2.6 TB/s when the row pitch is MBs -- one DRAM page per 64 B -- while 128-byte boxes
 // reach ~5.1 TB/s (tools/probe/tma_bw_probe.cu).  Item mode (batched LD blocks: one or two stages per item, bound by
 // the latency of an item rather than by bandwidth) keeps 64-byte boxes so that four stages can be in flight.
-template <bool ITEMS>
+template <bool ITEMS, int RT>
 struct ACfg {
   static constexpr int ROW_BYTES = ITEMS ? 64 : 128;
   static constexpr int HALVES = ROW_BYTES / 64;          // 256-field stages per A stage
   static constexpr int TILE_BYTES = 128 * ROW_BYTES;
-  static constexpr int STAGE_BYTES = 2 * TILE_BYTES;     // RT tiles
-  static constexpr int SA = 65536 / STAGE_BYTES;         // 64 KB of A stages either way
+  static constexpr int STAGE_BYTES = RT * TILE_BYTES;
+  static constexpr int RING_BYTES = 32768 * RT;          // 64 KB of A stages at RT = 2, 128 KB at RT = 4
+  static constexpr int SA = RING_BYTES / STAGE_BYTES;
+  static constexpr int NUM_THREADS = 128 + 128 * RT;     // warps 0..3: producers / issuer / idle; then 4 expander warps per row tile
+                                                         // (a multiple of 4 warps: warp & 3 is the TMEM lane quarter of the warp)
+  static constexpr int TMEM_COLS = RT == 2 ? 256 : 512;
+  static constexpr int A_COL0 = RT * 64;                 // accumulators: RT * 64 columns, then SLOTS * RT * 32 columns of A slots
+  static constexpr int CTAS_PER_SM = RT == 2 ? 2 : 1;
 };
-constexpr int NUM_THREADS = 384;   // 12 warps: a multiple of 4, so that warp & 3 is the TMEM lane quarter of the warp for every co-resident CTA (warp 3 idles)
 constexpr int NL = 32;             // logical columns
 constexpr int NM = 64;             // MMA N = hi | lo limbs
 #ifndef GPCA_I8_REGSPLIT
 #define GPCA_I8_REGSPLIT 1
 #endif
+// (RT = 2: 384 threads compiled at 80 registers; warpgroup 0 gives 128 x 48 registers up, the two expander warpgroups
+//  take 256 x 24.  RT = 4 runs one CTA per SM at the compiled allocation.)
 #if GPCA_I8_REGSPLIT
-#define REG_DEC() asm volatile("setmaxnreg.dec.sync.aligned.u32 32;")
-#define REG_INC() asm volatile("setmaxnreg.inc.sync.aligned.u32 104;")
+#define REG_DEC() do { if (RT == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;"); } while (0)
+#define REG_INC() do { if (RT == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;"); } while (0)
 #else
 #define REG_DEC()
 #define REG_INC()
@@ -62,14 +74,15 @@ __device__ __forceinline__ uint32_t prof_clock() { uint32_t c; asm volatile("mov
 #define PROF_T(x)
 #define PROF_ADD(acc, t0)
 #endif
-constexpr int SB = 3, SLOTS = 2;   // a TMEM slot holds a chunk pair (128 fields) of both row tiles
-constexpr int A_RING_BYTES = 65536;
+#ifndef GPCA_I8_TILE_SYNC_DEFAULT
+#define GPCA_I8_TILE_SYNC_DEFAULT false
+#endif
+constexpr int SB = 3, SLOTS = 2;   // a TMEM slot holds a chunk pair (128 fields) of every row tile
 constexpr int B_STAGE_BYTES = STAGE_FIELDS * NM;       // 1 byte per element
-constexpr int TMEM_COLS = 256;
-constexpr int D_COL0 = 0;                              // RT * 64 accumulator columns
-constexpr int A_COL0 = RT * NM;                        // SLOTS * RT * 32 columns
-static_assert(RT * NM + SLOTS * RT * 32 <= TMEM_COLS, "TMEM budget");
-constexpr int SMEM_BYTES = A_RING_BYTES + SB * B_STAGE_BYTES + 256 + 320;
+constexpr int D_COL0 = 0;
+static_assert(2 * NM + SLOTS * 2 * 32 <= 256 && 4 * NM + SLOTS * 4 * 32 <= 512, "TMEM budget");
+template <int RT>
+constexpr int smem_bytes_for() { return 32768 * RT + SB * B_STAGE_BYTES + 384 + 320; }
 constexpr uint32_t MAX_STAGES_PER_ITEM = 20000;        // 3 * 128 * 256 * 20000 < 2^31: no int32 overflow
 
 // 16 fields of a word -> 4 registers of 4 x u8 (register j holds fields j, j+4, j+8, j+12)
@@ -109,7 +122,7 @@ struct ItemInfo {
   uint64_t out_off;   // element offset of the item's first output row
 };
 
-template <bool ITEMS>
+template <bool ITEMS, int RT>
 __device__ __forceinline__ ItemInfo decode_item(const I8Params& p, uint32_t item) {
   ItemInfo ii;
   if (ITEMS) {
@@ -143,27 +156,33 @@ __device__ __forceinline__ ItemInfo decode_item(const I8Params& p, uint32_t item
   return ii;
 }
 
-template <bool ITEMS>
-__global__ void __launch_bounds__(NUM_THREADS, 2) sketch_i8_kernel(const __grid_constant__ CUtensorMap tmap,
-                                                                    const I8Params p) {
+// TS (tile sync): the TMEM hand-over between expanders and the MMA issuer is per ROW TILE (barriers of 4 warps) instead
+// of per CTA (all 4 * RT expander warps): a tile's MMAs start as soon as its own four warps have stored their chunk pair,
+// and its warps get the slot back without waiting for the other tile's MMAs.
+template <bool ITEMS, int RT, bool TS>
+__global__ void __launch_bounds__(ACfg<ITEMS, RT>::NUM_THREADS, ACfg<ITEMS, RT>::CTAS_PER_SM)
+sketch_i8_kernel(const __grid_constant__ CUtensorMap tmap, const I8Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);
   const uint32_t a_ring = smem_base;
-  constexpr int A_ROW_BYTES = ACfg<ITEMS>::ROW_BYTES, HALVES = ACfg<ITEMS>::HALVES, A_TILE_BYTES = ACfg<ITEMS>::TILE_BYTES,
-                A_STAGE_BYTES = ACfg<ITEMS>::STAGE_BYTES, SA = ACfg<ITEMS>::SA;
-  static_assert(RT == 2 && SA * A_STAGE_BYTES == A_RING_BYTES && SA <= 4, "A ring layout");
+  using AC = ACfg<ITEMS, RT>;
+  constexpr int A_ROW_BYTES = AC::ROW_BYTES, HALVES = AC::HALVES, A_TILE_BYTES = AC::TILE_BYTES,
+                A_STAGE_BYTES = AC::STAGE_BYTES, SA = AC::SA, A_RING_BYTES = AC::RING_BYTES, TMEM_COLS = AC::TMEM_COLS,
+                A_COL0 = AC::A_COL0;
+  static_assert((RT == 2 || RT == 4) && SA * A_STAGE_BYTES == A_RING_BYTES && SA >= 2 && SA <= 4, "A ring layout");
   const uint32_t b_ring = smem_base + A_RING_BYTES;
   const uint32_t bars = b_ring + SB * B_STAGE_BYTES;
   auto bar_afull = [&](int s) { return bars + 8u * s; };
   auto bar_aempty = [&](int s) { return bars + 8u * (4 + s); };
   auto bar_bfull = [&](int s) { return bars + 8u * (8 + s); };
-  auto bar_tfull = [&](int j) { return bars + 8u * (12 + j); };
-  auto bar_tempty = [&](int j) { return bars + 8u * (20 + j); };
+  // TMEM slot barriers: one pair per slot, or (TS) one pair per (slot, row tile)
+  auto bar_tfull = [&](int j, int t) { return bars + 8u * (32 + (TS ? j * RT + t : j)); };
+  auto bar_tempty = [&](int j, int t) { return bars + 8u * (40 + (TS ? j * RT + t : j)); };
   auto bar_bempty = [&](int s) { return bars + 8u * (24 + s); };
   const uint32_t bar_accfull = bars + 8u * 28;
   const uint32_t bar_accempty = bars + 8u * 29;
   const uint32_t tmem_slot = bars + 8u * 30;
-  const uint32_t cvec_smem = bars + 256;
+  const uint32_t cvec_smem = bars + 384;
   float* cv_s = reinterpret_cast<float*>(smem_raw + (cvec_smem - smem_base));
 
   const int warp = threadIdx.x >> 5;
@@ -178,10 +197,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) sketch_i8_kernel(const __grid_
       mbar_init(bar_bfull(s), 1);
       mbar_init(bar_bempty(s), 1);
     }
-    for (int j = 0; j < SLOTS; ++j) {
-      mbar_init(bar_tfull(j), 4 * RT);
-      mbar_init(bar_tempty(j), 1);
-    }
+    for (int j = 0; j < SLOTS; ++j)
+      for (int t = 0; t < (TS ? RT : 1); ++t) {
+        mbar_init(bar_tfull(j, t), TS ? 4 : 4 * RT);
+        mbar_init(bar_tempty(j, t), 1);
+      }
     mbar_init(bar_accfull, 1);
     mbar_init(bar_accempty, 4 * RT);
     fence_barrier_init();
@@ -216,7 +236,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) sketch_i8_kernel(const __grid_
     PROF_DECL(c_wait = 0);
     PROF_T(t_role);
     for (uint32_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-      const ItemInfo ii = decode_item<ITEMS>(p, item);
+      const ItemInfo ii = decode_item<ITEMS, RT>(p, item);
       const int row0 = (int)ii.row0;
       if (is_a) {
         const uint32_t n_ast = (ii.nst + HALVES - 1) / HALVES;
@@ -267,7 +287,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) sketch_i8_kernel(const __grid_
     PROF_DECL(c_acc = 0, c_bfull = 0, c_tfull = 0);
     PROF_T(t_role);
     for (uint32_t item = blockIdx.x; item < p.n_items; item += gridDim.x, ++item_idx) {
-      const uint32_t nst = decode_item<ITEMS>(p, item).nst;
+      const uint32_t nst = decode_item<ITEMS, RT>(p, item).nst;
       PROF_T(t_a);
       mbar_wait(bar_accempty, (item_idx & 1u) ^ 1u);
       PROF_ADD(c_acc, t_a);
@@ -284,13 +304,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) sketch_i8_kernel(const __grid_
         for (int q = 0; q < CHUNKS; q += 2, ++cit) {
           const int slot = cit % SLOTS;
           const uint32_t sph = (cit / SLOTS) & 1u;
-          PROF_T(t_t);
-          mbar_wait(bar_tfull(slot), sph);
-          PROF_ADD(c_tfull, t_t);
-          tc_fence_after();
-          if (elect_one()) {
+          if (!TS) {
+            PROF_T(t_t);
+            mbar_wait(bar_tfull(slot, 0), sph);
+            PROF_ADD(c_tfull, t_t);
+            tc_fence_after();
+          }
 #pragma unroll
-            for (int t = 0; t < RT; ++t) {
+          for (int t = 0; t < RT; ++t) {
+            if (TS) {
+              PROF_T(t_t);
+              mbar_wait(bar_tfull(slot, t), sph);
+              PROF_ADD(c_tfull, t_t);
+              tc_fence_after();
+            }
+            if (elect_one()) {
               const uint32_t d_t = tmem_base + D_COL0 + t * NM;
               const uint32_t a_t = tmem_base + A_COL0 + (slot * RT + t) * 32;
 #pragma unroll
@@ -303,8 +331,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) sketch_i8_kernel(const __grid_
                 if (i == 0 && GPCA_KO_MMA) tc_mma_ts_i8(d_t, a_t + 8 * i, bdesc, idesc, acc_flag | (uint32_t)i);
 #endif
               }
+              if (TS || t == RT - 1) tc_commit(bar_tempty(slot, TS ? t : 0));
             }
-            tc_commit(bar_tempty(slot));
+            __syncwarp();
           }
           __syncwarp();
           acc_flag = 1;
@@ -337,7 +366,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) sketch_i8_kernel(const __grid_
     PROF_DECL(c_afull = 0, c_tempty = 0, c_st = 0, c_epi = 0, c_accfull = 0, c_ldtm = 0, c_ab = 0);
     PROF_T(t_role);
     for (uint32_t item = blockIdx.x; item < p.n_items; item += gridDim.x, ++item_idx) {
-      const ItemInfo ii = decode_item<ITEMS>(p, item);
+      const ItemInfo ii = decode_item<ITEMS, RT>(p, item);
       const uint32_t n_ast = (ii.nst + HALVES - 1) / HALVES;
       for (uint32_t a = 0; a < n_ast; ++a, ++it) {
         const int s = it % SA;
@@ -376,7 +405,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) sketch_i8_kernel(const __grid_
             expand_word_u8(v[q + 1].w, r1 + 12);
 #endif
             PROF_T(t_te);
-            mbar_wait(bar_tempty(slot), sph ^ 1u);      // the MMAs that read this slot have completed
+            mbar_wait(bar_tempty(slot, tile), sph ^ 1u);      // the MMAs that read this slot (of this tile: TS) have completed
             PROF_ADD(c_tempty, t_te);
             tc_fence_after();
             PROF_T(t_st);
@@ -391,7 +420,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) sketch_i8_kernel(const __grid_
 #endif
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_tfull(slot));
+            if (lane == 0) mbar_arrive(bar_tfull(slot, tile));
           }
         }
         // The stage is released only now: every register loaded from it has been consumed by the expansions above, so
@@ -961,35 +990,59 @@ int launch_sketch_i8(gpca_ctx* c, const SketchProblem& p) {
     c->launches++;
     GPCA_CUDA_TRY(c, cudaGetLastError());
   }
-  const uint32_t row_groups = (uint32_t)((rows + RT * 128 - 1) / (RT * 128));
-  const uint32_t slots = (uint32_t)c->sm_count * 2;
   // K split: the items are dealt round-robin to the persistent CTAs, so a launch lasts ceil(items / slots) item times.
   // Pick the split that minimises rounds x stages per item plus the per-item epilogue and the split-K partial traffic,
   // with at least four items per CTA.  Measured on one box against the old "about four items per CTA" rule: -2.5 % on
   // the snp-side pass of the config-4 shard (6 splits, 2,052 items, 7 full rounds instead of 4 splits / 5 rounds at
   // 92 %); neutral at config 3, where the old rule left six CTAs with a fifth item -- the stragglers run alone on their
   // SMs and at a higher clock, so the tail costs far less than its share of the items.
-  uint32_t ksplit = 1;
-  {
+  // The plan is made for both CTA shapes (RT = 2: 256 rows, two CTAs per SM; RT = 4: 512 rows, one CTA per SM).
+  struct Plan {
+    uint32_t ksplit, row_groups, slots;
+    double est_us;
+  };
+  auto make_plan = [&](int rt) {
+    Plan pl;
+    pl.row_groups = (uint32_t)((rows + rt * 128 - 1) / (rt * 128));
+    pl.slots = (uint32_t)c->sm_count * (rt == 2 ? 2u : 1u);
+    pl.ksplit = 1;
     const uint32_t max_split = std::max<uint32_t>(1u, (total_stages + 7) / 8);
-    const uint32_t hi = std::min<uint32_t>(max_split, (8 * slots + row_groups - 1) / row_groups + 1);
-    const double t_stage_us = (double)slots * 16384.0 / 4.2e6;          // one stage on every slot at ~4.2 TB/s
+    const uint32_t hi = std::min<uint32_t>(max_split, (8 * pl.slots + pl.row_groups - 1) / pl.row_groups + 1);
+    const double t_stage_us = (double)c->sm_count * 2.0 * 16384.0 / 4.2e6;   // one stage on every SM's rows at ~4.2 TB/s
+    const double t_item_us = rt == 2 ? 2.0 : 4.0;     // epilogue / hand-over per item (not hidden behind a second CTA at RT = 4)
     double best = 1e300;
     for (uint32_t ks = 1; ks <= hi; ++ks) {
       const uint32_t spp_c = (total_stages + ks - 1) / ks;
       const uint32_t ks_eff = (total_stages + spp_c - 1) / spp_c;
       if (ks_eff != ks) continue;                                        // same split as a smaller candidate
-      const uint64_t items = (uint64_t)row_groups * ks;
-      const uint64_t rounds = (items + slots - 1) / slots;
+      const uint64_t items = (uint64_t)pl.row_groups * ks;
+      const uint64_t rounds = (items + pl.slots - 1) / pl.slots;
       if (rounds < 4 && ks < hi) continue;      // at least four items per CTA when the K range allows it
-      double est = (double)rounds * ((double)spp_c * t_stage_us + 2.0);  // + ~2 us of epilogue / hand-over per item
+      double est = (double)rounds * ((double)spp_c * t_stage_us + t_item_us);
       if (ks > 1) est += (double)ks * (double)rows * 128.0 * 2.0 / 3.0e6;  // partials written and read back (~3 TB/s)
       if (est < best * 0.999) {
         best = est;
-        ksplit = ks;
+        pl.ksplit = ks;
       }
     }
-  }
+    pl.est_us = best;
+    return pl;
+  };
+  const Plan plan2 = make_plan(2), plan4 = make_plan(4);
+  // RT = 4 when its items are long (the epilogue is a small share) and its schedule is not worse by more than the
+  // operand traffic it saves (measured: DESIGN.md section 4)
+  const uint32_t spp4 = (total_stages + plan4.ksplit - 1) / plan4.ksplit;
+  // Measured (profiles/r2_wide_cta_ab.txt, same box, alternating): RT = 4 is SLOWER -- 3.10 vs 2.55 ms at the config-4
+  // shard (500,000 x 87,500), 25.0 vs 23.0 ms at 500,000 x 700,000, 1.95 vs 1.63 ms at 2,504 x 10M.  The image stream
+  // out of L2 is not what limits the pass; two independent CTA pipelines per SM hide each other's hand-overs, and a
+  // hand-over that waits for 16 warps instead of 8 costs more than the halved operand traffic saves.  The shape stays
+  // available for experiments (GPCA_I8_WIDE=1) and is kept bit-identical to the regular one by the tests.
+  (void)spp4;
+  bool wide = false;
+  if (const char* e = getenv("GPCA_I8_WIDE")) wide = atoi(e) != 0 && rows >= 512;
+  const Plan& plan = wide ? plan4 : plan2;
+  const uint32_t row_groups = plan.row_groups, slots = plan.slots;
+  uint32_t ksplit = plan.ksplit;
   if (getenv("GPCA_DEBUG_OLD_KSPLIT")) {      // the rule before the cost model (A/B)
     ksplit = 1;
     if (row_groups < 4 * slots) {
@@ -1039,7 +1092,7 @@ int launch_sketch_i8(gpca_ctx* c, const SketchProblem& p) {
     EncodeTiledFn enc = get_encode_fn_i8();
     const cuuint64_t dims[2] = {(cuuint64_t)(p.G.avail ? p.G.avail : p.G.pitch), (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)p.G.pitch};
-    const cuuint32_t box[2] = {ACfg<false>::ROW_BYTES, 128};
+    const cuuint32_t box[2] = {ACfg<false, 2>::ROW_BYTES, 128};
     const cuuint32_t estr[2] = {1, 1};
     if (!enc || enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)p.G.p, dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, l2_promotion(),
@@ -1048,14 +1101,27 @@ int launch_sketch_i8(gpca_ctx* c, const SketchProblem& p) {
       return GPCA_ERR_CUDA;
     }
   }
-  int smem_bytes = SMEM_BYTES;
-  if (const char* dbg = getenv("GPCA_DEBUG_SMEM_EXTRA")) smem_bytes += atoi(dbg);
-  GPCA_CUDA_TRY(c, cudaFuncSetAttribute(sketch_i8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   uint32_t grid = tp.n_items < slots ? tp.n_items : slots;
   if (const char* dbg = getenv("GPCA_DEBUG_GRID")) grid = (uint32_t)atoi(dbg);
   KernelTimer kt(c);
-  sketch_i8_kernel<false><<<grid, NUM_THREADS, smem_bytes, c->stream>>>(tmap, tp);
-  kt.end(rows, K, ksplit, tp.n_items);
+  if (wide) {
+    constexpr int smem4 = smem_bytes_for<4>();
+    GPCA_CUDA_TRY(c, cudaFuncSetAttribute(sketch_i8_kernel<false, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem4));
+    sketch_i8_kernel<false, 4, false><<<grid, ACfg<false, 4>::NUM_THREADS, smem4, c->stream>>>(tmap, tp);
+  } else {
+    int smem_bytes = smem_bytes_for<2>();
+    if (const char* dbg = getenv("GPCA_DEBUG_SMEM_EXTRA")) smem_bytes += atoi(dbg);
+    const char* tsv = getenv("GPCA_I8_TILE_SYNC");
+    const bool tile_sync = tsv ? atoi(tsv) != 0 : GPCA_I8_TILE_SYNC_DEFAULT;
+    if (tile_sync) {
+      GPCA_CUDA_TRY(c, cudaFuncSetAttribute(sketch_i8_kernel<false, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+      sketch_i8_kernel<false, 2, true><<<grid, ACfg<false, 2>::NUM_THREADS, smem_bytes, c->stream>>>(tmap, tp);
+    } else {
+      GPCA_CUDA_TRY(c, cudaFuncSetAttribute(sketch_i8_kernel<false, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+      sketch_i8_kernel<false, 2, false><<<grid, ACfg<false, 2>::NUM_THREADS, smem_bytes, c->stream>>>(tmap, tp);
+    }
+  }
+  kt.end(rows, K, ksplit | (wide ? 0x10000u : 0u), tp.n_items);
   c->launches++;
   GPCA_CUDA_TRY(c, cudaGetLastError());
   if (ksplit > 1) {
@@ -1146,7 +1212,7 @@ int launch_sketch_i8_batch(gpca_ctx* c, const SketchBatch& sb) {
     EncodeTiledFn enc = get_encode_fn_i8();
     const cuuint64_t dims[2] = {(cuuint64_t)(sb.G.avail ? sb.G.avail : sb.G.pitch), (cuuint64_t)sb.G.rows};
     const cuuint64_t strides[1] = {(cuuint64_t)sb.G.pitch};
-    const cuuint32_t box[2] = {ACfg<true>::ROW_BYTES, 128};
+    const cuuint32_t box[2] = {ACfg<true, 2>::ROW_BYTES, 128};
     const cuuint32_t estr[2] = {1, 1};
     if (!enc || enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)sb.G.p, dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, l2_promotion(),
@@ -1155,11 +1221,13 @@ int launch_sketch_i8_batch(gpca_ctx* c, const SketchBatch& sb) {
       return GPCA_ERR_CUDA;
     }
   }
-  GPCA_CUDA_TRY(c, cudaFuncSetAttribute(sketch_i8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  constexpr int SMEM_BYTES = smem_bytes_for<2>();
+  constexpr int NUM_THREADS = ACfg<true, 2>::NUM_THREADS;
+  GPCA_CUDA_TRY(c, cudaFuncSetAttribute(sketch_i8_kernel<true, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   const uint32_t slots = (uint32_t)c->sm_count * 2;
   const uint32_t grid = tp.n_items < slots ? tp.n_items : slots;
   KernelTimer kt(c);
-  sketch_i8_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, c->stream>>>(tmap, tp);
+  sketch_i8_kernel<true, 2, false><<<grid, NUM_THREADS, SMEM_BYTES, c->stream>>>(tmap, tp);
   kt.end();
   c->launches++;
   GPCA_CUDA_TRY(c, cudaGetLastError());

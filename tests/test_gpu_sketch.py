@@ -179,3 +179,34 @@ def test_rfit_reproducible_at_multi_item_scale(gpu_ctx):
     from oracle import pca
     assert np.abs(a[1] / c[1] - 1).max() < 1e-4
     assert pca.subspace_angle(a[0], c[0]) < 1e-3
+
+
+@pytest.mark.parametrize("switch", ["GPCA_I8_WIDE", "GPCA_I8_TILE_SYNC"])
+@pytest.mark.parametrize("ksplit", ["1", "3"])
+def test_int8_engine_variants_equal_regular(gpu_ctx, monkeypatch, ksplit, switch):
+    """Variants of the integer engine's schedule -- the 512-row CTA shape (one CTA per SM, the whole TMEM: every
+    operand-image stage shared by twice as many rows) and the per-row-tile TMEM hand-over -- against the regular kernel on
+    the same K split: the integer accumulation is exact and the fp32 epilogue is per row, so they must agree bit for bit
+    -- odd row counts, several items per CTA, both pass orientations, with and without split-K partials."""
+    n, m, l = 4000 + 77, 150_000, 30
+    d = _device_dataset(gpu_ctx, n, m)
+    dev = torch.device("cuda", 0)
+    gpu_ctx.set_sketch_engine(2)
+    monkeypatch.setenv("GPCA_DEBUG_KSPLIT", ksplit)
+    ext = torch.cuda.ExternalStream(gpu_ctx.stream)
+    with torch.cuda.stream(ext):
+        g = torch.Generator(device=dev)
+        g.manual_seed(11)
+        Bs = torch.randn(n, l, device=dev, generator=g)
+        Bd = torch.randn(d, l, device=dev, generator=g)
+        ext.synchronize()
+        for fn, src, rows in ((gpu_ctx.sketch_snp_side, Bs, d), (gpu_ctx.sketch_sample_side, Bd, n)):
+            outs = {}
+            for wide in ("0", "1", "1"):
+                monkeypatch.setenv(switch, wide)
+                o = torch.full((rows, l), float("nan"), device=dev)
+                fn(src.data_ptr(), o.data_ptr(), l, l)
+                gpu_ctx.synchronize()
+                outs.setdefault(wide, []).append(o.cpu().numpy())
+            assert np.isfinite(outs["1"][0]).all()
+            assert np.array_equal(outs["0"][0], outs["1"][0]) and np.array_equal(outs["1"][0], outs["1"][1])
