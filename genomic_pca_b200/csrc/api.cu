@@ -203,6 +203,7 @@ static size_t eigensnp_buffer_bytes(const gpca_ctx* c) {
 }
 
 static void reset_loaded(gpca_ctx* c, bool keep_eigensnp_buffers = false) {
+  c->data_version++;
   c->have_counts = false;   // (the host vectors keep their storage: re-growing them would zero-fill hundreds of MB)
   c->D = 0;
   c->Gs = PackedMat();
@@ -441,6 +442,7 @@ static int derive_pca_vectors(gpca_ctx* c, uint64_t D) {
 static int build_pca_set(gpca_ctx* c, uint64_t D) {
   // c->pca_idx, c->h_mean, c->h_sd are filled; derive the device-side vectors and the resident copies
   GPCA_TRY(derive_pca_vectors(c, D));
+  c->data_version++;
   c->D = D;
   c->Gs.rows = D;
   c->Gs.cols = c->N;
@@ -512,6 +514,7 @@ static int reselect_resident(gpca_ctx* c, const uint64_t* snp_idx, uint64_t Dn, 
   c->h_mean.assign(mean, mean + Dn);
   c->h_sd.assign(sd, sd + Dn);
   GPCA_TRY(derive_pca_vectors(c, Dn));
+  c->data_version++;
   c->D = Dn;
   c->Gs.rows = Dn;
   c->Gt.cols = Dn;

@@ -149,6 +149,8 @@ struct gpca_ctx {
   ScratchPool es_pool;                                        // EigenSNP call-scoped temporaries
   std::vector<int64_t> es_subset;                             // the N_s-sample subset of the last EigenSNP call
   uint64_t es_subset_n = 0, es_subset_seed = 0;
+  // every change of the resident matrices bumps data_version; the subset copies of EigenSNP remember which one they were made from
+  uint64_t data_version = 1, es_sub_copies_version = 0, es_sub_copies_ns = 0, es_sub_copies_seed = 0;
   DevBuf<float> es_cn;                                        // EigenSNP condensed features
   std::string es_diag_json;                                   // diagnostics of the last gpca_eigensnp call that collected them
   // streaming ingest (gpca_ingest_bed): a ring of device staging buffers for the payload chunks, the sample-gathered
