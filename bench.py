@@ -374,6 +374,7 @@ def timed_rfit(torch, dist, ctx, dev, world, steps, warmup, rfit_out, sample_clo
     sk_kernel_ms = ctx.last_kernel_ms
     t_step = max_over_ranks(torch, dist, dev, world, [dev_s / steps])[0]
     return {"t_step": t_step, "wall_per_step": wall / steps, "clocks": clocks, "launches": launches, "sk_ms": sk_ms,
+            "engine": ctx.last_sketch_engine,
             "sk_n": sk_n, "sk_kernel_ms": sk_kernel_ms, "eigenvalues": ev, "scores": sc,
             "collectives_per_step": (ctx.collective_count - coll0) / steps}
 
@@ -639,7 +640,7 @@ def run_ours(args, rank, world):
     flops_per_launch = 2.0 * 4.0 * bpl * (K_COMPONENTS + OVERSAMPLE)
     ach_tf = flops_per_launch / t_kern / 1e12 if t_kern > 0 else 0.0
     l = K_COMPONENTS + OVERSAMPLE
-    eng = args.engine if args.engine is not None else int(os.environ.get("GPCA_SKETCH_ENGINE", "2"))
+    eng = r["engine"]          # the engine that actually ran (the library falls back by shape / l)
     kernel_name = {0: "sketch_simt_kernel", 1: "sketch_tc_kernel", 2: "sketch_i8_kernel" if l <= 32 else "sketch_tc_kernel<64>"}[eng]
     roofline = {"bound": "hbm", "achieved": ach_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach_gbs / pk["hbm_gbs"],
                 "traffic": 1.007 * bpl,

@@ -85,6 +85,7 @@ _sig("gpca_launch_count", C.c_uint64, C.c_void_p)
 _sig("gpca_reset_launch_count", None, C.c_void_p)
 _sig("gpca_set_sketch_engine", C.c_int, C.c_void_p, C.c_int)
 _sig("gpca_set_batch_blocks", C.c_int, C.c_void_p, C.c_int)
+_sig("gpca_last_sketch_engine", C.c_int, C.c_void_p)
 _sig("gpca_ingest_bed_file", C.c_int, C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p,
      C.c_double, _u8p, _f32p, _f32p, _u8p, _u64p)
 _sig("gpca_ingest_bed_file_rows", C.c_int, C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p,
@@ -287,6 +288,11 @@ class Context:
     @property
     def collective_count(self) -> int:
         return int(lib.gpca_collective_count(self._h))
+
+    @property
+    def last_sketch_engine(self) -> int:
+        """the engine the last sketch pass actually ran on (0 SIMT, 1 tcgen05 f16, 2 tcgen05 i8)"""
+        return int(lib.gpca_last_sketch_engine(self._h))
 
     def set_batch_blocks(self, on: bool):
         self._chk(lib.gpca_set_batch_blocks(self._h, 1 if on else 0))

@@ -95,6 +95,7 @@ extern "C" int gpca_set_sketch_engine(gpca_ctx* c, int engine) {
   c->engine = engine;
   return GPCA_OK;
 }
+extern "C" int gpca_last_sketch_engine(const gpca_ctx* c) { return c ? c->last_engine : -1; }
 extern "C" int gpca_set_batch_blocks(gpca_ctx* c, int on) {
   CHECK_CTX(c);
   c->batch_blocks = on ? 1 : 0;

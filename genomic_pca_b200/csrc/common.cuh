@@ -112,6 +112,7 @@ struct gpca_ctx {
   std::string err;
   uint64_t launches = 0;
   int engine = 2;   // 0 SIMT fp32, 1 tcgen05 f16, 2 tcgen05 i8 (default; l > 32 falls back to 1)
+  int last_engine = -1;   // the engine the last regular sketch pass actually ran on
   int batch_blocks = 1;   // EigenSNP: all LD blocks per launch (needs engine 2); 0 = one block at a time
 
   // exchange between shards: the library's own NCCL communicator (gpca_comm_init, comm.cu) or a host-provided hook

@@ -286,11 +286,14 @@ int launch_sketch(gpca_ctx* c, const SketchProblem& p) {
   if (c->engine == 2 && sketch_i8_supported(c, p)) {
     rc = launch_sketch_i8(c, p);
     done = true;
+    c->last_engine = 2;
   } else if (c->engine >= 1 && sketch_tc_supported(c, p)) {
     rc = launch_sketch_tc(c, p);
     done = true;
+    c->last_engine = 1;
   }
   if (!done) {
+    c->last_engine = 0;
     const uint64_t Kpad = round_up(p.G.cols, 32);
     if (p.l <= 32) {
       GPCA_TRY(run_prep<32>(c, p, Kpad));

@@ -55,6 +55,8 @@ void gpca_reset_launch_count(gpca_ctx* ctx);
 /* 0 = SIMT fp32 path, 1 = tcgen05 f16 path, 2 = tcgen05 i8 path (exact integer accumulation, l <= 32);
  * engines 1/2 fall back to the next lower one for shapes they do not take */
 int gpca_set_sketch_engine(gpca_ctx* ctx, int engine);
+/* the engine the last (non-batched) sketch pass actually ran on: 0 / 1 / 2, -1 before the first pass */
+int gpca_last_sketch_engine(const gpca_ctx* ctx);
 /* EigenSNP local bases / condensed features: 1 (default) = every LD block in one launch per stage (integer engine,
  * no missing calls; other cases use the per-block path automatically), 0 = always one block at a time.
  * Replaces the per-block loop inside EigenSNPCoreAlgorithm::compute_pca (call site src/main.rs:365). */
