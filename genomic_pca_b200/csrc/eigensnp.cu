@@ -745,6 +745,7 @@ extern "C" int gpca_eigensnp(gpca_ctx* c, const gpca_eigensnp_cfg* cfg, const ui
     pc.Bin = Ugrp.p; pc.ld = 32; pc.f = d_inv.p; pc.e = d_mu.p; pc.a = nullptr; pc.b = nullptr;
     pc.out = Cn.p; pc.ldo = ldc;
     pc.bytes = (double)N * (double)D / 4.0;
+    pc.wide_boxes = Et.pitch >= 32768 && max_KG >= 4 * 256;      // long items, row pitch of tens of KB: TMA-stream-bound
     GPCA_TRY(timed_sketch_batch(c, pc));
     GPCA_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   } else {

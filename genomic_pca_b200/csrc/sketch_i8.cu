@@ -34,9 +34,10 @@ constexpr int CHUNKS = 4;          // 64-field chunks per stage
 // boxes cap the TMA stream at ~2.6 TB/s when the row pitch is MBs -- one DRAM page per 64 B -- while 128-byte boxes
 // reach ~5.1 TB/s (tools/probe/tma_bw_probe.cu).  Item mode (batched LD blocks: one or two stages per item, bound by
 // the latency of an item rather than by bandwidth) keeps 64-byte boxes so that four stages can be in flight.
-template <bool ITEMS, int RT>
+// BOX = bytes of a packed row per TMA box (64 or 128), see the comment above
+template <int BOX, int RT>
 struct ACfg {
-  static constexpr int ROW_BYTES = ITEMS ? 64 : 128;
+  static constexpr int ROW_BYTES = BOX;
   static constexpr int HALVES = ROW_BYTES / 64;          // 256-field stages per A stage
   static constexpr int TILE_BYTES = 128 * ROW_BYTES;
   static constexpr int STAGE_BYTES = RT * TILE_BYTES;
@@ -159,13 +160,13 @@ __device__ __forceinline__ ItemInfo decode_item(const I8Params& p, uint32_t item
 // TS (tile sync): the TMEM hand-over between expanders and the MMA issuer is per ROW TILE (barriers of 4 warps) instead
 // of per CTA (all 4 * RT expander warps): a tile's MMAs start as soon as its own four warps have stored their chunk pair,
 // and its warps get the slot back without waiting for the other tile's MMAs.
-template <bool ITEMS, int RT, bool TS>
-__global__ void __launch_bounds__(ACfg<ITEMS, RT>::NUM_THREADS, ACfg<ITEMS, RT>::CTAS_PER_SM)
+template <bool ITEMS, int RT, bool TS, int BOX>
+__global__ void __launch_bounds__(ACfg<BOX, RT>::NUM_THREADS, ACfg<BOX, RT>::CTAS_PER_SM)
 sketch_i8_kernel(const __grid_constant__ CUtensorMap tmap, const I8Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);
   const uint32_t a_ring = smem_base;
-  using AC = ACfg<ITEMS, RT>;
+  using AC = ACfg<BOX, RT>;
   constexpr int A_ROW_BYTES = AC::ROW_BYTES, HALVES = AC::HALVES, A_TILE_BYTES = AC::TILE_BYTES,
                 A_STAGE_BYTES = AC::STAGE_BYTES, SA = AC::SA, A_RING_BYTES = AC::RING_BYTES, TMEM_COLS = AC::TMEM_COLS,
                 A_COL0 = AC::A_COL0;
@@ -1092,7 +1093,7 @@ int launch_sketch_i8(gpca_ctx* c, const SketchProblem& p) {
     EncodeTiledFn enc = get_encode_fn_i8();
     const cuuint64_t dims[2] = {(cuuint64_t)(p.G.avail ? p.G.avail : p.G.pitch), (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)p.G.pitch};
-    const cuuint32_t box[2] = {ACfg<false, 2>::ROW_BYTES, 128};
+    const cuuint32_t box[2] = {128, 128};
     const cuuint32_t estr[2] = {1, 1};
     if (!enc || enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)p.G.p, dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, l2_promotion(),
@@ -1106,19 +1107,19 @@ int launch_sketch_i8(gpca_ctx* c, const SketchProblem& p) {
   KernelTimer kt(c);
   if (wide) {
     constexpr int smem4 = smem_bytes_for<4>();
-    GPCA_CUDA_TRY(c, cudaFuncSetAttribute(sketch_i8_kernel<false, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem4));
-    sketch_i8_kernel<false, 4, false><<<grid, ACfg<false, 4>::NUM_THREADS, smem4, c->stream>>>(tmap, tp);
+    GPCA_CUDA_TRY(c, cudaFuncSetAttribute(sketch_i8_kernel<false, 4, false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem4));
+    sketch_i8_kernel<false, 4, false, 128><<<grid, ACfg<128, 4>::NUM_THREADS, smem4, c->stream>>>(tmap, tp);
   } else {
     int smem_bytes = smem_bytes_for<2>();
     if (const char* dbg = getenv("GPCA_DEBUG_SMEM_EXTRA")) smem_bytes += atoi(dbg);
     const char* tsv = getenv("GPCA_I8_TILE_SYNC");
     const bool tile_sync = tsv ? atoi(tsv) != 0 : GPCA_I8_TILE_SYNC_DEFAULT;
     if (tile_sync) {
-      GPCA_CUDA_TRY(c, cudaFuncSetAttribute(sketch_i8_kernel<false, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-      sketch_i8_kernel<false, 2, true><<<grid, ACfg<false, 2>::NUM_THREADS, smem_bytes, c->stream>>>(tmap, tp);
+      GPCA_CUDA_TRY(c, cudaFuncSetAttribute(sketch_i8_kernel<false, 2, true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+      sketch_i8_kernel<false, 2, true, 128><<<grid, ACfg<128, 2>::NUM_THREADS, smem_bytes, c->stream>>>(tmap, tp);
     } else {
-      GPCA_CUDA_TRY(c, cudaFuncSetAttribute(sketch_i8_kernel<false, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-      sketch_i8_kernel<false, 2, false><<<grid, ACfg<false, 2>::NUM_THREADS, smem_bytes, c->stream>>>(tmap, tp);
+      GPCA_CUDA_TRY(c, cudaFuncSetAttribute(sketch_i8_kernel<false, 2, false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+      sketch_i8_kernel<false, 2, false, 128><<<grid, ACfg<128, 2>::NUM_THREADS, smem_bytes, c->stream>>>(tmap, tp);
     }
   }
   kt.end(rows, K, ksplit | (wide ? 0x10000u : 0u), tp.n_items);
@@ -1148,6 +1149,8 @@ bool sketch_i8_batch_supported(gpca_ctx* c) {
 
 int launch_sketch_i8_batch(gpca_ctx* c, const SketchBatch& sb) {
   if (sb.n_items == 0 || sb.n_blocks == 0) return GPCA_OK;
+  bool wide_boxes = sb.wide_boxes && (sb.G.avail ? sb.G.avail : sb.G.pitch) >= 128;
+  if (const char* e = getenv("GPCA_I8_ITEM_BOX")) wide_boxes = atoi(e) == 128 && (sb.G.avail ? sb.G.avail : sb.G.pitch) >= 128;
   if (sb.G.pitch % 16 != 0 || (reinterpret_cast<uintptr_t>(sb.G.p) & 15) != 0 || sb.G.rows < 128 ||
       (sb.G.avail ? sb.G.avail : sb.G.pitch) < 64) {
     c->set_error("sketch_i8_batch: unsupported matrix shape");
@@ -1212,22 +1215,31 @@ int launch_sketch_i8_batch(gpca_ctx* c, const SketchBatch& sb) {
     EncodeTiledFn enc = get_encode_fn_i8();
     const cuuint64_t dims[2] = {(cuuint64_t)(sb.G.avail ? sb.G.avail : sb.G.pitch), (cuuint64_t)sb.G.rows};
     const cuuint64_t strides[1] = {(cuuint64_t)sb.G.pitch};
-    const cuuint32_t box[2] = {ACfg<true, 2>::ROW_BYTES, 128};
+    // Box width: items of one or two stages are bound by their own latency and keep 64-byte boxes (four stages in
+    // flight); long items on a matrix whose row pitch is tens of KB and more (the condensed-feature pass at 500,000 x
+    // 700,000: 7-stage items, 175 KB pitch) are bound by the TMA stream, which 64-byte boxes cap at about half of what
+    // 128-byte boxes reach -- one DRAM page per box (tools/probe/tma_bw_probe.cu).
+    const cuuint32_t box[2] = {wide_boxes ? 128u : 64u, 128};
     const cuuint32_t estr[2] = {1, 1};
     if (!enc || enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)sb.G.p, dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, l2_promotion(),
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, wide_boxes ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                    l2_promotion(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
       c->set_error("sketch_i8_batch: cuTensorMapEncodeTiled failed");
       return GPCA_ERR_CUDA;
     }
   }
   constexpr int SMEM_BYTES = smem_bytes_for<2>();
-  constexpr int NUM_THREADS = ACfg<true, 2>::NUM_THREADS;
-  GPCA_CUDA_TRY(c, cudaFuncSetAttribute(sketch_i8_kernel<true, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  constexpr int NUM_THREADS = ACfg<64, 2>::NUM_THREADS;
   const uint32_t slots = (uint32_t)c->sm_count * 2;
   const uint32_t grid = tp.n_items < slots ? tp.n_items : slots;
   KernelTimer kt(c);
-  sketch_i8_kernel<true, 2, false><<<grid, NUM_THREADS, SMEM_BYTES, c->stream>>>(tmap, tp);
+  if (wide_boxes) {
+    GPCA_CUDA_TRY(c, cudaFuncSetAttribute(sketch_i8_kernel<true, 2, false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    sketch_i8_kernel<true, 2, false, 128><<<grid, NUM_THREADS, SMEM_BYTES, c->stream>>>(tmap, tp);
+  } else {
+    GPCA_CUDA_TRY(c, cudaFuncSetAttribute(sketch_i8_kernel<true, 2, false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    sketch_i8_kernel<true, 2, false, 64><<<grid, NUM_THREADS, SMEM_BYTES, c->stream>>>(tmap, tp);
+  }
   kt.end();
   c->launches++;
   GPCA_CUDA_TRY(c, cudaGetLastError());

@@ -50,6 +50,7 @@ struct SketchBatch {
   float* out;
   uint32_t ldo;
   double bytes;                      // algorithmic bytes of the pass (statistics)
+  bool wide_boxes = false;           // 128-byte TMA boxes (long items on a matrix with a large row pitch), else 64-byte
 };
 bool sketch_i8_batch_supported(gpca_ctx* c);
 int launch_sketch_i8_batch(gpca_ctx* c, const SketchBatch& sb);

@@ -221,3 +221,34 @@ def test_eigensnp_shifted_copy_and_block_groups(gpu_ctx, monkeypatch):
                                     refine_passes=1)
     assert np.abs(ev / ev_o - 1).max() < 1e-4
     assert pca.subspace_angle(sc, sc_o) < 1e-3
+
+
+def test_eigensnp_item_passes_with_128_byte_boxes(gpu_ctx, monkeypatch):
+    """The batched per-LD-block passes with 128-byte TMA boxes (the shape the condensed-feature pass takes on matrices
+    with a large row pitch) against 64-byte boxes: exact integer accumulation on the same fields -> bit-identical
+    results; block sizes from 1 SNP to several stages, none aligned to a box."""
+    import genomic_pca_b200 as gp
+    S = _prep(gpu_ctx, 1000, 5000, 5, seed=52)
+    d = S.shape[0]
+    sizes = [65, 63, 1, 255, 257, 300, 130, 5, 700, 412, 412, 412, 412, 100, 1025]
+    edges = [0]
+    for sz in sizes:
+        if edges[-1] + sz < d:
+            edges.append(edges[-1] + sz)
+    edges.append(d)
+    blocks = [np.arange(edges[i], edges[i + 1]) for i in range(len(edges) - 1)]
+    cfg = gp.EigenSnpConfig(target_num_global_pcs=4, components_per_ld_block=7, subset_factor=0.5, min_subset_size=300,
+                            max_subset_size=700, local_oversampling=6, global_oversampling=8, random_seed=21,
+                            refine_pass_count=1)
+    gpu_ctx.set_sketch_engine(2)
+    gpu_ctx.set_batch_blocks(True)
+    monkeypatch.setenv("GPCA_I8_ITEM_BOX", "64")
+    r64 = gpu_ctx.eigensnp(blocks, cfg)
+    monkeypatch.setenv("GPCA_I8_ITEM_BOX", "128")
+    r128 = gpu_ctx.eigensnp(blocks, cfg)
+    assert all(np.array_equal(a, b) for a, b in zip(r64, r128))
+    monkeypatch.setenv("GPCA_DEBUG_NO_ID_ORDER", "1")          # ... and on the slot-ordered copies
+    r128s = gpu_ctx.eigensnp(blocks, cfg)
+    monkeypatch.setenv("GPCA_I8_ITEM_BOX", "64")
+    r64s = gpu_ctx.eigensnp(blocks, cfg)
+    assert all(np.array_equal(a, b) for a, b in zip(r64s, r128s))
