@@ -478,6 +478,11 @@ def run_c3(args, torch, gp, dev, pk, pk_src):
         payload = torch.empty((m, bps), dtype=torch.uint8, device=dev)
         gen = gp.Context(dev.index or 0)
         gen.synth_bed_device(payload.data_ptr(), n, m, 0, DATA_SEED, N_POPS, FST, 0.0, FST_GRADE)
+        # K-a alone (the decode / allele-count kernel of the ingest) on the resident payload: HBM-bound
+        ka_ms = gen.count_kernel_ms(payload.data_ptr(), n, m - 1, reps=10)      # (m - 1 rows: 16 readable bytes past the end)
+        rec["ka_counts_kernel"] = {"ms_per_launch": ka_ms, "bytes": int((m - 1) * bps), "achieved_GBps": (m - 1) * bps / ka_ms / 1e6,
+                                   "frac_of_hbm_peak": (m - 1) * bps / ka_ms / 1e6 / pk["hbm_gbs"],
+                                   "note": "chunk_counts_kernel on 626-byte rows at the file pitch (unaligned rows)"}
         gen.close()
         ev_x, v_x = exact_pca_f64(torch, payload, n, np.asarray(keep[:m], dtype=bool), mean[:m], sd[:m], K_COMPONENTS + 1)
         del payload

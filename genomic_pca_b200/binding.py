@@ -104,6 +104,7 @@ _sig("gpca_eigensnp_workspace_bytes", C.c_uint64, C.c_uint64, C.c_uint64, C.c_ui
 _sig("gpca_set_ingest_mask", C.c_int, C.c_void_p, _u8p, C.c_uint64)
 _sig("gpca_synth_bed_host", C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32,
      C.c_double, C.c_double, C.c_double)
+_sig("gpca_count_kernel_ms", C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, _f64p)
 _sig("gpca_host_alloc", C.c_void_p, C.c_void_p, C.c_uint64)
 _sig("gpca_host_free", None, C.c_void_p, C.c_void_p, C.c_uint64)
 _sig("gpca_comm_unique_id", C.c_int, _u8p)
@@ -231,6 +232,12 @@ class Context:
         """The same rows as synth_bed_device, written to host memory (stands in for a .bed file read by the host)."""
         self._chk(lib.gpca_synth_bed_host(self._h, host_ptr, n_samples, n_snps, snp_offset, seed, n_pops, fst,
                                           missing_rate, fst_grade))
+
+    def count_kernel_ms(self, dev_ptr: int, n_samples: int, n_snps: int, reps: int = 10) -> float:
+        """mean device time (ms) of one launch of the allele-count kernel (K-a) on a device-resident payload"""
+        ms = C.c_double(0.0)
+        self._chk(lib.gpca_count_kernel_ms(self._h, dev_ptr, n_samples, n_snps, reps, C.byref(ms)))
+        return float(ms.value)
 
     def set_host_threads(self, n: int):
         self._chk(lib.gpca_set_host_threads(self._h, int(n)))

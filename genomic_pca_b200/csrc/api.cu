@@ -1138,6 +1138,34 @@ extern "C" int gpca_synth_bed_device(gpca_ctx* c, uint8_t* dev_out, uint64_t n_s
   return GPCA_OK;
 }
 
+// Measurement hook for K-a alone: the allele-count kernel of the ingest (chunk_counts_kernel) on a payload that is
+// already on the device, `reps` launches between two CUDA events; *ms_out = mean time of one launch.
+extern "C" int gpca_count_kernel_ms(gpca_ctx* c, const uint8_t* dev_payload, uint64_t n_samples, uint64_t n_snps,
+                                    uint32_t reps, double* ms_out) {
+  CHECK_CTX(c);
+  GPCA_CUDA_TRY(c, cudaSetDevice(c->device));
+  if (!dev_payload || !ms_out || n_samples == 0 || n_snps == 0 || reps == 0)
+    return fail(c, GPCA_ERR_INVALID, "gpca_count_kernel_ms: bad argument");
+  GPCA_CUDA_TRY(c, c->d_cnt.alloc(n_snps));
+  const size_t pitch = (n_samples + 3) / 4;
+  GPCA_TRY(launch_chunk_counts(c, dev_payload, pitch, n_samples, n_snps, c->d_cnt.p));      // warm-up
+  cudaEvent_t e0, e1;
+  GPCA_CUDA_TRY(c, cudaEventCreate(&e0));
+  GPCA_CUDA_TRY(c, cudaEventCreate(&e1));
+  cudaEventRecord(e0, c->stream);
+  int rc = GPCA_OK;
+  for (uint32_t r = 0; r < reps && rc == GPCA_OK; ++r)
+    rc = launch_chunk_counts(c, dev_payload, pitch, n_samples, n_snps, c->d_cnt.p);
+  cudaEventRecord(e1, c->stream);
+  cudaEventSynchronize(e1);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ms_out = (double)ms / reps;
+  return rc;
+}
+
 // the same generator into HOST memory (chunks are generated on the device and copied back): the payload a host would
 // have read from a .bed file, for shapes whose payload does not fit on the device next to the resident matrices
 extern "C" int gpca_synth_bed_host(gpca_ctx* c, uint8_t* host_out, uint64_t n_samples, uint64_t n_snps,

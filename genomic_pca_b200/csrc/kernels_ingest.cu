@@ -126,6 +126,25 @@ __device__ __forceinline__ void count_word(uint32_t w, uint32_t& c01, uint32_t& 
   c10 += __popc(hi & ~lo);
   c01 += __popc(lo & ~hi);
 }
+// Two words per population count.  The class masks of a word have their bits on the even positions only, so the masks
+// of a second word fit on the odd positions of the same register: x is classified on the even bits (x & (x >> 1) ...),
+// y on the odd bits (y & (y << 1) ...), and one POPC counts both.  POPC issues at a quarter of the ALU rate (16 per
+// clock per SM): with one POPC per class and word the kernel sat at 4.5 TB/s, 0.69 of the HBM roofline, POPC-bound;
+// this halves the POPCs (six per 16 bytes) for two more logic operations per pair.
+__device__ __forceinline__ void count_pair(uint32_t x, uint32_t y, uint32_t& c01, uint32_t& c10, uint32_t& c11) {
+  const uint32_t xs = x >> 1, ys = y << 1;
+  // even bits: hi = xs, lo = x;  odd bits: hi = y, lo = ys
+  const uint32_t m11 = (x & xs & 0x55555555u) | (y & ys & 0xAAAAAAAAu);
+  const uint32_t m10 = (xs & ~x & 0x55555555u) | (y & ~ys & 0xAAAAAAAAu);
+  const uint32_t m01 = (x & ~xs & 0x55555555u) | (ys & ~y & 0xAAAAAAAAu);
+  c11 += __popc(m11);
+  c10 += __popc(m10);
+  c01 += __popc(m01);
+}
+__device__ __forceinline__ void count_chunk(const uint4& v, uint32_t& c01, uint32_t& c10, uint32_t& c11) {
+  count_pair(v.x, v.y, c01, c10, c11);
+  count_pair(v.z, v.w, c01, c10, c11);
+}
 
 template <int GROUP>
 __global__ void __launch_bounds__(256) bed_counts_kernel(const uint8_t* __restrict__ raw, size_t pitch, uint64_t M,
@@ -145,10 +164,7 @@ __global__ void __launch_bounds__(256) bed_counts_kernel(const uint8_t* __restri
       uint32_t c01 = 0, c10 = 0, c11 = 0;
       for (int i = lane; live && i < chunks; i += GROUP) {
         const uint4 v = ldg_nc_v4(p + i);
-        count_word(v.x, c01, c10, c11);
-        count_word(v.y, c01, c10, c11);
-        count_word(v.z, c01, c10, c11);
-        count_word(v.w, c01, c10, c11);
+        count_chunk(v, c01, c10, c11);
       }
 #pragma unroll
       for (int o = GROUP / 2; o > 0; o >>= 1) {
@@ -165,10 +181,7 @@ __global__ void __launch_bounds__(256) bed_counts_kernel(const uint8_t* __restri
       uint32_t c01 = 0, c10 = 0, c11 = 0;
       for (int i = threadIdx.x; i < chunks; i += blockDim.x) {
         const uint4 v = ldg_nc_v4(p + i);
-        count_word(v.x, c01, c10, c11);
-        count_word(v.y, c01, c10, c11);
-        count_word(v.z, c01, c10, c11);
-        count_word(v.w, c01, c10, c11);
+        count_chunk(v, c01, c10, c11);
       }
       c01 = warp_sum_u32(c01);
       c10 = warp_sum_u32(c10);
@@ -300,10 +313,47 @@ __device__ __forceinline__ uint4 load_row_chunk(const uint8_t* row, uint64_t n_f
 
 // K-a on a staged chunk: out[row] = {n(01), n(10), n(11), 0} over the row's first N fields.  `out` may be mapped
 // pinned host memory (the 16-byte records then land on the host without a copy in the transfer queue).
+// Counting does not care where a field sits, so the rows -- which start at any byte address -- are walked in ALIGNED
+// 16-byte chunks, each loaded exactly once; only the first and the last chunk of a row are masked (bytes of the
+// neighbouring rows, fields at or past N).  (The recode, which has to produce aligned rows, needs the two-load funnel
+// shift of load_row_chunk; the count kernel with it ran at 3.5 TB/s on 626-byte rows.)
+struct RowSpan {
+  const uint4* base;     // aligned chunk that holds the row's first byte
+  int64_t lo_bit;        // first valid bit, relative to base
+  int64_t hi_bit;        // one past the last valid bit (2 N fields further)
+  int chunks;            // aligned chunks the row touches
+};
+__device__ __forceinline__ RowSpan row_span(const uint8_t* row, uint64_t N) {
+  RowSpan r;
+  const uintptr_t ua = reinterpret_cast<uintptr_t>(row);
+  r.base = reinterpret_cast<const uint4*>(ua & ~(uintptr_t)15);
+  r.lo_bit = (int64_t)(ua & 15) * 8;
+  r.hi_bit = r.lo_bit + 2 * (int64_t)N;
+  r.chunks = (int)((r.hi_bit + 127) >> 7);
+  return r;
+}
+__device__ __forceinline__ uint4 span_chunk(const RowSpan& r, int ci) {
+  uint4 v = ldg_nc_v4(r.base + ci);
+  if (ci == 0 || ci == r.chunks - 1) {
+    const int64_t lo = r.lo_bit - 128 * (int64_t)ci, hi = r.hi_bit - 128 * (int64_t)ci;
+    uint32_t* w = &v.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t l = lo - 32 * j, h = hi - 32 * j;
+      uint32_t m = 0xffffffffu;
+      if (h <= 0) m = 0u;
+      else if (h < 32) m = (1u << (int)h) - 1u;
+      if (l >= 32) m = 0u;
+      else if (l > 0) m &= ~((1u << (int)l) - 1u);
+      w[j] &= m;
+    }
+  }
+  return v;
+}
+
 template <int GROUP>
 __global__ void __launch_bounds__(256) chunk_counts_kernel(const uint8_t* __restrict__ src, size_t pitch, uint64_t N,
                                                            uint64_t M, uint4* __restrict__ out) {
-  const int chunks = (int)((N + 63) / 64);
   if constexpr (GROUP > 0) {
     constexpr int GPW = 32 / GROUP;
     const uint64_t warp_id = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
@@ -313,14 +363,11 @@ __global__ void __launch_bounds__(256) chunk_counts_kernel(const uint8_t* __rest
     for (uint64_t base = warp_id * GPW; base < M; base += nwarps * GPW) {
       const uint64_t row = base + sub;
       const bool live = row < M;
-      const uint8_t* p = src + (live ? row : 0) * pitch;
+      const RowSpan sp = row_span(src + (live ? row : 0) * pitch, N);
       uint32_t c01 = 0, c10 = 0, c11 = 0;
-      for (int i = lane; live && i < chunks; i += GROUP) {
-        const uint4 v = load_row_chunk(p, N, (uint64_t)i);
-        count_word(v.x, c01, c10, c11);
-        count_word(v.y, c01, c10, c11);
-        count_word(v.z, c01, c10, c11);
-        count_word(v.w, c01, c10, c11);
+      for (int i = lane; live && i < sp.chunks; i += GROUP) {
+        const uint4 v = span_chunk(sp, i);
+        count_chunk(v, c01, c10, c11);
       }
 #pragma unroll
       for (int o = GROUP / 2; o > 0; o >>= 1) {
@@ -333,14 +380,11 @@ __global__ void __launch_bounds__(256) chunk_counts_kernel(const uint8_t* __rest
   } else {
     __shared__ uint32_t s[3][8];
     for (uint64_t row = blockIdx.x; row < M; row += gridDim.x) {
-      const uint8_t* p = src + row * pitch;
+      const RowSpan sp = row_span(src + row * pitch, N);
       uint32_t c01 = 0, c10 = 0, c11 = 0;
-      for (int i = threadIdx.x; i < chunks; i += blockDim.x) {
-        const uint4 v = load_row_chunk(p, N, (uint64_t)i);
-        count_word(v.x, c01, c10, c11);
-        count_word(v.y, c01, c10, c11);
-        count_word(v.z, c01, c10, c11);
-        count_word(v.w, c01, c10, c11);
+      for (int i = threadIdx.x; i < sp.chunks; i += blockDim.x) {
+        const uint4 v = span_chunk(sp, i);
+        count_chunk(v, c01, c10, c11);
       }
       c01 = warp_sum_u32(c01);
       c10 = warp_sum_u32(c10);
@@ -366,22 +410,42 @@ __global__ void __launch_bounds__(256) chunk_counts_kernel(const uint8_t* __rest
   }
 }
 
+template <int GROUP>
+static void launch_chunk_counts_g(gpca_ctx* c, const uint8_t* d_src, size_t pitch, uint64_t N, uint64_t M, uint4* out) {
+  const int threads = 256;
+  const int grid_full = c->sm_count * 8;      // a multiple of the SM count, 8 resident CTAs of 256 threads per SM
+  if (GROUP == 0) {
+    const int grid = (int)(M < (uint64_t)grid_full ? M : (uint64_t)grid_full);
+    chunk_counts_kernel<0><<<grid, threads, 0, c->stream>>>(d_src, pitch, N, M, out);
+  } else {
+    const uint64_t need = (M * (GROUP ? GROUP : 1) + threads - 1) / threads;
+    const int grid = (int)(need < (uint64_t)grid_full ? need : (uint64_t)grid_full);
+    chunk_counts_kernel<GROUP><<<grid, threads, 0, c->stream>>>(d_src, pitch, N, M, out);
+  }
+}
+
 int launch_chunk_counts(gpca_ctx* c, const uint8_t* d_src, size_t pitch, uint64_t N, uint64_t M, uint4* out) {
   if (M == 0) return GPCA_OK;
-  const int threads = 256;
-  const int chunks = (int)((N + 63) / 64);
-  const int grid_full = c->sm_count * 8;
-  if (chunks <= 128) {
-    uint64_t need = (M * 8 + threads - 1) / threads;
-    int grid = (int)(need < (uint64_t)grid_full ? need : (uint64_t)grid_full);
-    chunk_counts_kernel<8><<<grid, threads, 0, c->stream>>>(d_src, pitch, N, M, out);
-  } else if (chunks <= 1024) {
-    uint64_t need = (M * 32 + threads - 1) / threads;
-    int grid = (int)(need < (uint64_t)grid_full ? need : (uint64_t)grid_full);
-    chunk_counts_kernel<32><<<grid, threads, 0, c->stream>>>(d_src, pitch, N, M, out);
-  } else {
-    int grid = (int)(M < (uint64_t)grid_full ? M : (uint64_t)grid_full);
-    chunk_counts_kernel<0><<<grid, threads, 0, c->stream>>>(d_src, pitch, N, M, out);
+  const int chunks = (int)((N + 63) / 64) + 1;      // aligned 16-byte chunks a row may touch
+  // Lanes per row, from a sweep on B200 (profiles/r2_ka_counts_probe.txt): a lane per row for rows of a few chunks
+  // (64 samples = one chunk per SNP); otherwise at least four lanes (whole 64-byte runs per row and step) and about 128
+  // chunks per lane, up to a warp per row -- which beats a CTA per row even at 125 KB rows (6.26 vs 6.04 TB/s) as long
+  // as there are rows for every warp.
+  int group = 1;
+  if (chunks >= 8) {
+    group = 4;
+    while (group < 32 && group * 128 < chunks) group *= 2;
+  }
+  if (chunks > 1024 && M < (uint64_t)c->sm_count * 16) group = 0;      // few, very long rows: a CTA per row
+  if (const char* e = getenv("GPCA_DEBUG_COUNT_GROUP")) group = atoi(e);
+  switch (group) {
+    case 0: launch_chunk_counts_g<0>(c, d_src, pitch, N, M, out); break;
+    case 1: launch_chunk_counts_g<1>(c, d_src, pitch, N, M, out); break;
+    case 2: launch_chunk_counts_g<2>(c, d_src, pitch, N, M, out); break;
+    case 4: launch_chunk_counts_g<4>(c, d_src, pitch, N, M, out); break;
+    case 8: launch_chunk_counts_g<8>(c, d_src, pitch, N, M, out); break;
+    case 16: launch_chunk_counts_g<16>(c, d_src, pitch, N, M, out); break;
+    default: launch_chunk_counts_g<32>(c, d_src, pitch, N, M, out); break;
   }
   KLAUNCH_CHECK(c);
   return GPCA_OK;

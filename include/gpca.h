@@ -288,6 +288,11 @@ int gpca_map_snps_to_ld_blocks(const char* const* snp_chrom, const int32_t* snp_
  * eigenvalues, so that a top-k subspace is well defined for any k (0 = one F_ST for all: a degenerate cluster). */
 int gpca_synth_bed_device(gpca_ctx* ctx, uint8_t* dev_out, uint64_t n_samples, uint64_t n_snps, uint64_t snp_offset,
                           uint64_t seed, uint32_t n_pops, double fst, double missing_rate, double fst_grade);
+/* Measurement hook: mean device time (ms) of the ingest's allele-count kernel (K-a: 2-bit unpack + counts, the integer
+ * half of src/prepare.rs:1232-1279) over `reps` launches on a device-resident .bed payload of n_snps rows of
+ * ceil(n_samples/4) bytes (the payload must be readable 16 bytes past its end). */
+int gpca_count_kernel_ms(gpca_ctx* ctx, const uint8_t* dev_payload, uint64_t n_samples, uint64_t n_snps, uint32_t reps,
+                         double* ms_out);
 /* the same rows into host memory (generated on the device chunk by chunk): stands in for a .bed file read by the host */
 int gpca_synth_bed_host(gpca_ctx* ctx, uint8_t* host_out, uint64_t n_samples, uint64_t n_snps, uint64_t snp_offset,
                         uint64_t seed, uint32_t n_pops, double fst, double missing_rate, double fst_grade);
