@@ -911,13 +911,15 @@ static int ingest_core(gpca_ctx* c, const uint8_t* host_payload, int fd, uint64_
     else
       host_vcf_maf(N, nr, hc + 4 * r0, vcf_maf_threshold, keep_out + r0, mean_out + r0, sd_out + r0);
     if (pre_mask)      // rows outside the caller's pre-selection are dropped whatever the QC says (fail code 7)
-      for (uint64_t t = 0; t < nr; ++t)
-        if (!pre_mask[r0 + t] && keep_out[r0 + t]) {
-          keep_out[r0 + t] = 0;
-          mean_out[r0 + t] = 0.f;
-          sd_out[r0 + t] = 0.f;
-          if (fail_code_out) fail_code_out[r0 + t] = 7;
-        }
+      parallel_for(nr, [=](uint64_t lo, uint64_t hi) {
+        for (uint64_t t = lo; t < hi; ++t)
+          if (!pre_mask[r0 + t] && keep_out[r0 + t]) {
+            keep_out[r0 + t] = 0;
+            mean_out[r0 + t] = 0.f;
+            sd_out[r0 + t] = 0.f;
+            if (fail_code_out) fail_code_out[r0 + t] = 7;
+          }
+      });
     t_qc += ms_since(tp); tp = now();
     GPCA_CUDA_TRY(c, cudaEventSynchronize(up_free[sl]));
     const size_t uoff = (size_t)sl * up_bytes;
@@ -1297,8 +1299,14 @@ int for_each_gs_segment(gpca_ctx* c, const std::function<int(const PackedMat&, u
     v.avail = c->Gs.pitch;
     GPCA_TRY(fn(v, 0));
   }
+  const bool trace = getenv("GPCA_TRACE") != nullptr && res < D;
+  cudaEvent_t te[3] = {nullptr, nullptr, nullptr};
+  float t_tr = 0.f, t_fn = 0.f;
+  if (trace)
+    for (auto& e : te) cudaEventCreate(&e);
   for (uint64_t r = res; r < D; r += c->gs_win_rows) {
     const uint64_t nr = std::min<uint64_t>(c->gs_win_rows, D - r);
+    if (trace) cudaEventRecord(te[0], c->stream);
     PackedMat sv = c->Gt, dv = c->Gs;
     sv.p = c->Gt.p + r / 4;               // r is a multiple of 512 (res and the window are)
     sv.cols = nr;
@@ -1308,7 +1316,22 @@ int for_each_gs_segment(gpca_ctx* c, const std::function<int(const PackedMat&, u
     // the transpose reads Gt columns [r, r + nr) -- the last 512-column tile may run past nr inside Gt's row: those
     // fields are other SNPs' or zero pads, and land in window rows past nr that the pass does not read
     GPCA_TRY(launch_transpose(c, sv, dv));
+    if (trace) cudaEventRecord(te[1], c->stream);
     GPCA_TRY(fn(dv, r));
+    if (trace) {
+      cudaEventRecord(te[2], c->stream);
+      cudaEventSynchronize(te[2]);
+      float a = 0.f, b = 0.f;
+      cudaEventElapsedTime(&a, te[0], te[1]);
+      cudaEventElapsedTime(&b, te[1], te[2]);
+      t_tr += a;
+      t_fn += b;
+    }
+  }
+  if (trace) {
+    fprintf(stderr, "[for_each_gs_segment] %llu of %llu rows re-created from the sample-major matrix: transposes %.2f ms, "
+            "passes on the windows %.2f ms\n", (unsigned long long)(D - res), (unsigned long long)D, t_tr, t_fn);
+    for (auto& e : te) cudaEventDestroy(e);
   }
   return GPCA_OK;
 }

@@ -1,0 +1,32 @@
+"""Host-side logic of bench.py that does not need a GPU: the strong-scaling split of BASELINE config 4 over the ranks
+(whole LD blocks, every SNP exactly once) and the number formatting helpers it shares with the tests."""
+import numpy as np
+
+import bench
+
+
+def test_strong_scaling_shards_cover_every_snp_once():
+    m, nb = bench.C4_SNPS, bench.C4_BLOCKS
+    edges = np.linspace(0, m, nb + 1).astype(np.int64)
+    for world in (1, 2, 3, 4, 8):
+        seen_blocks, next_snp = 0, 0
+        for rank in range(world):
+            b0, b1, s0, s1 = bench.shard_of(rank, world, nb, m)
+            assert b0 == seen_blocks and s0 == next_snp            # contiguous, in rank order
+            assert s0 == edges[b0] and s1 == edges[b1]             # cut at LD-block boundaries only
+            assert b1 > b0 and s1 > s0
+            seen_blocks, next_snp = b1, s1
+        assert seen_blocks == nb and next_snp == m
+        sizes = [bench.shard_of(r, world, nb, m)[3] - bench.shard_of(r, world, nb, m)[2] for r in range(world)]
+        assert max(sizes) - min(sizes) <= 2 * (m // nb + 1)        # balanced to within a block or two
+
+
+def test_subspace_angle_helper():
+    rng = np.random.default_rng(0)
+    a = rng.standard_normal((200, 5))
+    q, _ = np.linalg.qr(a)
+    assert bench.subspace_angle(a, q @ rng.standard_normal((5, 5))) < 1e-7          # same span
+    b = q.copy()
+    b[:, 0] += 1e-3 * rng.standard_normal(200)
+    ang = bench.subspace_angle(q, b)
+    assert 1e-4 < ang < 5e-2
