@@ -8,11 +8,16 @@
 //   run_eigensnp_rust_workflow      src/main.rs:250-447
 //   MicroarrayDataPreparer          src/prepare.rs:922-1096 (BIM/FAM metadata, sample keep list), :1565-1616 (LD file)
 //   output_writer                   src/main.rs:682-839   (file names, headers, {:.6})
-// Deliberate differences: plain or gzip/BGZF VCF text is parsed with zlib (the reference uses noodles-vcf);
+// Deliberate differences: VCF text (plain, gzip or BGZF) is inflated with zlib and parsed here (the reference uses
+// noodles-vcf on one thread per file): BGZF blocks are inflated concurrently and the lines of a batch are parsed on all
+// host threads straight into 2-bit rows (no D x N byte matrix on the host);
 // --threads / --log-level are accepted; the rfit eigenvalues file is header-only exactly like the reference
 // (src/main.rs:676) unless --write-eigenvalues is given.
 #include <dirent.h>
+#include <fcntl.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <algorithm>
@@ -373,36 +378,179 @@ void close_shards(Shards& s) {
 }
 
 // ---------------------------------------------------------------------------------------------- VCF workflow
-struct GzLines {
-  gzFile f;
-  std::vector<char> buf;
-  size_t pos = 0, len = 0;
-  explicit GzLines(const std::string& path) : buf(1 << 20) {
-    f = gzopen(path.c_str(), "rb");
-    if (!f) die("cannot open " + path);
-    gzbuffer(f, 1 << 20);
+// The text of a VCF file as successive batches of whole lines.  Three containers:
+//   * BGZF (what bgzip / htslib write, and what the reference's fixtures are: tests/README.md): a concatenation of
+//     gzip members of <= 64 KiB, each carrying its own compressed size in a 'BC' extra field.  The block table is read
+//     off the mapped file without inflating anything, and the blocks of a batch are inflated CONCURRENTLY on the host
+//     threads, each to its own offset (the ISIZE trailers give the offsets by a prefix sum).  CRC32 is verified.
+//   * plain gzip: one stream, inflated serially by zlib (gzread).
+//   * plain text: read in batches.
+// (The reference reads through noodles-bgzf on one thread per FILE, src/main.rs:171-179; a biobank chromosome is one
+// file of tens of GB, so the parallelism has to come from inside the file.)
+template <class F>
+void run_threads(unsigned t, F&& fn) {
+  if (t <= 1) {
+    fn(0u);
+    return;
   }
-  ~GzLines() { gzclose(f); }
-  bool next(std::string& line) {
-    line.clear();
-    for (;;) {
-      if (pos == len) {
-        const int n = gzread(f, buf.data(), (unsigned)buf.size());
-        if (n <= 0) return !line.empty();
-        len = (size_t)n;
-        pos = 0;
-      }
-      const char* s = buf.data() + pos;
-      const char* nl = (const char*)memchr(s, '\n', len - pos);
-      if (nl) {
-        line.append(s, nl - s);
-        pos += (nl - s) + 1;
-        if (!line.empty() && line.back() == '\r') line.pop_back();
-        return true;
-      }
-      line.append(s, len - pos);
-      pos = len;
+  std::vector<std::thread> th;
+  for (unsigned i = 0; i < t; ++i) th.emplace_back([&fn, i] { fn(i); });
+  for (auto& x : th) x.join();
+}
+
+struct BgzfBlock {
+  size_t data_off, data_len;   // the raw deflate stream inside the mapped file
+  uint32_t isize, crc;
+};
+
+// parses the gzip member header at p (n bytes available); a BGZF member has FEXTRA with the subfield 'B','C',len 2
+bool bgzf_member(const uint8_t* p, size_t n, size_t* total, BgzfBlock* blk, size_t file_off) {
+  if (n < 18 || p[0] != 0x1f || p[1] != 0x8b || p[2] != 8 || !(p[3] & 4)) return false;
+  const size_t xlen = p[10] | ((size_t)p[11] << 8);
+  if (12 + xlen > n) return false;
+  size_t q = 12, bsize = 0;
+  bool found = false;
+  while (q + 4 <= 12 + xlen) {
+    const size_t slen = p[q + 2] | ((size_t)p[q + 3] << 8);
+    if (p[q] == 'B' && p[q + 1] == 'C' && slen == 2 && q + 6 <= 12 + xlen) {
+      bsize = (p[q + 4] | ((size_t)p[q + 5] << 8)) + 1;
+      found = true;
     }
+    q += 4 + slen;
+  }
+  if (!found || bsize < 12 + xlen + 8 || bsize > n) return false;
+  if (p[3] & ~4) return false;      // FNAME / FCOMMENT / FHCRC never appear in BGZF members
+  *total = bsize;
+  blk->data_off = file_off + 12 + xlen;
+  blk->data_len = bsize - (12 + xlen) - 8;
+  const uint8_t* t = p + bsize - 8;
+  blk->crc = t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
+  blk->isize = t[4] | ((uint32_t)t[5] << 8) | ((uint32_t)t[6] << 16) | ((uint32_t)t[7] << 24);
+  return true;
+}
+
+struct VcfText {
+  enum Kind { PLAIN, GZIP, BGZF } kind = PLAIN;
+  std::string path;
+  int fd = -1;
+  const uint8_t* map = nullptr;
+  size_t map_len = 0, off = 0;
+  gzFile gz = nullptr;
+  std::vector<char> carry;     // the unfinished last line of the previous batch
+  unsigned threads;
+  size_t batch_bytes;
+  bool eof = false;
+  uint64_t blocks_inflated = 0;
+
+  VcfText(const std::string& p, unsigned t, size_t batch) : path(p), threads(t ? t : 1), batch_bytes(batch) {
+    fd = open(path.c_str(), O_RDONLY);
+    if (fd < 0) die("cannot open " + path);
+    struct stat st;
+    if (fstat(fd, &st) != 0) die("cannot stat " + path);
+    map_len = (size_t)st.st_size;
+    if (map_len) {
+      void* m = mmap(nullptr, map_len, PROT_READ, MAP_PRIVATE, fd, 0);
+      if (m == MAP_FAILED) die("cannot map " + path);
+      map = (const uint8_t*)m;
+      madvise(m, map_len, MADV_SEQUENTIAL);
+    }
+    size_t total;
+    BgzfBlock b;
+    if (map_len >= 2 && map[0] == 0x1f && map[1] == 0x8b) {
+      kind = bgzf_member(map, map_len, &total, &b, 0) ? BGZF : GZIP;
+      if (kind == GZIP) {
+        gz = gzopen(path.c_str(), "rb");
+        if (!gz) die("cannot open " + path);
+        gzbuffer(gz, 1 << 20);
+      }
+    }
+  }
+  ~VcfText() {
+    if (gz) gzclose(gz);
+    if (map) munmap((void*)map, map_len);
+    if (fd >= 0) close(fd);
+  }
+  VcfText(const VcfText&) = delete;
+  VcfText& operator=(const VcfText&) = delete;
+
+  // text <- carry + the next batch, cut after its last newline (the remainder becomes the carry; at the end of the
+  // file it is returned as the last line).  false when nothing is left.
+  bool next(std::vector<char>& text) {
+    if (eof && carry.empty()) return false;
+    text.assign(carry.begin(), carry.end());
+    carry.clear();
+    if (!eof) {
+      if (kind == BGZF) fill_bgzf(text);
+      else if (kind == GZIP) fill_gzip(text);
+      else fill_plain(text);
+    }
+    if (!eof) {
+      size_t cut = text.size();
+      while (cut > 0 && text[cut - 1] != '\n') --cut;
+      carry.assign(text.begin() + cut, text.end());
+      text.resize(cut);
+      return true;               // (possibly no complete line yet: the caller just asks again)
+    }
+    return !text.empty();
+  }
+
+  void fill_plain(std::vector<char>& text) {
+    const size_t n = std::min(batch_bytes, map_len - off);
+    text.insert(text.end(), (const char*)map + off, (const char*)map + off + n);
+    off += n;
+    eof = off == map_len;
+  }
+  void fill_gzip(std::vector<char>& text) {
+    const size_t base = text.size();
+    text.resize(base + batch_bytes);
+    size_t got = 0;
+    while (got < batch_bytes) {
+      const int n = gzread(gz, text.data() + base + got, (unsigned)std::min<size_t>(batch_bytes - got, 1u << 30));
+      if (n < 0) die("gzip stream of " + path + " is corrupt");
+      if (n == 0) { eof = true; break; }
+      got += (size_t)n;
+    }
+    text.resize(base + got);
+  }
+  void fill_bgzf(std::vector<char>& text) {
+    std::vector<BgzfBlock> blk;
+    std::vector<size_t> out_off;
+    size_t out = text.size();
+    const size_t base = out;
+    while (off < map_len && out - base < batch_bytes) {
+      size_t total;
+      BgzfBlock b;
+      if (!bgzf_member(map + off, map_len - off, &total, &b, off))
+        die("BGZF block at byte " + std::to_string(off) + " of " + path + " is malformed");
+      off += total;
+      if (b.isize == 0) continue;            // the empty end-of-file marker (and any empty member)
+      blk.push_back(b);
+      out_off.push_back(out);
+      out += b.isize;
+    }
+    eof = off >= map_len;
+    text.resize(out);
+    std::atomic<size_t> next{0};
+    std::atomic<int> bad{0};
+    run_threads((unsigned)std::min<size_t>(threads, std::max<size_t>(1, blk.size() / 4)), [&](unsigned) {
+      z_stream zs;
+      memset(&zs, 0, sizeof zs);
+      if (inflateInit2(&zs, -15) != Z_OK) { bad = 1; return; }
+      for (size_t i = next.fetch_add(1); i < blk.size(); i = next.fetch_add(1)) {
+        inflateReset(&zs);
+        zs.next_in = const_cast<Bytef*>(map + blk[i].data_off);
+        zs.avail_in = (uInt)blk[i].data_len;
+        zs.next_out = (Bytef*)text.data() + out_off[i];
+        zs.avail_out = blk[i].isize;
+        const int rc = inflate(&zs, Z_FINISH);
+        if (rc != Z_STREAM_END || zs.avail_out != 0 ||
+            crc32(crc32(0L, Z_NULL, 0), (const Bytef*)text.data() + out_off[i], blk[i].isize) != blk[i].crc)
+          bad = 1;
+      }
+      inflateEnd(&zs);
+    });
+    if (bad) die("a BGZF block of " + path + " failed to inflate (corrupt data or CRC mismatch)");
+    blocks_inflated += blk.size();
   }
 };
 
@@ -410,162 +558,242 @@ bool ends_with(const std::string& s, const std::string& suf) {
   return s.size() >= suf.size() && s.compare(s.size() - suf.size(), suf.size(), suf) == 0;
 }
 
-int run_vcf(const Args& a) {
-  // discovery: regular files with extension vcf or gz whose name contains ".vcf", sorted (main.rs:139-152)
+// One VCF data line [p, e) -> id + 2-bit row, after the reference's filters; false = the variant is dropped.
+//   biallelic single-base REF / one ALT (vcf.rs:109-121); the GT key's position inside FORMAT (vcf.rs:218-224); the first
+//   two alleles of every sample, '/' or '|' separated, each exactly "0" or "1" (vcf.rs:52-63, 153-193); any other call
+//   drops the variant (vcf.rs:227-242); MAF filter p = sum / 2N in f64 (vcf.rs:244-266).
+// The row is written in PLINK coding (dosage 0 -> 11, 1 -> 10, 2 -> 00: what `count_a1` decodes back to the ALT count).
+bool parse_variant_line(const char* p, const char* e, size_t n, double maf_thr, uint8_t* row, size_t bps, std::string& id) {
+  const char* fld[9];
+  size_t flen[9];
+  const char* s = p;
+  for (int nf = 0; nf < 9; ++nf) {
+    const char* t = (const char*)memchr(s, '\t', (size_t)(e - s));
+    if (!t) return false;
+    fld[nf] = s;
+    flen[nf] = (size_t)(t - s);
+    s = t + 1;
+  }
+  if (flen[3] != 1) return false;
+  if ((flen[4] == 1 && fld[4][0] == '.') || memchr(fld[4], ',', flen[4])) return false;
+  int gt_pos = -1;
+  {
+    int idx = 0;
+    const char* q = fld[8];
+    const char* end = fld[8] + flen[8];
+    while (q <= end) {
+      const char* c = (const char*)memchr(q, ':', (size_t)(end - q));
+      const size_t l = c ? (size_t)(c - q) : (size_t)(end - q);
+      if (l == 2 && q[0] == 'G' && q[1] == 'T') { gt_pos = idx; break; }
+      if (!c) break;
+      q = c + 1;
+      ++idx;
+    }
+  }
+  if (gt_pos < 0) return false;
+  memset(row, 0, bps);
+  size_t si = 0;
+  uint32_t allele_sum = 0;
+  while (si < n && s < e) {
+    const char* t = (const char*)memchr(s, '\t', (size_t)(e - s));
+    const char* end = t ? t : e;
+    const char* q = s;
+    for (int g = 0; g < gt_pos && q < end; ++g) {
+      const char* c = (const char*)memchr(q, ':', (size_t)(end - q));
+      if (!c) { q = end; break; }
+      q = c + 1;
+    }
+    const char* qe = (const char*)memchr(q, ':', (size_t)(end - q));
+    if (!qe) qe = end;
+    int dos = 0, na = 0;
+    const char* r = q;
+    while (r < qe && na < 2) {
+      const char* sep = r;
+      while (sep < qe && *sep != '/' && *sep != '|') ++sep;
+      if (sep - r != 1 || (*r != '0' && *r != '1')) return false;
+      dos += *r - '0';
+      ++na;
+      r = sep + 1;
+    }
+    if (na != 2) return false;
+    const uint32_t code = dos == 0 ? 3u : dos == 1 ? 2u : 0u;
+    row[si >> 2] |= (uint8_t)(code << (2 * (si & 3)));
+    ++si;
+    allele_sum += (uint32_t)dos;
+    if (!t) break;
+    s = t + 1;
+  }
+  if (si != n || n == 0) return false;
+  const double freq = (double)allele_sum / (double)(uint32_t)(n * 2);
+  if (std::min(freq, 1.0 - freq) < maf_thr) return false;
+  id.assign(fld[0], flen[0]);
+  id += ':';
+  id.append(fld[1], flen[1]);
+  id += ':';
+  id += fld[3][0];
+  id += ':';
+  id.append(fld[4], flen[4]);
+  return true;
+}
+
+struct VcfSet {
+  std::vector<std::string> samples, ids;
+  std::vector<uint8_t> packed;          // variant-major rows of ceil(N / 4) bytes, PLINK coding
+  uint64_t bgzf_blocks = 0, batches = 0;
+};
+
+// The files in sorted-path order (main.rs:152, vcf.rs:293-315), each one read batch by batch; the lines of a batch are
+// split over the host threads at line boundaries and every thread appends to its own (ids, rows) piece; the pieces are
+// joined in order.  The sample set is the header of the first file; every other file must repeat it (main.rs:157-160).
+VcfSet parse_vcf_files(const std::vector<std::string>& files, double maf_thr, unsigned workers, size_t batch_bytes = 64u << 20) {
+  VcfSet out;
+  if (workers == 0) workers = 1;
+  struct Piece {
+    std::vector<std::string> ids;
+    std::vector<uint8_t> rows;
+  };
+  std::vector<char> text;
+  for (size_t fi = 0; fi < files.size(); ++fi) {
+    VcfText in(files[fi], workers, batch_bytes);
+    bool in_header = true, have_gt_format = false, have_chrom = false;
+    while (in.next(text)) {
+      ++out.batches;
+      const char* p = text.data();
+      const char* const e = p + text.size();
+      // header lines (serial: they come first and are few)
+      while (in_header && p < e) {
+        const char* nl = (const char*)memchr(p, '\n', (size_t)(e - p));
+        const char* le = nl ? nl : e;
+        const char* lt = le;
+        if (lt > p && lt[-1] == '\r') --lt;
+        if (lt == p) { p = nl ? nl + 1 : e; continue; }
+        if (*p != '#') { in_header = false; break; }
+        const std::string line(p, lt);
+        if (line.rfind("##FORMAT=<ID=GT", 0) == 0) have_gt_format = true;
+        if (line.rfind("#CHROM", 0) == 0) {
+          std::vector<std::string> hdr;
+          std::stringstream ss(line);
+          std::string t;
+          int col = 0;
+          while (std::getline(ss, t, '\t')) if (col++ >= 9) hdr.push_back(t);
+          if (fi == 0) {
+            if (hdr.empty()) die("VCF header from " + files[0] + " contains no samples.");                    // vcf.rs:32
+            out.samples = hdr;
+          } else if (hdr != out.samples) {
+            die("Sample mismatch in VCF " + files[fi] + ": all VCFs must match the sample set of the first VCF (" + files[0] + ").");
+          }
+          if (!have_gt_format) die("GT key (FORMAT=GT) not found in FORMAT header for VCF " + files[fi]);     // vcf.rs:93
+          have_chrom = true;
+        }
+        p = nl ? nl + 1 : e;
+      }
+      if (p >= e) continue;
+      if (!have_chrom) {
+        if (fi == 0) die("VCF header from " + files[0] + " contains no samples.");
+        die("VCF " + files[fi] + " has no #CHROM header line");
+      }
+      const size_t n = out.samples.size(), bps = (n + 3) / 4;
+      const size_t len = (size_t)(e - p);
+      const unsigned T = (unsigned)std::min<size_t>(workers, std::max<size_t>(1, len >> 16));
+      std::vector<Piece> pieces(T);
+      run_threads(T, [&](unsigned t) {
+        // piece t = the lines that START in [len t / T, len (t+1) / T)
+        auto line_start = [&](size_t pos) -> const char* {
+          if (pos == 0) return p;
+          if (pos >= len) return e;
+          const char* nl = (const char*)memchr(p + pos - 1, '\n', len - pos + 1);
+          return nl ? nl + 1 : e;
+        };
+        const char* q = line_start(len * t / T);
+        const char* const qe = line_start(len * (t + 1) / T);
+        Piece& pc = pieces[t];
+        std::vector<uint8_t> row(bps);
+        std::string id;
+        while (q < qe) {
+          const char* nl = (const char*)memchr(q, '\n', (size_t)(e - q));
+          const char* le = nl ? nl : e;
+          const char* lt = le;
+          if (lt > q && lt[-1] == '\r') --lt;
+          if (lt > q && *q != '#' && parse_variant_line(q, lt, n, maf_thr, row.data(), bps, id)) {
+            pc.ids.push_back(id);
+            pc.rows.insert(pc.rows.end(), row.begin(), row.end());
+          }
+          q = nl ? nl + 1 : e;
+        }
+      });
+      size_t add = 0;
+      for (const Piece& pc : pieces) add += pc.rows.size();
+      if (out.packed.capacity() < out.packed.size() + add) out.packed.reserve(std::max(out.packed.size() + add, out.packed.capacity() * 2));
+      for (Piece& pc : pieces) {
+        out.ids.insert(out.ids.end(), std::make_move_iterator(pc.ids.begin()), std::make_move_iterator(pc.ids.end()));
+        out.packed.insert(out.packed.end(), pc.rows.begin(), pc.rows.end());
+      }
+    }
+    out.bgzf_blocks += in.blocks_inflated;
+    if (fi == 0 && out.samples.empty()) die("VCF header from " + files[0] + " contains no samples.");           // vcf.rs:32
+  }
+  return out;
+}
+
+// (test / measurement hook) `genomic_pca --parse-vcf DIR MAF THREADS BATCH_BYTES [DUMP]`: the host side of the VCF
+// workflow alone -- no GPU involved; prints what was parsed and optionally dumps ids + packed rows.
+std::vector<std::string> discover_vcf_files(const std::string& dir);
+int parse_vcf_hook(int argc, char** argv) {
+  const std::vector<std::string> files = discover_vcf_files(argv[2]);
+  const auto t0 = std::chrono::steady_clock::now();
+  VcfSet vs = parse_vcf_files(files, strtod(argv[3], nullptr), (unsigned)atol(argv[4]), (size_t)strtoull(argv[5], nullptr, 10));
+  const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  uint64_t bytes = 0;
+  for (const auto& f : files) {
+    struct stat st;
+    if (stat(f.c_str(), &st) == 0) bytes += (uint64_t)st.st_size;
+  }
+  printf("{\"files\": %zu, \"samples\": %zu, \"variants\": %zu, \"bgzf_blocks\": %llu, \"batches\": %llu, \"threads\": %ld, "
+         "\"seconds\": %.3f, \"file_MB_per_s\": %.1f}\n",
+         files.size(), vs.samples.size(), vs.ids.size(), (unsigned long long)vs.bgzf_blocks, (unsigned long long)vs.batches,
+         atol(argv[4]), s, (double)bytes / s / 1e6);
+  if (argc > 6) {
+    FILE* f = fopen((std::string(argv[6]) + ".ids").c_str(), "w");
+    if (!f) die("cannot create dump");
+    for (const auto& id : vs.ids) fprintf(f, "%s\n", id.c_str());
+    fclose(f);
+    f = fopen((std::string(argv[6]) + ".packed").c_str(), "wb");
+    if (!f) die("cannot create dump");
+    fwrite(vs.packed.data(), 1, vs.packed.size(), f);
+    fclose(f);
+  }
+  return 0;
+}
+
+// discovery: regular files with extension vcf or gz whose name contains ".vcf", sorted (main.rs:139-152)
+std::vector<std::string> discover_vcf_files(const std::string& dir) {
   std::vector<std::string> files;
-  DIR* d = opendir(a.vcf_dir.c_str());
-  if (!d) die("cannot read directory " + a.vcf_dir);
+  DIR* d = opendir(dir.c_str());
+  if (!d) die("cannot read directory " + dir);
   while (dirent* e = readdir(d)) {
     const std::string name = e->d_name;
-    const std::string path = a.vcf_dir + "/" + name;
+    const std::string path = dir + "/" + name;
     struct stat st;
     if (stat(path.c_str(), &st) != 0 || !S_ISREG(st.st_mode)) continue;
     if ((ends_with(name, ".vcf") || ends_with(name, ".gz")) && name.find(".vcf") != std::string::npos) files.push_back(path);
   }
   closedir(d);
-  if (files.empty()) die("No VCF files (ending in .vcf or .vcf.gz) found in directory: " + a.vcf_dir);
+  if (files.empty()) die("No VCF files (ending in .vcf or .vcf.gz) found in directory: " + dir);
   std::sort(files.begin(), files.end());
+  return files;
+}
+
+int run_vcf(const Args& a) {
+  const std::vector<std::string> files = discover_vcf_files(a.vcf_dir);
   const double maf_thr = a.maf >= 0 ? a.maf : 0.01;                                 // vcf.rs:257
-  std::vector<std::string> samples, ids;
-  std::vector<uint8_t> dosage;                                                      // variant-major, D rows of N bytes
-  // the sample set comes from the header of the first file (main.rs:157-160); the files are then parsed concurrently,
-  // one task per file as the reference's par_iter does (main.rs:171-179), and aggregated in sorted-path order
-  // (vcf.rs:293-315)
-  {
-    GzLines in(files[0]);
-    std::string line;
-    while (in.next(line)) {
-      if (line.rfind("#CHROM", 0) == 0) {
-        std::stringstream ss(line);
-        std::string t;
-        int col = 0;
-        while (std::getline(ss, t, '\t')) if (col++ >= 9) samples.push_back(t);
-        break;
-      }
-      if (!line.empty() && line[0] != '#') break;
-    }
-    if (samples.empty()) die("VCF header from " + files[0] + " contains no samples.");   // vcf.rs:32
-  }
-  std::vector<std::vector<std::string>> ids_f(files.size());
-  std::vector<std::vector<uint8_t>> dosage_f(files.size());
-  auto parse_file = [&](size_t fi) {
-    std::vector<std::string>& ids = ids_f[fi];
-    std::vector<uint8_t>& dosage = dosage_f[fi];
-    std::vector<uint8_t> tmp;
-    GzLines in(files[fi]);
-    std::string line;
-    std::vector<std::string> hdr_samples;
-    bool have_gt_format = false;
-    while (in.next(line)) {
-      if (line.empty()) continue;
-      if (line[0] == '#') {
-        if (line.rfind("##FORMAT=<ID=GT", 0) == 0) have_gt_format = true;
-        if (line.rfind("#CHROM", 0) == 0) {
-          std::stringstream ss(line);
-          std::string t;
-          int col = 0;
-          while (std::getline(ss, t, '\t')) if (col++ >= 9) hdr_samples.push_back(t);
-          if (hdr_samples != samples) {
-            die("Sample mismatch in VCF " + files[fi] + ": all VCFs must match the sample set of the first VCF (" + files[0] + ").");
-          }
-          if (!have_gt_format) die("GT key (FORMAT=GT) not found in FORMAT header for VCF " + files[fi]);   // vcf.rs:93
-        }
-        continue;
-      }
-      // CHROM POS ID REF ALT QUAL FILTER INFO FORMAT samples...
-      const size_t n = samples.size();
-      const char* p = line.c_str();
-      const char* fld[9];
-      size_t flen[9];
-      int nf = 0;
-      const char* s = p;
-      while (nf < 9) {
-        const char* t = strchr(s, '\t');
-        if (!t) break;
-        fld[nf] = s;
-        flen[nf] = (size_t)(t - s);
-        ++nf;
-        s = t + 1;
-      }
-      if (nf < 9) continue;
-      const std::string ref(fld[3], flen[3]), alt(fld[4], flen[4]);
-      if (ref.size() != 1 || alt == "." || alt.find(',') != std::string::npos) continue;     // vcf.rs:109-121
-      // GT position inside FORMAT
-      int gt_pos = -1;
-      {
-        int idx = 0;
-        const char* q = fld[8];
-        const char* end = fld[8] + flen[8];
-        while (q <= end) {
-          const char* c = (const char*)memchr(q, ':', (size_t)(end - q));
-          const size_t l = c ? (size_t)(c - q) : (size_t)(end - q);
-          if (l == 2 && q[0] == 'G' && q[1] == 'T') { gt_pos = idx; break; }
-          if (!c) break;
-          q = c + 1;
-          ++idx;
-        }
-      }
-      if (gt_pos < 0) continue;                                                              // vcf.rs:218-224
-      tmp.assign(n, 0);
-      size_t si = 0;
-      bool bad = false;
-      uint32_t allele_sum = 0;
-      while (si < n && *s) {
-        const char* t = strchr(s, '\t');
-        const char* end = t ? t : s + strlen(s);
-        // select sub-field gt_pos
-        const char* q = s;
-        for (int g = 0; g < gt_pos && q < end; ++g) {
-          const char* c = (const char*)memchr(q, ':', (size_t)(end - q));
-          if (!c) { q = end; break; }
-          q = c + 1;
-        }
-        const char* qe = (const char*)memchr(q, ':', (size_t)(end - q));
-        if (!qe) qe = end;
-        // first two alleles, '/' or '|' separated, each exactly "0" or "1" (vcf.rs:52-63, 153-193)
-        int dos = 0, na = 0;
-        const char* r = q;
-        while (r < qe && na < 2) {
-          const char* sep = r;
-          while (sep < qe && *sep != '/' && *sep != '|') ++sep;
-          if (sep - r != 1 || (*r != '0' && *r != '1')) { bad = true; break; }
-          dos += *r - '0';
-          ++na;
-          r = sep + 1;
-        }
-        if (bad || na != 2) { bad = true; break; }
-        tmp[si++] = (uint8_t)dos;
-        allele_sum += (uint32_t)dos;
-        if (!t) break;
-        s = t + 1;
-      }
-      if (bad || si != n) continue;                                                          // vcf.rs:227-242
-      const uint32_t total = (uint32_t)(n * 2);
-      if (total == 0) continue;
-      const double freq = (double)allele_sum / (double)total;                                // vcf.rs:254
-      const double maf = std::min(freq, 1.0 - freq);
-      if (maf < maf_thr) continue;                                                           // vcf.rs:259
-      ids.push_back(std::string(fld[0], flen[0]) + ":" + std::string(fld[1], flen[1]) + ":" + ref + ":" + alt);
-      dosage.insert(dosage.end(), tmp.begin(), tmp.end());
-    }
-  };
-  {
-    unsigned hw = std::thread::hardware_concurrency();
-    if (hw == 0) hw = 4;
-    const size_t workers = std::min<size_t>(files.size(), a.threads > 0 ? (size_t)a.threads : hw);
-    std::atomic<size_t> next{0};
-    std::vector<std::thread> th;
-    for (size_t w = 0; w < workers; ++w)
-      th.emplace_back([&] {
-        for (size_t fi = next.fetch_add(1); fi < files.size(); fi = next.fetch_add(1)) parse_file(fi);
-      });
-    for (auto& t : th) t.join();
-  }
-  for (size_t fi = 0; fi < files.size(); ++fi) {
-    ids.insert(ids.end(), ids_f[fi].begin(), ids_f[fi].end());
-    dosage.insert(dosage.end(), dosage_f[fi].begin(), dosage_f[fi].end());
-    std::vector<uint8_t>().swap(dosage_f[fi]);
-  }
+  unsigned hw = std::thread::hardware_concurrency();
+  if (hw == 0) hw = 4;
+  const unsigned workers = (unsigned)(a.threads > 0 ? a.threads : (long)hw);
+  VcfSet vs = parse_vcf_files(files, maf_thr, workers);
+  const std::vector<std::string>& samples = vs.samples;
+  const std::vector<std::string>& ids = vs.ids;
+  const std::vector<uint8_t>& packed = vs.packed;
+  const uint64_t bps = (samples.size() + 3) / 4;
   const uint64_t n = samples.size(), dvar = ids.size();
   if (dvar == 0) die("No variants passed filters across all VCF files. Cannot proceed with PCA.");   // main.rs:198
   info("Aggregated " + std::to_string(dvar) + " variants in total across all VCFs.");
@@ -581,7 +809,8 @@ int run_vcf(const Args& a) {
   for_each_shard(sh, [&](int g) {
     gpca_ctx* ctx = sh.ctx[g];
     const uint64_t dv = v0[g + 1] - v0[g];
-    check(ctx, gpca_load_u8_variant_major(ctx, dosage.data() + v0[g] * n, n, dv), "load");
+    // 2-bit rows in PLINK coding, packed while parsing: a quarter of the bytes of the u8 matrix on the host and on the bus
+    check(ctx, gpca_load_bed(ctx, packed.data() + v0[g] * bps, n, dv, nullptr, 0), "load");
     std::vector<uint8_t> keep(dv);
     std::vector<float> mean(dv), sd(dv);
     check(ctx, gpca_vcf_maf_filter(ctx, maf_thr, keep.data(), mean.data(), sd.data()), "maf filter");
@@ -914,6 +1143,7 @@ int run_eigensnp(const Args& a) {
 int main(int argc, char** argv) {
   if (argc == 5 && std::string(argv[1]) == "--bench-writers")
     return bench_writers(strtoull(argv[2], nullptr, 10), (uint32_t)atol(argv[3]), argv[4]);
+  if (argc >= 6 && std::string(argv[1]) == "--parse-vcf") return parse_vcf_hook(argc, argv);
   const Args a = parse(argc, argv);
   const auto t0 = std::chrono::steady_clock::now();
   const int rc = a.eigensnp ? run_eigensnp(a) : run_vcf(a);

@@ -170,3 +170,112 @@ def test_cli_vcf_workflow(tmp_path, gpu_ctx):
     sc, ev, _ = gpu_ctx.rfit(3, 10, power_iters=2, seed=11, want_loadings=False)
     got = np.array([[float(x) for x in ln.split("\t")[1:]] for ln in pcs[1:]])
     assert np.abs(got - sc).max() <= 1e-6 + 1e-6 * np.abs(sc).max()
+
+
+# ------------------------------------------------------------------------------------------- VCF text on the host
+def _bgzf(data: bytes, block: int = 0xff00) -> bytes:
+    """BGZF as bgzip writes it: gzip members of <= 64 KiB input with the 'BC' extra field, then the empty EOF member."""
+    import struct
+    import zlib
+
+    def member(chunk):
+        c = zlib.compressobj(6, zlib.DEFLATED, -15)
+        raw = c.compress(chunk) + c.flush()
+        head = b"\x1f\x8b\x08\x04" + b"\0\0\0\0" + b"\x00\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, len(raw) + 25)
+        return head + raw + struct.pack("<II", zlib.crc32(chunk), len(chunk))
+
+    out = b"".join(member(data[i:i + block]) for i in range(0, len(data), block))
+    return out + member(b"")
+
+
+def _vcf_text(g, chrom, n, fmt="GT:DP", extra=(), crlf=False, final_newline=True):
+    lines = ["##fileformat=VCFv4.2", '##FORMAT=<ID=GT,Number=1,Type=String,Description="Genotype">',
+             "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + "\t".join(f"s{i}" for i in range(n))]
+    gt = {0: "0|0", 1: "0|1", 2: "1/1"}
+    gi = fmt.split(":").index("GT")
+    for j, row in enumerate(g):
+        def cell(v):
+            parts = ["7"] * len(fmt.split(":"))
+            parts[gi] = gt[int(v)]
+            return ":".join(parts)
+        lines.append(f"{chrom}\t{100 + j}\trs{j}\tA\tC\t.\t.\t.\t{fmt}\t" + "\t".join(cell(v) for v in row))
+    lines += list(extra)
+    t = ("\r\n" if crlf else "\n").join(lines)
+    return t + (("\r\n" if crlf else "\n") if final_newline else "")
+
+
+def _pack_plink(dos):
+    """dosage u8 [D x N] -> 2-bit rows in PLINK coding (0 -> 11, 1 -> 10, 2 -> 00), zero padding"""
+    d, n = dos.shape
+    code = np.array([3, 2, 0], dtype=np.uint8)[dos]
+    pad = (-n) % 4
+    code = np.pad(code, ((0, 0), (0, pad)))
+    c4 = code.reshape(d, -1, 4)
+    return (c4[:, :, 0] | (c4[:, :, 1] << 2) | (c4[:, :, 2] << 4) | (c4[:, :, 3] << 6)).astype(np.uint8)
+
+
+@pytest.mark.parametrize("threads,batch", [(1, 1 << 26), (4, 1 << 26), (8, 3000), (3, 150_000)])
+def test_vcf_host_parser_plain_gzip_bgzf(tmp_path, threads, batch):
+    """The host half of the VCF workflow without a GPU (`--parse-vcf`): three containers (plain text, one gzip stream,
+    BGZF with its blocks inflated concurrently), batches smaller than a line, CRLF, a last line without a newline,
+    GT at another FORMAT position, the reference's drop rules -- ids and 2-bit rows byte for byte what the oracle's
+    restatement of src/vcf.rs gives, in sorted-path order."""
+    import json
+    n = 203                                                # not a multiple of 4: padded last byte
+    g, _ = make_dataset(n, 1500, n_pops=3, seed=91)
+    g = g.astype(np.uint8)
+    bad = [f"3\t9000\t.\tAT\tC\t.\t.\t.\tGT\t" + "\t".join(["0|1"] * n),            # REF longer than one base
+           f"3\t9001\t.\tA\tC,G\t.\t.\t.\tGT\t" + "\t".join(["0|1"] * n),           # multi-allelic
+           f"3\t9002\t.\tA\t.\t.\t.\t.\tGT\t" + "\t".join(["0|1"] * n),             # no ALT
+           f"3\t9003\t.\tA\tC\t.\t.\t.\tGT\t" + "\t".join(["./."] + ["0|1"] * (n - 1)),   # a missing call
+           f"3\t9004\t.\tA\tC\t.\t.\t.\tDP\t" + "\t".join(["7"] * n),               # no GT key
+           f"3\t9005\t.\tA\tC\t.\t.\t.\tGT\t" + "\t".join(["0|1"] * (n - 1)),        # a sample short
+           f"3\t9006\t.\tA\tC\t.\t.\t.\tGT\t" + "\t".join(["0|2"] + ["0|1"] * (n - 1)),   # allele other than 0 / 1
+           f"3\t9007\t.\tA\tC\t.\t.\t.\tGT\t" + "\t".join(["0|0"] * n)]              # monomorphic: MAF filter
+    texts = {
+        "a.chr1.vcf": _vcf_text(g[:400], "1", n, final_newline=False),
+        "b.chr2.vcf.gz": _vcf_text(g[400:900], "2", n, fmt="DP:GT:GQ", crlf=True),
+        "c.chr3.vcf.gz": _vcf_text(g[900:], "3", n, extra=bad),
+    }
+    d = tmp_path / "vcfs"
+    d.mkdir()
+    (d / "a.chr1.vcf").write_text(texts["a.chr1.vcf"])
+    with gzip.open(d / "b.chr2.vcf.gz", "wb") as f:
+        f.write(texts["b.chr2.vcf.gz"].encode())
+    (d / "c.chr3.vcf.gz").write_bytes(_bgzf(texts["c.chr3.vcf.gz"].encode(), block=20_000))
+    (d / "notes.txt").write_text("ignored")
+    r = _run("--parse-vcf", str(d), "0.05", str(threads), str(batch), str(tmp_path / "dump"))
+    assert r.returncode == 0, r.stderr
+    info = json.loads(r.stdout)
+    ids, rows = [], []
+    for name in sorted(texts):
+        s, i, dos = vcf.parse_vcf_text(texts[name].replace("\r\n", "\n"), 0.05)
+        assert len(s) == n
+        ids += i
+        rows.append(dos)
+    dos = np.concatenate(rows)
+    assert info["samples"] == n and info["variants"] == len(ids) and info["files"] == 3
+    assert info["bgzf_blocks"] >= len(texts["c.chr3.vcf.gz"]) // 20_000          # the BGZF path really ran
+    assert (tmp_path / "dump.ids").read_text().split("\n")[:-1] == ids
+    got = np.frombuffer((tmp_path / "dump.packed").read_bytes(), dtype=np.uint8).reshape(len(ids), -1)
+    assert np.array_equal(got, _pack_plink(dos))
+
+
+def test_vcf_host_parser_errors(tmp_path):
+    n = 8
+    g = np.random.default_rng(3).integers(0, 3, size=(50, n)).astype(np.uint8)
+    d = tmp_path / "v"
+    d.mkdir()
+    blob = bytearray(_bgzf(_vcf_text(g, "1", n).encode(), block=700))
+    blob[len(blob) // 2] ^= 0x55                                     # a flipped byte inside a block
+    (d / "x.vcf.gz").write_bytes(bytes(blob))
+    r = _run("--parse-vcf", str(d), "0.0", "2", "100000")
+    assert r.returncode != 0 and ("BGZF" in r.stderr)
+    (d / "x.vcf.gz").unlink()
+    (d / "a.vcf").write_text(_vcf_text(g, "1", n))
+    (d / "b.vcf").write_text(_vcf_text(g, "2", n + 1))                # another sample set
+    r = _run("--parse-vcf", str(d), "0.0", "2", "100000")
+    assert r.returncode != 0 and "Sample mismatch" in r.stderr       # main.rs:157-160
+    (d / "b.vcf").write_text(_vcf_text(g, "2", n).replace('##FORMAT=<ID=GT', '##FORMAT=<ID=XX'))
+    r = _run("--parse-vcf", str(d), "0.0", "2", "100000")
+    assert r.returncode != 0 and "GT key" in r.stderr                # vcf.rs:93
