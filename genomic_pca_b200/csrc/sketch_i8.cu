@@ -35,19 +35,30 @@ constexpr int CHUNKS = 4;          // 64-field chunks per stage
 // reach ~5.1 TB/s (tools/probe/tma_bw_probe.cu).  Item mode (batched LD blocks: one or two stages per item, bound by
 // the latency of an item rather than by bandwidth) keeps 64-byte boxes so that four stages can be in flight.
 // BOX = bytes of a packed row per TMA box (64 or 128), see the comment above
-template <int BOX, int RT>
+#ifndef GPCA_I8_DEEP_KH
+#define GPCA_I8_DEEP_KH 1
+#endif
+// DEEP (RT = 2 only): ONE 256-row CTA per SM that owns the whole TMEM -- six A slots instead of two, so the expanders
+// run up to six chunk pairs ahead of the MMAs -- with two expander warps per (row tile, lane quarter), each expanding
+// one 64-field half of every chunk pair (16 expander warps per SM, as with two regular CTAs).
+template <int BOX, int RT, bool DEEP = false>
 struct ACfg {
+  static_assert(!DEEP || (RT == 2 && BOX == 128), "the deep-slot shape is a 256-row CTA with 128-byte boxes");
   static constexpr int ROW_BYTES = BOX;
   static constexpr int HALVES = ROW_BYTES / 64;          // 256-field stages per A stage
   static constexpr int TILE_BYTES = 128 * ROW_BYTES;
   static constexpr int STAGE_BYTES = RT * TILE_BYTES;
-  static constexpr int RING_BYTES = 32768 * RT;          // 64 KB of A stages at RT = 2, 128 KB at RT = 4
+  static constexpr int RING_BYTES = DEEP ? 131072 : 32768 * RT;   // 64 KB of A stages at RT = 2, 128 KB at RT = 4 / DEEP
   static constexpr int SA = RING_BYTES / STAGE_BYTES;
-  static constexpr int NUM_THREADS = 128 + 128 * RT;     // warps 0..3: producers / issuer / idle; then 4 expander warps per row tile
+  static constexpr int KH = (DEEP && GPCA_I8_DEEP_KH == 2) ? 2 : 1;   // expander warps per (row tile, lane quarter): K halves of a chunk pair
+  static constexpr int NUM_THREADS = 128 + 128 * RT * KH;   // warps 0..3: producers / issuer / idle; then 4 * KH expander warps per row tile
                                                          // (a multiple of 4 warps: warp & 3 is the TMEM lane quarter of the warp)
-  static constexpr int TMEM_COLS = RT == 2 ? 256 : 512;
+  static constexpr int TMEM_COLS = (RT == 2 && !DEEP) ? 256 : 512;
   static constexpr int A_COL0 = RT * 64;                 // accumulators: RT * 64 columns, then SLOTS * RT * 32 columns of A slots
-  static constexpr int CTAS_PER_SM = RT == 2 ? 2 : 1;
+  static constexpr int CTAS_PER_SM = (RT == 2 && !DEEP) ? 2 : 1;
+  static constexpr int SLOTS = DEEP ? 6 : 2;             // a TMEM slot holds a chunk pair (128 fields) of every row tile
+  static constexpr int SB = DEEP ? 4 : 3;                // B' stages
+  static_assert(RT * 64 + SLOTS * RT * 32 <= TMEM_COLS, "TMEM budget");
 };
 constexpr int NL = 32;             // logical columns
 constexpr int NM = 64;             // MMA N = hi | lo limbs
@@ -57,8 +68,8 @@ constexpr int NM = 64;             // MMA N = hi | lo limbs
 // (RT = 2: 384 threads compiled at 80 registers; warpgroup 0 gives 128 x 48 registers up, the two expander warpgroups
 //  take 256 x 24.  RT = 4 runs one CTA per SM at the compiled allocation.)
 #if GPCA_I8_REGSPLIT
-#define REG_DEC() do { if (RT == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;"); } while (0)
-#define REG_INC() do { if (RT == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;"); } while (0)
+#define REG_DEC() do { if (RT == 2 && !DEEP) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;"); } while (0)
+#define REG_INC() do { if (RT == 2 && !DEEP) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;"); } while (0)
 #else
 #define REG_DEC()
 #define REG_INC()
@@ -78,12 +89,10 @@ __device__ __forceinline__ uint32_t prof_clock() { uint32_t c; asm volatile("mov
 #ifndef GPCA_I8_TILE_SYNC_DEFAULT
 #define GPCA_I8_TILE_SYNC_DEFAULT false
 #endif
-constexpr int SB = 3, SLOTS = 2;   // a TMEM slot holds a chunk pair (128 fields) of every row tile
 constexpr int B_STAGE_BYTES = STAGE_FIELDS * NM;       // 1 byte per element
 constexpr int D_COL0 = 0;
-static_assert(2 * NM + SLOTS * 2 * 32 <= 256 && 4 * NM + SLOTS * 4 * 32 <= 512, "TMEM budget");
-template <int RT>
-constexpr int smem_bytes_for() { return 32768 * RT + SB * B_STAGE_BYTES + 384 + 320; }
+template <int RT, bool DEEP = false>
+constexpr int smem_bytes_for() { return ACfg<128, RT, DEEP>::RING_BYTES + ACfg<128, RT, DEEP>::SB * B_STAGE_BYTES + 512 + 320; }
 constexpr uint32_t MAX_STAGES_PER_ITEM = 20000;        // 3 * 128 * 256 * 20000 < 2^31: no int32 overflow
 
 // 16 fields of a word -> 4 registers of 4 x u8 (register j holds fields j, j+4, j+8, j+12)
@@ -160,16 +169,21 @@ __device__ __forceinline__ ItemInfo decode_item(const I8Params& p, uint32_t item
 // TS (tile sync): the TMEM hand-over between expanders and the MMA issuer is per ROW TILE (barriers of 4 warps) instead
 // of per CTA (all 4 * RT expander warps): a tile's MMAs start as soon as its own four warps have stored their chunk pair,
 // and its warps get the slot back without waiting for the other tile's MMAs.
-template <bool ITEMS, int RT, bool TS, int BOX>
-__global__ void __launch_bounds__(ACfg<BOX, RT>::NUM_THREADS, ACfg<BOX, RT>::CTAS_PER_SM)
+template <bool ITEMS, int RT, bool TS, int BOX, bool DEEP = false>
+__global__ void __launch_bounds__(ACfg<BOX, RT, DEEP>::NUM_THREADS, ACfg<BOX, RT, DEEP>::CTAS_PER_SM)
 sketch_i8_kernel(const __grid_constant__ CUtensorMap tmap, const I8Params p) {
+  static_assert(!(DEEP && ITEMS), "deep slots: regular mode");
+  // DEEP with the per-tile hand-over runs one MMA issuer per row tile (warps 1 and 3): a single thread issues one
+  // tcgen05.mma per ~48 cycles at best (tools/probe/mma_sttm_probe.cu) -- two CTAs per SM have two issuers between them,
+  // a lone CTA needs two of its own to keep the pipe (32 cycles per MMA at N = 64) busy.
+  constexpr bool DI = DEEP && TS;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);
   const uint32_t a_ring = smem_base;
-  using AC = ACfg<BOX, RT>;
+  using AC = ACfg<BOX, RT, DEEP>;
   constexpr int A_ROW_BYTES = AC::ROW_BYTES, HALVES = AC::HALVES, A_TILE_BYTES = AC::TILE_BYTES,
                 A_STAGE_BYTES = AC::STAGE_BYTES, SA = AC::SA, A_RING_BYTES = AC::RING_BYTES, TMEM_COLS = AC::TMEM_COLS,
-                A_COL0 = AC::A_COL0;
+                A_COL0 = AC::A_COL0, SLOTS = AC::SLOTS, SB = AC::SB, KH = AC::KH;
   static_assert((RT == 2 || RT == 4) && SA * A_STAGE_BYTES == A_RING_BYTES && SA >= 2 && SA <= 4, "A ring layout");
   const uint32_t b_ring = smem_base + A_RING_BYTES;
   const uint32_t bars = b_ring + SB * B_STAGE_BYTES;
@@ -178,12 +192,13 @@ sketch_i8_kernel(const __grid_constant__ CUtensorMap tmap, const I8Params p) {
   auto bar_bfull = [&](int s) { return bars + 8u * (8 + s); };
   // TMEM slot barriers: one pair per slot, or (TS) one pair per (slot, row tile)
   auto bar_tfull = [&](int j, int t) { return bars + 8u * (32 + (TS ? j * RT + t : j)); };
-  auto bar_tempty = [&](int j, int t) { return bars + 8u * (40 + (TS ? j * RT + t : j)); };
+  auto bar_tempty = [&](int j, int t) { return bars + 8u * (48 + (TS ? j * RT + t : j)); };
+  static_assert(SLOTS * (TS ? RT : 1) <= 16, "TMEM slot barriers");
   auto bar_bempty = [&](int s) { return bars + 8u * (24 + s); };
   const uint32_t bar_accfull = bars + 8u * 28;
   const uint32_t bar_accempty = bars + 8u * 29;
   const uint32_t tmem_slot = bars + 8u * 30;
-  const uint32_t cvec_smem = bars + 384;
+  const uint32_t cvec_smem = bars + 512;
   float* cv_s = reinterpret_cast<float*>(smem_raw + (cvec_smem - smem_base));
 
   const int warp = threadIdx.x >> 5;
@@ -192,18 +207,18 @@ sketch_i8_kernel(const __grid_constant__ CUtensorMap tmap, const I8Params p) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < SA; ++s) {
       mbar_init(bar_afull(s), 1);
-      mbar_init(bar_aempty(s), 4 * RT);
+      mbar_init(bar_aempty(s), 4 * RT * KH);
     }
     for (int s = 0; s < SB; ++s) {
       mbar_init(bar_bfull(s), 1);
-      mbar_init(bar_bempty(s), 1);
+      mbar_init(bar_bempty(s), DI ? 2 : 1);
     }
     for (int j = 0; j < SLOTS; ++j)
       for (int t = 0; t < (TS ? RT : 1); ++t) {
-        mbar_init(bar_tfull(j, t), TS ? 4 : 4 * RT);
+        mbar_init(bar_tfull(j, t), TS ? 4 * KH : 4 * RT * KH);
         mbar_init(bar_tempty(j, t), 1);
       }
-    mbar_init(bar_accfull, 1);
+    mbar_init(bar_accfull, DI ? 2 : 1);
     mbar_init(bar_accempty, 4 * RT);
     fence_barrier_init();
   }
@@ -232,11 +247,16 @@ sketch_i8_kernel(const __grid_constant__ CUtensorMap tmap, const I8Params p) {
   if (warp == 0 || warp == 2) {
     REG_DEC();
     // ---- producers: warp 0 = packed genotype tiles (TMA 2-D), warp 2 = B image (1-D bulk copies)
+    // ONE elected thread runs the whole role.  (Electing a lane around every issue -- `if (elect_one()) {...}
+    // __syncwarp();` per stage / per group of MMAs -- costs ~100 cycles of divergence and reconvergence each time:
+    // tools/probe/mma_sttm_probe.cu measures 74 cycles per tcgen05.mma with four MMAs per elected region against 32,
+    // the pipe's own rate, once the regions are gone.  That was what held the MMA issuer, and with it the pass.)
     const bool is_a = (warp == 0);
     uint32_t it = 0;
     PROF_DECL(c_wait = 0);
     PROF_T(t_role);
-    for (uint32_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+    const bool leader = elect_one();
+    for (uint32_t item = blockIdx.x; leader && item < p.n_items; item += gridDim.x) {
       const ItemInfo ii = decode_item<ITEMS, RT>(p, item);
       const int row0 = (int)ii.row0;
       if (is_a) {
@@ -247,15 +267,12 @@ sketch_i8_kernel(const __grid_constant__ CUtensorMap tmap, const I8Params p) {
           PROF_T(t0);
           mbar_wait(bar_aempty(s), ph ^ 1u);
           PROF_ADD(c_wait, t0);
-          if (elect_one()) {
-            const uint32_t sbase = a_ring + s * A_STAGE_BYTES;
-            mbar_arrive_expect_tx(bar_afull(s), A_STAGE_BYTES);
+          const uint32_t sbase = a_ring + s * A_STAGE_BYTES;
+          mbar_arrive_expect_tx(bar_afull(s), A_STAGE_BYTES);
 #pragma unroll
-            for (int t = 0; t < RT; ++t)
-              tma_load_2d(sbase + t * A_TILE_BYTES, &tmap, bar_afull(s), (int)(ii.kbyte0 + a * A_ROW_BYTES),
-                          row0 + t * 128);
-          }
-          __syncwarp();
+          for (int t = 0; t < RT; ++t)
+            tma_load_2d(sbase + t * A_TILE_BYTES, &tmap, bar_afull(s), (int)(ii.kbyte0 + a * A_ROW_BYTES),
+                        row0 + t * 128);
         }
       } else {
         for (uint32_t st = 0; st < ii.nst; ++st, ++it) {
@@ -264,21 +281,26 @@ sketch_i8_kernel(const __grid_constant__ CUtensorMap tmap, const I8Params p) {
           PROF_T(t0);
           mbar_wait(bar_bempty(s), ph ^ 1u);
           PROF_ADD(c_wait, t0);
-          if (elect_one()) {
-            mbar_arrive_expect_tx(bar_bfull(s), B_STAGE_BYTES);
-            bulk_load_1d(b_ring + s * B_STAGE_BYTES, p.bimg + (size_t)(ii.img_st0 + st) * B_STAGE_BYTES, B_STAGE_BYTES,
-                         bar_bfull(s));
+#ifdef GPCA_KO_BLOAD      // (measurement build: the image is copied for the first SB stages only -- wrong results, timing only)
+          if (it >= (uint32_t)SB) {
+            mbar_arrive(bar_bfull(s));
+            continue;
           }
-          __syncwarp();
+#endif
+          mbar_arrive_expect_tx(bar_bfull(s), B_STAGE_BYTES);
+          bulk_load_1d(b_ring + s * B_STAGE_BYTES, p.bimg + (size_t)(ii.img_st0 + st) * B_STAGE_BYTES, B_STAGE_BYTES,
+                       bar_bfull(s));
         }
       }
     }
 #ifdef GPCA_I8_PROF
-    if (blockIdx.x == 0 && lane == 0)
+    if (blockIdx.x == 0 && leader)
       printf("PROF %s producer: total %u wait_empty %u\n", is_a ? "A" : "B", prof_clock() - t_role, c_wait);
 #endif
-  } else if (warp == 1) {
+    __syncwarp();
+  } else if (warp == 1 || (DI && warp == 3)) {
     REG_DEC();
+    const int t_lo = DI ? (warp == 1 ? 0 : 1) : 0, t_hi = DI ? t_lo + 1 : RT;
     // ---- MMA issuer: D = s32, A = u8 (TMEM), B = s8 (smem, K-major, no swizzle), M = 128, N = 64, K = 32
     const uint32_t idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(NM >> 3) << 17) | (8u << 24);
     // B descriptor: LBO = 64 rows * 16 B = 1024 B (next 16-wide K chunk), SBO = 128 B (next 8 columns), version 1
@@ -287,7 +309,10 @@ sketch_i8_kernel(const __grid_constant__ CUtensorMap tmap, const I8Params p) {
     uint32_t it = 0, cit = 0, item_idx = 0;
     PROF_DECL(c_acc = 0, c_bfull = 0, c_tfull = 0);
     PROF_T(t_role);
-    for (uint32_t item = blockIdx.x; item < p.n_items; item += gridDim.x, ++item_idx) {
+    // one elected thread runs the whole role (see the producers above): waits, MMAs and commits without a divergent
+    // region per group of MMAs
+    const bool leader = elect_one();
+    for (uint32_t item = blockIdx.x; leader && item < p.n_items; item += gridDim.x, ++item_idx) {
       const uint32_t nst = decode_item<ITEMS, RT>(p, item).nst;
       PROF_T(t_a);
       mbar_wait(bar_accempty, (item_idx & 1u) ^ 1u);
@@ -313,49 +338,46 @@ sketch_i8_kernel(const __grid_constant__ CUtensorMap tmap, const I8Params p) {
           }
 #pragma unroll
           for (int t = 0; t < RT; ++t) {
+            if (t < t_lo || t >= t_hi) continue;
             if (TS) {
               PROF_T(t_t);
               mbar_wait(bar_tfull(slot, t), sph);
               PROF_ADD(c_tfull, t_t);
               tc_fence_after();
             }
-            if (elect_one()) {
-              const uint32_t d_t = tmem_base + D_COL0 + t * NM;
-              const uint32_t a_t = tmem_base + A_COL0 + (slot * RT + t) * 32;
+            const uint32_t d_t = tmem_base + D_COL0 + t * NM;
+            const uint32_t a_t = tmem_base + A_COL0 + (slot * RT + t) * 32;
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {      // 4 MMAs of K = 32 cover the 128 fields of the pair
-                const uint32_t baddr = bsm + (uint32_t)((q * 2 + i) * (32 * NM));
-                const uint64_t bdesc = ((uint64_t)desc_hi << 32) | (uint64_t)(desc_lo_const | ((baddr >> 4) & 0x3FFFu));
+            for (int i = 0; i < 4; ++i) {      // 4 MMAs of K = 32 cover the 128 fields of the pair
+              const uint32_t baddr = bsm + (uint32_t)((q * 2 + i) * (32 * NM));
+              const uint64_t bdesc = ((uint64_t)desc_hi << 32) | (uint64_t)(desc_lo_const | ((baddr >> 4) & 0x3FFFu));
 #ifndef GPCA_KO_MMA
-                tc_mma_ts_i8(d_t, a_t + 8 * i, bdesc, idesc, acc_flag | (uint32_t)i);
+              tc_mma_ts_i8(d_t, a_t + 8 * i, bdesc, idesc, acc_flag | (uint32_t)i);
 #else
-                if (i == 0 && GPCA_KO_MMA) tc_mma_ts_i8(d_t, a_t + 8 * i, bdesc, idesc, acc_flag | (uint32_t)i);
+              if (i == 0 && GPCA_KO_MMA) tc_mma_ts_i8(d_t, a_t + 8 * i, bdesc, idesc, acc_flag | (uint32_t)i);
 #endif
-              }
-              if (TS || t == RT - 1) tc_commit(bar_tempty(slot, TS ? t : 0));
             }
-            __syncwarp();
+            if (TS || t == t_hi - 1) tc_commit(bar_tempty(slot, TS ? t : 0));
           }
-          __syncwarp();
           acc_flag = 1;
         }
-        if (elect_one()) tc_commit(bar_bempty(s));
-        __syncwarp();
+        tc_commit(bar_bempty(s));
       }
-      if (elect_one()) tc_commit(bar_accfull);
-      __syncwarp();
+      tc_commit(bar_accfull);
     }
 #ifdef GPCA_I8_PROF
-    if (blockIdx.x == 0 && lane == 0)
+    if (blockIdx.x == 0 && leader)
       printf("PROF issuer: total %u wait_accempty %u wait_bfull %u wait_tfull %u pairs %u\n", prof_clock() - t_role, c_acc,
              c_bfull, c_tfull, cit);
 #endif
+    __syncwarp();
   } else if (warp == 3) {
     REG_DEC();
   } else {
     REG_INC();
     // ---- expanders + epilogue
-    const int tile = (warp - 4) >> 2;
+    const int tile = ((warp - 4) >> 2) % RT;
+    const int khalf = KH == 2 ? (warp - 4) / (4 * RT) : 0;      // DEEP: which 64-field half of every chunk pair this warp expands
     const int quarter = warp & 3;
     const int row_in_tile = quarter * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
@@ -379,6 +401,39 @@ sketch_i8_kernel(const __grid_constant__ CUtensorMap tmap, const I8Params p) {
 #pragma unroll
         for (int h = 0; h < HALVES; ++h) {
           if (a * HALVES + h >= ii.nst) break;     // odd stage count: the last A stage is half used
+          if (DEEP && KH == 2) {
+            // one 16-byte chunk (64 fields) of each of the two chunk pairs of the stage: 16 columns of the slot
+            uint4 v[CHUNKS / 2];
+#pragma unroll
+            for (int q = 0; q < CHUNKS / 2; ++q) {
+              const uint32_t addr = arow + (((uint32_t)(h * CHUNKS + 2 * q + khalf) ^ sw) << 4);
+              asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                           : "=r"(v[q].x), "=r"(v[q].y), "=r"(v[q].z), "=r"(v[q].w)
+                           : "r"(addr));
+            }
+#pragma unroll
+            for (int q = 0; q < CHUNKS / 2; ++q, ++cit) {
+              const int slot = cit % SLOTS;
+              const uint32_t sph = (cit / SLOTS) & 1u;
+              uint32_t r0[16];
+              expand_word_u8(v[q].x, r0 + 0);
+              expand_word_u8(v[q].y, r0 + 4);
+              expand_word_u8(v[q].z, r0 + 8);
+              expand_word_u8(v[q].w, r0 + 12);
+              PROF_T(t_te);
+              mbar_wait(bar_tempty(slot, tile), sph ^ 1u);
+              PROF_ADD(c_tempty, t_te);
+              tc_fence_after();
+              PROF_T(t_st);
+              tmem_st16(tmem_base + lane_addr + A_COL0 + (slot * RT + tile) * 32 + 16 * khalf, r0);
+              tc_wait_st();
+              PROF_ADD(c_st, t_st);
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar_tfull(slot, tile));
+            }
+            continue;
+          }
           uint4 v[CHUNKS];
 #pragma unroll
           for (int q = 0; q < CHUNKS; ++q) {
@@ -430,7 +485,8 @@ sketch_i8_kernel(const __grid_constant__ CUtensorMap tmap, const I8Params p) {
         // share an SM.)
         if (lane == 0) mbar_arrive(bar_aempty(s));
       }
-      // ---- epilogue
+      // ---- epilogue (DEEP: by the warps of K half 0; the others go on to the next item's stages)
+      if (KH == 2 && khalf != 0) continue;
       PROF_T(t_epi);
       const uint32_t lrow = (uint32_t)(tile * 128 + row_in_tile);
       const bool live = lrow < ii.nrows;
@@ -1002,15 +1058,16 @@ int launch_sketch_i8(gpca_ctx* c, const SketchProblem& p) {
     uint32_t ksplit, row_groups, slots;
     double est_us;
   };
-  auto make_plan = [&](int rt) {
+  auto make_plan = [&](int rt, bool deep_cta = false) {
     Plan pl;
     pl.row_groups = (uint32_t)((rows + rt * 128 - 1) / (rt * 128));
-    pl.slots = (uint32_t)c->sm_count * (rt == 2 ? 2u : 1u);
+    pl.slots = (uint32_t)c->sm_count * ((rt == 2 && !deep_cta) ? 2u : 1u);
     pl.ksplit = 1;
     const uint32_t max_split = std::max<uint32_t>(1u, (total_stages + 7) / 8);
     const uint32_t hi = std::min<uint32_t>(max_split, (8 * pl.slots + pl.row_groups - 1) / pl.row_groups + 1);
-    const double t_stage_us = (double)c->sm_count * 2.0 * 16384.0 / 4.2e6;   // one stage on every SM's rows at ~4.2 TB/s
-    const double t_item_us = rt == 2 ? 2.0 : 4.0;     // epilogue / hand-over per item (not hidden behind a second CTA at RT = 4)
+    // one stage of every resident CTA's rows at ~4.2 TB/s
+    const double t_stage_us = (double)c->sm_count * (deep_cta ? 1.0 : 2.0) * 16384.0 / 4.2e6;
+    const double t_item_us = (rt == 2 && !deep_cta) ? 2.0 : 4.0;   // epilogue / hand-over per item (not hidden behind a second CTA)
     double best = 1e300;
     for (uint32_t ks = 1; ks <= hi; ++ks) {
       const uint32_t spp_c = (total_stages + ks - 1) / ks;
@@ -1039,9 +1096,11 @@ int launch_sketch_i8(gpca_ctx* c, const SketchProblem& p) {
   // hand-over that waits for 16 warps instead of 8 costs more than the halved operand traffic saves.  The shape stays
   // available for experiments (GPCA_I8_WIDE=1) and is kept bit-identical to the regular one by the tests.
   (void)spp4;
-  bool wide = false;
+  bool wide = false, deep = false;
   if (const char* e = getenv("GPCA_I8_WIDE")) wide = atoi(e) != 0 && rows >= 512;
-  const Plan& plan = wide ? plan4 : plan2;
+  if (const char* e = getenv("GPCA_I8_DEEP")) deep = atoi(e) != 0 && !wide;
+  const Plan plan2d = make_plan(2, true);
+  const Plan& plan = wide ? plan4 : deep ? plan2d : plan2;
   const uint32_t row_groups = plan.row_groups, slots = plan.slots;
   uint32_t ksplit = plan.ksplit;
   if (getenv("GPCA_DEBUG_OLD_KSPLIT")) {      // the rule before the cost model (A/B)
@@ -1107,8 +1166,24 @@ int launch_sketch_i8(gpca_ctx* c, const SketchProblem& p) {
   KernelTimer kt(c);
   if (wide) {
     constexpr int smem4 = smem_bytes_for<4>();
-    GPCA_CUDA_TRY(c, cudaFuncSetAttribute(sketch_i8_kernel<false, 4, false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem4));
-    sketch_i8_kernel<false, 4, false, 128><<<grid, ACfg<128, 4>::NUM_THREADS, smem4, c->stream>>>(tmap, tp);
+    const char* tsv = getenv("GPCA_I8_TILE_SYNC");
+    if (tsv && atoi(tsv) != 0) {
+      GPCA_CUDA_TRY(c, cudaFuncSetAttribute(sketch_i8_kernel<false, 4, true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem4));
+      sketch_i8_kernel<false, 4, true, 128><<<grid, ACfg<128, 4>::NUM_THREADS, smem4, c->stream>>>(tmap, tp);
+    } else {
+      GPCA_CUDA_TRY(c, cudaFuncSetAttribute(sketch_i8_kernel<false, 4, false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem4));
+      sketch_i8_kernel<false, 4, false, 128><<<grid, ACfg<128, 4>::NUM_THREADS, smem4, c->stream>>>(tmap, tp);
+    }
+  } else if (deep) {
+    constexpr int smemd = smem_bytes_for<2, true>();
+    const char* tsv = getenv("GPCA_I8_TILE_SYNC");
+    if (tsv && atoi(tsv) != 0) {      // + one issuer per row tile
+      GPCA_CUDA_TRY(c, cudaFuncSetAttribute(sketch_i8_kernel<false, 2, true, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemd));
+      sketch_i8_kernel<false, 2, true, 128, true><<<grid, ACfg<128, 2, true>::NUM_THREADS, smemd, c->stream>>>(tmap, tp);
+    } else {
+      GPCA_CUDA_TRY(c, cudaFuncSetAttribute(sketch_i8_kernel<false, 2, false, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemd));
+      sketch_i8_kernel<false, 2, false, 128, true><<<grid, ACfg<128, 2, true>::NUM_THREADS, smemd, c->stream>>>(tmap, tp);
+    }
   } else {
     int smem_bytes = smem_bytes_for<2>();
     if (const char* dbg = getenv("GPCA_DEBUG_SMEM_EXTRA")) smem_bytes += atoi(dbg);
@@ -1122,7 +1197,7 @@ int launch_sketch_i8(gpca_ctx* c, const SketchProblem& p) {
       sketch_i8_kernel<false, 2, false, 128><<<grid, ACfg<128, 2>::NUM_THREADS, smem_bytes, c->stream>>>(tmap, tp);
     }
   }
-  kt.end(rows, K, ksplit | (wide ? 0x10000u : 0u), tp.n_items);
+  kt.end(rows, K, ksplit | (wide ? 0x10000u : 0u) | (deep ? 0x20000u : 0u), tp.n_items);
   c->launches++;
   GPCA_CUDA_TRY(c, cudaGetLastError());
   if (ksplit > 1) {

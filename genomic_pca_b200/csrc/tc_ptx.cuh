@@ -22,7 +22,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n"
       ".reg .pred P1;\n"
+#ifdef GPCA_MBAR_POLL      // (measurement build: non-suspending poll)
+      "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+#else
       "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+#endif
       "selp.b32 %0, 1, 0, P1;\n"
       "}\n"
       : "=r"(ok)

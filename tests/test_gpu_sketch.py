@@ -181,11 +181,13 @@ def test_rfit_reproducible_at_multi_item_scale(gpu_ctx):
     assert pca.subspace_angle(a[0], c[0]) < 1e-3
 
 
-@pytest.mark.parametrize("switch", ["GPCA_I8_WIDE", "GPCA_I8_TILE_SYNC"])
+@pytest.mark.parametrize("switch", ["GPCA_I8_WIDE", "GPCA_I8_TILE_SYNC", "GPCA_I8_DEEP", "GPCA_I8_WIDE+GPCA_I8_TILE_SYNC",
+                                    "GPCA_I8_DEEP+GPCA_I8_TILE_SYNC"])
 @pytest.mark.parametrize("ksplit", ["1", "3"])
 def test_int8_engine_variants_equal_regular(gpu_ctx, monkeypatch, ksplit, switch):
     """Variants of the integer engine's schedule -- the 512-row CTA shape (one CTA per SM, the whole TMEM: every
-    operand-image stage shared by twice as many rows) and the per-row-tile TMEM hand-over -- against the regular kernel on
+    operand-image stage shared by twice as many rows), the per-row-tile TMEM hand-over, both together, and the deep-slot
+    shape (one 256-row CTA per SM with six TMEM slots and two expander warps per lane quarter) -- against the regular kernel on
     the same K split: the integer accumulation is exact and the fp32 epilogue is per row, so they must agree bit for bit
     -- odd row counts, several items per CTA, both pass orientations, with and without split-K partials."""
     n, m, l = 4000 + 77, 150_000, 30
@@ -203,7 +205,8 @@ def test_int8_engine_variants_equal_regular(gpu_ctx, monkeypatch, ksplit, switch
         for fn, src, rows in ((gpu_ctx.sketch_snp_side, Bs, d), (gpu_ctx.sketch_sample_side, Bd, n)):
             outs = {}
             for wide in ("0", "1", "1"):
-                monkeypatch.setenv(switch, wide)
+                for name in switch.split("+"):
+                    monkeypatch.setenv(name, wide)
                 o = torch.full((rows, l), float("nan"), device=dev)
                 fn(src.data_ptr(), o.data_ptr(), l, l)
                 gpu_ctx.synchronize()

@@ -68,6 +68,8 @@ def main():
         shapes = [(2504, 10_000_000), (500_000, 87_500)]
         if os.environ.get("AB_SHAPES") == "c3":
             shapes = shapes[:1]
+        if os.environ.get("AB_SHAPES") == "shard":
+            shapes = shapes[1:]
         child(shapes)
         return
     variants = sys.argv[1:] or [""]
