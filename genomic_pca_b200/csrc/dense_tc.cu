@@ -126,9 +126,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) dense_tc_kernel(const __grid_c
 
   if (warp == 0 || warp == 2) {
     DENSE_REG_DEC();
+    // one elected thread runs the whole role (an elected region per stage costs ~100 cycles: tools/probe/mma_sttm_probe.cu)
     const bool is_a = (warp == 0);
     uint32_t it = 0;
-    for (uint32_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+    const bool leader = elect_one();
+    for (uint32_t item = blockIdx.x; leader && item < p.n_items; item += gridDim.x) {
       uint32_t rg, ks, st0, st1;
       item_range(item, rg, ks, st0, st1);
       const int row0 = (int)(rg * (RT * 128));
@@ -136,28 +138,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) dense_tc_kernel(const __grid_c
         if (is_a) {
           const int s = it % SA;
           mbar_wait(bar_aempty(s), ((it / SA) & 1u) ^ 1u);
-          if (elect_one()) {
-            const uint32_t sbase = a_ring + s * A_STAGE_BYTES;
-            mbar_arrive_expect_tx(bar_afull(s), A_STAGE_BYTES);
+          const uint32_t sbase = a_ring + s * A_STAGE_BYTES;
+          mbar_arrive_expect_tx(bar_afull(s), A_STAGE_BYTES);
 #pragma unroll
-            for (int t = 0; t < RT; ++t) {
-              if (COLS)      // box [128 rows-of-X (inner, contiguous in C) x 32 k]
-                tma_load_2d(sbase + t * A_TILE_BYTES, &tmap, bar_afull(s), row0 + t * 128, (int)(st * KS));
-              else           // box [32 k (inner) x 128 rows]
-                tma_load_2d(sbase + t * A_TILE_BYTES, &tmap, bar_afull(s), (int)(st * KS), row0 + t * 128);
-            }
+          for (int t = 0; t < RT; ++t) {
+            if (COLS)      // box [128 rows-of-X (inner, contiguous in C) x 32 k]
+              tma_load_2d(sbase + t * A_TILE_BYTES, &tmap, bar_afull(s), row0 + t * 128, (int)(st * KS));
+            else           // box [32 k (inner) x 128 rows]
+              tma_load_2d(sbase + t * A_TILE_BYTES, &tmap, bar_afull(s), (int)(st * KS), row0 + t * 128);
           }
         } else {
           const int s = it % SB;
           mbar_wait(bar_bempty(s), ((it / SB) & 1u) ^ 1u);
-          if (elect_one()) {
-            mbar_arrive_expect_tx(bar_bfull(s), B_STAGE_BYTES);
-            bulk_load_1d(b_ring + s * B_STAGE_BYTES, p.bimg + (size_t)st * KS * NC, B_STAGE_BYTES, bar_bfull(s));
-          }
+          mbar_arrive_expect_tx(bar_bfull(s), B_STAGE_BYTES);
+          bulk_load_1d(b_ring + s * B_STAGE_BYTES, p.bimg + (size_t)st * KS * NC, B_STAGE_BYTES, bar_bfull(s));
         }
-        __syncwarp();
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
     DENSE_REG_DEC();
     // D = f32, A = B = bf16, K-major both, M = 128; N = 64 (Xh x [Bh|Bl]) or 32 (Xl x Bh)
@@ -168,7 +166,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) dense_tc_kernel(const __grid_c
     const uint32_t desc_lo_const = (uint32_t)((NC * 16) >> 4) << 16;
     const uint32_t desc_hi = (uint32_t)(128 >> 4) | (1u << 14);
     uint32_t it = 0, item_idx = 0;
-    for (uint32_t item = blockIdx.x; item < p.n_items; item += gridDim.x, ++item_idx) {
+    const bool leader = elect_one();      // the whole role on one thread
+    for (uint32_t item = blockIdx.x; leader && item < p.n_items; item += gridDim.x, ++item_idx) {
       uint32_t rg, ks, st0, st1;
       item_range(item, rg, ks, st0, st1);
       mbar_wait(bar_accempty, (item_idx & 1u) ^ 1u);
@@ -181,28 +180,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) dense_tc_kernel(const __grid_c
         const int slot = it % SLOTS;
         mbar_wait(bar_tfull(slot), (it / SLOTS) & 1u);
         tc_fence_after();
-        if (elect_one()) {
 #pragma unroll
-          for (int t = 0; t < RT; ++t) {
-            const uint32_t d_t = tmem_base + D_COL0 + t * NC;
-            const uint32_t a_t = tmem_base + A_COL0 + (slot * RT + t) * 32;
+        for (int t = 0; t < RT; ++t) {
+          const uint32_t d_t = tmem_base + D_COL0 + t * NC;
+          const uint32_t a_t = tmem_base + A_COL0 + (slot * RT + t) * 32;
 #pragma unroll
-            for (int i = 0; i < KS / 16; ++i) {
-              const uint32_t baddr = bsm + (uint32_t)(i * 16 * NC * 2);
-              const uint64_t bdesc = ((uint64_t)desc_hi << 32) | (uint64_t)(desc_lo_const | ((baddr >> 4) & 0x3FFFu));
-              tc_mma_ts(d_t, a_t + 8 * i, bdesc, idesc64, acc_flag | (uint32_t)i);          // Xh x [Bh | Bl]
-              tc_mma_ts(d_t, a_t + 16 + 8 * i, bdesc, idesc32, 1u);                          // Xl x Bh
-            }
+          for (int i = 0; i < KS / 16; ++i) {
+            const uint32_t baddr = bsm + (uint32_t)(i * 16 * NC * 2);
+            const uint64_t bdesc = ((uint64_t)desc_hi << 32) | (uint64_t)(desc_lo_const | ((baddr >> 4) & 0x3FFFu));
+            tc_mma_ts(d_t, a_t + 8 * i, bdesc, idesc64, acc_flag | (uint32_t)i);          // Xh x [Bh | Bl]
+            tc_mma_ts(d_t, a_t + 16 + 8 * i, bdesc, idesc32, 1u);                          // Xl x Bh
           }
-          tc_commit(bar_tempty(slot));
-          tc_commit(bar_bempty(s));
         }
-        __syncwarp();
+        tc_commit(bar_tempty(slot));
+        tc_commit(bar_bempty(s));
         acc_flag = 1;
       }
-      if (elect_one()) tc_commit(bar_accfull);
-      __syncwarp();
+      tc_commit(bar_accfull);
     }
+    __syncwarp();
   } else if (warp == 3) {
     DENSE_REG_DEC();
   } else {

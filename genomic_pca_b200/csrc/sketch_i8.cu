@@ -86,6 +86,11 @@ __device__ __forceinline__ uint32_t prof_clock() { uint32_t c; asm volatile("mov
 #define PROF_T(x)
 #define PROF_ADD(acc, t0)
 #endif
+// GPCA_I8_DEFER_ST: tcgen05.wait::st of a chunk pair is issued after the NEXT pair has been expanded (the stores drain
+// while the warp computes) instead of right behind the stores.
+#ifndef GPCA_I8_DEFER_ST
+#define GPCA_I8_DEFER_ST 0
+#endif
 #ifndef GPCA_I8_TILE_SYNC_DEFAULT
 #define GPCA_I8_TILE_SYNC_DEFAULT false
 #endif
@@ -386,6 +391,10 @@ sketch_i8_kernel(const __grid_constant__ CUtensorMap tmap, const I8Params p) {
     const uint32_t sw = (A_ROW_BYTES == 128) ? (uint32_t)(row_in_tile & 7) : (uint32_t)((row_in_tile >> 1) & 3);
     uint32_t it = 0, cit = 0, item_idx = 0;
     float stat_max = 0.0f;     // by-product statistic of the output (see SketchProblem::emit_stats)
+#if GPCA_I8_DEFER_ST
+    bool st_pending = false;
+    int pend_slot = 0;
+#endif
     PROF_DECL(c_afull = 0, c_tempty = 0, c_st = 0, c_epi = 0, c_accfull = 0, c_ldtm = 0, c_ab = 0);
     PROF_T(t_role);
     for (uint32_t item = blockIdx.x; item < p.n_items; item += gridDim.x, ++item_idx) {
@@ -460,6 +469,18 @@ sketch_i8_kernel(const __grid_constant__ CUtensorMap tmap, const I8Params p) {
             expand_word_u8(v[q + 1].z, r1 + 8);
             expand_word_u8(v[q + 1].w, r1 + 12);
 #endif
+#if GPCA_I8_DEFER_ST
+            // the previous pair's TMEM stores were left in flight while this pair was expanded: complete and publish them
+            if (st_pending) {
+              PROF_T(t_st0);
+              tc_wait_st();
+              PROF_ADD(c_st, t_st0);
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar_tfull(pend_slot, tile));
+              st_pending = false;
+            }
+#endif
             PROF_T(t_te);
             mbar_wait(bar_tempty(slot, tile), sph ^ 1u);      // the MMAs that read this slot (of this tile: TS) have completed
             PROF_ADD(c_tempty, t_te);
@@ -469,6 +490,11 @@ sketch_i8_kernel(const __grid_constant__ CUtensorMap tmap, const I8Params p) {
 #ifndef GPCA_KO_STTM
             tmem_st16(ta, r0);
             tmem_st16(ta + 16, r1);
+#if GPCA_I8_DEFER_ST
+            st_pending = true;
+            pend_slot = slot;
+            continue;
+#endif
             tc_wait_st();
             PROF_ADD(c_st, t_st);
 #else
@@ -485,6 +511,15 @@ sketch_i8_kernel(const __grid_constant__ CUtensorMap tmap, const I8Params p) {
         // share an SM.)
         if (lane == 0) mbar_arrive(bar_aempty(s));
       }
+#if GPCA_I8_DEFER_ST
+      if (st_pending) {
+        tc_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tfull(pend_slot, tile));
+        st_pending = false;
+      }
+#endif
       // ---- epilogue (DEEP: by the warps of K half 0; the others go on to the next item's stages)
       if (KH == 2 && khalf != 0) continue;
       PROF_T(t_epi);

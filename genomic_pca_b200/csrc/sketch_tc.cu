@@ -141,12 +141,14 @@ sketch_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   if (warp == 0 || warp == 10) {
-    // ===================== producers (warp-uniform control flow, one elected lane issues) ==========
+    // ===================== producers (ONE elected thread runs the whole role: an elected region per stage costs
+    // ~100 cycles of divergence / reconvergence each, tools/probe/mma_sttm_probe.cu) ==========
     // warp 0 streams the packed genotype tiles (TMA 2-D, evict-first: read once from HBM);
     // warp 10 streams the B' image (1-D bulk copies, evict-last: shared by all CTAs through L2).
     const bool is_a = (warp == 0);
     uint32_t it = 0;
-    for (uint32_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+    const bool leader = elect_one();
+    for (uint32_t item = blockIdx.x; leader && item < p.n_items; item += gridDim.x) {
       const uint32_t ks = item / p.row_groups, rg = item - ks * p.row_groups;
       const uint32_t st0 = ks * p.stages_per_split;
       uint32_t st1 = st0 + p.stages_per_split;
@@ -157,35 +159,32 @@ sketch_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
           const int s = it % C::SA;
           const uint32_t ph = (it / C::SA) & 1u;
           mbar_wait(bar_aempty(s), ph ^ 1u);
-          if (elect_one()) {
-            const uint32_t sbase = a_ring + s * C::A_STAGE_BYTES;
-            mbar_arrive_expect_tx(bar_afull(s), C::A_STAGE_BYTES);
+          const uint32_t sbase = a_ring + s * C::A_STAGE_BYTES;
+          mbar_arrive_expect_tx(bar_afull(s), C::A_STAGE_BYTES);
 #pragma unroll
-            for (int t = 0; t < RT; ++t)
-              tma_load_2d(sbase + t * A_TILE_BYTES, &tmap, bar_afull(s), (int)(st * 64), row0 + t * 128);
-          }
+          for (int t = 0; t < RT; ++t)
+            tma_load_2d(sbase + t * A_TILE_BYTES, &tmap, bar_afull(s), (int)(st * 64), row0 + t * 128);
         } else {
           const int s = it % C::SB;
           const uint32_t ph = (it / C::SB) & 1u;
           mbar_wait(bar_bempty(s), ph ^ 1u);
-          if (elect_one()) {
-            mbar_arrive_expect_tx(bar_bfull(s), C::B_STAGE_BYTES);
-            bulk_load_1d(b_ring + s * C::B_STAGE_BYTES, p.bimg + (size_t)st * STAGE_FIELDS * NC, C::B_STAGE_BYTES,
-                         bar_bfull(s));
-          }
+          mbar_arrive_expect_tx(bar_bfull(s), C::B_STAGE_BYTES);
+          bulk_load_1d(b_ring + s * C::B_STAGE_BYTES, p.bimg + (size_t)st * STAGE_FIELDS * NC, C::B_STAGE_BYTES,
+                       bar_bfull(s));
         }
-        __syncwarp();
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
-    // ===================== MMA issuer (warp-uniform control flow, one elected lane issues) ============
+    // ===================== MMA issuer (one elected thread runs the whole role) ============
     // instruction descriptor: D=f32, A=B=f16, K-major both, N=NC, M=128
     const uint32_t idesc = (1u << 4) | ((uint32_t)(NC >> 3) << 17) | (8u << 24);
     // B smem descriptor: K-major, no swizzle; LBO = NC*16 B (next 8-wide K chunk), SBO = 128 B (next 8 n), version 1
     const uint32_t desc_lo_const = (uint32_t)((NC * 16) >> 4) << 16;
     const uint32_t desc_hi = (uint32_t)(128 >> 4) | (1u << 14);
     uint32_t it = 0, cit = 0, item_idx = 0;
-    for (uint32_t item = blockIdx.x; item < p.n_items; item += gridDim.x, ++item_idx) {
+    const bool leader = elect_one();
+    for (uint32_t item = blockIdx.x; leader && item < p.n_items; item += gridDim.x, ++item_idx) {
       const uint32_t ks = item / p.row_groups;
       const uint32_t st0 = ks * p.stages_per_split;
       uint32_t st1 = st0 + p.stages_per_split;
@@ -204,29 +203,25 @@ sketch_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
           const uint32_t sph = (cit / C::SLOTS) & 1u;
           mbar_wait(bar_tfull(slot), sph);
           tc_fence_after();
-          if (elect_one()) {
 #pragma unroll
-            for (int t = 0; t < RT; ++t) {
-              const uint32_t d_t = tmem_base + C::D_COL0 + t * NC;
-              const uint32_t a_t = tmem_base + C::A_COL0 + (slot * RT + t) * 32;
+          for (int t = 0; t < RT; ++t) {
+            const uint32_t d_t = tmem_base + C::D_COL0 + t * NC;
+            const uint32_t a_t = tmem_base + C::A_COL0 + (slot * RT + t) * 32;
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const uint32_t baddr = bsm + (uint32_t)((q * 4 + i) * (32 * NC));
-                const uint64_t bdesc = ((uint64_t)desc_hi << 32) | (uint64_t)(desc_lo_const | ((baddr >> 4) & 0x3FFFu));
-                tc_mma_ts(d_t, a_t + 8 * i, bdesc, idesc, acc_flag | (uint32_t)i);
-              }
+            for (int i = 0; i < 4; ++i) {
+              const uint32_t baddr = bsm + (uint32_t)((q * 4 + i) * (32 * NC));
+              const uint64_t bdesc = ((uint64_t)desc_hi << 32) | (uint64_t)(desc_lo_const | ((baddr >> 4) & 0x3FFFu));
+              tc_mma_ts(d_t, a_t + 8 * i, bdesc, idesc, acc_flag | (uint32_t)i);
             }
-            tc_commit(bar_tempty(slot));
           }
-          __syncwarp();
+          tc_commit(bar_tempty(slot));
           acc_flag = 1;
         }
-        if (elect_one()) tc_commit(bar_bempty(s));
-        __syncwarp();
+        tc_commit(bar_bempty(s));
       }
-      if (elect_one()) tc_commit(bar_accfull);
-      __syncwarp();
+      tc_commit(bar_accfull);
     }
+    __syncwarp();
   } else if (warp >= 2 && warp < 10) {
     // ===================== expanders + epilogue =====================
     const int tile = (warp - 2) >> 2;
