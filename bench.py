@@ -396,6 +396,52 @@ def e2e_loop(torch, dist, dev, world, fn, steps):
     return max_over_ranks(torch, dist, dev, world, [te])[0]
 
 
+def sampled_parity(torch, ctx, payload, n, keep, mean, sd, dev, l=K_COMPONENTS + OVERSAMPLE, n_rows=192, n_cols=96, seed=7):
+    """Parity of the hot kernel AT THE FULL SIZE of the run, by a size-independent route: both sketch orientations
+    (gpca_sketch_snp_side: S B, gpca_sketch_sample_side: S^T W, seeded Gaussian operands) are run over the whole resident
+    matrix, and a random sample of OUTPUT rows is recomputed in float64 by numpy from the genotypes decoded out of the
+    host payload (`payload`: uint8 [M x ceil(N/4)], PLINK coding; count_a1 decode 00 -> 2, 01 -> missing, 10 -> 1,
+    11 -> 0, src/prepare.rs:622-629) with the library's own mean / sd widened to f64 -- no kernel of the library on the
+    checking side.  Returns the relative L2 errors; the integer engine's only rounding is the 16-bit fixed point of the
+    dense operand (2^-15 of its maximum), so 1e-3 is a loose bound and ~1e-4 is what it measures."""
+    rng = np.random.default_rng(seed)
+    kept_idx = np.nonzero(np.asarray(keep))[0]
+    d = kept_idx.size
+    mu = np.asarray(mean)[kept_idx].astype(np.float64)
+    isd = 1.0 / np.asarray(sd)[kept_idx].astype(np.float64)
+    lut = np.array([2.0, np.nan, 1.0, 0.0])
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    b = torch.randn(n, l, device=dev, generator=g)
+    w = torch.randn(d, l, device=dev, generator=g)
+    out_s = torch.empty(d, l, device=dev)
+    out_n = torch.empty(n, l, device=dev)
+    torch.cuda.synchronize()
+    ctx.sketch_snp_side(b.data_ptr(), out_s.data_ptr(), l, l)
+    ctx.sketch_sample_side(w.data_ptr(), out_n.data_ptr(), l, l)
+    ctx.synchronize()
+    # snp side: sampled SNP rows, all samples
+    rows = np.sort(rng.choice(d, size=min(n_rows, d), replace=False))
+    by = payload[kept_idx[rows]]                                             # [rows x bps]
+    codes = ((by[:, :, None] >> np.array([0, 2, 4, 6], dtype=np.uint8)) & 3).reshape(rows.size, -1)[:, :n]
+    s_rows = np.nan_to_num((lut[codes] - mu[rows, None]) * isd[rows, None])   # a missing call standardises to 0
+    ref = s_rows @ b.cpu().double().numpy()
+    got = out_s[torch.as_tensor(rows, device=dev)].cpu().double().numpy()
+    e_snp = float(np.linalg.norm(got - ref) / np.linalg.norm(ref))
+    # sample side: sampled samples (columns of the payload), all kept SNPs
+    cols = np.sort(rng.choice(n, size=min(n_cols, n), replace=False))
+    by = payload[np.ix_(kept_idx, cols // 4)]                                # [d x cols]
+    codes = (by >> (2 * (cols % 4)).astype(np.uint8)[None, :]) & 3
+    s_cols = np.nan_to_num((lut[codes] - mu[:, None]) * isd[:, None])
+    ref = s_cols.T @ w.cpu().double().numpy()
+    got = out_n[torch.as_tensor(cols, device=dev)].cpu().double().numpy()
+    e_smp = float(np.linalg.norm(got - ref) / np.linalg.norm(ref))
+    del b, w, out_s, out_n
+    return {"snp_side_rel_l2": e_snp, "sample_side_rel_l2": e_smp, "output_rows_checked": [int(rows.size), int(cols.size)],
+            "l": int(l), "tolerance": 1e-3, "ok": bool(e_snp < 1e-3 and e_smp < 1e-3),
+            "reference": "numpy float64 on genotypes decoded from the host payload (sampled output rows of both orientations)"}
+
+
 def subspace_angle(a, b):
     """largest principal angle (rad) between the column spaces of two [n x k] matrices (float64 numpy)"""
     qa, _ = np.linalg.qr(np.asarray(a, dtype=np.float64))
@@ -575,6 +621,18 @@ def run_ours(args, rank, world):
                "pca_wall_s": te, "includes": "gpca_ingest_bed of every rank's shard from pinned host memory + gpca_rfit + "
                                              "scores / eigenvalues on the host"}
 
+    # ---- the kernel's arithmetic at this size, on sampled output rows (rank 0's shard) ---------------------------
+    parity_full = None
+    if rank == 0 and not args.no_parity:
+        try:
+            view = np.ctypeslib.as_array(ctypes.cast(host.ptr, ctypes.POINTER(ctypes.c_uint8)), shape=(m * bps,)).reshape(m, bps)
+            parity_full = sampled_parity(torch, ctx, view, n, keep, mean, sd, dev)
+            parity_full["shape"] = f"{n} samples x {int(d_kept)} SNPs (rank 0's shard of {world})"
+            del view
+        except Exception as e:      # supplementary record
+            parity_full = {"error": repr(e)}
+        torch.cuda.empty_cache()
+
     # ---- EigenSNP on the same configuration --------------------------------------------------------
     es = None
     if not args.no_eigensnp:
@@ -680,6 +738,8 @@ def run_ours(args, rank, world):
         "clocks": r["clocks"], "e2e": e2e, "gpu_launches": int(r["launches"]), "roofline": roofline,
         "eigenvalues_head": [float(x) for x in r["eigenvalues"][:3]],
     }
+    if parity_full is not None:
+        line["parity_full_size"] = parity_full
     if es is not None:
         line["eigensnp"] = es
     if c3 is not None:

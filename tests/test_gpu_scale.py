@@ -128,3 +128,25 @@ def test_eigensnp_at_scale_against_exact_f64_pca(scale_case):
     assert pca.subspace_angle(sc3, v_x) < 1e-3
     l64 = load.astype(np.float64)
     assert np.abs(l64.T @ l64 - np.eye(10)).max() < 1e-3          # orthonormal loadings
+
+
+def test_sketch_passes_at_scale_on_sampled_rows_against_f64(scale_case):
+    """Both orientations of the sketch pass over the whole 2,504 x 1M matrix; a random sample of output rows is recomputed
+    in float64 by numpy from the decoded payload (bench.sampled_parity: the same check `bench.py` prints as
+    `parity_full_size` for 500,000 x 700,000).  Every engine, l = 30 and the wide l = 50."""
+    import torch
+    import bench
+    import genomic_pca_b200 as gp
+    payload = scale_case(22)
+    host_payload = payload.cpu().numpy()
+    dev = torch.device("cuda", 0)
+    ctx = gp.Context(0)
+    ctx.load_bed_device(payload.data_ptr(), N, M)
+    keep, mean, sd = ctx.vcf_maf_filter(0.01)
+    ctx.set_pca_snps_mask(keep, mean, sd)
+    for engine, l, tol in [(2, 30, 3e-4), (1, 30, 1.5e-3), (2, 50, 1.5e-3), (0, 30, 1e-5)]:    # l = 50 runs on the fp16 engine
+        ctx.set_sketch_engine(engine)
+        r = bench.sampled_parity(torch, ctx, host_payload, N, keep, mean, sd, dev, l=l, n_rows=128, n_cols=64)
+        record("sampled_rows", engine=engine, l=l, **{k: v for k, v in r.items() if k.endswith("_l2")})
+        assert r["snp_side_rel_l2"] < tol and r["sample_side_rel_l2"] < tol, (engine, l, r)
+    ctx.close()
