@@ -91,6 +91,13 @@ __device__ __forceinline__ uint32_t prof_clock() { uint32_t c; asm volatile("mov
 #ifndef GPCA_I8_DEFER_ST
 #define GPCA_I8_DEFER_ST 0
 #endif
+// GPCA_I8_STAGGER (RT = 2, regular shape): the two row tiles of a CTA take turns storing a chunk pair to TMEM (tile 0,
+// then tile 1), so that at most 8 of the SM's 16 expander warps drive the TMEM store port at a time.  With all 16
+// storing at once the port saturates (221 B/clk) and a concurrent tcgen05.mma takes 45 cycles instead of 32; with 8 it
+// takes 33.5 (tools/probe/mma_sttm_probe.cu).
+#ifndef GPCA_I8_STAGGER
+#define GPCA_I8_STAGGER 0
+#endif
 #ifndef GPCA_I8_TILE_SYNC_DEFAULT
 #define GPCA_I8_TILE_SYNC_DEFAULT false
 #endif
@@ -200,6 +207,7 @@ sketch_i8_kernel(const __grid_constant__ CUtensorMap tmap, const I8Params p) {
   auto bar_tempty = [&](int j, int t) { return bars + 8u * (48 + (TS ? j * RT + t : j)); };
   static_assert(SLOTS * (TS ? RT : 1) <= 16, "TMEM slot barriers");
   auto bar_bempty = [&](int s) { return bars + 8u * (24 + s); };
+  auto bar_turn = [&](int t) { return bars + 8u * (12 + t); };     // GPCA_I8_STAGGER: "row tile t has stored its chunk pair"
   const uint32_t bar_accfull = bars + 8u * 28;
   const uint32_t bar_accempty = bars + 8u * 29;
   const uint32_t tmem_slot = bars + 8u * 30;
@@ -223,6 +231,8 @@ sketch_i8_kernel(const __grid_constant__ CUtensorMap tmap, const I8Params p) {
         mbar_init(bar_tfull(j, t), TS ? 4 * KH : 4 * RT * KH);
         mbar_init(bar_tempty(j, t), 1);
       }
+    mbar_init(bar_turn(0), 4);
+    mbar_init(bar_turn(1), 4);
     mbar_init(bar_accfull, DI ? 2 : 1);
     mbar_init(bar_accempty, 4 * RT);
     fence_barrier_init();
@@ -485,6 +495,15 @@ sketch_i8_kernel(const __grid_constant__ CUtensorMap tmap, const I8Params p) {
             mbar_wait(bar_tempty(slot, tile), sph ^ 1u);      // the MMAs that read this slot (of this tile: TS) have completed
             PROF_ADD(c_tempty, t_te);
             tc_fence_after();
+#if GPCA_I8_STAGGER
+            if (RT == 2 && !DEEP) {
+              if (tile == 0) {
+                if (cit > 0) mbar_wait(bar_turn(1), (cit - 1) & 1u);     // tile 1 has stored the previous pair
+              } else {
+                mbar_wait(bar_turn(0), cit & 1u);                        // tile 0 has stored this pair
+              }
+            }
+#endif
             PROF_T(t_st);
             const uint32_t ta = tmem_base + lane_addr + A_COL0 + (slot * RT + tile) * 32;
 #ifndef GPCA_KO_STTM
@@ -497,6 +516,9 @@ sketch_i8_kernel(const __grid_constant__ CUtensorMap tmap, const I8Params p) {
 #endif
             tc_wait_st();
             PROF_ADD(c_st, t_st);
+#if GPCA_I8_STAGGER
+            if (RT == 2 && !DEEP && lane == 0) mbar_arrive(bar_turn(tile));
+#endif
 #else
             asm volatile("" :: "r"(r0[0] ^ r0[1] ^ r0[2] ^ r0[3] ^ r0[4] ^ r0[5] ^ r0[6] ^ r0[7] ^ r0[8] ^ r0[9] ^ r0[10] ^ r0[11] ^ r0[12] ^ r0[13] ^ r0[14] ^ r0[15] ^ r1[0] ^ r1[1] ^ r1[2] ^ r1[3] ^ r1[4] ^ r1[5] ^ r1[6] ^ r1[7] ^ r1[8] ^ r1[9] ^ r1[10] ^ r1[11] ^ r1[12] ^ r1[13] ^ r1[14] ^ r1[15]), "r"(ta));
 #endif
