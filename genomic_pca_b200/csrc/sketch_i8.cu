@@ -91,12 +91,26 @@ __device__ __forceinline__ uint32_t prof_clock() { uint32_t c; asm volatile("mov
 #ifndef GPCA_I8_DEFER_ST
 #define GPCA_I8_DEFER_ST 0
 #endif
+#ifndef GPCA_I8_PIN_EXPAND
+#define GPCA_I8_PIN_EXPAND 0
+#endif
 // GPCA_I8_STAGGER (RT = 2, regular shape): the two row tiles of a CTA take turns storing a chunk pair to TMEM (tile 0,
 // then tile 1), so that at most 8 of the SM's 16 expander warps drive the TMEM store port at a time.  With all 16
 // storing at once the port saturates (221 B/clk) and a concurrent tcgen05.mma takes 45 cycles instead of 32; with 8 it
 // takes 33.5 (tools/probe/mma_sttm_probe.cu).
 #ifndef GPCA_I8_STAGGER
 #define GPCA_I8_STAGGER 0
+#endif
+// GPCA_I8_TRACE (with GPCA_I8_PROF): %clock timestamps of the hand-over events of 96 consecutive chunk pairs, for the two
+// CTAs resident on SM 0, printed at the end of the launch (measurement builds only).
+#if defined(GPCA_I8_TRACE) && defined(GPCA_I8_PROF)
+#define TR_FIRST 64u
+#define TR_COUNT 96u
+__device__ unsigned g_tr[2][TR_COUNT][8];
+__device__ unsigned g_tr_slot;
+#define TR(pair, ev) do { if (tr_slot >= 0 && (pair) >= TR_FIRST && (pair) < TR_FIRST + TR_COUNT) g_tr[tr_slot][(pair) - TR_FIRST][ev] = prof_clock(); } while (0)
+#else
+#define TR(pair, ev)
 #endif
 #ifndef GPCA_I8_TILE_SYNC_DEFAULT
 #define GPCA_I8_TILE_SYNC_DEFAULT false
@@ -237,6 +251,14 @@ sketch_i8_kernel(const __grid_constant__ CUtensorMap tmap, const I8Params p) {
     mbar_init(bar_accempty, 4 * RT);
     fence_barrier_init();
   }
+#if defined(GPCA_I8_TRACE) && defined(GPCA_I8_PROF)
+  __shared__ int tr_slot_s;
+  if (threadIdx.x == 0) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    tr_slot_s = (smid == 0 && !ITEMS) ? (int)(atomicAdd(&g_tr_slot, 1u) & 1u) : -1;
+  }
+#endif
   if (warp == 1) {
     tmem_alloc(tmem_slot, TMEM_COLS);
     tmem_relinquish();
@@ -253,6 +275,9 @@ sketch_i8_kernel(const __grid_constant__ CUtensorMap tmap, const I8Params p) {
   __syncthreads();
   tc_fence_after();
   const float s_scale = ITEMS ? 0.0f : cv_s[64];
+#if defined(GPCA_I8_TRACE) && defined(GPCA_I8_PROF)
+  const int tr_slot = tr_slot_s;
+#endif
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
@@ -350,6 +375,7 @@ sketch_i8_kernel(const __grid_constant__ CUtensorMap tmap, const I8Params p) {
             mbar_wait(bar_tfull(slot, 0), sph);
             PROF_ADD(c_tfull, t_t);
             tc_fence_after();
+            TR(cit, 4);
           }
 #pragma unroll
           for (int t = 0; t < RT; ++t) {
@@ -374,6 +400,7 @@ sketch_i8_kernel(const __grid_constant__ CUtensorMap tmap, const I8Params p) {
             }
             if (TS || t == t_hi - 1) tc_commit(bar_tempty(slot, TS ? t : 0));
           }
+          TR(cit, 5);
           acc_flag = 1;
         }
         tc_commit(bar_bempty(s));
@@ -479,6 +506,16 @@ sketch_i8_kernel(const __grid_constant__ CUtensorMap tmap, const I8Params p) {
             expand_word_u8(v[q + 1].z, r1 + 8);
             expand_word_u8(v[q + 1].w, r1 + 12);
 #endif
+#if GPCA_I8_PIN_EXPAND
+            // The expansions are plain register arithmetic: without this, the compiler sinks them below the barrier waits
+            // that follow (asm volatile), right in front of the tcgen05.st that consumes them -- and the warp then waits
+            // for the slot first and computes afterwards.  Naming the results as inputs of an (empty) volatile asm keeps
+            // the computation in front of the waits.
+            asm volatile("" ::"r"(r0[0]), "r"(r0[1]), "r"(r0[2]), "r"(r0[3]), "r"(r0[4]), "r"(r0[5]), "r"(r0[6]), "r"(r0[7]),
+                         "r"(r0[8]), "r"(r0[9]), "r"(r0[10]), "r"(r0[11]), "r"(r0[12]), "r"(r0[13]), "r"(r0[14]), "r"(r0[15]));
+            asm volatile("" ::"r"(r1[0]), "r"(r1[1]), "r"(r1[2]), "r"(r1[3]), "r"(r1[4]), "r"(r1[5]), "r"(r1[6]), "r"(r1[7]),
+                         "r"(r1[8]), "r"(r1[9]), "r"(r1[10]), "r"(r1[11]), "r"(r1[12]), "r"(r1[13]), "r"(r1[14]), "r"(r1[15]));
+#endif
 #if GPCA_I8_DEFER_ST
             // the previous pair's TMEM stores were left in flight while this pair was expanded: complete and publish them
             if (st_pending) {
@@ -492,8 +529,10 @@ sketch_i8_kernel(const __grid_constant__ CUtensorMap tmap, const I8Params p) {
             }
 #endif
             PROF_T(t_te);
+            if (lane == 0 && quarter == 0 && tile == 0) TR(cit, 0);
             mbar_wait(bar_tempty(slot, tile), sph ^ 1u);      // the MMAs that read this slot (of this tile: TS) have completed
             PROF_ADD(c_tempty, t_te);
+            if (lane == 0 && quarter == 0 && tile == 0) TR(cit, 1);
             tc_fence_after();
 #if GPCA_I8_STAGGER
             if (RT == 2 && !DEEP) {
@@ -516,6 +555,8 @@ sketch_i8_kernel(const __grid_constant__ CUtensorMap tmap, const I8Params p) {
 #endif
             tc_wait_st();
             PROF_ADD(c_st, t_st);
+            if (lane == 0 && quarter == 0) TR(cit, 2 + tile);
+            if (lane == 0 && quarter == 3) TR(cit, 6 + tile);
 #if GPCA_I8_STAGGER
             if (RT == 2 && !DEEP && lane == 0) mbar_arrive(bar_turn(tile));
 #endif
@@ -665,6 +706,15 @@ sketch_i8_kernel(const __grid_constant__ CUtensorMap tmap, const I8Params p) {
   }
   tc_fence_before();
   __syncthreads();
+#if defined(GPCA_I8_TRACE) && defined(GPCA_I8_PROF)
+  if (threadIdx.x == 0 && tr_slot >= 0) {
+    __threadfence();
+    for (unsigned i = 0; i < TR_COUNT; ++i)
+      printf("PROF TR %d %u exp_done %u slot_free %u stored_t0 %u stored_t1 %u stored_t0q3 %u stored_t1q3 %u tfull_seen %u mma_issued %u\n",
+             tr_slot, TR_FIRST + i, g_tr[tr_slot][i][0], g_tr[tr_slot][i][1], g_tr[tr_slot][i][2], g_tr[tr_slot][i][3],
+             g_tr[tr_slot][i][6], g_tr[tr_slot][i][7], g_tr[tr_slot][i][4], g_tr[tr_slot][i][5]);
+  }
+#endif
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);

@@ -1,7 +1,7 @@
 // Probe: how fast does the tensor pipe execute tcgen05.mma.kind::i8 (M = 128, K = 32, A from TMEM, B from shared memory)
 // at N = 64 and N = 32, alone and while expander-like warps stream tcgen05.st.32x32b.x16 into TMEM -- the two things
 // sketch_i8_kernel does at the same time.
-//   mma_sttm_probe [ctas_per_sm=2] [n_mma=4096] [N=64] [store_warps=8] [grid_sms=148] [unroll=1] [issuers=1] [commit_every=8]
+//   mma_sttm_probe [ctas_per_sm=2] [n_mma=4096] [N=64] [store_warps=8] [grid_sms=148] [unroll=1] [issuers=1] [commit_every=8] [store_delay=0]
 // unroll = MMAs per elected region (1, 4 or 16); issuers = 1 (warp 1) or 2 (warps 1 and 3, n_mma each, own accumulators)
 // Per resident CTA (same warp roles as the kernel): warp 1 issues n_mma MMAs back to back (a commit every 8) and waits
 // for the last one; warps 4.. store 2 x 16 registers per iteration (4 KB per warp) + tcgen05.wait::st until the issuer
@@ -29,7 +29,7 @@ __device__ __forceinline__ void issue_block(int it, uint32_t tb, uint32_t dcol, 
 }
 
 __global__ void __launch_bounds__(384, 2) probe(Res* out, int n_mma, int N, int store_warps, int tmem_cols, int spin,
-                                                int unroll, int issuers, int commit_every) {
+                                                int unroll, int issuers, int commit_every, int store_delay) {
   extern __shared__ __align__(1024) unsigned char sm[];
   const uint32_t base_s = smem_u32(sm);
   const uint32_t bsm = base_s;                // 16 KB operand stage (zeros)
@@ -99,6 +99,10 @@ __global__ void __launch_bounds__(384, 2) probe(Res* out, int n_mma, int N, int 
       tmem_st16(ta + 16, r);
       tc_wait_st();
       ++iters;
+      if (store_delay > 0) {      // throttle: idle cycles between store iterations (sets the store rate)
+        const long long d0 = clock64();
+        while (clock64() - d0 < store_delay) { }
+      }
     }
     const long long t1 = clock64();
     if (warp == 4 && lane == 0) {
@@ -123,13 +127,14 @@ int main(int argc, char** argv) {
   const int unroll = argc > 6 ? atoi(argv[6]) : 1;
   const int issuers = argc > 7 ? atoi(argv[7]) : 1;
   const int commit_every = argc > 8 ? atoi(argv[8]) : 8;
+  const int store_delay = argc > 9 ? atoi(argv[9]) : 0;
   const int grid = sms * per_sm;
   const int smem = per_sm == 2 ? 100 * 1024 : 200 * 1024;      // forces the residency asked for
   Res* d;
   cudaMalloc(&d, grid * sizeof(Res));
   cudaMemset(d, 0, grid * sizeof(Res));
   cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  for (int rep = 0; rep < 2; ++rep) probe<<<grid, 384, smem>>>(d, n_mma, N, store_warps, per_sm == 2 ? 256 : 512, 400000, unroll, issuers, commit_every);
+  for (int rep = 0; rep < 2; ++rep) probe<<<grid, 384, smem>>>(d, n_mma, N, store_warps, per_sm == 2 ? 256 : 512, 400000, unroll, issuers, commit_every, store_delay);
   const cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
     printf("status %s\n", cudaGetErrorString(e));
@@ -145,8 +150,8 @@ int main(int argc, char** argv) {
     sti += (double)h[b].st_iters;
   }
   const int nm = n_mma > 0 ? n_mma : 1;
-  printf("ctas/SM %d  N %d  mma %d x %d issuer(s), %d per elected region, commit every %d, store warps %d/CTA: ", per_sm, N, n_mma,
-         issuers, unroll, commit_every, store_warps);
+  printf("ctas/SM %d  N %d  mma %d x %d issuer(s), %d per elected region, commit every %d, store warps %d/CTA (+%d idle cycles per iteration): ",
+         per_sm, N, n_mma, issuers, unroll, commit_every, store_warps, store_delay);
   if (n_mma > 0)
     printf("%.1f cycles per MMA per issuer (issue loop %.1f) = %.1f per MMA on the SM's pipe; ", done / grid / nm, issue / grid / nm,
            done / grid / nm / per_sm / issuers);
