@@ -91,6 +91,10 @@ __device__ __forceinline__ uint32_t prof_clock() { uint32_t c; asm volatile("mov
 #ifndef GPCA_I8_DEFER_ST
 #define GPCA_I8_DEFER_ST 0
 #endif
+// GPCA_I8_L2PF = n: the A producer prefetches the stage n ahead into L2 (0 = off)
+#ifndef GPCA_I8_L2PF
+#define GPCA_I8_L2PF 0
+#endif
 #ifndef GPCA_I8_PIN_EXPAND
 #define GPCA_I8_PIN_EXPAND 0
 #endif
@@ -313,6 +317,16 @@ sketch_i8_kernel(const __grid_constant__ CUtensorMap tmap, const I8Params p) {
           for (int t = 0; t < RT; ++t)
             tma_load_2d(sbase + t * A_TILE_BYTES, &tmap, bar_afull(s), (int)(ii.kbyte0 + a * A_ROW_BYTES),
                         row0 + t * 128);
+#if GPCA_I8_L2PF
+          // The ring holds SA stages; the stage SA ahead is requested only when this one has been consumed -- about one
+          // HBM round trip before it is needed (trace: every new A stage arrived ~400 cycles late).  Pulling it into L2
+          // now makes that later load an L2 hit.
+          if (!ITEMS && a + GPCA_I8_L2PF < n_ast) {
+#pragma unroll
+            for (int t = 0; t < RT; ++t)
+              tma_prefetch_2d(&tmap, (int)(ii.kbyte0 + (a + GPCA_I8_L2PF) * A_ROW_BYTES), row0 + t * 128);
+          }
+#endif
         }
       } else {
         for (uint32_t st = 0; st < ii.nst; ++st, ++it) {

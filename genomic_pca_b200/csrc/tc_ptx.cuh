@@ -76,6 +76,10 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "l"(map), "r"(bar), "r"(x), "r"(y), "l"(GPCA_A_L2_HINT)
       : "memory");
 }
+// the box into L2 only (no shared memory, no barrier): lets a later tma_load_2d of the same box hit L2
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int x, int y) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(x), "r"(y) : "memory");
+}
 __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar), "l"(GPCA_B_L2_HINT)
