@@ -621,13 +621,15 @@ def run_ours(args, rank, world):
                "pca_wall_s": te, "includes": "gpca_ingest_bed of every rank's shard from pinned host memory + gpca_rfit + "
                                              "scores / eigenvalues on the host"}
 
-    # ---- the kernel's arithmetic at this size, on sampled output rows (rank 0's shard) ---------------------------
+    # ---- the kernel's arithmetic at this size, on sampled output rows --------------------------------------------
+    # One-GPU runs only: on a sharded context gpca_sketch_sample_side is a COLLECTIVE (it ends with the exchange of the
+    # N x l sketch), so a check issued by one rank alone would leave that rank waiting for the others for ever.
     parity_full = None
-    if rank == 0 and not args.no_parity:
+    if world == 1 and not args.no_parity:
         try:
             view = np.ctypeslib.as_array(ctypes.cast(host.ptr, ctypes.POINTER(ctypes.c_uint8)), shape=(m * bps,)).reshape(m, bps)
             parity_full = sampled_parity(torch, ctx, view, n, keep, mean, sd, dev)
-            parity_full["shape"] = f"{n} samples x {int(d_kept)} SNPs (rank 0's shard of {world})"
+            parity_full["shape"] = f"{n} samples x {int(d_kept)} SNPs"
             del view
         except Exception as e:      # supplementary record
             parity_full = {"error": repr(e)}

@@ -208,8 +208,11 @@ int gpca_get_standardized_block(gpca_ctx* ctx, const uint64_t* pca_snp_ids, uint
 /* S = standardized [D x N] (never materialised).  Missing calls contribute 0.
  *   snp side   : dev_out[D x l]  = S   * dev_in[N x l]      (reduction over samples)
  *   sample side: dev_out[N x l]  = S^T * dev_in[D x l]      (reduction over SNPs; summed over
- *                                                            shards through the allreduce hook)
- * l <= 64.  ld = row stride in floats of both dense operands. */
+ *                                                            shards through the exchange)
+ * l <= 64.  ld = row stride in floats of both dense operands.
+ * On a sharded context (gpca_set_shard + gpca_comm_init / gpca_set_allreduce) the sample-side call is a
+ * COLLECTIVE: it ends with the allreduce of the N x l result and needs ld == l; every shard must issue it,
+ * in the same order as its other collectives.  The snp-side call is local to the shard. */
 int gpca_sketch_snp_side(gpca_ctx* ctx, const float* dev_in, float* dev_out, uint32_t l, uint32_t ld);
 int gpca_sketch_sample_side(gpca_ctx* ctx, const float* dev_in, float* dev_out, uint32_t l, uint32_t ld);
 /* Product with a dense fp32 matrix C [n x r] (row stride ldc floats) on the device -- the condensed-feature matrix of

@@ -30,3 +30,40 @@ def test_subspace_angle_helper():
     b[:, 0] += 1e-3 * rng.standard_normal(200)
     ang = bench.subspace_angle(q, b)
     assert 1e-4 < ang < 5e-2
+
+
+def test_no_collective_call_under_a_rank_condition():
+    """bench.py under torchrun: every rank must issue the same collectives.  gpca_rfit, gpca_eigensnp and the sample-side
+    sketch of a sharded context end in an exchange, and the timing helpers reduce over the ranks -- none of them may sit
+    under a condition on the rank (a check that rank 0 ran alone once left the other ranks waiting for ever).  The
+    full-size parity check, which calls the sample-side sketch, must be tied to one-GPU runs."""
+    import ast
+    import inspect
+    collective = {"rfit", "eigensnp", "sketch_sample_side", "comm_init", "sampled_parity", "timed_rfit", "e2e_loop",
+                  "max_over_ranks", "sum_over_ranks", "barrier", "broadcast_object_list", "all_reduce"}
+    tree = ast.parse(inspect.getsource(bench.run_ours))
+
+    def names(node):
+        return {n.id for n in ast.walk(node) if isinstance(n, ast.Name)}
+
+    def calls(nodes):
+        out = set()
+        for node in nodes:
+            for c in ast.walk(node):
+                if isinstance(c, ast.Call):
+                    f = c.func
+                    out.add(f.attr if isinstance(f, ast.Attribute) else getattr(f, "id", ""))
+        return out
+
+    checked = parity_guard = 0
+    for node in ast.walk(tree):
+        if isinstance(node, ast.If):
+            if "rank" in names(node.test):
+                checked += 1
+                bad = calls(node.body) & collective
+                # (leaving the process group on the way out is the one rank-dependent collective-free exit)
+                assert not bad, f"collective call(s) {bad} under `if {ast.unparse(node.test)}`"
+            if "sampled_parity" in calls(node.body):
+                parity_guard += 1
+                assert ast.unparse(node.test).startswith("world == 1"), ast.unparse(node.test)
+    assert checked >= 2 and parity_guard == 1
