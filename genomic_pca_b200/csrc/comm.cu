@@ -15,6 +15,7 @@
 
 #include <cstring>
 #include <mutex>
+#include <string>
 
 #include "driver_util.cuh"
 
@@ -42,7 +43,8 @@ NcclApi* nccl_api() {
       if (api.handle) break;
     }
     if (!api.handle) {
-      api.why = std::string("libnccl.so.2 not found: ") + (dlerror() ? dlerror() : "");
+      const char* why = dlerror();      // (one call: dlerror() clears the message it returns)
+      api.why = std::string("libnccl.so.2 not found: ") + (why ? why : "");
       return;
     }
     auto sym = [&](const char* s) { return dlsym(api.handle, s); };
