@@ -760,8 +760,29 @@ def run_ours(args, rank, world):
         dist.destroy_process_group()
 
 
+def start_watchdog(limit_s=None):
+    """A run of this script takes one to three minutes.  If it is still going after `limit_s` seconds (default 900,
+    BENCH_WATCHDOG_S; 0 = off) something is waiting that will never come -- e.g. a collective that one rank did not
+    issue -- and the process ends itself with a one-line explanation instead of holding the GPUs until an outer limit."""
+    if limit_s is None:
+        limit_s = float(os.environ.get("BENCH_WATCHDOG_S", "900"))
+    if limit_s <= 0:
+        return None
+
+    def fire():
+        sys.stderr.write(f"bench.py: no result after {limit_s:.0f} s (rank {os.environ.get('RANK', '0')}): giving up\n")
+        sys.stderr.flush()
+        os._exit(3)
+
+    t = threading.Timer(limit_s, fire)
+    t.daemon = True
+    t.start()
+    return t
+
+
 def main():
     args = parse_args()
+    start_watchdog()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":

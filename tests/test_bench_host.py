@@ -67,3 +67,14 @@ def test_no_collective_call_under_a_rank_condition():
                 parity_guard += 1
                 assert ast.unparse(node.test).startswith("world == 1"), ast.unparse(node.test)
     assert checked >= 2 and parity_guard == 1
+
+
+def test_watchdog_ends_a_run_that_never_finishes():
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, "-c", "import time, bench; bench.start_watchdog(0.5); time.sleep(30)"],
+                       capture_output=True, text=True, cwd=bench.os.path.dirname(bench.os.path.abspath(bench.__file__)))
+    assert r.returncode == 3 and "giving up" in r.stderr
+    r = subprocess.run([sys.executable, "-c", "import bench; assert bench.start_watchdog(0) is None"],
+                       capture_output=True, text=True, cwd=bench.os.path.dirname(bench.os.path.abspath(bench.__file__)))
+    assert r.returncode == 0, r.stderr
