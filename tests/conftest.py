@@ -15,6 +15,17 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (sm_100a) GPU; run with `pytest -m gpu` on the GPU box")
 
 
+def pytest_collection_modifyitems(config, items):
+    """A GPU test takes seconds (the whole `-m gpu` suite under a minute).  With pytest-timeout present, one that is
+    still running after 15 minutes is a hang (the kernels' barrier waits are bounded and trap, so this is a last
+    resort): the run ends with the stacks of all threads instead of holding the GPU until an outer limit."""
+    if not config.pluginmanager.hasplugin("timeout"):
+        return
+    for item in items:
+        if item.get_closest_marker("gpu") and not item.get_closest_marker("timeout"):
+            item.add_marker(pytest.mark.timeout(900, method="thread"))
+
+
 @pytest.fixture(scope="session")
 def golden_rows():
     z = np.load(os.path.join(GOLDEN, "chr22_subset50_rows.npz"))
